@@ -1,0 +1,165 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference).
+
+Run in the authoring container only:   python tests/golden/make_golden.py
+The fixtures are small, committed, and are what pins `oracle/ot_oracle.py` (tests/test_oracle_golden.py)
+and - through the oracle and directly - the CUDA path (tests/test_gpu_parity.py).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _load_reference import load_reference  # noqa: E402
+
+load_reference()
+from ot_vae_lightning.ot import matrix_utils as ref_mu  # noqa: E402
+from ot_vae_lightning.ot import w2_utils as ref_w2  # noqa: E402
+from ot_vae_lightning.ot.distribution_models.codebook_model import CodebookModel  # noqa: E402
+from ot_vae_lightning.ot.distribution_models.gaussian_model import GaussianModel  # noqa: E402
+from ot_vae_lightning.ot.transport.gaussian_transport import GaussianTransport  # noqa: E402
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def spd(gen, *shape, kappa=50.0):
+    d = shape[-1]
+    q, _ = torch.linalg.qr(torch.randn(*shape, d, generator=gen, dtype=torch.double))
+    lam = torch.logspace(-np.log10(kappa), 0.0, d, dtype=torch.double)
+    return (q * lam) @ q.transpose(-1, -2)
+
+
+def latents(gen, n, d, lead=(), shift=0.0, scale=1.0):
+    mix = torch.randn(*lead, d, d, generator=gen, dtype=torch.double) / np.sqrt(d)
+    z = torch.randn(*lead, n, d, generator=gen, dtype=torch.double)
+    mu = torch.randn(*lead, 1, d, generator=gen, dtype=torch.double) + shift
+    return (scale * (z @ mix.transpose(-1, -2)) + mu).float()
+
+
+def case_matrix():
+    g = torch.Generator().manual_seed(101)
+    A = spd(g, 3, 12)
+    raw = torch.randn(2, 12, 12, generator=g, dtype=torch.double)
+    indef = raw + raw.transpose(-1, -2)  # symmetric, indefinite
+    repaired, shift = ref_mu.make_psd(indef, strict=True, return_correction=True)
+    s = torch.randn(2, 12, generator=g, dtype=torch.double) * 40
+    ss = spd(g, 2, 12) * 500 + s.unsqueeze(-1) * s.unsqueeze(-2) / 30
+    n = torch.tensor([30.0, 41.0], dtype=torch.double)
+    m, c = ref_mu.mean_cov(s.clone(), ss.clone(), n)
+    asym = A.clone()
+    asym[0, 1, 2] += 1e-3
+    np.savez(os.path.join(HERE, "matrix.npz"),
+             A=npy(A), sqrtm=npy(ref_mu.sqrtm(A)), invsqrtm=npy(ref_mu.invsqrtm(A)),
+             min_eig=npy(ref_mu.min_eig(A)), indef=npy(indef), indef_min_eig=npy(ref_mu.min_eig(indef)),
+             repaired=npy(repaired), shift=npy(shift),
+             sum=npy(s), sum_cov=npy(ss), n=npy(n), mean=npy(m), cov=npy(c),
+             asym=npy(asym), asym_is_symmetric=npy(ref_mu.is_symmetric(asym)),
+             A_is_spd=npy(ref_mu.is_spd(A)), indef_is_pd=npy(ref_mu.is_pd(indef)))
+
+
+def run_transport(src, tgt, lead, d, batch, decay=None, pg_star=0.0):
+    cfg = dict(dtype=torch.double)
+    if decay is not None:
+        cfg["update_decay"] = decay
+    op = GaussianTransport(*lead, d,
+                           transport_cfg=dict(diag=False, stochastic=False, make_pd=True, pg_star=pg_star,
+                                              dtype=torch.double),
+                           source_cfg=dict(cfg), target_cfg=dict(cfg))
+    for lo in range(0, src.shape[-2], batch):
+        op.update(source_samples=src[..., lo:lo + batch, :])
+    for lo in range(0, tgt.shape[-2], batch):
+        op.update(target_samples=tgt[..., lo:lo + batch, :])
+    w2 = op.compute()
+    moved = op.transport(src)
+    sm, tm = op.source_model, op.target_model
+    return dict(n_s=npy(sm._n_obs), sum_s=npy(sm._running_sum), sumcov_s=npy(sm._running_sum_cov),
+                mean_s=npy(sm.mean), cov_s=npy(sm.cov), mean_t=npy(tm.mean), cov_t=npy(tm.cov),
+                w2=npy(w2), T=npy(op.transport_operator), Cw=npy(op.cov_stochastic_noise), moved=npy(moved))
+
+
+def case_gaussian():
+    g = torch.Generator().manual_seed(202)
+    # single operator, d=16, ragged last batch (650 = 6*100 + 50)
+    src = latents(g, 650, 16, shift=0.5)
+    tgt = latents(g, 700, 16, shift=-1.0, scale=1.7)
+    out = run_transport(src, tgt, (), 16, 100)
+    np.savez(os.path.join(HERE, "gaussian_d16.npz"), src=npy(src), tgt=npy(tgt), batch=100, **out)
+    # two operators at once (leading shape (2,)), d=8, pg_star blend
+    src = latents(g, 300, 8, lead=(2,))
+    tgt = latents(g, 300, 8, lead=(2,), shift=2.0, scale=0.6)
+    out = run_transport(src, tgt, (2,), 8, 75, pg_star=0.25)
+    np.savez(os.path.join(HERE, "gaussian_lead2_d8.npz"), src=npy(src), tgt=npy(tgt), batch=75, pg_star=0.25, **out)
+    # EMA accumulation (update_decay), d=8
+    src = latents(g, 400, 8)
+    tgt = latents(g, 400, 8, shift=1.0)
+    out = run_transport(src, tgt, (), 8, 50, decay=0.9)
+    np.savez(os.path.join(HERE, "gaussian_ema_d8.npz"), src=npy(src), tgt=npy(tgt), batch=50, decay=0.9, **out)
+    # NOTE: the reference's *default* buffer dtype (fp32 buffers + fp64 `_n_obs`) cannot be pinned: `fit()` raises
+    # "Index put requires the source and destination dtypes match" at gaussian_model.py:182 (probed here), so every
+    # reference test passes dtype=torch.double.  The fixtures above therefore use fp64 buffers.
+
+
+def case_w2_functions():
+    g = torch.Generator().manual_seed(303)
+    lead, d = (2, 3), 3  # the reference tests' own shape (tests/test_w2_utils.py:23-24)
+    m1 = torch.randn(*lead, d, generator=g)
+    m2 = torch.randn(*lead, d, generator=g)
+    r1 = torch.randn(*lead, d, d, generator=g)
+    r2 = torch.randn(*lead, d, d, generator=g)
+    c1 = r1 @ r1.transpose(-1, -2) + torch.eye(d) * 1e-5
+    c2 = r2 @ r2.transpose(-1, -2) + torch.eye(d) * 1e-5
+    w2 = ref_w2.w2_gaussian(m1, m2, c1, c2)
+    T, Cw = ref_w2.compute_transport_operators(c1, c2, stochastic=False, diag=False, make_pd=True)
+    x = torch.randn(*lead, 7, d, generator=g)
+    y = ref_w2.apply_transport(x, m1.unsqueeze(-2), m2.unsqueeze(-2), T.unsqueeze(-3), Cw.unsqueeze(-3))
+    np.savez(os.path.join(HERE, "w2_d3.npz"), m1=npy(m1), m2=npy(m2), c1=npy(c1), c2=npy(c2),
+             w2=npy(w2), T=npy(T), x=npy(x), y=npy(y))
+    # d = 24, conditioned covariances
+    A, B = spd(g, 24, kappa=100.0), spd(g, 24, kappa=30.0) * 2.5
+    m1, m2 = torch.randn(24, generator=g, dtype=torch.double), torch.randn(24, generator=g, dtype=torch.double)
+    w2 = ref_w2.w2_gaussian(m1, m2, A, B)
+    T, _ = ref_w2.compute_transport_operators(A, B, stochastic=False, diag=False)
+    np.savez(os.path.join(HERE, "w2_d24.npz"), m1=npy(m1), m2=npy(m2), c1=npy(A), c2=npy(B), w2=npy(w2), T=npy(T))
+
+
+def case_sinkhorn():
+    g = torch.Generator().manual_seed(404)
+    # points in d=8, squared-euclidean cost normalised by its max (w2_utils.py:265-266), eps = 0.05
+    x = torch.randn(2, 40, 8, generator=g, dtype=torch.double)
+    y = torch.randn(2, 56, 8, generator=g, dtype=torch.double) * 1.3 + 0.4
+    C = (x * x).sum(-1, keepdim=True) + (y * y).sum(-1).unsqueeze(-2) - 2 * x @ y.transpose(-1, -2)
+    C = C / C.amax(dim=(-1, -2), keepdim=True)
+    a = torch.rand(2, 40, generator=g, dtype=torch.double); a /= a.sum(-1, keepdim=True)
+    b = torch.rand(2, 56, generator=g, dtype=torch.double); b /= b.sum(-1, keepdim=True)
+    plan_fixed = ref_w2.sinkhorn_log(a, b, C, reg=0.05, max_iter=25, threshold=0.0)
+    plan_conv = ref_w2.sinkhorn_log(a, b, C, reg=0.05, max_iter=1000, threshold=1e-6)
+    np.savez(os.path.join(HERE, "sinkhorn_points.npz"), x=npy(x), y=npy(y), a=npy(a), b=npy(b), C=npy(C),
+             reg=0.05, plan_fixed25=npy(plan_fixed), plan_thr1e6=npy(plan_conv))
+    # the reference test's own setting: 3x3 symmetric costs, reg = 1e-5 (tests/test_w2_utils.py:236-247)
+    cost = torch.randn(2, 3, 3, 3, generator=g).abs()
+    cost = (cost + cost.transpose(-1, -2)).double()
+    a3 = torch.randn(2, 3, 3, generator=g).abs(); a3 = (a3 / a3.sum(-1, keepdim=True)).double()
+    b3 = torch.randn(2, 3, 3, generator=g).abs(); b3 = (b3 / b3.sum(-1, keepdim=True)).double()
+    plan3 = ref_w2.sinkhorn_log(a3, b3, cost, reg=1e-5, max_iter=1000, threshold=1e-8)
+    np.savez(os.path.join(HERE, "sinkhorn_3x3.npz"), a=npy(a3), b=npy(b3), C=npy(cost), plan=npy(plan3))
+    # CodebookModel.energy cost (inverse distance), the DiscreteTransport cost producer
+    cb = CodebookModel(1, 8, mixture_cfg=dict(n_components=24), dtype=torch.double)
+    pts = torch.randn(1, 32, 8, generator=g, dtype=torch.double)
+    with torch.no_grad():
+        cb.codebook.copy_(torch.randn(1, 24, 8, generator=g, dtype=torch.double))
+    np.savez(os.path.join(HERE, "energy.npz"), pts=npy(pts), codebook=npy(cb.codebook), energy=npy(cb.energy(pts)))
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    case_matrix()
+    case_gaussian()
+    case_w2_functions()
+    case_sinkhorn()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,92 @@
+"""Pins oracle/ot_oracle.py against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
+tests/golden/make_golden.py).  fp64 on both sides, so the tolerance is round-off only."""
+import numpy as np
+import torch
+
+from oracle import ot_oracle as O
+
+RTOL, ATOL = 1e-10, 1e-12
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(got, want, rtol=RTOL, atol=ATOL):
+    got, want = torch.as_tensor(got).double(), T(want).double()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert torch.allclose(got, want, rtol=rtol, atol=atol), (got - want).abs().max().item()
+
+
+def test_matrix_primitives(golden):
+    g = golden("matrix")
+    A = T(g["A"])
+    close(O.sqrtm(A), g["sqrtm"])
+    close(O.invsqrtm(A), g["invsqrtm"])
+    close(O.min_eig(A), g["min_eig"])
+    close(O.min_eig(T(g["indef"])), g["indef_min_eig"])
+    repaired, shift = O.make_psd(T(g["indef"]), strict=True)
+    close(repaired, g["repaired"]); close(shift, g["shift"])
+    mean, cov = O.mean_cov(T(g["sum"]), T(g["sum_cov"]), T(g["n"]))
+    close(mean, g["mean"]); close(cov, g["cov"])
+    assert O.is_symmetric(T(g["asym"])).tolist() == g["asym_is_symmetric"].tolist()
+    assert (O.is_symmetric(A) & O.is_pd(A)).tolist() == g["A_is_spd"].tolist()
+    assert O.is_pd(T(g["indef"])).tolist() == g["indef_is_pd"].tolist()
+
+
+def _pipeline(g, lead_decay=None, pg_star=0.0):
+    src, tgt = T(g["src"]), T(g["tgt"])
+    out = O.gaussian_transport_pipeline(src, tgt, int(g["batch"]), decay=lead_decay, pg_star=pg_star)
+    for k in ("mean_s", "cov_s", "mean_t", "cov_t", "w2", "T"):
+        close(out[k], g[k], rtol=1e-9, atol=1e-10)
+    got, want = out["moved"], T(g["moved"])
+    assert got.dtype == want.dtype == torch.float32
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
+
+
+def test_gaussian_pipeline_d16(golden):
+    g = golden("gaussian_d16")
+    _pipeline(g)
+    st = O.GaussianStats(16)
+    src = T(g["src"])
+    for lo in range(0, src.shape[0], 100):
+        st.update(src[lo:lo + 100])
+    close(st.n_obs, g["n_s"]); close(st.sum, g["sum_s"]); close(st.sum_cov, g["sumcov_s"])
+    assert np.allclose(g["Cw"], 0)
+
+
+def test_gaussian_pipeline_leading_dims_and_pgstar(golden):
+    g = golden("gaussian_lead2_d8")
+    _pipeline(g, pg_star=float(g["pg_star"]))
+
+
+def test_gaussian_pipeline_ema(golden):
+    g = golden("gaussian_ema_d8")
+    _pipeline(g, lead_decay=float(g["decay"]))
+
+
+def test_w2_functions(golden):
+    for name in ("w2_d3", "w2_d24"):
+        g = golden(name)
+        m1, m2, c1, c2 = (T(g[k]) for k in ("m1", "m2", "c1", "c2"))
+        close(O.w2_gaussian(m1, m2, c1, c2), g["w2"], rtol=1e-9, atol=1e-10)
+        Top, _ = O.transport_operator_full(c1, c2)
+        close(Top, g["T"], rtol=1e-8, atol=1e-9)
+        if "x" in g:
+            close(O.apply_transport(T(g["x"]), m1, m2, Top), g["y"], rtol=1e-8, atol=1e-9)
+
+
+def test_sinkhorn(golden):
+    g = golden("sinkhorn_points")
+    a, b, C = T(g["a"]), T(g["b"]), T(g["C"])
+    close(O.sqeuclidean_cost(T(g["x"]), T(g["y"])) /
+          O.sqeuclidean_cost(T(g["x"]), T(g["y"])).amax(dim=(-1, -2), keepdim=True), g["C"])
+    close(O.sinkhorn_log(a, b, C, reg=0.05, max_iter=25, threshold=0.0), g["plan_fixed25"])
+    close(O.sinkhorn_log(a, b, C, reg=0.05, max_iter=1000, threshold=1e-6), g["plan_thr1e6"])
+    g3 = golden("sinkhorn_3x3")
+    close(O.sinkhorn_log(T(g3["a"]), T(g3["b"]), T(g3["C"]), reg=1e-5, max_iter=1000, threshold=1e-8), g3["plan"])
+
+
+def test_energy_cost(golden):
+    g = golden("energy")
+    close(O.inverse_distance_energy(T(g["pts"]), T(g["codebook"])), g["energy"])
