@@ -1,0 +1,192 @@
+/*
+ * otk.h - C ABI of libotk.so: the B200 (sm_100a) kernels behind the latent optimal-transport path of
+ * theoad/ot-vae-lightning.
+ *
+ * The reference has no FFI layer: its boundary is the Python API of `ot_vae_lightning/ot/` and
+ * `ot_vae_lightning/metrics/`.  Each entry point below names the reference interface it replaces
+ * (file:line relative to /root/reference/ot_vae_lightning).  The host-side Python mirror of that API
+ * (`ot-vae-lightning_b200/`) binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no ownership transfer.  Every function returns an otk_status (0 = ok).
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - matrices are row-major and dense: a `[L, d, d]` batch is L contiguous d*d blocks.
+ *   - `dtype` arguments use otk_dtype.  Latents are always fp32; statistics / matrix results are fp32 or fp64.
+ *   - work is enqueued on `stream` (a cudaStream_t / CUstream); nothing synchronises unless stated.
+ *   - no hidden allocation: scratch memory is caller-provided, sized by the matching `*_workspace_bytes`.
+ *   - re-entrant per stream; no global mutable state besides a per-process cache of function attributes.
+ */
+#ifndef OTK_H_
+#define OTK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTK_ABI_VERSION 1
+
+typedef void* otk_stream_t; /* cudaStream_t */
+
+typedef enum {
+  OTK_OK = 0,
+  OTK_ERR_INVALID_ARGUMENT = -1, /* bad shape / null pointer / unsupported dtype      -> ValueError          */
+  OTK_ERR_WORKSPACE = -2,        /* workspace too small                                -> ValueError          */
+  OTK_ERR_CUDA = -3,             /* a CUDA runtime / driver call failed                -> RuntimeError        */
+  OTK_ERR_UNSUPPORTED_DEVICE = -4, /* not an sm_100 device                             -> RuntimeError        */
+  OTK_ERR_NOT_CONVERGED = -5     /* reserved                                                                  */
+} otk_status;
+
+typedef enum { OTK_F32 = 0, OTK_F64 = 1 } otk_dtype;
+
+/* cost kinds for the point-cloud Sinkhorn (K8/K9) */
+typedef enum {
+  OTK_COST_SQEUCLIDEAN = 0, /* |x-y|^2            : w2_utils.py:121-125 (mean part), SURVEY 8d cfg3 */
+  OTK_COST_INV_EUCLIDEAN = 1 /* 1/(|x-y|_2 + 1e-8) : CodebookModel.energy, codebook_model.py:155-160 */
+} otk_cost_kind;
+
+int otk_abi_version(void);
+const char* otk_status_string(int status);
+/* last CUDA error text seen by this thread inside libotk (empty string if none) */
+const char* otk_last_error(void);
+/* 1 if the current device is sm_100 (B200); entry points return OTK_ERR_UNSUPPORTED_DEVICE otherwise */
+int otk_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  streaming sufficient statistics.
+ * Replaces GaussianModel._stats + update (ot/distribution_models/gaussian_model.py:99-108, 144-157),
+ * utils.ema (utils/__init__.py:204-206) and FrechetInceptionDistance._extract_features/update
+ * (metrics/fid.py:99-122).
+ *   x        [L, rows, dim] fp32 latents; row stride `row_stride`, batch stride `batch_stride` (elements)
+ *   n_obs    [L]            running count      (dtype n_dtype)
+ *   sum      [L, dim]       running sum x      (dtype buf_dtype)
+ *   sum_cov  [L, dim, dim]  running sum x x^T  (dtype buf_dtype)
+ * running <- running + new            if decay < 0   (update_decay=None)
+ * running <- running*decay + new*(1-decay) otherwise (update_decay=decay, applied to n_obs too)
+ * `new` is accumulated in fp32 over short row chunks on the tensor cores (3xTF32) or FFMA and across
+ * chunks in fp64.  Workspace is an fp64 staging area (zeroed internally).
+ * ---------------------------------------------------------------------------------------------- */
+size_t otk_stats_update_workspace_bytes(int64_t L, int64_t rows, int64_t dim);
+int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,
+                     int64_t batch_stride, double decay, void* n_obs, int n_dtype, void* sum,
+                     void* sum_cov, int buf_dtype, void* workspace, size_t workspace_bytes,
+                     otk_stream_t stream);
+
+/* K2  mean = sum/n ; cov = sum_cov/n - mean mean^T (biased).  Replaces mean_cov, ot/matrix_utils.py:145-158
+ * (full-matrix branch).  n is a device vector [L] (a python int crashes the reference: utils/__init__.py:322). */
+int otk_mean_cov(const void* sum, const void* sum_cov, const void* n_obs, int n_dtype, int64_t L,
+                 int64_t dim, void* mean, void* cov, int dtype, otk_stream_t stream);
+
+/* The `Symmetric` + `MakePositiveDefinite` parametrizations read on every `.cov` access
+ * (gaussian_model.py:204-229): out = triu(a) + triu(a,1)^T + shift*I, shift [L] (may be NULL). */
+int otk_symmetrize_shift(const void* a, const void* shift, int64_t L, int64_t dim, void* out,
+                         int dtype, otk_stream_t stream);
+
+/* sum((A - A^T)^2) per matrix -> asym [L] fp64.  Replaces is_symmetric, ot/matrix_utils.py:79-88
+ * (the `< 1e-8` comparison is done by the caller). */
+int otk_asymmetry(const void* a, int64_t L, int64_t dim, int dtype, double* asym, otk_stream_t stream);
+
+/* K4  smallest eigenvalue per matrix -> lam_min [L] fp64.  Replaces min_eig, ot/matrix_utils.py:91-98
+ * (used by is_pd :109 and make_psd :132).  Lanczos with full re-orthogonalisation (steps <= dim,
+ * default when steps<=0: min(dim, 96)) + Sturm bisection; not a full eigensolve. */
+size_t otk_min_eig_workspace_bytes(int64_t L, int64_t dim, int steps);
+int otk_min_eig(const void* a, int64_t L, int64_t dim, int dtype, int steps, double* lam_min,
+                void* workspace, size_t workspace_bytes, otk_stream_t stream);
+
+/* K3  matrix square root and inverse square root of SPD matrices by coupled Newton-Schulz in fp32-accurate
+ * arithmetic (3xTF32 on tcgen05 / FFMA), optionally followed by `polish` fp64 correction steps.
+ * Replaces sqrtm / invsqrtm / _matrix_operator, ot/matrix_utils.py:37-76.
+ *   a [L,d,d] (dtype) -> root [L,d,d], iroot [L,d,d] (either may be NULL), same dtype.
+ *   `ridge` is added to the diagonal before the iteration (the reference adds 1e-8 for the inverse
+ *   root, w2_utils.py:766).  iters<=0 selects the default (adaptive, <= 40). */
+size_t otk_sqrtm_workspace_bytes(int64_t L, int64_t dim);
+int otk_sqrtm(const void* a, int64_t L, int64_t dim, int dtype, double ridge, int iters, int polish,
+              void* root, void* iroot, void* workspace, size_t workspace_bytes, otk_stream_t stream);
+
+/* K5  W2^2 = |ms-mt|^2 + tr(Cs + Ct - 2 (Ct^1/2 Cs Ct^1/2)^1/2) -> w2 [L] fp64.
+ * Replaces w2_gaussian, ot/w2_utils.py:40-80 (validation stays in the Python host). */
+size_t otk_w2_gaussian_workspace_bytes(int64_t L, int64_t dim);
+int otk_w2_gaussian(const void* mean_s, const void* mean_t, const void* cov_s, const void* cov_t,
+                    int64_t L, int64_t dim, int dtype, int iters, int polish, double* w2,
+                    void* workspace, size_t workspace_bytes, otk_stream_t stream);
+
+/* K6  T = (1-p) Cs^-1/2 (Cs^1/2 Ct Cs^1/2)^1/2 Cs^-1/2 + p I -> T [L,d,d] (dtype).
+ * Replaces _compute_transport_full_mat, ot/w2_utils.py:756-768 (deterministic full-matrix branch of
+ * compute_transport_operators :391-458).  If w2 != NULL also writes W2^2 [L] fp64 reusing the same roots
+ * (tr((Cs^1/2 Ct Cs^1/2)^1/2) == tr((Ct^1/2 Cs Ct^1/2)^1/2)); means may then not be NULL. */
+size_t otk_transport_operator_workspace_bytes(int64_t L, int64_t dim);
+int otk_transport_operator(const void* cov_s, const void* cov_t, int64_t L, int64_t dim, int dtype,
+                           double pg_star, int iters, int polish, void* T, const void* mean_s,
+                           const void* mean_t, double* w2, void* workspace, size_t workspace_bytes,
+                           otk_stream_t stream);
+
+/* K7  y[l,b,:] = T[l] (x[l,b,:] - mean_s[l]) + mean_t[l].  Replaces apply_transport, ot/w2_utils.py:464-527
+ * (deterministic, full-matrix; as called by W2Mixin.apply_transport :581-597 and
+ * GaussianTransport.transport, transport/gaussian_transport.py:80-95).
+ *   x, y [L, rows, dim] fp32 ; mean_s, mean_t [L, dim] and T [L, dim, dim] in `dtype`.
+ * Workspace holds the fp32 hi/lo split of T and the folded bias. */
+size_t otk_apply_transport_workspace_bytes(int64_t L, int64_t rows, int64_t dim);
+int otk_apply_transport(const float* x, int64_t L, int64_t rows, int64_t dim, const void* mean_s,
+                        const void* mean_t, const void* T, int dtype, float* y, void* workspace,
+                        size_t workspace_bytes, otk_stream_t stream);
+
+/* K8  log-domain Sinkhorn on a materialised cost.  Replaces sinkhorn_log, ot/w2_utils.py:276-319:
+ *   u = v = 0; per iteration v = log(b+1e-8) - LSE_i(u_i - C_ij/reg), then u = log(a+1e-8) - LSE_j(v_j - C_ij/reg);
+ *   stop after the iteration in which min over the batch of sum|du| + sum|dv| < threshold (device-side flag,
+ *   polled from the host every `poll_every` iterations; iterations after the stop are no-ops).
+ *   a [L,N], b [L,M], C [L,N,M] (dtype) -> u [L,N], v [L,M]; plan [L,N,M] = exp(u_i+v_j-C_ij/reg) if not NULL.
+ *   iters_done_host (may be NULL) receives the number of iterations executed (forces a stream sync). */
+size_t otk_sinkhorn_dense_workspace_bytes(int64_t L, int64_t N, int64_t M);
+int otk_sinkhorn_dense(const void* a, const void* b, const void* C, int64_t L, int64_t N, int64_t M,
+                       int dtype, double reg, int max_iter, double threshold, int poll_every, void* u,
+                       void* v, void* plan, int* iters_done_host, void* workspace,
+                       size_t workspace_bytes, otk_stream_t stream);
+
+/* K8/K9  log-domain Sinkhorn between point clouds with the cost tile recomputed on the fly (no N x M matrix
+ * in HBM).  API extension (the reference only takes a materialised C); same recurrences as above with
+ * C_ij = scale * cost(x_i, y_j).  Replaces the cost producers + sinkhorn_log pair in
+ * DiscreteTransport.compute (transport/discrete_transport.py:55-68) and batch_ot_gmm (w2_utils.py:255-269).
+ *   x [N,d], y [M,d] fp32; a [N], b [M] fp32; u [N], v [M] fp32 in/out (not reset if `warm_start`).
+ *   Row-sharded multi-GPU use: call otk_sinkhorn_points_colstep on the local rows of x, combine the
+ *   (max, sumexp) partials of all ranks, then otk_sinkhorn_points_rowstep. */
+size_t otk_sinkhorn_points_workspace_bytes(int64_t N, int64_t M, int64_t dim);
+/* scale = 1/max_ij cost (w2_utils.py:265-266) if scale_inv_max != 0, else `scale`; result in *scale_out_host */
+int otk_sinkhorn_points(const float* x, const float* y, int64_t N, int64_t M, int64_t dim,
+                        const float* a, const float* b, int cost_kind, double scale, int scale_inv_max,
+                        double reg, int max_iter, double threshold, int poll_every, int precision,
+                        float* u, float* v, double* summary /* [4]: <C,pi>, sum pi, max|row err|, max|col err| */,
+                        int* iters_done_host, void* workspace, size_t workspace_bytes,
+                        otk_stream_t stream);
+/* half-steps for the row-sharded path: partial column LSE over local rows (m,s) [2,M]; combine; row step */
+int otk_sinkhorn_points_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M,
+                                int64_t dim, const float* u_local, int cost_kind, double scale, double reg,
+                                int precision, float* col_max, float* col_sum, void* workspace,
+                                size_t workspace_bytes, otk_stream_t stream);
+int otk_lse_combine(const float* part_max, const float* part_sum, int64_t parts, int64_t M,
+                    const float* b, float* v, float* diff /* += sum|dv| */, otk_stream_t stream);
+int otk_sinkhorn_points_rowstep(const float* x_local, const float* y, int64_t n_local, int64_t M,
+                                int64_t dim, const float* a_local, const float* v, int cost_kind,
+                                double scale, double reg, int precision, float* u_local,
+                                float* diff /* += sum|du| */, void* workspace, size_t workspace_bytes,
+                                otk_stream_t stream);
+/* max_ij cost(x_i, y_j) -> *out (device fp32), for the 1/max normalisation */
+int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
+                 float* out, void* workspace, size_t workspace_bytes, otk_stream_t stream);
+/* materialise scale*cost(x_i,y_j) -> C [N,M] fp32 (CodebookModel.energy, codebook_model.py:155-160);
+ * workspace >= (N+M)*4 + 512 bytes (same for otk_cost_max) */
+int otk_cost_matrix(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
+                    double scale, float* C, void* workspace, size_t workspace_bytes, otk_stream_t stream);
+
+/* general fp32-accurate GEMM on the tensor cores used by the kernels above, exported for tests:
+ * C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C   (A, B, C row-major, leading dims lda/ldb/ldc), batched.
+ * engine: 0 = auto, 1 = FFMA (any shape), 2 = tcgen05 3xTF32 (K%4==0, lda/ldb%4==0), 3 = tcgen05 1xTF32 */
+int otk_gemm_nt(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                float alpha, float beta, int engine, otk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTK_H_ */

@@ -1,0 +1,24 @@
+#include "gemm.cuh"
+namespace otk {
+int gemm_f32(const GemmArgs<float>& g, int64_t batch, int engine, cudaStream_t st) {
+  if (engine != ENGINE_SIMT) {
+    int r = gemm_umma_try(g, batch, engine == ENGINE_UMMA_1X ? 1 : 3, st);
+    if (r != 0) return r < 0 ? r : OTK_OK;
+    if (engine == ENGINE_UMMA_3X || engine == ENGINE_UMMA_1X) {
+      set_last_error_msg("gemm: shape not eligible for the tcgen05 engine");
+      return OTK_ERR_INVALID_ARGUMENT;
+    }
+  }
+  return gemm_simt<float>(g, batch, st);
+}
+}  // namespace otk
+using namespace otk;
+extern "C" int otk_gemm_nt(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                           int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                           float alpha, float beta, int engine, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_nt: bad arguments");
+  OTK_REQUIRE(lda >= K && ldb >= K && ldc >= N, "gemm_nt: leading dimension too small");
+  return gemm_f32(nt_args(A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, beta), batch, engine,
+                  as_stream(stream));
+}

@@ -1,0 +1,13 @@
+// fp32-accurate GEMM front end: tcgen05 3xTF32 when the shape is eligible, FFMA otherwise.
+#pragma once
+#include "gemm_simt.cuh"
+namespace otk {
+enum { ENGINE_AUTO = 0, ENGINE_SIMT = 1, ENGINE_UMMA_3X = 2, ENGINE_UMMA_1X = 3 };
+// returns 1 if launched on tcgen05, 0 if not eligible, <0 on error   (gemm_umma.cu)
+int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStream_t st);
+int gemm_f32(const GemmArgs<float>& g, int64_t batch, int engine, cudaStream_t st);
+inline GemmArgs<float> nt_args(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                               int64_t ldb, int64_t ldc, int64_t sA, int64_t sB, int64_t sC, float alpha, float beta) {
+  return GemmArgs<float>{A, B, C, M, N, K, lda, 1, ldb, 1, ldc, sA, sB, sC, alpha, beta, nullptr, 0, nullptr, 0, 0.f, nullptr};
+}
+}  // namespace otk

@@ -1,0 +1,126 @@
+// Generic-shape FFMA/DFMA GEMM (any M, N, K, strides).  This is the engine for shapes the tcgen05 path
+// cannot take (dims that are not multiples of 4, fp64 polish steps, tiny matrices such as the reference
+// tests' d = 3) and the on-device fp32 yardstick the tcgen05 kernels are tested against.
+//
+//   C[m,n] = alpha * sum_k (A(m,k) - a_off[k]) * B(n,k) + beta * C[m,n] + bias[n] + diag_add * delta_mn
+//   A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk],  C row-major with leading dim ldc.
+#pragma once
+#include "otk_common.cuh"
+
+namespace otk {
+
+template <typename T>
+struct GemmArgs {
+  const T* A; const T* B; T* C;
+  int64_t M, N, K;
+  int64_t sam, sak, sbn, sbk, ldc;
+  int64_t strideA, strideB, strideC;  // batch strides (elements)
+  T alpha, beta;
+  const T* a_off; int64_t stride_aoff;  // optional [K] per batch
+  const T* bias;  int64_t stride_bias;  // optional [N] per batch
+  T diag_add;                           // added to C[m,m] (after alpha/beta)
+  double* resid;                        // optional [batch]: += sum_mn (acc[m,n] - delta_mn)^2 of the raw product
+};
+
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmArgs<T> g) {
+  __shared__ T As[SG_BK][SG_BM + 4];
+  __shared__ T Bs[SG_BK][SG_BN + 4];
+  const int64_t batch = blockIdx.z;
+  const T* A = g.A + batch * g.strideA;
+  const T* B = g.B + batch * g.strideB;
+  T* C = g.C + batch * g.strideC;
+  const T* a_off = g.a_off ? g.a_off + batch * g.stride_aoff : nullptr;
+  const T* bias = g.bias ? g.bias + batch * g.stride_bias : nullptr;
+  const int64_t m0 = (int64_t)blockIdx.y * SG_BM, n0 = (int64_t)blockIdx.x * SG_BN;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads, 4 x 4 outputs each
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+
+  // loader mapping: choose the unit-stride direction for coalescing
+  const bool a_kfast = (g.sak == 1), b_kfast = (g.sbk == 1);
+  for (int64_t k0 = 0; k0 < g.K; k0 += SG_BK) {
+#pragma unroll
+    for (int r = 0; r < (SG_BM * SG_BK) / SG_THREADS; ++r) {
+      int e = tid + r * SG_THREADS;
+      int kk = a_kfast ? e % SG_BK : e / SG_BM;
+      int mm = a_kfast ? e / SG_BK : e % SG_BM;
+      int64_t m = m0 + mm, k = k0 + kk;
+      T v = T(0);
+      if (m < g.M && k < g.K) {
+        v = A[m * g.sam + k * g.sak];
+        if (a_off) v -= a_off[k];
+      }
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < (SG_BN * SG_BK) / SG_THREADS; ++r) {
+      int e = tid + r * SG_THREADS;
+      int kk = b_kfast ? e % SG_BK : e / SG_BN;
+      int nn = b_kfast ? e / SG_BK : e % SG_BN;
+      int64_t n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < g.N && k < g.K) ? B[n * g.sbn + k * g.sbk] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double res = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      T r = g.alpha * acc[i][j];
+      if (g.beta != T(0)) r += g.beta * C[m * g.ldc + n];
+      if (bias) r += bias[n];
+      if (m == n) r += g.diag_add;
+      C[m * g.ldc + n] = r;
+      if (g.resid) { double e = (double)acc[i][j] - (m == n ? 1.0 : 0.0); res += e * e; }
+    }
+  }
+  if (g.resid) {
+    res = warp_sum(res);
+    if (tid % 32 == 0) atomicAdd(&g.resid[batch], res);
+  }
+}
+
+template <typename T>
+inline int gemm_simt(const GemmArgs<T>& g, int64_t batch, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || batch <= 0) return OTK_OK;
+  dim3 grid((unsigned)ceil_div(g.N, SG_BN), (unsigned)ceil_div(g.M, SG_BM), (unsigned)batch);
+  gemm_simt_kernel<T><<<grid, SG_THREADS, 0, st>>>(g);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+// convenience: C = alpha * A * B^T (+ beta C) for row-major square-ish operands
+template <typename T>
+inline int gemm_nt_simt(const T* A, const T* B, T* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                        int64_t ldc, int64_t batch, int64_t sA, int64_t sB, int64_t sC, T alpha, T beta,
+                        cudaStream_t st) {
+  GemmArgs<T> g{A, B, C, M, N, K, lda, 1, ldb, 1, ldc, sA, sB, sC, alpha, beta, nullptr, 0, nullptr, 0, T(0), nullptr};
+  return gemm_simt(g, batch, st);
+}
+
+}  // namespace otk

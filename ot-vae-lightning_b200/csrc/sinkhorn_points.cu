@@ -1,0 +1,299 @@
+// K8/K9 (point clouds): log-domain Sinkhorn with the cost recomputed from the points.
+// Reference pair: cost producers (ot/w2_utils.py:121-125 squared distance; CodebookModel.energy,
+// ot/distribution_models/codebook_model.py:155-160) + sinkhorn_log (ot/w2_utils.py:276-319).
+//
+// Two engines behind the same entry points:
+//   * fused tcgen05 engine (sinkhorn_umma.cu): cost tiles on the tensor cores, online LSE out of TMEM, no N x M
+//     matrix in HBM - used when sk_umma_eligible();
+//   * streaming engine: the cost slab is materialised in the caller's workspace and the dense HBM-bound kernels run
+//     on it (any dim / cost kind).
+#include "sinkhorn_dense.cuh"
+#include "sinkhorn_umma.cuh"
+#include <cfloat>
+
+namespace otk {
+
+__global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t n, int64_t d, float* __restrict__ out) {
+  const int lane = threadIdx.x % 32;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  if (row >= n) return;
+  float acc = 0;
+  for (int64_t k = lane; k < d; k += 32) { float v = x[row * d + k]; acc = fmaf(v, v, acc); }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
+__device__ __forceinline__ float cost_from_dot(float dot, float nx, float ny, int kind) {
+  float sq = fmaxf(nx + ny - 2.f * dot, 0.f);
+  return kind == OTK_COST_SQEUCLIDEAN ? sq : 1.f / (sqrtf(sq) + 1e-8f);
+}
+
+// 64x64 tile of cost(x_i, y_j); MODE 0: write scale*cost to C ; MODE 1: max-reduce into *out_max
+constexpr int CT = 64, CT_BK = 16;
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cost_tile_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ nx,
+                 const float* __restrict__ ny, int64_t N, int64_t M, int64_t d, int kind, const float* scale_dev,
+                 float scale_host, float* __restrict__ C, float* out_max) {
+  __shared__ float As[CT_BK][CT + 4], Bs[CT_BK][CT + 4];
+  const int64_t i0 = (int64_t)blockIdx.y * CT, j0 = (int64_t)blockIdx.x * CT;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[4][4] = {};
+  for (int64_t k0 = 0; k0 < d; k0 += CT_BK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int e = tid + r * 256, kk = e % CT_BK, mm = e / CT_BK;
+      int64_t k = k0 + kk;
+      As[kk][mm] = (i0 + mm < N && k < d) ? x[(i0 + mm) * d + k] : 0.f;
+      Bs[kk][mm] = (j0 + mm < M && k < d) ? y[(j0 + mm) * d + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < CT_BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float sc = scale_dev ? *scale_dev : scale_host;
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t gi = i0 + ty * 4 + i;
+    if (gi >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t gj = j0 + tx * 4 + j;
+      if (gj >= M) continue;
+      float c = cost_from_dot(acc[i][j], nx[gi], ny[gj], kind);
+      if (MODE == 0) C[gi * M + gj] = c * sc;
+      else mx = fmaxf(mx, c);
+    }
+  }
+  if (MODE == 1) {
+    mx = warp_max(mx);
+    if (tid % 32 == 0) atomicMax(reinterpret_cast<unsigned*>(out_max), __float_as_uint(mx));  // costs are >= 0
+  }
+}
+
+__global__ void inv_kernel(const float* in, float* out) { *out = 1.f / *in; }
+__global__ void set_kernel(float* out, float v) { *out = v; }
+
+// summary of the plan pi = exp(u_i + v_j - C_ij/reg) without storing it:
+//   rows: row sums (-> max |row - (a+1e-8)| ... compared by the caller against a), <C,pi>, total mass
+__global__ void __launch_bounds__(256)
+plan_row_summary_kernel(const float* __restrict__ C, const float* __restrict__ u, const float* __restrict__ v,
+                        const float* __restrict__ a, int64_t N, int64_t M, float nir, double* summary,
+                        float* __restrict__ colsum) {
+  // one block per row; also accumulates column sums with atomics (M floats)
+  __shared__ double red_c[8], red_m[8];
+  const int64_t i = blockIdx.x;
+  const float ui = u[i];
+  double cost = 0, mass = 0;
+  for (int64_t j = threadIdx.x; j < M; j += 256) {
+    float c = C[i * M + j];
+    float p = __expf(fmaf(c, nir, ui + v[j]));
+    cost += (double)c * p;
+    mass += p;
+    atomicAdd(&colsum[j], p);
+  }
+  cost = warp_sum(cost); mass = warp_sum(mass);
+  if (threadIdx.x % 32 == 0) { red_c[threadIdx.x / 32] = cost; red_m[threadIdx.x / 32] = mass; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tc = 0, tm = 0;
+    for (int w = 0; w < 8; ++w) { tc += red_c[w]; tm += red_m[w]; }
+    atomicAdd(&summary[0], tc);
+    atomicAdd(&summary[1], tm);
+    double err = fabs(tm - (double)a[i]);
+    // max via atomicMax on the bit pattern of a non-negative double
+    atomicMax(reinterpret_cast<unsigned long long*>(&summary[2]), (unsigned long long)__double_as_longlong(err));
+  }
+}
+__global__ void plan_col_err_kernel(const float* colsum, const float* b, int64_t M, double* summary) {
+  double mx = 0;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x)
+    mx = fmax(mx, fabs((double)colsum[j] - (double)b[j]));
+  mx = warp_max(mx);
+  if (threadIdx.x % 32 == 0)
+    atomicMax(reinterpret_cast<unsigned long long*>(&summary[3]), (unsigned long long)__double_as_longlong(mx));
+}
+
+static int build_cost(const float* x, const float* y, int64_t N, int64_t M, int64_t d, int kind, const float* scale_dev,
+                      float scale_host, float* nx, float* ny, float* C, cudaStream_t st) {
+  row_sqnorm_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(x, N, d, nx);
+  row_sqnorm_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, d, ny);
+  dim3 grid((unsigned)ceil_div(M, CT), (unsigned)ceil_div(N, CT));
+  cost_tile_kernel<0><<<grid, 256, 0, st>>>(x, y, nx, ny, N, M, d, kind, scale_dev, scale_host, C, nullptr);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+static size_t stream_ws_bytes(int64_t N, int64_t M) {
+  return align_up((size_t)N * M * 4, 256) + 2 * align_up((size_t)N * 4, 256) + 3 * align_up((size_t)M * 4, 256) +
+         otk_sinkhorn_dense_workspace_bytes(1, N, M) + 4096;
+}
+
+}  // namespace otk
+using namespace otk;
+
+extern "C" size_t otk_sinkhorn_points_workspace_bytes(int64_t N, int64_t M, int64_t dim) {
+  size_t fused = sk_umma_workspace_bytes(N, M, dim);
+  if (sk_umma_eligible(N, M, dim, OTK_COST_SQEUCLIDEAN)) return fused;
+  return stream_ws_bytes(N, M);
+}
+
+extern "C" int otk_cost_matrix(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
+                               double scale, float* C, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x && y && C && N > 0 && M > 0 && dim > 0, "cost_matrix: bad arguments");
+  if (!workspace || workspace_bytes < (size_t)(N + M) * 4 + 512) return OTK_ERR_WORKSPACE;
+  Arena ar(workspace, workspace_bytes);
+  float* nx = ar.take<float>((size_t)N);
+  float* ny = ar.take<float>((size_t)M);
+  return build_cost(x, y, N, M, dim, cost_kind, nullptr, (float)scale, nx, ny, C, as_stream(stream));
+}
+
+extern "C" int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind, float* out,
+                            void* workspace, size_t workspace_bytes, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x && y && out && N > 0 && M > 0 && dim > 0, "cost_max: bad arguments");
+  if (!workspace || workspace_bytes < (size_t)(N + M) * 4 + 512) return OTK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  Arena ar(workspace, workspace_bytes);
+  float* nx = ar.take<float>((size_t)N);
+  float* ny = ar.take<float>((size_t)M);
+  row_sqnorm_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(x, N, dim, nx);
+  row_sqnorm_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, dim, ny);
+  set_kernel<<<1, 1, 0, st>>>(out, 0.f);
+  dim3 grid((unsigned)ceil_div(M, CT), (unsigned)ceil_div(N, CT));
+  cost_tile_kernel<1><<<grid, 256, 0, st>>>(x, y, nx, ny, N, M, dim, cost_kind, nullptr, 1.f, nullptr, out);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+extern "C" int otk_sinkhorn_points(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, const float* a,
+                                   const float* b, int cost_kind, double scale, int scale_inv_max, double reg,
+                                   int max_iter, double threshold, int poll_every, int precision, float* u, float* v,
+                                   double* summary, int* iters_done_host, void* workspace, size_t workspace_bytes,
+                                   otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x && y && a && b && u && v && N > 0 && M > 0 && dim > 0, "sinkhorn_points: bad arguments");
+  OTK_REQUIRE(reg > 0 && max_iter >= 0, "sinkhorn_points: reg must be > 0");
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(N, M, dim)) return OTK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  if (sk_umma_eligible(N, M, dim, cost_kind))
+    return sk_umma_solve(x, y, N, M, dim, a, b, scale, scale_inv_max, reg, max_iter, threshold, poll_every, precision, u,
+                         v, summary, iters_done_host, workspace, workspace_bytes, st);
+  // streaming engine
+  Arena ar(workspace, workspace_bytes);
+  float* C = ar.take<float>((size_t)N * M);
+  float* nx = ar.take<float>((size_t)N);
+  float* ny = ar.take<float>((size_t)M);
+  float* sc = ar.take<float>(64);
+  float* colsum = ar.take<float>((size_t)M);
+  size_t used = align_up(ar.off, 256);
+  const float* scale_dev = nullptr;
+  if (scale_inv_max) {
+    row_sqnorm_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(x, N, dim, nx);
+    row_sqnorm_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, dim, ny);
+    set_kernel<<<1, 1, 0, st>>>(sc + 1, 0.f);
+    dim3 grid((unsigned)ceil_div(M, CT), (unsigned)ceil_div(N, CT));
+    cost_tile_kernel<1><<<grid, 256, 0, st>>>(x, y, nx, ny, N, M, dim, cost_kind, nullptr, 1.f, nullptr, sc + 1);
+    inv_kernel<<<1, 1, 0, st>>>(sc + 1, sc);
+    scale_dev = sc;
+  }
+  OTK_TRY(build_cost(x, y, N, M, dim, cost_kind, scale_dev, (float)scale, nx, ny, C, st));
+  OTK_TRY(sinkhorn_dense_f32(a, b, C, 1, N, M, reg, max_iter, threshold, poll_every, u, v, nullptr, iters_done_host,
+                             (char*)workspace + used, workspace_bytes - used, false, st));
+  if (summary) {
+    OTK_CUDA(cudaMemsetAsync(summary, 0, 4 * sizeof(double), st));
+    OTK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)M * 4, st));
+    plan_row_summary_kernel<<<(unsigned)N, 256, 0, st>>>(C, u, v, a, N, M, (float)(-1.0 / reg), summary, colsum);
+    plan_col_err_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(colsum, b, M, summary);
+    OTK_LAUNCH_CHECK();
+  }
+  return OTK_OK;
+}
+
+extern "C" int otk_sinkhorn_points_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
+                                           const float* u_local, int cost_kind, double scale, double reg, int precision,
+                                           float* col_max, float* col_sum, void* workspace, size_t workspace_bytes,
+                                           otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x_local && y && u_local && col_max && col_sum && n_local > 0 && M > 0 && dim > 0, "colstep: bad arguments");
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim)) return OTK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  if (sk_umma_eligible(n_local, M, dim, cost_kind))
+    return sk_umma_colstep(x_local, y, n_local, M, dim, u_local, scale, reg, precision, col_max, col_sum, workspace,
+                           workspace_bytes, st);
+  Arena ar(workspace, workspace_bytes);
+  float* C = ar.take<float>((size_t)n_local * M);
+  float* nx = ar.take<float>((size_t)n_local);
+  float* ny = ar.take<float>((size_t)M);
+  size_t used = align_up(ar.off, 256);
+  OTK_TRY(build_cost(x_local, y, n_local, M, dim, cost_kind, nullptr, (float)scale, nx, ny, C, st));
+  return dense_col_partial_f32(C, u_local, n_local, M, reg, col_max, col_sum, (char*)workspace + used,
+                               workspace_bytes - used, st);
+}
+
+namespace otk {
+__global__ void lse_combine_kernel(const float* pm, const float* ps, int64_t parts, int64_t M, const float* b, float* v,
+                                   float* diff) {
+  __shared__ float red[32];
+  float acc = 0;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+    float mm = pm[j], ss = ps[j];
+    for (int64_t p = 1; p < parts; ++p) {
+      float m2 = pm[p * M + j], s2 = ps[p * M + j];
+      if (m2 > mm) { ss = ss * __expf(mm - m2) + s2; mm = m2; } else ss += s2 * __expf(m2 - mm);
+    }
+    float vn = logf(b[j] + 1e-8f) - (mm + logf(ss));
+    acc += fabsf(vn - v[j]);
+    v[j] = vn;
+  }
+  acc = warp_sum(acc);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && diff) { float t = 0; for (int w = 0; w < blockDim.x / 32; ++w) t += red[w]; atomicAdd(diff, t); }
+}
+}  // namespace otk
+
+extern "C" int otk_lse_combine(const float* part_max, const float* part_sum, int64_t parts, int64_t M, const float* b,
+                               float* v, float* diff, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(part_max && part_sum && b && v && parts > 0 && M > 0, "lse_combine: bad arguments");
+  int64_t blocks = ceil_div(M, 256);
+  if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+  lse_combine_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(part_max, part_sum, parts, M, b, v, diff);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+extern "C" int otk_sinkhorn_points_rowstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
+                                           const float* a_local, const float* v, int cost_kind, double scale, double reg,
+                                           int precision, float* u_local, float* diff, void* workspace,
+                                           size_t workspace_bytes, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x_local && y && a_local && v && u_local && n_local > 0 && M > 0 && dim > 0, "rowstep: bad arguments");
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim)) return OTK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  if (sk_umma_eligible(n_local, M, dim, cost_kind))
+    return sk_umma_rowstep(x_local, y, n_local, M, dim, a_local, v, scale, reg, precision, u_local, diff, workspace,
+                           workspace_bytes, st);
+  Arena ar(workspace, workspace_bytes);
+  float* C = ar.take<float>((size_t)n_local * M);
+  float* nx = ar.take<float>((size_t)n_local);
+  float* ny = ar.take<float>((size_t)M);
+  size_t used = align_up(ar.off, 256);
+  OTK_TRY(build_cost(x_local, y, n_local, M, dim, cost_kind, nullptr, (float)scale, nx, ny, C, st));
+  return dense_row_step_f32(C, v, n_local, M, reg, a_local, u_local, diff, (char*)workspace + used, workspace_bytes - used,
+                            st);
+}

@@ -1,0 +1,17 @@
+// fused tcgen05 Sinkhorn engine hooks (sinkhorn_umma.cu)
+#pragma once
+#include "otk_common.cuh"
+namespace otk {
+bool sk_umma_eligible(int64_t N, int64_t M, int64_t dim, int cost_kind);
+size_t sk_umma_workspace_bytes(int64_t N, int64_t M, int64_t dim);
+int sk_umma_solve(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, const float* a, const float* b,
+                  double scale, int scale_inv_max, double reg, int max_iter, double threshold, int poll_every, int precision,
+                  float* u, float* v, double* summary, int* iters_done_host, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st);
+int sk_umma_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* u_local,
+                    double scale, double reg, int precision, float* col_max, float* col_sum, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+int sk_umma_rowstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* a_local,
+                    const float* v, double scale, double reg, int precision, float* u_local, float* diff, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+}  // namespace otk

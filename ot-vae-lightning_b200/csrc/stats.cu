@@ -1,0 +1,221 @@
+// K1/K2: streaming sufficient statistics (sum x, sum x x^T, n) and the mean/cov finaliser.
+// Reference: ot/distribution_models/gaussian_model.py:99-108,144-157 ; utils/__init__.py:204-206 ;
+//            metrics/fid.py:99-122 ; ot/matrix_utils.py:145-158.
+#include "otk_common.cuh"
+#include "stats_umma.cuh"
+
+namespace otk {
+
+// ------------------------------------------------------------------------------------------------
+// FFMA engine (any dim): one CTA = one upper-triangular 64x64 tile pair x one chunk of rows.
+// fp32 accumulation inside the chunk (<= ST_MAX_CHUNK rows), fp64 atomics across chunks.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_T = 64, ST_BK = 16, ST_THREADS = 256;
+
+__global__ void __launch_bounds__(ST_THREADS)
+stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
+                  int64_t chunk_rows, int n_tiles, double* __restrict__ ws_cov, double* __restrict__ ws_sum) {
+  __shared__ float As[ST_BK][ST_T + 4];
+  __shared__ float Bs[ST_BK][ST_T + 4];
+  // decode the upper-triangular tile pair (ti <= tj) from blockIdx.x
+  int p = blockIdx.x, ti = 0;
+  while (p >= n_tiles - ti) { p -= n_tiles - ti; ++ti; }
+  const int tj = ti + p;
+  const int64_t l = blockIdx.z;
+  const int64_t r0 = (int64_t)blockIdx.y * chunk_rows;
+  const int64_t r1 = min(rows, r0 + chunk_rows);
+  const float* xb = x + l * batch_stride;
+  const int64_t i0 = (int64_t)ti * ST_T, j0 = (int64_t)tj * ST_T;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float colsum = 0.f;  // threads 0..63 of a diagonal CTA own one column each
+
+  for (int64_t k0 = r0; k0 < r1; k0 += ST_BK) {
+#pragma unroll
+    for (int r = 0; r < (ST_T * ST_BK) / ST_THREADS; ++r) {
+      int e = tid + r * ST_THREADS;
+      int kk = e / ST_T, cc = e % ST_T;
+      int64_t row = k0 + kk;
+      bool rok = row < r1;
+      As[kk][cc] = (rok && i0 + cc < dim) ? xb[row * row_stride + i0 + cc] : 0.f;
+      Bs[kk][cc] = (rok && j0 + cc < dim) ? xb[row * row_stride + j0 + cc] : 0.f;
+    }
+    __syncthreads();
+    if (ti == tj && tid < ST_T) {
+#pragma unroll
+      for (int kk = 0; kk < ST_BK; ++kk) colsum += As[kk][tid];
+    }
+#pragma unroll
+    for (int kk = 0; kk < ST_BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double* cov = ws_cov + l * dim * dim;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t gi = i0 + ty * 4 + i;
+    if (gi >= dim) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t gj = j0 + tx * 4 + j;
+      if (gj < dim) atomicAdd(&cov[gi * dim + gj], (double)acc[i][j]);
+    }
+  }
+  if (ti == tj && tid < ST_T && i0 + tid < dim) atomicAdd(&ws_sum[l * dim + i0 + tid], (double)colsum);
+}
+
+// merge the fp64 staging area into the running buffers (mirror the lower triangle, apply the EMA rule)
+__global__ void stats_merge_kernel(const double* __restrict__ ws_cov, const double* __restrict__ ws_sum, int64_t L,
+                                   int64_t dim, int tile, double rows, double decay, void* n_obs, int n_dtype,
+                                   void* sum, void* sum_cov, int buf_dtype) {
+  const int64_t total = L * dim * dim;
+  const double keep = decay < 0 ? 1.0 : decay, gain = decay < 0 ? 1.0 : 1.0 - decay;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
+    // only tiles with tile(i) <= tile(j) were accumulated
+    double v = (i / tile <= j / tile) ? ws_cov[l * dim * dim + i * dim + j] : ws_cov[l * dim * dim + j * dim + i];
+    store_real(sum_cov, e, buf_dtype, load_real(sum_cov, e, buf_dtype) * keep + v * gain);
+    if (r < dim) {
+      int64_t s = l * dim + r;
+      store_real(sum, s, buf_dtype, load_real(sum, s, buf_dtype) * keep + ws_sum[s] * gain);
+    }
+    if (r == 0) store_real(n_obs, l, n_dtype, load_real(n_obs, l, n_dtype) * keep + rows * gain);
+  }
+}
+
+__global__ void mean_cov_kernel(const void* sum, const void* sum_cov, const void* n_obs, int n_dtype, int64_t L,
+                                int64_t dim, void* mean, void* cov, int dt) {
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
+    double n = load_real(n_obs, l, n_dtype);
+    double mi = load_real(sum, l * dim + i, dt) / n, mj = load_real(sum, l * dim + j, dt) / n;
+    store_real(cov, e, dt, load_real(sum_cov, e, dt) / n - mi * mj);
+    if (j == 0) store_real(mean, l * dim + i, dt, mi);
+  }
+}
+
+__global__ void symmetrize_shift_kernel(const void* a, const void* shift, int64_t L, int64_t dim, void* out, int dt) {
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
+    double v = load_real(a, l * dim * dim + (i <= j ? i * dim + j : j * dim + i), dt);
+    if (i == j && shift) v += load_real(shift, l, dt);
+    store_real(out, e, dt, v);
+  }
+}
+
+__global__ void asymmetry_kernel(const void* a, int64_t L, int64_t dim, int dt, double* asym) {
+  // one block per matrix
+  const int64_t l = blockIdx.x;
+  double acc = 0;
+  for (int64_t e = threadIdx.x; e < dim * dim; e += blockDim.x) {
+    int64_t i = e / dim, j = e % dim;
+    double d = load_real(a, l * dim * dim + e, dt) - load_real(a, l * dim * dim + j * dim + i, dt);
+    acc += d * d;
+  }
+  __shared__ double red[32];
+  acc = warp_sum(acc);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < blockDim.x / 32 ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) asym[l] = v;
+  }
+}
+
+static inline unsigned ew_grid(int64_t total) {
+  int64_t b = ceil_div(total, 256);
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace otk
+
+using namespace otk;
+
+extern "C" size_t otk_stats_update_workspace_bytes(int64_t L, int64_t rows, int64_t dim) {
+  (void)rows;
+  return align_up((size_t)L * dim * dim * 8, 256) + align_up((size_t)L * dim * 8, 256) + stats_umma_extra_workspace(L, dim);
+}
+
+extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,
+                                int64_t batch_stride, double decay, void* n_obs, int n_dtype, void* sum, void* sum_cov,
+                                int buf_dtype, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(L > 0 && dim > 0 && rows >= 0, "stats_update: bad shape");
+  OTK_REQUIRE(rows == 0 || x, "stats_update: null latents");
+  OTK_REQUIRE(n_obs && sum && sum_cov, "stats_update: null running buffer");
+  OTK_REQUIRE(row_stride >= dim, "stats_update: row_stride < dim");
+  if (workspace_bytes < otk_stats_update_workspace_bytes(L, rows, dim) || !workspace) return OTK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  Arena ar(workspace, workspace_bytes);
+  double* ws_cov = ar.take<double>((size_t)L * dim * dim);
+  double* ws_sum = ar.take<double>((size_t)L * dim);
+  OTK_CUDA(cudaMemsetAsync(workspace, 0, align_up((size_t)L * dim * dim * 8, 256) + (size_t)L * dim * 8, st));
+  int tile = ST_T;
+  if (rows > 0) {
+    int used = stats_umma_try(x, L, rows, dim, row_stride, batch_stride, ws_cov, ws_sum, ar, st, &tile);
+    if (used < 0) return used;
+    if (!used) {
+      tile = ST_T;
+      int n_tiles = (int)ceil_div(dim, ST_T);
+      int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
+      // enough chunks for ~4 waves, chunk length a multiple of ST_BK and <= 2048 rows (fp32 accumulation span)
+      int64_t want = ceil_div((int64_t)sm_count() * 4, pairs * L);
+      int64_t chunk = ceil_div(ceil_div(rows, want), ST_BK) * ST_BK;
+      if (chunk < 64) chunk = 64;
+      if (chunk > 2048) chunk = 2048;
+      dim3 grid((unsigned)pairs, (unsigned)ceil_div(rows, chunk), (unsigned)L);
+      OTK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stats_update: too many row chunks / batches");
+      stats_simt_kernel<<<grid, ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride, chunk, n_tiles, ws_cov,
+                                                     ws_sum);
+      OTK_LAUNCH_CHECK();
+    }
+  }
+  stats_merge_kernel<<<ew_grid(L * dim * dim), 256, 0, st>>>(ws_cov, ws_sum, L, dim, tile, (double)rows, decay, n_obs,
+                                                            n_dtype, sum, sum_cov, buf_dtype);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+extern "C" int otk_mean_cov(const void* sum, const void* sum_cov, const void* n_obs, int n_dtype, int64_t L,
+                            int64_t dim, void* mean, void* cov, int dtype, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(L > 0 && dim > 0 && sum && sum_cov && n_obs && mean && cov, "mean_cov: bad arguments");
+  mean_cov_kernel<<<ew_grid(L * dim * dim), 256, 0, as_stream(stream)>>>(sum, sum_cov, n_obs, n_dtype, L, dim, mean,
+                                                                        cov, dtype);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+extern "C" int otk_symmetrize_shift(const void* a, const void* shift, int64_t L, int64_t dim, void* out, int dtype,
+                                    otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(L > 0 && dim > 0 && a && out && a != out, "symmetrize_shift: bad arguments (in-place not allowed)");
+  symmetrize_shift_kernel<<<ew_grid(L * dim * dim), 256, 0, as_stream(stream)>>>(a, shift, L, dim, out, dtype);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+extern "C" int otk_asymmetry(const void* a, int64_t L, int64_t dim, int dtype, double* asym, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(L > 0 && dim > 0 && a && asym, "asymmetry: bad arguments");
+  asymmetry_kernel<<<(unsigned)L, 256, 0, as_stream(stream)>>>(a, L, dim, dtype, asym);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}

@@ -1,0 +1,10 @@
+// tcgen05 engine hook for the streaming statistics (filled in by stats_umma.cu).
+#pragma once
+#include "otk_common.cuh"
+namespace otk {
+size_t stats_umma_extra_workspace(int64_t L, int64_t dim);
+// returns 1 if the tcgen05 kernel handled the update (and sets *tile to its output tile size),
+// 0 if the shape is not eligible, <0 on error.
+int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
+                   double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile);
+}  // namespace otk

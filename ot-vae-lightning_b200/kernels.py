@@ -1,0 +1,322 @@
+"""Tensor-level wrappers over the C ABI (one function per libotk entry point).
+
+Inputs may live on the host: they are copied to the compute device (H2D on the current stream) and the
+caller decides where results go.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native as N
+
+
+def _dev_tensor(t: Tensor, device: torch.device, dtype: Optional[torch.dtype] = None) -> Tensor:
+    if dtype is None:
+        dtype = t.dtype if t.dtype in (torch.float32, torch.float64) else torch.float32
+    return t.detach().to(device=device, dtype=dtype, non_blocking=True).contiguous()
+
+
+def _lead(shape, tail: int) -> Tuple[torch.Size, int]:
+    lead = torch.Size(shape[:len(shape) - tail])
+    return lead, int(lead.numel())
+
+
+def stats_update(x: Tensor, n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, decay: Optional[float]) -> None:
+    """In-place update of the running buffers (all on one CUDA device) with latents x [*L, B, d] (fp32)."""
+    dev = run_sum.device
+    d = run_sum.shape[-1]
+    lead, L = _lead(run_sum.shape, 1)
+    x = _dev_tensor(x, dev, torch.float32)
+    x = x.expand(*lead, *x.shape[-2:]) if x.shape[:-2] != lead else x
+    x = x.contiguous().view(L, -1, d)
+    rows = x.shape[1]
+    lib = N.load()
+    for buf in (n_obs, run_sum, run_cov):
+        if not (buf.is_cuda and buf.is_contiguous()):
+            raise ValueError("running buffers must be contiguous CUDA tensors")
+    with torch.cuda.device(dev):
+        need = lib.otk_stats_update_workspace_bytes(L, rows, d)
+        ws = N.workspace(need, dev)
+        st = lib.otk_stats_update(N.ptr(x), L, rows, d, d, rows * d, -1.0 if decay is None else float(decay),
+                                  N.ptr(n_obs), N.dtype_code(n_obs.dtype), N.ptr(run_sum), N.ptr(run_cov),
+                                  N.dtype_code(run_sum.dtype), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_stats_update")
+
+
+def mean_cov(run_sum: Tensor, run_cov: Tensor, n_obs: Tensor) -> Tuple[Tensor, Tensor]:
+    dev = N.compute_device(run_sum)
+    dt = run_sum.dtype if run_sum.dtype in (torch.float32, torch.float64) else torch.float32
+    s, c = _dev_tensor(run_sum, dev, dt), _dev_tensor(run_cov, dev, dt)
+    d = s.shape[-1]
+    lead, L = _lead(s.shape, 1)
+    n = _dev_tensor(n_obs, dev, torch.float64).expand(lead).contiguous()
+    mean, cov = torch.empty_like(s), torch.empty_like(c)
+    with torch.cuda.device(dev):
+        st = N.load().otk_mean_cov(N.ptr(s), N.ptr(c), N.ptr(n), N.F64, L, d, N.ptr(mean), N.ptr(cov),
+                                   N.dtype_code(dt), N.stream_ptr(dev))
+    N.check(st, "otk_mean_cov")
+    return mean, cov
+
+
+def symmetrize_shift(a: Tensor, shift: Optional[Tensor]) -> Tensor:
+    dev = N.compute_device(a)
+    a = _dev_tensor(a, dev)
+    d = a.shape[-1]
+    lead, L = _lead(a.shape, 2)
+    sh = None if shift is None else _dev_tensor(shift, dev, a.dtype).expand(lead).contiguous()
+    out = torch.empty_like(a)
+    with torch.cuda.device(dev):
+        st = N.load().otk_symmetrize_shift(N.ptr(a), N.ptr(sh), L, d, N.ptr(out), N.dtype_code(a.dtype),
+                                           N.stream_ptr(dev))
+    N.check(st, "otk_symmetrize_shift")
+    return out
+
+
+def asymmetry(a: Tensor) -> Tensor:
+    dev = N.compute_device(a)
+    a = _dev_tensor(a, dev)
+    d = a.shape[-1]
+    lead, L = _lead(a.shape, 2)
+    out = torch.empty(lead, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = N.load().otk_asymmetry(N.ptr(a), L, d, N.dtype_code(a.dtype), N.ptr(out), N.stream_ptr(dev))
+    N.check(st, "otk_asymmetry")
+    return out
+
+
+def min_eig(a: Tensor, steps: int = 0) -> Tensor:
+    dev = N.compute_device(a)
+    a = _dev_tensor(a, dev)
+    d = a.shape[-1]
+    lead, L = _lead(a.shape, 2)
+    out = torch.empty(lead, dtype=torch.float64, device=dev)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_min_eig_workspace_bytes(L, d, steps), dev)
+        st = lib.otk_min_eig(N.ptr(a), L, d, N.dtype_code(a.dtype), steps, N.ptr(out), N.ptr(ws), ws.numel(),
+                             N.stream_ptr(dev))
+    N.check(st, "otk_min_eig")
+    return out
+
+
+def sqrtm_pair(a: Tensor, want_root: bool = True, want_iroot: bool = True, ridge: float = 0.0, iters: int = 0
+               ) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    dev = N.compute_device(a)
+    a = _dev_tensor(a, dev)
+    d = a.shape[-1]
+    lead, L = _lead(a.shape, 2)
+    root = torch.empty_like(a) if want_root else None
+    iroot = torch.empty_like(a) if want_iroot else None
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_sqrtm_workspace_bytes(L, d), dev)
+        st = lib.otk_sqrtm(N.ptr(a), L, d, N.dtype_code(a.dtype), float(ridge), int(iters), 0, N.ptr(root),
+                           N.ptr(iroot), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_sqrtm")
+    return root, iroot
+
+
+def _bcast(t: Tensor, lead: torch.Size, tail: int) -> Tensor:
+    return t.expand(*lead, *t.shape[t.dim() - tail:]).contiguous()
+
+
+def w2_gaussian(mean_s: Tensor, mean_t: Tensor, cov_s: Tensor, cov_t: Tensor, iters: int = 0) -> Tensor:
+    dev = N.compute_device(cov_s, cov_t, mean_s, mean_t)
+    dt = torch.float64 if any(t.dtype == torch.float64 for t in (mean_s, mean_t, cov_s, cov_t)) else torch.float32
+    ms, mt, cs, ct = (_dev_tensor(t, dev, dt) for t in (mean_s, mean_t, cov_s, cov_t))
+    d = cs.shape[-1]
+    lead = torch.broadcast_shapes(ms.shape[:-1], mt.shape[:-1], cs.shape[:-2], ct.shape[:-2])
+    L = int(lead.numel())
+    ms, mt, cs, ct = _bcast(ms, lead, 1), _bcast(mt, lead, 1), _bcast(cs, lead, 2), _bcast(ct, lead, 2)
+    out = torch.empty(lead, dtype=torch.float64, device=dev)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_w2_gaussian_workspace_bytes(L, d), dev)
+        st = lib.otk_w2_gaussian(N.ptr(ms), N.ptr(mt), N.ptr(cs), N.ptr(ct), L, d, N.dtype_code(dt), int(iters), 0,
+                                 N.ptr(out), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_w2_gaussian")
+    return out
+
+
+def transport_operator(cov_s: Tensor, cov_t: Tensor, pg_star: float = 0.0, mean_s: Optional[Tensor] = None,
+                       mean_t: Optional[Tensor] = None, iters: int = 0) -> Tuple[Tensor, Optional[Tensor]]:
+    """T [*L,d,d] (dtype of the covariances) and, if means are given, W2^2 [*L] (fp64) from the same roots."""
+    dev = N.compute_device(cov_s, cov_t)
+    dt = torch.float64 if (cov_s.dtype == torch.float64 or cov_t.dtype == torch.float64) else torch.float32
+    cs, ct = _dev_tensor(cov_s, dev, dt), _dev_tensor(cov_t, dev, dt)
+    d = cs.shape[-1]
+    lead = torch.broadcast_shapes(cs.shape[:-2], ct.shape[:-2])
+    L = int(lead.numel())
+    cs, ct = _bcast(cs, lead, 2), _bcast(ct, lead, 2)
+    T = torch.empty_like(cs)
+    ms = mt = w2 = None
+    if mean_s is not None and mean_t is not None:
+        ms, mt = _bcast(_dev_tensor(mean_s, dev, dt), lead, 1), _bcast(_dev_tensor(mean_t, dev, dt), lead, 1)
+        w2 = torch.empty(lead, dtype=torch.float64, device=dev)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_transport_operator_workspace_bytes(L, d), dev)
+        st = lib.otk_transport_operator(N.ptr(cs), N.ptr(ct), L, d, N.dtype_code(dt), float(pg_star), int(iters), 0,
+                                        N.ptr(T), N.ptr(ms), N.ptr(mt), N.ptr(w2), N.ptr(ws), ws.numel(),
+                                        N.stream_ptr(dev))
+    N.check(st, "otk_transport_operator")
+    return T, w2
+
+
+def apply_transport(x: Tensor, mean_s: Tensor, mean_t: Tensor, T: Tensor) -> Tensor:
+    """y = T (x - mean_s) + mean_t; x [*L, B, d] any float dtype/device -> fp32 result on the compute device."""
+    dev = N.compute_device(T, mean_s, x)
+    dt = T.dtype if T.dtype in (torch.float32, torch.float64) else torch.float32
+    Td, ms, mt = _dev_tensor(T, dev, dt), _dev_tensor(mean_s, dev, dt), _dev_tensor(mean_t, dev, dt)
+    xd = _dev_tensor(x, dev, torch.float32)
+    d = xd.shape[-1]
+    lead = torch.broadcast_shapes(xd.shape[:-2], Td.shape[:-2], ms.shape[:-1], mt.shape[:-1])
+    L = int(lead.numel())
+    rows = xd.shape[-2]
+    xd = _bcast(xd, lead, 2)
+    Td, ms, mt = _bcast(Td, lead, 2), _bcast(ms, lead, 1), _bcast(mt, lead, 1)
+    y = torch.empty_like(xd)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_apply_transport_workspace_bytes(L, rows, d), dev)
+        st = lib.otk_apply_transport(N.ptr(xd), L, rows, d, N.ptr(ms), N.ptr(mt), N.ptr(Td), N.dtype_code(dt),
+                                     N.ptr(y), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_apply_transport")
+    return y
+
+
+def sinkhorn_dense(a: Tensor, b: Tensor, Cm: Tensor, reg: float, max_iter: int, threshold: float,
+                   want_plan: bool = True, poll_every: int = 16):
+    """Returns (plan or None, u, v, iterations) on the compute device, dtype of C (fp32/fp64)."""
+    dev = N.compute_device(Cm, a, b)
+    dt = torch.float64 if Cm.dtype == torch.float64 else torch.float32
+    Cd = _dev_tensor(Cm, dev, dt)
+    n, m = Cd.shape[-2:]
+    lead = torch.broadcast_shapes(Cd.shape[:-2], a.shape[:-1], b.shape[:-1])
+    L = int(lead.numel())
+    Cd = _bcast(Cd, lead, 2)
+    ad, bd = _bcast(_dev_tensor(a, dev, dt), lead, 1), _bcast(_dev_tensor(b, dev, dt), lead, 1)
+    u, v = torch.empty_like(ad), torch.empty_like(bd)
+    plan = torch.empty_like(Cd) if want_plan else None
+    iters = C.c_int(0)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_sinkhorn_dense_workspace_bytes(L, n, m), dev)
+        st = lib.otk_sinkhorn_dense(N.ptr(ad), N.ptr(bd), N.ptr(Cd), L, n, m, N.dtype_code(dt), float(reg),
+                                    int(max_iter), float(threshold), int(poll_every), N.ptr(u), N.ptr(v), N.ptr(plan),
+                                    C.byref(iters), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_sinkhorn_dense")
+    return plan, u, v, iters.value
+
+
+def sinkhorn_points(x: Tensor, y: Tensor, a: Tensor, b: Tensor, reg: float, max_iter: int, threshold: float = 0.0,
+                    cost: int = N.COST_SQEUCLIDEAN, scale: Optional[float] = None, precision: int = 0,
+                    poll_every: int = 16, want_summary: bool = True, want_iters: bool = True):
+    """Point-cloud Sinkhorn (no N x M matrix in HBM on the fused engine).  scale=None -> 1/max cost.
+    Returns dict(u, v, summary=[<C,pi>, mass, max row err, max col err] or None, iters)."""
+    dev = N.compute_device(x, y)
+    xd, yd = _dev_tensor(x, dev, torch.float32), _dev_tensor(y, dev, torch.float32)
+    ad, bd = _dev_tensor(a, dev, torch.float32), _dev_tensor(b, dev, torch.float32)
+    n, d = xd.shape
+    m = yd.shape[0]
+    u = torch.zeros(n, dtype=torch.float32, device=dev)
+    v = torch.zeros(m, dtype=torch.float32, device=dev)
+    summary = torch.zeros(4, dtype=torch.float64, device=dev) if want_summary else None
+    iters = C.c_int(0)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d), dev)
+        st = lib.otk_sinkhorn_points(N.ptr(xd), N.ptr(yd), n, m, d, N.ptr(ad), N.ptr(bd), int(cost),
+                                     1.0 if scale is None else float(scale), 1 if scale is None else 0, float(reg),
+                                     int(max_iter), float(threshold), int(poll_every), int(precision), N.ptr(u),
+                                     N.ptr(v), N.ptr(summary), C.byref(iters) if want_iters else None, N.ptr(ws),
+                                     ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_sinkhorn_points")
+    return dict(u=u, v=v, summary=summary, iters=iters.value)
+
+
+def cost_matrix(x: Tensor, y: Tensor, cost: int, scale: float = 1.0) -> Tensor:
+    dev = N.compute_device(x, y)
+    xd, yd = _dev_tensor(x, dev, torch.float32), _dev_tensor(y, dev, torch.float32)
+    n, d = xd.shape
+    m = yd.shape[0]
+    out = torch.empty(n, m, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = N.workspace((n + m) * 4 + 512, dev)
+        st = N.load().otk_cost_matrix(N.ptr(xd), N.ptr(yd), n, m, d, int(cost), float(scale), N.ptr(out), N.ptr(ws),
+                                      ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_cost_matrix")
+    return out
+
+
+def cost_max(x: Tensor, y: Tensor, cost: int) -> Tensor:
+    dev = N.compute_device(x, y)
+    xd, yd = _dev_tensor(x, dev, torch.float32), _dev_tensor(y, dev, torch.float32)
+    n, d = xd.shape
+    m = yd.shape[0]
+    out = torch.zeros(1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = N.workspace((n + m) * 4 + 512, dev)
+        st = N.load().otk_cost_max(N.ptr(xd), N.ptr(yd), n, m, d, int(cost), N.ptr(out), N.ptr(ws), ws.numel(),
+                                   N.stream_ptr(dev))
+    N.check(st, "otk_cost_max")
+    return out
+
+
+def colstep(x_local: Tensor, y: Tensor, u_local: Tensor, scale: float, reg: float, cost: int = N.COST_SQEUCLIDEAN,
+            precision: int = 0) -> Tuple[Tensor, Tensor]:
+    dev = x_local.device
+    n, d = x_local.shape
+    m = y.shape[0]
+    cm = torch.empty(m, dtype=torch.float32, device=dev)
+    cs = torch.empty(m, dtype=torch.float32, device=dev)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d), dev)
+        st = lib.otk_sinkhorn_points_colstep(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(u_local), int(cost), float(scale),
+                                             float(reg), int(precision), N.ptr(cm), N.ptr(cs), N.ptr(ws), ws.numel(),
+                                             N.stream_ptr(dev))
+    N.check(st, "otk_sinkhorn_points_colstep")
+    return cm, cs
+
+
+def lse_combine(part_max: Tensor, part_sum: Tensor, b: Tensor, v: Tensor, diff: Optional[Tensor]) -> None:
+    dev = v.device
+    parts, m = part_max.shape
+    with torch.cuda.device(dev):
+        st = N.load().otk_lse_combine(N.ptr(part_max), N.ptr(part_sum), parts, m, N.ptr(b), N.ptr(v), N.ptr(diff),
+                                      N.stream_ptr(dev))
+    N.check(st, "otk_lse_combine")
+
+
+def rowstep(x_local: Tensor, y: Tensor, a_local: Tensor, v: Tensor, u_local: Tensor, diff: Optional[Tensor],
+            scale: float, reg: float, cost: int = N.COST_SQEUCLIDEAN, precision: int = 0) -> None:
+    dev = x_local.device
+    n, d = x_local.shape
+    m = y.shape[0]
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d), dev)
+        st = lib.otk_sinkhorn_points_rowstep(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(a_local), N.ptr(v), int(cost),
+                                             float(scale), float(reg), int(precision), N.ptr(u_local), N.ptr(diff),
+                                             N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_sinkhorn_points_rowstep")
+
+
+def gemm_nt(A: Tensor, B: Tensor, alpha: float = 1.0, engine: int = 0) -> Tensor:
+    """C = alpha * A @ B^T (fp32, [*, M, K] x [*, N, K]); exported for the kernel unit tests."""
+    dev = A.device
+    A, B = A.contiguous(), B.contiguous()
+    M, K = A.shape[-2:]
+    Nn = B.shape[-2]
+    batch = int(torch.Size(A.shape[:-2]).numel())
+    out = torch.empty(*A.shape[:-2], M, Nn, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = N.load().otk_gemm_nt(N.ptr(A), N.ptr(B), N.ptr(out), M, Nn, K, K, K, Nn, batch, M * K, Nn * K, M * Nn,
+                                  float(alpha), 0.0, int(engine), N.stream_ptr(dev))
+    N.check(st, "otk_gemm_nt")
+    return out

@@ -1,0 +1,3 @@
+from .base import *  # noqa: F401,F403
+from .gaussian_model import *  # noqa: F401,F403
+from .codebook_model import *  # noqa: F401,F403

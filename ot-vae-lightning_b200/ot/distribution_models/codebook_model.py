@@ -1,0 +1,177 @@
+"""Discrete codebook model: the cost producer of `DiscreteTransport` (mirror of reference
+ot/distribution_models/codebook_model.py:27-214).
+
+On the hot path: `energy` = 1/(|x-c|_2 + 1e-8) via the libotk cost-tile kernel and `w2` through the
+Sinkhorn kernels.  The online k-means bookkeeping (`update`/`fit`/`_update_*`) is control-heavy glue on tiny tensors
+and stays in stock PyTorch, as SURVEY 2.1 row 3 scopes it.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributions as D
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+from ... import _native as N
+from ... import kernels as K
+from ..w2_utils import sinkhorn_log
+from .base import DistributionModel, MixtureMixin
+
+__all__ = ["CategoricalEmbeddings", "CodebookModel"]
+
+
+class CategoricalEmbeddings(D.Categorical):
+    """Categorical over codebook rows (reference codebook_model.py:27-66)."""
+
+    def __init__(self, embeddings: Tensor, probs: Optional[Tensor] = None, logits: Optional[Tensor] = None) -> None:
+        super().__init__(probs, logits)
+        self.embeddings = embeddings
+        if self.probs.shape != self.embeddings.shape[:-1]:
+            raise ValueError("`probs` and `embeddings` should have the same leading dimensions")
+
+    def _select(self, weights: Tensor) -> Tensor:
+        return (weights.unsqueeze(-2).type_as(self.embeddings) @ self.embeddings).squeeze(-2)
+
+    def _select_one_hot(self, index_list: Tensor) -> Tensor:
+        return self._select(F.one_hot(index_list, self._num_events).type_as(index_list))
+
+    def expand(self, batch_shape, _instance=None):
+        new = super().expand(batch_shape, _instance)
+        new.embeddings = new.embeddings.expand(torch.Size(batch_shape) + torch.Size((self._num_events,)))
+        return new
+
+    @property
+    def mean(self):
+        return self._select(self.probs)
+
+    @property
+    def mode(self):
+        return self._select_one_hot(self.probs.argmax(-1))
+
+    def sample(self, sample_shape=torch.Size()) -> Tensor:
+        return self._select_one_hot(super().sample(sample_shape))
+
+
+class CodebookModel(DistributionModel, MixtureMixin):
+    Distribution = CategoricalEmbeddings
+
+    def __init__(self, *size: int, mixture_cfg={}, **kwargs) -> None:
+        MixtureMixin.__init__(self, *size[:-1], **mixture_cfg)
+        DistributionModel.__init__(self, *size, **kwargs)
+        self.register_buffer("weight_init", self._weight_init.to(self.vec_init))
+        self.codebook = nn.Parameter(self.vec_init.clone(), requires_grad=self.update_with_autograd)
+        if not self.update_with_autograd:
+            self.register_buffer("_running_sum", torch.zeros_like(self.vec_init))
+            self.register_buffer("_n_obs", torch.zeros(*self.leading_shape, self.n_components).to(self.vec_init))
+
+    @property
+    def weights(self):
+        if not hasattr(self, "_n_obs") or bool(torch.allclose(self._n_obs, torch.zeros_like(self._n_obs))):
+            return self.weight_init.type_as(self.codebook)
+        return self._n_obs.type_as(self.codebook) / self._n_obs.sum(-1, keepdim=True)
+
+    @property
+    def vec_shape(self):
+        return *self.leading_shape, self.n_components, self.dim
+
+    @torch.no_grad()
+    def reset(self) -> None:
+        self.codebook.copy_(self.vec_init)
+        if not self.update_with_autograd:
+            self._running_sum.zero_()
+            self._n_obs.zero_()
+
+    @property
+    def distribution(self) -> Distribution:
+        return CategoricalEmbeddings(self.codebook, probs=self.weights)
+
+    @property
+    def batched_distribution(self) -> Distribution:
+        return CategoricalEmbeddings(self.codebook.unsqueeze(-3), probs=self.weights.unsqueeze(-2))
+
+    @torch.no_grad()
+    def update(self, samples: Tensor) -> None:
+        self._update_warn()
+        self._validate_samples(samples)
+        samples = samples.detach().to(self._running_sum)
+        self._init_parameters(samples)
+        res = self.kmean_iteration(samples)
+        if self.reduce_on_update:
+            res = [self.reduce(r) for r in res]
+        self._update_parameters(*self._update_buffers(*res, decay=True))
+
+    @torch.no_grad()
+    def fit(self, samples: Optional[Tensor] = None) -> None:
+        self._fit_warn()
+        if samples is not None:
+            self._validate_samples(samples)
+            samples = samples.detach().to(self._running_sum)
+            self._init_parameters(samples)
+        res = None
+        for _ in range(self.kmeans_iter):
+            res = self.kmean_iteration(samples)
+            self._update_parameters(*[self.reduce(r) for r in res])
+        if self.kmeans_iter > 0:
+            self._update_buffers(*res, decay=False)
+
+    def predict(self, features: Tensor) -> Tuple[Tensor, Tensor, D.Categorical]:
+        weights, indices, distribution = self.assign(features)
+        return weights @ self.codebook, indices, distribution
+
+    def energy(self, samples: Tensor) -> Tensor:
+        """[*L, b, d] -> [*L, b, n_comp]: inverse p-distance (euclidean) or |cosine| similarity
+        (reference codebook_model.py:155-168)."""
+        self._validate_samples(samples)
+        samples = samples.to(self.codebook)
+        if self.metric == "euclidean":
+            if self.p == 2 and samples.is_cuda and samples.dim() == self.codebook.dim():
+                lead = torch.broadcast_shapes(samples.shape[:-2], self.codebook.shape[:-2])
+                xs = samples.expand(*lead, *samples.shape[-2:]).reshape(-1, *samples.shape[-2:])
+                cs = self.codebook.expand(*lead, *self.codebook.shape[-2:]).reshape(-1, *self.codebook.shape[-2:])
+                tiles = [K.cost_matrix(xs[i], cs[i], N.COST_INV_EUCLIDEAN) for i in range(xs.shape[0])]
+                return torch.stack(tiles).reshape(*lead, samples.shape[-2], self.codebook.shape[-2]).to(samples.dtype)
+            return 1 / (torch.cdist(samples, self.codebook, self.p) + 1e-8)
+        if self.metric == "cosine":
+            norm_x = samples.abs().pow(self.p).sum(-1, keepdim=True)
+            norm_c = self.codebook.abs().pow(self.p).sum(-1).unsqueeze(-2)
+            dot = (samples @ self.codebook.transpose(-2, -1)).abs()
+            return dot / (norm_x * norm_c + 1e-8) ** (1 / self.p)
+        raise NotImplementedError(f"Supported `metric`: 'cosine', 'euclidean'. Got `metric`={self.metric}")
+
+    def kmean_iteration(self, samples: Optional[Tensor]) -> Tuple[Tensor, ...]:
+        if samples is None:
+            return self._n_obs, self._running_sum
+        return super().kmean_iteration(samples)
+
+    def w2(self, other: Distribution) -> Tensor:
+        cost = 1 / (self.energy(other.embeddings) + 1e-8)
+        plan = sinkhorn_log(self.distribution.probs, other.probs, cost, reg=1e-5, max_iter=100, threshold=1e-3)
+        return (cost * plan).sum(dim=(-2, -1))
+
+    def extra_repr(self) -> str:
+        return DistributionModel.extra_repr(self) + ", " + MixtureMixin.extra_repr(self)
+
+    def _update_parameters(self, *kmeans_iter_res: Tensor) -> None:
+        weights_sum, samples_sum = kmeans_iter_res
+        hit = weights_sum > 1e-8
+        self.codebook.data[hit] = samples_sum[hit] / self.laplace_smoothing(weights_sum[hit]).unsqueeze(-1)
+
+    def _update_buffers(self, *kmeans_iter_res: Tensor, decay: bool = False):
+        weights_sum, samples_sum = kmeans_iter_res
+        hit = weights_sum > 1e-8
+        if decay:
+            self._n_obs[hit] = self.ema_update(self._n_obs[hit], weights_sum[hit])
+            self._running_sum[hit] = self.ema_update(self._running_sum[hit], samples_sum[hit])
+        else:
+            self._n_obs[hit] = weights_sum[hit]
+            self._running_sum[hit] = samples_sum[hit]
+        return self._n_obs, self._running_sum
+
+    def _init_parameters(self, samples: Tensor) -> None:
+        if bool(torch.allclose(self.codebook, self.vec_init)):
+            pick = torch.randperm(samples.size(-2), device=samples.device)[:self.n_components]
+            self.codebook.copy_(samples[..., pick, :])
+            self._n_obs += 1

@@ -1,0 +1,72 @@
+"""Multi-GPU drivers for the two parts of the path that shard: one process per GPU,
+`torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests) for the plumbing.
+
+* sufficient statistics: every rank streams its own latents (`reduce_on_update=False`), `GaussianModel.fit()` does
+  ONE packed all-reduce of [n | sum x | sum x x^T]  (see GaussianModel._packed_reduce);
+* Sinkhorn: source rows are sharded, y / b / v are replicated; per iteration one all-gather of the
+  column (max, sum-exp) partials [2, M] - the only data-path collective - and one scalar all-reduce for the stop rule.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import kernels as K
+
+
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def shard_rows(n: int, rank: int, world: int):
+    """Contiguous row range of `rank` (first ranks take the remainder)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def global_cost_scale(x_local: Tensor, y: Tensor, cost: int = 0, group=None) -> float:
+    """1 / max_ij cost over ALL ranks' rows (the normalisation of reference w2_utils.py:265-266)."""
+    mx = K.cost_max(x_local, y, cost)
+    if _world(group) > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return 1.0 / float(mx.item())
+
+
+def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg: float, max_iter: int,
+                     threshold: float = 0.0, scale: Optional[float] = None, cost: int = 0, precision: int = 0,
+                     poll_every: int = 16, group=None, kernels=K):
+    """Row-sharded log-domain Sinkhorn (same recurrences / stop rule as reference w2_utils.py:301-319).
+    x_local [n_g, d], a_local [n_g] are this rank's rows; y [M, d], b [M] are replicated.
+    Returns dict(u_local, v, iters, scale).  `kernels` is injectable for the CPU (gloo) tests."""
+    world = _world(group)
+    dev = x_local.device
+    if scale is None:
+        scale = global_cost_scale(x_local, y, cost, group) if kernels is K else kernels.global_cost_scale(x_local, y)
+    m = y.shape[0]
+    u = torch.zeros(x_local.shape[0], dtype=torch.float32, device=dev)
+    v = torch.zeros(m, dtype=torch.float32, device=dev)
+    diffs = torch.zeros(2, dtype=torch.float32, device=dev)  # [sum|du| local, sum|dv| replicated]
+    gathered = torch.empty(world, 2, m, dtype=torch.float32, device=dev) if world > 1 else None
+    done_iters = 0
+    for it in range(max_iter):
+        cmax, csum = kernels.colstep(x_local, y, u, scale, reg, cost, precision)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), torch.stack([cmax, csum]).view(-1), group=group)
+            pm, ps = gathered[:, 0].contiguous(), gathered[:, 1].contiguous()
+        else:
+            pm, ps = cmax.unsqueeze(0), csum.unsqueeze(0)
+        diffs.zero_()
+        kernels.lse_combine(pm, ps, b, v, diffs[1:2])
+        kernels.rowstep(x_local, y, a_local, v, u, diffs[0:1], scale, reg, cost, precision)
+        done_iters = it + 1
+        if threshold > 0 and ((it + 1) % poll_every == 0 or it + 1 == max_iter):
+            du = diffs[0:1].clone()
+            if world > 1:
+                dist.all_reduce(du, group=group)
+            if float(du.item() + diffs[1].item()) < threshold:
+                break
+    return dict(u_local=u, v=v, iters=done_iters, scale=scale)

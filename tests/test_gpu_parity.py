@@ -1,0 +1,312 @@
+"""Parity of the CUDA path (through the Python mirror -> C ABI -> sm_100a kernels) against
+ (1) the committed golden outputs of the unmodified reference (tests/golden/*.npz),
+ (2) the CPU oracle on seeded synthetic inputs,
+ (3) size-independent properties at larger sizes.
+Tolerances are BASELINE.json's: rel <= 1e-4 mean/cov, <= 1e-3 sqrtm / W2 / transported latents,
+<= 1e-4 Sinkhorn marginals and cost (relative Frobenius unless stated)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATS, TOL_MATFUN, TOL_SINKHORN = 1e-4, 1e-3, 1e-4
+
+
+def T(a, dev="cuda"):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def rel(got, want):
+    got, want = got.detach().double().cpu(), torch.as_tensor(np.asarray(want)).double()
+    return ((got - want).norm() / want.norm().clamp_min(1e-300)).item()
+
+
+@pytest.fixture(scope="module")
+def api():
+    import ot_vae_lightning_b200.ot as ot
+    return ot
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import ot_oracle
+    return ot_oracle
+
+
+# ------------------------------------------------------------------------------------------------- golden fixtures
+
+def test_golden_matrix_primitives(api, golden):
+    g = golden("matrix")
+    A = T(g["A"])
+    assert rel(api.sqrtm(A), g["sqrtm"]) < TOL_MATFUN
+    assert rel(api.invsqrtm(A), g["invsqrtm"]) < TOL_MATFUN
+    assert api.sqrtm(A).dtype == torch.float64 and api.sqrtm(A.float()).dtype == torch.float32
+    assert np.allclose(api.min_eig(A).cpu().numpy(), g["min_eig"], rtol=1e-6, atol=1e-9)
+    assert np.allclose(api.min_eig(T(g["indef"])).cpu().numpy(), g["indef_min_eig"], rtol=1e-6)
+    fixed, shift = api.make_psd(T(g["indef"]), strict=True, return_correction=True)
+    assert rel(fixed, g["repaired"]) < 1e-6 and rel(shift, g["shift"]) < 1e-6
+    mean, cov = api.mean_cov(T(g["sum"]), T(g["sum_cov"]), T(g["n"]))
+    assert rel(mean, g["mean"]) < 1e-12 and rel(cov, g["cov"]) < 1e-12
+    assert api.is_symmetric(T(g["asym"])).cpu().tolist() == g["asym_is_symmetric"].tolist()
+    assert api.is_spd(A).cpu().tolist() == g["A_is_spd"].tolist()
+    assert api.is_pd(T(g["indef"])).cpu().tolist() == g["indef_is_pd"].tolist()
+
+
+def _run_transport(api, g, lead, d, decay=None, pg_star=0.0):
+    cfg = dict(dtype=torch.double)
+    if decay is not None:
+        cfg["update_decay"] = decay
+    op = api.GaussianTransport(*lead, d, transport_cfg=dict(diag=False, stochastic=False, make_pd=True,
+                                                            pg_star=pg_star, dtype=torch.double),
+                               source_cfg=dict(cfg), target_cfg=dict(cfg)).cuda()
+    src, tgt, bs = T(g["src"]), T(g["tgt"]), int(g["batch"])
+    for lo in range(0, src.shape[-2], bs):
+        op.update(source_samples=src[..., lo:lo + bs, :])
+    for lo in range(0, tgt.shape[-2], bs):
+        op.update(target_samples=tgt[..., lo:lo + bs, :])
+    w2 = op.compute()
+    moved = op.transport(src)
+    sm, tm = op.source_model, op.target_model
+    assert rel(sm._n_obs, g["n_s"]) < 1e-12
+    assert rel(sm._running_sum, g["sum_s"]) < TOL_STATS and rel(sm._running_sum_cov, g["sumcov_s"]) < TOL_STATS
+    assert rel(sm.mean, g["mean_s"]) < TOL_STATS and rel(tm.mean, g["mean_t"]) < TOL_STATS
+    assert rel(sm.cov, g["cov_s"]) < TOL_STATS and rel(tm.cov, g["cov_t"]) < TOL_STATS
+    assert rel(w2, g["w2"]) < TOL_MATFUN
+    assert rel(op.transport_operator, g["T"]) < TOL_MATFUN
+    assert moved.dtype == src.dtype and moved.device == src.device and rel(moved, g["moved"]) < TOL_MATFUN
+    assert float(op.cov_stochastic_noise.abs().max()) == 0.0
+    return op
+
+
+def test_golden_gaussian_transport_d16_ragged_batches(api, golden):
+    op = _run_transport(api, golden("gaussian_d16"), (), 16)
+    assert sorted(op.source_model.state_dict().keys()) == sorted(
+        ["mean", "vec_init", "mat_init", "cov_init", "_running_sum", "_running_sum_cov", "_n_obs",
+         "parametrizations.cov.original"])
+    assert all(v.dtype == torch.float64 for v in op.source_model.state_dict().values())
+
+
+def test_golden_gaussian_transport_leading_dims_pgstar(api, golden):
+    g = golden("gaussian_lead2_d8")
+    _run_transport(api, g, (2,), 8, pg_star=float(g["pg_star"]))
+
+
+def test_golden_gaussian_transport_ema(api, golden):
+    g = golden("gaussian_ema_d8")
+    _run_transport(api, g, (), 8, decay=float(g["decay"]))
+
+
+def test_golden_w2_functions(api, golden):
+    for name in ("w2_d3", "w2_d24"):
+        g = golden(name)
+        m1, m2, c1, c2 = (T(g[k]) for k in ("m1", "m2", "c1", "c2"))
+        w2 = api.w2_gaussian(m1, m2, c1, c2)
+        assert w2.dtype == torch.float64 and w2.shape == torch.Size(g["w2"].shape)
+        assert rel(w2, g["w2"]) < TOL_MATFUN
+        Top, Cw = api.compute_transport_operators(c1, c2, stochastic=False, diag=False, make_pd=True)
+        assert rel(Top, g["T"]) < TOL_MATFUN and float(Cw.abs().max()) == 0.0
+        if "x" in g:
+            y = api.apply_transport(T(g["x"]), m1.unsqueeze(-2), m2.unsqueeze(-2), Top.unsqueeze(-3), Cw.unsqueeze(-3))
+            assert y.dtype == torch.float64 and rel(y, g["y"]) < TOL_MATFUN
+
+
+def test_golden_sinkhorn(api, golden):
+    g = golden("sinkhorn_points")
+    a, b, C = T(g["a"]), T(g["b"]), T(g["C"])
+    for key, kw in (("plan_fixed25", dict(max_iter=25, threshold=0.0)), ("plan_thr1e6", dict(max_iter=1000, threshold=1e-6))):
+        plan = api.sinkhorn_log(a, b, C, reg=float(g["reg"]), **kw)            # fp64 in -> fp64 solve
+        assert plan.dtype == torch.float64 and rel(plan, g[key]) < 1e-9
+        plan32 = api.sinkhorn_log(a.float(), b.float(), C.float(), reg=float(g["reg"]), **kw)
+        want = torch.from_numpy(g[key])
+        assert rel(plan32.sum(-1), want.sum(-1)) < TOL_SINKHORN and rel(plan32.sum(-2), want.sum(-2)) < TOL_SINKHORN
+        assert rel((plan32.double().cpu() * C.cpu()).sum((-1, -2)), (want * C.cpu()).sum((-1, -2))) < TOL_SINKHORN
+    g3 = golden("sinkhorn_3x3")  # the reference test's own case: reg = 1e-5, allclose(rtol 1e-5, atol 1e-8)
+    plan = api.sinkhorn_log(T(g3["a"]), T(g3["b"]), T(g3["C"]), reg=1e-5, max_iter=1000, threshold=1e-8)
+    assert torch.allclose(plan.cpu(), torch.from_numpy(g3["plan"]), rtol=1e-5, atol=1e-8)
+
+
+def test_golden_energy_cost(golden):
+    from ot_vae_lightning_b200 import kernels as K
+    g = golden("energy")
+    got = K.cost_matrix(T(g["pts"][0]).float(), T(g["codebook"][0]).float(), cost=1)
+    assert rel(got, g["energy"][0]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------- oracle, synthetic
+
+@pytest.mark.parametrize("d,n,bs", [(64, 10000, 100), (128, 10000, 250), (256, 20000, 1000), (512, 65536, 8192)])
+def test_streaming_stats_vs_oracle(api, oracle, d, n, bs):
+    """the reference's test_empirical_cov protocol (tests/test_empirical_cov.py:47-72): batched accumulation then
+    mean_cov must equal the one-shot mean / biased covariance."""
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    x = gaussian_latents(n, d, seed=10 + d, device="cuda")
+    gm = api.GaussianModel(d, w2_cfg=dict(make_pd=True), dtype=torch.double).cuda()
+    for lo in range(0, n, bs):
+        gm.update(x[lo:lo + bs])
+    gm.fit()
+    x64 = x.double().cpu()
+    mean = x64.mean(0)
+    cov = (x64 - mean).T @ (x64 - mean) / n
+    assert rel(gm.mean, mean) < TOL_STATS and rel(gm.cov, cov) < TOL_STATS
+    st = oracle.GaussianStats(d)
+    st.update(x64)
+    assert rel(gm._running_sum_cov, st.sum_cov) < 1e-5 and rel(gm._running_sum, st.sum) < 1e-5
+
+
+@pytest.mark.parametrize("d,kappa", [(64, 1e2), (128, 1e2), (128, 1e4), (512, 1e2), (1024, 1e2)])
+def test_sqrtm_w2_operator_vs_oracle(api, oracle, d, kappa):
+    from ot_vae_lightning_b200.synthetic import gaussian_spec
+    _, hs = gaussian_spec(d, seed=3, kappa=kappa)
+    _, ht = gaussian_spec(d, seed=4, kappa=kappa)
+    cs, ct = hs @ hs.T, 1.7 * (ht @ ht.T)
+    ms, mt = torch.randn(d, dtype=torch.double), torch.randn(d, dtype=torch.double)
+    root = api.sqrtm(cs.cuda())
+    assert rel(root, oracle.sqrtm(cs)) < TOL_MATFUN and rel(api.invsqrtm(cs.cuda()), oracle.invsqrtm(cs)) < TOL_MATFUN
+    assert rel(root @ root, cs) < TOL_MATFUN
+    assert rel(api.w2_gaussian(ms.cuda(), mt.cuda(), cs.cuda(), ct.cuda()), oracle.w2_gaussian(ms, mt, cs, ct)) < TOL_MATFUN
+    Top, _ = api.compute_transport_operators(cs.cuda(), ct.cuda(), stochastic=False, diag=False)
+    want, _ = oracle.transport_operator_full(cs, ct)
+    assert rel(Top, want) < TOL_MATFUN
+    # defining property of the Monge map: T Cs T = Ct
+    assert rel(Top @ cs.cuda() @ Top, ct) < 5 * TOL_MATFUN
+
+
+def test_conditional_batch_of_operators(api, oracle):
+    """cfg4 shape: one operator per class (leading shape (10,)), d reduced to keep the oracle fast."""
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    L, d, n = 10, 96, 1024
+    src = torch.stack([gaussian_latents(n, d, seed=20 + k, device="cuda") for k in range(L)])
+    tgt = torch.stack([gaussian_latents(n, d, seed=40 + k, device="cuda", shift=1.0, scale=0.8) for k in range(L)])
+    op = api.GaussianTransport(L, d, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double),
+                               target_cfg=dict(dtype=torch.double)).cuda()
+    for lo in range(0, n, 256):
+        op.update(src[:, lo:lo + 256], tgt[:, lo:lo + 256])
+    w2 = op.compute()
+    moved = op.transport(src)
+    want = oracle.gaussian_transport_pipeline(src.cpu(), tgt.cpu(), 256)
+    assert w2.shape == (L,) and rel(w2, want["w2"]) < TOL_MATFUN
+    assert rel(op.transport_operator, want["T"]) < TOL_MATFUN and rel(moved, want["moved"]) < TOL_MATFUN
+
+
+@pytest.mark.parametrize("n,m,d", [(256, 192, 16), (1024, 1024, 128), (2048, 1536, 128), (1000, 1333, 72)])
+def test_sinkhorn_points_vs_oracle(oracle, n, m, d):
+    from ot_vae_lightning_b200 import kernels as K
+    from ot_vae_lightning_b200.synthetic import point_clouds
+    x, y = point_clouds(n, m, d, seed=5, device="cuda")
+    a = torch.rand(n, device="cuda") + 0.5
+    a /= a.sum()
+    b = torch.full((m,), 1.0 / m, device="cuda")
+    res = K.sinkhorn_points(x, y, a, b, reg=0.05, max_iter=40, threshold=0.0)
+    C = oracle.sqeuclidean_cost(x.double().cpu(), y.double().cpu())
+    scale = 1.0 / C.max()
+    plan, u, v, _ = oracle.sinkhorn_log(a.double().cpu(), b.double().cpu(), C * scale, reg=0.05, max_iter=40,
+                                        threshold=0.0, return_potentials=True)
+    s = res["summary"].cpu()
+    assert abs(s[0].item() - (C * scale * plan).sum().item()) / (C * scale * plan).sum().item() < TOL_SINKHORN
+    assert abs(s[1].item() - plan.sum().item()) < TOL_SINKHORN
+    # marginals: rebuild them from the returned potentials on the oracle's cost
+    got = torch.exp(res["u"].double().cpu()[:, None] + res["v"].double().cpu()[None, :] - C * scale / 0.05)
+    assert rel(got.sum(1), plan.sum(1)) < TOL_SINKHORN and rel(got.sum(0), plan.sum(0)) < TOL_SINKHORN
+    assert res["iters"] == 40
+
+
+def test_sinkhorn_stop_rule_matches_oracle(api, oracle):
+    """the MIN-over-batch stop rule (reference w2_utils.py:314-315): same iteration count as the oracle."""
+    from ot_vae_lightning_b200 import kernels as K
+    g = torch.Generator().manual_seed(9)
+    C = torch.rand(3, 50, 60, generator=g, dtype=torch.double)
+    a = torch.full((3, 50), 1 / 50, dtype=torch.double)
+    b = torch.full((3, 60), 1 / 60, dtype=torch.double)
+    plan, u, v, iters = oracle.sinkhorn_log(a, b, C, reg=0.1, max_iter=500, threshold=1e-5, return_potentials=True)
+    got_plan, gu, gv, got_iters = K.sinkhorn_dense(a.cuda(), b.cuda(), C.cuda(), 0.1, 500, 1e-5, poll_every=7)
+    assert got_iters == iters and iters < 500
+    assert rel(got_plan, plan) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------- properties / edges
+
+def test_stats_linearity_and_empty_batch(api):
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    d, n = 384, 200_000
+    x = gaussian_latents(n, d, seed=77, device="cuda")
+    whole = api.GaussianModel(d, dtype=torch.double).cuda()
+    whole.update(x)
+    parts = api.GaussianModel(d, dtype=torch.double).cuda()
+    parts.update(x[:1]); parts.update(x[1:70_001]); parts.update(x[70_001:70_001]); parts.update(x[70_001:])
+    assert float(parts._n_obs) == n == float(whole._n_obs)
+    assert rel(parts._running_sum_cov, whole._running_sum_cov.cpu()) < 1e-6
+    assert rel(parts._running_sum, whole._running_sum.cpu()) < 1e-6
+    sc = whole._running_sum_cov
+    assert float((sc - sc.T).abs().max()) == 0.0  # exactly symmetric
+
+
+def test_transport_round_trip_at_scale(api):
+    """encode -> decode property at a size the oracle cannot reach: T_{t->s}(T_{s->t}(x)) = x."""
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    d, n = 256, 500_000
+    src = gaussian_latents(n, d, seed=5, device="cuda")
+    tgt = gaussian_latents(n, d, seed=6, device="cuda", shift=-0.3, scale=2.0)
+    fwd = api.GaussianTransport(d, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double),
+                                target_cfg=dict(dtype=torch.double)).cuda()
+    bwd = api.GaussianTransport(d, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double),
+                                target_cfg=dict(dtype=torch.double)).cuda()
+    for lo in range(0, n, 65536):
+        fwd.update(src[lo:lo + 65536], tgt[lo:lo + 65536])
+        bwd.update(tgt[lo:lo + 65536], src[lo:lo + 65536])
+    w_f, w_b = fwd.compute(), bwd.compute()
+    assert abs(float(w_f) - float(w_b)) / float(w_f) < TOL_MATFUN          # W2 is symmetric
+    back = bwd.transport(fwd.transport(src))
+    assert ((back - src).norm() / src.norm()).item() < TOL_MATFUN
+    moved = fwd.transport(src[:200_000]).double()
+    mean = moved.mean(0)
+    cov = (moved - mean).T @ (moved - mean) / moved.shape[0]
+    assert rel(mean, fwd.target_model.mean.cpu()) < 1e-2 and rel(cov, fwd.target_model.cov.cpu()) < 2e-2
+
+
+def test_small_and_odd_dims(api, oracle):
+    """d = 3 is the reference test-suite's own dimension (tests/test_w2_utils.py:24); 130 is not a multiple of 4."""
+    for d in (3, 5, 130):
+        g = torch.Generator().manual_seed(d)
+        r = torch.randn(2, d, d, generator=g, dtype=torch.double)
+        c1 = r @ r.transpose(-1, -2) + 0.1 * torch.eye(d, dtype=torch.double)
+        r = torch.randn(2, d, d, generator=g, dtype=torch.double)
+        c2 = r @ r.transpose(-1, -2) + 0.1 * torch.eye(d, dtype=torch.double)
+        m1, m2 = torch.randn(2, d, generator=g, dtype=torch.double), torch.randn(2, d, generator=g, dtype=torch.double)
+        assert rel(api.w2_gaussian(m1.cuda(), m2.cuda(), c1.cuda(), c2.cuda()), oracle.w2_gaussian(m1, m2, c1, c2)) < TOL_MATFUN
+        x = torch.randn(2, 33, d, generator=g)
+        Top, Cw = api.compute_transport_operators(c1.cuda(), c2.cuda(), stochastic=False, diag=False)
+        y = api.apply_transport(x.cuda(), m1.cuda().unsqueeze(-2), m2.cuda().unsqueeze(-2), Top.unsqueeze(-3), Cw.unsqueeze(-3))
+        want = oracle.apply_transport(x, m1, m2, oracle.transport_operator_full(c1, c2)[0])
+        assert rel(y, want) < TOL_MATFUN
+
+
+def test_w2_self_distance_is_small(api):
+    """reference tests/test_w2_utils.py:35-41 asks |W2(x,x)| <= 1e-8 d in fp64; the fp32-accurate kernels give
+    ~1e-6 relative to tr(C) (documented deviation)."""
+    g = torch.Generator().manual_seed(1)
+    r = torch.randn(2, 3, 8, 8, generator=g)
+    cov = (r @ r.transpose(-1, -2) + 1e-5 * torch.eye(8)).cuda()
+    mean = torch.randn(2, 3, 8, generator=g).cuda()
+    w = api.w2_gaussian(mean, mean, cov, cov)
+    assert w.shape == (2, 3)
+    tr = cov.diagonal(dim1=-1, dim2=-2).sum(-1).double()
+    assert float((w.abs() / tr).max()) < 1e-5
+
+
+def test_validation_errors_match_reference_conditions(api):
+    eye = torch.eye(4, dtype=torch.double, device="cuda")
+    v = torch.zeros(4, dtype=torch.double, device="cuda")
+    with pytest.raises(ValueError):
+        api.w2_gaussian(v, v, eye, [[1.0]])                                  # not a tensor
+    with pytest.raises(ValueError):
+        api.w2_gaussian(v, v, eye, -eye)                                     # not PD, make_pd=False
+    with pytest.raises(ValueError):
+        api.w2_gaussian(v, v, eye, eye + torch.triu(torch.ones_like(eye), 1))  # asymmetric
+    with pytest.raises(ValueError):
+        api.w2_gaussian(v, v[:3], eye, eye)                                  # dims mismatch
+    with pytest.raises(ValueError):
+        api.apply_transport(v, v, v, eye, None)                              # Cw=None is rejected (reference :619)
+    assert float(api.w2_gaussian(v, v, eye, -eye, make_pd=True)) > 0        # repaired instead
+    with pytest.raises((ValueError, AttributeError, TypeError)):
+        api.mean_cov(v, eye, 3)                                              # python int crashes the reference too

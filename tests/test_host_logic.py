@@ -1,0 +1,151 @@
+"""Host-side logic of the Python mirror, run WITHOUT a GPU: the kernel wrappers are swapped for oracle-backed
+stand-ins (tests/fake_kernels.py), so what is tested here is everything above the C ABI - argument validation and its
+error conditions, broadcasting over leading dims, the GaussianModel / GaussianTransport state machine and state_dict,
+layout helpers - against the golden outputs of the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from tests import fake_kernels
+
+
+@pytest.fixture()
+def api():
+    import ot_vae_lightning_b200.ot as ot
+    with fake_kernels.installed():
+        yield ot
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(got, want, rtol=1e-8, atol=1e-10):
+    got, want = got.detach().double(), T(want).double()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert torch.allclose(got, want, rtol=rtol, atol=atol), (got - want).abs().max().item()
+
+
+def _run(api, g, lead, d, decay=None, pg_star=0.0):
+    cfg = dict(dtype=torch.double, device="cpu")
+    if decay is not None:
+        cfg["update_decay"] = decay
+    op = api.GaussianTransport(*lead, d, transport_cfg=dict(make_pd=True, pg_star=pg_star), source_cfg=dict(cfg),
+                               target_cfg=dict(cfg))
+    src, tgt, bs = T(g["src"]), T(g["tgt"]), int(g["batch"])
+    for lo in range(0, src.shape[-2], bs):
+        op.update(source_samples=src[..., lo:lo + bs, :])
+    for lo in range(0, tgt.shape[-2], bs):
+        op.update(target_samples=tgt[..., lo:lo + bs, :])
+    w2 = op.compute()
+    moved = op.transport(src)
+    for name, key in (("_n_obs", "n_s"), ("_running_sum", "sum_s"), ("_running_sum_cov", "sumcov_s"), ("mean", "mean_s"),
+                      ("cov", "cov_s")):
+        close(getattr(op.source_model, name), g[key])
+    close(op.target_model.cov, g["cov_t"]); close(w2, g["w2"]); close(op.transport_operator, g["T"])
+    assert moved.dtype == torch.float32 and torch.allclose(moved, T(g["moved"]), rtol=1e-5, atol=1e-5)
+    return op
+
+
+def test_gaussian_transport_state_machine(api, golden):
+    op = _run(api, golden("gaussian_d16"), (), 16)
+    keys = {"mean", "vec_init", "mat_init", "cov_init", "_running_sum", "_running_sum_cov", "_n_obs",
+            "parametrizations.cov.original"}
+    assert set(op.source_model.state_dict()) == keys
+    op.reset()
+    assert op.transport_operator is None and float(op.source_model._n_obs) == 0
+    close(op.source_model.mean, op.source_model.vec_init.numpy())
+    with pytest.raises(ValueError):
+        op.transport(torch.zeros(4, 15))
+
+
+def test_leading_dims_pgstar_and_ema(api, golden):
+    g = golden("gaussian_lead2_d8")
+    _run(api, g, (2,), 8, pg_star=float(g["pg_star"]))
+    g = golden("gaussian_ema_d8")
+    _run(api, g, (), 8, decay=float(g["decay"]))
+
+
+def test_functional_api_on_golden(api, golden):
+    g = golden("w2_d3")
+    m1, m2, c1, c2 = (T(g[k]) for k in ("m1", "m2", "c1", "c2"))
+    close(api.w2_gaussian(m1, m2, c1, c2), g["w2"])
+    Top, Cw = api.compute_transport_operators(c1, c2, stochastic=False, diag=False, make_pd=True)
+    close(Top, g["T"], rtol=1e-7)
+    y = api.apply_transport(T(g["x"]), m1.unsqueeze(-2), m2.unsqueeze(-2), Top.unsqueeze(-3), Cw.unsqueeze(-3))
+    close(y, g["y"], rtol=1e-5, atol=1e-5)
+    gm = golden("matrix")
+    mean, cov = api.mean_cov(T(gm["sum"]), T(gm["sum_cov"]), T(gm["n"]))
+    close(mean, gm["mean"]); close(cov, gm["cov"])
+    fixed, shift = api.make_psd(T(gm["indef"]), strict=True, return_correction=True)
+    close(fixed, gm["repaired"]); close(shift, gm["shift"])
+    gs = golden("sinkhorn_points")
+    close(api.sinkhorn_log(T(gs["a"]), T(gs["b"]), T(gs["C"]), reg=0.05, max_iter=25, threshold=0.0), gs["plan_fixed25"])
+
+
+def test_validation_error_conditions(api):
+    eye, v = torch.eye(4, dtype=torch.double), torch.zeros(4, dtype=torch.double)
+    for bad in (lambda: api.w2_gaussian(v, v, eye, [[1.0]]),
+                lambda: api.w2_gaussian(v, v, eye, -eye),
+                lambda: api.w2_gaussian(v, v, eye, eye + torch.triu(torch.ones(4, 4, dtype=torch.double), 1)),
+                lambda: api.w2_gaussian(v, v[:3], eye, eye),
+                lambda: api.w2_gaussian(torch.zeros((), dtype=torch.double), v, eye, eye),
+                lambda: api.apply_transport(v, v, v, eye, None),
+                lambda: api.batch_ot_gmm(torch.zeros(3, 4), torch.zeros(2, 4), -torch.ones(3, 4), torch.ones(2, 4), diag=True),
+                lambda: api.batch_ot_gmm(torch.zeros(3, 4), torch.zeros(2, 4), torch.ones(3, 4), torch.ones(2, 4), diag=True,
+                                         weight_source=torch.tensor([0.5, 0.2, 0.2]))):
+        with pytest.raises(ValueError):
+            bad()
+    with pytest.warns(UserWarning):
+        assert float(api.w2_gaussian(v, v, eye, -eye, make_pd=True, verbose=True)) > 0
+
+
+def test_diag_variants_and_gmm(api):
+    g = torch.Generator().manual_seed(0)
+    ms, mt = torch.randn(2, 5, 3, generator=g), torch.randn(2, 4, 3, generator=g)
+    vs, vt = torch.rand(2, 5, 3, generator=g) + 0.1, torch.rand(2, 4, 3, generator=g) + 0.1
+    D = api.batch_w2_dissimilarity_gaussian_diag(ms, mt, vs, vt)
+    want = ((ms[:, :, None] - mt[:, None]) ** 2).sum(-1) + ((vs.sqrt()[:, :, None] - vt.sqrt()[:, None]) ** 2).sum(-1)
+    close(D, want.double().numpy(), rtol=1e-5, atol=1e-6)
+    cost, plan = api.batch_ot_gmm(ms, mt, vs, vt, diag=True, reg=0.05, max_iter=200, threshold=1e-9)
+    assert plan.shape == (2, 5, 4) and torch.allclose(plan.sum(-1), torch.full((2, 5), 0.2, dtype=plan.dtype), atol=1e-6)
+    Tm, Cw = api.compute_transport_operators(vs, vs * 4, stochastic=False, diag=True)
+    close(Tm, torch.full_like(vs, 2.0).double().numpy(), rtol=1e-6)
+    mb, vb = api.gaussian_barycenter(ms, vs, torch.full((2, 5), 0.2), diag=True)
+    assert mb.shape == (2, 3) and vb.shape == (2, 3)
+
+
+def test_layout_helpers_round_trip():
+    from ot_vae_lightning_b200.utils import ema, permute_and_flatten, unflatten_and_unpermute, unsqueeze_like
+    x = torch.randn(10, 1, 2, 3, 4, 5)
+    assert permute_and_flatten(x, (1, 3)).shape == (10, 40, 3)
+    assert permute_and_flatten(x, (1, 3), batch_first=False).shape == (40, 10, 3)
+    assert permute_and_flatten(x, (1, 3), flatten_batch=True).shape == (400, 3)
+    for kw in (dict(), dict(batch_first=False), dict(flatten_batch=True)):
+        assert torch.equal(unflatten_and_unpermute(permute_and_flatten(x, (1, 3), **kw), x.shape, (1, 3), **kw), x)
+    lat = torch.randn(6, 128, 1, 1)  # MNIST32 CNN-VAE latent, transport_dims=(1,2,3) -> [B,128]
+    assert permute_and_flatten(lat, (1, 2, 3)).shape == (6, 128)
+    assert permute_and_flatten(lat, (1, 2, 3), flatten_batch=True).shape == (768,)  # reference quirk (utils:258)
+    assert unsqueeze_like(torch.ones(3), torch.ones(3, 4, 5)).shape == (3, 1, 1)
+    with pytest.raises(ValueError):
+        unsqueeze_like(torch.ones(3, 4), torch.ones(3))
+    assert float(ema(torch.tensor(2.0), torch.tensor(4.0), None)) == 6.0
+    assert float(ema(torch.tensor(2.0), torch.tensor(4.0), 0.5)) == 3.0
+
+
+def test_install_as_reference_aliases():
+    import sys
+    import ot_vae_lightning_b200 as pkg
+    saved = {k: v for k, v in sys.modules.items() if k == "ot_vae_lightning" or k.startswith("ot_vae_lightning.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        pkg.install_as_reference()
+        from ot_vae_lightning.ot.w2_utils import mean_cov, w2_gaussian  # noqa: F401
+        from ot_vae_lightning.ot.transport.gaussian_transport import GaussianTransport
+        import ot_vae_lightning_b200.ot as ot
+        assert GaussianTransport is ot.GaussianTransport
+    finally:
+        for k in [k for k in sys.modules if k == "ot_vae_lightning" or k.startswith("ot_vae_lightning.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
