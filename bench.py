@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the latent optimal-transport hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Primary metric  "cov+W2-map latents/s" on BASELINE.json configs[1]:
+    one step = stream 2^20 source + 2^20 target synthetic 512-d latents (chunks of 65536) through the statistics
+    kernel, compute the Gaussian W2 map (`GaussianTransport.compute`), transport the 2^20 source latents.
+    value = latents transported per second, whole job (all ranks; weak scaling: every rank has its own 2^20).
+Secondary metric (same JSON line, key "sinkhorn"): log-domain Sinkhorn iterations/s at N=M=65536, d=128, eps=0.05
+    (BASELINE.json configs[2]; rows sharded over the ranks, strong scaling).
+`e2e` measures the same step through the public Python API with pinned HOST buffers (H2D of both latent sets and
+D2H of the transported latents inside the timed region).  `--impl reference` times the CPU oracle port of the
+reference (torch fp64, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+D_LAT, N_LAT, CHUNK = 512, 1 << 20, 1 << 16
+SK_N, SK_D, SK_EPS = 65536, 128, 0.05
+METRIC, UNIT = "cov+W2-map latents/s", "latents/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=[])
+        s = sorted(self.samples)
+        return dict(sm_mhz=s[len(s) // 2], sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+
+def cpu_pipeline(sample_rows, threads):
+    """Reference CPU path (oracle port, torch fp64) on `sample_rows` source + target latents of the same workload."""
+    from oracle import ot_oracle as O
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    torch.set_num_threads(threads)
+    src = gaussian_latents(sample_rows, D_LAT, seed=1234)
+    tgt = gaussian_latents(sample_rows, D_LAT, seed=4321, shift=0.5, scale=1.5)
+    t0 = time.perf_counter()
+    out = O.gaussian_transport_pipeline(src, tgt, min(CHUNK, sample_rows))
+    dt = time.perf_counter() - t0
+    assert torch.isfinite(out["moved"]).all()
+    return dt
+
+
+def cpu_sinkhorn(n, iters, threads):
+    from oracle import ot_oracle as O
+    from ot_vae_lightning_b200.synthetic import point_clouds
+    torch.set_num_threads(threads)
+    x, y = point_clouds(n, n, SK_D, seed=1234)
+    C = O.sqeuclidean_cost(x, y)
+    C = C / C.max()
+    a = torch.full((n,), 1.0 / n)
+    t0 = time.perf_counter()
+    O.sinkhorn_log(a, a, C, reg=SK_EPS, max_iter=iters, threshold=0.0)
+    return (time.perf_counter() - t0) / iters
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 1 << 17  # bounded sample: 131072 source + 131072 target latents per step
+    for _ in range(min(args.warmup, 1)):
+        cpu_pipeline(1 << 14, threads)
+    times = [cpu_pipeline(sample, threads) for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    val = sample / t
+    sk_n = 4096
+    sk_t = cpu_sinkhorn(sk_n, 3, threads)
+    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic",
+                config=dict(workload="cfg2: streaming cov + W2 map + transport, 512-d latents",
+                            latents_per_step=sample, dim=D_LAT, note="bounded sample of the 2^20-latent step"),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port",
+                                  sample=f"{sample} source + {sample} target latents, d={D_LAT}, fp64 (oracle port of the "
+                                         f"reference: einsum SYRK, eigh sqrtm, fp64 mat-vecs)"),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                sinkhorn=dict(metric="Sinkhorn iters/s", value=1.0 / (sk_t * (SK_N / sk_n) ** 2), unit="iters/s",
+                              measured_at=f"N=M={sk_n} fp32 ({1.0 / sk_t:.3f} it/s), extrapolated to 65536^2 by N*M",
+                              cores=threads))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--sinkhorn-iters", type=int, default=20)
+    ap.add_argument("--skip-sinkhorn", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ot_vae_lightning_b200 import _native as NV
+    from ot_vae_lightning_b200 import kernels as K
+    from ot_vae_lightning_b200 import parallel
+    from ot_vae_lightning_b200.ot import GaussianTransport
+    from ot_vae_lightning_b200.synthetic import gaussian_latents, point_clouds
+    lib = NV.load()
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- workload: every rank owns its own 2^20 source / target latents (weak scaling)
+    src = gaussian_latents(N_LAT, D_LAT, seed=1234 + rank, device=dev)
+    tgt = gaussian_latents(N_LAT, D_LAT, seed=4321 + rank, device=dev, shift=0.5, scale=1.5)
+    out = torch.empty_like(src)
+    cfg = dict(dtype=torch.double, device=dev, reduce_on_update=False)
+    op = GaussianTransport(D_LAT, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).to(dev)
+
+    def step_device():
+        op.reset()
+        for lo in range(0, N_LAT, CHUNK):
+            op.update(source_samples=src[lo:lo + CHUNK], target_samples=tgt[lo:lo + CHUNK])
+        w2 = op.compute()              # one packed all-reduce of the statistics inside fit() when world > 1
+        for lo in range(0, N_LAT, CHUNK):
+            out[lo:lo + CHUNK] = op.transport(src[lo:lo + CHUNK])
+        return w2
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), res
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.otk_launch_count()
+    total_ms, w2 = timed(step_device, args.steps)
+    launches = lib.otk_launch_count() - launches0
+    ms_per_step = total_ms / args.steps
+    value = world * N_LAT / (ms_per_step * 1e-3)
+
+    # ---- per-kernel roofline: the statistics kernel over one rank's 2^20 x 512 latents
+    def stats_only():
+        op.source_model.reset()
+        for lo in range(0, N_LAT, CHUNK):
+            op.source_model.update(src[lo:lo + CHUNK])
+
+    def apply_only():
+        for lo in range(0, N_LAT, CHUNK):
+            out[lo:lo + CHUNK] = op.transport(src[lo:lo + CHUNK])
+
+    stats_only()
+    stats_ms, _ = timed(stats_only, 3)
+    apply_ms, _ = timed(apply_only, 3)
+    compute_ms, _ = timed(lambda: op.compute(), 3)
+    clocks = sampler.result()
+    flops = 2.0 * N_LAT * D_LAT * D_LAT
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    stats_tflops = flops / (stats_ms / 3 * 1e-3) / 1e12
+    apply_tflops = flops / (apply_ms / 3 * 1e-3) / 1e12
+    roofline = dict(kernel="stats_update (K1: sum x x^T, sum x, n) over 2^20 x 512 fp32 latents",
+                    bound="tensor", achieved=stats_tflops, peak=tf32_peak, unit="TFLOP/s", frac=stats_tflops / tf32_peak,
+                    traffic=None,
+                    note=f"algorithmic flops 2*N*d^2; peak = TF32 dense = 1/2 of bf16_tflops_sustained ({peaks['source']})",
+                    others=dict(apply_transport_tflops=apply_tflops, apply_frac=apply_tflops / tf32_peak,
+                                compute_map_ms=compute_ms / 3, stats_ms=stats_ms / 3, apply_ms=apply_ms / 3,
+                                stats_gbs=N_LAT * D_LAT * 4 / (stats_ms / 3 * 1e-3) / 1e9,
+                                apply_gbs=2 * N_LAT * D_LAT * 4 / (apply_ms / 3 * 1e-3) / 1e9, hbm_peak_gbs=peaks["hbm"]))
+
+    # ---- e2e: same step through the public API with pinned HOST buffers
+    e2e = None
+    if not args.skip_e2e:
+        h_src, h_tgt = src.cpu().pin_memory(), tgt.cpu().pin_memory()
+        h_out = torch.empty_like(h_src).pin_memory()
+
+        def step_host():
+            op.reset()
+            for lo in range(0, N_LAT, CHUNK):
+                op.update(source_samples=h_src[lo:lo + CHUNK], target_samples=h_tgt[lo:lo + CHUNK])
+            op.compute()
+            for lo in range(0, N_LAT, CHUNK):
+                h_out[lo:lo + CHUNK].copy_(op.transport(h_src[lo:lo + CHUNK].to(dev, non_blocking=True)), non_blocking=True)
+            torch.cuda.synchronize()
+            return float(h_out[0, 0])
+
+        step_host()
+        e2e_ms, _ = timed(step_host, max(1, min(args.steps, 3)))
+        e2e_ms /= max(1, min(args.steps, 3))
+        e2e = dict(value=world * N_LAT / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=3 * N_LAT * D_LAT * 4,
+                   d2h_bytes_per_step=N_LAT * D_LAT * 4, ms_per_step=e2e_ms,
+                   note="pinned host latents -> update(src,tgt) -> compute -> transport(src) -> pinned host result")
+        del h_src, h_tgt, h_out
+
+    # ---- Sinkhorn secondary metric: N=M=65536, d=128, eps=0.05, rows sharded over the ranks
+    sinkhorn = None
+    if not args.skip_sinkhorn:
+        try:
+            del src, tgt, out
+            torch.cuda.empty_cache()
+            x, y = point_clouds(SK_N, SK_N, SK_D, seed=99, device=dev)
+            lo, hi = parallel.shard_rows(SK_N, rank, world)
+            a = torch.full((SK_N,), 1.0 / SK_N, device=dev)
+            iters = args.sinkhorn_iters
+            if world == 1:
+                scale = 1.0 / float(K.cost_max(x, y, 0).item())
+                run = lambda: K.sinkhorn_points(x, y, a, a, reg=SK_EPS, max_iter=iters, threshold=0.0, scale=scale,
+                                                want_summary=False, want_iters=False)
+            else:
+                scale = parallel.global_cost_scale(x[lo:hi], y)
+                xl, al = x[lo:hi].contiguous(), a[lo:hi].contiguous()
+                run = lambda: parallel.sharded_sinkhorn(xl, y, al, a, reg=SK_EPS, max_iter=iters, threshold=0.0, scale=scale)
+            run()
+            l0 = lib.otk_launch_count()
+            sk_ms, _ = timed(run, 1)
+            sk_launches = lib.otk_launch_count() - l0
+            it_s = iters / (sk_ms * 1e-3)
+            alg_gb = 2.0 * SK_N * SK_N * 4 / 1e9
+            res = K.sinkhorn_points(x, y, a, a, reg=SK_EPS, max_iter=iters, threshold=0.0, scale=scale) if world == 1 else None
+            sinkhorn = dict(metric="Sinkhorn iters/s", value=it_s, unit="iters/s", ms_per_iter=sk_ms / iters, n_gpus=world,
+                            scaling="strong", config=dict(N=SK_N, M=SK_N, d=SK_D, eps=SK_EPS, iters=iters, threshold=0.0,
+                                                          cost="sqeuclidean / max", scale=scale),
+                            gpu_launches=int(sk_launches),
+                            roofline=dict(bound="hbm", achieved=alg_gb * it_s, peak=peaks["hbm"], unit="GB/s",
+                                          frac=alg_gb * it_s / peaks["hbm"], traffic=None,
+                                          note="algorithmic bytes 2*N*M*4 per iteration (one fp32 cost read per half-step)"))
+            if res is not None:
+                s = res["summary"].cpu().tolist()
+                sinkhorn["check"] = dict(cost=s[0], mass=s[1], max_row_err=s[2], max_col_err=s[3])
+        except Exception as e:  # keep the primary line even if the secondary workload fails
+            sinkhorn = dict(error=f"{type(e).__name__}: {e}")
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        sample = 1 << 17
+        cpu_pipeline(1 << 13, threads)
+        t = cpu_pipeline(sample, threads)
+        cpu = dict(value=sample / t, unit=UNIT, cores=threads, kind="port",
+                   sample=f"{sample} source + {sample} target latents, d={D_LAT}, fp64, one pass ({t:.1f} s)")
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload="cfg2: streaming cov (2^20 source + 2^20 target 512-d latents, chunks of 65536) "
+                                         "+ Gaussian W2 map + transport of the 2^20 source latents, per rank",
+                                dim=D_LAT, latents_per_rank=N_LAT, chunk=CHUNK, l2="inputs (2 x 2 GiB) exceed L2",
+                                arithmetic="fp32-accurate (3xTF32 / FFMA) products, fp64 running statistics",
+                                w2=float(w2)),
+                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
+                    sinkhorn=sinkhorn)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,8 @@ const char* otk_status_string(int status);
 const char* otk_last_error(void);
 /* 1 if the current device is sm_100 (B200); entry points return OTK_ERR_UNSUPPORTED_DEVICE otherwise */
 int otk_device_supported(void);
+/* number of libotk kernels launched by this process so far (bench.py reports the delta as gpu_launches) */
+unsigned long long otk_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  streaming sufficient statistics.

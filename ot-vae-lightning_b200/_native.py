@@ -30,6 +30,7 @@ SIGNATURES = {
     "otk_status_string": (C.c_char_p, [_int]),
     "otk_last_error": (C.c_char_p, []),
     "otk_device_supported": (_int, []),
+    "otk_launch_count": (C.c_ulonglong, []),
     "otk_stats_update_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_stats_update": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _dbl, _ptr, _int, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
     "otk_mean_cov": (_int, [_ptr, _ptr, _ptr, _int, _i64, _i64, _ptr, _ptr, _int, _ptr]),

@@ -1,5 +1,6 @@
 // libotk: process-level plumbing of the C ABI (include/otk.h).
 #include "otk_common.cuh"
+#include <atomic>
 
 namespace otk {
 char* last_error_buffer() {
@@ -8,6 +9,7 @@ char* last_error_buffer() {
 }
 static int g_dev_checked[64] = {0};  // 0 unknown, 1 ok, -1 unsupported
 static int g_sms[64] = {0};
+unsigned long long launches();
 int require_device() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -26,6 +28,9 @@ int require_device() {
   }
   return OTK_OK;
 }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -33,6 +38,7 @@ int sm_count() {
 }
 }  // namespace otk
 
+extern "C" unsigned long long otk_launch_count(void) { return otk::launches(); }
 extern "C" int otk_abi_version(void) { return OTK_ABI_VERSION; }
 extern "C" const char* otk_last_error(void) { return otk::last_error_buffer(); }
 extern "C" int otk_device_supported(void) { return otk::require_device() == OTK_OK ? 1 : 0; }

@@ -1,13 +1,26 @@
-// K3-K6: SPD matrix square roots by coupled Newton-Schulz, Gaussian W2^2 and the transport operator; K4 min_eig.
-// Reference: ot/matrix_utils.py:37-76,91-98 ; ot/w2_utils.py:40-80,756-768.
+// K3-K6: SPD matrix square roots by coupled Newton-Schulz, Gaussian W2^2 and the transport operator.
+// Reference: ot/matrix_utils.py:37-76 ; ot/w2_utils.py:40-80,756-768.
 //
-// All d x d products run through gemm_f32 (tcgen05 3xTF32 when eligible).  Every iterate is a polynomial in the
-// (symmetric) input, so row-major operands are used as their own transposes: A*B is issued as the NT product A*B^T.
+// All d x d products run through gemm_any: fp32 work -> tcgen05 3xTF32 (or FFMA for odd shapes), fp64 work -> DFMA.
+// Products are true NN products (see gemm.cuh: substituting B^T for the nearly-symmetric B destabilises the iteration).
+//
+// Precision policy: the fp32-accurate engine is tried first.  Its accuracy is ~1e-7 * cond(A), so when the iteration
+// needs more than NS_F32_MAX_ITERS steps (which happens when lambda_min/||A||_F is below ~1e-4) and the caller's
+// data is fp64 (the reference default), the whole computation is repeated in fp64 on the same device.
 #include "gemm.cuh"
 
 namespace otk {
 
-constexpr int NS_MAX_ITERS = 60;
+constexpr int NS_MAX_ITERS = 96;       // size of the residual log
+constexpr int NS_F32_MAX_ITERS = 32;   // fp32 engine: beyond this the input is too ill-conditioned for fp32
+constexpr int NS_F64_MAX_ITERS = 90;
+// iterations-to-converge grows like log_2.25(||A||_F / lambda_min): used as the conditioning estimate that decides
+// when the fp32 engine's ~1e-7 * cond error would exceed the parity tolerance (measured: T err 3e-5 at cond 1e2,
+// 3e-3 at cond 1e4)
+constexpr int NS_F32_OPERATOR_ITERS = 20;
+constexpr double NS_F32_RICCATI_TOL = 2e-4;   // ||T Cs T - Ct||_F / ||Ct||_F accepted from the fp32 engine
+constexpr int64_t NS_SMALL_DIM = 64;          // fp64 data with dim <= 64: the DFMA engine is as fast and exact
+constexpr int NS_F32_IROOT_ITERS = 18;
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
   v = warp_sum(v);
@@ -26,7 +39,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 // c[l] = || A_l + ridge I ||_F
-__global__ void frob_kernel(const void* a, int dt, int64_t dim, double ridge, float* c) {
+__global__ void frob_kernel(const void* a, int dt, int64_t dim, double ridge, double* c) {
   __shared__ double red[32];
   const int64_t l = blockIdx.x;
   double acc = 0;
@@ -36,53 +49,72 @@ __global__ void frob_kernel(const void* a, int dt, int64_t dim, double ridge, fl
     acc += v * v;
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) c[l] = (float)sqrt(acc);
+  if (threadIdx.x == 0) c[l] = sqrt(acc);
 }
 
 // Y = (A + ridge I)/c, Z = I
-__global__ void ns_init_kernel(const void* a, int dt, int64_t L, int64_t dim, double ridge, const float* c, float* Y,
-                               float* Z) {
+template <typename W>
+__global__ void ns_init_kernel(const void* a, int dt, int64_t L, int64_t dim, double ridge, const double* c, W* Y, W* Z) {
   const int64_t total = L * dim * dim;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t l = e / (dim * dim), r = e % (dim * dim);
     bool diag = (r / dim == r % dim);
     double v = load_real(a, e, dt) + (diag ? ridge : 0.0);
-    Y[e] = (float)(v / (double)c[l]);
-    Z[e] = diag ? 1.f : 0.f;
+    Y[e] = (W)(v / c[l]);
+    Z[e] = diag ? W(1) : W(0);
   }
 }
 
-// out = scale(l) * (in + in^T)/2 [+ diag], scale = s0 * c[l]^pw ; optionally cast to dt
-__global__ void sym_scale_kernel(const float* in, int64_t L, int64_t dim, const float* c, double pw, double s0,
-                                 double diag_add, void* out, int out_dt) {
+// out = s0 * c[l]^pw * (in + in^T)/2 + s1 * c[l]^pw1 * (in2 + in2^T)/2 + diag_add * I   (in2 optional), cast to out_dt
+template <typename W>
+__global__ void sym_scale_kernel(const W* in, const W* in2, int64_t L, int64_t dim, const double* c, double pw, double s0,
+                                 double pw1, double s1, double diag_add, void* out, int out_dt) {
   const int64_t total = L * dim * dim;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
-    double sc = s0 * (c ? pow((double)c[l], pw) : 1.0);
-    double v = 0.5 * ((double)in[e] + (double)in[l * dim * dim + j * dim + i]) * sc;
+    int64_t et = l * dim * dim + j * dim + i;
+    double v = 0.5 * ((double)in[e] + (double)in[et]) * s0 * (c ? pow(c[l], pw) : 1.0);
+    if (in2) v += 0.5 * ((double)in2[e] + (double)in2[et]) * s1 * (c ? pow(c[l], pw1) : 1.0);
     if (i == j) v += diag_add;
     store_real(out, e, out_dt, v);
   }
 }
 
-__global__ void cast_f32_kernel(const void* a, int dt, int64_t n, float* out) {
+template <typename W>
+__global__ void cast_kernel(const void* a, int dt, int64_t n, W* out) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
-    out[e] = (float)load_real(a, e, dt);
+    out[e] = (W)load_real(a, e, dt);
 }
 
 // w2[l] = |ms - mt|^2 + tr(Cs) + tr(Ct) - 2 * sqrt(c[l]) * tr(Y_l)      (one block per l)
+template <typename W>
 __global__ void w2_trace_kernel(const void* ms, const void* mt, const void* cs, const void* ct, int dt, int64_t dim,
-                                const float* Y, const float* c, double* w2) {
+                                const W* Y, const double* c, double* w2) {
   __shared__ double red[32];
   const int64_t l = blockIdx.x;
   double acc = 0;
   for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
     double dm = load_real(ms, l * dim + i, dt) - load_real(mt, l * dim + i, dt);
     int64_t dgl = l * dim * dim + i * dim + i;
-    acc += dm * dm + load_real(cs, dgl, dt) + load_real(ct, dgl, dt) - 2.0 * sqrt((double)c[l]) * (double)Y[dgl];
+    acc += dm * dm + load_real(cs, dgl, dt) + load_real(ct, dgl, dt) - 2.0 * sqrt(c[l]) * (double)Y[dgl];
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) w2[l] = acc;
+}
+
+// rel[l] = || R_l - target_l ||_F / || target_l ||_F    (one block per l)
+__global__ void rel_residual_kernel(const float* R, const float* target, int64_t dim, double* rel) {
+  __shared__ double red[32];
+  const int64_t l = blockIdx.x;
+  double num = 0, den = 0;
+  for (int64_t e = threadIdx.x; e < dim * dim; e += blockDim.x) {
+    double t = target[l * dim * dim + e], df = (double)R[l * dim * dim + e] - t;
+    num += df * df;
+    den += t * t;
+  }
+  num = block_sum(num, red);
+  den = block_sum(den, red);
+  if (threadIdx.x == 0) rel[l] = sqrt(num / fmax(den, 1e-300));
 }
 
 static inline unsigned ew_grid(int64_t total) {
@@ -90,167 +122,253 @@ static inline unsigned ew_grid(int64_t total) {
   return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+template <typename W>
 struct NsWork {
-  float *Y[2], *Z[2], *T, *c;
-  double* resid;  // [NS_MAX_ITERS][L]
+  W *Y[2], *Z[2], *T;
+  double *c, *resid;  // c [L]; resid [NS_MAX_ITERS][L]
   static size_t bytes(int64_t L, int64_t d) {
-    return 5 * align_up((size_t)L * d * d * 4, 256) + align_up((size_t)L * 4, 256) +
+    return 5 * align_up((size_t)L * d * d * sizeof(W), 256) + align_up((size_t)L * 8, 256) +
            align_up((size_t)NS_MAX_ITERS * L * 8, 256);
   }
   void carve(Arena& ar, int64_t L, int64_t d) {
-    for (int i = 0; i < 2; ++i) { Y[i] = ar.take<float>((size_t)L * d * d); Z[i] = ar.take<float>((size_t)L * d * d); }
-    T = ar.take<float>((size_t)L * d * d);
-    c = ar.take<float>((size_t)L);
+    for (int i = 0; i < 2; ++i) { Y[i] = ar.take<W>((size_t)L * d * d); Z[i] = ar.take<W>((size_t)L * d * d); }
+    T = ar.take<W>((size_t)L * d * d);
+    c = ar.take<double>((size_t)L);
     resid = ar.take<double>((size_t)NS_MAX_ITERS * L);
   }
 };
 
+enum { NS_CONVERGED = 0, NS_SLOW = 1 };
+
 // Coupled Newton-Schulz on (A + ridge I)/c:  T = (3I - Z Y)/2, Y <- Y T, Z <- T Z.
-// On return w.Y[*cur] ~ sqrt(A/c), w.Z[*cur] ~ (A/c)^-1/2 (unsymmetrised), c in w.c.
-static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, int iters, NsWork& w, int* cur_out,
-                    cudaStream_t st) {
+// On return w.Y[*cur] ~ sqrt(A/c), w.Z[*cur] ~ (A/c)^-1/2 (unsymmetrised), c in w.c; *verdict says whether the
+// residual reached the working-precision floor within the budget.
+template <typename W>
+static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, int iters, NsWork<W>& w, int* cur_out,
+                    int* verdict, int* used, cudaStream_t st) {
   const int64_t dd = d * d;
+  const bool f32 = sizeof(W) == 4;
   frob_kernel<<<(unsigned)L, 256, 0, st>>>(a, dt, d, ridge, w.c);
   OTK_LAUNCH_CHECK();
-  ns_init_kernel<<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, ridge, w.c, w.Y[0], w.Z[0]);
+  ns_init_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, ridge, w.c, w.Y[0], w.Z[0]);
   OTK_LAUNCH_CHECK();
   OTK_CUDA(cudaMemsetAsync(w.resid, 0, (size_t)NS_MAX_ITERS * L * 8, st));
   const bool adaptive = iters <= 0;
-  const int max_iters = adaptive ? (L <= 64 ? NS_MAX_ITERS : 32) : (iters < NS_MAX_ITERS ? iters : NS_MAX_ITERS);
+  const int budget = f32 ? NS_F32_MAX_ITERS : NS_F64_MAX_ITERS;
+  const int max_iters = adaptive ? budget : (iters < NS_MAX_ITERS ? iters : NS_MAX_ITERS);
+  // quadratic convergence: once ||I - ZY||_F^2 < tol_near one more update lands on the floor
+  const double tol_done = f32 ? 1e-9 : 1e-22, tol_near = f32 ? 9e-4 : 1e-8;
   int cur = 0, stop_at = max_iters;
-  double host_res[64];
+  *verdict = adaptive ? NS_SLOW : NS_CONVERGED;
+  double host_res[256];
   for (int k = 0; k < max_iters && k < stop_at; ++k) {
-    GemmArgs<float> g = nt_args(w.Z[cur], w.Y[cur], w.T, d, d, d, d, d, d, dd, dd, dd, -0.5f, 0.f);
-    g.diag_add = 1.5f;
+    GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.T, d, dd, W(-0.5));
+    g.diag_add = W(1.5);
     g.resid = w.resid + (size_t)k * L;
-    OTK_TRY(gemm_f32(g, L, ENGINE_AUTO, st));
-    OTK_TRY(gemm_f32(nt_args(w.Y[cur], w.T, w.Y[cur ^ 1], d, d, d, d, d, d, dd, dd, dd, 1.f, 0.f), L, ENGINE_AUTO, st));
-    OTK_TRY(gemm_f32(nt_args(w.T, w.Z[cur], w.Z[cur ^ 1], d, d, d, d, d, d, dd, dd, dd, 1.f, 0.f), L, ENGINE_AUTO, st));
+    OTK_TRY(gemm_any(g, L, st));
+    OTK_TRY(gemm_any(nn_args_t<W>(w.Y[cur], w.T, w.Y[cur ^ 1], d, dd, W(1)), L, st));
+    OTK_TRY(gemm_any(nn_args_t<W>(w.T, w.Z[cur], w.Z[cur ^ 1], d, dd, W(1)), L, st));
     cur ^= 1;
-    if (adaptive && (k % 2 == 1) && L <= 64) {
-      OTK_CUDA(cudaMemcpyAsync(host_res, w.resid + (size_t)k * L, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
-      OTK_CUDA(cudaStreamSynchronize(st));
+    if (adaptive && (k >= 5 || k + 1 == max_iters)) {
       double worst = 0;
-      for (int64_t l = 0; l < L; ++l) {
-        if (!(host_res[l] == host_res[l])) { set_last_error_msg("sqrtm: Newton-Schulz produced NaN"); return OTK_ERR_NOT_CONVERGED; }
-        if (host_res[l] > worst) worst = host_res[l];
+      for (int64_t l0 = 0; l0 < L; l0 += 256) {
+        int64_t nl = L - l0 < 256 ? L - l0 : 256;
+        OTK_CUDA(cudaMemcpyAsync(host_res, w.resid + (size_t)k * L + l0, (size_t)nl * 8, cudaMemcpyDeviceToHost, st));
+        OTK_CUDA(cudaStreamSynchronize(st));
+        for (int64_t l = 0; l < nl; ++l) {
+          if (!(host_res[l] == host_res[l]) || host_res[l] > 1e30) { worst = 1e300; break; }
+          if (host_res[l] > worst) worst = host_res[l];
+        }
       }
-      // resid holds ||I - Z_k Y_k||_F^2 of the state *before* update k; convergence is quadratic.
-      if (worst < 1e-8) stop_at = k + 1;            // already at the fp32 floor
-      else if (worst < 9e-4) stop_at = k + 2;       // ||.||_F < 0.03 -> one more update reaches the floor
+      if (worst >= 1e300) { *verdict = NS_SLOW; break; }  // diverged (numerically indefinite input)
+      // resid[k] is ||I - Z_k Y_k||_F^2 of the state BEFORE update k
+      if (worst < tol_done) { stop_at = k + 1; *verdict = NS_CONVERGED; }
+      else if (worst < tol_near) { stop_at = k + 2; *verdict = NS_CONVERGED; }
     }
   }
   *cur_out = cur;
+  *used = stop_at < max_iters ? stop_at : max_iters;
+  return OTK_OK;
+}
+
+template <typename W>
+static int sqrtm_impl(const void* a, int64_t L, int64_t dim, int dtype, double ridge, int iters, void* root, void* iroot,
+                      void* workspace, size_t workspace_bytes, int* verdict, int* used, cudaStream_t st) {
+  Arena ar(workspace, workspace_bytes);
+  NsWork<W> w; w.carve(ar, L, dim);
+  int cur = 0;
+  OTK_TRY(ns_solve<W>(a, dtype, L, dim, ridge, iters, w, &cur, verdict, used, st));
+  const W* none = nullptr;
+  if (root) {
+    sym_scale_kernel<W><<<ew_grid(L * dim * dim), 256, 0, st>>>(w.Y[cur], none, L, dim, w.c, 0.5, 1.0, 0, 0, 0.0, root, dtype);
+    OTK_LAUNCH_CHECK();
+  }
+  if (iroot) {
+    sym_scale_kernel<W><<<ew_grid(L * dim * dim), 256, 0, st>>>(w.Z[cur], none, L, dim, w.c, -0.5, 1.0, 0, 0, 0.0, iroot, dtype);
+    OTK_LAUNCH_CHECK();
+  }
+  return OTK_OK;
+}
+
+// Shared by w2_gaussian and transport_operator.  Given covariances P (rooted, + ridge) and Q:
+//   S  = P^1/2  (first-order ridge correction: sqrt(P) = sqrt(P + eI) - e/2 (P + eI)^-1/2), Zp = (P + eI)^-1/2,
+//   leaves sqrt(S Q S)/sqrt(c) in w.Y[*cur2] with c in w.c.
+template <typename W>
+static int rooted_mix(const void* P, const void* Q, int dt, int64_t L, int64_t d, double ridge, int iters, NsWork<W>& w,
+                      W* S, W* Zp, W* Q32, W* G, W* mix, int* cur2, int* verdict, int* used_first, cudaStream_t st) {
+  const int64_t dd = d * d;
+  const W* none = nullptr;
+  int cur = 0, v1 = 0, v2 = 0, used2 = 0;
+  OTK_TRY(ns_solve<W>(P, dt, L, d, ridge, iters, w, &cur, &v1, used_first, st));
+  const int wdt = sizeof(W) == 8 ? OTK_F64 : OTK_F32;
+  sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(w.Y[cur], w.Z[cur], L, d, w.c, 0.5, 1.0, -0.5, -0.5 * ridge, 0.0, S, wdt);
+  OTK_LAUNCH_CHECK();
+  if (Zp) {
+    sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(w.Z[cur], none, L, d, w.c, -0.5, 1.0, 0, 0, 0.0, Zp, wdt);
+    OTK_LAUNCH_CHECK();
+  }
+  cast_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(Q, dt, L * dd, Q32);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(gemm_any(nn_args_t<W>(S, Q32, G, d, dd, W(1)), L, st));     // S Q
+  OTK_TRY(gemm_any(nn_args_t<W>(G, S, Q32, d, dd, W(1)), L, st));     // (S Q) S
+  sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(Q32, none, L, d, nullptr, 0, 1.0, 0, 0, 0.0, mix, wdt);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(ns_solve<W>(mix, wdt, L, d, 0.0, iters, w, cur2, &v2, &used2, st));
+  *verdict = (v1 == NS_CONVERGED && v2 == NS_CONVERGED) ? NS_CONVERGED : NS_SLOW;
+  return OTK_OK;
+}
+
+template <typename W>
+static int w2_impl(const void* mean_s, const void* mean_t, const void* cov_s, const void* cov_t, int64_t L, int64_t dim,
+                   int dtype, int iters, double* w2, void* workspace, size_t workspace_bytes, int* verdict,
+                   cudaStream_t st) {
+  int used_first = 0;
+  Arena ar(workspace, workspace_bytes);
+  NsWork<W> w; w.carve(ar, L, dim);
+  const size_t n = (size_t)L * dim * dim;
+  W *S = ar.take<W>(n), *Q32 = ar.take<W>(n), *G = ar.take<W>(n), *mix = ar.take<W>(n);
+  int cur2 = 0;
+  // the reference roots the TARGET covariance for the distance (w2_utils.py:70-71)
+  OTK_TRY(rooted_mix<W>(cov_t, cov_s, dtype, L, dim, 0.0, iters, w, S, nullptr, Q32, G, mix, &cur2, verdict, &used_first, st));
+  w2_trace_kernel<W><<<(unsigned)L, 256, 0, st>>>(mean_s, mean_t, cov_s, cov_t, dtype, dim, w.Y[cur2], w.c, w2);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+template <typename W>
+static int operator_impl(const void* cov_s, const void* cov_t, int64_t L, int64_t dim, int dtype, double pg_star, int iters,
+                         void* T, const void* mean_s, const void* mean_t, double* w2, void* workspace,
+                         size_t workspace_bytes, int* verdict, int* used_first, cudaStream_t st) {
+  Arena ar(workspace, workspace_bytes);
+  NsWork<W> w; w.carve(ar, L, dim);
+  const size_t n = (size_t)L * dim * dim;
+  const int64_t d = dim, dd = dim * dim;
+  const W* none = nullptr;
+  const int wdt = sizeof(W) == 8 ? OTK_F64 : OTK_F32;
+  W *S = ar.take<W>(n), *Zp = ar.take<W>(n), *Q32 = ar.take<W>(n), *G = ar.take<W>(n), *mix = ar.take<W>(n);
+  int cur2 = 0;
+  // the map roots the SOURCE covariance (w2_utils.py:766-767); the 1e-8 ridge of the inverse root is kept
+  OTK_TRY(rooted_mix<W>(cov_s, cov_t, dtype, L, dim, 1e-8, iters, w, S, Zp, Q32, G, mix, &cur2, verdict, used_first, st));
+  if (w2) {
+    w2_trace_kernel<W><<<(unsigned)L, 256, 0, st>>>(mean_s, mean_t, cov_s, cov_t, dtype, dim, w.Y[cur2], w.c, w2);
+    OTK_LAUNCH_CHECK();
+  }
+  // R = sqrt(mix) = sqrt(c) * sym(Y);  T = (1-p) Zp R Zp + p I
+  sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(w.Y[cur2], none, L, d, w.c, 0.5, 1.0, 0, 0, 0.0, mix, wdt);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(gemm_any(nn_args_t<W>(Zp, mix, G, d, dd, W(1)), L, st));
+  OTK_TRY(gemm_any(nn_args_t<W>(G, Zp, Q32, d, dd, W(1)), L, st));
+  sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(Q32, none, L, d, nullptr, 0, 1.0 - pg_star, 0, 0, pg_star, T, dtype);
+  OTK_LAUNCH_CHECK();
+  if constexpr (sizeof(W) == 4) {
+    // accuracy gate of the fp32 engine: the Monge map must satisfy T Cs T = Ct.  Z R Z cancels by a factor
+    // cond(Cs), so an ill-conditioned source covariance shows up here and sends the computation to fp64.
+    if (*verdict == NS_CONVERGED && L <= 256) {
+      float* T0 = S;  // S, Zp, mix are free now
+      float *Cs32 = Zp, *Ct32 = mix;
+      sym_scale_kernel<float><<<ew_grid(L * dd), 256, 0, st>>>(Q32, none, L, d, nullptr, 0, 1.0, 0, 0, 0.0, T0, OTK_F32);
+      cast_kernel<float><<<ew_grid(L * dd), 256, 0, st>>>(cov_s, dtype, L * dd, Cs32);
+      cast_kernel<float><<<ew_grid(L * dd), 256, 0, st>>>(cov_t, dtype, L * dd, Ct32);
+      count_launch(2);
+      OTK_LAUNCH_CHECK();
+      OTK_TRY(gemm_any(nn_args_t<float>(T0, Cs32, G, d, dd, 1.f), L, st));
+      OTK_TRY(gemm_any(nn_args_t<float>(G, T0, Q32, d, dd, 1.f), L, st));
+      rel_residual_kernel<<<(unsigned)L, 256, 0, st>>>(Q32, Ct32, d, w.resid);
+      OTK_LAUNCH_CHECK();
+      double host_rel[256];
+      OTK_CUDA(cudaMemcpyAsync(host_rel, w.resid, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+      OTK_CUDA(cudaStreamSynchronize(st));
+      for (int64_t l = 0; l < L; ++l)
+        if (!(host_rel[l] < NS_F32_RICCATI_TOL)) *verdict = NS_SLOW;
+    }
+  }
   return OTK_OK;
 }
 
 }  // namespace otk
 using namespace otk;
 
-extern "C" size_t otk_sqrtm_workspace_bytes(int64_t L, int64_t dim) { return NsWork::bytes(L, dim) + 4096; }
+// workspaces are sized for the fp64 escalation
+extern "C" size_t otk_sqrtm_workspace_bytes(int64_t L, int64_t dim) { return NsWork<double>::bytes(L, dim) + 4096; }
+extern "C" size_t otk_w2_gaussian_workspace_bytes(int64_t L, int64_t dim) {
+  return NsWork<double>::bytes(L, dim) + 5 * align_up((size_t)L * dim * dim * 8, 256) + 4096;
+}
+extern "C" size_t otk_transport_operator_workspace_bytes(int64_t L, int64_t dim) {
+  return NsWork<double>::bytes(L, dim) + 6 * align_up((size_t)L * dim * dim * 8, 256) + 4096;
+}
 
+// `polish`: 0 = precision policy above (fp32 engine, fp64 escalation for fp64 data); 1 = force the fp64 engine;
+//           -1 = fp32 engine only.
 extern "C" int otk_sqrtm(const void* a, int64_t L, int64_t dim, int dtype, double ridge, int iters, int polish, void* root,
                          void* iroot, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
-  (void)polish;
   OTK_TRY(require_device());
   OTK_REQUIRE(a && L > 0 && dim > 0 && (root || iroot), "sqrtm: bad arguments");
   if (!workspace || workspace_bytes < otk_sqrtm_workspace_bytes(L, dim)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  Arena ar(workspace, workspace_bytes);
-  NsWork w; w.carve(ar, L, dim);
-  int cur = 0;
-  OTK_TRY(ns_solve(a, dtype, L, dim, ridge, iters, w, &cur, st));
-  if (root) {
-    sym_scale_kernel<<<ew_grid(L * dim * dim), 256, 0, st>>>(w.Y[cur], L, dim, w.c, 0.5, 1.0, 0.0, root, dtype);
-    OTK_LAUNCH_CHECK();
+  int verdict = NS_SLOW, used = 0;
+  if (polish == 0 && dtype == OTK_F64 && dim <= NS_SMALL_DIM && iters <= 0) polish = 1;
+  if (polish <= 0) {
+    OTK_TRY(sqrtm_impl<float>(a, L, dim, dtype, ridge, iters, root, iroot, workspace, workspace_bytes, &verdict, &used, st));
+    // the inverse root loses ~1e-7 * cond: escalate it earlier than the root
+    const bool accurate = verdict == NS_CONVERGED && (!iroot || used <= NS_F32_IROOT_ITERS);
+    if (accurate || polish < 0 || iters > 0) return OTK_OK;
   }
-  if (iroot) {
-    sym_scale_kernel<<<ew_grid(L * dim * dim), 256, 0, st>>>(w.Z[cur], L, dim, w.c, -0.5, 1.0, 0.0, iroot, dtype);
-    OTK_LAUNCH_CHECK();
-  }
-  return OTK_OK;
-}
-
-// shared by w2_gaussian and transport_operator: given covariances P (rooted) and Q, computes
-//   S = P^1/2, Zp = P^-1/2 (fp32, symmetrised, in `S`/`Zp`) and leaves sqrt(S Q S)/sqrt(c2) in w.Y[cur2] with c2 in w.c.
-static int rooted_mix(const void* P, const void* Q, int dt, int64_t L, int64_t d, double ridge, int iters, NsWork& w,
-                      float* S, float* Zp, float* Q32, float* G, float* mix, int* cur2, cudaStream_t st) {
-  const int64_t dd = d * d;
-  int cur = 0;
-  OTK_TRY(ns_solve(P, dt, L, d, ridge, iters, w, &cur, st));
-  sym_scale_kernel<<<ew_grid(L * dd), 256, 0, st>>>(w.Y[cur], L, d, w.c, 0.5, 1.0, 0.0, S, OTK_F32);
-  OTK_LAUNCH_CHECK();
-  if (Zp) {
-    sym_scale_kernel<<<ew_grid(L * dd), 256, 0, st>>>(w.Z[cur], L, d, w.c, -0.5, 1.0, 0.0, Zp, OTK_F32);
-    OTK_LAUNCH_CHECK();
-  }
-  cast_f32_kernel<<<ew_grid(L * dd), 256, 0, st>>>(Q, dt, L * dd, Q32);
-  OTK_LAUNCH_CHECK();
-  OTK_TRY(gemm_f32(nt_args(S, Q32, G, d, d, d, d, d, d, dd, dd, dd, 1.f, 0.f), L, ENGINE_AUTO, st));     // S Q
-  OTK_TRY(gemm_f32(nt_args(G, S, Q32, d, d, d, d, d, d, dd, dd, dd, 1.f, 0.f), L, ENGINE_AUTO, st));     // (S Q) S
-  sym_scale_kernel<<<ew_grid(L * dd), 256, 0, st>>>(Q32, L, d, nullptr, 0.0, 1.0, 0.0, mix, OTK_F32);
-  OTK_LAUNCH_CHECK();
-  OTK_TRY(ns_solve(mix, OTK_F32, L, d, 0.0, iters, w, cur2, st));
-  return OTK_OK;
-}
-
-extern "C" size_t otk_w2_gaussian_workspace_bytes(int64_t L, int64_t dim) {
-  return NsWork::bytes(L, dim) + 5 * align_up((size_t)L * dim * dim * 4, 256) + 4096;
+  return sqrtm_impl<double>(a, L, dim, dtype, ridge, iters, root, iroot, workspace, workspace_bytes, &verdict, &used, st);
 }
 
 extern "C" int otk_w2_gaussian(const void* mean_s, const void* mean_t, const void* cov_s, const void* cov_t, int64_t L,
                                int64_t dim, int dtype, int iters, int polish, double* w2, void* workspace,
                                size_t workspace_bytes, otk_stream_t stream) {
-  (void)polish;
   OTK_TRY(require_device());
   OTK_REQUIRE(mean_s && mean_t && cov_s && cov_t && w2 && L > 0 && dim > 0, "w2_gaussian: bad arguments");
   if (!workspace || workspace_bytes < otk_w2_gaussian_workspace_bytes(L, dim)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  Arena ar(workspace, workspace_bytes);
-  NsWork w; w.carve(ar, L, dim);
-  const size_t n = (size_t)L * dim * dim;
-  float *S = ar.take<float>(n), *Q32 = ar.take<float>(n), *G = ar.take<float>(n), *mix = ar.take<float>(n);
-  int cur2 = 0;
-  // the reference roots the TARGET covariance for the distance (w2_utils.py:70-71)
-  OTK_TRY(rooted_mix(cov_t, cov_s, dtype, L, dim, 0.0, iters, w, S, nullptr, Q32, G, mix, &cur2, st));
-  w2_trace_kernel<<<(unsigned)L, 256, 0, st>>>(mean_s, mean_t, cov_s, cov_t, dtype, dim, w.Y[cur2], w.c, w2);
-  OTK_LAUNCH_CHECK();
-  return OTK_OK;
-}
-
-extern "C" size_t otk_transport_operator_workspace_bytes(int64_t L, int64_t dim) {
-  return NsWork::bytes(L, dim) + 6 * align_up((size_t)L * dim * dim * 4, 256) + 4096;
+  int verdict = NS_SLOW;
+  if (polish == 0 && dtype == OTK_F64 && dim <= NS_SMALL_DIM && iters <= 0) polish = 1;
+  if (polish <= 0) {
+    OTK_TRY(w2_impl<float>(mean_s, mean_t, cov_s, cov_t, L, dim, dtype, iters, w2, workspace, workspace_bytes, &verdict, st));
+    if (verdict == NS_CONVERGED || polish < 0 || iters > 0) return OTK_OK;
+  }
+  return w2_impl<double>(mean_s, mean_t, cov_s, cov_t, L, dim, dtype, iters, w2, workspace, workspace_bytes, &verdict, st);
 }
 
 extern "C" int otk_transport_operator(const void* cov_s, const void* cov_t, int64_t L, int64_t dim, int dtype,
                                       double pg_star, int iters, int polish, void* T, const void* mean_s,
                                       const void* mean_t, double* w2, void* workspace, size_t workspace_bytes,
                                       otk_stream_t stream) {
-  (void)polish;
   OTK_TRY(require_device());
   OTK_REQUIRE(cov_s && cov_t && T && L > 0 && dim > 0, "transport_operator: bad arguments");
   OTK_REQUIRE(!w2 || (mean_s && mean_t), "transport_operator: w2 requested without means");
   if (!workspace || workspace_bytes < otk_transport_operator_workspace_bytes(L, dim)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  Arena ar(workspace, workspace_bytes);
-  NsWork w; w.carve(ar, L, dim);
-  const size_t n = (size_t)L * dim * dim;
-  const int64_t d = dim, dd = dim * dim;
-  float *S = ar.take<float>(n), *Zp = ar.take<float>(n), *Q32 = ar.take<float>(n), *G = ar.take<float>(n),
-        *mix = ar.take<float>(n);
-  int cur2 = 0;
-  // the map roots the SOURCE covariance (w2_utils.py:766-767); the 1e-8 ridge of the inverse root is kept
-  OTK_TRY(rooted_mix(cov_s, cov_t, dtype, L, dim, 1e-8, iters, w, S, Zp, Q32, G, mix, &cur2, st));
-  if (w2) {
-    w2_trace_kernel<<<(unsigned)L, 256, 0, st>>>(mean_s, mean_t, cov_s, cov_t, dtype, dim, w.Y[cur2], w.c, w2);
-    OTK_LAUNCH_CHECK();
+  int verdict = NS_SLOW, used = 0;
+  if (polish == 0 && dtype == OTK_F64 && dim <= NS_SMALL_DIM && iters <= 0) polish = 1;
+  if (polish <= 0) {
+    OTK_TRY(operator_impl<float>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, mean_s, mean_t, w2, workspace,
+                                 workspace_bytes, &verdict, &used, st));
+    // T = Zp R Zp cancels by a factor cond(Cs): fp32 is only kept while the source root converged quickly
+    if ((verdict == NS_CONVERGED && used <= NS_F32_OPERATOR_ITERS) || polish < 0 || iters > 0) return OTK_OK;
   }
-  // R = sqrt(mix) = sqrt(c) * sym(Y);  T = (1-p) Zp R Zp + p I
-  sym_scale_kernel<<<ew_grid(L * dd), 256, 0, st>>>(w.Y[cur2], L, d, w.c, 0.5, 1.0, 0.0, mix, OTK_F32);
-  OTK_LAUNCH_CHECK();
-  OTK_TRY(gemm_f32(nt_args(Zp, mix, G, d, d, d, d, d, d, dd, dd, dd, 1.f, 0.f), L, ENGINE_AUTO, st));
-  OTK_TRY(gemm_f32(nt_args(G, Zp, Q32, d, d, d, d, d, d, dd, dd, dd, 1.f, 0.f), L, ENGINE_AUTO, st));
-  sym_scale_kernel<<<ew_grid(L * dd), 256, 0, st>>>(Q32, L, d, nullptr, 0.0, 1.0 - pg_star, pg_star, T, dtype);
-  OTK_LAUNCH_CHECK();
-  return OTK_OK;
+  return operator_impl<double>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, mean_s, mean_t, w2, workspace,
+                               workspace_bytes, &verdict, &used, st);
 }

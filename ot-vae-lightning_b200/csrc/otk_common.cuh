@@ -25,8 +25,11 @@ inline void set_last_error_msg(const char* what) { snprintf(last_error_buffer(),
     }                                                   \
   } while (0)
 
+void count_launch(int n);  // process-wide kernel-launch counter (api.cu), read by otk_launch_count()
+
 #define OTK_LAUNCH_CHECK()                              \
   do {                                                  \
+    ::otk::count_launch(1);                             \
     cudaError_t e__ = cudaGetLastError();               \
     if (e__ != cudaSuccess) {                           \
       ::otk::set_last_error("kernel launch", e__);      \

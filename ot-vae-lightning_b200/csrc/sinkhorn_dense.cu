@@ -225,6 +225,7 @@ static int sinkhorn_dense_impl(const T* a, const T* b, const T* C, int64_t L, in
       sk_row_kernel<T, 256><<<g, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
     }
     sk_check_kernel<T><<<(unsigned)L, 256, 0, st>>>(du, dv, L, N, M, threshold, diff, ticket, state);
+    count_launch(3);
     OTK_LAUNCH_CHECK();
     if (threshold > 0 && (it + 1) % poll_every == 0 && it + 1 < max_iter) {
       OTK_CUDA(cudaMemcpyAsync(&host_state, state, sizeof(SkState), cudaMemcpyDeviceToHost, st));
@@ -287,6 +288,7 @@ int dense_col_partial_f32(const float* C, const float* u, int64_t N, int64_t M, 
   dim3 gcol((unsigned)ceil_div(M, SKC_COLS), (unsigned)slabs, 1);
   sk_col_partial_kernel<float><<<gcol, SKC_WARPS * 32, 0, st>>>(C, u, N, M, ceil_div(N, slabs), (float)(-1.0 / reg), pm, ps, state);
   sk_slab_merge_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(pm, ps, slabs, M, col_max, col_sum);
+  count_launch(2);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }
@@ -310,6 +312,7 @@ int dense_row_step_f32(const float* C, const float* v, int64_t N, int64_t M, dou
     sk_row_kernel<float, 256><<<g, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
   }
   if (diff) sk_sum_abs_kernel<<<g1, 256, 0, st>>>(du, N, diff);
+  count_launch(diff ? 3 : 2);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }

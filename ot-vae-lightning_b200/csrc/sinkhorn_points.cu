@@ -132,6 +132,7 @@ static int build_cost(const float* x, const float* y, int64_t N, int64_t M, int6
   row_sqnorm_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, d, ny);
   dim3 grid((unsigned)ceil_div(M, CT), (unsigned)ceil_div(N, CT));
   cost_tile_kernel<0><<<grid, 256, 0, st>>>(x, y, nx, ny, N, M, d, kind, scale_dev, scale_host, C, nullptr);
+  count_launch(2);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }
@@ -175,6 +176,7 @@ extern "C" int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M
   set_kernel<<<1, 1, 0, st>>>(out, 0.f);
   dim3 grid((unsigned)ceil_div(M, CT), (unsigned)ceil_div(N, CT));
   cost_tile_kernel<1><<<grid, 256, 0, st>>>(x, y, nx, ny, N, M, dim, cost_kind, nullptr, 1.f, nullptr, out);
+  count_launch(3);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }
@@ -208,6 +210,7 @@ extern "C" int otk_sinkhorn_points(const float* x, const float* y, int64_t N, in
     dim3 grid((unsigned)ceil_div(M, CT), (unsigned)ceil_div(N, CT));
     cost_tile_kernel<1><<<grid, 256, 0, st>>>(x, y, nx, ny, N, M, dim, cost_kind, nullptr, 1.f, nullptr, sc + 1);
     inv_kernel<<<1, 1, 0, st>>>(sc + 1, sc);
+    count_launch(5);
     scale_dev = sc;
   }
   OTK_TRY(build_cost(x, y, N, M, dim, cost_kind, scale_dev, (float)scale, nx, ny, C, st));
@@ -218,6 +221,7 @@ extern "C" int otk_sinkhorn_points(const float* x, const float* y, int64_t N, in
     OTK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)M * 4, st));
     plan_row_summary_kernel<<<(unsigned)N, 256, 0, st>>>(C, u, v, a, N, M, (float)(-1.0 / reg), summary, colsum);
     plan_col_err_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(colsum, b, M, summary);
+    count_launch(1);
     OTK_LAUNCH_CHECK();
   }
   return OTK_OK;
