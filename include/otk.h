@@ -181,12 +181,21 @@ int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t d
 int otk_cost_matrix(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
                     double scale, float* C, void* workspace, size_t workspace_bytes, otk_stream_t stream);
 
-/* general fp32-accurate GEMM on the tensor cores used by the kernels above, exported for tests:
- * C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C   (A, B, C row-major, leading dims lda/ldb/ldc), batched.
- * engine: 0 = auto, 1 = FFMA (any shape), 2 = tcgen05 3xTF32 (K%4==0, lda/ldb%4==0), 3 = tcgen05 1xTF32 */
+/* fp32-accurate GEMMs on the tensor cores used inside the kernels above, exported for the kernel unit tests:
+ *   otk_gemm_nt: C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C      (B K-major)
+ *   otk_gemm_nn: C[M,N] = alpha * A[M,K] * B[K,N]   + beta * C      (B N-major, the Newton-Schulz case)
+ * row-major, leading dims lda/ldb/ldc, batched with element strides.
+ * engine: 0 = auto, 1 = FFMA (any shape), 2 = tcgen05 3xTF32, 3 = tcgen05 1xTF32 (2/3 fail if the shape is not
+ * eligible: dims >= 64, 16-byte aligned rows).  Workspace (otk_gemm_workspace_bytes) holds the TF32 hi/lo planes. */
+size_t otk_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch);
 int otk_gemm_nt(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                 int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
-                float alpha, float beta, int engine, otk_stream_t stream);
+                float alpha, float beta, int engine, void* workspace, size_t workspace_bytes,
+                otk_stream_t stream);
+int otk_gemm_nn(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                float alpha, float beta, int engine, void* workspace, size_t workspace_bytes,
+                otk_stream_t stream);
 
 #ifdef __cplusplus
 }

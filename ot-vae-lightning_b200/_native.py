@@ -59,8 +59,11 @@ SIGNATURES = {
                                            _ptr, _sz, _ptr]),
     "otk_cost_max": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _ptr, _sz, _ptr]),
     "otk_cost_matrix": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _dbl, _ptr, _ptr, _sz, _ptr]),
+    "otk_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "otk_gemm_nt": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _flt, _flt,
-                           _int, _ptr]),
+                           _int, _ptr, _sz, _ptr]),
+    "otk_gemm_nn": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _flt, _flt,
+                           _int, _ptr, _sz, _ptr]),
 }
 
 _lib: Optional[C.CDLL] = None

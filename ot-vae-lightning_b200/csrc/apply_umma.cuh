@@ -4,5 +4,5 @@
 namespace otk {
 // 1 = handled, 0 = not eligible, <0 = error
 int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const float* ms32, const float* mt32,
-                   const float* T32, float* Tlo_scratch, float* y, cudaStream_t st);
+                   const float* T32, float* Thi_scratch, float* Tlo_scratch, float* y, cudaStream_t st);
 }

@@ -13,12 +13,33 @@ int gemm_f32(const GemmArgs<float>& g, int64_t batch, int engine, cudaStream_t s
 }
 }  // namespace otk
 using namespace otk;
+static int gemm_export(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                       int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC, float alpha, float beta,
+                       int engine, bool nn, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm: bad arguments");
+  OTK_REQUIRE(lda >= K && ldb >= (nn ? N : K) && ldc >= N, "gemm: leading dimension too small");
+  GemmArgs<float> g = nt_args(A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, beta);
+  if (nn) { g.sbn = 1; g.sbk = ldb; }
+  const size_t need = (size_t)2 * batch * (M * K + N * K) * sizeof(float);
+  if (workspace && workspace_bytes >= need) g.scratch = static_cast<float*>(workspace);
+  else if (engine == ENGINE_UMMA_3X) return OTK_ERR_WORKSPACE;
+  return gemm_f32(g, batch, engine, as_stream(stream));
+}
+extern "C" size_t otk_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch) {
+  return (size_t)2 * batch * (M * K + N * K) * sizeof(float) + 256;
+}
 extern "C" int otk_gemm_nt(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                            int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
-                           float alpha, float beta, int engine, otk_stream_t stream) {
-  OTK_TRY(require_device());
-  OTK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_nt: bad arguments");
-  OTK_REQUIRE(lda >= K && ldb >= K && ldc >= N, "gemm_nt: leading dimension too small");
-  return gemm_f32(nt_args(A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, beta), batch, engine,
-                  as_stream(stream));
+                           float alpha, float beta, int engine, void* workspace, size_t workspace_bytes,
+                           otk_stream_t stream) {
+  return gemm_export(A, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, alpha, beta, engine, false,
+                     workspace, workspace_bytes, stream);
+}
+extern "C" int otk_gemm_nn(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                           int64_t ldb, int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                           float alpha, float beta, int engine, void* workspace, size_t workspace_bytes,
+                           otk_stream_t stream) {
+  return gemm_export(A, B, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, alpha, beta, engine, true,
+                     workspace, workspace_bytes, stream);
 }

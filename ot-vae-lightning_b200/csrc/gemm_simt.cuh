@@ -20,6 +20,12 @@ struct GemmArgs {
   const T* bias;  int64_t stride_bias;  // optional [N] per batch
   T diag_add;                           // added to C[m,m] (after alpha/beta)
   double* resid;                        // optional [batch]: += sum_mn (acc[m,n] - delta_mn)^2 of the raw product
+  // --- tcgen05 3xTF32 engine only (ignored by the FFMA/DFMA engine) ---
+  const T* A_lo = nullptr;              // if set, A is the TF32 "hi" plane and A_lo the "lo" plane (same layout)
+  const T* B_lo = nullptr;
+  T* C_hi = nullptr;                    // optional split output planes (layout of C); C itself may then be null
+  T* C_lo = nullptr;
+  T* scratch = nullptr;                 // >= 2*batch*(M*K + N*K) elements: used to split A / B when no lo plane is given
 };
 
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
@@ -31,7 +37,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmArgs<T> g) {
   const int64_t batch = blockIdx.z;
   const T* A = g.A + batch * g.strideA;
   const T* B = g.B + batch * g.strideB;
-  T* C = g.C + batch * g.strideC;
+  T* C = g.C ? g.C + batch * g.strideC : nullptr;
   const T* a_off = g.a_off ? g.a_off + batch * g.stride_aoff : nullptr;
   const T* bias = g.bias ? g.bias + batch * g.stride_bias : nullptr;
   const int64_t m0 = (int64_t)blockIdx.y * SG_BM, n0 = (int64_t)blockIdx.x * SG_BN;
@@ -92,10 +98,10 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmArgs<T> g) {
       int64_t n = n0 + tx * 4 + j;
       if (n >= g.N) continue;
       T r = g.alpha * acc[i][j];
-      if (g.beta != T(0)) r += g.beta * C[m * g.ldc + n];
+      if (g.beta != T(0) && C) r += g.beta * C[m * g.ldc + n];
       if (bias) r += bias[n];
       if (m == n) r += g.diag_add;
-      C[m * g.ldc + n] = r;
+      if (C) C[m * g.ldc + n] = r;
       if (g.resid) { double e = (double)acc[i][j] - (m == n ? 1.0 : 0.0); res += e * e; }
     }
   }

@@ -1,0 +1,263 @@
+// tcgen05 GEMM with fp32-accurate 3xTF32 arithmetic (sm_100a).
+//
+//   C[m,n] = alpha * sum_k A(m,k) B(n,k) + beta*C + bias[n] + diag_add*delta_mn      (optionally also emitted as a
+//   TF32 hi/lo pair so that the next GEMM of a chain - the Newton-Schulz iteration - needs no conversion pass).
+//
+// Operands arrive as two TF32-exact planes (hi = rna_tf32(x), lo = rna_tf32(x - hi)); the product is
+//   hi*hi' + hi*lo' + lo*hi'   accumulated in fp32 in TMEM (the dropped lo*lo' term is ~2^-22 relative).
+// Data path: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma kind::tf32 (one elected thread)
+// -> 128 x 128 fp32 accumulator in TMEM -> tcgen05.ld -> registers -> global.
+// A is K-major ([M,K], K contiguous).  B is either K-major ([N,K]: "NT") or N-major ([K,N] row-major: "NN"); the
+// N-major case uses the MN-major canonical UMMA layout so that a true A*B needs no transpose pass.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..+31).  One 128x128 output tile per CTA; UG_STAGES-deep smem ring over K.
+#include <cuda.h>
+
+#include "gemm.cuh"
+#include "otk_ptx.cuh"
+#include "tensormap.cuh"
+
+namespace otk {
+
+constexpr int UG_BM = 128, UG_BN = 128, UG_BK = 32, UG_STAGES = 3, UG_THREADS = 192;
+constexpr int UG_TILE_BYTES = UG_BM * UG_BK * 4;                   // 16 KiB per operand plane per stage
+constexpr int UG_STAGE_BYTES = 4 * UG_TILE_BYTES;                  // A_hi, A_lo, B_hi, B_lo
+constexpr int UG_SMEM_BYTES = UG_STAGES * UG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct UmmaGemmParams {
+  int M, N, K, passes, b_mn_major;
+  float *C, *C_hi, *C_lo;
+  int64_t ldc, strideC;
+  float alpha, beta, diag_add;
+  const float* bias;
+  int64_t stride_bias;
+  double* resid;
+};
+
+__global__ void __launch_bounds__(UG_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                 const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                 const UmmaGemmParams p) {
+  using namespace ptx;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + UG_STAGES * UG_STAGE_BYTES);
+  uint64_t* empty = full + UG_STAGES;
+  uint64_t* tmem_full = empty + UG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m0 = blockIdx.x * UG_BM, n0 = blockIdx.y * UG_BN, batch = blockIdx.z;
+  const int num_k = (p.K + UG_BK - 1) / UG_BK;
+  const bool three = p.passes == 3;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA_hi); tma_prefetch_desc(&mapB_hi);
+    if (three) { tma_prefetch_desc(&mapA_lo); tma_prefetch_desc(&mapB_lo); }
+    for (int s = 0; s < UG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, UG_BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t stage_tx = (three ? 4u : 2u) * UG_TILE_BYTES;
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % UG_STAGES, it = kt / UG_STAGES;
+        mbar_wait(&empty[s], (it & 1) ^ 1);
+        uint8_t* st = smem + s * UG_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], stage_tx);
+        const int k0 = kt * UG_BK;
+        tma_load_3d(st, &mapA_hi, k0, m0, batch, &full[s]);
+        if (three) tma_load_3d(st + UG_TILE_BYTES, &mapA_lo, k0, m0, batch, &full[s]);
+        if (!p.b_mn_major) {
+          tma_load_3d(st + 2 * UG_TILE_BYTES, &mapB_hi, k0, n0, batch, &full[s]);
+          if (three) tma_load_3d(st + 3 * UG_TILE_BYTES, &mapB_lo, k0, n0, batch, &full[s]);
+        } else {
+          // B is [K, N] row-major: four 32(n) x 32(k) boxes per plane, one per 128-byte MN slab
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            tma_load_3d(st + 2 * UG_TILE_BYTES + sl * 4096, &mapB_hi, n0 + 32 * sl, k0, batch, &full[s]);
+            if (three) tma_load_3d(st + 3 * UG_TILE_BYTES + sl * 4096, &mapB_lo, n0 + 32 * sl, k0, batch, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(UG_BM, UG_BN, 0, p.b_mn_major);
+      const uint32_t b_kstep = p.b_mn_major ? 1024u : 32u;        // bytes per UMMA_K = 8 along K
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % UG_STAGES, it = kt / UG_STAGES;
+        mbar_wait(&full[s], it & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * UG_STAGE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < UG_BK / 8; ++kk) {
+          const uint64_t a_hi = smem_desc_sw128(base + kk * 32, 16, 1024);
+          const uint64_t a_lo = smem_desc_sw128(base + UG_TILE_BYTES + kk * 32, 16, 1024);
+          const uint32_t b_hi_addr = base + 2 * UG_TILE_BYTES + kk * b_kstep, b_lo_addr = b_hi_addr + UG_TILE_BYTES;
+          const uint64_t b_hi = p.b_mn_major ? smem_desc_mn_tf32(b_hi_addr, 4096) : smem_desc_sw128(b_hi_addr, 16, 1024);
+          const uint64_t b_lo = p.b_mn_major ? smem_desc_mn_tf32(b_lo_addr, 4096) : smem_desc_sw128(b_lo_addr, 16, 1024);
+          if (three) {
+            umma_tf32(tmem_base, a_lo, b_hi, idesc, (kt | kk) != 0);   // small terms first
+            umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+            umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, a_hi, b_hi, idesc, (kt | kk) != 0);
+          }
+        }
+        umma_commit(&empty[s]);                    // frees the smem stage when these MMAs have read it
+      }
+      umma_commit(tmem_full);                      // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp % 4;                        // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* C = p.C ? p.C + (int64_t)batch * p.strideC : nullptr;
+    float* Ch = p.C_hi ? p.C_hi + (int64_t)batch * p.strideC : nullptr;
+    float* Cl = p.C_lo ? p.C_lo + (int64_t)batch * p.strideC : nullptr;
+    const float* bias = p.bias ? p.bias + (int64_t)batch * p.stride_bias : nullptr;
+    double res = 0.0;
+    const bool vec_ok = (p.ldc % 4 == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < UG_BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (m < p.M) {
+        const int64_t row = (int64_t)m * p.ldc;
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const int n = n0 + c0 + j4;
+          float r[4], h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int nj = n + j;
+            const float acc = v[j4 + j];
+            if (p.resid && nj < p.N) { double e = (double)acc - (m == nj ? 1.0 : 0.0); res += e * e; }
+            float t = p.alpha * acc;
+            if (p.beta != 0.f && C && nj < p.N) t += p.beta * C[row + nj];
+            if (bias && nj < p.N) t += bias[nj];
+            if (m == nj) t += p.diag_add;
+            r[j] = t;
+            split_tf32(t, h[j], l[j]);
+          }
+          if (vec_ok && n + 3 < p.N) {
+            if (C) *reinterpret_cast<float4*>(C + row + n) = make_float4(r[0], r[1], r[2], r[3]);
+            if (Ch) *reinterpret_cast<float4*>(Ch + row + n) = make_float4(h[0], h[1], h[2], h[3]);
+            if (Cl) *reinterpret_cast<float4*>(Cl + row + n) = make_float4(l[0], l[1], l[2], l[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < p.N) {
+                if (C) C[row + n + j] = r[j];
+                if (Ch) Ch[row + n + j] = h[j];
+                if (Cl) Cl[row + n + j] = l[j];
+              }
+          }
+        }
+      }
+    }
+    if (p.resid) {
+      res = warp_sum(res);
+      if (lane == 0) atomicAdd(&p.resid[batch], res);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, UG_BN); }
+}
+
+// elementwise split of a strided [batch][rows][cols] operand into dense TF32 hi/lo planes [batch][rows][cols]
+__global__ void split_planes_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t bstride,
+                                    int64_t batch, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = batch * rows * cols;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = e / (rows * cols), r = (e / cols) % rows, c = e % cols;
+    float h, l;
+    ptx::split_tf32(x[b * bstride + r * ld + c], h, l);
+    hi[e] = h;
+    lo[e] = l;
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStream_t st) {
+  // ---- eligibility
+  if (g.a_off || g.sak != 1) return 0;                               // A must be K-major, no centring here
+  const bool b_kmajor = (g.sbk == 1), b_nmajor = (g.sbn == 1);
+  if (!b_kmajor && !b_nmajor) return 0;
+  const int b_mn = b_kmajor ? 0 : 1;
+  const int64_t lda = g.sam, ldb = b_kmajor ? g.sbn : g.sbk;
+  if (g.M < 64 || g.N < 64 || g.K < 8) return 0;                     // tiny problems: FFMA engine
+  if (g.M > INT32_MAX || g.N > INT32_MAX || g.K > INT32_MAX || batch > 65535) return 0;
+  if ((lda % 4) || (ldb % 4) || (g.strideA % 4) || (g.strideB % 4)) return 0;   // TMA: 16-byte strides
+  if (!aligned16(g.A) || !aligned16(g.B) || (g.A_lo && !aligned16(g.A_lo)) || (g.B_lo && !aligned16(g.B_lo))) return 0;
+  if (!g.C && !(g.C_hi && g.C_lo)) return 0;
+  const bool need_split_a = passes == 3 && !g.A_lo, need_split_b = passes == 3 && !g.B_lo;
+  if ((need_split_a || need_split_b) && !g.scratch) return 0;
+  if (!tensormap_encoder()) return 0;
+
+  // ---- operand planes
+  const float *A_hi = g.A, *A_lo = g.A_lo, *B_hi = g.B, *B_lo = g.B_lo;
+  int64_t a_ld = lda, a_bs = g.strideA, b_ld = ldb, b_bs = g.strideB;
+  const int64_t b_rows = b_mn ? g.K : g.N, b_cols = b_mn ? g.N : g.K;
+  float* scratch = g.scratch;
+  auto ew_grid = [](int64_t total) { int64_t b = ceil_div(total, 256), cap = (int64_t)sm_count() * 16; return (unsigned)(b < cap ? (b ? b : 1) : cap); };
+  if (need_split_a) {
+    const int64_t n = batch * g.M * g.K;
+    float *h = scratch, *l = scratch + n;
+    scratch += 2 * n;
+    split_planes_kernel<<<ew_grid(n), 256, 0, st>>>(g.A, g.M, g.K, lda, g.strideA, batch, h, l);
+    OTK_LAUNCH_CHECK();
+    A_hi = h; A_lo = l; a_ld = g.K; a_bs = g.M * g.K;
+  }
+  if (need_split_b) {
+    const int64_t n = batch * b_rows * b_cols;
+    float *h = scratch, *l = scratch + n;
+    split_planes_kernel<<<ew_grid(n), 256, 0, st>>>(g.B, b_rows, b_cols, ldb, g.strideB, batch, h, l);
+    OTK_LAUNCH_CHECK();
+    B_hi = h; B_lo = l; b_ld = b_cols; b_bs = b_rows * b_cols;
+  }
+  if ((a_ld % 4) || (b_ld % 4)) return 0;
+
+  // ---- tensor maps: [batch][rows][cols] fp32, 128B swizzle, box 32 cols x {128 | 32} rows
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  const int b_box_rows = b_mn ? 32 : UG_BN;
+  if (!encode_map_f32_3d(&mA_hi, A_hi, g.K, g.M, batch, a_ld, a_bs, 32, UG_BM)) return 0;
+  if (!encode_map_f32_3d(&mB_hi, B_hi, b_cols, b_rows, batch, b_ld, b_bs, 32, b_box_rows, b_mn != 0)) return 0;
+  mA_lo = mA_hi; mB_lo = mB_hi;
+  if (passes == 3) {
+    if (!encode_map_f32_3d(&mA_lo, A_lo, g.K, g.M, batch, a_ld, a_bs, 32, UG_BM)) return 0;
+    if (!encode_map_f32_3d(&mB_lo, B_lo, b_cols, b_rows, batch, b_ld, b_bs, 32, b_box_rows, b_mn != 0)) return 0;
+  }
+  UmmaGemmParams p{(int)g.M, (int)g.N, (int)g.K, passes == 3 ? 3 : 1, b_mn, g.C, g.C_hi, g.C_lo, g.ldc, g.strideC,
+                   g.alpha, g.beta, g.diag_add, g.bias, g.stride_bias, g.resid};
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OTK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  dim3 grid((unsigned)ceil_div(g.M, UG_BM), (unsigned)ceil_div(g.N, UG_BN), (unsigned)batch);
+  if (grid.y > 65535) return 0;
+  umma_gemm_kernel<<<grid, UG_THREADS, UG_SMEM_BYTES, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  OTK_LAUNCH_CHECK();
+  return 1;
+}
+
+}  // namespace otk

@@ -8,6 +8,7 @@
 // needs more than NS_F32_MAX_ITERS steps (which happens when lambda_min/||A||_F is below ~1e-4) and the caller's
 // data is fp64 (the reference default), the whole computation is repeated in fp64 on the same device.
 #include "gemm.cuh"
+#include "otk_ptx.cuh"
 
 namespace otk {
 
@@ -38,18 +39,33 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return r;
 }
 
-// c[l] = || A_l + ridge I ||_F
-__global__ void frob_kernel(const void* a, int dt, int64_t dim, double ridge, double* c) {
+// c[l] = || A_l + ridge I ||_F : partial sums of squares with fp64 atomics (grid = blocks x L), then a sqrt pass
+__global__ void frob_sq_kernel(const void* a, int dt, int64_t dim, double ridge, double* c) {
   __shared__ double red[32];
-  const int64_t l = blockIdx.x;
+  const int64_t l = blockIdx.y;
   double acc = 0;
-  for (int64_t e = threadIdx.x; e < dim * dim; e += blockDim.x) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < dim * dim; e += (int64_t)gridDim.x * blockDim.x) {
     double v = load_real(a, l * dim * dim + e, dt);
     if (e / dim == e % dim) v += ridge;
     acc += v * v;
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) c[l] = sqrt(acc);
+  if (threadIdx.x == 0) atomicAdd(&c[l], acc);
+}
+__global__ void sqrt_inplace_kernel(double* c, int64_t n) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < n) c[e] = sqrt(c[e]);
+}
+static int frob_norm(const void* a, int dt, int64_t L, int64_t dim, double ridge, double* c, cudaStream_t st) {
+  OTK_CUDA(cudaMemsetAsync(c, 0, (size_t)L * 8, st));
+  int64_t bx = ceil_div(dim * dim, 256 * 8);
+  if (bx > 256) bx = 256;
+  if (bx < 1) bx = 1;
+  frob_sq_kernel<<<dim3((unsigned)bx, (unsigned)L), 256, 0, st>>>(a, dt, dim, ridge, c);
+  sqrt_inplace_kernel<<<(unsigned)ceil_div(L, 256), 256, 0, st>>>(c, L);
+  count_launch(1);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
 }
 
 // Y = (A + ridge I)/c, Z = I
@@ -117,6 +133,9 @@ __global__ void rel_residual_kernel(const float* R, const float* target, int64_t
   if (threadIdx.x == 0) rel[l] = sqrt(num / fmax(den, 1e-300));
 }
 
+template <typename T>
+static inline GemmArgs<T> with_scratch(GemmArgs<T> g, T* scratch) { g.scratch = scratch; return g; }
+
 static inline unsigned ew_grid(int64_t total) {
   int64_t b = ceil_div(total, 256), cap = (int64_t)sm_count() * 16;
   return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
@@ -125,18 +144,62 @@ static inline unsigned ew_grid(int64_t total) {
 template <typename W>
 struct NsWork {
   W *Y[2], *Z[2], *T;
+  // TF32 hi/lo planes of the iterates (fp32 / tcgen05 engine only): no conversion pass between chained GEMMs
+  W *Yh[2], *Yl[2], *Zh[2], *Zl[2], *Th, *Tl;
+  W* scratch;         // 4 planes: operand splits for the products outside the iteration
   double *c, *resid;  // c [L]; resid [NS_MAX_ITERS][L]
+  static constexpr int kPlanes = sizeof(W) == 4 ? 5 + 10 + 4 : 5;
   static size_t bytes(int64_t L, int64_t d) {
-    return 5 * align_up((size_t)L * d * d * sizeof(W), 256) + align_up((size_t)L * 8, 256) +
+    return kPlanes * align_up((size_t)L * d * d * sizeof(W), 256) + align_up((size_t)L * 8, 256) +
            align_up((size_t)NS_MAX_ITERS * L * 8, 256);
   }
   void carve(Arena& ar, int64_t L, int64_t d) {
-    for (int i = 0; i < 2; ++i) { Y[i] = ar.take<W>((size_t)L * d * d); Z[i] = ar.take<W>((size_t)L * d * d); }
-    T = ar.take<W>((size_t)L * d * d);
+    const size_t n = (size_t)L * d * d;
+    for (int i = 0; i < 2; ++i) { Y[i] = ar.take<W>(n); Z[i] = ar.take<W>(n); }
+    T = ar.take<W>(n);
+    if (sizeof(W) == 4) {
+      for (int i = 0; i < 2; ++i) { Yh[i] = ar.take<W>(n); Yl[i] = ar.take<W>(n); Zh[i] = ar.take<W>(n); Zl[i] = ar.take<W>(n); }
+      Th = ar.take<W>(n); Tl = ar.take<W>(n);
+      scratch = ar.take<W>(4 * n);
+    } else {
+      scratch = nullptr;
+    }
     c = ar.take<double>((size_t)L);
     resid = ar.take<double>((size_t)NS_MAX_ITERS * L);
   }
 };
+static size_t ns_work_bytes(int64_t L, int64_t d) {
+  size_t a = NsWork<float>::bytes(L, d), b = NsWork<double>::bytes(L, d);
+  return a > b ? a : b;
+}
+
+// plane-mode helpers (fp32 engine on tcgen05)
+__global__ void ns_init_planes_kernel(const void* a, int dt, int64_t L, int64_t dim, double ridge, const double* c, float* Yh,
+                                      float* Yl, float* Zh, float* Zl) {
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t l = e / (dim * dim), r = e % (dim * dim);
+    bool diag = (r / dim == r % dim);
+    float v = (float)((load_real(a, e, dt) + (diag ? ridge : 0.0)) / c[l]);
+    float h, lo;
+    ptx::split_tf32(v, h, lo);
+    Yh[e] = h; Yl[e] = lo;
+    Zh[e] = diag ? 1.f : 0.f; Zl[e] = 0.f;
+  }
+}
+__global__ void join_planes_kernel(const float* hi, const float* lo, int64_t n, float* out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = hi[e] + lo[e];
+}
+static bool ns_planes_eligible(int64_t d) { return d >= 64 && d % 4 == 0; }
+static int plane_gemm(const float* Ah, const float* Al, const float* Bh, const float* Bl, float* Ch, float* Cl, int64_t d,
+                      int64_t L, float alpha, float diag, double* resid, cudaStream_t st) {
+  GemmArgs<float> g = nn_args_t<float>(Ah, Bh, nullptr, d, d * d, alpha);
+  g.A_lo = Al; g.B_lo = Bl; g.C_hi = Ch; g.C_lo = Cl; g.diag_add = diag; g.resid = resid;
+  int r = gemm_umma_try(g, L, 3, st);
+  if (r == 0) { set_last_error_msg("sqrtm: tcgen05 engine rejected an eligible shape"); return OTK_ERR_CUDA; }
+  return r < 0 ? r : OTK_OK;
+}
 
 enum { NS_CONVERGED = 0, NS_SLOW = 1 };
 
@@ -148,9 +211,13 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
                     int* verdict, int* used, cudaStream_t st) {
   const int64_t dd = d * d;
   const bool f32 = sizeof(W) == 4;
-  frob_kernel<<<(unsigned)L, 256, 0, st>>>(a, dt, d, ridge, w.c);
-  OTK_LAUNCH_CHECK();
-  ns_init_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, ridge, w.c, w.Y[0], w.Z[0]);
+  bool planes = false;
+  if constexpr (sizeof(W) == 4) planes = ns_planes_eligible(d) && L <= 65535;
+  OTK_TRY(frob_norm(a, dt, L, d, ridge, w.c, st));
+  if constexpr (sizeof(W) == 4) {
+    if (planes) ns_init_planes_kernel<<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, ridge, w.c, w.Yh[0], w.Yl[0], w.Zh[0], w.Zl[0]);
+  }
+  if (!planes) ns_init_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, ridge, w.c, w.Y[0], w.Z[0]);
   OTK_LAUNCH_CHECK();
   OTK_CUDA(cudaMemsetAsync(w.resid, 0, (size_t)NS_MAX_ITERS * L * 8, st));
   const bool adaptive = iters <= 0;
@@ -162,12 +229,23 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
   *verdict = adaptive ? NS_SLOW : NS_CONVERGED;
   double host_res[256];
   for (int k = 0; k < max_iters && k < stop_at; ++k) {
-    GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.T, d, dd, W(-0.5));
-    g.diag_add = W(1.5);
-    g.resid = w.resid + (size_t)k * L;
-    OTK_TRY(gemm_any(g, L, st));
-    OTK_TRY(gemm_any(nn_args_t<W>(w.Y[cur], w.T, w.Y[cur ^ 1], d, dd, W(1)), L, st));
-    OTK_TRY(gemm_any(nn_args_t<W>(w.T, w.Z[cur], w.Z[cur ^ 1], d, dd, W(1)), L, st));
+    bool done_planes = false;
+    if constexpr (sizeof(W) == 4) {
+      if (planes) {
+        OTK_TRY(plane_gemm(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, L, -0.5f, 1.5f, w.resid + (size_t)k * L, st));
+        OTK_TRY(plane_gemm(w.Yh[cur], w.Yl[cur], w.Th, w.Tl, w.Yh[cur ^ 1], w.Yl[cur ^ 1], d, L, 1.f, 0.f, nullptr, st));
+        OTK_TRY(plane_gemm(w.Th, w.Tl, w.Zh[cur], w.Zl[cur], w.Zh[cur ^ 1], w.Zl[cur ^ 1], d, L, 1.f, 0.f, nullptr, st));
+        done_planes = true;
+      }
+    }
+    if (!done_planes) {
+      GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.T, d, dd, W(-0.5));
+      g.diag_add = W(1.5);
+      g.resid = w.resid + (size_t)k * L;
+      OTK_TRY(gemm_any(g, L, st));
+      OTK_TRY(gemm_any(nn_args_t<W>(w.Y[cur], w.T, w.Y[cur ^ 1], d, dd, W(1)), L, st));
+      OTK_TRY(gemm_any(nn_args_t<W>(w.T, w.Z[cur], w.Z[cur ^ 1], d, dd, W(1)), L, st));
+    }
     cur ^= 1;
     if (adaptive && (k >= 5 || k + 1 == max_iters)) {
       double worst = 0;
@@ -184,6 +262,14 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
       // resid[k] is ||I - Z_k Y_k||_F^2 of the state BEFORE update k
       if (worst < tol_done) { stop_at = k + 1; *verdict = NS_CONVERGED; }
       else if (worst < tol_near) { stop_at = k + 2; *verdict = NS_CONVERGED; }
+    }
+  }
+  if constexpr (sizeof(W) == 4) {
+    if (planes) {
+      join_planes_kernel<<<ew_grid(L * dd), 256, 0, st>>>(w.Yh[cur], w.Yl[cur], L * dd, w.Y[cur]);
+      join_planes_kernel<<<ew_grid(L * dd), 256, 0, st>>>(w.Zh[cur], w.Zl[cur], L * dd, w.Z[cur]);
+      count_launch(1);
+      OTK_LAUNCH_CHECK();
     }
   }
   *cur_out = cur;
@@ -229,8 +315,8 @@ static int rooted_mix(const void* P, const void* Q, int dt, int64_t L, int64_t d
   }
   cast_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(Q, dt, L * dd, Q32);
   OTK_LAUNCH_CHECK();
-  OTK_TRY(gemm_any(nn_args_t<W>(S, Q32, G, d, dd, W(1)), L, st));     // S Q
-  OTK_TRY(gemm_any(nn_args_t<W>(G, S, Q32, d, dd, W(1)), L, st));     // (S Q) S
+  OTK_TRY(gemm_any(with_scratch(nn_args_t<W>(S, Q32, G, d, dd, W(1)), w.scratch), L, st));     // S Q
+  OTK_TRY(gemm_any(with_scratch(nn_args_t<W>(G, S, Q32, d, dd, W(1)), w.scratch), L, st));     // (S Q) S
   sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(Q32, none, L, d, nullptr, 0, 1.0, 0, 0, 0.0, mix, wdt);
   OTK_LAUNCH_CHECK();
   OTK_TRY(ns_solve<W>(mix, wdt, L, d, 0.0, iters, w, cur2, &v2, &used2, st));
@@ -276,8 +362,8 @@ static int operator_impl(const void* cov_s, const void* cov_t, int64_t L, int64_
   // R = sqrt(mix) = sqrt(c) * sym(Y);  T = (1-p) Zp R Zp + p I
   sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(w.Y[cur2], none, L, d, w.c, 0.5, 1.0, 0, 0, 0.0, mix, wdt);
   OTK_LAUNCH_CHECK();
-  OTK_TRY(gemm_any(nn_args_t<W>(Zp, mix, G, d, dd, W(1)), L, st));
-  OTK_TRY(gemm_any(nn_args_t<W>(G, Zp, Q32, d, dd, W(1)), L, st));
+  OTK_TRY(gemm_any(with_scratch(nn_args_t<W>(Zp, mix, G, d, dd, W(1)), w.scratch), L, st));
+  OTK_TRY(gemm_any(with_scratch(nn_args_t<W>(G, Zp, Q32, d, dd, W(1)), w.scratch), L, st));
   sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(Q32, none, L, d, nullptr, 0, 1.0 - pg_star, 0, 0, pg_star, T, dtype);
   OTK_LAUNCH_CHECK();
   if constexpr (sizeof(W) == 4) {
@@ -291,8 +377,8 @@ static int operator_impl(const void* cov_s, const void* cov_t, int64_t L, int64_
       cast_kernel<float><<<ew_grid(L * dd), 256, 0, st>>>(cov_t, dtype, L * dd, Ct32);
       count_launch(2);
       OTK_LAUNCH_CHECK();
-      OTK_TRY(gemm_any(nn_args_t<float>(T0, Cs32, G, d, dd, 1.f), L, st));
-      OTK_TRY(gemm_any(nn_args_t<float>(G, T0, Q32, d, dd, 1.f), L, st));
+      OTK_TRY(gemm_any(with_scratch(nn_args_t<float>(T0, Cs32, G, d, dd, 1.f), w.scratch), L, st));
+      OTK_TRY(gemm_any(with_scratch(nn_args_t<float>(G, T0, Q32, d, dd, 1.f), w.scratch), L, st));
       rel_residual_kernel<<<(unsigned)L, 256, 0, st>>>(Q32, Ct32, d, w.resid);
       OTK_LAUNCH_CHECK();
       double host_rel[256];
@@ -309,12 +395,12 @@ static int operator_impl(const void* cov_s, const void* cov_t, int64_t L, int64_
 using namespace otk;
 
 // workspaces are sized for the fp64 escalation
-extern "C" size_t otk_sqrtm_workspace_bytes(int64_t L, int64_t dim) { return NsWork<double>::bytes(L, dim) + 4096; }
+extern "C" size_t otk_sqrtm_workspace_bytes(int64_t L, int64_t dim) { return ns_work_bytes(L, dim) + 4096; }
 extern "C" size_t otk_w2_gaussian_workspace_bytes(int64_t L, int64_t dim) {
-  return NsWork<double>::bytes(L, dim) + 5 * align_up((size_t)L * dim * dim * 8, 256) + 4096;
+  return ns_work_bytes(L, dim) + 5 * align_up((size_t)L * dim * dim * 8, 256) + 4096;
 }
 extern "C" size_t otk_transport_operator_workspace_bytes(int64_t L, int64_t dim) {
-  return NsWork<double>::bytes(L, dim) + 6 * align_up((size_t)L * dim * dim * 8, 256) + 4096;
+  return ns_work_bytes(L, dim) + 6 * align_up((size_t)L * dim * dim * 8, 256) + 4096;
 }
 
 // `polish`: 0 = precision policy above (fp32 engine, fp64 escalation for fp64 data); 1 = force the fp64 engine;

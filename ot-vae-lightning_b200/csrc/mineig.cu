@@ -4,7 +4,7 @@
 
 namespace otk {
 
-constexpr int LZ_MAX_STEPS = 128, LZ_THREADS = 256;
+constexpr int LZ_MAX_STEPS = 128, LZ_THREADS = 512;
 
 __global__ void lower_to_full_kernel(const void* a, int dt, int64_t L, int64_t dim, double* out) {
   const int64_t total = L * dim * dim;
@@ -32,7 +32,7 @@ __device__ __forceinline__ double lz_block_sum(double v, double* red) {
 
 __global__ void __launch_bounds__(LZ_THREADS)
 lanczos_min_eig_kernel(const double* __restrict__ A, int64_t d, int steps, double* __restrict__ V, double* out) {
-  __shared__ double alpha[LZ_MAX_STEPS], beta[LZ_MAX_STEPS], red[32];
+  __shared__ double alpha[LZ_MAX_STEPS], beta[LZ_MAX_STEPS], proj[LZ_MAX_STEPS], red[32];
   __shared__ int m_eff;
   const int64_t l = blockIdx.x;
   const double* Al = A + l * d * d;
@@ -56,23 +56,39 @@ lanczos_min_eig_kernel(const double* __restrict__ A, int64_t d, int steps, doubl
     double* w = Vl + (int64_t)(j + 1) * d;
     double dot = 0;
     for (int64_t i = tid; i < d; i += LZ_THREADS) {
-      double acc = 0;
-      for (int64_t k = 0; k < d; ++k) acc += Al[k * d + i] * vj[k];  // symmetric: column access is coalesced
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // symmetric: column access is coalesced across threads
+      int64_t k = 0;
+      for (; k + 3 < d; k += 4) {
+        a0 += Al[k * d + i] * vj[k];
+        a1 += Al[(k + 1) * d + i] * vj[k + 1];
+        a2 += Al[(k + 2) * d + i] * vj[k + 2];
+        a3 += Al[(k + 3) * d + i] * vj[k + 3];
+      }
+      for (; k < d; ++k) a0 += Al[k * d + i] * vj[k];
+      const double acc = (a0 + a1) + (a2 + a3);
       w[i] = acc;
       dot += acc * vj[i];
     }
     dot = lz_block_sum(dot, red);
     if (tid == 0) alpha[j] = dot;
-    // full re-orthogonalisation against v_0..v_j (two sweeps of classical Gram-Schmidt, one vector at a time)
-    for (int sweep = 0; sweep < 2; ++sweep)
-      for (int t = j; t >= 0; --t) {
+    // full re-orthogonalisation against v_0..v_j: two sweeps of block classical Gram-Schmidt (all j+1 projections
+    // per sweep are computed together - one warp per basis vector - so a sweep costs two block barriers)
+    for (int sweep = 0; sweep < 2; ++sweep) {
+      for (int t = tid / 32; t <= j; t += LZ_THREADS / 32) {
         const double* vt = Vl + (int64_t)t * d;
         double p = 0;
-        for (int64_t i = tid; i < d; i += LZ_THREADS) p += w[i] * vt[i];
-        p = lz_block_sum(p, red);
-        for (int64_t i = tid; i < d; i += LZ_THREADS) w[i] -= p * vt[i];
-        __syncthreads();
+        for (int64_t i = tid % 32; i < d; i += 32) p += w[i] * vt[i];
+        p = warp_sum(p);
+        if (tid % 32 == 0) proj[t] = p;
       }
+      __syncthreads();
+      for (int64_t i = tid; i < d; i += LZ_THREADS) {
+        double acc = w[i];
+        for (int t = 0; t <= j; ++t) acc -= proj[t] * Vl[(int64_t)t * d + i];
+        w[i] = acc;
+      }
+      __syncthreads();
+    }
     double nn = 0;
     for (int64_t i = tid; i < d; i += LZ_THREADS) nn += w[i] * w[i];
     nn = sqrt(lz_block_sum(nn, red));

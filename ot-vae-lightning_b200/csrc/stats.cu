@@ -7,8 +7,10 @@
 namespace otk {
 
 // ------------------------------------------------------------------------------------------------
-// FFMA engine (any dim): one CTA = one upper-triangular 64x64 tile pair x one chunk of rows.
-// fp32 accumulation inside the chunk (<= ST_MAX_CHUNK rows), fp64 atomics across chunks.
+// DFMA engine (any dim): one CTA = one upper-triangular 64x64 tile pair x one chunk of rows.
+// fp32 latents are widened to fp64 and accumulated with DFMA (products of fp32 values are exact in fp64), i.e. the
+// same arithmetic as the reference's fp64 einsum on `samples.type_as(buffer)` (gaussian_model.py:103,148); fp64
+// atomics across chunks.  This is the engine for small / unaligned dims; aligned dims go to the tcgen05 kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int ST_T = 64, ST_BK = 16, ST_THREADS = 256;
 
@@ -27,12 +29,12 @@ stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_
   const float* xb = x + l * batch_stride;
   const int64_t i0 = (int64_t)ti * ST_T, j0 = (int64_t)tj * ST_T;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-  float acc[4][4];
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float colsum = 0.f;  // threads 0..63 of a diagonal CTA own one column each
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  double colsum = 0.0;  // threads 0..63 of a diagonal CTA own one column each
 
   for (int64_t k0 = r0; k0 < r1; k0 += ST_BK) {
 #pragma unroll
@@ -47,19 +49,19 @@ stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_
     __syncthreads();
     if (ti == tj && tid < ST_T) {
 #pragma unroll
-      for (int kk = 0; kk < ST_BK; ++kk) colsum += As[kk][tid];
+      for (int kk = 0; kk < ST_BK; ++kk) colsum += (double)As[kk][tid];
     }
 #pragma unroll
     for (int kk = 0; kk < ST_BK; ++kk) {
-      float a[4], b[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = (double)As[kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = (double)Bs[kk][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -71,10 +73,10 @@ stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int64_t gj = j0 + tx * 4 + j;
-      if (gj < dim) atomicAdd(&cov[gi * dim + gj], (double)acc[i][j]);
+      if (gj < dim) atomicAdd(&cov[gi * dim + gj], acc[i][j]);
     }
   }
-  if (ti == tj && tid < ST_T && i0 + tid < dim) atomicAdd(&ws_sum[l * dim + i0 + tid], (double)colsum);
+  if (ti == tj && tid < ST_T && i0 + tid < dim) atomicAdd(&ws_sum[l * dim + i0 + tid], colsum);
 }
 
 // merge the fp64 staging area into the running buffers (mirror the lower triangle, apply the EMA rule)
@@ -85,8 +87,11 @@ __global__ void stats_merge_kernel(const double* __restrict__ ws_cov, const doub
   const double keep = decay < 0 ? 1.0 : decay, gain = decay < 0 ? 1.0 : 1.0 - decay;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
-    // only tiles with tile(i) <= tile(j) were accumulated
-    double v = (i / tile <= j / tile) ? ws_cov[l * dim * dim + i * dim + j] : ws_cov[l * dim * dim + j * dim + i];
+    // only tiles with tile(i) <= tile(j) were accumulated; always reading the (min, max) element also makes the
+    // result exactly symmetric
+    (void)tile;
+    const int64_t lo_i = i < j ? i : j, hi_j = i < j ? j : i;
+    double v = ws_cov[l * dim * dim + lo_i * dim + hi_j];
     store_real(sum_cov, e, buf_dtype, load_real(sum_cov, e, buf_dtype) * keep + v * gain);
     if (r < dim) {
       int64_t s = l * dim + r;
@@ -175,11 +180,11 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
       tile = ST_T;
       int n_tiles = (int)ceil_div(dim, ST_T);
       int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
-      // enough chunks for ~4 waves, chunk length a multiple of ST_BK and <= 2048 rows (fp32 accumulation span)
+      // enough chunks for ~4 waves, chunk length a multiple of ST_BK
       int64_t want = ceil_div((int64_t)sm_count() * 4, pairs * L);
       int64_t chunk = ceil_div(ceil_div(rows, want), ST_BK) * ST_BK;
       if (chunk < 64) chunk = 64;
-      if (chunk > 2048) chunk = 2048;
+      if (chunk > 65536) chunk = 65536;
       dim3 grid((unsigned)pairs, (unsigned)ceil_div(rows, chunk), (unsigned)L);
       OTK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stats_update: too many row chunks / batches");
       stats_simt_kernel<<<grid, ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride, chunk, n_tiles, ws_cov,

@@ -4,10 +4,6 @@
 #include "apply_umma.cuh"
 #include "sinkhorn_umma.cuh"
 namespace otk {
-int gemm_umma_try(const GemmArgs<float>&, int64_t, int, cudaStream_t) { return 0; }
-size_t stats_umma_extra_workspace(int64_t, int64_t) { return 0; }
-int stats_umma_try(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, double*, double*, Arena&, cudaStream_t, int*) { return 0; }
-int apply_umma_try(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, float*, float*, cudaStream_t) { return 0; }
 bool sk_umma_eligible(int64_t, int64_t, int64_t, int) { return false; }
 size_t sk_umma_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
 int sk_umma_solve(const float*, const float*, int64_t, int64_t, int64_t, const float*, const float*, double, int, double, int, double, int, int, float*, float*, double*, int*, void*, size_t, cudaStream_t) { return OTK_ERR_INVALID_ARGUMENT; }

@@ -307,16 +307,20 @@ def rowstep(x_local: Tensor, y: Tensor, a_local: Tensor, v: Tensor, u_local: Ten
     N.check(st, "otk_sinkhorn_points_rowstep")
 
 
-def gemm_nt(A: Tensor, B: Tensor, alpha: float = 1.0, engine: int = 0) -> Tensor:
-    """C = alpha * A @ B^T (fp32, [*, M, K] x [*, N, K]); exported for the kernel unit tests."""
+def gemm(A: Tensor, B: Tensor, alpha: float = 1.0, engine: int = 0, nn: bool = False) -> Tensor:
+    """C = alpha * A @ B^T (nn=False, B [*, N, K]) or alpha * A @ B (nn=True, B [*, K, N]); fp32.
+    engine: 0 auto, 1 FFMA, 2 tcgen05 3xTF32, 3 tcgen05 1xTF32.  Exported for the kernel unit tests."""
     dev = A.device
     A, B = A.contiguous(), B.contiguous()
-    M, K = A.shape[-2:]
-    Nn = B.shape[-2]
+    M, Kd = A.shape[-2:]
+    Nn = B.shape[-1] if nn else B.shape[-2]
     batch = int(torch.Size(A.shape[:-2]).numel())
     out = torch.empty(*A.shape[:-2], M, Nn, dtype=torch.float32, device=dev)
+    lib = N.load()
+    fn = lib.otk_gemm_nn if nn else lib.otk_gemm_nt
     with torch.cuda.device(dev):
-        st = N.load().otk_gemm_nt(N.ptr(A), N.ptr(B), N.ptr(out), M, Nn, K, K, K, Nn, batch, M * K, Nn * K, M * Nn,
-                                  float(alpha), 0.0, int(engine), N.stream_ptr(dev))
-    N.check(st, "otk_gemm_nt")
+        ws = N.workspace(lib.otk_gemm_workspace_bytes(M, Nn, Kd, batch), dev)
+        st = fn(N.ptr(A), N.ptr(B), N.ptr(out), M, Nn, Kd, Kd, B.shape[-1], Nn, batch, M * Kd, B.shape[-2] * B.shape[-1],
+                M * Nn, float(alpha), 0.0, int(engine), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_gemm")
     return out

@@ -192,7 +192,8 @@ class GaussianModel(DistributionModel, W2Mixin):
     def _update_cov(self, val: Optional[Tensor], seen: Optional[Tensor] = None):
         if val is None:
             return
-        if seen is None:
+        if seen is None or bool(seen.all()):
+            # every leading index is overwritten: no need to read (and re-parametrize) the current value
             self.cov = val.to(self.parametrizations.cov.original)
         else:
             current = self.cov  # parametrized read, as in the reference (:181)
