@@ -153,12 +153,13 @@ int otk_sinkhorn_dense(const void* a, const void* b, const void* C, int64_t L, i
  *   x [N,d], y [M,d] fp32; a [N], b [M] fp32; u [N], v [M] fp32 in/out (not reset if `warm_start`).
  *   Row-sharded multi-GPU use: call otk_sinkhorn_points_colstep on the local rows of x, combine the
  *   (max, sumexp) partials of all ranks, then otk_sinkhorn_points_rowstep. */
-size_t otk_sinkhorn_points_workspace_bytes(int64_t N, int64_t M, int64_t dim);
+size_t otk_sinkhorn_points_workspace_bytes(int64_t N, int64_t M, int64_t dim, int cost_kind);
 /* scale = 1/max_ij cost (w2_utils.py:265-266) if scale_inv_max != 0, else `scale`; result in *scale_out_host */
 int otk_sinkhorn_points(const float* x, const float* y, int64_t N, int64_t M, int64_t dim,
                         const float* a, const float* b, int cost_kind, double scale, int scale_inv_max,
                         double reg, int max_iter, double threshold, int poll_every, int precision,
                         float* u, float* v, double* summary /* [4]: <C,pi>, sum pi, max|row err|, max|col err| */,
+                        float* row_marginal /* [N] or NULL */, float* col_marginal /* [M] or NULL */,
                         int* iters_done_host, void* workspace, size_t workspace_bytes,
                         otk_stream_t stream);
 /* half-steps for the row-sharded path: partial column LSE over local rows (m,s) [2,M]; combine; row step */

@@ -49,9 +49,9 @@ SIGNATURES = {
     "otk_sinkhorn_dense_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_sinkhorn_dense": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _dbl, _int, _dbl, _int, _ptr, _ptr, _ptr,
                                   C.POINTER(_int), _ptr, _sz, _ptr]),
-    "otk_sinkhorn_points_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "otk_sinkhorn_points_workspace_bytes": (_sz, [_i64, _i64, _i64, _int]),
     "otk_sinkhorn_points": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _dbl, _int, _dbl, _int, _dbl, _int,
-                                   _int, _ptr, _ptr, _ptr, C.POINTER(_int), _ptr, _sz, _ptr]),
+                                   _int, _ptr, _ptr, _ptr, _ptr, _ptr, C.POINTER(_int), _ptr, _sz, _ptr]),
     "otk_sinkhorn_points_colstep": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _int, _dbl, _dbl, _int, _ptr, _ptr, _ptr,
                                            _sz, _ptr]),
     "otk_lse_combine": (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),

@@ -91,7 +91,7 @@ __global__ void set_kernel(float* out, float v) { *out = v; }
 __global__ void __launch_bounds__(256)
 plan_row_summary_kernel(const float* __restrict__ C, const float* __restrict__ u, const float* __restrict__ v,
                         const float* __restrict__ a, int64_t N, int64_t M, float nir, double* summary,
-                        float* __restrict__ colsum) {
+                        float* __restrict__ colsum, float* __restrict__ rowsum_out) {
   // one block per row; also accumulates column sums with atomics (M floats)
   __shared__ double red_c[8], red_m[8];
   const int64_t i = blockIdx.x;
@@ -112,6 +112,7 @@ plan_row_summary_kernel(const float* __restrict__ C, const float* __restrict__ u
     for (int w = 0; w < 8; ++w) { tc += red_c[w]; tm += red_m[w]; }
     atomicAdd(&summary[0], tc);
     atomicAdd(&summary[1], tm);
+    if (rowsum_out) rowsum_out[i] = (float)tm;
     double err = fabs(tm - (double)a[i]);
     // max via atomicMax on the bit pattern of a non-negative double
     atomicMax(reinterpret_cast<unsigned long long*>(&summary[2]), (unsigned long long)__double_as_longlong(err));
@@ -145,9 +146,8 @@ static size_t stream_ws_bytes(int64_t N, int64_t M) {
 }  // namespace otk
 using namespace otk;
 
-extern "C" size_t otk_sinkhorn_points_workspace_bytes(int64_t N, int64_t M, int64_t dim) {
-  size_t fused = sk_umma_workspace_bytes(N, M, dim);
-  if (sk_umma_eligible(N, M, dim, OTK_COST_SQEUCLIDEAN)) return fused;
+extern "C" size_t otk_sinkhorn_points_workspace_bytes(int64_t N, int64_t M, int64_t dim, int cost_kind) {
+  if (sk_umma_eligible(N, M, dim, cost_kind)) return sk_umma_workspace_bytes(N, M, dim);
   return stream_ws_bytes(N, M);
 }
 
@@ -168,6 +168,8 @@ extern "C" int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M
   OTK_REQUIRE(x && y && out && N > 0 && M > 0 && dim > 0, "cost_max: bad arguments");
   if (!workspace || workspace_bytes < (size_t)(N + M) * 4 + 512) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
+  if (sk_umma_eligible(N, M, dim, cost_kind) && workspace_bytes >= sk_umma_workspace_bytes(N, M, dim))
+    return sk_umma_cost_max(x, y, N, M, dim, out, workspace, workspace_bytes, st);
   Arena ar(workspace, workspace_bytes);
   float* nx = ar.take<float>((size_t)N);
   float* ny = ar.take<float>((size_t)M);
@@ -184,16 +186,16 @@ extern "C" int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M
 extern "C" int otk_sinkhorn_points(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, const float* a,
                                    const float* b, int cost_kind, double scale, int scale_inv_max, double reg,
                                    int max_iter, double threshold, int poll_every, int precision, float* u, float* v,
-                                   double* summary, int* iters_done_host, void* workspace, size_t workspace_bytes,
-                                   otk_stream_t stream) {
+                                   double* summary, float* row_marginal, float* col_marginal, int* iters_done_host,
+                                   void* workspace, size_t workspace_bytes, otk_stream_t stream) {
   OTK_TRY(require_device());
   OTK_REQUIRE(x && y && a && b && u && v && N > 0 && M > 0 && dim > 0, "sinkhorn_points: bad arguments");
   OTK_REQUIRE(reg > 0 && max_iter >= 0, "sinkhorn_points: reg must be > 0");
-  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(N, M, dim)) return OTK_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(N, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   if (sk_umma_eligible(N, M, dim, cost_kind))
     return sk_umma_solve(x, y, N, M, dim, a, b, scale, scale_inv_max, reg, max_iter, threshold, poll_every, precision, u,
-                         v, summary, iters_done_host, workspace, workspace_bytes, st);
+                         v, summary, row_marginal, col_marginal, iters_done_host, workspace, workspace_bytes, st);
   // streaming engine
   Arena ar(workspace, workspace_bytes);
   float* C = ar.take<float>((size_t)N * M);
@@ -219,8 +221,9 @@ extern "C" int otk_sinkhorn_points(const float* x, const float* y, int64_t N, in
   if (summary) {
     OTK_CUDA(cudaMemsetAsync(summary, 0, 4 * sizeof(double), st));
     OTK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)M * 4, st));
-    plan_row_summary_kernel<<<(unsigned)N, 256, 0, st>>>(C, u, v, a, N, M, (float)(-1.0 / reg), summary, colsum);
+    plan_row_summary_kernel<<<(unsigned)N, 256, 0, st>>>(C, u, v, a, N, M, (float)(-1.0 / reg), summary, colsum, row_marginal);
     plan_col_err_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(colsum, b, M, summary);
+    if (col_marginal) OTK_CUDA(cudaMemcpyAsync(col_marginal, colsum, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
     count_launch(1);
     OTK_LAUNCH_CHECK();
   }
@@ -233,7 +236,7 @@ extern "C" int otk_sinkhorn_points_colstep(const float* x_local, const float* y,
                                            otk_stream_t stream) {
   OTK_TRY(require_device());
   OTK_REQUIRE(x_local && y && u_local && col_max && col_sum && n_local > 0 && M > 0 && dim > 0, "colstep: bad arguments");
-  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim)) return OTK_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   if (sk_umma_eligible(n_local, M, dim, cost_kind))
     return sk_umma_colstep(x_local, y, n_local, M, dim, u_local, scale, reg, precision, col_max, col_sum, workspace,
@@ -287,7 +290,7 @@ extern "C" int otk_sinkhorn_points_rowstep(const float* x_local, const float* y,
                                            size_t workspace_bytes, otk_stream_t stream) {
   OTK_TRY(require_device());
   OTK_REQUIRE(x_local && y && a_local && v && u_local && n_local > 0 && M > 0 && dim > 0, "rowstep: bad arguments");
-  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim)) return OTK_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   if (sk_umma_eligible(n_local, M, dim, cost_kind))
     return sk_umma_rowstep(x_local, y, n_local, M, dim, a_local, v, scale, reg, precision, u_local, diff, workspace,

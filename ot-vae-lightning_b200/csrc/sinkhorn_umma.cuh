@@ -4,10 +4,12 @@
 namespace otk {
 bool sk_umma_eligible(int64_t N, int64_t M, int64_t dim, int cost_kind);
 size_t sk_umma_workspace_bytes(int64_t N, int64_t M, int64_t dim);
+int sk_umma_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, float* out, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st);
 int sk_umma_solve(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, const float* a, const float* b,
                   double scale, int scale_inv_max, double reg, int max_iter, double threshold, int poll_every, int precision,
-                  float* u, float* v, double* summary, int* iters_done_host, void* workspace, size_t workspace_bytes,
-                  cudaStream_t st);
+                  float* u, float* v, double* summary, float* row_marginal, float* col_marginal, int* iters_done_host,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st);
 int sk_umma_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* u_local,
                     double scale, double reg, int precision, float* col_max, float* col_sum, void* workspace,
                     size_t workspace_bytes, cudaStream_t st);

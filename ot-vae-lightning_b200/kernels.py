@@ -217,7 +217,7 @@ def sinkhorn_points(x: Tensor, y: Tensor, a: Tensor, b: Tensor, reg: float, max_
                     cost: int = N.COST_SQEUCLIDEAN, scale: Optional[float] = None, precision: int = 0,
                     poll_every: int = 16, want_summary: bool = True, want_iters: bool = True):
     """Point-cloud Sinkhorn (no N x M matrix in HBM on the fused engine).  scale=None -> 1/max cost.
-    Returns dict(u, v, summary=[<C,pi>, mass, max row err, max col err] or None, iters)."""
+    Returns dict(u, v, summary=[<C,pi>, mass, max row err, max col err] or None, row_marginal, col_marginal, iters)."""
     dev = N.compute_device(x, y)
     xd, yd = _dev_tensor(x, dev, torch.float32), _dev_tensor(y, dev, torch.float32)
     ad, bd = _dev_tensor(a, dev, torch.float32), _dev_tensor(b, dev, torch.float32)
@@ -226,17 +226,19 @@ def sinkhorn_points(x: Tensor, y: Tensor, a: Tensor, b: Tensor, reg: float, max_
     u = torch.zeros(n, dtype=torch.float32, device=dev)
     v = torch.zeros(m, dtype=torch.float32, device=dev)
     summary = torch.zeros(4, dtype=torch.float64, device=dev) if want_summary else None
+    row_marg = torch.empty(n, dtype=torch.float32, device=dev) if want_summary else None
+    col_marg = torch.empty(m, dtype=torch.float32, device=dev) if want_summary else None
     iters = C.c_int(0)
     lib = N.load()
     with torch.cuda.device(dev):
-        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d), dev)
+        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev)
         st = lib.otk_sinkhorn_points(N.ptr(xd), N.ptr(yd), n, m, d, N.ptr(ad), N.ptr(bd), int(cost),
                                      1.0 if scale is None else float(scale), 1 if scale is None else 0, float(reg),
                                      int(max_iter), float(threshold), int(poll_every), int(precision), N.ptr(u),
-                                     N.ptr(v), N.ptr(summary), C.byref(iters) if want_iters else None, N.ptr(ws),
+                                     N.ptr(v), N.ptr(summary), N.ptr(row_marg), N.ptr(col_marg), C.byref(iters) if want_iters else None, N.ptr(ws),
                                      ws.numel(), N.stream_ptr(dev))
     N.check(st, "otk_sinkhorn_points")
-    return dict(u=u, v=v, summary=summary, iters=iters.value)
+    return dict(u=u, v=v, summary=summary, row_marginal=row_marg, col_marginal=col_marg, iters=iters.value)
 
 
 def cost_matrix(x: Tensor, y: Tensor, cost: int, scale: float = 1.0) -> Tensor:
@@ -260,7 +262,8 @@ def cost_max(x: Tensor, y: Tensor, cost: int) -> Tensor:
     m = yd.shape[0]
     out = torch.zeros(1, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        ws = N.workspace((n + m) * 4 + 512, dev)
+        ws = N.workspace(max((n + m) * 4 + 512, N.load().otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost))
+                             if cost == N.COST_SQEUCLIDEAN and d <= 128 and d % 4 == 0 else 0), dev)
         st = N.load().otk_cost_max(N.ptr(xd), N.ptr(yd), n, m, d, int(cost), N.ptr(out), N.ptr(ws), ws.numel(),
                                    N.stream_ptr(dev))
     N.check(st, "otk_cost_max")
@@ -276,7 +279,7 @@ def colstep(x_local: Tensor, y: Tensor, u_local: Tensor, scale: float, reg: floa
     cs = torch.empty(m, dtype=torch.float32, device=dev)
     lib = N.load()
     with torch.cuda.device(dev):
-        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d), dev)
+        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev)
         st = lib.otk_sinkhorn_points_colstep(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(u_local), int(cost), float(scale),
                                              float(reg), int(precision), N.ptr(cm), N.ptr(cs), N.ptr(ws), ws.numel(),
                                              N.stream_ptr(dev))
@@ -300,7 +303,7 @@ def rowstep(x_local: Tensor, y: Tensor, a_local: Tensor, v: Tensor, u_local: Ten
     m = y.shape[0]
     lib = N.load()
     with torch.cuda.device(dev):
-        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d), dev)
+        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev)
         st = lib.otk_sinkhorn_points_rowstep(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(a_local), N.ptr(v), int(cost),
                                              float(scale), float(reg), int(precision), N.ptr(u_local), N.ptr(diff),
                                              N.ptr(ws), ws.numel(), N.stream_ptr(dev))

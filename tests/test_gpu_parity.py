@@ -205,9 +205,12 @@ def test_sinkhorn_points_vs_oracle(oracle, n, m, d):
     s = res["summary"].cpu()
     assert abs(s[0].item() - (C * scale * plan).sum().item()) / (C * scale * plan).sum().item() < TOL_SINKHORN
     assert abs(s[1].item() - plan.sum().item()) < TOL_SINKHORN
-    # marginals: rebuild them from the returned potentials on the oracle's cost
+    # marginals of the plan the kernels hold (never materialised) against the reference plan's marginals
+    assert rel(res["row_marginal"], plan.sum(1)) < TOL_SINKHORN and rel(res["col_marginal"], plan.sum(0)) < TOL_SINKHORN
+    # the potentials themselves, rebuilt on the oracle's exact fp64 cost: the TF32 rounding of the points (2^-12
+    # relative) perturbs individual plan entries by ~1e-4, it must average out of the marginals to a few 1e-4
     got = torch.exp(res["u"].double().cpu()[:, None] + res["v"].double().cpu()[None, :] - C * scale / 0.05)
-    assert rel(got.sum(1), plan.sum(1)) < TOL_SINKHORN and rel(got.sum(0), plan.sum(0)) < TOL_SINKHORN
+    assert rel(got.sum(1), plan.sum(1)) < 5e-4 and rel(got.sum(0), plan.sum(0)) < 5e-4
     assert res["iters"] == 40
 
 
