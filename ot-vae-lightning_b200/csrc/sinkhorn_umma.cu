@@ -13,6 +13,7 @@
 // x one contiguous range of Q tiles; the (max, sum) partials of the ranges - and, in the row-sharded multi-GPU path,
 // of the ranks - are merged by sk_finalize_kernel.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cfloat>
 
 #include "otk_ptx.cuh"
@@ -21,11 +22,12 @@
 
 namespace otk {
 
-constexpr int FS_BM = 128, FS_BN = 128, FS_SLAB_BYTES = 128 * 128, FS_MAX_SLABS = 4, FS_QSTAGES = 2, FS_SBUF = 4;
-constexpr int FS_THREADS = 320;
-constexpr int FS_P_BYTES = FS_MAX_SLABS * FS_SLAB_BYTES;            // 64 KiB
-constexpr int FS_Q_BYTES = FS_MAX_SLABS * FS_SLAB_BYTES;            // 64 KiB per stage
-constexpr int FS_SMEM = FS_P_BYTES + FS_QSTAGES * FS_Q_BYTES + 1024 /*align*/ + 4096 /*bias staging, merge, barriers*/;
+constexpr int FS_SUB = 128, FS_BM = 2 * FS_SUB, FS_BN = 128, FS_SLAB = 64 /*fp16 per 128-byte row*/;
+constexpr int FS_SLAB_BYTES = 128 * 128, FS_MAX_SLABS = 2, FS_QSTAGES = 3, FS_SBUF = 4;
+constexpr int FS_THREADS = 64 + 4 * 128;   // TMA warp, MMA warp, four softmax warpgroups
+constexpr int FS_P_BYTES = 2 * FS_MAX_SLABS * FS_SLAB_BYTES;       // 64 KiB: two 128-row sub-blocks
+constexpr int FS_Q_BYTES = FS_MAX_SLABS * FS_SLAB_BYTES;            // 32 KiB per stage
+constexpr int FS_SMEM = FS_P_BYTES + FS_QSTAGES * FS_Q_BYTES + 1024 /*align*/ + 4096 /*bias staging, barriers*/;
 constexpr float FS_NEG = -1.0e30f;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
@@ -38,23 +40,24 @@ __device__ __forceinline__ float ex2(float x) {
 }
 __device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// Operands are FP16 planes of the points divided by sigma = max |coordinate| (10-bit mantissa, the same rounding as
+// TF32, at twice the tensor rate and half the bytes); *sig2 = sigma^2 rescales the dot products.
 // out: part_m / part_l [split][Np] (base-2 max and sum of 2^(t - max)); COST also part_c = sum 2^(t-max) (nq_q - 2 p.q)
 template <bool COST>
 __global__ void __launch_bounds__(FS_THREADS, 1)
 fused_lse_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ,
-                 const float* __restrict__ bias2, const float* __restrict__ nq, float g2, int Np, int Nq, int dim,
-                 int tiles_per_split, float* __restrict__ part_m, float* __restrict__ part_l, float* __restrict__ part_c,
-                 const FsState* __restrict__ state) {
+                 const float* __restrict__ bias2, const float* __restrict__ nq, float g2_unit,
+                 const float* __restrict__ sig2, int Np, int Nq, int dim, int tiles_per_split, float* __restrict__ part_m,
+                 float* __restrict__ part_l, float* __restrict__ part_c, const FsState* __restrict__ state) {
   using namespace ptx;
   if (state && state->done) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sP = smem;
-  uint8_t* sQ = smem + FS_P_BYTES;
-  float* s_bias = reinterpret_cast<float*>(smem + FS_P_BYTES + FS_QSTAGES * FS_Q_BYTES);   // [2 wg][128]
-  float* s_nq = s_bias + 256;                                                                // [2 wg][128]
-  float* s_merge = s_nq + 256;                                                               // [3][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_merge + 384);
+  uint8_t* sP = smem;                                   // [sub][slab][128 rows x 128 B]
+  uint8_t* sQ = smem + FS_P_BYTES;                      // [stage][slab][128 rows x 128 B]
+  float* s_bias = reinterpret_cast<float*>(smem + FS_P_BYTES + FS_QSTAGES * FS_Q_BYTES);   // [4 groups][64]
+  float* s_nq = s_bias + 256;                                                                // [4 groups][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_nq + 256);
   uint64_t* p_full = bars;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = q_full + FS_QSTAGES;
@@ -68,13 +71,14 @@ fused_lse_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
   const int jt0 = split * tiles_per_split;
   const int jt1 = min(total_tiles, jt0 + tiles_per_split);
   const int n_tiles = max(0, jt1 - jt0);
-  const int nks = (dim + 31) / 32;
+  const int nks = (dim + FS_SLAB - 1) / FS_SLAB;
+  const float g2 = g2_unit * (*sig2);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapP); tma_prefetch_desc(&mapQ);
     mbar_init(p_full, 1);
     for (int s = 0; s < FS_QSTAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    for (int b = 0; b < FS_SBUF; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128); }
+    for (int b = 0; b < FS_SBUF; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 256); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -85,115 +89,107 @@ fused_lse_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(p_full, (uint32_t)nks * FS_SLAB_BYTES);
-      for (int sl = 0; sl < nks; ++sl) tma_load_3d(sP + sl * FS_SLAB_BYTES, &mapP, sl * 32, pb * FS_BM, 0, p_full);
+      mbar_arrive_expect_tx(p_full, (uint32_t)(2 * nks) * FS_SLAB_BYTES);
+      for (int sub = 0; sub < 2; ++sub)
+        for (int sl = 0; sl < nks; ++sl)
+          tma_load_2d(sP + (sub * FS_MAX_SLABS + sl) * FS_SLAB_BYTES, &mapP, sl * FS_SLAB, pb * FS_BM + sub * FS_SUB, p_full);
       for (int idx = 0; idx < n_tiles; ++idx) {
         const int s = idx % FS_QSTAGES, it = idx / FS_QSTAGES;
         mbar_wait(&q_empty[s], (it & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[s], (uint32_t)nks * FS_SLAB_BYTES);
         for (int sl = 0; sl < nks; ++sl)
-          tma_load_3d(sQ + s * FS_Q_BYTES + sl * FS_SLAB_BYTES, &mapQ, sl * 32, (jt0 + idx) * FS_BN, 0, &q_full[s]);
+          tma_load_2d(sQ + s * FS_Q_BYTES + sl * FS_SLAB_BYTES, &mapQ, sl * FS_SLAB, (jt0 + idx) * FS_BN, &q_full[s]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(FS_BM, FS_BN, 0, 0);
+      const uint32_t idesc = idesc_f16(FS_SUB, FS_BN);
       mbar_wait(p_full, 0);
       for (int idx = 0; idx < n_tiles; ++idx) {
-        const int s = idx % FS_QSTAGES, b = idx % FS_SBUF;
+        const int s = idx % FS_QSTAGES, pair = idx % 2;
         mbar_wait(&q_full[s], (idx / FS_QSTAGES) & 1);
-        mbar_wait(&s_empty[b], ((idx / FS_SBUF) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t pbase = smem_u32(sP), qbase = smem_u32(sQ + s * FS_Q_BYTES);
-        for (int sl = 0; sl < nks; ++sl) {
-          const int ksteps = min(4, (dim - sl * 32 + 7) / 8);
+        const uint32_t qbase = smem_u32(sQ + s * FS_Q_BYTES);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int b = 2 * pair + sub;
+          mbar_wait(&s_empty[b], ((idx / 2) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t pbase = smem_u32(sP + sub * FS_MAX_SLABS * FS_SLAB_BYTES);
+          for (int sl = 0; sl < nks; ++sl) {
+            const int ksteps = min(4, (dim - sl * FS_SLAB + 15) / 16);
 #pragma unroll 4
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t pd = smem_desc_sw128(pbase + sl * FS_SLAB_BYTES + kk * 32, 16, 1024);
-            const uint64_t qd = smem_desc_sw128(qbase + sl * FS_SLAB_BYTES + kk * 32, 16, 1024);
-            umma_tf32(tmem_base + b * FS_BN, pd, qd, idesc, (sl | kk) != 0);
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t pd = smem_desc_sw128(pbase + sl * FS_SLAB_BYTES + kk * 32, 16, 1024);
+              const uint64_t qd = smem_desc_sw128(qbase + sl * FS_SLAB_BYTES + kk * 32, 16, 1024);
+              umma_f16(tmem_base + b * FS_BN, pd, qd, idesc, (sl | kk) != 0);
+            }
           }
+          umma_commit(&s_full[b]);
         }
         umma_commit(&q_empty[s]);
-        umma_commit(&s_full[b]);
       }
     }
   } else {
-    // ===== online log-sum-exp: thread <-> row of S, two warpgroups alternate over the tiles =====
-    const int wg = (warp - 2) / 4;
+    // ===== online log-sum-exp: four warpgroups = (P sub-block) x (column half of the Q tile); thread <-> row.
+    // Four softmax warps per SM sub-partition keep the MUFU pipe fed while the others wait on TMEM / the FMA pipe.
+    const int grp = (warp - 2) / 4;                      // 0..3
+    const int sub = grp >> 1, half = grp & 1;
     const int tid = (warp - 2) % 4 * 32 + lane;          // 0..127 inside the warpgroup
     const int q4 = warp % 4;                             // TMEM lane quarter of this warp
-    float* sb = s_bias + wg * 128;
-    float* sn = s_nq + wg * 128;
+    float* sb = s_bias + grp * 64;
+    float* sn = s_nq + grp * 64;
+    const float k2 = COST ? -2.f / g2_unit : 0.f;       // t - bias2 = g2_unit * (x.y)  ->  -2 x.y
     float m = -3.0e38f, l = 0.f, lc = 0.f;
-    for (int idx = wg; idx < n_tiles; idx += 2) {
-      const int b = idx % FS_SBUF;
-      const int qcol = (jt0 + idx) * FS_BN + tid;
-      const float my_bias = qcol < Nq ? bias2[qcol] : FS_NEG;
-      float my_nq = 0.f;
-      if (COST) my_nq = qcol < Nq ? nq[qcol] : 0.f;
-      mbar_wait(&s_full[b], (idx / FS_SBUF) & 1);
+    for (int idx = 0; idx < n_tiles; ++idx) {
+      const int b = 2 * (idx % 2) + sub;
+      const int qcol = (jt0 + idx) * FS_BN + half * 64 + tid;
+      float my_bias = FS_NEG, my_nq = 0.f;
+      if (tid < 64 && qcol < Nq) { my_bias = bias2[qcol]; if (COST) my_nq = nq[qcol]; }
+      named_bar(1 + grp, 128);                           // everyone is done reading the previous tile's staging
+      if (tid < 64) { sb[tid] = my_bias; if (COST) sn[tid] = my_nq; }
+      named_bar(1 + grp, 128);
+      mbar_wait(&s_full[b], (idx / 2) & 1);
       tc_fence_after();
-      named_bar(1 + wg, 128);                            // everyone is done reading the previous tile's staging
-      sb[tid] = my_bias;
-      if (COST) sn[tid] = my_nq;
-      named_bar(1 + wg, 128);
-      // software pipeline over the four 32-column chunks: the TMEM load of chunk c+1 is in flight while chunk c is reduced
-      const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * FS_BN;
-      float va[32], vb[32];
-      tmem_ld32(trow, va);
+      const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * FS_BN + half * 64;
+      float v[64];
+      tmem_ld32(trow, v);
+      tmem_ld32(trow + 32, v + 32);
       tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float* v = (c & 1) ? vb : va;
-        float* vnext = (c & 1) ? va : vb;
-        if (c < 3) tmem_ld32(trow + (c + 1) * 32, vnext);
-        const int c0 = c * 32;
-        float cmax = -3.0e38f;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + j);
-          v[j] = fmaf(v[j], g2, bb.x); v[j + 1] = fmaf(v[j + 1], g2, bb.y);
-          v[j + 2] = fmaf(v[j + 2], g2, bb.z); v[j + 3] = fmaf(v[j + 3], g2, bb.w);
-          cmax = fmaxf(cmax, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
-        }
-        const float m_new = fmaxf(m, cmax);
-        const float rescale = ex2(m - m_new);
-        l *= rescale;
-        if (COST) lc *= rescale;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float e0 = ex2(v[j] - m_new), e1 = ex2(v[j + 1] - m_new), e2 = ex2(v[j + 2] - m_new), e3 = ex2(v[j + 3] - m_new);
-          a0 += e0; a1 += e1; a2 += e2; a3 += e3;
-          if (COST) {
-            // v holds t = g2 * s + bias2: recover the raw dot product s for the cost term
-            const float4 nn = *reinterpret_cast<const float4*>(sn + c0 + j);
-            const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + j);
-            const float ig = 1.f / g2;
-            lc += e0 * fmaf((v[j] - bb.x) * ig, -2.f, nn.x) + e1 * fmaf((v[j + 1] - bb.y) * ig, -2.f, nn.y) +
-                  e2 * fmaf((v[j + 2] - bb.z) * ig, -2.f, nn.z) + e3 * fmaf((v[j + 3] - bb.w) * ig, -2.f, nn.w);
-          }
-        }
-        l += (a0 + a1) + (a2 + a3);
-        m = m_new;
-        if (c < 3) tmem_ld_wait();
-      }
       tc_fence_before();
-      mbar_arrive(&s_empty[b]);
-    }
-    if (wg == 1) { s_merge[tid] = m; s_merge[128 + tid] = l; if (COST) s_merge[256 + tid] = lc; }
-    named_bar(3, 256);
-    if (wg == 0) {
-      const float m1 = s_merge[tid], l1 = s_merge[128 + tid];
-      const float mm = fmaxf(m, m1);
-      const float w0 = ex2(m - mm), w1 = ex2(m1 - mm);
-      const int row = pb * FS_BM + q4 * 32 + lane;
-      if (row < Np) {
-        part_m[(int64_t)split * Np + row] = mm;
-        part_l[(int64_t)split * Np + row] = l * w0 + l1 * w1;
-        if (COST) part_c[(int64_t)split * Np + row] = lc * w0 + s_merge[256 + tid] * w1;
+      mbar_arrive(&s_empty[b]);                          // the accumulator buffer can be refilled already
+      float cm0 = -3.0e38f, cm1 = -3.0e38f, cm2 = -3.0e38f, cm3 = -3.0e38f;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(sb + j);
+        v[j] = fmaf(v[j], g2, bb.x); v[j + 1] = fmaf(v[j + 1], g2, bb.y);
+        v[j + 2] = fmaf(v[j + 2], g2, bb.z); v[j + 3] = fmaf(v[j + 3], g2, bb.w);
+        cm0 = fmaxf(cm0, v[j]); cm1 = fmaxf(cm1, v[j + 1]); cm2 = fmaxf(cm2, v[j + 2]); cm3 = fmaxf(cm3, v[j + 3]);
       }
+      const float m_new = fmaxf(fmaxf(m, fmaxf(cm0, cm1)), fmaxf(cm2, cm3));
+      const float rescale = ex2(m - m_new);
+      l *= rescale;
+      if (COST) lc *= rescale;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const float e0 = ex2(v[j] - m_new), e1 = ex2(v[j + 1] - m_new), e2 = ex2(v[j + 2] - m_new), e3 = ex2(v[j + 3] - m_new);
+        a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+        if (COST) {
+          const float4 nn = *reinterpret_cast<const float4*>(sn + j);
+          const float4 bb = *reinterpret_cast<const float4*>(sb + j);
+          lc += e0 * fmaf(v[j] - bb.x, k2, nn.x) + e1 * fmaf(v[j + 1] - bb.y, k2, nn.y) +
+                e2 * fmaf(v[j + 2] - bb.z, k2, nn.z) + e3 * fmaf(v[j + 3] - bb.w, k2, nn.w);
+        }
+      }
+      l += (a0 + a1) + (a2 + a3);
+      m = m_new;
+    }
+    const int row = pb * FS_BM + sub * FS_SUB + q4 * 32 + lane;
+    if (row < Np) {
+      const int64_t part = (int64_t)split * 2 + half;
+      part_m[part * Np + row] = m;
+      part_l[part * Np + row] = l;
+      if (COST) part_c[part * Np + row] = lc;
     }
   }
   __syncthreads();
@@ -201,16 +197,29 @@ fused_lse_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
 }
 
 // ---- small kernels ----------------------------------------------------------------------------------------------
-// hi plane (TF32-rounded points, the tensor-core operands) and squared norms of the ORIGINAL points (exact norms keep
+// sigma = max |coordinate| over a cloud (atomicMax on the bit pattern of a non-negative float)
+__global__ void fs_absmax_kernel(const float* __restrict__ x, int64_t n, float* out) {
+  float mx = 0.f;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) mx = fmaxf(mx, fabsf(x[e]));
+  mx = warp_max(mx);
+  if (threadIdx.x % 32 == 0) atomicMax(reinterpret_cast<unsigned*>(out), __float_as_uint(mx));
+}
+__global__ void fs_sigma_kernel(float* sig) {   // sig[0] = sigma (>= tiny), sig[1] = sigma^2, sig[2] = 1/sigma
+  const float s = fmaxf(sig[0], 1e-30f);
+  sig[0] = s; sig[1] = s * s; sig[2] = 1.f / s;
+}
+// FP16 operand plane x / sigma (the tensor-core operands) and squared norms of the ORIGINAL points (exact norms keep
 // the rounding of the cross term zero-mean along both axes, so it averages out of the marginals); one warp per point
-__global__ void fs_prep_kernel(const float* __restrict__ x, int64_t n, int64_t d, float* __restrict__ hi, float* __restrict__ sq) {
+__global__ void fs_prep_kernel(const float* __restrict__ x, int64_t n, int64_t d, const float* __restrict__ sig,
+                               __half* __restrict__ hi, float* __restrict__ sq) {
   const int lane = threadIdx.x % 32;
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
   if (row >= n) return;
+  const float inv = sig[2];
   float acc = 0.f;
   for (int64_t k = lane; k < d; k += 32) {
     const float xv = x[row * d + k];
-    hi[row * d + k] = ptx::tf32_rna(xv);
+    hi[row * d + k] = __float2half_rn(xv * inv);
     acc = fmaf(xv, xv, acc);
   }
   acc = warp_sum(acc);
@@ -314,43 +323,48 @@ __global__ void fs_summary_kernel(const float* __restrict__ pm, const float* __r
 
 // ---- host side --------------------------------------------------------------------------------------------------
 bool sk_umma_eligible(int64_t N, int64_t M, int64_t dim, int cost_kind) {
-  return cost_kind == OTK_COST_SQEUCLIDEAN && dim >= 8 && dim <= 128 && dim % 4 == 0 && N >= 1 && M >= 1 &&
+  return cost_kind == OTK_COST_SQEUCLIDEAN && dim >= 8 && dim <= 128 && dim % 8 == 0 && N >= 1 && M >= 1 &&
          N < (1ll << 30) && M < (1ll << 30) && tensormap_encoder() != nullptr;
+}
+
+static unsigned fs_grid(int64_t n) {
+  int64_t b = ceil_div(n, 256), cap = (int64_t)sm_count() * 4;
+  return (unsigned)(b < cap ? (b ? b : 1) : cap);
 }
 
 static int fs_splits(int64_t p_rows, int64_t q_rows) {
   const int64_t pblocks = ceil_div(p_rows, FS_BM), qtiles = ceil_div(q_rows, FS_BN);
   int64_t want = ceil_div((int64_t)sm_count() * 6, pblocks);       // ~6 waves of CTAs
   if (want > qtiles) want = qtiles;
-  if (want > 64) want = 64;
+  if (want > 32) want = 32;
   if (want < 1) want = 1;
   return (int)want;
 }
 
 struct FsSide {           // one point cloud, prepared
-  const float* raw; float* hi; float* sq; int64_t n;
+  const float* raw; __half* hi; float* sq; int64_t n;
   CUtensorMap map;
 };
 
 struct FsWork {
   FsSide X, Y;
-  float *biasX2, *biasY2, *pm, *pl, *pc, *diff, *scratch_n;
+  float *biasX2, *biasY2, *pm, *pl, *pc, *diff, *scratch_n, *sig;
   FsState* state;
   int max_parts;
 };
 
 size_t sk_umma_workspace_bytes(int64_t N, int64_t M, int64_t dim) {
   const int64_t mx = N > M ? N : M;
-  return align_up((size_t)N * dim * 4, 256) + align_up((size_t)M * dim * 4, 256) + 6 * align_up((size_t)mx * 4, 256) +
-         3 * align_up((size_t)64 * mx * 4, 256) + 4096;
+  return align_up((size_t)N * dim * 2, 256) + align_up((size_t)M * dim * 2, 256) + 6 * align_up((size_t)mx * 4, 256) +
+         3 * align_up((size_t)64 * mx * 4, 256) + 8192;
 }
 
 static int fs_carve(FsWork& w, const float* x, const float* y, int64_t N, int64_t M, int64_t dim, void* workspace,
                     size_t workspace_bytes, cudaStream_t st) {
   Arena ar(workspace, workspace_bytes);
   const int64_t mx = N > M ? N : M;
-  w.X = FsSide{x, ar.take<float>((size_t)N * dim), ar.take<float>((size_t)N), N, {}};
-  w.Y = FsSide{y, ar.take<float>((size_t)M * dim), ar.take<float>((size_t)M), M, {}};
+  w.X = FsSide{x, ar.take<__half>((size_t)N * dim), ar.take<float>((size_t)N), N, {}};
+  w.Y = FsSide{y, ar.take<__half>((size_t)M * dim), ar.take<float>((size_t)M), M, {}};
   w.biasX2 = ar.take<float>((size_t)N);
   w.biasY2 = ar.take<float>((size_t)M);
   w.scratch_n = ar.take<float>((size_t)mx);
@@ -359,15 +373,20 @@ static int fs_carve(FsWork& w, const float* x, const float* y, int64_t N, int64_
   w.pl = ar.take<float>((size_t)64 * mx);
   w.pc = ar.take<float>((size_t)64 * mx);
   w.diff = ar.take<float>(64);
+  w.sig = ar.take<float>(64);
   w.state = ar.take<FsState>(1);
   if (!ar.ok()) return OTK_ERR_WORKSPACE;
-  fs_prep_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(x, N, dim, w.X.hi, w.X.sq);
-  fs_prep_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, dim, w.Y.hi, w.Y.sq);
-  count_launch(1);
+  OTK_CUDA(cudaMemsetAsync(w.sig, 0, 16, st));
+  fs_absmax_kernel<<<fs_grid(N * dim), 256, 0, st>>>(x, N * dim, w.sig);
+  fs_absmax_kernel<<<fs_grid(M * dim), 256, 0, st>>>(y, M * dim, w.sig);
+  fs_sigma_kernel<<<1, 1, 0, st>>>(w.sig);
+  fs_prep_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(x, N, dim, w.sig, w.X.hi, w.X.sq);
+  fs_prep_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, dim, w.sig, w.Y.hi, w.Y.sq);
+  count_launch(4);
   OTK_LAUNCH_CHECK();
-  // 2-D maps [rows, dim], box 32 x 128, 128B swizzle (K-major operands)
-  if (!encode_map_f32_3d(&w.X.map, w.X.hi, dim, N, 1, dim, N * dim, 32, FS_BM)) return OTK_ERR_CUDA;
-  if (!encode_map_f32_3d(&w.Y.map, w.Y.hi, dim, M, 1, dim, M * dim, 32, FS_BM)) return OTK_ERR_CUDA;
+  // 2-D fp16 maps [rows, dim], box 64 x 128, 128B swizzle (K-major operands)
+  if (!encode_map_f16_2d(&w.X.map, w.X.hi, dim, N, dim, FS_SLAB, FS_SUB)) return OTK_ERR_CUDA;
+  if (!encode_map_f16_2d(&w.Y.map, w.Y.hi, dim, M, dim, FS_SLAB, FS_SUB)) return OTK_ERR_CUDA;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -381,23 +400,18 @@ static int fs_carve(FsWork& w, const float* x, const float* y, int64_t N, int64_
 
 // one pass: partials of LSE_q(bias2_q + g2 * p.q) for every row of P; returns the number of parts written
 template <bool COST>
-static int fs_pass(const FsSide& P, const FsSide& Q, const float* biasQ2, float g2, int64_t dim, float* pm, float* pl,
-                   float* pc, const FsState* state, int* parts_out, cudaStream_t st) {
+static int fs_pass(const FsSide& P, const FsSide& Q, const float* biasQ2, float g2, const float* sig2, int64_t dim, float* pm,
+                   float* pl, float* pc, const FsState* state, int* parts_out, cudaStream_t st) {
   const int splits = fs_splits(P.n, Q.n);
   const int64_t qtiles = ceil_div(Q.n, FS_BN);
   const int tps = (int)ceil_div(qtiles, splits);
   const int parts = (int)ceil_div(qtiles, tps);
   dim3 grid((unsigned)ceil_div(P.n, FS_BM), (unsigned)parts);
-  fused_lse_kernel<COST><<<grid, FS_THREADS, FS_SMEM, st>>>(P.map, Q.map, biasQ2, Q.sq, g2, (int)P.n, (int)Q.n, (int)dim,
-                                                          tps, pm, pl, pc, state);
+  fused_lse_kernel<COST><<<grid, FS_THREADS, FS_SMEM, st>>>(P.map, Q.map, biasQ2, Q.sq, g2, sig2, (int)P.n, (int)Q.n,
+                                                          (int)dim, tps, pm, pl, pc, state);
   OTK_LAUNCH_CHECK();
-  *parts_out = parts;
+  *parts_out = 2 * parts;   // two column halves per split
   return OTK_OK;
-}
-
-static unsigned fs_grid(int64_t n) {
-  int64_t b = ceil_div(n, 256), cap = (int64_t)sm_count() * 4;
-  return (unsigned)(b < cap ? (b ? b : 1) : cap);
 }
 
 // max_ij |x_i - y_j|^2 on the device -> *out_dev (one fused pass with g2 = -2, bias = |y|^2: the running max is the answer)
@@ -405,7 +419,7 @@ static int fs_cost_max(FsWork& w, int64_t dim, float* out_dev, cudaStream_t st) 
   int parts = 0;
   fs_bias_kernel<<<fs_grid(w.Y.n), 256, 0, st>>>(nullptr, w.Y.sq, -1.f / LOG2E, w.Y.n, w.biasY2);  // bias2 = +|y|^2
   // the LSE pass maximises bias2 + g2 * s ; we need max(|y|^2 - 2 x.y): g2 = -2
-  OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, -2.f, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
+  OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, -2.f, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
   fs_finalize_kernel<<<fs_grid(w.X.n), 256, 0, st>>>(w.pm, w.pl, parts, w.X.n, 2, nullptr, w.X.sq, 0.f, nullptr, nullptr,
                                                     w.scratch_n, nullptr, nullptr, nullptr);
   OTK_CUDA(cudaMemsetAsync(out_dev, 0, 4, st));
@@ -450,10 +464,10 @@ int sk_umma_solve(const float* x, const float* y, int64_t N, int64_t M, int64_t 
   int parts = 0;
   for (int it = 0; it < max_iter; ++it) {
     // v first: rows = Y, reduce over X (bias from u) ; then u: rows = X, reduce over Y (bias from the new v)
-    OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, dim, w.pm, w.pl, w.pc, w.state, &parts, st));
+    OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, w.state, &parts, st));
     fs_finalize_kernel<<<fs_grid(M), 256, 0, st>>>(w.pm, w.pl, parts, M, 0, b, w.Y.sq, nrm_scale, v, w.biasY2, nullptr, nullptr,
                                                   w.diff + 1, w.state);
-    OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, dim, w.pm, w.pl, w.pc, w.state, &parts, st));
+    OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, w.state, &parts, st));
     fs_finalize_kernel<<<fs_grid(N), 256, 0, st>>>(w.pm, w.pl, parts, N, 0, a, w.X.sq, nrm_scale, u, w.biasX2, nullptr, nullptr,
                                                   w.diff, w.state);
     fs_check_kernel<<<1, 1, 0, st>>>(w.diff, threshold, w.state);
@@ -467,9 +481,9 @@ int sk_umma_solve(const float* x, const float* y, int64_t N, int64_t M, int64_t 
   }
   if (summary) {
     OTK_CUDA(cudaMemsetAsync(summary, 0, 4 * sizeof(double), st));
-    OTK_TRY(fs_pass<true>(w.X, w.Y, w.biasY2, g2, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
+    OTK_TRY(fs_pass<true>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
     fs_summary_kernel<<<fs_grid(N), 256, 0, st>>>(w.pm, w.pl, w.pc, parts, N, u, w.X.sq, nrm_scale, (float)scale, a, summary, 2, row_marginal);
-    OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
+    OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
     fs_summary_kernel<<<fs_grid(M), 256, 0, st>>>(w.pm, w.pl, nullptr, parts, M, v, w.Y.sq, nrm_scale, (float)scale, b, summary, 3, col_marginal);
     count_launch(1);
     OTK_LAUNCH_CHECK();
@@ -497,7 +511,7 @@ int sk_umma_colstep(const float* x_local, const float* y, int64_t n_local, int64
   const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
   fs_bias_kernel<<<fs_grid(n_local), 256, 0, st>>>(u_local, w.X.sq, nrm_scale, n_local, w.biasX2);
   int parts = 0;
-  OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
+  OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
   // partial over the LOCAL rows of LSE_i(u_i + Cr_ij) = -nrm_j + LSE_i(bias_i + gamma x_i.y_j), natural log
   fs_finalize_kernel<<<fs_grid(M), 256, 0, st>>>(w.pm, w.pl, parts, M, 1, nullptr, nullptr, 0.f, nullptr, nullptr, col_max, col_sum,
                                                 nullptr, nullptr);
@@ -539,7 +553,7 @@ int sk_umma_rowstep(const float* x_local, const float* y, int64_t n_local, int64
   const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
   fs_bias_kernel<<<fs_grid(M), 256, 0, st>>>(v, w.Y.sq, nrm_scale, M, w.biasY2);
   int parts = 0;
-  OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
+  OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
   fs_rowstep_finish_kernel<<<fs_grid(n_local), 256, 0, st>>>(w.pm, w.pl, parts, n_local, a_local, w.X.sq, nrm_scale, u_local, diff);
   count_launch(1);
   OTK_LAUNCH_CHECK();

@@ -42,4 +42,19 @@ inline bool encode_map_f32_3d(CUtensorMap* map, const float* base, int64_t cols,
   return r == CUDA_SUCCESS;
 }
 
+// fp16 tensor [rows][cols] (cols contiguous, row stride `ld` elements); box = box_cols x box_rows, 128-byte swizzle
+inline bool encode_map_f16_2d(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols,
+                              int box_rows) {
+  TensorMapEncodeTiledFn enc = tensormap_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace otk
