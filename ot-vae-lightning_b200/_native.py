@@ -74,6 +74,10 @@ class NativeError(RuntimeError):
     pass
 
 
+class NotConverged(NativeError):
+    """An iterative kernel (Newton-Schulz) did not converge: the input is not positive definite."""
+
+
 def declared_symbols(header: str = HEADER_PATH):
     """Function names declared in include/otk.h."""
     with open(header) as f:
@@ -109,6 +113,8 @@ def check(status: int, what: str) -> None:
     detail = lib.otk_last_error().decode() or lib.otk_status_string(status).decode()
     if status in (ERR_INVALID, ERR_WORKSPACE):
         raise ValueError(f"{what}: {detail}")
+    if status == ERR_NOT_CONVERGED:
+        raise NotConverged(f"{what}: {detail}")
     raise NativeError(f"{what}: {lib.otk_status_string(status).decode()} ({detail})")
 
 

@@ -15,35 +15,40 @@
 
 namespace otk {
 
-constexpr int AP_BM = 128, AP_BN = 128, AP_BK = 32, AP_STAGES = 3, AP_THREADS = 192;
+constexpr int AP_BM = 128, AP_BN = 128, AP_BK = 32, AP_STAGES = 3, AP_THREADS = 320, AP_ACC = 2;
 constexpr int AP_TILE = AP_BM * AP_BK * 4;          // 16 KiB
 constexpr int AP_STAGE = 4 * AP_TILE;               // X hi (raw in place), X lo, T hi, T lo
 constexpr int AP_SMEM = AP_STAGES * AP_STAGE + 1024 + 256;
 
+// Persistent: one CTA per SM walks the (row tile, column tile) list; the smem ring keeps streaming across tiles and the
+// two TMEM accumulators let the epilogue of tile i overlap the main loop of tile i+1.
+// warp 0 TMA producer | warp 1 TMEM alloc + MMA issuer | warps 2-5 converter | warps 6-9 epilogue
 __global__ void __launch_bounds__(AP_THREADS, 1)
 apply_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT_hi,
                   const __grid_constant__ CUtensorMap mapT_lo, const float* __restrict__ mean_s,
-                  const float* __restrict__ mean_t, float* __restrict__ y, int rows, int dim) {
+                  const float* __restrict__ mean_t, float* __restrict__ y, int rows, int dim, int m_tiles, int n_tiles,
+                  int total_tiles) {
   using namespace ptx;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + AP_STAGES * AP_STAGE);   // TMA landed
   uint64_t* ready = full + AP_STAGES;                                           // converted, MMA may read
   uint64_t* empty = ready + AP_STAGES;                                          // MMA done with the stage
-  uint64_t* tmem_full = empty + AP_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* acc_full = empty + AP_STAGES;                                       // accumulator complete
+  uint64_t* acc_empty = acc_full + AP_ACC;                                      // accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + AP_ACC);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int m0 = blockIdx.x * AP_BM, n0 = blockIdx.y * AP_BN, l = blockIdx.z;
   const int num_k = (dim + AP_BK - 1) / AP_BK;
+  const int tiles_per_l = m_tiles * n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapT_hi); tma_prefetch_desc(&mapT_lo);
     for (int s = 0; s < AP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < AP_ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, AP_BN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, AP_ACC * AP_BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -51,104 +56,127 @@ apply_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % AP_STAGES, it = kt / AP_STAGES;
-        mbar_wait(&empty[s], (it & 1) ^ 1);
-        uint8_t* st = smem + s * AP_STAGE;
-        mbar_arrive_expect_tx(&full[s], 3u * AP_TILE);
-        tma_load_3d(st, &mapX, kt * AP_BK, m0, l, &full[s]);
-        tma_load_3d(st + 2 * AP_TILE, &mapT_hi, kt * AP_BK, n0, l, &full[s]);
-        tma_load_3d(st + 3 * AP_TILE, &mapT_lo, kt * AP_BK, n0, l, &full[s]);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
+        const int m0 = (rem / n_tiles) * AP_BM, n0 = (rem % n_tiles) * AP_BN;
+        for (int kt = 0; kt < num_k; ++kt, ++it) {
+          const int s = it % AP_STAGES;
+          mbar_wait(&empty[s], ((it / AP_STAGES) & 1) ^ 1);
+          uint8_t* st = smem + s * AP_STAGE;
+          mbar_arrive_expect_tx(&full[s], 3u * AP_TILE);
+          tma_load_3d(st, &mapX, kt * AP_BK, m0, l, &full[s]);
+          tma_load_3d(st + 2 * AP_TILE, &mapT_hi, kt * AP_BK, n0, l, &full[s]);
+          tma_load_3d(st + 3 * AP_TILE, &mapT_lo, kt * AP_BK, n0, l, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(AP_BM, AP_BN, 0, 0);
-      for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % AP_STAGES, it = kt / AP_STAGES;
-        mbar_wait(&ready[s], it & 1);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int a = ti % AP_ACC;
+        mbar_wait(&acc_empty[a], ((ti / AP_ACC) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * AP_STAGE);
+        const uint32_t acc = tmem_base + a * AP_BN;
+        for (int kt = 0; kt < num_k; ++kt, ++it) {
+          const int s = it % AP_STAGES;
+          mbar_wait(&ready[s], (it / AP_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * AP_STAGE);
 #pragma unroll
-        for (int kk = 0; kk < AP_BK / 8; ++kk) {
-          const uint64_t x_hi = smem_desc_sw128(base + kk * 32, 16, 1024);
-          const uint64_t x_lo = smem_desc_sw128(base + AP_TILE + kk * 32, 16, 1024);
-          const uint64_t t_hi = smem_desc_sw128(base + 2 * AP_TILE + kk * 32, 16, 1024);
-          const uint64_t t_lo = smem_desc_sw128(base + 3 * AP_TILE + kk * 32, 16, 1024);
-          umma_tf32(tmem_base, x_lo, t_hi, idesc, (kt | kk) != 0);
-          umma_tf32(tmem_base, x_hi, t_lo, idesc, 1);
-          umma_tf32(tmem_base, x_hi, t_hi, idesc, 1);
+          for (int kk = 0; kk < AP_BK / 8; ++kk) {
+            const uint64_t x_hi = smem_desc_sw128(base + kk * 32, 16, 1024);
+            const uint64_t x_lo = smem_desc_sw128(base + AP_TILE + kk * 32, 16, 1024);
+            const uint64_t t_hi = smem_desc_sw128(base + 2 * AP_TILE + kk * 32, 16, 1024);
+            const uint64_t t_lo = smem_desc_sw128(base + 3 * AP_TILE + kk * 32, 16, 1024);
+            umma_tf32(acc, x_lo, t_hi, idesc, (kt | kk) != 0);
+            umma_tf32(acc, x_hi, t_lo, idesc, 1);
+            umma_tf32(acc, x_hi, t_hi, idesc, 1);
+          }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&acc_full[a]);
       }
-      umma_commit(tmem_full);
     }
-  } else {
+  } else if (warp < 6) {
     // ===== converter: thread r owns row r of the 128 x 32 tile (eight 16-byte chunks, XOR-swizzled by r % 8) =====
     const int r = (warp - 2) * 32 + lane;
-    const float* ms = mean_s + (int64_t)l * dim;
-    for (int kt = 0; kt < num_k; ++kt) {
-      const int s = kt % AP_STAGES, it = kt / AP_STAGES;
-      mbar_wait(&full[s], it & 1);
-      uint8_t* hi_row = smem + s * AP_STAGE + r * 128;
-      uint8_t* lo_row = hi_row + AP_TILE;
-      const int k0 = kt * AP_BK;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int l = tile / tiles_per_l;
+      const float* ms = mean_s + (int64_t)l * dim;
+      for (int kt = 0; kt < num_k; ++kt, ++it) {
+        const int s = it % AP_STAGES;
+        mbar_wait(&full[s], (it / AP_STAGES) & 1);
+        uint8_t* hi_row = smem + s * AP_STAGE + r * 128;
+        uint8_t* lo_row = hi_row + AP_TILE;
+        const int k0 = kt * AP_BK;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int phys = (c ^ (r & 7)) * 16;
-        float4 x = *reinterpret_cast<const float4*>(hi_row + phys);
-        const int k = k0 + c * 4;
-        float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k + 3 < dim) mu = *reinterpret_cast<const float4*>(ms + k);
-        else {
-          if (k < dim) mu.x = ms[k];
-          if (k + 1 < dim) mu.y = ms[k + 1];
-          if (k + 2 < dim) mu.z = ms[k + 2];
+        for (int c = 0; c < 8; ++c) {
+          const int phys = (c ^ (r & 7)) * 16;
+          float4 x = *reinterpret_cast<const float4*>(hi_row + phys);
+          const int k = k0 + c * 4;
+          float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k + 3 < dim) mu = *reinterpret_cast<const float4*>(ms + k);
+          else {
+            if (k < dim) mu.x = ms[k];
+            if (k + 1 < dim) mu.y = ms[k + 1];
+            if (k + 2 < dim) mu.z = ms[k + 2];
+          }
+          float4 h, lo;
+          split_tf32(x.x - mu.x, h.x, lo.x);
+          split_tf32(x.y - mu.y, h.y, lo.y);
+          split_tf32(x.z - mu.z, h.z, lo.z);
+          split_tf32(x.w - mu.w, h.w, lo.w);
+          *reinterpret_cast<float4*>(hi_row + phys) = h;
+          *reinterpret_cast<float4*>(lo_row + phys) = lo;
         }
-        float4 h, lo;
-        split_tf32(x.x - mu.x, h.x, lo.x);
-        split_tf32(x.y - mu.y, h.y, lo.y);
-        split_tf32(x.z - mu.z, h.z, lo.z);
-        split_tf32(x.w - mu.w, h.w, lo.w);
-        *reinterpret_cast<float4*>(hi_row + phys) = h;
-        *reinterpret_cast<float4*>(lo_row + phys) = lo;
+        fence_proxy_async_smem();   // make the generic-proxy writes visible to the tensor core (async proxy)
+        mbar_arrive(&ready[s]);
       }
-      fence_proxy_async_smem();   // make the generic-proxy writes visible to the tensor core (async proxy)
-      mbar_arrive(&ready[s]);
     }
-    // ===== epilogue =====
+  } else {
+    // ===== epilogue: TMEM -> + mean_t -> global; overlaps the next tile's main loop =====
     const int q = warp % 4;
-    const int m = m0 + q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const float* mt = mean_t + (int64_t)l * dim;
-    float* yl = y + (int64_t)l * rows * dim;
     const bool vec_ok = (dim % 4 == 0);
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
+      const int m0 = (rem / n_tiles) * AP_BM, n0 = (rem % n_tiles) * AP_BN;
+      const int a = ti % AP_ACC;
+      const int m = m0 + q * 32 + lane;
+      const float* mt = mean_t + (int64_t)l * dim;
+      float* dst = y + ((int64_t)l * rows + m) * dim;
+      mbar_wait(&acc_full[a], (ti / AP_ACC) & 1);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < AP_BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      if (m < rows) {
-        float* dst = yl + (int64_t)m * dim;
+      for (int c0 = 0; c0 < AP_BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * AP_BN + c0, v);
+        tmem_ld_wait();
+        if (m < rows) {
 #pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const int n = n0 + c0 + j4;
-          if (vec_ok && n + 3 < dim) {
-            const float4 b = *reinterpret_cast<const float4*>(mt + n);
-            *reinterpret_cast<float4*>(dst + n) = make_float4(v[j4] + b.x, v[j4 + 1] + b.y, v[j4 + 2] + b.z, v[j4 + 3] + b.w);
-          } else {
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const int n = n0 + c0 + j4;
+            if (vec_ok && n + 3 < dim) {
+              const float4 b = *reinterpret_cast<const float4*>(mt + n);
+              *reinterpret_cast<float4*>(dst + n) = make_float4(v[j4] + b.x, v[j4 + 1] + b.y, v[j4 + 2] + b.z, v[j4 + 3] + b.w);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < dim) dst[n + j] = v[j4 + j] + mt[n + j];
+              for (int j = 0; j < 4; ++j)
+                if (n + j < dim) dst[n + j] = v[j4 + j] + mt[n + j];
+            }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[a]);
     }
-    tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, AP_BN); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, AP_ACC * AP_BN); }
 }
 
 __global__ void split_matrix_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
@@ -183,9 +211,12 @@ int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const f
     OTK_CUDA(cudaFuncSetAttribute(apply_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM));
     attr_set[dev] = true;
   }
-  dim3 grid((unsigned)ceil_div(rows, AP_BM), (unsigned)ceil_div(dim, AP_BN), (unsigned)L);
-  if (grid.y > 65535) return 0;
-  apply_umma_kernel<<<grid, AP_THREADS, AP_SMEM, st>>>(mX, mTh, mTl, ms32, mt32, y, (int)rows, (int)dim);
+  const int64_t m_tiles = ceil_div(rows, AP_BM), n_tiles = ceil_div(dim, AP_BN);
+  const int64_t total = L * m_tiles * n_tiles;
+  if (total > INT32_MAX) return 0;
+  const unsigned grid = (unsigned)(total < sm_count() ? total : sm_count());
+  apply_umma_kernel<<<grid, AP_THREADS, AP_SMEM, st>>>(mX, mTh, mTl, ms32, mt32, y, (int)rows, (int)dim, (int)m_tiles,
+                                                      (int)n_tiles, (int)total);
   OTK_LAUNCH_CHECK();
   return 1;
 }

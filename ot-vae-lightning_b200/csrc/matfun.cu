@@ -419,7 +419,12 @@ extern "C" int otk_sqrtm(const void* a, int64_t L, int64_t dim, int dtype, doubl
     const bool accurate = verdict == NS_CONVERGED && (!iroot || used <= NS_F32_IROOT_ITERS);
     if (accurate || polish < 0 || iters > 0) return OTK_OK;
   }
-  return sqrtm_impl<double>(a, L, dim, dtype, ridge, iters, root, iroot, workspace, workspace_bytes, &verdict, &used, st);
+  OTK_TRY(sqrtm_impl<double>(a, L, dim, dtype, ridge, iters, root, iroot, workspace, workspace_bytes, &verdict, &used, st));
+  if (verdict != NS_CONVERGED && iters <= 0) {
+    set_last_error_msg("sqrtm: Newton-Schulz did not converge (the matrix is not positive definite)");
+    return OTK_ERR_NOT_CONVERGED;
+  }
+  return OTK_OK;
 }
 
 extern "C" int otk_w2_gaussian(const void* mean_s, const void* mean_t, const void* cov_s, const void* cov_t, int64_t L,
@@ -435,7 +440,12 @@ extern "C" int otk_w2_gaussian(const void* mean_s, const void* mean_t, const voi
     OTK_TRY(w2_impl<float>(mean_s, mean_t, cov_s, cov_t, L, dim, dtype, iters, w2, workspace, workspace_bytes, &verdict, st));
     if (verdict == NS_CONVERGED || polish < 0 || iters > 0) return OTK_OK;
   }
-  return w2_impl<double>(mean_s, mean_t, cov_s, cov_t, L, dim, dtype, iters, w2, workspace, workspace_bytes, &verdict, st);
+  OTK_TRY(w2_impl<double>(mean_s, mean_t, cov_s, cov_t, L, dim, dtype, iters, w2, workspace, workspace_bytes, &verdict, st));
+  if (verdict != NS_CONVERGED && iters <= 0) {
+    set_last_error_msg("w2_gaussian: Newton-Schulz did not converge (a covariance is not positive definite)");
+    return OTK_ERR_NOT_CONVERGED;
+  }
+  return OTK_OK;
 }
 
 extern "C" int otk_transport_operator(const void* cov_s, const void* cov_t, int64_t L, int64_t dim, int dtype,
@@ -455,6 +465,11 @@ extern "C" int otk_transport_operator(const void* cov_s, const void* cov_t, int6
     // T = Zp R Zp cancels by a factor cond(Cs): fp32 is only kept while the source root converged quickly
     if ((verdict == NS_CONVERGED && used <= NS_F32_OPERATOR_ITERS) || polish < 0 || iters > 0) return OTK_OK;
   }
-  return operator_impl<double>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, mean_s, mean_t, w2, workspace,
-                               workspace_bytes, &verdict, &used, st);
+  OTK_TRY(operator_impl<double>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, mean_s, mean_t, w2, workspace,
+                                workspace_bytes, &verdict, &used, st));
+  if (verdict != NS_CONVERGED && iters <= 0) {
+    set_last_error_msg("transport_operator: Newton-Schulz did not converge (a covariance is not positive definite)");
+    return OTK_ERR_NOT_CONVERGED;
+  }
+  return OTK_OK;
 }

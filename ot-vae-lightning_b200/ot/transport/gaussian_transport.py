@@ -12,6 +12,8 @@ import torch.nn.utils.parametrize as P
 from torch import Tensor
 
 from ... import kernels as K
+from ..._native import NotConverged
+from ..matrix_utils import STABILITY_CONST
 from ..distribution_models.gaussian_model import GaussianModel
 from ..w2_utils import W2Mixin
 from .base import TransportOperator
@@ -38,6 +40,10 @@ class GaussianTransport(TransportOperator, W2Mixin):
     def compute(self) -> Tensor:
         """Fit both Gaussians, then W2^2 [*leading_shape] and the operators (reference :64-78)."""
         self.fit_models()
+        if not (self.diag or self.stochastic):
+            fast = self._compute_full_deterministic()
+            if fast is not None:
+                return fast
         with P.cached():  # evaluate each `.cov` parametrization once for everything below
             mean_s, mean_t = self.source_model.mean, self.target_model.mean
             cov_s, cov_t = self.source_model.cov, self.target_model.cov
@@ -49,9 +55,31 @@ class GaussianTransport(TransportOperator, W2Mixin):
             # reference's per-call validation (5 eigh, SURVEY A4) cannot fail here
             T, w2 = K.transport_operator(cov_s.to(self.dtype), cov_t.to(self.dtype), pg_star=float(self.pg_star),
                                          mean_s=mean_s.to(self.dtype), mean_t=mean_t.to(self.dtype))
-        self.transport_operator = T.to(device=cov_s.device, dtype=self.dtype)
+        return self._store(T, w2, cov_s.device)
+
+    def _store(self, T: Tensor, w2: Tensor, device) -> Tensor:
+        self.transport_operator = T.to(device=device, dtype=self.dtype)
         self.cov_stochastic_noise = torch.zeros_like(self.transport_operator)
-        return w2.to(cov_s.device)
+        return w2.to(device)
+
+    def _compute_full_deterministic(self):
+        """Fast path of the common case.  Reading `.cov` costs a smallest-eigenvalue solve per model only to learn
+        that a covariance is PD, in which case the parametrization adds exactly 1e-8 I (reference
+        matrix_utils.py:132-139).  The Newton-Schulz solves of the map converge only for PD input, so they are their
+        own certificate: run them on triu-mirror(raw) + 1e-8 I and fall back to the eigenvalue repair (return None)
+        only if they report an indefinite matrix."""
+        sm, tm = self.source_model, self.target_model
+        raw_s, raw_t = sm.parametrizations.cov.original, tm.parametrizations.cov.original
+        if not raw_s.is_cuda:
+            return None
+        eps = torch.full(raw_s.shape[:-2], STABILITY_CONST, dtype=raw_s.dtype, device=raw_s.device)
+        cov_s, cov_t = K.symmetrize_shift(raw_s, eps), K.symmetrize_shift(raw_t, eps)
+        try:
+            T, w2 = K.transport_operator(cov_s.to(self.dtype), cov_t.to(self.dtype), pg_star=float(self.pg_star),
+                                         mean_s=sm.mean.to(self.dtype), mean_t=tm.mean.to(self.dtype))
+        except NotConverged:
+            return None
+        return self._store(T, w2, raw_s.device)
 
     def transport(self, inputs: Tensor) -> Tensor:
         """[*leading_shape, (B,) dim] -> same shape, dtype and device as `inputs` (reference :80-95)."""

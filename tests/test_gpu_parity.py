@@ -318,3 +318,28 @@ def test_validation_errors_match_reference_conditions(api):
     assert float(api.w2_gaussian(v, v, eye, -eye, make_pd=True)) > 0        # repaired instead
     with pytest.raises((ValueError, AttributeError, TypeError)):
         api.mean_cov(v, eye, 3)                                              # python int crashes the reference too
+
+
+def test_compute_falls_back_to_eigenvalue_repair_for_indefinite_covariance(api, oracle, golden):
+    """`compute()` skips the smallest-eigenvalue solve when Newton-Schulz certifies a PD covariance; an indefinite
+    matrix written into `.cov` must still get the reference's make_psd(strict) repair (gaussian_model.py:204-217)."""
+    d = 12
+    indef = T(golden("matrix")["indef"][0])                      # symmetric, lambda_min ~ -10
+    op = api.GaussianTransport(d, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double),
+                               target_cfg=dict(dtype=torch.double)).cuda()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(500, d, generator=g) * 1.5 + 0.3).cuda()
+    op.update(target_samples=x)
+    op.target_model.fit()
+    with torch.no_grad():
+        op.source_model.cov = indef.clone()
+        op.source_model.mean.copy_(torch.zeros(d, dtype=torch.double))
+    op.fit_models = lambda: None                                  # keep the hand-written source statistics
+    w2 = op.compute()
+    cov_s = oracle.parametrized_cov(indef.cpu())
+    cov_t = op.target_model.cov.cpu()
+    want_w2 = oracle.w2_gaussian(torch.zeros(d, dtype=torch.double), op.target_model.mean.cpu(), cov_s, cov_t)
+    # the repaired matrix has lambda_min = 1e-8 exactly, so T itself is ill-posed (it depends on that eigenvalue to
+    # 1e-9); the distance and the repaired covariance are the robust observables
+    assert rel(w2, want_w2) < TOL_MATFUN and bool(torch.isfinite(op.transport_operator).all())
+    assert float((op.source_model.cov.cpu() - cov_s).abs().max()) < 1e-4
