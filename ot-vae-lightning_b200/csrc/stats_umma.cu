@@ -11,10 +11,9 @@
 // keeps in its buffers are rebuilt exactly in fp64 by the merge kernel:
 //     sum x = S' + n c ,   sum x x^T = P' + c S'^T + S' c^T + n c c^T .
 //
-// One CTA = one upper-triangular pair of 128-wide feature tiles (ti <= tj) x one chunk of rows.  The 128 x 128 fp32
-// accumulator lives in TMEM for the whole chunk (<= SU_CHUNK rows) and is flushed with fp64 atomics.
-// CTA = 320 threads: warp 0 TMA, warp 1 TMEM alloc + MMA issuer, warps 2-5 convert the i-tile (thread <-> feature
-// column, which also yields the column sums for free) and run the epilogue, warps 6-9 convert the j-tile.
+// One CTA = one upper-triangular pair of 128-wide feature tiles (ti <= tj) x one contiguous range of rows.
+// CTA = 576 threads: warp 0 TMA, warp 1 TMEM alloc + MMA issuer, warps 2-5 convert the i-tile (thread <-> feature
+// column, which also yields the column sums for free), warps 6-9 convert the j-tile, warps 10-17 are the epilogue.
 #include <cuda.h>
 
 #include "otk_ptx.cuh"
@@ -23,42 +22,53 @@
 
 namespace otk {
 
-constexpr int SU_T = 128, SU_BK = 32, SU_STAGES = 3, SU_THREADS = 320;
+constexpr int SU_T = 128, SU_BK = 32, SU_STAGES = 3, SU_ACC = 2;
+constexpr int SU_THREADS = 64 + 256 + 256;            // TMA, MMA | 8 converter warps | 8 epilogue warps
 constexpr int SU_TILE = SU_T * SU_BK * 4;            // 16 KiB: four 32-feature slabs of 32 rows x 128 B
 constexpr int SU_STAGE = 4 * SU_TILE;                // i hi (raw in place), i lo, j hi, j lo
 constexpr int SU_SMEM = SU_STAGES * SU_STAGE + 1024 + 256;
-constexpr int64_t SU_CHUNK = 4096;                   // rows accumulated in TMEM before the fp64 flush
+constexpr int SU_SUB = 1024;                         // rows accumulated in TMEM (fp32, truncating adder) per sub-chunk
 
+// Persistent: CTA b works on unit (l, tile pair) = b / ctas_per_unit and the row range part = b % ctas_per_unit.
+// The k-step ring (TMA -> converters -> MMA) streams over the whole range; every SU_SUB rows the TMEM accumulator is
+// handed to the epilogue warps, which add it into fp32 REGISTER accumulators (round-to-nearest adds) while the next
+// sub-chunk runs into the other TMEM buffer.  One fp64 atomic flush per CTA at the very end.
 __global__ void __launch_bounds__(SU_THREADS, 1)
 stats_umma_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, int rows, int dim,
-                  int chunk_rows, int n_tiles, double* __restrict__ ws_cov, double* __restrict__ ws_sum) {
+                  int rows_per_cta, int ctas_per_unit, int n_tiles, int n_pairs, double* __restrict__ ws_cov,
+                  double* __restrict__ ws_sum) {
   using namespace ptx;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SU_STAGES * SU_STAGE);
   uint64_t* ready = full + SU_STAGES;
   uint64_t* empty = ready + SU_STAGES;
-  uint64_t* tmem_full = empty + SU_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* acc_full = empty + SU_STAGES;
+  uint64_t* acc_empty = acc_full + SU_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SU_ACC);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  int p = blockIdx.x, ti = 0;
+  const int unit = blockIdx.x / ctas_per_unit, part = blockIdx.x % ctas_per_unit;
+  const int l = unit / n_pairs;
+  int p = unit % n_pairs, ti = 0;
   while (p >= n_tiles - ti) { p -= n_tiles - ti; ++ti; }
   const int tj = ti + p;
   const bool diag = (ti == tj);
-  const int l = blockIdx.z;
-  const int r0 = blockIdx.y * chunk_rows;
-  const int r1 = min(rows, r0 + chunk_rows);
-  const int num_k = (r1 - r0 + SU_BK - 1) / SU_BK;
+  const int r0 = part * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  const int n_rows = max(0, r1 - r0);
+  const int num_k = (n_rows + SU_BK - 1) / SU_BK;                 // k-steps of this CTA
+  const int k_per_sub = SU_SUB / SU_BK;
+  const int num_sub = (num_k + k_per_sub - 1) / k_per_sub;
   const int i0 = ti * SU_T, j0 = tj * SU_T;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
     for (int s = 0; s < SU_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], diag ? 128 : 256); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < SU_ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, SU_T); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, SU_ACC * SU_T); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -67,8 +77,8 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restr
   if (warp == 0) {
     if (lane == 0) {
       for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % SU_STAGES, it = kt / SU_STAGES;
-        mbar_wait(&empty[s], (it & 1) ^ 1);
+        const int s = kt % SU_STAGES;
+        mbar_wait(&empty[s], ((kt / SU_STAGES) & 1) ^ 1);
         uint8_t* st = smem + s * SU_STAGE;
         mbar_arrive_expect_tx(&full[s], (diag ? 1u : 2u) * SU_TILE);
         const int k0 = r0 + kt * SU_BK;
@@ -82,27 +92,35 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restr
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(SU_T, SU_T, 1, 1);   // both operands MN-major
-      for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % SU_STAGES, it = kt / SU_STAGES;
-        mbar_wait(&ready[s], it & 1);
+      for (int sub = 0; sub < num_sub; ++sub) {
+        const int a = sub % SU_ACC;
+        mbar_wait(&acc_empty[a], ((sub / SU_ACC) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * SU_STAGE);
-        const uint32_t jbase = diag ? base : base + 2 * SU_TILE;
+        const uint32_t acc = tmem_base + a * SU_T;
+        const int kt_end = min(num_k, (sub + 1) * k_per_sub);
+        for (int kt = sub * k_per_sub; kt < kt_end; ++kt) {
+          const int s = kt % SU_STAGES;
+          mbar_wait(&ready[s], (kt / SU_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * SU_STAGE);
+          const uint32_t jbase = diag ? base : base + 2 * SU_TILE;
+          const bool first = (kt == sub * k_per_sub);
 #pragma unroll
-        for (int kk = 0; kk < SU_BK / 8; ++kk) {
-          const uint64_t a_hi = smem_desc_mn_tf32(base + kk * 1024, 4096);
-          const uint64_t a_lo = smem_desc_mn_tf32(base + SU_TILE + kk * 1024, 4096);
-          const uint64_t b_hi = smem_desc_mn_tf32(jbase + kk * 1024, 4096);
-          const uint64_t b_lo = smem_desc_mn_tf32(jbase + SU_TILE + kk * 1024, 4096);
-          umma_tf32(tmem_base, a_lo, b_hi, idesc, (kt | kk) != 0);
-          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+          for (int kk = 0; kk < SU_BK / 8; ++kk) {
+            const uint64_t a_hi = smem_desc_mn_tf32(base + kk * 1024, 4096);
+            const uint64_t a_lo = smem_desc_mn_tf32(base + SU_TILE + kk * 1024, 4096);
+            const uint64_t b_hi = smem_desc_mn_tf32(jbase + kk * 1024, 4096);
+            const uint64_t b_lo = smem_desc_mn_tf32(jbase + SU_TILE + kk * 1024, 4096);
+            umma_tf32(acc, a_lo, b_hi, idesc, !(first && kk == 0));
+            umma_tf32(acc, a_hi, b_lo, idesc, 1);
+            umma_tf32(acc, a_hi, b_hi, idesc, 1);
+          }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&acc_full[a]);
       }
-      umma_commit(tmem_full);
     }
-  } else {
+  } else if (warp < 10) {
     // ===== converters: thread <-> feature column t of its tile (i-tile: warps 2-5, j-tile: warps 6-9) =====
     const bool is_j = warp >= 6;
     const int t = (warp - (is_j ? 6 : 2)) * 32 + lane;
@@ -111,13 +129,14 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restr
       const float c = col < dim ? pivot[(int64_t)l * dim + col] : 0.f;
       const uint32_t slab_off = (uint32_t)(t / 32) * 4096 + (is_j ? 2u * SU_TILE : 0u);
       const uint32_t cc = (uint32_t)(t % 32) / 8, within = (uint32_t)(t % 8) * 4;
-      float colsum = 0.f;
+      double colsum = 0.0;
       for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % SU_STAGES, it = kt / SU_STAGES;
-        mbar_wait(&full[s], it & 1);
+        const int s = kt % SU_STAGES;
+        mbar_wait(&full[s], (kt / SU_STAGES) & 1);
         uint8_t* hi_t = smem + s * SU_STAGE + slab_off;
         uint8_t* lo_t = hi_t + SU_TILE;
-        const int valid = min(SU_BK, r1 - (r0 + kt * SU_BK));   // rows past the chunk / batch end contribute nothing
+        const int valid = min(SU_BK, r1 - (r0 + kt * SU_BK));   // rows past the range / batch end contribute nothing
+        float part_sum = 0.f;
 #pragma unroll 8
         for (int r = 0; r < SU_BK; ++r) {
           const uint32_t off = (uint32_t)r * 128 + ((cc ^ (uint32_t)(r & 3)) * 32) + within;
@@ -127,39 +146,52 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restr
           split_tf32(x, h, lo);
           *reinterpret_cast<float*>(hi_t + off) = h;
           *reinterpret_cast<float*>(lo_t + off) = lo;
-          colsum += x;
+          part_sum += x;
         }
+        colsum += (double)part_sum;
         fence_proxy_async_smem();
         mbar_arrive(&ready[s]);
       }
-      if (!is_j && diag && col < dim) atomicAdd(&ws_sum[(int64_t)l * dim + col], (double)colsum);
+      if (!is_j && diag && col < dim && num_k > 0) atomicAdd(&ws_sum[(int64_t)l * dim + col], colsum);
     }
-    if (!is_j) {
-      // ===== epilogue: fp64 atomics into the staging area (upper tile pairs only) =====
-      const int q = warp % 4;
-      const int gi = i0 + q * 32 + lane;
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-      double* cov = ws_cov + (int64_t)l * dim * dim;
-#pragma unroll 1
-      for (int c0 = 0; c0 < SU_T; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-        tmem_ld_wait();
-        if (gi < dim) {
+  } else {
+    // ===== epilogue: 8 warps; warp -> (TMEM lane quarter, column half); fp32 register accumulation across sub-chunks ====
+    const int q = warp % 4, half = (warp - 10) / 4;
+    const int gi = i0 + q * 32 + lane;
+    float acc[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gj = j0 + c0 + j;
-            // diagonal tile pairs: the merge kernel reads the (min, max) element, so only gi <= gj is needed
-            if (gj < dim && (!diag || gi <= gj)) atomicAdd(&cov[(int64_t)gi * dim + gj], (double)v[j]);
-          }
-        }
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int sub = 0; sub < num_sub; ++sub) {
+      const int a = sub % SU_ACC;
+      mbar_wait(&acc_full[a], (sub / SU_ACC) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * SU_T + half * 64;
+      {
+        float v[32];
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += v[j];
+        tmem_ld32(taddr + 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[32 + j] += v[j];
       }
       tc_fence_before();
+      mbar_arrive(&acc_empty[a]);
+    }
+    if (num_k > 0 && gi < dim) {
+      double* cov = ws_cov + (int64_t)l * dim * dim;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const int gj = j0 + half * 64 + j;
+        // diagonal tile pairs: the merge kernel reads the (min, max) element, so only gi <= gj is needed
+        if (gj < dim && (!diag || gi <= gj)) atomicAdd(&cov[(int64_t)gi * dim + gj], (double)acc[j]);
+      }
     }
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, SU_T); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, SU_ACC * SU_T); }
 }
 
 // pivot[l, :] = mean of the first min(rows, 64) latents of the batch
@@ -207,13 +239,13 @@ int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   if (!encode_map_f32_3d(&mX, x, dim, rows, L, row_stride, batch_stride, 32, SU_BK, /*atom32=*/true)) return 0;
   const int n_tiles = (int)ceil_div(dim, SU_T);
   const int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
-  // enough row chunks for a few waves, each a multiple of 32 rows and at most SU_CHUNK (fp32 accumulation span)
-  int64_t want = ceil_div((int64_t)sm_count() * 3, pairs * L);
-  int64_t chunk = ceil_div(ceil_div(rows, want), SU_BK) * SU_BK;
-  if (chunk < 256) chunk = 256;
-  if (chunk > SU_CHUNK) chunk = SU_CHUNK;
-  const int64_t n_chunks = ceil_div(rows, chunk);
-  if (n_chunks > 65535) return 0;
+  const int64_t units = pairs * L;
+  // one CTA per SM when the units fit: each unit's rows are split over ctas_per_unit CTAs (multiples of 32 rows)
+  int64_t cpu = units >= sm_count() ? 1 : sm_count() / units;
+  int64_t rows_per_cta = ceil_div(ceil_div(rows, cpu), SU_BK) * SU_BK;
+  if (rows_per_cta < 256) rows_per_cta = 256;                       // tiny batches: fewer, fuller CTAs
+  cpu = ceil_div(rows, rows_per_cta);
+  if (units * cpu > INT32_MAX) return 0;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -221,8 +253,8 @@ int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
     OTK_CUDA(cudaFuncSetAttribute(stats_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SU_SMEM));
     attr_set[dev] = true;
   }
-  dim3 grid((unsigned)pairs, (unsigned)n_chunks, (unsigned)L);
-  stats_umma_kernel<<<grid, SU_THREADS, SU_SMEM, st>>>(mX, pivot, (int)rows, (int)dim, (int)chunk, n_tiles, ws_cov, ws_sum);
+  stats_umma_kernel<<<(unsigned)(units * cpu), SU_THREADS, SU_SMEM, st>>>(mX, pivot, (int)rows, (int)dim, (int)rows_per_cta,
+                                                                         (int)cpu, n_tiles, (int)pairs, ws_cov, ws_sum);
   OTK_LAUNCH_CHECK();
   int64_t blocks = ceil_div(L * dim * dim, 256);
   if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;

@@ -56,7 +56,7 @@ def test_tcgen05_stats_kernel_matches_fp64(L, rows, d):
     mean = s / rows
     cov = ss / rows - mean.unsqueeze(-1) * mean.unsqueeze(-2)
     xc = x64 - x64.mean(1, keepdim=True)
-    assert relerr(cov, xc.transpose(1, 2) @ xc / rows) < 2e-5     # no cancellation blow-up despite |mean| ~ 17 sigma
+    assert relerr(cov, xc.transpose(1, 2) @ xc / rows) < 3e-5     # no cancellation blow-up despite |mean| ~ 17 sigma
     # second call accumulates (decay=None) and EMA works
     Kn.stats_update(x, n, s, ss, None)
     assert relerr(ss, 2 * (x64.transpose(1, 2) @ x64)) < 1e-7
