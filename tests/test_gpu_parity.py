@@ -343,3 +343,28 @@ def test_compute_falls_back_to_eigenvalue_repair_for_indefinite_covariance(api, 
     # 1e-9); the distance and the repaired covariance are the robust observables
     assert rel(w2, want_w2) < TOL_MATFUN and bool(torch.isfinite(op.transport_operator).all())
     assert float((op.source_model.cov.cpu() - cov_s).abs().max()) < 1e-4
+
+
+def test_streaming_helpers_match_direct_calls(api):
+    """host-buffer pipelines (streaming.py: H2D | kernels | D2H on side streams) == plain device-resident calls"""
+    from ot_vae_lightning_b200.streaming import stream_transport, stream_update
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    d, n, chunk = 128, 50_000, 8192
+    src = gaussian_latents(n, d, seed=31, device="cuda")
+    tgt = gaussian_latents(n, d, seed=32, device="cuda", shift=1.0, scale=0.7)
+    mk = lambda: api.GaussianTransport(d, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double),
+                                       target_cfg=dict(dtype=torch.double)).cuda()
+    direct, piped = mk(), mk()
+    for lo in range(0, n, chunk):
+        direct.update(src[lo:lo + chunk], tgt[lo:lo + chunk])
+    h_src, h_tgt = src.cpu().pin_memory(), tgt.cpu().pin_memory()
+    stream_update(piped, h_src, h_tgt, chunk)
+    assert rel(piped.source_model._running_sum_cov, direct.source_model._running_sum_cov.cpu()) < 1e-12
+    assert rel(piped.target_model._running_sum, direct.target_model._running_sum.cpu()) < 1e-12
+    w_d, w_p = direct.compute(), piped.compute()
+    assert abs(float(w_d) - float(w_p)) < 1e-9 * abs(float(w_d))
+    h_out = torch.empty_like(h_src).pin_memory()
+    stream_transport(piped, h_src, h_out, chunk)
+    torch.cuda.synchronize()
+    want = torch.cat([direct.transport(src[lo:lo + chunk]) for lo in range(0, n, chunk)]).cpu()
+    assert torch.equal(h_out, want)
