@@ -1,12 +1,20 @@
-// K7 on tcgen05: Y = (X - 1 mean_s^T) T^T + 1 mean_t^T  with fp32-accurate 3xTF32 arithmetic.
-// Reference: apply_transport, ot/w2_utils.py:517-520 (B broadcast fp64 mat-vecs) - here one streaming GEMM.
+// K7 on tcgen05: Y = (X - 1 mean_s^T) T^T + 1 mean_t^T with fp32-accurate 3xTF32 arithmetic.
+// Reference: apply_transport, ot/w2_utils.py:517-520 (B broadcast fp64 mat-vecs).
 //
-// X is streamed ONCE from HBM: TMA drops the raw fp32 tile (128 latents x 32 features, 128B swizzle) into shared
-// memory, four converter warps centre it (x - mean_s) and split it in place into TF32 hi / lo planes, and one thread
-// issues tcgen05.mma kind::tf32 (lo*hi' + hi*lo' + hi*hi') against the pre-split rows of T, accumulating a
-// 128 x 128 fp32 tile in TMEM.  The converter warps then become the epilogue (TMEM -> + mean_t -> global).
+// Data flow of one k-step (32 features of 128 latents per CTA):
+//   TMA            raw X tile [128 x 32] fp32 -> shared memory (128B swizzle), T_hi / T_lo tiles -> shared memory
+//   converter warps  read the raw tile (thread <-> latent row), subtract mean_s, split into TF32 hi / lo and write both
+//                    planes straight into TENSOR MEMORY with tcgen05.st  (the A operand never returns to shared memory)
+//   MMA thread       three kind::tf32 MMAs per K=8 slice with A from TMEM and B (= T planes) from shared memory:
+//                    lo*hi + hi*lo + hi*hi into one fp32 TMEM accumulator
+//   epilogue warps   tcgen05.ld -> + mean_t -> swizzled staging tile -> TMA store (clips the ragged edges)
+// Keeping A in TMEM halves the shared-memory traffic of the main loop: an SS-mode 128x128x8 TF32 MMA reads 8 KB of
+// operands per 64 cycles, i.e. the SM's whole 128 B/clk, so the TMA fills and the converter used to starve it.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 converter / epilogue.
+// Two instantiations:
+//   <CG=1, BN=128>  one CTA per 128 x 128 tile, two accumulators (epilogue overlaps the next tile)      - dim < 256
+//   <CG=2, BN=256>  a CTA pair per 256 x 256 tile (tcgen05 cta_group::2): each CTA converts its own 128 latents and
+//                   stages half of the T tile, so T is fetched once per 256 latents and X once per 256 outputs - dim >= 256
 #include <cuda.h>
 
 #include "apply_umma.cuh"
@@ -15,168 +23,213 @@
 
 namespace otk {
 
-constexpr int AP_BM = 128, AP_BN = 128, AP_BK = 32, AP_STAGES = 3, AP_THREADS = 320, AP_ACC = 2;
-constexpr int AP_TILE = AP_BM * AP_BK * 4;          // 16 KiB
-constexpr int AP_STAGE = 4 * AP_TILE;               // X hi (raw in place), X lo, T hi, T lo
-constexpr int AP_SMEM = AP_STAGES * AP_STAGE + 1024 + 256;
+constexpr int AP_BM = 128, AP_BK = 32;
+constexpr int AP_XS = 3, AP_TS = 4, AP_AS = 4;       // ring depths: raw X (smem), T planes (smem), converted A (TMEM)
+constexpr int AP_XTILE = AP_BM * AP_BK * 4;          // 16 KiB raw X tile
+constexpr int AP_TPLANE = 128 * AP_BK * 4;           // 16 KiB: the 128 rows of one T plane a CTA stages per k-step
+constexpr int AP_TSTAGE = 2 * AP_TPLANE;             // hi + lo
+constexpr int AP_OUT = 32 * 32 * 4;                  // 4 KiB staging tile per TMA store
+constexpr int AP_THREADS = 14 * 32;                  // TMA, MMA | 8 converter warps | 4 epilogue warps
+constexpr int AP_ACOL0 = 256;                        // TMEM columns [0,256): accumulators, [256,512): A ring
+constexpr int AP_SMEM = AP_XS * AP_XTILE + AP_TS * AP_TSTAGE + 8 * AP_OUT + 1024 + 512;
 
-// Persistent: one CTA per SM walks the (row tile, column tile) list; the smem ring keeps streaming across tiles and the
-// two TMEM accumulators let the epilogue of tile i overlap the main loop of tile i+1.
-// warp 0 TMA producer | warp 1 TMEM alloc + MMA issuer | warps 2-5 converter | warps 6-9 epilogue
+template <int CG, int BN>
 __global__ void __launch_bounds__(AP_THREADS, 1)
-apply_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT_hi,
-                  const __grid_constant__ CUtensorMap mapT_lo, const float* __restrict__ mean_s,
-                  const float* __restrict__ mean_t, float* __restrict__ y, int rows, int dim, int m_tiles, int n_tiles,
-                  int total_tiles) {
+apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT_hi,
+                const __grid_constant__ CUtensorMap mapT_lo, const __grid_constant__ CUtensorMap mapY,
+                const float* __restrict__ mean_s, const float* __restrict__ mean_t, int rows, int dim, int m_tiles,
+                int n_tiles, int total_tiles) {
   using namespace ptx;
+  constexpr int NACC = 256 / BN;                      // accumulator buffers
+  static_assert(BN / CG == 128, "each CTA stages 128 rows of the T tile");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + AP_STAGES * AP_STAGE);   // TMA landed
-  uint64_t* ready = full + AP_STAGES;                                           // converted, MMA may read
-  uint64_t* empty = ready + AP_STAGES;                                          // MMA done with the stage
-  uint64_t* acc_full = empty + AP_STAGES;                                       // accumulator complete
-  uint64_t* acc_empty = acc_full + AP_ACC;                                      // accumulator drained by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + AP_ACC);
+  uint8_t* xraw = smem;
+  uint8_t* tpl = xraw + AP_XS * AP_XTILE;
+  uint8_t* outb = tpl + AP_TS * AP_TSTAGE;
+  uint64_t* full_x = reinterpret_cast<uint64_t*>(outb + 8 * AP_OUT);   // TMA landed the raw X tile
+  uint64_t* empty_x = full_x + AP_XS;                                  // converters have read it
+  uint64_t* full_t = empty_x + AP_XS;                                  // T planes landed (leader: both CTAs' halves)
+  uint64_t* empty_t = full_t + AP_TS;                                  // MMAs reading them retired
+  uint64_t* ready_a = empty_t + AP_TS;                                 // A planes in TMEM written (leader: both CTAs)
+  uint64_t* empty_a = ready_a + AP_AS;                                 // MMAs reading them retired
+  uint64_t* acc_full = empty_a + AP_AS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const int group = CG == 2 ? blockIdx.x / 2 : blockIdx.x;           // tile-processing unit (CTA or CTA pair)
+  const int n_groups = CG == 2 ? gridDim.x / 2 : gridDim.x;
   const int num_k = (dim + AP_BK - 1) / AP_BK;
   const int tiles_per_l = m_tiles * n_tiles;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapT_hi); tma_prefetch_desc(&mapT_lo);
-    for (int s = 0; s < AP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < AP_ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapT_hi); tma_prefetch_desc(&mapT_lo); tma_prefetch_desc(&mapY);
+    for (int s = 0; s < AP_XS; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 8); }
+    for (int s = 0; s < AP_TS; ++s) { mbar_init(&full_t[s], 1); mbar_init(&empty_t[s], 1); }
+    for (int s = 0; s < AP_AS; ++s) { mbar_init(&ready_a[s], 8 * CG); mbar_init(&empty_a[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4 * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, AP_ACC * AP_BN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc_cg<CG>(tmem_slot, 512); tmem_relinquish_cg<CG>(); }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ===== TMA producer: raw X tile of this CTA's 128 latents, and this CTA's 128 rows of the T hi/lo tiles =====
     if (lane == 0) {
+      const uint32_t full_t_leader0 = CG == 2 ? map_to_cta(smem_u32(&full_t[0]), 0) : smem_u32(&full_t[0]);
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < total_tiles; tile += n_groups) {
         const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
-        const int m0 = (rem / n_tiles) * AP_BM, n0 = (rem % n_tiles) * AP_BN;
+        const int m0 = (rem / n_tiles) * (AP_BM * CG) + (int)rank * AP_BM;
+        const int n0 = (rem % n_tiles) * BN + (int)rank * 128;
         for (int kt = 0; kt < num_k; ++kt, ++it) {
-          const int s = it % AP_STAGES;
-          mbar_wait(&empty[s], ((it / AP_STAGES) & 1) ^ 1);
-          uint8_t* st = smem + s * AP_STAGE;
-          mbar_arrive_expect_tx(&full[s], 3u * AP_TILE);
-          tma_load_3d(st, &mapX, kt * AP_BK, m0, l, &full[s]);
-          tma_load_3d(st + 2 * AP_TILE, &mapT_hi, kt * AP_BK, n0, l, &full[s]);
-          tma_load_3d(st + 3 * AP_TILE, &mapT_lo, kt * AP_BK, n0, l, &full[s]);
+          const int sx = it % AP_XS, st = it % AP_TS;
+          mbar_wait(&empty_x[sx], ((it / AP_XS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_x[sx], AP_XTILE);
+          tma_load_3d(xraw + sx * AP_XTILE, &mapX, kt * AP_BK, m0, l, &full_x[sx]);
+          mbar_wait(&empty_t[st], ((it / AP_TS) & 1) ^ 1);
+          uint8_t* td = tpl + st * AP_TSTAGE;
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(&full_t[st], AP_TSTAGE);
+            tma_load_3d(td, &mapT_hi, kt * AP_BK, n0, l, &full_t[st]);
+            tma_load_3d(td + AP_TPLANE, &mapT_lo, kt * AP_BK, n0, l, &full_t[st]);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&full_t[st], 2 * AP_TSTAGE);   // both CTAs' bytes land on the leader's barrier
+            const uint32_t bar = full_t_leader0 + st * 8;
+            tma_load_3d_cg2(td, &mapT_hi, kt * AP_BK, n0, l, bar);
+            tma_load_3d_cg2(td + AP_TPLANE, &mapT_lo, kt * AP_BK, n0, l, bar);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(AP_BM, AP_BN, 0, 0);
+    // ===== MMA issuer (leader CTA of the pair only) =====
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = idesc_tf32(AP_BM * CG, BN, 0, 0);
       int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int a = ti % AP_ACC;
-        mbar_wait(&acc_empty[a], ((ti / AP_ACC) & 1) ^ 1);
+      for (int tile = group; tile < total_tiles; tile += n_groups, ++ti) {
+        const int a = ti % NACC;
+        mbar_wait(&acc_empty[a], ((ti / NACC) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + a * AP_BN;
+        const uint32_t acc = tmem_base + a * BN;
         for (int kt = 0; kt < num_k; ++kt, ++it) {
-          const int s = it % AP_STAGES;
-          mbar_wait(&ready[s], (it / AP_STAGES) & 1);
+          const int st = it % AP_TS, sa = it % AP_AS;
+          mbar_wait(&full_t[st], (it / AP_TS) & 1);
+          mbar_wait(&ready_a[sa], (it / AP_AS) & 1);
           tc_fence_after();
-          const uint32_t base = smem_u32(smem + s * AP_STAGE);
+          const uint32_t tb = smem_u32(tpl + st * AP_TSTAGE);
+          const uint32_t ab = tmem_base + AP_ACOL0 + sa * 64;
 #pragma unroll
           for (int kk = 0; kk < AP_BK / 8; ++kk) {
-            const uint64_t x_hi = smem_desc_sw128(base + kk * 32, 16, 1024);
-            const uint64_t x_lo = smem_desc_sw128(base + AP_TILE + kk * 32, 16, 1024);
-            const uint64_t t_hi = smem_desc_sw128(base + 2 * AP_TILE + kk * 32, 16, 1024);
-            const uint64_t t_lo = smem_desc_sw128(base + 3 * AP_TILE + kk * 32, 16, 1024);
-            umma_tf32(acc, x_lo, t_hi, idesc, (kt | kk) != 0);
-            umma_tf32(acc, x_hi, t_lo, idesc, 1);
-            umma_tf32(acc, x_hi, t_hi, idesc, 1);
+            const uint64_t t_hi = smem_desc_sw128(tb + kk * 32, 16, 1024);
+            const uint64_t t_lo = smem_desc_sw128(tb + AP_TPLANE + kk * 32, 16, 1024);
+            umma_tf32_ts<CG>(acc, ab + 32 + kk * 8, t_hi, idesc, (kt | kk) != 0);   // lo * hi
+            umma_tf32_ts<CG>(acc, ab + kk * 8, t_lo, idesc, 1);                     // hi * lo
+            umma_tf32_ts<CG>(acc, ab + kk * 8, t_hi, idesc, 1);                     // hi * hi
           }
-          umma_commit(&empty[s]);
+          umma_commit_cg<CG>(&empty_t[st]);
+          umma_commit_cg<CG>(&empty_a[sa]);
         }
-        umma_commit(&acc_full[a]);
+        umma_commit_cg<CG>(&acc_full[a]);
       }
     }
-  } else if (warp < 6) {
-    // ===== converter: thread r owns row r of the 128 x 32 tile (eight 16-byte chunks, XOR-swizzled by r % 8) =====
-    const int r = (warp - 2) * 32 + lane;
+  } else if (warp < 10) {
+    // ===== converters: thread <-> latent row r (TMEM lane r); warps 2-5 take features 0-15 of the k-step, 6-9 take 16-31
+    const int q = warp % 4, half = (warp - 2) / 4;
+    const int r = q * 32 + lane;
+    const uint32_t row_off = (uint32_t)r * 128;
+    const uint32_t ready_addr = CG == 2 ? map_to_cta(smem_u32(&ready_a[0]), 0) : smem_u32(&ready_a[0]);
+    const uint32_t xbase = smem_u32(xraw);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = group; tile < total_tiles; tile += n_groups) {
       const int l = tile / tiles_per_l;
       const float* ms = mean_s + (int64_t)l * dim;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
-        const int s = it % AP_STAGES;
-        mbar_wait(&full[s], (it / AP_STAGES) & 1);
-        uint8_t* hi_row = smem + s * AP_STAGE + r * 128;
-        uint8_t* lo_row = hi_row + AP_TILE;
-        const int k0 = kt * AP_BK;
+        const int sx = it % AP_XS, sa = it % AP_AS;
+        mbar_wait(&full_x[sx], (it / AP_XS) & 1);
+        float4 x[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int phys = (c ^ (r & 7)) * 16;
-          float4 x = *reinterpret_cast<const float4*>(hi_row + phys);
-          const int k = k0 + c * 4;
-          float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k + 3 < dim) mu = *reinterpret_cast<const float4*>(ms + k);
-          else {
-            if (k < dim) mu.x = ms[k];
-            if (k + 1 < dim) mu.y = ms[k + 1];
-            if (k + 2 < dim) mu.z = ms[k + 2];
-          }
-          float4 h, lo;
-          split_tf32(x.x - mu.x, h.x, lo.x);
-          split_tf32(x.y - mu.y, h.y, lo.y);
-          split_tf32(x.z - mu.z, h.z, lo.z);
-          split_tf32(x.w - mu.w, h.w, lo.w);
-          *reinterpret_cast<float4*>(hi_row + phys) = h;
-          *reinterpret_cast<float4*>(lo_row + phys) = lo;
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t chunk = (uint32_t)(half * 4 + c);
+          x[c] = lds128(xbase + sx * AP_XTILE + row_off + ((chunk ^ (uint32_t)(r & 7)) * 16));
         }
-        fence_proxy_async_smem();   // make the generic-proxy writes visible to the tensor core (async proxy)
-        mbar_arrive(&ready[s]);
+        float hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = kt * AP_BK + half * 16 + c * 4;
+          float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < dim) mu = __ldg(reinterpret_cast<const float4*>(ms + k));   // dim % 4 == 0
+          split_tf32_fast(x[c].x - mu.x, hi[4 * c + 0], lo[4 * c + 0]);
+          split_tf32_fast(x[c].y - mu.y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32_fast(x[c].z - mu.z, hi[4 * c + 2], lo[4 * c + 2]);
+          split_tf32_fast(x[c].w - mu.w, hi[4 * c + 3], lo[4 * c + 3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_x[sx]);                 // raw tile consumed (values are in registers)
+        mbar_wait(&empty_a[sa], ((it / AP_AS) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + AP_ACOL0 + sa * 64 + half * 16;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ready_addr + sa * 8);
       }
     }
   } else {
-    // ===== epilogue: TMEM -> + mean_t -> global; overlaps the next tile's main loop =====
+    // ===== epilogue: TMEM -> + mean_t -> 32x32 swizzled staging tile -> TMA store; overlaps the next tile's main loop
     const int q = warp % 4;
-    const bool vec_ok = (dim % 4 == 0);
-    int ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    const uint32_t stage0 = smem_u32(outb) + (uint32_t)(warp - 10) * 2 * AP_OUT;
+    const uint32_t acc_empty_addr = CG == 2 ? map_to_cta(smem_u32(&acc_empty[0]), 0) : smem_u32(&acc_empty[0]);
+    int ti = 0, nstore = 0;
+    for (int tile = group; tile < total_tiles; tile += n_groups, ++ti) {
       const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
-      const int m0 = (rem / n_tiles) * AP_BM, n0 = (rem % n_tiles) * AP_BN;
-      const int a = ti % AP_ACC;
-      const int m = m0 + q * 32 + lane;
+      const int m0 = (rem / n_tiles) * (AP_BM * CG) + (int)rank * AP_BM + q * 32;
+      const int n0 = (rem % n_tiles) * BN;
+      const int a = ti % NACC;
       const float* mt = mean_t + (int64_t)l * dim;
-      float* dst = y + ((int64_t)l * rows + m) * dim;
-      mbar_wait(&acc_full[a], (ti / AP_ACC) & 1);
+      mbar_wait(&acc_full[a], (ti / NACC) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < AP_BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 32, ++nstore) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * AP_BN + c0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + c0, v);
         tmem_ld_wait();
-        if (m < rows) {
+        if (c0 + 32 == BN) {                                      // accumulator fully read: hand it back to the MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_addr + a * 8);
+        }
+        const uint32_t buf = stage0 + (uint32_t)(nstore & 1) * AP_OUT;
+        if (lane == 0) tma_store_wait_read<1>();                  // the store issued two chunks ago has read this buffer
+        __syncwarp();
 #pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            const int n = n0 + c0 + j4;
-            if (vec_ok && n + 3 < dim) {
-              const float4 b = *reinterpret_cast<const float4*>(mt + n);
-              *reinterpret_cast<float4*>(dst + n) = make_float4(v[j4] + b.x, v[j4 + 1] + b.y, v[j4 + 2] + b.z, v[j4 + 3] + b.w);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (n + j < dim) dst[n + j] = v[j4 + j] + mt[n + j];
-            }
-          }
+        for (int c = 0; c < 8; ++c) {
+          const int n = n0 + c0 + c * 4;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n < dim) b = __ldg(reinterpret_cast<const float4*>(mt + n));
+          sts128(buf + (uint32_t)lane * 128 + (((uint32_t)c ^ (uint32_t)(lane & 7)) * 16),
+                 make_float4(v[4 * c] + b.x, v[4 * c + 1] + b.y, v[4 * c + 2] + b.z, v[4 * c + 3] + b.w));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && n0 + c0 < dim && m0 < rows) {
+          tma_store_3d(&mapY, buf, n0 + c0, m0, l);
+          tma_store_commit();
         }
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[a]);
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, AP_ACC * AP_BN); }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_cg<CG>(tmem_base, 512); }
 }
 
 __global__ void split_matrix_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
@@ -188,8 +241,42 @@ __global__ void split_matrix_kernel(const float* __restrict__ x, int64_t n, floa
   }
 }
 
-// Thi: in-place over T32 is not allowed (T32 stays the caller's); uses T32 -> (Tlo_scratch as lo, and the hi plane is
-// written over ... ) - we need two planes: hi goes to `Thi_scratch`, lo to `Tlo_scratch`.
+template <int CG, int BN>
+static int launch_apply(const CUtensorMap& mX, const CUtensorMap& mTh, const CUtensorMap& mTl, const CUtensorMap& mY,
+                        const float* ms32, const float* mt32, int64_t L, int64_t rows, int64_t dim, cudaStream_t st) {
+  auto kern = apply_ts_kernel<CG, BN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM));
+    attr_set[dev] = true;
+  }
+  const int64_t m_tiles = ceil_div(rows, AP_BM * CG), n_tiles = ceil_div(dim, BN);
+  const int64_t total = L * m_tiles * n_tiles;
+  if (total > INT32_MAX) return 0;
+  const int64_t max_groups = sm_count() / CG;
+  const unsigned groups = (unsigned)(total < max_groups ? total : max_groups);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(AP_THREADS);
+  cfg.dynamicSmemBytes = AP_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, mX, mTh, mTl, mY, ms32, mt32, (int)rows, (int)dim, (int)m_tiles, (int)n_tiles,
+                              (int)total));
+  OTK_LAUNCH_CHECK();
+  return 1;
+}
+
+int g_apply_force_cg = 0;   // tuning aid: 1 / 2 force the single-CTA / CTA-pair instantiation
+
 int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const float* ms32, const float* mt32,
                    const float* T32, float* Thi_scratch, float* Tlo_scratch, float* y, cudaStream_t st) {
   if (dim < 64 || dim % 4 != 0 || rows < 1 || L > 65535 || rows > INT32_MAX || dim > INT32_MAX) return 0;
@@ -200,25 +287,14 @@ int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const f
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   split_matrix_kernel<<<(unsigned)blocks, 256, 0, st>>>(T32, n, Thi_scratch, Tlo_scratch);
   OTK_LAUNCH_CHECK();
-  CUtensorMap mX, mTh, mTl;
+  CUtensorMap mX, mTh, mTl, mY;
   if (!encode_map_f32_3d(&mX, x, dim, rows, L, dim, rows * dim, 32, AP_BM)) return 0;
-  if (!encode_map_f32_3d(&mTh, Thi_scratch, dim, dim, L, dim, dim * dim, 32, AP_BN)) return 0;
-  if (!encode_map_f32_3d(&mTl, Tlo_scratch, dim, dim, L, dim, dim * dim, 32, AP_BN)) return 0;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OTK_CUDA(cudaFuncSetAttribute(apply_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM));
-    attr_set[dev] = true;
-  }
-  const int64_t m_tiles = ceil_div(rows, AP_BM), n_tiles = ceil_div(dim, AP_BN);
-  const int64_t total = L * m_tiles * n_tiles;
-  if (total > INT32_MAX) return 0;
-  const unsigned grid = (unsigned)(total < sm_count() ? total : sm_count());
-  apply_umma_kernel<<<grid, AP_THREADS, AP_SMEM, st>>>(mX, mTh, mTl, ms32, mt32, y, (int)rows, (int)dim, (int)m_tiles,
-                                                      (int)n_tiles, (int)total);
-  OTK_LAUNCH_CHECK();
-  return 1;
+  if (!encode_map_f32_3d(&mTh, Thi_scratch, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
+  if (!encode_map_f32_3d(&mTl, Tlo_scratch, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
+  if (!encode_map_f32_3d(&mY, y, dim, rows, L, dim, rows * dim, 32, 32)) return 0;
+  const bool pair = g_apply_force_cg ? g_apply_force_cg == 2 : (dim >= 256 && rows > 128);
+  if (pair) return launch_apply<2, 256>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st);
+  return launch_apply<1, 128>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st);
 }
 
 }  // namespace otk

@@ -23,7 +23,8 @@ namespace otk {
 constexpr int UG_BM = 128, UG_BN = 128, UG_BK = 32, UG_STAGES = 3, UG_THREADS = 192;
 constexpr int UG_TILE_BYTES = UG_BM * UG_BK * 4;                   // 16 KiB per operand plane per stage
 constexpr int UG_STAGE_BYTES = 4 * UG_TILE_BYTES;                  // A_hi, A_lo, B_hi, B_lo
-constexpr int UG_SMEM_BYTES = UG_STAGES * UG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int UG_XPOSE = 32 * 33 * 4;                              // per-epilogue-warp transpose buffer
+constexpr int UG_SMEM_BYTES = UG_STAGES * UG_STAGE_BYTES + 4 * UG_XPOSE + 1024 /*align*/ + 256 /*barriers*/;
 
 struct UmmaGemmParams {
   int M, N, K, passes, b_mn_major;
@@ -33,6 +34,7 @@ struct UmmaGemmParams {
   const float* bias;
   int64_t stride_bias;
   double* resid;
+  long long* dbg;   // optional timestamps of CTA 0 (kernel tuning aid)
 };
 
 __global__ void __launch_bounds__(UG_THREADS, 1)
@@ -42,7 +44,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   using namespace ptx;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + UG_STAGES * UG_STAGE_BYTES);
+  float* xpose = reinterpret_cast<float*>(smem + UG_STAGES * UG_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + UG_STAGES * UG_STAGE_BYTES + 4 * UG_XPOSE);
   uint64_t* empty = full + UG_STAGES;
   uint64_t* tmem_full = empty + UG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -64,6 +67,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (trace && threadIdx.x == 0) p.dbg[0] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -72,6 +77,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % UG_STAGES, it = kt / UG_STAGES;
         mbar_wait(&empty[s], (it & 1) ^ 1);
+        if (trace && kt < 24) p.dbg[40 + kt] = clock64();
         uint8_t* st = smem + s * UG_STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], stage_tx);
         const int k0 = kt * UG_BK;
@@ -98,6 +104,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % UG_STAGES, it = kt / UG_STAGES;
         mbar_wait(&full[s], it & 1);
+        if (trace && kt < 24) p.dbg[8 + kt] = clock64();
         tc_fence_after();
         const uint32_t base = smem_u32(smem + s * UG_STAGE_BYTES);
 #pragma unroll
@@ -120,64 +127,62 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       umma_commit(tmem_full);                      // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> (per-warp 32x32 smem transpose) -> global =====
+    // TMEM gives each lane one row; after the transpose lanes hold consecutive columns, so every store instruction
+    // writes a full 128-byte line of C / C_hi / C_lo.
     const int q = warp % 4;                        // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
+    float* xp = xpose + (warp - 2) * (32 * 33);
+    const int mrow0 = m0 + q * 32;
     mbar_wait(tmem_full, 0);
+    if (trace && warp == 2 && lane == 0) p.dbg[1] = clock64();
     tc_fence_after();
     float* C = p.C ? p.C + (int64_t)batch * p.strideC : nullptr;
     float* Ch = p.C_hi ? p.C_hi + (int64_t)batch * p.strideC : nullptr;
     float* Cl = p.C_lo ? p.C_lo + (int64_t)batch * p.strideC : nullptr;
     const float* bias = p.bias ? p.bias + (int64_t)batch * p.stride_bias : nullptr;
     double res = 0.0;
-    const bool vec_ok = (p.ldc % 4 == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < UG_BN; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
       tmem_ld_wait();
-      if (m < p.M) {
-        const int64_t row = (int64_t)m * p.ldc;
 #pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const int n = n0 + c0 + j4;
-          float r[4], h[4], l[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int nj = n + j;
-            const float acc = v[j4 + j];
-            if (p.resid && nj < p.N) { double e = (double)acc - (m == nj ? 1.0 : 0.0); res += e * e; }
-            float t = p.alpha * acc;
-            if (p.beta != 0.f && C && nj < p.N) t += p.beta * C[row + nj];
-            if (bias && nj < p.N) t += bias[nj];
-            if (m == nj) t += p.diag_add;
-            r[j] = t;
-            split_tf32(t, h[j], l[j]);
-          }
-          if (vec_ok && n + 3 < p.N) {
-            if (C) *reinterpret_cast<float4*>(C + row + n) = make_float4(r[0], r[1], r[2], r[3]);
-            if (Ch) *reinterpret_cast<float4*>(Ch + row + n) = make_float4(h[0], h[1], h[2], h[3]);
-            if (Cl) *reinterpret_cast<float4*>(Cl + row + n) = make_float4(l[0], l[1], l[2], l[3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < p.N) {
-                if (C) C[row + n + j] = r[j];
-                if (Ch) Ch[row + n + j] = h[j];
-                if (Cl) Cl[row + n + j] = l[j];
-              }
+      for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = v[j];
+      __syncwarp();
+      const int n = n0 + c0 + lane;
+      if (n < p.N) {
+        const float bn = bias ? bias[n] : 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int m = mrow0 + r;
+          if (m >= p.M) continue;
+          const float acc = xp[r * 33 + lane];
+          const int64_t idx = (int64_t)m * p.ldc + n;
+          if (p.resid) { const float e = acc - (m == n ? 1.f : 0.f); res += (double)(e * e); }
+          float t = p.alpha * acc + bn;
+          if (p.beta != 0.f && C) t += p.beta * C[idx];
+          if (m == n) t += p.diag_add;
+          if (C) C[idx] = t;
+          if (Ch) {
+            float h, lo;
+            split_tf32(t, h, lo);
+            Ch[idx] = h;
+            Cl[idx] = lo;
           }
         }
       }
+      __syncwarp();
     }
     if (p.resid) {
       res = warp_sum(res);
       if (lane == 0) atomicAdd(&p.resid[batch], res);
     }
     tc_fence_before();
+    if (trace && warp == 2 && lane == 0) p.dbg[2] = clock64();
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, UG_BN); }
+  if (trace && threadIdx.x == 0) p.dbg[3] = clock64();
 }
 
 // elementwise split of a strided [batch][rows][cols] operand into dense TF32 hi/lo planes [batch][rows][cols]
@@ -193,6 +198,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int64_t rows, i
   }
 }
 
+long long* g_gemm_dbg = nullptr;
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStream_t st) {
@@ -245,7 +251,7 @@ int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStrea
     if (!encode_map_f32_3d(&mB_lo, B_lo, b_cols, b_rows, batch, b_ld, b_bs, 32, b_box_rows, b_mn != 0)) return 0;
   }
   UmmaGemmParams p{(int)g.M, (int)g.N, (int)g.K, passes == 3 ? 3 : 1, b_mn, g.C, g.C_hi, g.C_lo, g.ldc, g.strideC,
-                   g.alpha, g.beta, g.diag_add, g.bias, g.stride_bias, g.resid};
+                   g.alpha, g.beta, g.diag_add, g.bias, g.stride_bias, g.resid, g_gemm_dbg};
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
