@@ -79,8 +79,11 @@ apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer: raw X tile of this CTA's 128 latents, and this CTA's 128 rows of the T hi/lo tiles =====
-    if (lane == 0) {
+    // ===== TMA producer: raw X tile of this CTA's 128 latents, and this CTA's 128 rows of the T hi/lo tiles.
+    // The whole warp runs the loop and one elected lane issues: with warp-uniform control flow the descriptors stay in
+    // uniform registers (a lane-0-only branch makes the compiler wrap every UTMALDG / UTCHMMA in an elect+R2UR loop,
+    // measured at ~56 clk per instruction instead of ~20).
+    {
       const uint32_t full_t_leader0 = CG == 2 ? map_to_cta(smem_u32(&full_t[0]), 0) : smem_u32(&full_t[0]);
       int it = 0;
       for (int tile = group; tile < total_tiles; tile += n_groups) {
@@ -90,26 +93,32 @@ apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         for (int kt = 0; kt < num_k; ++kt, ++it) {
           const int sx = it % AP_XS, st = it % AP_TS;
           mbar_wait(&empty_x[sx], ((it / AP_XS) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_x[sx], AP_XTILE);
-          tma_load_3d(xraw + sx * AP_XTILE, &mapX, kt * AP_BK, m0, l, &full_x[sx]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_x[sx], AP_XTILE);
+            tma_load_3d(xraw + sx * AP_XTILE, &mapX, kt * AP_BK, m0, l, &full_x[sx]);
+          }
+          __syncwarp();
           mbar_wait(&empty_t[st], ((it / AP_TS) & 1) ^ 1);
           uint8_t* td = tpl + st * AP_TSTAGE;
-          if constexpr (CG == 1) {
-            mbar_arrive_expect_tx(&full_t[st], AP_TSTAGE);
-            tma_load_3d(td, &mapT_hi, kt * AP_BK, n0, l, &full_t[st]);
-            tma_load_3d(td + AP_TPLANE, &mapT_lo, kt * AP_BK, n0, l, &full_t[st]);
-          } else {
-            if (rank == 0) mbar_arrive_expect_tx(&full_t[st], 2 * AP_TSTAGE);   // both CTAs' bytes land on the leader's barrier
-            const uint32_t bar = full_t_leader0 + st * 8;
-            tma_load_3d_cg2(td, &mapT_hi, kt * AP_BK, n0, l, bar);
-            tma_load_3d_cg2(td + AP_TPLANE, &mapT_lo, kt * AP_BK, n0, l, bar);
+          if (elect_one()) {
+            if constexpr (CG == 1) {
+              mbar_arrive_expect_tx(&full_t[st], AP_TSTAGE);
+              tma_load_3d(td, &mapT_hi, kt * AP_BK, n0, l, &full_t[st]);
+              tma_load_3d(td + AP_TPLANE, &mapT_lo, kt * AP_BK, n0, l, &full_t[st]);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&full_t[st], 2 * AP_TSTAGE);   // both CTAs' bytes land on the leader's barrier
+              const uint32_t bar = full_t_leader0 + st * 8;
+              tma_load_3d_cg2(td, &mapT_hi, kt * AP_BK, n0, l, bar);
+              tma_load_3d_cg2(td + AP_TPLANE, &mapT_lo, kt * AP_BK, n0, l, bar);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA of the pair only) =====
-    if (lane == 0 && rank == 0) {
+    // ===== MMA issuer (leader CTA of the pair only): warp-uniform loop, one elected lane issues =====
+    if (rank == 0) {
       const uint32_t idesc = idesc_tf32(AP_BM * CG, BN, 0, 0);
       int it = 0, ti = 0;
       for (int tile = group; tile < total_tiles; tile += n_groups, ++ti) {
@@ -124,18 +133,21 @@ apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           tc_fence_after();
           const uint32_t tb = smem_u32(tpl + st * AP_TSTAGE);
           const uint32_t ab = tmem_base + AP_ACOL0 + sa * 64;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < AP_BK / 8; ++kk) {
-            const uint64_t t_hi = smem_desc_sw128(tb + kk * 32, 16, 1024);
-            const uint64_t t_lo = smem_desc_sw128(tb + AP_TPLANE + kk * 32, 16, 1024);
-            umma_tf32_ts<CG>(acc, ab + 32 + kk * 8, t_hi, idesc, (kt | kk) != 0);   // lo * hi
-            umma_tf32_ts<CG>(acc, ab + kk * 8, t_lo, idesc, 1);                     // hi * lo
-            umma_tf32_ts<CG>(acc, ab + kk * 8, t_hi, idesc, 1);                     // hi * hi
+            for (int kk = 0; kk < AP_BK / 8; ++kk) {
+              const uint64_t t_hi = smem_desc_sw128(tb + kk * 32, 16, 1024);
+              const uint64_t t_lo = smem_desc_sw128(tb + AP_TPLANE + kk * 32, 16, 1024);
+              umma_tf32_ts<CG>(acc, ab + 32 + kk * 8, t_hi, idesc, (kt | kk) != 0);   // lo * hi
+              umma_tf32_ts<CG>(acc, ab + kk * 8, t_lo, idesc, 1);                     // hi * lo
+              umma_tf32_ts<CG>(acc, ab + kk * 8, t_hi, idesc, 1);                     // hi * hi
+            }
+            umma_commit_cg<CG>(&empty_t[st]);
+            umma_commit_cg<CG>(&empty_a[sa]);
+            if (kt == num_k - 1) umma_commit_cg<CG>(&acc_full[a]);
           }
-          umma_commit_cg<CG>(&empty_t[st]);
-          umma_commit_cg<CG>(&empty_a[sa]);
+          __syncwarp();
         }
-        umma_commit_cg<CG>(&acc_full[a]);
       }
     }
   } else if (warp < 10) {
@@ -207,7 +219,7 @@ apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           if (lane == 0) mbar_arrive_cluster(acc_empty_addr + a * 8);
         }
         const uint32_t buf = stage0 + (uint32_t)(nstore & 1) * AP_OUT;
-        if (lane == 0) tma_store_wait_read<1>();                  // the store issued two chunks ago has read this buffer
+        if (elect_one()) tma_store_wait_read<1>();                // the store issued two chunks ago has read this buffer
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -219,13 +231,16 @@ apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && n0 + c0 < dim && m0 < rows) {
-          tma_store_3d(&mapY, buf, n0 + c0, m0, l);
-          tma_store_commit();
+        if (n0 + c0 < dim && m0 < rows) {
+          if (elect_one()) {
+            tma_store_3d(&mapY, buf, n0 + c0, m0, l);
+            tma_store_commit();
+          }
         }
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (elect_one()) tma_store_wait_all<0>();
+    __syncwarp();
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();

@@ -1,19 +1,27 @@
 // K1 on tcgen05: streaming sum (x-c)(x-c)^T and sum (x-c) with fp32-accurate 3xTF32 arithmetic.
 // Reference: GaussianModel._stats (gaussian_model.py:144-157: einsum SYRK + column sum) and fid.py:103-104.
 //
-// The latents X [rows, dim] are row-major, so BOTH operands of X^T X are MN-major: one TMA-loaded tile of
-// 32 latents x 128 features serves as the A operand of one output tile and the B operand of another.  MN-major TF32
-// operands require the 32-byte-atom 128B swizzle (TMA SWIZZLE_128B_ATOM_32B / UMMA layout SWIZZLE_128B_BASE32B).
+// X^T X with row-major latents X [rows, dim]: the reduction index K is the latent row.
+//   A operand = (X^T) block, 128 features per CTA: TMA brings the raw [32 rows x 128 features] tile into shared memory,
+//               converter warps (thread <-> feature = TMEM lane) subtract the pivot, split into TF32 hi / lo and write
+//               both planes into TENSOR MEMORY (tcgen05.st); A never returns to shared memory.
+//   B operand = X block, MN-major in shared memory (32-byte-atom 128B swizzle, the only layout tcgen05 takes for
+//               MN-major TF32): converted in place (hi) plus a second plane (lo).
+//   MMA       = lo*hi + hi*lo + hi*hi, kind::tf32, A from TMEM, fp32 accumulator in TMEM.
+// With CG == 2 a CTA pair (tcgen05 cta_group::2) computes a 256 x 128 block: each CTA converts its own 128 A-features
+// and stages 64 of the 128 B-features, which halves the shared-memory traffic per flop.
 //
-// Pivot shift: the converter warps subtract a per-feature pivot c (an estimate of the mean taken from the head of the
-// batch) before the TF32 hi/lo split, so the fp32 tensor-core accumulation works on centred data and the
-// cancellation in  cov = Sxx/n - mu mu^T  (ot/matrix_utils.py:155-157) is not amplified; the raw sums the reference
-// keeps in its buffers are rebuilt exactly in fp64 by the merge kernel:
+// Pivot shift: the converters subtract a per-feature pivot c (mean of the head of the batch) so that the fp32
+// accumulation works on centred data and the cancellation in cov = Sxx/n - mu mu^T (ot/matrix_utils.py:155-157) is not
+// amplified; the raw sums the reference keeps are rebuilt exactly in fp64 by the unshift kernel:
 //     sum x = S' + n c ,   sum x x^T = P' + c S'^T + S' c^T + n c c^T .
 //
-// One CTA = one upper-triangular pair of 128-wide feature tiles (ti <= tj) x one contiguous range of rows.
-// CTA = 576 threads: warp 0 TMA, warp 1 TMEM alloc + MMA issuer, warps 2-5 convert the i-tile (thread <-> feature
-// column, which also yields the column sums for free), warps 6-9 convert the j-tile, warps 10-17 are the epilogue.
+// TMEM accumulation truncates (error grows with the number of accumulation steps), so every SU_SUB rows the accumulator
+// is handed to the epilogue warps, which add it into fp32 REGISTER accumulators (round-to-nearest) while the next
+// sub-chunk runs into the other TMEM buffer; one fp64 atomic flush per work segment.
+//
+// Work split: the (unit, row) space - unit = (l, block row I, block column j) of the upper block triangle - is cut
+// into equal contiguous ranges, one per CTA (pair); a range that crosses a unit boundary is processed as two segments.
 #include <cuda.h>
 
 #include "otk_ptx.cuh"
@@ -22,176 +30,332 @@
 
 namespace otk {
 
-constexpr int SU_T = 128, SU_BK = 32, SU_STAGES = 3, SU_ACC = 2;
-constexpr int SU_THREADS = 64 + 256 + 256;            // TMA, MMA | 8 converter warps | 8 epilogue warps
-constexpr int SU_TILE = SU_T * SU_BK * 4;            // 16 KiB: four 32-feature slabs of 32 rows x 128 B
-constexpr int SU_STAGE = 4 * SU_TILE;                // i hi (raw in place), i lo, j hi, j lo
-constexpr int SU_SMEM = SU_STAGES * SU_STAGE + 1024 + 256;
-constexpr int SU_SUB = 1024;                         // rows accumulated in TMEM (fp32, truncating adder) per sub-chunk
+constexpr int SU_T = 128, SU_BK = 32;
+constexpr int SU_AS = 4, SU_ACC = 2;                 // A-in-TMEM ring depth; accumulators
+// smem ring depths.  The B ring is the deep one: a B stage is only released by the MMA that consumed it, so its refill
+// (HBM/L2 latency + conversion) must be hidden behind the other stages' MMAs; the raw A ring is released by the converters.
+template <int CG> __host__ __device__ constexpr int su_xs() { return CG == 1 ? 2 : 3; }
+template <int CG> __host__ __device__ constexpr int su_bs() { return CG == 1 ? 4 : 7; }
+constexpr int SU_THREADS = 22 * 32;                  // TMA, MMA | 2x4 A-converter | 2x4 B-converter | 4 epilogue warps
+constexpr int SU_ATILE = SU_T * SU_BK * 4;           // 16 KiB: four 32-feature slabs of [32 rows x 128 B]
+constexpr int SU_SLAB = 32 * SU_BK * 4;              // 4 KiB
+constexpr int SU_SUB = 1024;                         // rows accumulated in TMEM per sub-chunk
+constexpr int SU_ACOL0 = 256;                        // TMEM columns [0,256): two accumulators, [256,512): A ring
+template <int CG> constexpr int su_bplane() { return (4 / CG) * SU_SLAB; }
+constexpr int SU_SACC = SU_T * SU_T * 4;             // 64 KiB fp32 second-stage accumulators [column][row]
+template <int CG> constexpr int su_smem() { return su_xs<CG>() * SU_ATILE + su_bs<CG>() * 2 * su_bplane<CG>() + SU_SACC + 1024 + 512; }
 
-// Persistent: CTA b works on unit (l, tile pair) = b / ctas_per_unit and the row range part = b % ctas_per_unit.
-// The k-step ring (TMA -> converters -> MMA) streams over the whole range; every SU_SUB rows the TMEM accumulator is
-// handed to the epilogue warps, which add it into fp32 REGISTER accumulators (round-to-nearest adds) while the next
-// sub-chunk runs into the other TMEM buffer.  One fp64 atomic flush per CTA at the very end.
+struct SegIter {
+  int64_t cur, end;
+  int rows;
+  __device__ bool next(int& unit, int& r0, int& r1) {
+    if (cur >= end) return false;
+    unit = (int)(cur / rows);
+    r0 = (int)(cur % rows);
+    const int64_t left = end - cur;
+    r1 = (int)(left < (int64_t)(rows - r0) ? r0 + left : rows);
+    cur += r1 - r0;
+    return true;
+  }
+};
+
+// unit -> (l, I, j): block row I of 128*CG features, block column j of 128 features, j >= I*CG
+template <int CG>
+__device__ __forceinline__ void decode_unit(int unit, int upl, int nJ, int& l, int& I, int& j) {
+  l = unit / upl;
+  int w = unit % upl;
+  I = 0;
+  while (w >= nJ - I * CG) { w -= nJ - I * CG; ++I; }
+  j = I * CG + w;
+}
+
+template <int CG>
 __global__ void __launch_bounds__(SU_THREADS, 1)
-stats_umma_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, int rows, int dim,
-                  int rows_per_cta, int ctas_per_unit, int n_tiles, int n_pairs, double* __restrict__ ws_cov,
-                  double* __restrict__ ws_sum) {
+stats_ts_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, int rows, int dim, int upl,
+                int nJ, long long range_len, long long flat_total, int parts, double* __restrict__ ws_cov,
+                double* __restrict__ ws_sum, int dbg) {
   using namespace ptx;
+  constexpr int SU_XS = su_xs<CG>(), SU_BS = su_bs<CG>();
+  constexpr int BSL = 4 / CG;                          // 32-feature slabs of the B block staged by this CTA
+  constexpr int BPLANE = BSL * SU_SLAB, BSTAGE = 2 * BPLANE;
+  constexpr int BROWS = SU_BK / CG;                    // rows of a slab one B-converter warp handles
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SU_STAGES * SU_STAGE);
-  uint64_t* ready = full + SU_STAGES;
-  uint64_t* empty = ready + SU_STAGES;
-  uint64_t* acc_full = empty + SU_STAGES;
+  uint8_t* xa = smem;
+  uint8_t* xb = xa + SU_XS * SU_ATILE;
+  uint8_t* sacc = xb + SU_BS * BSTAGE;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sacc + SU_SACC);        // raw A tile landed
+  uint64_t* empty_ra = full_a + SU_XS;                                   // A converters have read it
+  uint64_t* full_b = empty_ra + SU_XS;                                   // raw B tile landed
+  uint64_t* ready_b = full_b + SU_BS;                                    // B planes converted (leader: both CTAs)
+  uint64_t* empty_b = ready_b + SU_BS;                                   // MMAs reading them retired
+  uint64_t* ready_a = empty_b + SU_BS;                                   // A planes written to TMEM (leader: both CTAs)
+  uint64_t* empty_a = ready_a + SU_AS;                                   // MMAs reading them retired
+  uint64_t* acc_full = empty_a + SU_AS;
   uint64_t* acc_empty = acc_full + SU_ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SU_ACC);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int unit = blockIdx.x / ctas_per_unit, part = blockIdx.x % ctas_per_unit;
-  const int l = unit / n_pairs;
-  int p = unit % n_pairs, ti = 0;
-  while (p >= n_tiles - ti) { p -= n_tiles - ti; ++ti; }
-  const int tj = ti + p;
-  const bool diag = (ti == tj);
-  const int r0 = part * rows_per_cta;
-  const int r1 = min(rows, r0 + rows_per_cta);
-  const int n_rows = max(0, r1 - r0);
-  const int num_k = (n_rows + SU_BK - 1) / SU_BK;                 // k-steps of this CTA
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const int group = CG == 2 ? blockIdx.x / 2 : blockIdx.x;
+  // parts > 0: every unit is cut into the same `parts` row ranges (CTAs working on the same rows of different units run
+  // in lockstep, so X is fetched from HBM once and re-read from L2); parts == 0: equal cuts of the flat (unit, row) space
+  int64_t flat0, flat1;
+  if (parts > 0) {
+    const int64_t ubase = (int64_t)(group / parts) * rows;
+    flat0 = ubase + (int64_t)(group % parts) * range_len;
+    flat1 = flat0 + range_len < ubase + rows ? flat0 + range_len : ubase + rows;
+    if (flat0 > flat1) flat0 = flat1;
+  } else {
+    flat0 = (int64_t)group * range_len;
+    flat1 = flat0 + range_len < flat_total ? flat0 + range_len : flat_total;
+  }
   const int k_per_sub = SU_SUB / SU_BK;
-  const int num_sub = (num_k + k_per_sub - 1) / k_per_sub;
-  const int i0 = ti * SU_T, j0 = tj * SU_T;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
-    for (int s = 0; s < SU_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], diag ? 128 : 256); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < SU_ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
+    for (int s = 0; s < SU_XS; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_ra[s], 4); }
+    for (int s = 0; s < SU_BS; ++s) { mbar_init(&full_b[s], 1); mbar_init(&ready_b[s], 4 * CG); mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < SU_AS; ++s) { mbar_init(&ready_a[s], 4 * CG); mbar_init(&empty_a[s], 1); }
+    for (int a = 0; a < SU_ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4 * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, SU_ACC * SU_T); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc_cg<CG>(tmem_slot, 512); tmem_relinquish_cg<CG>(); }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  SegIter seg{flat0, flat1, rows};
+  int unit, r0, r1, l, I, j;
+
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % SU_STAGES;
-        mbar_wait(&empty[s], ((kt / SU_STAGES) & 1) ^ 1);
-        uint8_t* st = smem + s * SU_STAGE;
-        mbar_arrive_expect_tx(&full[s], (diag ? 1u : 2u) * SU_TILE);
-        const int k0 = r0 + kt * SU_BK;
+    // ===== TMA producer: raw tile of this CTA's 128 A-features and of its 128/CG B-features, 32 latent rows per step.
+    // Warp-uniform loop, one elected lane issues (keeps the descriptors in uniform registers, see apply_umma.cu).
+    {
+      int it = 0;
+      while (seg.next(unit, r0, r1)) {
+        decode_unit<CG>(unit, upl, nJ, l, I, j);
+        const int i0 = I * SU_T * CG + (int)rank * SU_T;
+        const int j0 = j * SU_T + (int)rank * (SU_T / CG);
+        const int num_k = (r1 - r0 + SU_BK - 1) / SU_BK;
+        for (int kt = 0; kt < num_k; ++kt, ++it) {
+          const int sx = it % SU_XS, sb = it % SU_BS;
+          const int k0 = r0 + kt * SU_BK;
+          mbar_wait(&empty_ra[sx], ((it / SU_XS) & 1) ^ 1);
+          if (dbg & 1) {
+            if (elect_one()) mbar_arrive(&full_a[sx]);
+            __syncwarp();
+            mbar_wait(&empty_b[sb], ((it / SU_BS) & 1) ^ 1);
+            if (elect_one()) mbar_arrive(&full_b[sb]);
+            __syncwarp();
+            continue;
+          }
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_a[sx], SU_ATILE);
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-          tma_load_3d(st + sl * 4096, &mapX, i0 + 32 * sl, k0, l, &full[s]);
-          if (!diag) tma_load_3d(st + 2 * SU_TILE + sl * 4096, &mapX, j0 + 32 * sl, k0, l, &full[s]);
+            for (int sl = 0; sl < 4; ++sl) tma_load_3d(xa + sx * SU_ATILE + sl * SU_SLAB, &mapX, i0 + 32 * sl, k0, l, &full_a[sx]);
+          }
+          __syncwarp();
+          mbar_wait(&empty_b[sb], ((it / SU_BS) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_b[sb], BPLANE);
+#pragma unroll
+            for (int sl = 0; sl < BSL; ++sl) tma_load_3d(xb + sb * BSTAGE + sl * SU_SLAB, &mapX, j0 + 32 * sl, k0, l, &full_b[sb]);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(SU_T, SU_T, 1, 1);   // both operands MN-major
-      for (int sub = 0; sub < num_sub; ++sub) {
-        const int a = sub % SU_ACC;
-        mbar_wait(&acc_empty[a], ((sub / SU_ACC) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t acc = tmem_base + a * SU_T;
-        const int kt_end = min(num_k, (sub + 1) * k_per_sub);
-        for (int kt = sub * k_per_sub; kt < kt_end; ++kt) {
-          const int s = kt % SU_STAGES;
-          mbar_wait(&ready[s], (kt / SU_STAGES) & 1);
+    // ===== MMA issuer (leader CTA only): warp-uniform loop, one elected lane issues =====
+    if (rank == 0) {
+      const uint32_t idesc = idesc_tf32(SU_T * CG, SU_T, 0, 1);   // A: TMEM (K-major), B: MN-major
+      int it = 0, subc = 0;
+      while (seg.next(unit, r0, r1)) {
+        const int num_k = (r1 - r0 + SU_BK - 1) / SU_BK;
+        const int num_sub = (num_k + k_per_sub - 1) / k_per_sub;
+        for (int sub = 0; sub < num_sub; ++sub, ++subc) {
+          const int a = subc % SU_ACC;
+          mbar_wait(&acc_empty[a], ((subc / SU_ACC) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t base = smem_u32(smem + s * SU_STAGE);
-          const uint32_t jbase = diag ? base : base + 2 * SU_TILE;
-          const bool first = (kt == sub * k_per_sub);
+          const uint32_t acc = tmem_base + a * SU_T;
+          const int kt_end = min(num_k, (sub + 1) * k_per_sub);
+          for (int kt = sub * k_per_sub; kt < kt_end; ++kt, ++it) {
+            const int sb = it % SU_BS, sa = it % SU_AS;
+            mbar_wait(&ready_b[sb], (it / SU_BS) & 1);
+            mbar_wait(&ready_a[sa], (it / SU_AS) & 1);
+            tc_fence_after();
+            const uint32_t bb = smem_u32(xb + sb * BSTAGE);
+            const uint32_t ab = tmem_base + SU_ACOL0 + sa * 64;
+            const bool first = (kt == sub * k_per_sub);
+            if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < SU_BK / 8; ++kk) {
-            const uint64_t a_hi = smem_desc_mn_tf32(base + kk * 1024, 4096);
-            const uint64_t a_lo = smem_desc_mn_tf32(base + SU_TILE + kk * 1024, 4096);
-            const uint64_t b_hi = smem_desc_mn_tf32(jbase + kk * 1024, 4096);
-            const uint64_t b_lo = smem_desc_mn_tf32(jbase + SU_TILE + kk * 1024, 4096);
-            umma_tf32(acc, a_lo, b_hi, idesc, !(first && kk == 0));
-            umma_tf32(acc, a_hi, b_lo, idesc, 1);
-            umma_tf32(acc, a_hi, b_hi, idesc, 1);
+              for (int kk = 0; kk < SU_BK / 8; ++kk) {
+                if (dbg & 8) break;
+                const uint64_t b_hi = smem_desc_mn_tf32(bb + kk * 1024, SU_SLAB);
+                const uint64_t b_lo = smem_desc_mn_tf32(bb + BPLANE + kk * 1024, SU_SLAB);
+                umma_tf32_ts<CG>(acc, ab + 32 + kk * 8, b_hi, idesc, !(first && kk == 0));   // lo * hi
+                umma_tf32_ts<CG>(acc, ab + kk * 8, b_lo, idesc, 1);                           // hi * lo
+                umma_tf32_ts<CG>(acc, ab + kk * 8, b_hi, idesc, 1);                           // hi * hi
+              }
+              umma_commit_cg<CG>(&empty_b[sb]);
+              umma_commit_cg<CG>(&empty_a[sa]);
+              if (kt == kt_end - 1) umma_commit_cg<CG>(&acc_full[a]);
+            }
+            __syncwarp();
           }
-          umma_commit(&empty[s]);
         }
-        umma_commit(&acc_full[a]);
       }
     }
   } else if (warp < 10) {
-    // ===== converters: thread <-> feature column t of its tile (i-tile: warps 2-5, j-tile: warps 6-9) =====
-    const bool is_j = warp >= 6;
-    const int t = (warp - (is_j ? 6 : 2)) * 32 + lane;
-    if (!(is_j && diag)) {
-      const int col = (is_j ? j0 : i0) + t;
-      const float c = col < dim ? pivot[(int64_t)l * dim + col] : 0.f;
-      const uint32_t slab_off = (uint32_t)(t / 32) * 4096 + (is_j ? 2u * SU_TILE : 0u);
-      const uint32_t cc = (uint32_t)(t % 32) / 8, within = (uint32_t)(t % 8) * 4;
+    // ===== A converters: thread <-> feature (TMEM lane q*32 + lane) of slab q; also yields the column sums.
+    // Two sets of four warps take alternate k-steps, so one step's latency chain (smem read -> split -> tcgen05.st ->
+    // wait) may span two MMA step times.
+    const int q = warp % 4, cset = (warp - 2) / 4;
+    const uint32_t ready_addr = CG == 2 ? map_to_cta(smem_u32(&ready_a[0]), 0) : smem_u32(&ready_a[0]);
+    const uint32_t cc = (uint32_t)lane / 8, within = (uint32_t)(lane % 8) * 4;
+    const uint32_t xbase = smem_u32(xa) + (uint32_t)q * SU_SLAB;
+    int it = 0;
+    while (seg.next(unit, r0, r1)) {
+      decode_unit<CG>(unit, upl, nJ, l, I, j);
+      const int col = I * SU_T * CG + (int)rank * SU_T + q * 32 + lane;
+      const bool in = col < dim;
+      const float c = in ? pivot[(int64_t)l * dim + col] : 0.f;
+      const bool do_sum = (j == I * CG);                     // one unit per block row contributes the column sums
+      const int num_k = (r1 - r0 + SU_BK - 1) / SU_BK;
       double colsum = 0.0;
-      for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % SU_STAGES;
-        mbar_wait(&full[s], (kt / SU_STAGES) & 1);
-        uint8_t* hi_t = smem + s * SU_STAGE + slab_off;
-        uint8_t* lo_t = hi_t + SU_TILE;
-        const int valid = min(SU_BK, r1 - (r0 + kt * SU_BK));   // rows past the range / batch end contribute nothing
+      for (int kt = 0; kt < num_k; ++kt, ++it) {
+        const int sx = it % SU_XS, sa = it % SU_AS;
+        if ((it & 1) != cset) continue;
+        const int valid = in ? min(SU_BK, r1 - (r0 + kt * SU_BK)) : 0;   // rows past the segment end contribute nothing
+        mbar_wait(&full_a[sx], (it / SU_XS) & 1);
+        if (dbg & 2) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_ra[sx]);
+          mbar_wait(&empty_a[sa], ((it / SU_AS) & 1) ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(ready_addr + sa * 8);
+          continue;
+        }
         float part_sum = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < SU_BK; ++r) {
-          const uint32_t off = (uint32_t)r * 128 + ((cc ^ (uint32_t)(r & 3)) * 32) + within;
-          float x = *reinterpret_cast<const float*>(hi_t + off);
-          x = (r < valid && col < dim) ? x - c : 0.f;
-          float h, lo;
-          split_tf32(x, h, lo);
-          *reinterpret_cast<float*>(hi_t + off) = h;
-          *reinterpret_cast<float*>(lo_t + off) = lo;
-          part_sum += x;
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + SU_ACOL0 + sa * 64;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {                        // two halves of 16 rows keep the register footprint low
+          float hi[16], lo[16];
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = h2 * 16 + rr;
+            float x = lds32(xbase + sx * SU_ATILE + (uint32_t)r * 128 + ((cc ^ (uint32_t)(r & 3)) * 32) + within);
+            x = r < valid ? x - c : 0.f;
+            split_tf32_fast(x, hi[rr], lo[rr]);
+            part_sum += x;
+          }
+          if (h2 == 0) { mbar_wait(&empty_a[sa], ((it / SU_AS) & 1) ^ 1); tc_fence_after(); }
+          tmem_st16(ta + h2 * 16, hi);
+          tmem_st16(ta + 32 + h2 * 16, lo);
         }
         colsum += (double)part_sum;
-        fence_proxy_async_smem();
-        mbar_arrive(&ready[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_ra[sx]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ready_addr + sa * 8);
       }
-      if (!is_j && diag && col < dim && num_k > 0) atomicAdd(&ws_sum[(int64_t)l * dim + col], colsum);
+      if (do_sum && in && num_k > 0) atomicAdd(&ws_sum[(int64_t)l * dim + col], colsum);
+    }
+  } else if (warp < 18) {
+    // ===== B converters: warp -> (slab, row range); thread <-> feature; hi in place, lo into the second plane;
+    // two sets of four warps on alternate k-steps =====
+    const int cw = (warp - 10) % 4, cset = (warp - 10) / 4;
+    const int sl = cw / CG, rh = cw % CG;                    // CG == 1: four slabs x 32 rows; CG == 2: two slabs x 2 x 16 rows
+    const uint32_t ready_addr = CG == 2 ? map_to_cta(smem_u32(&ready_b[0]), 0) : smem_u32(&ready_b[0]);
+    const uint32_t cc = (uint32_t)lane / 8, within = (uint32_t)(lane % 8) * 4;
+    const uint32_t bbase = smem_u32(xb) + (uint32_t)sl * SU_SLAB;
+    int it = 0;
+    while (seg.next(unit, r0, r1)) {
+      decode_unit<CG>(unit, upl, nJ, l, I, j);
+      const int col = j * SU_T + (int)rank * (SU_T / CG) + sl * 32 + lane;
+      const bool in = col < dim;
+      const float c = in ? pivot[(int64_t)l * dim + col] : 0.f;
+      const int num_k = (r1 - r0 + SU_BK - 1) / SU_BK;
+      for (int kt = 0; kt < num_k; ++kt, ++it) {
+        const int sb = it % SU_BS;
+        if ((it & 1) != cset) continue;
+        const int valid = in ? min(SU_BK, r1 - (r0 + kt * SU_BK)) : 0;
+        mbar_wait(&full_b[sb], (it / SU_BS) & 1);
+        const uint32_t hb = bbase + sb * BSTAGE;
+#pragma unroll
+        for (int rr = 0; rr < ((dbg & 4) ? 0 : BROWS); ++rr) {
+          const int r = rh * BROWS + rr;
+          const uint32_t off = (uint32_t)r * 128 + ((cc ^ (uint32_t)(r & 3)) * 32) + within;
+          float x = lds32(hb + off);
+          x = r < valid ? x - c : 0.f;
+          float h, lo;
+          split_tf32_fast(x, h, lo);
+          sts32(hb + off, h);
+          sts32(hb + BPLANE + off, lo);
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ready_addr + sb * 8);
+      }
     }
   } else {
-    // ===== epilogue: 8 warps; warp -> (TMEM lane quarter, column half); fp32 register accumulation across sub-chunks ====
-    const int q = warp % 4, half = (warp - 10) / 4;
-    const int gi = i0 + q * 32 + lane;
-    float acc[64];
+    // ===== epilogue: 4 warps (warp <-> TMEM lane quarter); second-stage fp32 accumulation in shared memory =====
+    // sacc[column][row]: the 32 lanes of a warp touch 32 consecutive floats, so the read-modify-write is conflict-free
+    const int q = warp % 4;
+    const uint32_t acc_empty_addr = CG == 2 ? map_to_cta(smem_u32(&acc_empty[0]), 0) : smem_u32(&acc_empty[0]);
+    const uint32_t srow = smem_u32(sacc) + (uint32_t)(q * 32 + lane) * 4;
+    int subc = 0;
+    while (seg.next(unit, r0, r1)) {
+      decode_unit<CG>(unit, upl, nJ, l, I, j);
+      const int num_k = (r1 - r0 + SU_BK - 1) / SU_BK;
+      const int num_sub = (num_k + k_per_sub - 1) / k_per_sub;
+      for (int sub = 0; sub < num_sub; ++sub, ++subc) {
+        const int a = subc % SU_ACC;
+        mbar_wait(&acc_full[a], (subc / SU_ACC) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * SU_T;
+#pragma unroll 1
+        for (int c0 = 0; c0 < SU_T; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (c0 + 32 == SU_T) {                               // accumulator fully read: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_addr + a * 8);
+          }
+          if (sub == 0) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-    for (int sub = 0; sub < num_sub; ++sub) {
-      const int a = sub % SU_ACC;
-      mbar_wait(&acc_full[a], (sub / SU_ACC) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * SU_T + half * 64;
-      {
-        float v[32];
-        tmem_ld32(taddr, v);
-        tmem_ld_wait();
+            for (int jj = 0; jj < 32; ++jj) sts32(srow + (uint32_t)(c0 + jj) * (SU_T * 4), v[jj]);
+          } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] += v[j];
-        tmem_ld32(taddr + 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[32 + j] += v[j];
+            for (int jj = 0; jj < 32; ++jj) {
+              const uint32_t ad = srow + (uint32_t)(c0 + jj) * (SU_T * 4);
+              sts32(ad, lds32(ad) + v[jj]);
+            }
+          }
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[a]);
-    }
-    if (num_k > 0 && gi < dim) {
-      double* cov = ws_cov + (int64_t)l * dim * dim;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const int gj = j0 + half * 64 + j;
-        // diagonal tile pairs: the merge kernel reads the (min, max) element, so only gi <= gj is needed
-        if (gj < dim && (!diag || gi <= gj)) atomicAdd(&cov[(int64_t)gi * dim + gj], (double)acc[j]);
+      // flush: P'[gi][gj] for gi <= gj, stored TRANSPOSED (ws[gj][gi]) so that the 32 lanes of an atomic instruction
+      // hit 32 consecutive doubles; the unshift kernel moves it to the (min, max) position the merge kernel reads
+      const int gi = I * SU_T * CG + (int)rank * SU_T + q * 32 + lane;
+      if (num_k > 0 && gi < dim) {
+        double* cov = ws_cov + (int64_t)l * dim * dim;
+#pragma unroll 4
+        for (int jj = 0; jj < SU_T; ++jj) {
+          const int gj = j * SU_T + jj;
+          if (gj < dim && gi <= gj) atomicAdd(&cov[(int64_t)gj * dim + gi], (double)lds32(srow + (uint32_t)jj * (SU_T * 4)));
+        }
       }
     }
   }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, SU_ACC * SU_T); }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_cg<CG>(tmem_base, 512); }
 }
 
 // pivot[l, :] = mean of the first min(rows, 64) latents of the batch
@@ -206,16 +370,17 @@ __global__ void pivot_kernel(const float* __restrict__ x, int64_t rows, int64_t 
   pivot[l * dim + col] = acc / (float)n;
 }
 
-// ws holds P' = sum (x-c)(x-c)^T (upper tile pairs) and S' = sum (x-c); rebuild the raw sums in place (fp64)
-__global__ void unshift_kernel(double* __restrict__ ws_cov, double* __restrict__ ws_sum, const float* __restrict__ pivot,
+// ws holds P' = sum (x-c)(x-c)^T transposed (element (i <= j) at [j][i]) and S' = sum (x-c); rebuild the raw sums (fp64)
+// at the (min, max) position the merge kernel reads
+__global__ void unshift_kernel(double* __restrict__ ws_cov, const double* __restrict__ ws_sum, const float* __restrict__ pivot,
                                int64_t L, int64_t dim, double rows) {
   const int64_t total = L * dim * dim;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
-    if (i > j) continue;  // the merge kernel only reads (min, max)
+    if (i > j) continue;
     const double ci = pivot[l * dim + i], cj = pivot[l * dim + j];
     const double si = ws_sum[l * dim + i], sj = ws_sum[l * dim + j];
-    ws_cov[e] += ci * sj + si * cj + rows * ci * cj;
+    ws_cov[e] = ws_cov[l * dim * dim + j * dim + i] + ci * sj + si * cj + rows * ci * cj;
   }
 }
 __global__ void unshift_sum_kernel(double* __restrict__ ws_sum, const float* __restrict__ pivot, int64_t n, double rows) {
@@ -225,10 +390,61 @@ __global__ void unshift_sum_kernel(double* __restrict__ ws_sum, const float* __r
 
 size_t stats_umma_extra_workspace(int64_t L, int64_t dim) { return align_up((size_t)L * dim * 4, 256) + 256; }
 
+int g_stats_dbg = 0;        // tuning aid: bit0 no TMA loads, bit1 no A conversion, bit2 no B conversion, bit3 no MMAs
+template <int CG>
+static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, int64_t rows, int64_t dim, double* ws_cov,
+                        double* ws_sum, cudaStream_t st) {
+  auto kern = stats_ts_kernel<CG>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, su_smem<CG>()));
+    attr_set[dev] = true;
+  }
+  const int nJ = (int)ceil_div(dim, SU_T), nI = (int)ceil_div(dim, SU_T * CG);
+  int upl = 0;
+  for (int I = 0; I < nI; ++I) upl += nJ - I * CG;
+  const int64_t flat_total = L * upl * rows;
+  const int64_t max_groups = sm_count() / CG;
+  // equal contiguous ranges of the (unit, row) space; multiples of 32 rows, at least 256 rows each (tiny batches: fewer CTAs)
+  int64_t range_len = ceil_div(ceil_div(flat_total, max_groups), SU_BK) * SU_BK;
+  if (range_len < 256) range_len = 256;
+  int64_t groups = ceil_div(flat_total, range_len);
+  // prefer the aligned cut (same row ranges in every unit) when it keeps >= 90 % of the CTAs busy
+  const int64_t n_units = L * upl;
+  int parts = 0;
+  if (n_units <= max_groups) {
+    int64_t p = max_groups / n_units;
+    int64_t rl = ceil_div(ceil_div(rows, p), SU_BK) * SU_BK;
+    if (rl < 256) rl = 256;
+    p = ceil_div(rows, rl);
+    if (n_units * p * 10 >= groups * 9) { parts = (int)p; range_len = rl; groups = n_units * p; }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(SU_THREADS);
+  cfg.dynamicSmemBytes = su_smem<CG>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, mX, pivot, (int)rows, (int)dim, upl, nJ, (long long)range_len,
+                              (long long)flat_total, parts, ws_cov, ws_sum, g_stats_dbg));
+  OTK_LAUNCH_CHECK();
+  return 1;
+}
+
+int g_stats_force_cg = 0;   // tuning aid: 1 / 2 force the single-CTA / CTA-pair instantiation
+
 int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
                    double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile) {
   if (dim < 64 || dim % 4 != 0 || row_stride % 4 != 0 || batch_stride % 4 != 0) return 0;
-  if (rows < 1 || rows > INT32_MAX || dim > INT32_MAX || L > 65535) return 0;
+  if (rows < 1 || rows > INT32_MAX || dim > 16384 || L > 65535) return 0;
   if (reinterpret_cast<uintptr_t>(x) & 15) return 0;
   if (!tensormap_encoder()) return 0;
   float* pivot = ar.take<float>((size_t)L * dim);
@@ -237,30 +453,15 @@ int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   OTK_LAUNCH_CHECK();
   CUtensorMap mX;
   if (!encode_map_f32_3d(&mX, x, dim, rows, L, row_stride, batch_stride, 32, SU_BK, /*atom32=*/true)) return 0;
-  const int n_tiles = (int)ceil_div(dim, SU_T);
-  const int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
-  const int64_t units = pairs * L;
-  // one CTA per SM when the units fit: each unit's rows are split over ctas_per_unit CTAs (multiples of 32 rows)
-  int64_t cpu = units >= sm_count() ? 1 : sm_count() / units;
-  int64_t rows_per_cta = ceil_div(ceil_div(rows, cpu), SU_BK) * SU_BK;
-  if (rows_per_cta < 256) rows_per_cta = 256;                       // tiny batches: fewer, fuller CTAs
-  cpu = ceil_div(rows, rows_per_cta);
-  if (units * cpu > INT32_MAX) return 0;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OTK_CUDA(cudaFuncSetAttribute(stats_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SU_SMEM));
-    attr_set[dev] = true;
-  }
-  stats_umma_kernel<<<(unsigned)(units * cpu), SU_THREADS, SU_SMEM, st>>>(mX, pivot, (int)rows, (int)dim, (int)rows_per_cta,
-                                                                         (int)cpu, n_tiles, (int)pairs, ws_cov, ws_sum);
-  OTK_LAUNCH_CHECK();
+  const bool pair = g_stats_force_cg ? g_stats_force_cg == 2 : dim >= 512;
+  int used = pair ? launch_stats<2>(mX, pivot, L, rows, dim, ws_cov, ws_sum, st)
+                  : launch_stats<1>(mX, pivot, L, rows, dim, ws_cov, ws_sum, st);
+  if (used <= 0) return used;
   int64_t blocks = ceil_div(L * dim * dim, 256);
   if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
   unshift_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws_cov, ws_sum, pivot, L, dim, (double)rows);
+  OTK_LAUNCH_CHECK();
   unshift_sum_kernel<<<(unsigned)ceil_div(L * dim, 256), 256, 0, st>>>(ws_sum, pivot, L * dim, (double)rows);
-  count_launch(1);
   OTK_LAUNCH_CHECK();
   *tile = SU_T;
   return 1;
