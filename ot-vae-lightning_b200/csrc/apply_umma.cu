@@ -24,21 +24,21 @@
 namespace otk {
 
 constexpr int AP_BM = 128, AP_BK = 32;
-constexpr int AP_XS = 3, AP_TS = 4, AP_AS = 4;       // ring depths: raw X (smem), T planes (smem), converted A (TMEM)
+constexpr int AP_XS = 3, AP_TS = 3, AP_AS = 4;       // ring depths: raw X (smem), T planes (smem), converted A (TMEM)
 constexpr int AP_XTILE = AP_BM * AP_BK * 4;          // 16 KiB raw X tile
 constexpr int AP_TPLANE = 128 * AP_BK * 4;           // 16 KiB: the 128 rows of one T plane a CTA stages per k-step
 constexpr int AP_TSTAGE = 2 * AP_TPLANE;             // hi + lo
 constexpr int AP_OUT = 32 * 32 * 4;                  // 4 KiB staging tile per TMA store
-constexpr int AP_THREADS = 14 * 32;                  // TMA, MMA | 8 converter warps | 4 epilogue warps
+constexpr int AP_THREADS = 18 * 32;                  // TMA, MMA | 8 converter warps | 8 epilogue warps
 constexpr int AP_ACOL0 = 256;                        // TMEM columns [0,256): accumulators, [256,512): A ring
-constexpr int AP_SMEM = AP_XS * AP_XTILE + AP_TS * AP_TSTAGE + 8 * AP_OUT + 1024 + 512;
+constexpr int AP_SMEM = AP_XS * AP_XTILE + AP_TS * AP_TSTAGE + 16 * AP_OUT + 1024 + 512;
 
 template <int CG, int BN>
 __global__ void __launch_bounds__(AP_THREADS, 1)
 apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT_hi,
                 const __grid_constant__ CUtensorMap mapT_lo, const __grid_constant__ CUtensorMap mapY,
                 const float* __restrict__ mean_s, const float* __restrict__ mean_t, int rows, int dim, int m_tiles,
-                int n_tiles, int total_tiles) {
+                int n_tiles, int total_tiles, int dbg) {
   using namespace ptx;
   constexpr int NACC = 256 / BN;                      // accumulator buffers
   static_assert(BN / CG == 128, "each CTA stages 128 rows of the T tile");
@@ -47,7 +47,7 @@ apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   uint8_t* xraw = smem;
   uint8_t* tpl = xraw + AP_XS * AP_XTILE;
   uint8_t* outb = tpl + AP_TS * AP_TSTAGE;
-  uint64_t* full_x = reinterpret_cast<uint64_t*>(outb + 8 * AP_OUT);   // TMA landed the raw X tile
+  uint64_t* full_x = reinterpret_cast<uint64_t*>(outb + 16 * AP_OUT);   // TMA landed the raw X tile
   uint64_t* empty_x = full_x + AP_XS;                                  // converters have read it
   uint64_t* full_t = empty_x + AP_XS;                                  // T planes landed (leader: both CTAs' halves)
   uint64_t* empty_t = full_t + AP_TS;                                  // MMAs reading them retired
@@ -69,7 +69,7 @@ apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     for (int s = 0; s < AP_XS; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 8); }
     for (int s = 0; s < AP_TS; ++s) { mbar_init(&full_t[s], 1); mbar_init(&empty_t[s], 1); }
     for (int s = 0; s < AP_AS; ++s) { mbar_init(&ready_a[s], 8 * CG); mbar_init(&empty_a[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4 * CG); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8 * CG); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc_cg<CG>(tmem_slot, 512); tmem_relinquish_cg<CG>(); }
@@ -195,29 +195,33 @@ apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue: TMEM -> + mean_t -> 32x32 swizzled staging tile -> TMA store; overlaps the next tile's main loop
-    const int q = warp % 4;
+    // ===== epilogue: TMEM -> + mean_t -> 32x32 swizzled staging tile -> TMA store.  Eight warps (two per TMEM lane
+    // quarter, half of the tile's columns each): with a single 256-column accumulator the MMA thread waits for the drain,
+    // so the drain is kept short; with two accumulators it overlaps the next tile's main loop.
+    const int q = warp % 4, half = (warp - 10) / 4;
+    constexpr int HC = BN / 2;                                  // columns drained by this warp
     const uint32_t stage0 = smem_u32(outb) + (uint32_t)(warp - 10) * 2 * AP_OUT;
     const uint32_t acc_empty_addr = CG == 2 ? map_to_cta(smem_u32(&acc_empty[0]), 0) : smem_u32(&acc_empty[0]);
     int ti = 0, nstore = 0;
     for (int tile = group; tile < total_tiles; tile += n_groups, ++ti) {
       const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
       const int m0 = (rem / n_tiles) * (AP_BM * CG) + (int)rank * AP_BM + q * 32;
-      const int n0 = (rem % n_tiles) * BN;
+      const int n0 = (rem % n_tiles) * BN + half * HC;
       const int a = ti % NACC;
       const float* mt = mean_t + (int64_t)l * dim;
       mbar_wait(&acc_full[a], (ti / NACC) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32, ++nstore) {
+      for (int c0 = 0; c0 < HC; c0 += 32, ++nstore) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + c0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + half * HC + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 == BN) {                                      // accumulator fully read: hand it back to the MMA thread
+        if (c0 + 32 == HC) {                                      // this warp's share is read: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(acc_empty_addr + a * 8);
         }
+        if (dbg & 1) continue;
         const uint32_t buf = stage0 + (uint32_t)(nstore & 1) * AP_OUT;
         if (elect_one()) tma_store_wait_read<1>();                // the store issued two chunks ago has read this buffer
         __syncwarp();
@@ -256,6 +260,7 @@ __global__ void split_matrix_kernel(const float* __restrict__ x, int64_t n, floa
   }
 }
 
+int g_apply_dbg = 0;        // tuning aid: bit0 = epilogue drains TMEM but stores nothing
 template <int CG, int BN>
 static int launch_apply(const CUtensorMap& mX, const CUtensorMap& mTh, const CUtensorMap& mTl, const CUtensorMap& mY,
                         const float* ms32, const float* mt32, int64_t L, int64_t rows, int64_t dim, cudaStream_t st) {
@@ -285,7 +290,7 @@ static int launch_apply(const CUtensorMap& mX, const CUtensorMap& mTh, const CUt
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, mX, mTh, mTl, mY, ms32, mt32, (int)rows, (int)dim, (int)m_tiles, (int)n_tiles,
-                              (int)total));
+                              (int)total, g_apply_dbg));
   OTK_LAUNCH_CHECK();
   return 1;
 }

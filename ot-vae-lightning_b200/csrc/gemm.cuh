@@ -6,6 +6,10 @@ enum { ENGINE_AUTO = 0, ENGINE_SIMT = 1, ENGINE_UMMA_3X = 2, ENGINE_UMMA_1X = 3 
 // returns 1 if launched on tcgen05, 0 if not eligible, <0 on error   (gemm_umma.cu)
 int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStream_t st);
 int gemm_f32(const GemmArgs<float>& g, int64_t batch, int engine, cudaStream_t st);
+// one or two independent 3xTF32 products (operands given as hi/lo planes) in one launch; with ctrl != nullptr the launch
+// is a no-op when ctrl[0] <= ctrl_index (device-side iteration limit of the Newton-Schulz loop)   (gemm_umma.cu)
+int gemm_umma_dual(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t batch, const int* ctrl, int ctrl_index,
+                   cudaStream_t st);
 // precision-generic NT product: float -> tcgen05 / FFMA dispatch, double -> DFMA
 inline int gemm_any(const GemmArgs<float>& g, int64_t batch, cudaStream_t st) { return gemm_f32(g, batch, ENGINE_AUTO, st); }
 inline int gemm_any(const GemmArgs<double>& g, int64_t batch, cudaStream_t st) { return gemm_simt<double>(g, batch, st); }

@@ -5,13 +5,19 @@
 //
 // Operands arrive as two TF32-exact planes (hi = rna_tf32(x), lo = rna_tf32(x - hi)); the product is
 //   hi*hi' + hi*lo' + lo*hi'   accumulated in fp32 in TMEM (the dropped lo*lo' term is ~2^-22 relative).
-// Data path: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma kind::tf32 (one elected thread)
-// -> 128 x 128 fp32 accumulator in TMEM -> tcgen05.ld -> registers -> global.
+// Data path: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma kind::tf32 (one elected lane of a
+// warp-uniform loop) -> 128 x BN fp32 accumulator in TMEM -> tcgen05.ld -> registers -> global.
 // A is K-major ([M,K], K contiguous).  B is either K-major ([N,K]: "NT") or N-major ([K,N] row-major: "NN"); the
 // N-major case uses the MN-major canonical UMMA layout so that a true A*B needs no transpose pass.
 //
+// The d x d products of the Newton-Schulz chain are latency-bound (a 512^3 product is 16 tiles of 128 x 128), so
+//   * BN = 64 tiles are used when 128-wide tiles would leave most SMs idle,
+//   * one launch can carry TWO independent products (Y <- Y T and Z <- T Z of an iteration) through blockIdx.z,
+//   * a launch can be made conditional on a device-side iteration limit (`ctrl[0]`), so the host enqueues iterations
+//     without synchronising and the ones past convergence retire immediately.
+//
 // CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-// (warp w reads TMEM lanes 32*(w%4)..+31).  One 128x128 output tile per CTA; UG_STAGES-deep smem ring over K.
+// (warp w reads TMEM lanes 32*(w%4)..+31).  One 128 x BN output tile per CTA; UG_STAGES-deep smem ring over K.
 #include <cuda.h>
 
 #include "gemm.cuh"
@@ -20,11 +26,13 @@
 
 namespace otk {
 
-constexpr int UG_BM = 128, UG_BN = 128, UG_BK = 32, UG_STAGES = 3, UG_THREADS = 192;
-constexpr int UG_TILE_BYTES = UG_BM * UG_BK * 4;                   // 16 KiB per operand plane per stage
-constexpr int UG_STAGE_BYTES = 4 * UG_TILE_BYTES;                  // A_hi, A_lo, B_hi, B_lo
+constexpr int UG_BM = 128, UG_BK = 32, UG_THREADS = 192;
+template <int BN> __host__ __device__ constexpr int ug_stages() { return BN == 128 ? 3 : 4; }
+constexpr int UG_TILE_BYTES = UG_BM * UG_BK * 4;                   // 16 KiB per A plane per stage
 constexpr int UG_XPOSE = 32 * 33 * 4;                              // per-epilogue-warp transpose buffer
-constexpr int UG_SMEM_BYTES = UG_STAGES * UG_STAGE_BYTES + 4 * UG_XPOSE + 1024 /*align*/ + 256 /*barriers*/;
+template <int BN> __host__ __device__ constexpr int ug_btile() { return BN * UG_BK * 4; }
+template <int BN> __host__ __device__ constexpr int ug_stage() { return 2 * UG_TILE_BYTES + 2 * ug_btile<BN>(); }   // A_hi, A_lo, B_hi, B_lo
+template <int BN> __host__ __device__ constexpr int ug_smem() { return ug_stages<BN>() * ug_stage<BN>() + 4 * UG_XPOSE + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct UmmaGemmParams {
   int M, N, K, passes, b_mn_major;
@@ -34,84 +42,87 @@ struct UmmaGemmParams {
   const float* bias;
   int64_t stride_bias;
   double* resid;
-  long long* dbg;   // optional timestamps of CTA 0 (kernel tuning aid)
 };
+struct UmmaGemmMaps { CUtensorMap A_hi, A_lo, B_hi, B_lo; };
 
+template <int BN>
 __global__ void __launch_bounds__(UG_THREADS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
-                 const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
-                 const UmmaGemmParams p) {
+umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_constant__ UmmaGemmMaps maps1,
+                 const UmmaGemmParams p0, const UmmaGemmParams p1, int batch_per_problem, const int* __restrict__ ctrl,
+                 int ctrl_index) {
   using namespace ptx;
+  if (ctrl && ctrl_index >= ctrl[0]) return;       // past the device-side iteration limit: nothing to do
+  constexpr int BTILE = ug_btile<BN>(), STAGE = ug_stage<BN>(), UG_STAGES = ug_stages<BN>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* xpose = reinterpret_cast<float*>(smem + UG_STAGES * UG_STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + UG_STAGES * UG_STAGE_BYTES + 4 * UG_XPOSE);
+  float* xpose = reinterpret_cast<float*>(smem + UG_STAGES * STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + UG_STAGES * STAGE + 4 * UG_XPOSE);
   uint64_t* empty = full + UG_STAGES;
   uint64_t* tmem_full = empty + UG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int m0 = blockIdx.x * UG_BM, n0 = blockIdx.y * UG_BN, batch = blockIdx.z;
+  const bool second = (int)blockIdx.z >= batch_per_problem;          // which of the two products of the launch
+  const UmmaGemmMaps& maps = second ? maps1 : maps0;
+  const UmmaGemmParams& p = second ? p1 : p0;
+  const int m0 = blockIdx.x * UG_BM, n0 = blockIdx.y * BN, batch = (int)blockIdx.z - (second ? batch_per_problem : 0);
   const int num_k = (p.K + UG_BK - 1) / UG_BK;
   const bool three = p.passes == 3;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapA_hi); tma_prefetch_desc(&mapB_hi);
-    if (three) { tma_prefetch_desc(&mapA_lo); tma_prefetch_desc(&mapB_lo); }
+    tma_prefetch_desc(&maps.A_hi); tma_prefetch_desc(&maps.B_hi);
+    if (three) { tma_prefetch_desc(&maps.A_lo); tma_prefetch_desc(&maps.B_lo); }
     for (int s = 0; s < UG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, UG_BN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  if (trace && threadIdx.x == 0) p.dbg[0] = clock64();
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const uint32_t stage_tx = (three ? 4u : 2u) * UG_TILE_BYTES;
-      for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % UG_STAGES, it = kt / UG_STAGES;
-        mbar_wait(&empty[s], (it & 1) ^ 1);
-        if (trace && kt < 24) p.dbg[40 + kt] = clock64();
-        uint8_t* st = smem + s * UG_STAGE_BYTES;
+    // ===== TMA producer: warp-uniform loop, one elected lane issues (descriptors stay in uniform registers) =====
+    const uint32_t stage_tx = (three ? 2u : 1u) * (UG_TILE_BYTES + BTILE);
+    for (int kt = 0; kt < num_k; ++kt) {
+      const int s = kt % UG_STAGES, it = kt / UG_STAGES;
+      mbar_wait(&empty[s], (it & 1) ^ 1);
+      uint8_t* st = smem + s * STAGE;
+      const int k0 = kt * UG_BK;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], stage_tx);
-        const int k0 = kt * UG_BK;
-        tma_load_3d(st, &mapA_hi, k0, m0, batch, &full[s]);
-        if (three) tma_load_3d(st + UG_TILE_BYTES, &mapA_lo, k0, m0, batch, &full[s]);
+        tma_load_3d(st, &maps.A_hi, k0, m0, batch, &full[s]);
+        if (three) tma_load_3d(st + UG_TILE_BYTES, &maps.A_lo, k0, m0, batch, &full[s]);
         if (!p.b_mn_major) {
-          tma_load_3d(st + 2 * UG_TILE_BYTES, &mapB_hi, k0, n0, batch, &full[s]);
-          if (three) tma_load_3d(st + 3 * UG_TILE_BYTES, &mapB_lo, k0, n0, batch, &full[s]);
+          tma_load_3d(st + 2 * UG_TILE_BYTES, &maps.B_hi, k0, n0, batch, &full[s]);
+          if (three) tma_load_3d(st + 2 * UG_TILE_BYTES + BTILE, &maps.B_lo, k0, n0, batch, &full[s]);
         } else {
-          // B is [K, N] row-major: four 32(n) x 32(k) boxes per plane, one per 128-byte MN slab
+          // B is [K, N] row-major: BN/32 boxes of 32(n) x 32(k) per plane, one per 128-byte MN slab
 #pragma unroll
-          for (int sl = 0; sl < 4; ++sl) {
-            tma_load_3d(st + 2 * UG_TILE_BYTES + sl * 4096, &mapB_hi, n0 + 32 * sl, k0, batch, &full[s]);
-            if (three) tma_load_3d(st + 3 * UG_TILE_BYTES + sl * 4096, &mapB_lo, n0 + 32 * sl, k0, batch, &full[s]);
+          for (int sl = 0; sl < BN / 32; ++sl) {
+            tma_load_3d(st + 2 * UG_TILE_BYTES + sl * 4096, &maps.B_hi, n0 + 32 * sl, k0, batch, &full[s]);
+            if (three) tma_load_3d(st + 2 * UG_TILE_BYTES + BTILE + sl * 4096, &maps.B_lo, n0 + 32 * sl, k0, batch, &full[s]);
           }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(UG_BM, UG_BN, 0, p.b_mn_major);
-      const uint32_t b_kstep = p.b_mn_major ? 1024u : 32u;        // bytes per UMMA_K = 8 along K
-      for (int kt = 0; kt < num_k; ++kt) {
-        const int s = kt % UG_STAGES, it = kt / UG_STAGES;
-        mbar_wait(&full[s], it & 1);
-        if (trace && kt < 24) p.dbg[8 + kt] = clock64();
-        tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * UG_STAGE_BYTES);
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+    const uint32_t idesc = idesc_tf32(UG_BM, BN, 0, p.b_mn_major);
+    const uint32_t b_kstep = p.b_mn_major ? 1024u : 32u;        // bytes per UMMA_K = 8 along K
+    for (int kt = 0; kt < num_k; ++kt) {
+      const int s = kt % UG_STAGES, it = kt / UG_STAGES;
+      mbar_wait(&full[s], it & 1);
+      tc_fence_after();
+      const uint32_t base = smem_u32(smem + s * STAGE);
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < UG_BK / 8; ++kk) {
           const uint64_t a_hi = smem_desc_sw128(base + kk * 32, 16, 1024);
           const uint64_t a_lo = smem_desc_sw128(base + UG_TILE_BYTES + kk * 32, 16, 1024);
-          const uint32_t b_hi_addr = base + 2 * UG_TILE_BYTES + kk * b_kstep, b_lo_addr = b_hi_addr + UG_TILE_BYTES;
+          const uint32_t b_hi_addr = base + 2 * UG_TILE_BYTES + kk * b_kstep, b_lo_addr = b_hi_addr + BTILE;
           const uint64_t b_hi = p.b_mn_major ? smem_desc_mn_tf32(b_hi_addr, 4096) : smem_desc_sw128(b_hi_addr, 16, 1024);
           const uint64_t b_lo = p.b_mn_major ? smem_desc_mn_tf32(b_lo_addr, 4096) : smem_desc_sw128(b_lo_addr, 16, 1024);
           if (three) {
@@ -123,8 +134,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
           }
         }
         umma_commit(&empty[s]);                    // frees the smem stage when these MMAs have read it
+        if (kt == num_k - 1) umma_commit(tmem_full);   // accumulator complete
       }
-      umma_commit(tmem_full);                      // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (per-warp 32x32 smem transpose) -> global =====
@@ -134,7 +146,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     float* xp = xpose + (warp - 2) * (32 * 33);
     const int mrow0 = m0 + q * 32;
     mbar_wait(tmem_full, 0);
-    if (trace && warp == 2 && lane == 0) p.dbg[1] = clock64();
     tc_fence_after();
     float* C = p.C ? p.C + (int64_t)batch * p.strideC : nullptr;
     float* Ch = p.C_hi ? p.C_hi + (int64_t)batch * p.strideC : nullptr;
@@ -142,7 +153,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     const float* bias = p.bias ? p.bias + (int64_t)batch * p.stride_bias : nullptr;
     double res = 0.0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < UG_BN; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
       tmem_ld_wait();
@@ -178,11 +189,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
       if (lane == 0) atomicAdd(&p.resid[batch], res);
     }
     tc_fence_before();
-    if (trace && warp == 2 && lane == 0) p.dbg[2] = clock64();
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, UG_BN); }
-  if (trace && threadIdx.x == 0) p.dbg[3] = clock64();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
 // elementwise split of a strided [batch][rows][cols] operand into dense TF32 hi/lo planes [batch][rows][cols]
@@ -198,18 +207,22 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int64_t rows, i
   }
 }
 
-long long* g_gemm_dbg = nullptr;
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStream_t st) {
-  // ---- eligibility
+struct PreparedGemm {
+  UmmaGemmMaps maps;
+  UmmaGemmParams p;
+};
+
+// eligibility, operand planes (splitting A / B into scratch when no lo plane is given) and tensor maps of one product
+static int prepare_gemm(const GemmArgs<float>& g, int64_t batch, int passes, int bn, cudaStream_t st, PreparedGemm* out) {
   if (g.a_off || g.sak != 1) return 0;                               // A must be K-major, no centring here
   const bool b_kmajor = (g.sbk == 1), b_nmajor = (g.sbn == 1);
   if (!b_kmajor && !b_nmajor) return 0;
   const int b_mn = b_kmajor ? 0 : 1;
   const int64_t lda = g.sam, ldb = b_kmajor ? g.sbn : g.sbk;
   if (g.M < 64 || g.N < 64 || g.K < 8) return 0;                     // tiny problems: FFMA engine
-  if (g.M > INT32_MAX || g.N > INT32_MAX || g.K > INT32_MAX || batch > 65535) return 0;
+  if (g.M > INT32_MAX || g.N > INT32_MAX || g.K > INT32_MAX || batch > 32767) return 0;
   if ((lda % 4) || (ldb % 4) || (g.strideA % 4) || (g.strideB % 4)) return 0;   // TMA: 16-byte strides
   if (!aligned16(g.A) || !aligned16(g.B) || (g.A_lo && !aligned16(g.A_lo)) || (g.B_lo && !aligned16(g.B_lo))) return 0;
   if (!g.C && !(g.C_hi && g.C_lo)) return 0;
@@ -217,7 +230,6 @@ int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStrea
   if ((need_split_a || need_split_b) && !g.scratch) return 0;
   if (!tensormap_encoder()) return 0;
 
-  // ---- operand planes
   const float *A_hi = g.A, *A_lo = g.A_lo, *B_hi = g.B, *B_lo = g.B_lo;
   int64_t a_ld = lda, a_bs = g.strideA, b_ld = ldb, b_bs = g.strideB;
   const int64_t b_rows = b_mn ? g.K : g.N, b_cols = b_mn ? g.N : g.K;
@@ -240,30 +252,64 @@ int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStrea
   }
   if ((a_ld % 4) || (b_ld % 4)) return 0;
 
-  // ---- tensor maps: [batch][rows][cols] fp32, 128B swizzle, box 32 cols x {128 | 32} rows
-  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
-  const int b_box_rows = b_mn ? 32 : UG_BN;
-  if (!encode_map_f32_3d(&mA_hi, A_hi, g.K, g.M, batch, a_ld, a_bs, 32, UG_BM)) return 0;
-  if (!encode_map_f32_3d(&mB_hi, B_hi, b_cols, b_rows, batch, b_ld, b_bs, 32, b_box_rows, b_mn != 0)) return 0;
-  mA_lo = mA_hi; mB_lo = mB_hi;
+  // tensor maps: [batch][rows][cols] fp32, 128B swizzle, box 32 cols x {128 | BN | 32} rows
+  const int b_box_rows = b_mn ? 32 : bn;
+  if (!encode_map_f32_3d(&out->maps.A_hi, A_hi, g.K, g.M, batch, a_ld, a_bs, 32, UG_BM)) return 0;
+  if (!encode_map_f32_3d(&out->maps.B_hi, B_hi, b_cols, b_rows, batch, b_ld, b_bs, 32, b_box_rows, b_mn != 0)) return 0;
+  out->maps.A_lo = out->maps.A_hi; out->maps.B_lo = out->maps.B_hi;
   if (passes == 3) {
-    if (!encode_map_f32_3d(&mA_lo, A_lo, g.K, g.M, batch, a_ld, a_bs, 32, UG_BM)) return 0;
-    if (!encode_map_f32_3d(&mB_lo, B_lo, b_cols, b_rows, batch, b_ld, b_bs, 32, b_box_rows, b_mn != 0)) return 0;
+    if (!encode_map_f32_3d(&out->maps.A_lo, A_lo, g.K, g.M, batch, a_ld, a_bs, 32, UG_BM)) return 0;
+    if (!encode_map_f32_3d(&out->maps.B_lo, B_lo, b_cols, b_rows, batch, b_ld, b_bs, 32, b_box_rows, b_mn != 0)) return 0;
   }
-  UmmaGemmParams p{(int)g.M, (int)g.N, (int)g.K, passes == 3 ? 3 : 1, b_mn, g.C, g.C_hi, g.C_lo, g.ldc, g.strideC,
-                   g.alpha, g.beta, g.diag_add, g.bias, g.stride_bias, g.resid, g_gemm_dbg};
+  out->p = UmmaGemmParams{(int)g.M, (int)g.N, (int)g.K, passes == 3 ? 3 : 1, b_mn, g.C, g.C_hi, g.C_lo, g.ldc, g.strideC,
+                          g.alpha, g.beta, g.diag_add, g.bias, g.stride_bias, g.resid};
+  return 1;
+}
+
+template <int BN>
+static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, const int* ctrl,
+                       int ctrl_index, cudaStream_t st) {
+  auto kern = umma_gemm_kernel<BN>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OTK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM_BYTES));
+    OTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ug_smem<BN>()));
     attr_set[dev] = true;
   }
-  dim3 grid((unsigned)ceil_div(g.M, UG_BM), (unsigned)ceil_div(g.N, UG_BN), (unsigned)batch);
-  if (grid.y > 65535) return 0;
-  umma_gemm_kernel<<<grid, UG_THREADS, UG_SMEM_BYTES, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  dim3 grid((unsigned)ceil_div(a.p.M, UG_BM), (unsigned)ceil_div(a.p.N, BN), (unsigned)(batch * n_problems));
+  if (grid.y > 65535 || grid.z > 65535) return 0;
+  kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index);
   OTK_LAUNCH_CHECK();
   return 1;
+}
+
+// 64-wide tiles when 128-wide ones would fill less than half of the SMs
+static int pick_bn(int64_t M, int64_t N, int64_t batch, int n_problems) {
+  const int64_t ctas128 = ceil_div(M, UG_BM) * ceil_div(N, 128) * batch * n_problems;
+  return ctas128 * 2 <= sm_count() ? 64 : 128;
+}
+
+int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStream_t st) {
+  const int bn = pick_bn(g.M, g.N, batch, 1);
+  PreparedGemm a;
+  int r = prepare_gemm(g, batch, passes, bn, st, &a);
+  if (r <= 0) return r;
+  return bn == 64 ? launch_gemm<64>(a, a, 1, batch, nullptr, 0, st) : launch_gemm<128>(a, a, 1, batch, nullptr, 0, st);
+}
+
+// two independent products of identical shape in one launch, optionally conditional on ctrl[0] > ctrl_index
+int gemm_umma_dual(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t batch, const int* ctrl, int ctrl_index,
+                   cudaStream_t st) {
+  const int n_problems = g1 ? 2 : 1;
+  if (g1 && (g0.M != g1->M || g0.N != g1->N || g0.K != g1->K)) return 0;
+  const int bn = pick_bn(g0.M, g0.N, batch, n_problems);
+  PreparedGemm a, b;
+  int r = prepare_gemm(g0, batch, 3, bn, st, &a);
+  if (r <= 0) return r;
+  if (g1) { r = prepare_gemm(*g1, batch, 3, bn, st, &b); if (r <= 0) return r; } else b = a;
+  return bn == 64 ? launch_gemm<64>(a, b, n_problems, batch, ctrl, ctrl_index, st)
+                  : launch_gemm<128>(a, b, n_problems, batch, ctrl, ctrl_index, st);
 }
 
 }  // namespace otk

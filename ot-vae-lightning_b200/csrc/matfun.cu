@@ -118,19 +118,48 @@ __global__ void w2_trace_kernel(const void* ms, const void* mt, const void* cs, 
   if (threadIdx.x == 0) w2[l] = acc;
 }
 
-// rel[l] = || R_l - target_l ||_F / || target_l ||_F    (one block per l)
-__global__ void rel_residual_kernel(const float* R, const float* target, int64_t dim, double* rel) {
+// acc[2l] += || R_l - target_l ||_F^2 , acc[2l+1] += || target_l ||_F^2    (grid = blocks x L; acc zeroed by the caller)
+__global__ void rel_residual_kernel(const float* R, const float* target, int64_t dim, double* acc) {
   __shared__ double red[32];
-  const int64_t l = blockIdx.x;
+  const int64_t l = blockIdx.y;
   double num = 0, den = 0;
-  for (int64_t e = threadIdx.x; e < dim * dim; e += blockDim.x) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < dim * dim; e += (int64_t)gridDim.x * blockDim.x) {
     double t = target[l * dim * dim + e], df = (double)R[l * dim * dim + e] - t;
     num += df * df;
     den += t * t;
   }
   num = block_sum(num, red);
   den = block_sum(den, red);
-  if (threadIdx.x == 0) rel[l] = sqrt(num / fmax(den, 1e-300));
+  if (threadIdx.x == 0) { atomicAdd(&acc[2 * l], num); atomicAdd(&acc[2 * l + 1], den); }
+}
+
+// Device-side control of the Newton-Schulz loop.  ctrl[0] = number of iterations to execute (kernels of iteration
+// k >= ctrl[0] retire immediately), ctrl[1] = verdict, ctrl[2] = diverged.  Runs after the Z*Y product of iteration k,
+// whose epilogue accumulated resid_k[l] = ||I - Z_k Y_k||_F^2; mirrors the stopping rule the host used to apply after a
+// synchronisation per iteration.
+__global__ void ns_ctrl_init_kernel(int* ctrl, int max_iters, int verdict0) {
+  if (threadIdx.x == 0) { ctrl[0] = max_iters; ctrl[1] = verdict0; ctrl[2] = 0; ctrl[3] = 0; }
+}
+__global__ void ns_ctrl_kernel(const double* resid_k, int64_t L, int k, int max_iters, double tol_done, double tol_near,
+                               int* ctrl) {
+  __shared__ double red[32];
+  if (k >= ctrl[0]) return;
+  if (!(k >= 5 || k + 1 == max_iters)) return;
+  double worst = 0;
+  for (int64_t l = threadIdx.x; l < L; l += blockDim.x) {
+    const double r = resid_k[l];
+    const double v = (r == r && r <= 1e30) ? r : 1e300;
+    worst = v > worst ? v : worst;
+  }
+  worst = warp_max(worst);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = worst;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)blockDim.x / 32; ++w) worst = red[w] > worst ? red[w] : worst;
+    if (worst >= 1e300) { ctrl[0] = k + 1; ctrl[1] = 1; ctrl[2] = 1; }          // diverged: numerically indefinite input
+    else if (worst < tol_done) { if (k + 1 < ctrl[0]) ctrl[0] = k + 1; ctrl[1] = 0; }
+    else if (worst < tol_near) { if (k + 2 < ctrl[0]) ctrl[0] = k + 2; ctrl[1] = 0; }
+  }
 }
 
 template <typename T>
@@ -148,10 +177,11 @@ struct NsWork {
   W *Yh[2], *Yl[2], *Zh[2], *Zl[2], *Th, *Tl;
   W* scratch;         // 4 planes: operand splits for the products outside the iteration
   double *c, *resid;  // c [L]; resid [NS_MAX_ITERS][L]
+  int* ctrl;          // device-side loop control (ns_ctrl_kernel)
   static constexpr int kPlanes = sizeof(W) == 4 ? 5 + 10 + 4 : 5;
   static size_t bytes(int64_t L, int64_t d) {
     return kPlanes * align_up((size_t)L * d * d * sizeof(W), 256) + align_up((size_t)L * 8, 256) +
-           align_up((size_t)NS_MAX_ITERS * L * 8, 256);
+           align_up((size_t)NS_MAX_ITERS * L * 8, 256) + 256;
   }
   void carve(Arena& ar, int64_t L, int64_t d) {
     const size_t n = (size_t)L * d * d;
@@ -166,6 +196,7 @@ struct NsWork {
     }
     c = ar.take<double>((size_t)L);
     resid = ar.take<double>((size_t)NS_MAX_ITERS * L);
+    ctrl = ar.take<int>(16);
   }
 };
 static size_t ns_work_bytes(int64_t L, int64_t d) {
@@ -192,11 +223,14 @@ __global__ void join_planes_kernel(const float* hi, const float* lo, int64_t n, 
     out[e] = hi[e] + lo[e];
 }
 static bool ns_planes_eligible(int64_t d) { return d >= 64 && d % 4 == 0; }
-static int plane_gemm(const float* Ah, const float* Al, const float* Bh, const float* Bl, float* Ch, float* Cl, int64_t d,
-                      int64_t L, float alpha, float diag, double* resid, cudaStream_t st) {
+static GemmArgs<float> plane_args(const float* Ah, const float* Al, const float* Bh, const float* Bl, float* Ch, float* Cl,
+                                  int64_t d, float alpha, float diag, double* resid) {
   GemmArgs<float> g = nn_args_t<float>(Ah, Bh, nullptr, d, d * d, alpha);
   g.A_lo = Al; g.B_lo = Bl; g.C_hi = Ch; g.C_lo = Cl; g.diag_add = diag; g.resid = resid;
-  int r = gemm_umma_try(g, L, 3, st);
+  return g;
+}
+static int plane_gemm2(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t L, const int* ctrl, int k, cudaStream_t st) {
+  int r = gemm_umma_dual(g0, g1, L, ctrl, k, st);
   if (r == 0) { set_last_error_msg("sqrtm: tcgen05 engine rejected an eligible shape"); return OTK_ERR_CUDA; }
   return r < 0 ? r : OTK_OK;
 }
@@ -225,45 +259,59 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
   const int max_iters = adaptive ? budget : (iters < NS_MAX_ITERS ? iters : NS_MAX_ITERS);
   // quadratic convergence: once ||I - ZY||_F^2 < tol_near one more update lands on the floor
   const double tol_done = f32 ? 1e-9 : 1e-22, tol_near = f32 ? 9e-4 : 1e-8;
-  int cur = 0, stop_at = max_iters;
-  *verdict = adaptive ? NS_SLOW : NS_CONVERGED;
-  double host_res[256];
-  for (int k = 0; k < max_iters && k < stop_at; ++k) {
-    bool done_planes = false;
-    if constexpr (sizeof(W) == 4) {
-      if (planes) {
-        OTK_TRY(plane_gemm(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, L, -0.5f, 1.5f, w.resid + (size_t)k * L, st));
-        OTK_TRY(plane_gemm(w.Yh[cur], w.Yl[cur], w.Th, w.Tl, w.Yh[cur ^ 1], w.Yl[cur ^ 1], d, L, 1.f, 0.f, nullptr, st));
-        OTK_TRY(plane_gemm(w.Th, w.Tl, w.Zh[cur], w.Zl[cur], w.Zh[cur ^ 1], w.Zl[cur ^ 1], d, L, 1.f, 0.f, nullptr, st));
-        done_planes = true;
-      }
-    }
-    if (!done_planes) {
-      GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.T, d, dd, W(-0.5));
-      g.diag_add = W(1.5);
-      g.resid = w.resid + (size_t)k * L;
-      OTK_TRY(gemm_any(g, L, st));
-      OTK_TRY(gemm_any(nn_args_t<W>(w.Y[cur], w.T, w.Y[cur ^ 1], d, dd, W(1)), L, st));
-      OTK_TRY(gemm_any(nn_args_t<W>(w.T, w.Z[cur], w.Z[cur ^ 1], d, dd, W(1)), L, st));
-    }
-    cur ^= 1;
-    if (adaptive && (k >= 5 || k + 1 == max_iters)) {
-      double worst = 0;
-      for (int64_t l0 = 0; l0 < L; l0 += 256) {
-        int64_t nl = L - l0 < 256 ? L - l0 : 256;
-        OTK_CUDA(cudaMemcpyAsync(host_res, w.resid + (size_t)k * L + l0, (size_t)nl * 8, cudaMemcpyDeviceToHost, st));
-        OTK_CUDA(cudaStreamSynchronize(st));
-        for (int64_t l = 0; l < nl; ++l) {
-          if (!(host_res[l] == host_res[l]) || host_res[l] > 1e30) { worst = 1e300; break; }
-          if (host_res[l] > worst) worst = host_res[l];
+  // The host enqueues iterations without waiting: the stopping rule runs on the device (ns_ctrl_kernel) and the kernels
+  // of iterations past ctrl[0] retire immediately.  One readback after the first NS_FIRST_BATCH iterations, then one per
+  // NS_NEXT_BATCH, instead of one host synchronisation per iteration.
+  constexpr int NS_FIRST_BATCH = 12, NS_NEXT_BATCH = 4;
+  ns_ctrl_init_kernel<<<1, 32, 0, st>>>(w.ctrl, max_iters, adaptive ? NS_SLOW : NS_CONVERGED);
+  OTK_LAUNCH_CHECK();
+  int h_ctrl[4] = {max_iters, adaptive ? NS_SLOW : NS_CONVERGED, 0, 0};
+  int enq = 0;
+  while (enq < max_iters) {
+    int n = adaptive ? (enq == 0 ? (planes ? NS_FIRST_BATCH : 6) : (planes ? NS_NEXT_BATCH : 1)) : max_iters;
+    if (enq + n > max_iters) n = max_iters - enq;
+    for (int k = enq; k < enq + n; ++k) {
+      const int cur = k & 1;
+      bool done_planes = false;
+      if constexpr (sizeof(W) == 4) {
+        if (planes) {
+          GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, -0.5f, 1.5f, w.resid + (size_t)k * L);
+          OTK_TRY(plane_gemm2(zy, nullptr, L, w.ctrl, k, st));
+          if (adaptive) {
+            ns_ctrl_kernel<<<1, 256, 0, st>>>(w.resid + (size_t)k * L, L, k, max_iters, tol_done, tol_near, w.ctrl);
+            OTK_LAUNCH_CHECK();
+          }
+          GemmArgs<float> yt = plane_args(w.Yh[cur], w.Yl[cur], w.Th, w.Tl, w.Yh[cur ^ 1], w.Yl[cur ^ 1], d, 1.f, 0.f, nullptr);
+          GemmArgs<float> tz = plane_args(w.Th, w.Tl, w.Zh[cur], w.Zl[cur], w.Zh[cur ^ 1], w.Zl[cur ^ 1], d, 1.f, 0.f, nullptr);
+          OTK_TRY(plane_gemm2(yt, &tz, L, w.ctrl, k, st));
+          done_planes = true;
         }
       }
-      if (worst >= 1e300) { *verdict = NS_SLOW; break; }  // diverged (numerically indefinite input)
-      // resid[k] is ||I - Z_k Y_k||_F^2 of the state BEFORE update k
-      if (worst < tol_done) { stop_at = k + 1; *verdict = NS_CONVERGED; }
-      else if (worst < tol_near) { stop_at = k + 2; *verdict = NS_CONVERGED; }
+      if (!done_planes) {
+        // generic engines (FFMA / DFMA): the launches are unconditional, so they are only enqueued up to the next readback
+        GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.T, d, dd, W(-0.5));
+        g.diag_add = W(1.5);
+        g.resid = w.resid + (size_t)k * L;
+        OTK_TRY(gemm_any(g, L, st));
+        OTK_TRY(gemm_any(nn_args_t<W>(w.Y[cur], w.T, w.Y[cur ^ 1], d, dd, W(1)), L, st));
+        OTK_TRY(gemm_any(nn_args_t<W>(w.T, w.Z[cur], w.Z[cur ^ 1], d, dd, W(1)), L, st));
+        if (adaptive) {
+          ns_ctrl_kernel<<<1, 256, 0, st>>>(w.resid + (size_t)k * L, L, k, max_iters, tol_done, tol_near, w.ctrl);
+          OTK_LAUNCH_CHECK();
+        }
+      }
     }
+    enq += n;
+    if (!adaptive) break;
+    OTK_CUDA(cudaMemcpyAsync(h_ctrl, w.ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, st));
+    OTK_CUDA(cudaStreamSynchronize(st));
+    if (h_ctrl[0] <= enq) break;   // converged (or diverged) within what has been enqueued
   }
+  // conditional (tcgen05) launches stop at ctrl[0]; the unconditional engines executed everything that was enqueued
+  const int executed = planes ? (h_ctrl[0] < enq ? h_ctrl[0] : enq) : enq;
+  int cur = executed & 1;
+  const int stop_at = h_ctrl[0];
+  *verdict = h_ctrl[1];
   if constexpr (sizeof(W) == 4) {
     if (planes) {
       join_planes_kernel<<<ew_grid(L * dd), 256, 0, st>>>(w.Yh[cur], w.Yl[cur], L * dd, w.Y[cur]);
@@ -379,11 +427,13 @@ static int operator_impl(const void* cov_s, const void* cov_t, int64_t L, int64_
       OTK_LAUNCH_CHECK();
       OTK_TRY(gemm_any(with_scratch(nn_args_t<float>(T0, Cs32, G, d, dd, 1.f), w.scratch), L, st));
       OTK_TRY(gemm_any(with_scratch(nn_args_t<float>(G, T0, Q32, d, dd, 1.f), w.scratch), L, st));
-      rel_residual_kernel<<<(unsigned)L, 256, 0, st>>>(Q32, Ct32, d, w.resid);
+      OTK_CUDA(cudaMemsetAsync(w.resid, 0, (size_t)2 * L * 8, st));
+      rel_residual_kernel<<<dim3(32, (unsigned)L), 256, 0, st>>>(Q32, Ct32, d, w.resid);
       OTK_LAUNCH_CHECK();
-      double host_rel[256];
-      OTK_CUDA(cudaMemcpyAsync(host_rel, w.resid, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+      double host_rel[512];
+      OTK_CUDA(cudaMemcpyAsync(host_rel, w.resid, (size_t)2 * L * 8, cudaMemcpyDeviceToHost, st));
       OTK_CUDA(cudaStreamSynchronize(st));
+      for (int64_t l = 0; l < L; ++l) host_rel[l] = sqrt(host_rel[2 * l] / fmax(host_rel[2 * l + 1], 1e-300));
       for (int64_t l = 0; l < L; ++l)
         if (!(host_rel[l] < NS_F32_RICCATI_TOL)) *verdict = NS_SLOW;
     }
