@@ -215,7 +215,12 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.otk_launch_count()
+    profiling = os.environ.get("OTK_PROFILE_TIMED") == "1"     # ncu --profile-from-start off: only the timed region
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStart()
     total_ms, w2 = timed(step_device, args.steps)
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = lib.otk_launch_count() - launches0
     ms_per_step = total_ms / args.steps
     value = world * N_LAT / (ms_per_step * 1e-3)

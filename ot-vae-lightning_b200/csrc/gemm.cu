@@ -12,7 +12,7 @@ int gemm_f32(const GemmArgs<float>& g, int64_t batch, int engine, cudaStream_t s
   return gemm_simt<float>(g, batch, st);
 }
 }  // namespace otk
-namespace otk { extern int g_apply_force_cg; extern int g_stats_force_cg; extern int g_stats_dbg; extern int g_apply_dbg; }
+namespace otk { extern int g_apply_force_cg; extern int g_stats_force_cg; extern int g_stats_dbg; extern int g_apply_dbg; extern int g_fs_fast; }
 using namespace otk;
 // tuning aids (not part of include/otk.h)
 // tuning aid: 0 = automatic, 1 / 2 = force the single-CTA / CTA-pair apply kernel
@@ -20,6 +20,7 @@ extern "C" void otkdbg_set_apply_cg(int cg) { g_apply_force_cg = cg; }
 extern "C" void otkdbg_set_stats_cg(int cg) { g_stats_force_cg = cg; }
 extern "C" void otkdbg_set_stats_dbg(int m) { g_stats_dbg = m; }
 extern "C" void otkdbg_set_apply_dbg(int m) { g_apply_dbg = m; }
+extern "C" void otkdbg_set_sinkhorn_fast(int m) { g_fs_fast = m; }
 static int gemm_export(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                        int64_t ldc, int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC, float alpha, float beta,
                        int engine, bool nn, void* workspace, size_t workspace_bytes, otk_stream_t stream) {

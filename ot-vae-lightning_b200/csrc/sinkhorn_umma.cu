@@ -27,7 +27,7 @@ constexpr int FS_SLAB_BYTES = 128 * 128, FS_MAX_SLABS = 2, FS_QSTAGES = 3, FS_SB
 constexpr int FS_THREADS = 64 + 4 * 128;   // TMA warp, MMA warp, four softmax warpgroups
 constexpr int FS_P_BYTES = 2 * FS_MAX_SLABS * FS_SLAB_BYTES;       // 64 KiB: two 128-row sub-blocks
 constexpr int FS_Q_BYTES = FS_MAX_SLABS * FS_SLAB_BYTES;            // 32 KiB per stage
-constexpr int FS_SMEM = FS_P_BYTES + FS_QSTAGES * FS_Q_BYTES + 1024 /*align*/ + 4096 /*bias staging, barriers*/;
+constexpr int FS_SMEM = FS_P_BYTES + FS_QSTAGES * FS_Q_BYTES + 1024 /*align*/ + 4096 /*bias staging*/ + 512 /*barriers*/;
 constexpr float FS_NEG = -1.0e30f;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
@@ -38,6 +38,13 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// packed fp32 pairs (FFMA2 / FADD2: one issue slot for two lanes of work) and the 3-input maximum (FMNMX3)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // Operands are FP16 planes of the points divided by sigma = max |coordinate| (10-bit mantissa, the same rounding as
@@ -48,16 +55,17 @@ __global__ void __launch_bounds__(FS_THREADS, 1)
 fused_lse_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ,
                  const float* __restrict__ bias2, const float* __restrict__ nq, float g2_unit,
                  const float* __restrict__ sig2, int Np, int Nq, int dim, int tiles_per_split, float* __restrict__ part_m,
-                 float* __restrict__ part_l, float* __restrict__ part_c, const FsState* __restrict__ state) {
+                 float* __restrict__ part_l, float* __restrict__ part_c, const FsState* __restrict__ state,
+                 const float* __restrict__ lse_prev, const float* __restrict__ dmax) {
   using namespace ptx;
   if (state && state->done) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sP = smem;                                   // [sub][slab][128 rows x 128 B]
   uint8_t* sQ = smem + FS_P_BYTES;                      // [stage][slab][128 rows x 128 B]
-  float* s_bias = reinterpret_cast<float*>(smem + FS_P_BYTES + FS_QSTAGES * FS_Q_BYTES);   // [4 groups][64]
-  float* s_nq = s_bias + 256;                                                                // [4 groups][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_nq + 256);
+  float* s_bias = reinterpret_cast<float*>(smem + FS_P_BYTES + FS_QSTAGES * FS_Q_BYTES);   // [2 buffers][4 groups][64]
+  float* s_nq = s_bias + 512;                                                                // [2 buffers][4 groups][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_nq + 512);
   uint64_t* p_full = bars;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = q_full + FS_QSTAGES;
@@ -136,18 +144,43 @@ fused_lse_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
     const int sub = grp >> 1, half = grp & 1;
     const int tid = (warp - 2) % 4 * 32 + lane;          // 0..127 inside the warpgroup
     const int q4 = warp % 4;                             // TMEM lane quarter of this warp
-    float* sb = s_bias + grp * 64;
-    float* sn = s_nq + grp * 64;
     const float k2 = COST ? -2.f / g2_unit : 0.f;       // t - bias2 = g2_unit * (x.y)  ->  -2 x.y
     float m = -3.0e38f, l = 0.f, lc = 0.f;
+    // Bounded-shift mode (Sinkhorn iterations >= 2): every row's LSE of the previous iteration is known and the biases
+    // moved by at most *dmax since, so U = lse_prev + dmax + 1 bounds every exponent of the row from above and
+    // overestimates the new LSE by < 2 dmax + 2.  With dmax < 32 the sum of 2^(t - U) can neither overflow nor
+    // vanish, and the running maximum (a second sweep over the tile plus a rescale) is not needed at all.
+    bool fast = false;
+    if constexpr (!COST) {
+      if (lse_prev != nullptr) {
+        const float dm = *dmax;
+        if (dm < 32.f) {
+          fast = true;
+          const int r = min(pb * FS_BM + sub * FS_SUB + q4 * 32 + lane, Np - 1);
+          m = lse_prev[r] + dm + 1.f;
+        }
+      }
+    }
+    const f2 NU = pack2(-m, -m);
+    // bias / |q|^2 of a Q tile are staged in shared memory by the first 64 threads of the warpgroup, double-buffered and
+    // loaded one tile ahead, so a tile costs one named barrier and no exposed global-load latency
+    float nx_bias = FS_NEG, nx_nq = 0.f;
+    {
+      const int qcol = jt0 * FS_BN + half * 64 + tid;
+      if (tid < 64 && n_tiles > 0 && qcol < Nq) { nx_bias = bias2[qcol]; if (COST) nx_nq = nq[qcol]; }
+    }
     for (int idx = 0; idx < n_tiles; ++idx) {
       const int b = 2 * (idx % 2) + sub;
-      const int qcol = (jt0 + idx) * FS_BN + half * 64 + tid;
-      float my_bias = FS_NEG, my_nq = 0.f;
-      if (tid < 64 && qcol < Nq) { my_bias = bias2[qcol]; if (COST) my_nq = nq[qcol]; }
-      named_bar(1 + grp, 128);                           // everyone is done reading the previous tile's staging
-      if (tid < 64) { sb[tid] = my_bias; if (COST) sn[tid] = my_nq; }
-      named_bar(1 + grp, 128);
+      float* sb = s_bias + (idx & 1) * 256 + grp * 64;
+      float* sn = s_nq + (idx & 1) * 256 + grp * 64;
+      if (tid < 64) {
+        sb[tid] = nx_bias;
+        if (COST) sn[tid] = nx_nq;
+        const int qcol = (jt0 + idx + 1) * FS_BN + half * 64 + tid;
+        nx_bias = FS_NEG; nx_nq = 0.f;
+        if (idx + 1 < n_tiles && qcol < Nq) { nx_bias = bias2[qcol]; if (COST) nx_nq = nq[qcol]; }
+      }
+      named_bar(1 + grp, 128);                           // staging of this tile visible; buffer of tile idx-1 is free
       mbar_wait(&s_full[b], (idx / 2) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * FS_BN + half * 64;
@@ -157,6 +190,67 @@ fused_lse_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[b]);                          // the accumulator buffer can be refilled already
+      if constexpr (!COST) {
+        if (fast) {
+          const f2 G = pack2(g2, g2);
+          f2 acc0 = pack2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+#pragma unroll
+          for (int j = 0; j < 64; j += 8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + j), b1 = *reinterpret_cast<const float4*>(sb + j + 4);
+            const f2 xa = add2(fma2(pack2(v[j], v[j + 1]), G, pack2(b0.x, b0.y)), NU);
+            const f2 xb = add2(fma2(pack2(v[j + 2], v[j + 3]), G, pack2(b0.z, b0.w)), NU);
+            const f2 xc = add2(fma2(pack2(v[j + 4], v[j + 5]), G, pack2(b1.x, b1.y)), NU);
+            const f2 xd = add2(fma2(pack2(v[j + 6], v[j + 7]), G, pack2(b1.z, b1.w)), NU);
+            float x0, x1;
+            f2 ea, eb, ec, ed;
+            unpack2(xa, x0, x1); ea = pack2(ex2(x0), ex2(x1));
+            unpack2(xb, x0, x1); eb = pack2(ex2(x0), ex2(x1));
+            unpack2(xc, x0, x1); ec = pack2(ex2(x0), ex2(x1));
+            unpack2(xd, x0, x1); ed = pack2(ex2(x0), ex2(x1));
+            acc0 = add2(acc0, ea); acc1 = add2(acc1, eb); acc2 = add2(acc2, ec); acc3 = add2(acc3, ed);
+          }
+          float s0, s1;
+          unpack2(add2(add2(acc0, acc1), add2(acc2, acc3)), s0, s1);
+          l += s0 + s1;
+          continue;
+        }
+        // packed path: t = g2 s + bias (FFMA2), running maximum (FMNMX3), 2^(t - max) on the MUFU pipe for
+        // 2^(t - max) on the MUFU pipe, packed accumulation (FADD2).  (A degree-4 polynomial 2^x on the FMA pipe for a
+        // fraction of the pairs was measured SLOWER on B200 - the kernel runs at the 1000 W power cap - and was removed.)
+        f2 t[32];
+        const f2 G = pack2(g2, g2);
+        float cm0 = -3.0e38f, cm1 = -3.0e38f, cm2 = -3.0e38f, cm3 = -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < 64; j += 8) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sb + j), b1 = *reinterpret_cast<const float4*>(sb + j + 4);
+          t[j / 2] = fma2(pack2(v[j], v[j + 1]), G, pack2(b0.x, b0.y));
+          t[j / 2 + 1] = fma2(pack2(v[j + 2], v[j + 3]), G, pack2(b0.z, b0.w));
+          t[j / 2 + 2] = fma2(pack2(v[j + 4], v[j + 5]), G, pack2(b1.x, b1.y));
+          t[j / 2 + 3] = fma2(pack2(v[j + 6], v[j + 7]), G, pack2(b1.z, b1.w));
+          float x0, x1;
+          unpack2(t[j / 2], x0, x1); cm0 = max3(cm0, x0, x1);
+          unpack2(t[j / 2 + 1], x0, x1); cm1 = max3(cm1, x0, x1);
+          unpack2(t[j / 2 + 2], x0, x1); cm2 = max3(cm2, x0, x1);
+          unpack2(t[j / 2 + 3], x0, x1); cm3 = max3(cm3, x0, x1);
+        }
+        const float m_new = fmaxf(max3(m, cm0, cm1), fmaxf(cm2, cm3));
+        l *= ex2(m - m_new);
+        const f2 NM = pack2(-m_new, -m_new);
+        f2 acc0 = pack2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const f2 x = add2(t[q], NM);
+          float x0, x1;
+          unpack2(x, x0, x1);
+          const f2 e = pack2(ex2(x0), ex2(x1));
+          if (q & 1) acc1 = add2(acc1, e); else acc0 = add2(acc0, e);
+        }
+        float s0, s1;
+        unpack2(add2(acc0, acc1), s0, s1);
+        l += s0 + s1;
+        m = m_new;
+        continue;
+      }
       float cm0 = -3.0e38f, cm1 = -3.0e38f, cm2 = -3.0e38f, cm3 = -3.0e38f;
 #pragma unroll
       for (int j = 0; j < 64; j += 4) {
@@ -233,10 +327,11 @@ __global__ void fs_prep_kernel(const float* __restrict__ x, int64_t n, int64_t d
 __global__ void fs_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ pl, int parts, int64_t n, int mode,
                                    const float* __restrict__ marg, const float* __restrict__ sq, float nrm_scale,
                                    float* __restrict__ pot, float* __restrict__ bias2_out, float* __restrict__ out_m,
-                                   float* __restrict__ out_l, float* __restrict__ diff, const FsState* state) {
+                                   float* __restrict__ out_l, float* __restrict__ diff, const FsState* state,
+                                   float* __restrict__ lse_out = nullptr, float* __restrict__ dmax_out = nullptr) {
   if (state && state->done) return;
   __shared__ float red[32];
-  float acc = 0.f;
+  float acc = 0.f, dmx = 0.f;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     float m = pm[r], l = pl[r];
     for (int p = 1; p < parts; ++p) {
@@ -250,14 +345,20 @@ __global__ void fs_finalize_kernel(const float* __restrict__ pm, const float* __
       const float bnat = logf(marg[r] + 1e-8f) - L;
       const float pn = bnat + sq[r] * nrm_scale;
       acc += fabsf(pn - pot[r]);
+      dmx = fmaxf(dmx, fabsf(pn - pot[r]));
       pot[r] = pn;
       bias2_out[r] = bnat * LOG2E;
+      if (lse_out) lse_out[r] = m + log2f(l);       // base-2 LSE of this row: next iteration's shift
     } else if (mode == 1) {
       out_m[r] = m * LN2;
       out_l[r] = l;
     } else {
       out_m[r] = sq[r] + m;
     }
+  }
+  if (mode == 0 && dmax_out) {                     // largest move of a bias of this side, in base-2 units
+    dmx = warp_max(dmx);
+    if (threadIdx.x % 32 == 0) atomicMax(reinterpret_cast<unsigned*>(dmax_out), __float_as_uint(dmx * LOG2E));
   }
   if (mode == 0 && diff) {
     acc = warp_sum(acc);
@@ -274,14 +375,20 @@ __global__ void fs_bias_kernel(const float* __restrict__ pot, const float* __res
     bias2[r] = (pot ? pot[r] - sq[r] * nrm_scale : -sq[r] * nrm_scale) * LOG2E;
 }
 
-__global__ void fs_check_kernel(float* diff, double threshold, FsState* state) {
+__global__ void fs_check_kernel(float* diff, double threshold, FsState* state, float* dmax_next_x = nullptr,
+                                float* dmax_next_y = nullptr) {
   if (state->done) return;
+  if (dmax_next_x) { *dmax_next_x = 0.f; *dmax_next_y = 0.f; }
   const double d = (double)diff[0] + (double)diff[1];
   diff[0] = 0.f; diff[1] = 0.f;
   state->iters += 1;
   if (d < threshold) state->done = 1;
 }
-__global__ void fs_init_state_kernel(FsState* st, float* diff) { st->done = 0; st->iters = 0; diff[0] = 0.f; diff[1] = 0.f; }
+// diff[0..1]: sum |delta potential| of the two sides; diff[16..19]: max |delta bias| slots, [side][iteration parity]
+__global__ void fs_init_state_kernel(FsState* st, float* diff) {
+  st->done = 0; st->iters = 0; diff[0] = 0.f; diff[1] = 0.f;
+  diff[16] = 0.f; diff[17] = 0.f; diff[18] = 0.f; diff[19] = 0.f;
+}
 
 __global__ void fs_max_reduce_kernel(const float* __restrict__ rowmax, int64_t n, float* out) {
   float mx = 0.f;
@@ -348,14 +455,14 @@ struct FsSide {           // one point cloud, prepared
 
 struct FsWork {
   FsSide X, Y;
-  float *biasX2, *biasY2, *pm, *pl, *pc, *diff, *scratch_n, *sig;
+  float *biasX2, *biasY2, *pm, *pl, *pc, *diff, *scratch_n, *sig, *lseX, *lseY;
   FsState* state;
   int max_parts;
 };
 
 size_t sk_umma_workspace_bytes(int64_t N, int64_t M, int64_t dim) {
   const int64_t mx = N > M ? N : M;
-  return align_up((size_t)N * dim * 2, 256) + align_up((size_t)M * dim * 2, 256) + 6 * align_up((size_t)mx * 4, 256) +
+  return align_up((size_t)N * dim * 2, 256) + align_up((size_t)M * dim * 2, 256) + 8 * align_up((size_t)mx * 4, 256) +
          3 * align_up((size_t)64 * mx * 4, 256) + 8192;
 }
 
@@ -368,6 +475,8 @@ static int fs_carve(FsWork& w, const float* x, const float* y, int64_t N, int64_
   w.biasX2 = ar.take<float>((size_t)N);
   w.biasY2 = ar.take<float>((size_t)M);
   w.scratch_n = ar.take<float>((size_t)mx);
+  w.lseX = ar.take<float>((size_t)N);
+  w.lseY = ar.take<float>((size_t)M);
   w.max_parts = 64;
   w.pm = ar.take<float>((size_t)64 * mx);
   w.pl = ar.take<float>((size_t)64 * mx);
@@ -391,24 +500,26 @@ static int fs_carve(FsWork& w, const float* x, const float* y, int64_t N, int64_
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OTK_CUDA(cudaFuncSetAttribute(fused_lse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
     OTK_CUDA(cudaFuncSetAttribute(fused_lse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+    OTK_CUDA(cudaFuncSetAttribute(fused_lse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
     attr_set[dev] = true;
   }
   return OTK_OK;
 }
 
+int g_fs_fast = 1;    // tuning aid: 0 disables the bounded-shift mode
 // one pass: partials of LSE_q(bias2_q + g2 * p.q) for every row of P; returns the number of parts written
 template <bool COST>
 static int fs_pass(const FsSide& P, const FsSide& Q, const float* biasQ2, float g2, const float* sig2, int64_t dim, float* pm,
-                   float* pl, float* pc, const FsState* state, int* parts_out, cudaStream_t st) {
+                   float* pl, float* pc, const FsState* state, int* parts_out, cudaStream_t st,
+                   const float* lse_prev = nullptr, const float* dmax = nullptr) {
   const int splits = fs_splits(P.n, Q.n);
   const int64_t qtiles = ceil_div(Q.n, FS_BN);
   const int tps = (int)ceil_div(qtiles, splits);
   const int parts = (int)ceil_div(qtiles, tps);
   dim3 grid((unsigned)ceil_div(P.n, FS_BM), (unsigned)parts);
-  fused_lse_kernel<COST><<<grid, FS_THREADS, FS_SMEM, st>>>(P.map, Q.map, biasQ2, Q.sq, g2, sig2, (int)P.n, (int)Q.n,
-                                                          (int)dim, tps, pm, pl, pc, state);
+  fused_lse_kernel<COST><<<grid, FS_THREADS, FS_SMEM, st>>>(P.map, Q.map, biasQ2, Q.sq, g2, sig2, (int)P.n, (int)Q.n, (int)dim, tps, pm, pl, pc,
+                                          state, g_fs_fast ? lse_prev : nullptr, dmax);
   OTK_LAUNCH_CHECK();
   *parts_out = 2 * parts;   // two column halves per split
   return OTK_OK;
@@ -464,13 +575,20 @@ int sk_umma_solve(const float* x, const float* y, int64_t N, int64_t M, int64_t 
   int parts = 0;
   for (int it = 0; it < max_iter; ++it) {
     // v first: rows = Y, reduce over X (bias from u) ; then u: rows = X, reduce over Y (bias from the new v)
-    OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, w.state, &parts, st));
+    // max |delta bias| slots: dX = diff[16 + parity], dY = diff[18 + parity]; the first iteration has no previous LSE
+    float* dX_prev = w.diff + 16 + ((it + 1) & 1);
+    float* dX_cur = w.diff + 16 + (it & 1);
+    float* dY_cur = w.diff + 18 + (it & 1);
+    float* dY_next = w.diff + 18 + ((it + 1) & 1);
+    OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, w.state, &parts, st,
+                           it > 0 ? w.lseY : nullptr, dX_prev));
     fs_finalize_kernel<<<fs_grid(M), 256, 0, st>>>(w.pm, w.pl, parts, M, 0, b, w.Y.sq, nrm_scale, v, w.biasY2, nullptr, nullptr,
-                                                  w.diff + 1, w.state);
-    OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, w.state, &parts, st));
+                                                  w.diff + 1, w.state, w.lseY, dY_cur);
+    OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, w.state, &parts, st,
+                           it > 0 ? w.lseX : nullptr, dY_cur));
     fs_finalize_kernel<<<fs_grid(N), 256, 0, st>>>(w.pm, w.pl, parts, N, 0, a, w.X.sq, nrm_scale, u, w.biasX2, nullptr, nullptr,
-                                                  w.diff, w.state);
-    fs_check_kernel<<<1, 1, 0, st>>>(w.diff, threshold, w.state);
+                                                  w.diff, w.state, w.lseX, dX_cur);
+    fs_check_kernel<<<1, 1, 0, st>>>(w.diff, threshold, w.state, dX_prev, dY_next);
     count_launch(2);
     OTK_LAUNCH_CHECK();
     if (threshold > 0 && (it + 1) % poll_every == 0 && it + 1 < max_iter) {

@@ -79,23 +79,33 @@ stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_
   if (ti == tj && tid < ST_T && i0 + tid < dim) atomicAdd(&ws_sum[l * dim + i0 + tid], colsum);
 }
 
-// merge the fp64 staging area into the running buffers (mirror the lower triangle, apply the EMA rule)
-__global__ void stats_merge_kernel(const double* __restrict__ ws_cov, const double* __restrict__ ws_sum, int64_t L,
-                                   int64_t dim, int tile, double rows, double decay, void* n_obs, int n_dtype,
-                                   void* sum, void* sum_cov, int buf_dtype) {
+// merge the fp64 staging area into the running buffers (mirror the lower triangle, apply the EMA rule).
+// pivot == nullptr: the staging area holds the raw sums, element (i <= j) at [i][j].
+// pivot != nullptr: it holds the pivot-shifted sums of the tcgen05 kernel, P' transposed (element (i <= j) at [j][i]) and
+//   S'; the raw sums are rebuilt exactly in fp64:  sum x = S' + n c ,  sum x x^T = P' + c S'^T + S' c^T + n c c^T .
+__global__ void stats_merge_kernel(const double* __restrict__ ws_cov, const double* __restrict__ ws_sum,
+                                   const float* __restrict__ pivot, int64_t L, int64_t dim, double rows, double decay,
+                                   void* n_obs, int n_dtype, void* sum, void* sum_cov, int buf_dtype) {
   const int64_t total = L * dim * dim;
   const double keep = decay < 0 ? 1.0 : decay, gain = decay < 0 ? 1.0 : 1.0 - decay;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
     // only tiles with tile(i) <= tile(j) were accumulated; always reading the (min, max) element also makes the
     // result exactly symmetric
-    (void)tile;
     const int64_t lo_i = i < j ? i : j, hi_j = i < j ? j : i;
-    double v = ws_cov[l * dim * dim + lo_i * dim + hi_j];
+    double v;
+    if (pivot) {
+      const double ci = pivot[l * dim + lo_i], cj = pivot[l * dim + hi_j];
+      const double si = ws_sum[l * dim + lo_i], sj = ws_sum[l * dim + hi_j];
+      v = ws_cov[l * dim * dim + hi_j * dim + lo_i] + ci * sj + si * cj + rows * ci * cj;
+    } else {
+      v = ws_cov[l * dim * dim + lo_i * dim + hi_j];
+    }
     store_real(sum_cov, e, buf_dtype, load_real(sum_cov, e, buf_dtype) * keep + v * gain);
     if (r < dim) {
       int64_t s = l * dim + r;
-      store_real(sum, s, buf_dtype, load_real(sum, s, buf_dtype) * keep + ws_sum[s] * gain);
+      const double sv = ws_sum[s] + (pivot ? rows * (double)pivot[s] : 0.0);
+      store_real(sum, s, buf_dtype, load_real(sum, s, buf_dtype) * keep + sv * gain);
     }
     if (r == 0) store_real(n_obs, l, n_dtype, load_real(n_obs, l, n_dtype) * keep + rows * gain);
   }
@@ -173,11 +183,13 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
   double* ws_sum = ar.take<double>((size_t)L * dim);
   OTK_CUDA(cudaMemsetAsync(workspace, 0, align_up((size_t)L * dim * dim * 8, 256) + (size_t)L * dim * 8, st));
   int tile = ST_T;
+  const float* pivot = nullptr;
   if (rows > 0) {
-    int used = stats_umma_try(x, L, rows, dim, row_stride, batch_stride, ws_cov, ws_sum, ar, st, &tile);
+    int used = stats_umma_try(x, L, rows, dim, row_stride, batch_stride, ws_cov, ws_sum, ar, st, &tile, &pivot);
     if (used < 0) return used;
     if (!used) {
       tile = ST_T;
+      pivot = nullptr;
       int n_tiles = (int)ceil_div(dim, ST_T);
       int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
       // enough chunks for ~4 waves, chunk length a multiple of ST_BK
@@ -192,7 +204,7 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
       OTK_LAUNCH_CHECK();
     }
   }
-  stats_merge_kernel<<<ew_grid(L * dim * dim), 256, 0, st>>>(ws_cov, ws_sum, L, dim, tile, (double)rows, decay, n_obs,
+  stats_merge_kernel<<<ew_grid(L * dim * dim), 256, 0, st>>>(ws_cov, ws_sum, pivot, L, dim, (double)rows, decay, n_obs,
                                                             n_dtype, sum, sum_cov, buf_dtype);
   OTK_LAUNCH_CHECK();
   return OTK_OK;

@@ -13,7 +13,7 @@
 //
 // Pivot shift: the converters subtract a per-feature pivot c (mean of the head of the batch) so that the fp32
 // accumulation works on centred data and the cancellation in cov = Sxx/n - mu mu^T (ot/matrix_utils.py:155-157) is not
-// amplified; the raw sums the reference keeps are rebuilt exactly in fp64 by the unshift kernel:
+// amplified; the raw sums the reference keeps are rebuilt exactly in fp64 by the merge kernel (stats.cu):
 //     sum x = S' + n c ,   sum x x^T = P' + c S'^T + S' c^T + n c c^T .
 //
 // TMEM accumulation truncates (error grows with the number of accumulation steps), so every SU_SUB rows the accumulator
@@ -341,7 +341,7 @@ stats_ts_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         }
       }
       // flush: P'[gi][gj] for gi <= gj, stored TRANSPOSED (ws[gj][gi]) so that the 32 lanes of an atomic instruction
-      // hit 32 consecutive doubles; the unshift kernel moves it to the (min, max) position the merge kernel reads
+      // hit 32 consecutive doubles; the merge kernel reads the transposed position
       const int gi = I * SU_T * CG + (int)rank * SU_T + q * 32 + lane;
       if (num_k > 0 && gi < dim) {
         double* cov = ws_cov + (int64_t)l * dim * dim;
@@ -358,34 +358,23 @@ stats_ts_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
   if (warp == 1) { tc_fence_after(); tmem_dealloc_cg<CG>(tmem_base, 512); }
 }
 
-// pivot[l, :] = mean of the first min(rows, 64) latents of the batch
+// pivot[l, :] = mean of the first min(rows, 64) latents of the batch.  Block = 32 features x 8 row groups.
 __global__ void pivot_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
                              float* __restrict__ pivot) {
+  __shared__ float part[8][33];
   const int64_t l = blockIdx.y;
-  const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (col >= dim) return;
+  const int64_t col = blockIdx.x * 32 + threadIdx.x;
   const int64_t n = rows < 64 ? rows : 64;
   float acc = 0.f;
-  for (int64_t r = 0; r < n; ++r) acc += x[l * batch_stride + r * row_stride + col];
-  pivot[l * dim + col] = acc / (float)n;
-}
-
-// ws holds P' = sum (x-c)(x-c)^T transposed (element (i <= j) at [j][i]) and S' = sum (x-c); rebuild the raw sums (fp64)
-// at the (min, max) position the merge kernel reads
-__global__ void unshift_kernel(double* __restrict__ ws_cov, const double* __restrict__ ws_sum, const float* __restrict__ pivot,
-                               int64_t L, int64_t dim, double rows) {
-  const int64_t total = L * dim * dim;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
-    if (i > j) continue;
-    const double ci = pivot[l * dim + i], cj = pivot[l * dim + j];
-    const double si = ws_sum[l * dim + i], sj = ws_sum[l * dim + j];
-    ws_cov[e] = ws_cov[l * dim * dim + j * dim + i] + ci * sj + si * cj + rows * ci * cj;
+  if (col < dim)
+    for (int64_t r = threadIdx.y; r < n; r += 8) acc += x[l * batch_stride + r * row_stride + col];
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < dim) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) acc += part[g][threadIdx.x];
+    pivot[l * dim + col] = acc / (float)n;
   }
-}
-__global__ void unshift_sum_kernel(double* __restrict__ ws_sum, const float* __restrict__ pivot, int64_t n, double rows) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e < n) ws_sum[e] += rows * (double)pivot[e];
 }
 
 size_t stats_umma_extra_workspace(int64_t L, int64_t dim) { return align_up((size_t)L * dim * 4, 256) + 256; }
@@ -442,14 +431,14 @@ static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, in
 int g_stats_force_cg = 0;   // tuning aid: 1 / 2 force the single-CTA / CTA-pair instantiation
 
 int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
-                   double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile) {
+                   double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile, const float** pivot_out) {
   if (dim < 64 || dim % 4 != 0 || row_stride % 4 != 0 || batch_stride % 4 != 0) return 0;
   if (rows < 1 || rows > INT32_MAX || dim > 16384 || L > 65535) return 0;
   if (reinterpret_cast<uintptr_t>(x) & 15) return 0;
   if (!tensormap_encoder()) return 0;
   float* pivot = ar.take<float>((size_t)L * dim);
   if (!ar.ok()) return OTK_ERR_WORKSPACE;
-  pivot_kernel<<<dim3((unsigned)ceil_div(dim, 128), (unsigned)L), 128, 0, st>>>(x, rows, dim, row_stride, batch_stride, pivot);
+  pivot_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, row_stride, batch_stride, pivot);
   OTK_LAUNCH_CHECK();
   CUtensorMap mX;
   if (!encode_map_f32_3d(&mX, x, dim, rows, L, row_stride, batch_stride, 32, SU_BK, /*atom32=*/true)) return 0;
@@ -457,12 +446,7 @@ int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   int used = pair ? launch_stats<2>(mX, pivot, L, rows, dim, ws_cov, ws_sum, st)
                   : launch_stats<1>(mX, pivot, L, rows, dim, ws_cov, ws_sum, st);
   if (used <= 0) return used;
-  int64_t blocks = ceil_div(L * dim * dim, 256);
-  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-  unshift_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws_cov, ws_sum, pivot, L, dim, (double)rows);
-  OTK_LAUNCH_CHECK();
-  unshift_sum_kernel<<<(unsigned)ceil_div(L * dim, 256), 256, 0, st>>>(ws_sum, pivot, L * dim, (double)rows);
-  OTK_LAUNCH_CHECK();
+  *pivot_out = pivot;     // the merge kernel rebuilds the raw sums from (P' transposed, S', pivot)
   *tile = SU_T;
   return 1;
 }

@@ -3,8 +3,9 @@
 #include "otk_common.cuh"
 namespace otk {
 size_t stats_umma_extra_workspace(int64_t L, int64_t dim);
-// returns 1 if the tcgen05 kernel handled the update (and sets *tile to its output tile size),
-// 0 if the shape is not eligible, <0 on error.
+// returns 1 if the tcgen05 kernel handled the update (and sets *tile to its output tile size and *pivot_out to the
+// per-feature pivot: the staging area then holds P' = sum (x-c)(x-c)^T TRANSPOSED (element (i <= j) at [j][i]) and
+// S' = sum (x-c)), 0 if the shape is not eligible, <0 on error.
 int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
-                   double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile);
+                   double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile, const float** pivot_out);
 }  // namespace otk
