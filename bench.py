@@ -154,6 +154,9 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,8 +188,9 @@ def main():
         return float(t.item())
 
     # ---- workload: every rank owns its own 2^20 source / target latents (weak scaling)
-    src = gaussian_latents(N_LAT, D_LAT, seed=1234 + rank, device=dev)
-    tgt = gaussian_latents(N_LAT, D_LAT, seed=4321 + rank, device=dev, shift=0.5, scale=1.5)
+    # of the SAME two distributions (the ranks differ in the draws, as the shards of one validation set would)
+    src = gaussian_latents(N_LAT, D_LAT, seed=1234, device=dev, sample_seed=9001 + rank)
+    tgt = gaussian_latents(N_LAT, D_LAT, seed=4321, device=dev, shift=0.5, scale=1.5, sample_seed=7001 + rank)
     out = torch.empty_like(src)
     cfg = dict(dtype=torch.double, device=dev, reduce_on_update=False)
     op = GaussianTransport(D_LAT, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).to(dev)
@@ -337,7 +341,8 @@ def main():
                                 w2=float(w2)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
                     sinkhorn=sinkhorn)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

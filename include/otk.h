@@ -162,18 +162,24 @@ int otk_sinkhorn_points(const float* x, const float* y, int64_t N, int64_t M, in
                         float* row_marginal /* [N] or NULL */, float* col_marginal /* [M] or NULL */,
                         int* iters_done_host, void* workspace, size_t workspace_bytes,
                         otk_stream_t stream);
-/* half-steps for the row-sharded path: partial column LSE over local rows (m,s) [2,M]; combine; row step */
+/* half-steps for the row-sharded path: partial column LSE over local rows (m,s) [2,M]; combine; row step.
+ * reuse_prepared != 0: the workspace still holds the operand planes (FP16 points, squared norms) an earlier
+ * colstep / rowstep call prepared for the SAME (x_local, y, sizes) - the preparation passes are skipped; the
+ * caller must then hand in the same, otherwise untouched, workspace.
+ * otk_lse_combine: part_max / part_sum rows are `part_stride` floats apart (e.g. 2*M for an all-gathered
+ * [ranks, 2, M] buffer). */
 int otk_sinkhorn_points_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M,
                                 int64_t dim, const float* u_local, int cost_kind, double scale, double reg,
-                                int precision, float* col_max, float* col_sum, void* workspace,
-                                size_t workspace_bytes, otk_stream_t stream);
-int otk_lse_combine(const float* part_max, const float* part_sum, int64_t parts, int64_t M,
-                    const float* b, float* v, float* diff /* += sum|dv| */, otk_stream_t stream);
+                                int precision, int reuse_prepared, float* col_max, float* col_sum,
+                                void* workspace, size_t workspace_bytes, otk_stream_t stream);
+int otk_lse_combine(const float* part_max, const float* part_sum, int64_t parts, int64_t part_stride,
+                    int64_t M, const float* b, float* v, float* diff /* += sum|dv| */,
+                    otk_stream_t stream);
 int otk_sinkhorn_points_rowstep(const float* x_local, const float* y, int64_t n_local, int64_t M,
                                 int64_t dim, const float* a_local, const float* v, int cost_kind,
-                                double scale, double reg, int precision, float* u_local,
-                                float* diff /* += sum|du| */, void* workspace, size_t workspace_bytes,
-                                otk_stream_t stream);
+                                double scale, double reg, int precision, int reuse_prepared,
+                                float* u_local, float* diff /* += sum|du| */, void* workspace,
+                                size_t workspace_bytes, otk_stream_t stream);
 /* max_ij cost(x_i, y_j) -> *out (device fp32), for the 1/max normalisation */
 int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
                  float* out, void* workspace, size_t workspace_bytes, otk_stream_t stream);

@@ -232,14 +232,14 @@ extern "C" int otk_sinkhorn_points(const float* x, const float* y, int64_t N, in
 
 extern "C" int otk_sinkhorn_points_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
                                            const float* u_local, int cost_kind, double scale, double reg, int precision,
-                                           float* col_max, float* col_sum, void* workspace, size_t workspace_bytes,
-                                           otk_stream_t stream) {
+                                           int reuse_prepared, float* col_max, float* col_sum, void* workspace,
+                                           size_t workspace_bytes, otk_stream_t stream) {
   OTK_TRY(require_device());
   OTK_REQUIRE(x_local && y && u_local && col_max && col_sum && n_local > 0 && M > 0 && dim > 0, "colstep: bad arguments");
   if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   if (sk_umma_eligible(n_local, M, dim, cost_kind))
-    return sk_umma_colstep(x_local, y, n_local, M, dim, u_local, scale, reg, precision, col_max, col_sum, workspace,
+    return sk_umma_colstep(x_local, y, n_local, M, dim, u_local, scale, reg, reuse_prepared, col_max, col_sum, workspace,
                            workspace_bytes, st);
   Arena ar(workspace, workspace_bytes);
   float* C = ar.take<float>((size_t)n_local * M);
@@ -252,14 +252,14 @@ extern "C" int otk_sinkhorn_points_colstep(const float* x_local, const float* y,
 }
 
 namespace otk {
-__global__ void lse_combine_kernel(const float* pm, const float* ps, int64_t parts, int64_t M, const float* b, float* v,
-                                   float* diff) {
+__global__ void lse_combine_kernel(const float* pm, const float* ps, int64_t parts, int64_t stride, int64_t M, const float* b,
+                                   float* v, float* diff) {
   __shared__ float red[32];
   float acc = 0;
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
     float mm = pm[j], ss = ps[j];
     for (int64_t p = 1; p < parts; ++p) {
-      float m2 = pm[p * M + j], s2 = ps[p * M + j];
+      float m2 = pm[p * stride + j], s2 = ps[p * stride + j];
       if (m2 > mm) { ss = ss * __expf(mm - m2) + s2; mm = m2; } else ss += s2 * __expf(m2 - mm);
     }
     float vn = logf(b[j] + 1e-8f) - (mm + logf(ss));
@@ -273,27 +273,27 @@ __global__ void lse_combine_kernel(const float* pm, const float* ps, int64_t par
 }
 }  // namespace otk
 
-extern "C" int otk_lse_combine(const float* part_max, const float* part_sum, int64_t parts, int64_t M, const float* b,
-                               float* v, float* diff, otk_stream_t stream) {
+extern "C" int otk_lse_combine(const float* part_max, const float* part_sum, int64_t parts, int64_t part_stride, int64_t M,
+                               const float* b, float* v, float* diff, otk_stream_t stream) {
   OTK_TRY(require_device());
-  OTK_REQUIRE(part_max && part_sum && b && v && parts > 0 && M > 0, "lse_combine: bad arguments");
+  OTK_REQUIRE(part_max && part_sum && b && v && parts > 0 && M > 0 && part_stride >= M, "lse_combine: bad arguments");
   int64_t blocks = ceil_div(M, 256);
   if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
-  lse_combine_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(part_max, part_sum, parts, M, b, v, diff);
+  lse_combine_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(part_max, part_sum, parts, part_stride, M, b, v, diff);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }
 
 extern "C" int otk_sinkhorn_points_rowstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
                                            const float* a_local, const float* v, int cost_kind, double scale, double reg,
-                                           int precision, float* u_local, float* diff, void* workspace,
+                                           int precision, int reuse_prepared, float* u_local, float* diff, void* workspace,
                                            size_t workspace_bytes, otk_stream_t stream) {
   OTK_TRY(require_device());
   OTK_REQUIRE(x_local && y && a_local && v && u_local && n_local > 0 && M > 0 && dim > 0, "rowstep: bad arguments");
   if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   if (sk_umma_eligible(n_local, M, dim, cost_kind))
-    return sk_umma_rowstep(x_local, y, n_local, M, dim, a_local, v, scale, reg, precision, u_local, diff, workspace,
+    return sk_umma_rowstep(x_local, y, n_local, M, dim, a_local, v, scale, reg, reuse_prepared, u_local, diff, workspace,
                            workspace_bytes, st);
   Arena ar(workspace, workspace_bytes);
   float* C = ar.take<float>((size_t)n_local * M);

@@ -467,7 +467,7 @@ size_t sk_umma_workspace_bytes(int64_t N, int64_t M, int64_t dim) {
 }
 
 static int fs_carve(FsWork& w, const float* x, const float* y, int64_t N, int64_t M, int64_t dim, void* workspace,
-                    size_t workspace_bytes, cudaStream_t st) {
+                    size_t workspace_bytes, cudaStream_t st, bool prepare = true) {
   Arena ar(workspace, workspace_bytes);
   const int64_t mx = N > M ? N : M;
   w.X = FsSide{x, ar.take<__half>((size_t)N * dim), ar.take<float>((size_t)N), N, {}};
@@ -485,14 +485,16 @@ static int fs_carve(FsWork& w, const float* x, const float* y, int64_t N, int64_
   w.sig = ar.take<float>(64);
   w.state = ar.take<FsState>(1);
   if (!ar.ok()) return OTK_ERR_WORKSPACE;
-  OTK_CUDA(cudaMemsetAsync(w.sig, 0, 16, st));
-  fs_absmax_kernel<<<fs_grid(N * dim), 256, 0, st>>>(x, N * dim, w.sig);
-  fs_absmax_kernel<<<fs_grid(M * dim), 256, 0, st>>>(y, M * dim, w.sig);
-  fs_sigma_kernel<<<1, 1, 0, st>>>(w.sig);
-  fs_prep_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(x, N, dim, w.sig, w.X.hi, w.X.sq);
-  fs_prep_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, dim, w.sig, w.Y.hi, w.Y.sq);
-  count_launch(4);
-  OTK_LAUNCH_CHECK();
+  if (prepare) {       // otherwise the planes / norms / sigma of an earlier call on the same operands are still in place
+    OTK_CUDA(cudaMemsetAsync(w.sig, 0, 16, st));
+    fs_absmax_kernel<<<fs_grid(N * dim), 256, 0, st>>>(x, N * dim, w.sig);
+    fs_absmax_kernel<<<fs_grid(M * dim), 256, 0, st>>>(y, M * dim, w.sig);
+    fs_sigma_kernel<<<1, 1, 0, st>>>(w.sig);
+    fs_prep_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(x, N, dim, w.sig, w.X.hi, w.X.sq);
+    fs_prep_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, dim, w.sig, w.Y.hi, w.Y.sq);
+    count_launch(4);
+    OTK_LAUNCH_CHECK();
+  }
   // 2-D fp16 maps [rows, dim], box 64 x 128, 128B swizzle (K-major operands)
   if (!encode_map_f16_2d(&w.X.map, w.X.hi, dim, N, dim, FS_SLAB, FS_SUB)) return OTK_ERR_CUDA;
   if (!encode_map_f16_2d(&w.Y.map, w.Y.hi, dim, M, dim, FS_SLAB, FS_SUB)) return OTK_ERR_CUDA;
@@ -619,13 +621,12 @@ __global__ void fs_fold_kernel(float* m, const float* sq, float nrm_scale, int64
     m[r] -= sq[r] * nrm_scale;
 }
 
-// row-sharded half-steps (stateless: the operands are re-prepared per call, ~2 passes over the points)
+// row-sharded half-steps; the prepared operands live in the caller's workspace and are reused when the caller says so
 int sk_umma_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* u_local,
-                    double scale, double reg, int precision, float* col_max, float* col_sum, void* workspace,
+                    double scale, double reg, int reuse_prepared, float* col_max, float* col_sum, void* workspace,
                     size_t workspace_bytes, cudaStream_t st) {
-  (void)precision;
   FsWork w;
-  OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st));
+  OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st, !reuse_prepared));
   const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
   fs_bias_kernel<<<fs_grid(n_local), 256, 0, st>>>(u_local, w.X.sq, nrm_scale, n_local, w.biasX2);
   int parts = 0;
@@ -663,11 +664,10 @@ __global__ void fs_rowstep_finish_kernel(const float* __restrict__ pm, const flo
 }
 
 int sk_umma_rowstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* a_local,
-                    const float* v, double scale, double reg, int precision, float* u_local, float* diff, void* workspace,
+                    const float* v, double scale, double reg, int reuse_prepared, float* u_local, float* diff, void* workspace,
                     size_t workspace_bytes, cudaStream_t st) {
-  (void)precision;
   FsWork w;
-  OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st));
+  OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st, !reuse_prepared));
   const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
   fs_bias_kernel<<<fs_grid(M), 256, 0, st>>>(v, w.Y.sq, nrm_scale, M, w.biasY2);
   int parts = 0;

@@ -11,9 +11,9 @@ int sk_umma_solve(const float* x, const float* y, int64_t N, int64_t M, int64_t 
                   float* u, float* v, double* summary, float* row_marginal, float* col_marginal, int* iters_done_host,
                   void* workspace, size_t workspace_bytes, cudaStream_t st);
 int sk_umma_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* u_local,
-                    double scale, double reg, int precision, float* col_max, float* col_sum, void* workspace,
+                    double scale, double reg, int reuse_prepared, float* col_max, float* col_sum, void* workspace,
                     size_t workspace_bytes, cudaStream_t st);
 int sk_umma_rowstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* a_local,
-                    const float* v, double scale, double reg, int precision, float* u_local, float* diff, void* workspace,
+                    const float* v, double scale, double reg, int reuse_prepared, float* u_local, float* diff, void* workspace,
                     size_t workspace_bytes, cudaStream_t st);
 }  // namespace otk

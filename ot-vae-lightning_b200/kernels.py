@@ -270,43 +270,58 @@ def cost_max(x: Tensor, y: Tensor, cost: int) -> Tensor:
     return out
 
 
+def points_workspace(n: int, m: int, d: int, cost: int, device) -> Tensor:
+    """A dedicated workspace for a sequence of colstep / rowstep calls that reuse the prepared operands."""
+    return torch.empty(N.load().otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dtype=torch.uint8, device=device)
+
+
 def colstep(x_local: Tensor, y: Tensor, u_local: Tensor, scale: float, reg: float, cost: int = N.COST_SQEUCLIDEAN,
-            precision: int = 0) -> Tuple[Tensor, Tensor]:
+            precision: int = 0, out: Optional[Tensor] = None, ws: Optional[Tensor] = None, reuse: bool = False
+            ) -> Tuple[Tensor, Tensor]:
+    """Partial column LSE over the local rows: (max, sumexp), written into `out` [2, M] if given.  `ws` + `reuse`: the
+    caller's dedicated workspace still holds the operands prepared by an earlier colstep / rowstep on the same clouds."""
     dev = x_local.device
     n, d = x_local.shape
     m = y.shape[0]
-    cm = torch.empty(m, dtype=torch.float32, device=dev)
-    cs = torch.empty(m, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(2, m, dtype=torch.float32, device=dev)
+    cm, cs = out[0], out[1]
     lib = N.load()
     with torch.cuda.device(dev):
-        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev)
+        if ws is None:
+            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), False
         st = lib.otk_sinkhorn_points_colstep(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(u_local), int(cost), float(scale),
-                                             float(reg), int(precision), N.ptr(cm), N.ptr(cs), N.ptr(ws), ws.numel(),
-                                             N.stream_ptr(dev))
+                                             float(reg), int(precision), int(bool(reuse)), N.ptr(cm), N.ptr(cs), N.ptr(ws),
+                                             ws.numel(), N.stream_ptr(dev))
     N.check(st, "otk_sinkhorn_points_colstep")
     return cm, cs
 
 
 def lse_combine(part_max: Tensor, part_sum: Tensor, b: Tensor, v: Tensor, diff: Optional[Tensor]) -> None:
+    """v = log(b + 1e-8) - LSE over the parts; part_max / part_sum are [parts, M] views with a common row stride."""
     dev = v.device
     parts, m = part_max.shape
+    stride = part_max.stride(0) if parts > 1 else m
+    assert part_max.stride(1) == 1 and part_sum.stride(1) == 1 and (parts == 1 or part_sum.stride(0) == stride)
     with torch.cuda.device(dev):
-        st = N.load().otk_lse_combine(N.ptr(part_max), N.ptr(part_sum), parts, m, N.ptr(b), N.ptr(v), N.ptr(diff),
+        st = N.load().otk_lse_combine(N.ptr(part_max), N.ptr(part_sum), parts, stride, m, N.ptr(b), N.ptr(v), N.ptr(diff),
                                       N.stream_ptr(dev))
     N.check(st, "otk_lse_combine")
 
 
 def rowstep(x_local: Tensor, y: Tensor, a_local: Tensor, v: Tensor, u_local: Tensor, diff: Optional[Tensor],
-            scale: float, reg: float, cost: int = N.COST_SQEUCLIDEAN, precision: int = 0) -> None:
+            scale: float, reg: float, cost: int = N.COST_SQEUCLIDEAN, precision: int = 0, ws: Optional[Tensor] = None,
+            reuse: bool = False) -> None:
     dev = x_local.device
     n, d = x_local.shape
     m = y.shape[0]
     lib = N.load()
     with torch.cuda.device(dev):
-        ws = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev)
+        if ws is None:
+            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), False
         st = lib.otk_sinkhorn_points_rowstep(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(a_local), N.ptr(v), int(cost),
-                                             float(scale), float(reg), int(precision), N.ptr(u_local), N.ptr(diff),
-                                             N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+                                             float(scale), float(reg), int(precision), int(bool(reuse)), N.ptr(u_local),
+                                             N.ptr(diff), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
     N.check(st, "otk_sinkhorn_points_rowstep")
 
 

@@ -50,18 +50,18 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
     u = torch.zeros(x_local.shape[0], dtype=torch.float32, device=dev)
     v = torch.zeros(m, dtype=torch.float32, device=dev)
     diffs = torch.zeros(2, dtype=torch.float32, device=dev)  # [sum|du| local, sum|dv| replicated]
-    gathered = torch.empty(world, 2, m, dtype=torch.float32, device=dev) if world > 1 else None
+    part = torch.empty(2, m, dtype=torch.float32, device=dev)             # this rank's column (max, sumexp)
+    gathered = torch.empty(world, 2, m, dtype=torch.float32, device=dev) if world > 1 else part.unsqueeze(0)
+    # the operands (FP16 planes, norms) are prepared by the first half-step and then reused from a dedicated workspace
+    ws = kernels.points_workspace(x_local.shape[0], m, x_local.shape[1], cost, dev) if hasattr(kernels, "points_workspace") else None
     done_iters = 0
     for it in range(max_iter):
-        cmax, csum = kernels.colstep(x_local, y, u, scale, reg, cost, precision)
+        kernels.colstep(x_local, y, u, scale, reg, cost, precision, out=part, ws=ws, reuse=it > 0)
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), torch.stack([cmax, csum]).view(-1), group=group)
-            pm, ps = gathered[:, 0].contiguous(), gathered[:, 1].contiguous()
-        else:
-            pm, ps = cmax.unsqueeze(0), csum.unsqueeze(0)
+            dist.all_gather_into_tensor(gathered.view(-1), part.view(-1), group=group)
         diffs.zero_()
-        kernels.lse_combine(pm, ps, b, v, diffs[1:2])
-        kernels.rowstep(x_local, y, a_local, v, u, diffs[0:1], scale, reg, cost, precision)
+        kernels.lse_combine(gathered[:, 0], gathered[:, 1], b, v, diffs[1:2])
+        kernels.rowstep(x_local, y, a_local, v, u, diffs[0:1], scale, reg, cost, precision, ws=ws, reuse=True)
         done_iters = it + 1
         if threshold > 0 and ((it + 1) % poll_every == 0 or it + 1 == max_iter):
             du = diffs[0:1].clone()

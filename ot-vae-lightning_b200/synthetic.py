@@ -18,11 +18,12 @@ def gaussian_spec(d: int, seed: int, kappa: float = 1e2, device="cpu") -> Tuple[
 
 
 def gaussian_latents(n: int, d: int, seed: int, kappa: float = 1e2, device="cpu", chunk: int = 1 << 16,
-                     shift: float = 0.0, scale: float = 1.0) -> Tensor:
-    """x = mu + H z, fp32 [n, d], generated chunk-wise on `device`."""
+                     shift: float = 0.0, scale: float = 1.0, sample_seed: int = None) -> Tensor:
+    """x = mu + H z, fp32 [n, d], generated chunk-wise on `device`.  `seed` fixes the distribution (mu, H);
+    `sample_seed` (default: derived from `seed`) the draws - ranks of a data-parallel run share `seed` only."""
     mu, half = gaussian_spec(d, seed, kappa, device)
     mu32, half32 = (mu + shift).float(), (half * scale).float()
-    g = torch.Generator(device=device).manual_seed(seed + 7919)
+    g = torch.Generator(device=device).manual_seed(seed + 7919 if sample_seed is None else sample_seed)
     out = torch.empty(n, d, dtype=torch.float32, device=device)
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)

@@ -81,10 +81,15 @@ def global_cost_scale(x_local, y):
     return 1.0 / float(mx)
 
 
-def colstep(x_local, y, u_local, scale, reg, cost=0, precision=0):
+def colstep(x_local, y, u_local, scale, reg, cost=0, precision=0, out=None, ws=None, reuse=False):
     t = u_local.double()[:, None] - cost_matrix(x_local, y, cost, scale).double() / reg
     m = t.max(0).values
-    return m.float(), torch.exp(t - m).sum(0).float()
+    cm, cs = m.float(), torch.exp(t - m).sum(0).float()
+    if out is not None:
+        out[0].copy_(cm)
+        out[1].copy_(cs)
+        return out[0], out[1]
+    return cm, cs
 
 
 def lse_combine(pm, ps, b, v, diff):
@@ -96,7 +101,7 @@ def lse_combine(pm, ps, b, v, diff):
     v.copy_(new.float())
 
 
-def rowstep(x_local, y, a_local, v, u_local, diff, scale, reg, cost=0, precision=0):
+def rowstep(x_local, y, a_local, v, u_local, diff, scale, reg, cost=0, precision=0, ws=None, reuse=False):
     t = v.double()[None, :] - cost_matrix(x_local, y, cost, scale).double() / reg
     new = torch.log(a_local.double() + 1e-8) - torch.logsumexp(t, dim=1)
     if diff is not None:
