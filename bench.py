@@ -29,6 +29,9 @@ import torch.distributed as dist  # noqa: E402
 D_LAT, N_LAT, CHUNK = 512, 1 << 20, 1 << 16
 SK_N, SK_D, SK_EPS = 65536, 128, 0.05
 METRIC, UNIT = "cov+W2-map latents/s", "latents/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one stats_ts_kernel<2> launch on a 65536 x 512 chunk
+# (ncu --set full, profiles/prof_step_r02.md): 135.34 MB + 3.9 MB; the algorithmic figure is 134.2 MB
+STATS_TRAFFIC_BYTES_PER_LAUNCH = 139.2e6
 
 
 def load_peaks():
@@ -147,7 +150,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--sinkhorn-iters", type=int, default=20)
+    ap.add_argument("--sinkhorn-iters", type=int, default=100)   # threshold=0, max_iter=100 for timing
     ap.add_argument("--skip-sinkhorn", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -248,11 +251,23 @@ def main():
     tf32_peak = peaks["bf16_sustained"] / 2.0
     stats_tflops = flops / (stats_ms / 3 * 1e-3) / 1e12
     apply_tflops = flops / (apply_ms / 3 * 1e-3) / 1e12
-    roofline = dict(kernel="stats_update (K1: sum x x^T, sum x, n) over 2^20 x 512 fp32 latents",
+    n_chunks = N_LAT // CHUNK
+    # executed MMA flops of the statistics kernel: 3 TF32 MMAs per product (3xTF32 split) on the 256x128 blocks of the
+    # upper block triangle (6 of 8 at d = 512)
+    tri = 0.75 if D_LAT == 512 else 1.0
+    roofline = dict(kernel="stats_ts_kernel<2> (K1: sum x x^T, sum x, n), one launch per 65536 x 512 fp32 chunk",
                     bound="tensor", achieved=stats_tflops, peak=tf32_peak, unit="TFLOP/s", frac=stats_tflops / tf32_peak,
-                    traffic=None,
-                    note=f"algorithmic flops 2*N*d^2; peak = TF32 dense = 1/2 of bf16_tflops_sustained ({peaks['source']})",
+                    traffic=STATS_TRAFFIC_BYTES_PER_LAUNCH,
+                    algorithmic=dict(flops_per_launch=2.0 * CHUNK * D_LAT * D_LAT, bytes_per_launch=CHUNK * D_LAT * 4,
+                                     launches_per_step=2 * n_chunks, avg_launch_ms=stats_ms / 3 / n_chunks),
+                    executed=dict(tflops=3.0 * tri * stats_tflops, frac=3.0 * tri * stats_tflops / tf32_peak,
+                                  note="3 TF32 MMAs per fp32-accurate product, upper block triangle only: the ceiling of "
+                                       "`frac` for this scheme is 1/(3*0.75) = 0.44"),
+                    note=f"achieved = algorithmic flops 2*N*d^2 / CUDA-event time of the update calls (kernel + its 2 small "
+                         f"helper kernels); peak = TF32 dense = 1/2 of bf16_tflops_sustained ({peaks['source']}); traffic = "
+                         f"dram read+write bytes per launch from profiles/prof_step_r02.md (algorithmic: {CHUNK * D_LAT * 4})",
                     others=dict(apply_transport_tflops=apply_tflops, apply_frac=apply_tflops / tf32_peak,
+                                apply_executed_frac=3.0 * apply_tflops / tf32_peak,
                                 compute_map_ms=compute_ms / 3, stats_ms=stats_ms / 3, apply_ms=apply_ms / 3,
                                 stats_gbs=N_LAT * D_LAT * 4 / (stats_ms / 3 * 1e-3) / 1e9,
                                 apply_gbs=2 * N_LAT * D_LAT * 4 / (apply_ms / 3 * 1e-3) / 1e9, hbm_peak_gbs=peaks["hbm"]))
@@ -312,8 +327,20 @@ def main():
                                                           cost="sqeuclidean / max", scale=scale),
                             gpu_launches=int(sk_launches),
                             roofline=dict(bound="hbm", achieved=alg_gb * it_s, peak=peaks["hbm"], unit="GB/s",
-                                          frac=alg_gb * it_s / peaks["hbm"], traffic=None,
-                                          note="algorithmic bytes 2*N*M*4 per iteration (one fp32 cost read per half-step)"))
+                                          frac=alg_gb * it_s / peaks["hbm"], traffic=34.1e6,
+                                          note="algorithmic bytes 2*N*M*4 per iteration (one fp32 cost read per half-step: "
+                                               "what a streamed cost matrix would move); the fused kernel never "
+                                               "materialises the cost, so frac > 1; measured dram traffic per pass "
+                                               "launch: 34 MB (profiles/prof_sinkhorn_r02.md)",
+                                          binding=dict(bound="mufu", achieved=2.0 * SK_N * SK_N * it_s / 1e12,
+                                                       frac=2.0 * SK_N * SK_N * it_s / (world * 148 * 16 * (clocks.get("sm_max_mhz") or 1965) * 1e6),
+                                                       peak=world * 148 * 16 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12,
+                                                       unit="T ex2/s",
+                                                       note="2*N*M exponentials per iteration on the 16/clk/SM MUFU pipe at "
+                                                            "the maximum SM clock; ncu: XU pipe 79 % active"),
+                                          tensor=dict(achieved=4.0 * SK_N * SK_N * SK_D * it_s / 1e12 / world,
+                                                      peak=peaks["bf16_sustained"], unit="TFLOP/s per GPU",
+                                                      note="executed FP16 MMA flops 2 passes x 2*N*M*d")))
             if res is not None:
                 s = res["summary"].cpu().tolist()
                 sinkhorn["check"] = dict(cost=s[0], mass=s[1], max_row_err=s[2], max_col_err=s[3])
@@ -338,6 +365,7 @@ def main():
                                          "+ Gaussian W2 map + transport of the 2^20 source latents, per rank",
                                 dim=D_LAT, latents_per_rank=N_LAT, chunk=CHUNK, l2="inputs (2 x 2 GiB) exceed L2",
                                 arithmetic="fp32-accurate (3xTF32 / FFMA) products, fp64 running statistics",
+                                sinkhorn_arithmetic="FP16 operand planes (TF32-size mantissa), fp32 accumulation and softmax",
                                 w2=float(w2)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
                     sinkhorn=sinkhorn)

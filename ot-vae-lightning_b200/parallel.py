@@ -8,6 +8,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -38,10 +39,14 @@ def global_cost_scale(x_local: Tensor, y: Tensor, cost: int = 0, group=None) -> 
 
 def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg: float, max_iter: int,
                      threshold: float = 0.0, scale: Optional[float] = None, cost: int = 0, precision: int = 0,
-                     poll_every: int = 16, group=None, kernels=K):
+                     poll_every: int = 16, group=None, kernels=K, use_graph: Optional[bool] = None):
     """Row-sharded log-domain Sinkhorn (same recurrences / stop rule as reference w2_utils.py:301-319).
     x_local [n_g, d], a_local [n_g] are this rank's rows; y [M, d], b [M] are replicated.
-    Returns dict(u_local, v, iters, scale).  `kernels` is injectable for the CPU (gloo) tests."""
+    Returns dict(u_local, v, iters, scale).  `kernels` is injectable for the CPU (gloo) tests.
+
+    One iteration = column half-step on the local rows -> all-gather of the [2, M] (max, sumexp) partials (the only
+    data-path collective) -> combine -> row half-step.  On CUDA the iteration (kernels + the NCCL all-gather) is
+    captured once into a CUDA graph and replayed, so the host enqueues one launch per iteration instead of ~10."""
     world = _world(group)
     dev = x_local.device
     if scale is None:
@@ -54,19 +59,50 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
     gathered = torch.empty(world, 2, m, dtype=torch.float32, device=dev) if world > 1 else part.unsqueeze(0)
     # the operands (FP16 planes, norms) are prepared by the first half-step and then reused from a dedicated workspace
     ws = kernels.points_workspace(x_local.shape[0], m, x_local.shape[1], cost, dev) if hasattr(kernels, "points_workspace") else None
-    done_iters = 0
-    for it in range(max_iter):
-        kernels.colstep(x_local, y, u, scale, reg, cost, precision, out=part, ws=ws, reuse=it > 0)
+
+    def iteration(first: bool) -> None:
+        kernels.colstep(x_local, y, u, scale, reg, cost, precision, out=part, ws=ws, reuse=not first)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), part.view(-1), group=group)
         diffs.zero_()
         kernels.lse_combine(gathered[:, 0], gathered[:, 1], b, v, diffs[1:2])
         kernels.rowstep(x_local, y, a_local, v, u, diffs[0:1], scale, reg, cost, precision, ws=ws, reuse=True)
+
+    def converged() -> bool:
+        du = diffs[0:1].clone()
+        if world > 1:
+            dist.all_reduce(du, group=group)
+        return float(du.item() + diffs[1].item()) < threshold
+
+    if use_graph is None:   # capture costs about as much as a few iterations: only worth it for long runs
+        use_graph = (kernels is K and dev.type == "cuda" and max_iter >= 32
+                     and os.environ.get("OTK_SINKHORN_GRAPH", "1") != "0")
+    graph = None
+    done_iters = 0
+    for it in range(max_iter):
+        if use_graph and it == 2 and graph is None:
+            graph = _capture(iteration, dev)
+            use_graph = graph is not None
+        if graph is not None:
+            graph.replay()
+        else:
+            iteration(first=(it == 0))
         done_iters = it + 1
-        if threshold > 0 and ((it + 1) % poll_every == 0 or it + 1 == max_iter):
-            du = diffs[0:1].clone()
-            if world > 1:
-                dist.all_reduce(du, group=group)
-            if float(du.item() + diffs[1].item()) < threshold:
-                break
+        if threshold > 0 and ((it + 1) % poll_every == 0 or it + 1 == max_iter) and converged():
+            break
     return dict(u_local=u, v=v, iters=done_iters, scale=scale)
+
+
+def _capture(iteration, dev):
+    """Capture one steady-state iteration (prepared operands reused) into a CUDA graph; None if capture is refused."""
+    try:
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            iteration(first=False)
+        return g
+    except Exception as e:  # noqa: BLE001 - capture is an optimisation; the eager loop is always valid
+        import warnings
+        warnings.warn(f"sharded_sinkhorn: CUDA-graph capture unavailable ({type(e).__name__}: {e}); running eagerly")
+        torch.cuda.synchronize(dev)
+        return None
