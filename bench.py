@@ -272,6 +272,38 @@ def main():
                                 stats_gbs=N_LAT * D_LAT * 4 / (stats_ms / 3 * 1e-3) / 1e9,
                                 apply_gbs=2 * N_LAT * D_LAT * 4 / (apply_ms / 3 * 1e-3) / 1e9, hbm_peak_gbs=peaks["hbm"]))
 
+    # ---- d = 128 (the latent width north_star's target is quoted on): the two streaming kernels over 2^20 latents
+    d128 = None
+    try:
+        x128 = gaussian_latents(N_LAT, 128, seed=77, device=dev)
+        op128 = GaussianTransport(128, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).to(dev)
+        op128.update(source_samples=x128, target_samples=x128 * 1.5 + 0.5)
+        op128.compute()
+
+        def stats128():
+            op128.source_model.reset()
+            op128.source_model.update(x128)
+
+        def apply128():
+            op128.transport(x128)
+
+        stats128(); apply128()
+        s_ms, _ = timed(stats128, 5)
+        a_ms, _ = timed(apply128, 5)
+        s_ms, a_ms = s_ms / 5, a_ms / 5
+        f128 = 2.0 * N_LAT * 128 * 128
+        d128 = dict(latents=N_LAT, dim=128,
+                    stats=dict(ms=s_ms, gbs=N_LAT * 128 * 4 / (s_ms * 1e-3) / 1e9, hbm_frac=N_LAT * 128 * 4 / (s_ms * 1e-3) / 1e9 / peaks["hbm"],
+                               executed_tflops=3 * f128 / (s_ms * 1e-3) / 1e12, executed_tensor_frac=3 * f128 / (s_ms * 1e-3) / 1e12 / tf32_peak,
+                               note="one update() call (pivot + kernel + merge); 3xTF32 makes the SYRK tensor-bound at d = 128: "
+                                    "3*2*N*d^2 executed flops need 148 us at the sustained TF32 peak, one read of X needs 82 us"),
+                    apply=dict(ms=a_ms, gbs=2 * N_LAT * 128 * 4 / (a_ms * 1e-3) / 1e9,
+                               hbm_frac=2 * N_LAT * 128 * 4 / (a_ms * 1e-3) / 1e9 / peaks["hbm"],
+                               note="one transport() call; HBM-bound (read X, write Y)"))
+        del x128, op128
+    except Exception as e:  # secondary numbers must never take the primary line down
+        d128 = dict(error=f"{type(e).__name__}: {e}")
+
     # ---- e2e: same step through the public API with pinned HOST buffers
     e2e = None
     if not args.skip_e2e:
@@ -368,7 +400,7 @@ def main():
                                 sinkhorn_arithmetic="FP16 operand planes (TF32-size mantissa), fp32 accumulation and softmax",
                                 w2=float(w2)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
-                    sinkhorn=sinkhorn)
+                    d128=d128, sinkhorn=sinkhorn)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
