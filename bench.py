@@ -294,9 +294,11 @@ def main():
         f128 = 2.0 * N_LAT * 128 * 128
         d128 = dict(latents=N_LAT, dim=128,
                     stats=dict(ms=s_ms, gbs=N_LAT * 128 * 4 / (s_ms * 1e-3) / 1e9, hbm_frac=N_LAT * 128 * 4 / (s_ms * 1e-3) / 1e9 / peaks["hbm"],
-                               executed_tflops=3 * f128 / (s_ms * 1e-3) / 1e12, executed_tensor_frac=3 * f128 / (s_ms * 1e-3) / 1e12 / tf32_peak,
-                               note="one update() call (pivot + kernel + merge); 3xTF32 makes the SYRK tensor-bound at d = 128: "
-                                    "3*2*N*d^2 executed flops need 148 us at the sustained TF32 peak, one read of X needs 82 us"),
+                               executed_tflops=3 * f128 / (s_ms * 1e-3) / 1e12,
+                               executed_tensor_frac=3 * f128 / (s_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                               note="one update() call (pivot/scale + FP16 hi/lo split kernel stats_h_kernel + merge); HBM-bound: one "
+                                    "read of X needs 82 us; executed flops are FP16 MMAs (3 per product) against the measured "
+                                    "16-bit dense peak"),
                     apply=dict(ms=a_ms, gbs=2 * N_LAT * 128 * 4 / (a_ms * 1e-3) / 1e9,
                                hbm_frac=2 * N_LAT * 128 * 4 / (a_ms * 1e-3) / 1e9 / peaks["hbm"],
                                note="one transport() call; HBM-bound (read X, write Y)"))

@@ -73,8 +73,10 @@ template <int CG>
 __global__ void __launch_bounds__(SU_THREADS, 1)
 stats_ts_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, int rows, int dim, int upl,
                 int nJ, long long range_len, long long flat_total, int parts, double* __restrict__ ws_cov,
-                double* __restrict__ ws_sum, int dbg) {
+                double* __restrict__ ws_sum, int dbg, const int* __restrict__ run_flag) {
   using namespace ptx;
+  // fallback launch behind the FP16-split kernel (stats_h.cu): nothing to do unless that kernel raised its overflow flag
+  if (run_flag != nullptr && *run_flag == 0) return;
   constexpr int SU_XS = su_xs<CG>(), SU_BS = su_bs<CG>();
   constexpr int BSL = 4 / CG;                          // 32-feature slabs of the B block staged by this CTA
   constexpr int BPLANE = BSL * SU_SLAB, BSTAGE = 2 * BPLANE;
@@ -377,12 +379,14 @@ __global__ void pivot_kernel(const float* __restrict__ x, int64_t rows, int64_t 
   }
 }
 
-size_t stats_umma_extra_workspace(int64_t L, int64_t dim) { return align_up((size_t)L * dim * 4, 256) + 256; }
+size_t stats_umma_extra_workspace(int64_t L, int64_t dim) {
+  return align_up((size_t)L * dim * 4, 256) + 256 + stats_h_extra_workspace(L, dim) + 512;
+}
 
 int g_stats_dbg = 0;        // tuning aid: bit0 no TMA loads, bit1 no A conversion, bit2 no B conversion, bit3 no MMAs
 template <int CG>
 static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, int64_t rows, int64_t dim, double* ws_cov,
-                        double* ws_sum, cudaStream_t st) {
+                        double* ws_sum, cudaStream_t st, const int* run_flag = nullptr) {
   auto kern = stats_ts_kernel<CG>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -423,7 +427,7 @@ static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, in
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, mX, pivot, (int)rows, (int)dim, upl, nJ, (long long)range_len,
-                              (long long)flat_total, parts, ws_cov, ws_sum, g_stats_dbg));
+                              (long long)flat_total, parts, ws_cov, ws_sum, g_stats_dbg, run_flag));
   OTK_LAUNCH_CHECK();
   return 1;
 }
@@ -438,6 +442,24 @@ int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   if (!tensormap_encoder()) return 0;
   float* pivot = ar.take<float>((size_t)L * dim);
   if (!ar.ok()) return OTK_ERR_WORKSPACE;
+  if (!g_stats_force_cg && stats_h_eligible(L, rows, dim)) {
+    // narrow latents: FP16-split kernel (HBM-bound); the TF32 kernel follows as a device-gated fallback that only runs
+    // if a value left the FP16 range (it then recomputes into the re-zeroed staging area with the same pivot)
+    int* flag = nullptr;
+    int used = stats_h_launch(x, L, rows, dim, row_stride, batch_stride, pivot, ws_cov, ws_sum, ar, st, &flag);
+    if (used < 0) return used;
+    if (used == 1) {
+      CUtensorMap mF;
+      if (!encode_map_f32_3d(&mF, x, dim, rows, L, row_stride, batch_stride, 32, SU_BK, /*atom32=*/true)) return 0;
+      const int64_t staged = (reinterpret_cast<char*>(ws_sum) - reinterpret_cast<char*>(ws_cov)) / 8 + L * dim;
+      OTK_TRY(stats_zero_if(ws_cov, staged, flag, st));
+      used = launch_stats<1>(mF, pivot, L, rows, dim, ws_cov, ws_sum, st, flag);
+      if (used <= 0) return used < 0 ? used : OTK_ERR_CUDA;
+      *pivot_out = pivot;
+      *tile = SU_T;
+      return 1;
+    }
+  }
   pivot_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, row_stride, batch_stride, pivot);
   OTK_LAUNCH_CHECK();
   CUtensorMap mX;

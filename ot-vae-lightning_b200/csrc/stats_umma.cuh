@@ -8,4 +8,10 @@ size_t stats_umma_extra_workspace(int64_t L, int64_t dim);
 // S' = sum (x-c)), 0 if the shape is not eligible, <0 on error.
 int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
                    double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile, const float** pivot_out);
+// FP16-split engine for dim <= 128 (stats_h.cu)
+size_t stats_h_extra_workspace(int64_t L, int64_t dim);
+bool stats_h_eligible(int64_t L, int64_t rows, int64_t dim);
+int stats_h_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
+                   float* pivot, double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int** flag_out);
+int stats_zero_if(double* p, int64_t n, const int* flag, cudaStream_t st);
 }  // namespace otk

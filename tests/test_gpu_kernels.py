@@ -64,6 +64,32 @@ def test_tcgen05_stats_kernel_matches_fp64(L, rows, d):
     assert relerr(ss, (0.75 * 2 + 0.25) * (x64.transpose(1, 2) @ x64)) < 1e-7 and relerr(n, torch.full_like(n, 1.75 * rows)) < 1e-12
 
 
+@pytest.mark.parametrize("L,rows,d", [(1, 20000, 128), (5, 3000, 96), (150, 700, 64), (1, 131, 72)])
+def test_fp16_split_stats_kernel_scales_and_overflow_fallback(L, rows, d):
+    """dim <= 128 runs the FP16 hi/lo split kernel (stats_h.cu): per-feature power-of-two scales must absorb feature
+    scales six decades apart, and a value outside the FP16 window (planted AFTER the head rows the scales are taken
+    from) must raise the device flag and be recomputed by the gated TF32 kernel - same accuracy either way."""
+    from ot_vae_lightning_b200 import kernels as Kn
+    g = torch.Generator(device="cuda").manual_seed(7 * rows + d)
+    feat = torch.logspace(-3, 3, d, device="cuda")
+    x = torch.randn(L, rows, d, device="cuda", generator=g) * feat + 2.0 * feat
+    for outlier in (False, True):
+        if outlier:
+            x[:, rows // 2 + 3, d // 3] = 3.0e8
+        n = torch.zeros(L, dtype=torch.float64, device="cuda")
+        s = torch.zeros(L, d, dtype=torch.float64, device="cuda")
+        ss = torch.zeros(L, d, d, dtype=torch.float64, device="cuda")
+        Kn.stats_update(x, n, s, ss, None)
+        x64 = x.double()
+        want = x64.transpose(1, 2) @ x64
+        assert torch.equal(n, torch.full_like(n, rows))
+        assert relerr(s, x64.sum(1)) < 1e-7
+        # every entry is accurate relative to its own scale sqrt(S_ii S_jj), not only relative to the largest one
+        scale = torch.sqrt(torch.diagonal(want, dim1=1, dim2=2).unsqueeze(-1) * torch.diagonal(want, dim1=1, dim2=2).unsqueeze(-2))
+        assert float(((ss - want).abs() / scale).max()) < 2e-6
+        assert float((ss - ss.transpose(1, 2)).abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("L,rows,d", [(1, 4096, 128), (1, 1000, 64), (2, 777, 192), (1, 65536, 512), (1, 5, 128), (2, 3000, 260)])
 def test_tcgen05_apply_kernel_matches_fp64(L, rows, d):
     from ot_vae_lightning_b200 import kernels as Kn
