@@ -42,7 +42,6 @@ constexpr int SH_SACC = SH_T * SH_T * 4;             // 64 KiB second-stage accu
 constexpr int SH_SUB = 1024;                         // rows accumulated in tensor memory per sub-chunk
 constexpr int SH_ACOL0 = 256;                        // TMEM columns [0,256): two accumulators, [256,448): A ring (3 x 64)
 constexpr int SH_SMEM = SH_XS * SH_RAW + SH_BS * SH_BSTAGE + SH_SACC + 1024 + 512;
-constexpr float SH_LIMIT = 32768.f;                  // |x'| above this raises the overflow flag (FP16 max = 65504)
 
 __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -61,6 +60,33 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Converter core, thread <-> feature: 32 rows of the raw slab -> 16 packed hi words + 16 packed lo words (two consecutive
+// rows per word, even row in the low half).  v = x s - c s is one FFMA (exact in the same sense as (x - c) s: s is a power
+// of two); `vsum` accumulates sum v (the caller divides by s); `chk` stays 0 unless a value left the FP16 range or was not
+// finite: then hi = inf, the residual v - hi is -inf / NaN and 0 * residual poisons chk - detection costs FMA-pipe slots
+// only.  FULL tiles need no row masking (features past `dim` are zero-filled by TMA and have c = 0).
+template <bool FULL>
+__device__ __forceinline__ void split_rows32(uint32_t slab, int row0, int valid, uint32_t cc, uint32_t within, float s,
+                                             float ncs, float& vsum, float& chk, uint32_t* hw, uint32_t* lw) {
+  using namespace ptx;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const int ra = row0 + 2 * p, rb = ra + 1;
+    const float x0 = lds32(slab + (uint32_t)ra * 128 + ((cc ^ (uint32_t)(ra & 3)) * 32) + within);
+    const float x1 = lds32(slab + (uint32_t)rb * 128 + ((cc ^ (uint32_t)(rb & 3)) * 32) + within);
+    float v0 = fmaf(x0, s, ncs), v1 = fmaf(x1, s, ncs);
+    if (!FULL) { v0 = ra < valid ? v0 : 0.f; v1 = rb < valid ? v1 : 0.f; }
+    vsum += v0 + v1;
+    const __half2 h = __floats2half2_rn(v0, v1);                  // .x (low half) = the even row
+    const float2 hf = __half22float2(h);
+    const float l0 = v0 - hf.x, l1 = v1 - hf.y;
+    chk = fmaf(l0, 0.f, fmaf(l1, 0.f, chk));
+    const __half2 lo = __floats2half2_rn(l0, l1);
+    hw[p] = *reinterpret_cast<const uint32_t*>(&h);
+    lw[p] = *reinterpret_cast<const uint32_t*>(&lo);
+  }
 }
 
 __global__ void __launch_bounds__(SH_THREADS, 1)
@@ -161,11 +187,12 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
     const uint32_t xbase = smem_u32(xa) + (uint32_t)q * SH_SLAB;
     const uint32_t brow = smem_u32(xb) + (uint32_t)col * 128;            // this feature's 128-byte row of a B plane
     const uint32_t sw = (uint32_t)(col & 7);
+    const float ncs = -c * s;
     double colsum = 0.0;
-    float maxabs = 0.f;
+    float chk = 0.f;
     for (int it = cset; it < num_k; it += SH_SETS) {
       const int sx = it % SH_XS, sa = it % SH_AS, sb = it % SH_BS;
-      const int valid = in ? min(SH_BK, r1 - (r0 + it * SH_BK)) : 0;     // rows past the range end contribute nothing
+      const int valid = min(SH_BK, r1 - (r0 + it * SH_BK));              // rows past the range end contribute nothing
       // Order matters: a set's consecutive tiles are SH_SETS apart, more than one phase of the two-deep B ring.  Once the
       // MMAs of this set's previous tile (it - SH_SETS, same A slot) have retired, tile it-2 is the only user of the B
       // stage that can still be pending, i.e. empty_b is at most one phase behind.
@@ -173,28 +200,15 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
       tc_fence_after();
       mbar_wait(&full_a[sx], (it / SH_XS) & 1);
       mbar_wait(&empty_b[sb], ((it / SH_BS) & 1) ^ 1);
-      float part_sum = 0.f;
+      float vsum = 0.f;
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + SH_ACOL0 + sa * 64;
       const uint32_t hb = brow + sb * SH_BSTAGE;
+      const uint32_t slab = xbase + sx * SH_RAW;
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {                                   // two halves of 32 rows
         uint32_t hw[16], lw[16];
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const int ra = h2 * 32 + 2 * p, rb = ra + 1;
-          float xa0 = lds32(xbase + sx * SH_RAW + (uint32_t)ra * 128 + ((cc ^ (uint32_t)(ra & 3)) * 32) + within);
-          float xa1 = lds32(xbase + sx * SH_RAW + (uint32_t)rb * 128 + ((cc ^ (uint32_t)(rb & 3)) * 32) + within);
-          xa0 = ra < valid ? xa0 - c : 0.f;
-          xa1 = rb < valid ? xa1 - c : 0.f;
-          part_sum += xa0 + xa1;
-          const float v0 = xa0 * s, v1 = xa1 * s;
-          maxabs = fmaxf(maxabs, fmaxf(fabsf(v0), fabsf(v1)));
-          const __half2 h = __floats2half2_rn(v0, v1);                  // .x (low half) = the even row
-          const float2 hf = __half22float2(h);
-          const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-          hw[p] = *reinterpret_cast<const uint32_t*>(&h);
-          lw[p] = *reinterpret_cast<const uint32_t*>(&lo);
-        }
+        if (valid == SH_BK) split_rows32<true>(slab, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        else split_rows32<false>(slab, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
         tmem_st16u(ta + h2 * 16, hw);
         tmem_st16u(ta + 32 + h2 * 16, lw);
 #pragma unroll
@@ -204,7 +218,7 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
           sts128u(hb + SH_BPLANE + off, lw[4 * ch], lw[4 * ch + 1], lw[4 * ch + 2], lw[4 * ch + 3]);
         }
       }
-      colsum += (double)part_sum;
+      colsum += (double)vsum;
       fence_proxy_async_smem();   // generic-proxy writes of the B planes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) { mbar_arrive(&empty_ra[sx]); mbar_arrive(&ready_b[sb]); }
@@ -213,8 +227,8 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready_a[sa]);
     }
-    if (in && num_k > 0) atomicAdd(&ws_sum[(int64_t)l * dim + col], colsum);
-    if (!(maxabs < SH_LIMIT)) atomicOr(overflow, 1);                    // also catches NaN / inf inputs
+    if (in && num_k > 0) atomicAdd(&ws_sum[(int64_t)l * dim + col], colsum / (double)s);
+    if (!(chk == 0.f)) atomicOr(overflow, 1);                           // a value left the FP16 window, or NaN / inf input
   } else {
     // ===== epilogue: 4 warps (warp <-> TMEM lane quarter); second-stage fp32 accumulation in shared memory =====
     const int q = warp % 4;
@@ -261,6 +275,273 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Wide latents (dim > 128): the same FP16 hi/lo split on the 128 x 128 blocks (bi <= bj) of the upper block triangle.
+// Work item = (row segment, block); items are dealt round-robin to a persistent grid, segment-major, so the CTAs that run
+// concurrently read the same rows and X comes from HBM once (re-reads are L2 hits).  The A block (-> tensor memory) and the
+// B block (-> K-major swizzled planes in shared memory) have their own raw rings and eight converter warps each (TMEM lane
+// quarter x 32-row half of the tile).  Every converter warp visits every tile in order, so no barrier can run two phases
+// ahead of a waiter and the output rings may be deep (4 A slots in tensor memory, 3 B stages): the converters run up to
+// three tiles ahead of the MMAs instead of ping-ponging with them.
+// A segment is short enough (<= 2048 rows) for the truncating tensor-memory accumulation; its 128 x 128 fp32 tile is
+// written with plain stores to a per-item slot and the partial tiles are summed in fp64 by stats_h2_reduce_kernel (no
+// atomics on the covariance, no second-stage accumulators in shared memory).
+constexpr int S2_XS = 2, S2_PB = 3, S2_AS = 4, S2_ACC = 2;           // raw rings (per side), B planes ring, A slots, accumulators
+constexpr int S2_THREADS = (2 + 8 + 8 + 4 + 1) * 32;                   // TMA (A), MMA | 8 A conv. | 8 B conv. | 4 epilogue | TMA (B)
+constexpr int S2_SMEM = 2 * S2_XS * SH_RAW + S2_PB * SH_BSTAGE + 1024 + 512;
+constexpr int S2_TILE = SH_T * SH_T;                                    // floats per partial tile
+constexpr int S2_MAX_ITEMS = 1024;                                      // partial-tile slots per launch (64 MiB)
+
+struct S2Item { int l, bi, bj, r0, r1; };
+__device__ __forceinline__ S2Item s2_decode(int item, int n_units, int upl, int nB, int seg_len, int row_lo, int row_hi) {
+  S2Item t;
+  const int seg = item / n_units, u = item % n_units;
+  t.l = u / upl;
+  int w = u % upl;
+  t.bi = 0;
+  while (w >= nB - t.bi) { w -= nB - t.bi; ++t.bi; }
+  t.bj = t.bi + w;
+  t.r0 = row_lo + seg * seg_len;
+  t.r1 = min(row_hi, t.r0 + seg_len);
+  return t;
+}
+
+__global__ void __launch_bounds__(S2_THREADS, 1)
+stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, const float* __restrict__ scale,
+                int dim, int nB, int upl, int n_units, int n_items, int seg_len, int row_lo, int row_hi,
+                float* __restrict__ parts, double* __restrict__ ws_sum, int* __restrict__ overflow) {
+  using namespace ptx;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xa = smem;                                     // raw A ring
+  uint8_t* xr = xa + S2_XS * SH_RAW;                      // raw B ring
+  uint8_t* xb = xr + S2_XS * SH_RAW;                      // B planes ring
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(xb + S2_PB * SH_BSTAGE);
+  uint64_t* empty_ra = full_a + S2_XS;
+  uint64_t* full_b = empty_ra + S2_XS;
+  uint64_t* empty_rb = full_b + S2_XS;
+  uint64_t* ready_a = empty_rb + S2_XS;
+  uint64_t* empty_a = ready_a + S2_AS;
+  uint64_t* ready_b = empty_a + S2_AS;
+  uint64_t* empty_b = ready_b + S2_PB;
+  uint64_t* acc_full = empty_b + S2_PB;
+  uint64_t* acc_empty = acc_full + S2_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + S2_ACC);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    for (int s = 0; s < S2_XS; ++s) {
+      mbar_init(&full_a[s], 1); mbar_init(&empty_ra[s], 8);
+      mbar_init(&full_b[s], 1); mbar_init(&empty_rb[s], 8);
+    }
+    for (int s = 0; s < S2_AS; ++s) { mbar_init(&ready_a[s], 8); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < S2_PB; ++s) { mbar_init(&ready_b[s], 8); mbar_init(&empty_b[s], 1); }
+    for (int a = 0; a < S2_ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 || warp == 22) {
+    // ===== TMA producers: warp 0 streams the A blocks, warp 22 the B blocks (independent rings: a slow side must not
+    // hold back the other side's loads) =====
+    const bool side_b = warp == 22;
+    uint8_t* ring = side_b ? xr : xa;
+    uint64_t* full = side_b ? full_b : full_a;
+    uint64_t* empty = side_b ? empty_rb : empty_ra;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
+      const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
+      const int f0 = (side_b ? t.bj : t.bi) * SH_T;
+      for (int kt = 0; kt < num_k; ++kt, ++it) {
+        const int sx = it % S2_XS;
+        mbar_wait(&empty[sx], ((it / S2_XS) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[sx], SH_RAW);
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl)
+            tma_load_3d(ring + sx * SH_RAW + sl * SH_SLAB, &mapX, f0 + 32 * sl, t.r0 + kt * SH_BK, t.l, &full[sx]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = idesc_f16(SH_T, SH_T);
+    int it = 0, n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
+      const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
+      const int a = n % S2_ACC;
+      mbar_wait(&acc_empty[a], ((n / S2_ACC) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + a * SH_T;
+      for (int kt = 0; kt < num_k; ++kt, ++it) {
+        const int sp = it % S2_PB, sa = it % S2_AS;
+        mbar_wait(&ready_b[sp], (it / S2_PB) & 1);
+        mbar_wait(&ready_a[sa], (it / S2_AS) & 1);
+        tc_fence_after();
+        const uint32_t bb = smem_u32(xb + sp * SH_BSTAGE);
+        const uint32_t ab = tmem_base + SH_ACOL0 + sa * 64;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < SH_BK / 16; ++kk) {
+            const uint64_t b_hi = smem_desc_sw128(bb + kk * 32, 16, 1024);
+            const uint64_t b_lo = smem_desc_sw128(bb + SH_BPLANE + kk * 32, 16, 1024);
+            umma_f16_ts(acc, ab + 32 + kk * 8, b_hi, idesc, !(kt == 0 && kk == 0));   // lo * hi
+            umma_f16_ts(acc, ab + kk * 8, b_lo, idesc, 1);                             // hi * lo
+            umma_f16_ts(acc, ab + kk * 8, b_hi, idesc, 1);                             // hi * hi
+          }
+          umma_commit(&empty_b[sp]);
+          umma_commit(&empty_a[sa]);
+          if (kt == num_k - 1) umma_commit(&acc_full[a]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 10) {
+    // ===== A converters: thread <-> feature of block bi (TMEM lane q*32 + lane), warp <-> (lane quarter, 32-row half) =====
+    const int q = warp % 4, h2 = (warp - 2) / 4;
+    const uint32_t cc = (uint32_t)lane / 8, within = (uint32_t)(lane % 8) * 4;
+    const uint32_t slab0 = smem_u32(xa) + (uint32_t)q * SH_SLAB;
+    const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + SH_ACOL0 + h2 * 16;
+    float chk = 0.f;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
+      const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
+      const int col = t.bi * SH_T + q * 32 + lane;
+      const bool in = col < dim;
+      const float c = in ? pivot[(int64_t)t.l * dim + col] : 0.f;
+      const float s = in ? scale[(int64_t)t.l * dim + col] : 1.f;
+      const float ncs = -c * s;
+      double colsum = 0.0;
+      float vsum = 0.f;                                   // fp32 over at most four tiles (128 values), then fp64
+      for (int kt = 0; kt < num_k; ++kt, ++it) {
+        const int sx = it % S2_XS, sa = it % S2_AS;
+        const int valid = min(SH_BK, t.r1 - (t.r0 + kt * SH_BK));
+        mbar_wait(&empty_a[sa], ((it / S2_AS) & 1) ^ 1);
+        tc_fence_after();
+        mbar_wait(&full_a[sx], (it / S2_XS) & 1);
+        uint32_t hw[16], lw[16];
+        if (valid == SH_BK) split_rows32<true>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        else split_rows32<false>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        tmem_st16u(ta0 + sa * 64, hw);
+        tmem_st16u(ta0 + sa * 64 + 32, lw);
+        if ((kt & 3) == 3 || kt == num_k - 1) { colsum += (double)vsum; vsum = 0.f; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_ra[sx]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_a[sa]);
+      }
+      if (t.bi == t.bj && in && num_k > 0) atomicAdd(&ws_sum[(int64_t)t.l * dim + col], colsum / (double)s);   // each feature once
+    }
+    if (!(chk == 0.f)) atomicOr(overflow, 1);
+  } else if (warp < 18) {
+    // ===== B converters: thread <-> feature of block bj (row of the K-major planes), warp <-> (quarter, 32-row half) =====
+    const int q = warp % 4, h2 = (warp - 10) / 4;
+    const int nloc = q * 32 + lane;
+    const uint32_t cc = (uint32_t)lane / 8, within = (uint32_t)(lane % 8) * 4;
+    const uint32_t slab0 = smem_u32(xr) + (uint32_t)q * SH_SLAB;
+    const uint32_t hb0 = smem_u32(xb) + (uint32_t)nloc * 128;
+    const uint32_t sw = (uint32_t)(nloc & 7);
+    float chk = 0.f, vsum = 0.f;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
+      const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
+      const int col = t.bj * SH_T + nloc;
+      const bool in = col < dim;
+      const float c = in ? pivot[(int64_t)t.l * dim + col] : 0.f;
+      const float s = in ? scale[(int64_t)t.l * dim + col] : 1.f;
+      const float ncs = -c * s;
+      for (int kt = 0; kt < num_k; ++kt, ++it) {
+        const int sx = it % S2_XS, sp = it % S2_PB;
+        const int valid = min(SH_BK, t.r1 - (t.r0 + kt * SH_BK));
+        mbar_wait(&empty_b[sp], ((it / S2_PB) & 1) ^ 1);
+        tc_fence_after();
+        mbar_wait(&full_b[sx], (it / S2_XS) & 1);
+        uint32_t hw[16], lw[16];
+        if (valid == SH_BK) split_rows32<true>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        else split_rows32<false>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        const uint32_t hb = hb0 + sp * SH_BSTAGE;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint32_t off = (((uint32_t)(h2 * 4 + ch)) ^ sw) * 16;
+          sts128u(hb + off, hw[4 * ch], hw[4 * ch + 1], hw[4 * ch + 2], hw[4 * ch + 3]);
+          sts128u(hb + SH_BPLANE + off, lw[4 * ch], lw[4 * ch + 1], lw[4 * ch + 2], lw[4 * ch + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&empty_rb[sx]); mbar_arrive(&ready_b[sp]); }
+      }
+    }
+    if (!(chk == 0.f) || !(vsum == vsum)) atomicOr(overflow, 1);
+  } else if (warp < 22) {
+    // ===== epilogue: TMEM accumulator of an item -> its partial-tile slot (thread <-> row of the block) =====
+    const int q = warp % 4;
+    int n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const int a = n % S2_ACC;
+      mbar_wait(&acc_full[a], (n / S2_ACC) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * SH_T;
+      float4* out = reinterpret_cast<float4*>(parts + (int64_t)item * S2_TILE + (q * 32 + lane) * SH_T);
+#pragma unroll 1
+      for (int c0 = 0; c0 < SH_T; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 == SH_T) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) out[c0 / 4 + j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ws_cov[l][gj][gi] (the transposed position the merge kernel reads, gi <= gj) += sum over the segments of the partial
+// tiles, in fp64, with the power-of-two scales divided out.  Once the overflow flag is up the staging area is cleared
+// instead (covariance and column sums): the TF32 kernel launched behind recomputes the whole call into it.
+__global__ void stats_h2_reduce_kernel(const float* __restrict__ parts, const float* __restrict__ scale, int64_t L, int dim,
+                                       int nB, int upl, int n_units, int n_seg, double* __restrict__ ws_cov,
+                                       double* __restrict__ ws_sum, const int* __restrict__ overflow) {
+  const int64_t total = L * (int64_t)dim * dim;
+  if (*overflow) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+      ws_cov[e] = 0.0;
+      if (e < L * dim) ws_sum[e] = 0.0;
+    }
+    return;
+  }
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = e / ((int64_t)dim * dim);
+    const int r = (int)(e % ((int64_t)dim * dim)), gi = r / dim, gj = r % dim;
+    if (gi > gj) continue;
+    const int bi = gi / SH_T, bj = gj / SH_T;
+    const int u = (int)l * upl + bi * nB - bi * (bi - 1) / 2 + (bj - bi);
+    const float* p = parts + (int64_t)u * S2_TILE + (gi % SH_T) * SH_T + (gj % SH_T);
+    double acc = 0.0;
+    for (int sg = 0; sg < n_seg; ++sg) acc += (double)p[(int64_t)sg * n_units * S2_TILE];
+    const float* sc = scale + l * dim;
+    ws_cov[l * dim * dim + (int64_t)gj * dim + gi] += acc / ((double)sc[gi] * (double)sc[gj]);
+  }
 }
 
 // pivot[l, f] = mean of the first min(rows, 64) latents; scale[l, f] = power of two mapping the largest deviation from
@@ -345,6 +626,72 @@ int stats_h_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   stats_h_kernel<<<(unsigned)(L * parts), SH_THREADS, SH_SMEM, st>>>(mX, pivot, scale, (int)rows, (int)dim, (int)parts,
                                                                     (int)range_len, ws_cov, ws_sum, flag);
   OTK_LAUNCH_CHECK();
+  *flag_out = flag;
+  return 1;
+}
+
+size_t stats_h2_extra_workspace(int64_t L, int64_t dim) {
+  const int64_t nB = ceil_div(dim, SH_T), units = L * nB * (nB + 1) / 2;
+  const int64_t slots = units < S2_MAX_ITEMS ? S2_MAX_ITEMS : 0;      // not eligible beyond: no partial-tile area needed
+  return align_up((size_t)slots * S2_TILE * 4, 256) + stats_h_extra_workspace(L, dim);
+}
+
+bool stats_h2_eligible(int64_t L, int64_t rows, int64_t dim) {
+  const int64_t nB = ceil_div(dim, SH_T);
+  return dim > SH_T && rows >= 1 && L * nB * (nB + 1) / 2 <= S2_MAX_ITEMS && rows <= INT32_MAX;
+}
+
+// FP16-split kernel for dim > 128: pivot/scale, then one launch + one partial-tile reduction per super-chunk of rows.
+int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
+                    float* pivot, double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int** flag_out) {
+  const int64_t nB = ceil_div(dim, SH_T), upl = nB * (nB + 1) / 2, n_units = L * upl;
+  float* scale = ar.take<float>((size_t)L * dim);
+  int* flag = ar.take<int>(16);
+  float* parts = ar.take<float>((size_t)S2_MAX_ITEMS * S2_TILE);
+  if (!ar.ok()) return OTK_ERR_WORKSPACE;
+  OTK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  pivot_scale_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, row_stride, batch_stride,
+                                                                                             pivot, scale);
+  OTK_LAUNCH_CHECK();
+  CUtensorMap mX;
+  if (!encode_map_f32_3d(&mX, x, dim, rows, L, row_stride, batch_stride, 32, SH_BK, /*atom32=*/true)) return 0;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OTK_CUDA(cudaFuncSetAttribute(stats_h2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+    attr_set[dev] = true;
+  }
+  const int64_t sms = sm_count();
+  const int64_t max_seg = S2_MAX_ITEMS / n_units;                       // segments per launch (>= 1 by eligibility)
+  for (int64_t row_lo = 0; row_lo < rows;) {
+    // segment length: the smallest number of "rounds" k of the persistent grid whose segments are <= 2048 rows
+    // (tensor-memory accumulation truncates) - items = n_units * segments just below k * #SMs
+    int64_t left = rows - row_lo, seg_len = 0, n_seg = 0;
+    for (int64_t k = 1;; ++k) {
+      int64_t sgs = sms * k / n_units;
+      if (sgs < 1) continue;
+      if (sgs > max_seg) sgs = max_seg;
+      seg_len = ceil_div(ceil_div(left, sgs), SH_BK) * SH_BK;
+      if (seg_len < 256) seg_len = 256;
+      if (seg_len <= 2048 || sgs == max_seg) break;
+    }
+    if (seg_len > 2048) seg_len = 2048;
+    n_seg = ceil_div(left, seg_len);
+    if (n_seg > max_seg) n_seg = max_seg;
+    const int64_t row_hi = row_lo + n_seg * seg_len < rows ? row_lo + n_seg * seg_len : rows;
+    const int64_t n_items = n_units * n_seg;
+    const unsigned grid = (unsigned)(n_items < sms ? n_items : sms);
+    stats_h2_kernel<<<grid, S2_THREADS, S2_SMEM, st>>>(mX, pivot, scale, (int)dim, (int)nB, (int)upl, (int)n_units, (int)n_items,
+                                                      (int)seg_len, (int)row_lo, (int)row_hi, parts, ws_sum, flag);
+    OTK_LAUNCH_CHECK();
+    int64_t blocks = ceil_div(L * dim * dim, 256);
+    if (blocks > sms * 16) blocks = sms * 16;
+    stats_h2_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(parts, scale, L, (int)dim, (int)nB, (int)upl, (int)n_units, (int)n_seg,
+                                                            ws_cov, ws_sum, flag);
+    OTK_LAUNCH_CHECK();
+    row_lo = row_hi;
+  }
   *flag_out = flag;
   return 1;
 }

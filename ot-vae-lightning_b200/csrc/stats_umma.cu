@@ -380,7 +380,7 @@ __global__ void pivot_kernel(const float* __restrict__ x, int64_t rows, int64_t 
 }
 
 size_t stats_umma_extra_workspace(int64_t L, int64_t dim) {
-  return align_up((size_t)L * dim * 4, 256) + 256 + stats_h_extra_workspace(L, dim) + 512;
+  return align_up((size_t)L * dim * 4, 256) + 256 + stats_h2_extra_workspace(L, dim) + 1024;
 }
 
 int g_stats_dbg = 0;        // tuning aid: bit0 no TMA loads, bit1 no A conversion, bit2 no B conversion, bit3 no MMAs
@@ -442,18 +442,23 @@ int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   if (!tensormap_encoder()) return 0;
   float* pivot = ar.take<float>((size_t)L * dim);
   if (!ar.ok()) return OTK_ERR_WORKSPACE;
-  if (!g_stats_force_cg && stats_h_eligible(L, rows, dim)) {
-    // narrow latents: FP16-split kernel (HBM-bound); the TF32 kernel follows as a device-gated fallback that only runs
-    // if a value left the FP16 range (it then recomputes into the re-zeroed staging area with the same pivot)
+  const bool narrow = stats_h_eligible(L, rows, dim), wide = stats_h2_eligible(L, rows, dim);
+  if (!g_stats_force_cg && (narrow || wide)) {
+    // FP16-split kernels; the TF32 kernel follows as a device-gated fallback that only runs if a value left the FP16
+    // range (it then recomputes into the re-zeroed staging area with the same pivot)
     int* flag = nullptr;
-    int used = stats_h_launch(x, L, rows, dim, row_stride, batch_stride, pivot, ws_cov, ws_sum, ar, st, &flag);
+    int used = narrow ? stats_h_launch(x, L, rows, dim, row_stride, batch_stride, pivot, ws_cov, ws_sum, ar, st, &flag)
+                      : stats_h2_launch(x, L, rows, dim, row_stride, batch_stride, pivot, ws_cov, ws_sum, ar, st, &flag);
     if (used < 0) return used;
     if (used == 1) {
       CUtensorMap mF;
       if (!encode_map_f32_3d(&mF, x, dim, rows, L, row_stride, batch_stride, 32, SU_BK, /*atom32=*/true)) return 0;
-      const int64_t staged = (reinterpret_cast<char*>(ws_sum) - reinterpret_cast<char*>(ws_cov)) / 8 + L * dim;
-      OTK_TRY(stats_zero_if(ws_cov, staged, flag, st));
-      used = launch_stats<1>(mF, pivot, L, rows, dim, ws_cov, ws_sum, st, flag);
+      if (narrow) {   // (the wide path's reduction kernel clears the staging area itself when the flag is up)
+        const int64_t staged = (reinterpret_cast<char*>(ws_sum) - reinterpret_cast<char*>(ws_cov)) / 8 + L * dim;
+        OTK_TRY(stats_zero_if(ws_cov, staged, flag, st));
+      }
+      used = dim >= 512 ? launch_stats<2>(mF, pivot, L, rows, dim, ws_cov, ws_sum, st, flag)
+                        : launch_stats<1>(mF, pivot, L, rows, dim, ws_cov, ws_sum, st, flag);
       if (used <= 0) return used < 0 ? used : OTK_ERR_CUDA;
       *pivot_out = pivot;
       *tile = SU_T;

@@ -14,4 +14,9 @@ bool stats_h_eligible(int64_t L, int64_t rows, int64_t dim);
 int stats_h_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
                    float* pivot, double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int** flag_out);
 int stats_zero_if(double* p, int64_t n, const int* flag, cudaStream_t st);
+// same scheme on the 128 x 128 blocks of the upper block triangle for dim > 128 (stats_h.cu)
+size_t stats_h2_extra_workspace(int64_t L, int64_t dim);
+bool stats_h2_eligible(int64_t L, int64_t rows, int64_t dim);
+int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
+                    float* pivot, double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int** flag_out);
 }  // namespace otk

@@ -64,9 +64,11 @@ def test_tcgen05_stats_kernel_matches_fp64(L, rows, d):
     assert relerr(ss, (0.75 * 2 + 0.25) * (x64.transpose(1, 2) @ x64)) < 1e-7 and relerr(n, torch.full_like(n, 1.75 * rows)) < 1e-12
 
 
-@pytest.mark.parametrize("L,rows,d", [(1, 20000, 128), (5, 3000, 96), (150, 700, 64), (1, 131, 72)])
+@pytest.mark.parametrize("L,rows,d", [(1, 20000, 128), (5, 3000, 96), (150, 700, 64), (1, 131, 72), (1, 40000, 512),
+                                      (3, 2500, 260), (1, 170000, 192), (10, 1500, 1024)])
 def test_fp16_split_stats_kernel_scales_and_overflow_fallback(L, rows, d):
-    """dim <= 128 runs the FP16 hi/lo split kernel (stats_h.cu): per-feature power-of-two scales must absorb feature
+    """The FP16 hi/lo split kernels (stats_h.cu; one block for dim <= 128, the upper block triangle beyond, several
+    launches for long inputs): per-feature power-of-two scales must absorb feature
     scales six decades apart, and a value outside the FP16 window (planted AFTER the head rows the scales are taken
     from) must raise the device flag and be recomputed by the gated TF32 kernel - same accuracy either way."""
     from ot_vae_lightning_b200 import kernels as Kn
@@ -86,7 +88,7 @@ def test_fp16_split_stats_kernel_scales_and_overflow_fallback(L, rows, d):
         assert relerr(s, x64.sum(1)) < 1e-7
         # every entry is accurate relative to its own scale sqrt(S_ii S_jj), not only relative to the largest one
         scale = torch.sqrt(torch.diagonal(want, dim1=1, dim2=2).unsqueeze(-1) * torch.diagonal(want, dim1=1, dim2=2).unsqueeze(-2))
-        assert float(((ss - want).abs() / scale).max()) < 2e-6
+        assert float(((ss - want).abs() / scale).max()) < 5e-6
         assert float((ss - ss.transpose(1, 2)).abs().max()) == 0.0
 
 
