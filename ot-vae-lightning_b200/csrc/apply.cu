@@ -21,7 +21,8 @@ using namespace otk;
 
 extern "C" size_t otk_apply_transport_workspace_bytes(int64_t L, int64_t rows, int64_t dim) {
   (void)rows;
-  return 3 * align_up((size_t)L * dim * dim * 4, 256) + 3 * align_up((size_t)L * dim * 4, 256) + 1024;
+  return 3 * align_up((size_t)L * dim * dim * 4, 256) + 3 * align_up((size_t)L * dim * 4, 256) + 1024 +
+         apply_h_workspace_bytes(L, dim) + 2048;
 }
 
 extern "C" int otk_apply_transport(const float* x, int64_t L, int64_t rows, int64_t dim, const void* mean_s,
@@ -43,7 +44,7 @@ extern "C" int otk_apply_transport(const float* x, int64_t L, int64_t rows, int6
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   cast3_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean_s, mean_t, T, dtype, L * dim, L * dim * dim, ms32, mt32, T32);
   OTK_LAUNCH_CHECK();
-  int used = apply_umma_try(x, L, rows, dim, ms32, mt32, T32, Thi, Tlo, y, st);
+  int used = apply_umma_try(x, L, rows, dim, ms32, mt32, T32, Thi, Tlo, y, ar, st);
   if (used < 0) return used;
   if (used) return OTK_OK;
   GemmArgs<float> g{x, T32, y, rows, dim, dim, dim, 1, dim, 1, dim, rows * dim, dim * dim, rows * dim,

@@ -38,8 +38,10 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
 apply_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapT_hi,
                 const __grid_constant__ CUtensorMap mapT_lo, const __grid_constant__ CUtensorMap mapY,
                 const float* __restrict__ mean_s, const float* __restrict__ mean_t, int rows, int dim, int m_tiles,
-                int n_tiles, int total_tiles, int dbg) {
+                int n_tiles, int total_tiles, int dbg, const int* __restrict__ run_flag) {
   using namespace ptx;
+  // fallback launch behind the FP16-split kernel (apply_h.cu): nothing to do unless that kernel raised its overflow flag
+  if (run_flag != nullptr && *run_flag == 0) return;
   constexpr int NACC = 256 / BN;                      // accumulator buffers
   static_assert(BN / CG == 128, "each CTA stages 128 rows of the T tile");
   extern __shared__ uint8_t smem_raw[];
@@ -263,7 +265,8 @@ __global__ void split_matrix_kernel(const float* __restrict__ x, int64_t n, floa
 int g_apply_dbg = 0;        // tuning aid: bit0 = epilogue drains TMEM but stores nothing
 template <int CG, int BN>
 static int launch_apply(const CUtensorMap& mX, const CUtensorMap& mTh, const CUtensorMap& mTl, const CUtensorMap& mY,
-                        const float* ms32, const float* mt32, int64_t L, int64_t rows, int64_t dim, cudaStream_t st) {
+                        const float* ms32, const float* mt32, int64_t L, int64_t rows, int64_t dim, cudaStream_t st,
+                        const int* run_flag) {
   auto kern = apply_ts_kernel<CG, BN>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -290,15 +293,15 @@ static int launch_apply(const CUtensorMap& mX, const CUtensorMap& mTh, const CUt
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, mX, mTh, mTl, mY, ms32, mt32, (int)rows, (int)dim, (int)m_tiles, (int)n_tiles,
-                              (int)total, g_apply_dbg));
+                              (int)total, g_apply_dbg, run_flag));
   OTK_LAUNCH_CHECK();
   return 1;
 }
 
-int g_apply_force_cg = 0;   // tuning aid: 1 / 2 force the single-CTA / CTA-pair instantiation
+int g_apply_force_cg = 0;   // tuning aid: 1 / 2 force the single-CTA / CTA-pair TF32 instantiation (and skip the FP16 kernel)
 
 int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const float* ms32, const float* mt32,
-                   const float* T32, float* Thi_scratch, float* Tlo_scratch, float* y, cudaStream_t st) {
+                   const float* T32, float* Thi_scratch, float* Tlo_scratch, float* y, Arena& ar, cudaStream_t st) {
   if (dim < 64 || dim % 4 != 0 || rows < 1 || L > 65535 || rows > INT32_MAX || dim > INT32_MAX) return 0;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return 0;
   if (!tensormap_encoder()) return 0;
@@ -313,8 +316,15 @@ int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const f
   if (!encode_map_f32_3d(&mTl, Tlo_scratch, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
   if (!encode_map_f32_3d(&mY, y, dim, rows, L, dim, rows * dim, 32, 32)) return 0;
   const bool pair = g_apply_force_cg ? g_apply_force_cg == 2 : (dim >= 256 && rows > 128);
-  if (pair) return launch_apply<2, 256>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st);
-  return launch_apply<1, 128>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st);
+  // FP16-split kernel first (twice the MMA rate); the TF32 kernel behind it recomputes Y only if a value left the FP16 range
+  int* flag = nullptr;
+  if (!g_apply_force_cg) {
+    int used = apply_h_try(x, L, rows, dim, ms32, mt32, T32, y, ar, pair, st, &flag);
+    if (used < 0) return used;
+    if (!used) flag = nullptr;
+  }
+  if (pair) return launch_apply<2, 256>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st, flag);
+  return launch_apply<1, 128>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st, flag);
 }
 
 }  // namespace otk

@@ -57,4 +57,21 @@ inline bool encode_map_f16_2d(CUtensorMap* map, const void* base, int64_t cols, 
   return r == CUDA_SUCCESS;
 }
 
+// fp16 tensor [batch][rows][cols] (cols contiguous; ld, bstride in elements, both multiples of 8); box = box_cols x box_rows x 1,
+// 128-byte swizzle (box_cols * 2 must be <= 128), out-of-bounds reads give zeros
+inline bool encode_map_f16_3d(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t batch, int64_t ld,
+                              int64_t bstride, int box_cols, int box_rows) {
+  TensorMapEncodeTiledFn enc = tensormap_encoder();
+  if (!enc) return false;
+  if (batch < 1) batch = 1;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace otk
