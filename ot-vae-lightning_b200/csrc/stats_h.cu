@@ -530,17 +530,39 @@ __global__ void stats_h2_reduce_kernel(const float* __restrict__ parts, const fl
     }
     return;
   }
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t l = e / ((int64_t)dim * dim);
-    const int r = (int)(e % ((int64_t)dim * dim)), gi = r / dim, gj = r % dim;
-    if (gi > gj) continue;
+  // one thread per 4 consecutive columns gj of a row gi (dim % 4 == 0; a group never straddles a 128-column block);
+  // groups entirely below the diagonal are skipped; the segment loop keeps four independent 16-byte loads in flight
+  const int dq = dim / 4;
+  const int64_t groups = L * (int64_t)dim * dq;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < groups; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = e / ((int64_t)dim * dq);
+    const int r = (int)(e % ((int64_t)dim * dq)), gi = r / dq, gj = (r % dq) * 4;
+    if (gi > gj + 3) continue;
     const int bi = gi / SH_T, bj = gj / SH_T;
     const int u = (int)l * upl + bi * nB - bi * (bi - 1) / 2 + (bj - bi);
-    const float* p = parts + (int64_t)u * S2_TILE + (gi % SH_T) * SH_T + (gj % SH_T);
-    double acc = 0.0;
-    for (int sg = 0; sg < n_seg; ++sg) acc += (double)p[(int64_t)sg * n_units * S2_TILE];
+    const float4* p = reinterpret_cast<const float4*>(parts + (int64_t)u * S2_TILE + (gi % SH_T) * SH_T + (gj % SH_T));
+    const int64_t stride = (int64_t)n_units * S2_TILE / 4;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int sg = 0;
+    for (; sg + 4 <= n_seg; sg += 4) {
+      const float4 v0 = p[(int64_t)sg * stride], v1 = p[(int64_t)(sg + 1) * stride], v2 = p[(int64_t)(sg + 2) * stride],
+                   v3 = p[(int64_t)(sg + 3) * stride];
+      a0 += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+      a1 += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+      a2 += ((double)v0.z + (double)v1.z) + ((double)v2.z + (double)v3.z);
+      a3 += ((double)v0.w + (double)v1.w) + ((double)v2.w + (double)v3.w);
+    }
+    for (; sg < n_seg; ++sg) {
+      const float4 v = p[(int64_t)sg * stride];
+      a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+    }
     const float* sc = scale + l * dim;
-    ws_cov[l * dim * dim + (int64_t)gj * dim + gi] += acc / ((double)sc[gi] * (double)sc[gj]);
+    const double inv_i = 1.0 / (double)sc[gi];
+    double* out = ws_cov + l * dim * dim + gi;                      // transposed position: [gj][gi]
+    if (gi <= gj) out[(int64_t)gj * dim] += a0 * (inv_i / (double)sc[gj]);
+    if (gi <= gj + 1) out[(int64_t)(gj + 1) * dim] += a1 * (inv_i / (double)sc[gj + 1]);
+    if (gi <= gj + 2) out[(int64_t)(gj + 2) * dim] += a2 * (inv_i / (double)sc[gj + 2]);
+    out[(int64_t)(gj + 3) * dim] += a3 * (inv_i / (double)sc[gj + 3]);
   }
 }
 
@@ -685,7 +707,7 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
     stats_h2_kernel<<<grid, S2_THREADS, S2_SMEM, st>>>(mX, pivot, scale, (int)dim, (int)nB, (int)upl, (int)n_units, (int)n_items,
                                                       (int)seg_len, (int)row_lo, (int)row_hi, parts, ws_sum, flag);
     OTK_LAUNCH_CHECK();
-    int64_t blocks = ceil_div(L * dim * dim, 256);
+    int64_t blocks = ceil_div(L * dim * dim / 4, 256);
     if (blocks > sms * 16) blocks = sms * 16;
     stats_h2_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(parts, scale, L, (int)dim, (int)nB, (int)upl, (int)n_units, (int)n_seg,
                                                             ws_cov, ws_sum, flag);

@@ -100,18 +100,13 @@ stats_ts_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
   const int group = CG == 2 ? blockIdx.x / 2 : blockIdx.x;
-  // parts > 0: every unit is cut into the same `parts` row ranges (CTAs working on the same rows of different units run
-  // in lockstep, so X is fetched from HBM once and re-read from L2); parts == 0: equal cuts of the flat (unit, row) space
-  int64_t flat0, flat1;
-  if (parts > 0) {
-    const int64_t ubase = (int64_t)(group / parts) * rows;
-    flat0 = ubase + (int64_t)(group % parts) * range_len;
-    flat1 = flat0 + range_len < ubase + rows ? flat0 + range_len : ubase + rows;
-    if (flat0 > flat1) flat0 = flat1;
-  } else {
-    flat0 = (int64_t)group * range_len;
-    flat1 = flat0 + range_len < flat_total ? flat0 + range_len : flat_total;
-  }
+  // Every unit of this launch (units unit_off ... ) is cut into the same `parts` row ranges: CTAs working on the same rows
+  // of different units run in lockstep, so X is fetched from HBM once and re-read from L2, and a CTA (pair) owns exactly
+  // one segment.  (`flat_total` carries unit_off; a launch covers at most #SMs / CG units, the host loops over the rest.)
+  const int64_t ubase = (int64_t)((int)flat_total + group / parts) * rows;
+  int64_t flat0 = ubase + (int64_t)(group % parts) * range_len;
+  const int64_t flat1 = flat0 + range_len < ubase + rows ? flat0 + range_len : ubase + rows;
+  if (flat0 > flat1) flat0 = flat1;
   const int k_per_sub = SU_SUB / SU_BK;
 
   if (warp == 0 && lane == 0) {
@@ -398,22 +393,21 @@ static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, in
   const int nJ = (int)ceil_div(dim, SU_T), nI = (int)ceil_div(dim, SU_T * CG);
   int upl = 0;
   for (int I = 0; I < nI; ++I) upl += nJ - I * CG;
-  const int64_t flat_total = L * upl * rows;
+  // Aligned cuts only: each launch takes at most #SMs / CG units and gives every unit the same `parts` row ranges
+  // (multiples of 32 rows, at least 256 rows each).  Wide / batched problems with more units than CTA groups take several
+  // launches.  (An earlier "flat" cut, where a CTA's range crossed unit boundaries, produced wrong sums for some of its
+  // multi-segment schedules and was removed.)
   const int64_t max_groups = sm_count() / CG;
-  // equal contiguous ranges of the (unit, row) space; multiples of 32 rows, at least 256 rows each (tiny batches: fewer CTAs)
-  int64_t range_len = ceil_div(ceil_div(flat_total, max_groups), SU_BK) * SU_BK;
-  if (range_len < 256) range_len = 256;
-  int64_t groups = ceil_div(flat_total, range_len);
-  // prefer the aligned cut (same row ranges in every unit) when it keeps >= 90 % of the CTAs busy
   const int64_t n_units = L * upl;
-  int parts = 0;
-  if (n_units <= max_groups) {
-    int64_t p = max_groups / n_units;
-    int64_t rl = ceil_div(ceil_div(rows, p), SU_BK) * SU_BK;
-    if (rl < 256) rl = 256;
-    p = ceil_div(rows, rl);
-    if (n_units * p * 10 >= groups * 9) { parts = (int)p; range_len = rl; groups = n_units * p; }
-  }
+  for (int64_t unit_off = 0; unit_off < n_units; unit_off += max_groups) {
+  const int64_t nu = n_units - unit_off < max_groups ? n_units - unit_off : max_groups;
+  int64_t p = max_groups / nu;
+  int64_t range_len = ceil_div(ceil_div(rows, p), SU_BK) * SU_BK;
+  if (range_len < 256) range_len = 256;
+  p = ceil_div(rows, range_len);
+  const int parts = (int)p;
+  const int64_t groups = nu * p;
+  const long long flat_total = unit_off;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CG));
   cfg.blockDim = dim3(SU_THREADS);
@@ -429,6 +423,7 @@ static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, in
   OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, mX, pivot, (int)rows, (int)dim, upl, nJ, (long long)range_len,
                               (long long)flat_total, parts, ws_cov, ws_sum, g_stats_dbg, run_flag));
   OTK_LAUNCH_CHECK();
+  }
   return 1;
 }
 
