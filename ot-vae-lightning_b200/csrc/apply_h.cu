@@ -320,6 +320,26 @@ __global__ void apply_scale_kernel(const float* __restrict__ x, int64_t rows, in
   }
 }
 
+// prepared form: s_k from the source standard deviation (8 sigma_k mapped into [64, 128), i.e. +-4000 sigma fit the FP16
+// range), nms_k = -mean_s_k s_k
+__global__ void apply_scale_from_var_kernel(const float* __restrict__ var_s, const float* __restrict__ mean_s, int64_t n,
+                                            float* __restrict__ sk, float* __restrict__ nmsk) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float dev = 8.f * sqrtf(fmaxf(var_s[e], 0.f));
+  float s = 1.f;
+  if (dev > 0.f && dev < 3.0e38f) {
+    int ex;
+    frexpf(dev, &ex);
+    ex = 7 - ex;
+    ex = ex < -100 ? -100 : (ex > 100 ? 100 : ex);
+    s = ldexpf(1.f, ex);
+  }
+  sk[e] = s;
+  nmsk[e] = -mean_s[e] * s;
+}
+__global__ void clear_flag_kernel(int* flag) { *flag = 0; }
+
 // one warp per output row j of T: g_j = power of two mapping max_k |T_jk / s_k| into [512, 1024); FP16 hi / lo planes of
 // T_jk g_j / s_k; inv_g[j] = 1 / g_j
 __global__ void apply_split_t_kernel(const float* __restrict__ T, const float* __restrict__ sk, int64_t L, int64_t dim,
@@ -393,30 +413,63 @@ bool apply_h_eligible(int64_t L, int64_t rows, int64_t dim) {
   return dim >= 64 && dim % 8 == 0 && rows >= 1 && L <= 65535 && rows <= INT32_MAX;
 }
 
+struct ApplyHPlanes { __half *Thi, *Tlo; float *sk, *nmsk, *inv_g; int* flag; };
+static bool carve_apply_h(Arena& ar, int64_t L, int64_t dim, ApplyHPlanes* p) {
+  p->Thi = ar.take<__half>((size_t)L * dim * dim);
+  p->Tlo = ar.take<__half>((size_t)L * dim * dim);
+  p->sk = ar.take<float>((size_t)L * dim);
+  p->nmsk = ar.take<float>((size_t)L * dim);
+  p->inv_g = ar.take<float>((size_t)L * dim);
+  p->flag = ar.take<int>(16);
+  return ar.ok();
+}
+static int run_apply_h(const float* x, int64_t L, int64_t rows, int64_t dim, const float* mt32, const ApplyHPlanes& p, float* y,
+                       bool pair, cudaStream_t st) {
+  CUtensorMap mX, mTh, mTl, mY;
+  if (!encode_map_f32_3d(&mX, x, dim, rows, L, dim, rows * dim, 32, HP_BM)) return 0;
+  if (!encode_map_f16_3d(&mTh, p.Thi, dim, dim, L, dim, dim * dim, HP_TK, 128)) return 0;
+  if (!encode_map_f16_3d(&mTl, p.Tlo, dim, dim, L, dim, dim * dim, HP_TK, 128)) return 0;
+  if (!encode_map_f32_3d(&mY, y, dim, rows, L, dim, rows * dim, 32, 32)) return 0;
+  return pair ? launch_apply_h<2, 256>(mX, mTh, mTl, mY, p.sk, p.nmsk, p.inv_g, mt32, L, rows, dim, p.flag, st)
+              : launch_apply_h<1, 128>(mX, mTh, mTl, mY, p.sk, p.nmsk, p.inv_g, mt32, L, rows, dim, p.flag, st);
+}
+
 // FP16-split transport.  Returns 1 if launched (*flag_out: device int, non-zero afterwards iff a value left the FP16 range
 // and Y must be recomputed by the TF32 kernel), 0 if not eligible, < 0 on error.
 int apply_h_try(const float* x, int64_t L, int64_t rows, int64_t dim, const float* ms32, const float* mt32, const float* T32,
                 float* y, Arena& ar, bool pair, cudaStream_t st, int** flag_out) {
   if (!apply_h_eligible(L, rows, dim) || !tensormap_encoder()) return 0;
-  __half* Thi = ar.take<__half>((size_t)L * dim * dim);
-  __half* Tlo = ar.take<__half>((size_t)L * dim * dim);
-  float* sk = ar.take<float>((size_t)L * dim);
-  float* nmsk = ar.take<float>((size_t)L * dim);
-  float* inv_g = ar.take<float>((size_t)L * dim);
-  int* flag = ar.take<int>(16);
-  if (!ar.ok()) return OTK_ERR_WORKSPACE;
-  apply_scale_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, ms32, sk, nmsk, flag);
+  ApplyHPlanes p;
+  if (!carve_apply_h(ar, L, dim, &p)) return OTK_ERR_WORKSPACE;
+  apply_scale_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, ms32, p.sk, p.nmsk, p.flag);
   OTK_LAUNCH_CHECK();
-  apply_split_t_kernel<<<(unsigned)ceil_div(L * dim * 32, 256), 256, 0, st>>>(T32, sk, L, dim, Thi, Tlo, inv_g);
+  apply_split_t_kernel<<<(unsigned)ceil_div(L * dim * 32, 256), 256, 0, st>>>(T32, p.sk, L, dim, p.Thi, p.Tlo, p.inv_g);
   OTK_LAUNCH_CHECK();
-  CUtensorMap mX, mTh, mTl, mY;
-  if (!encode_map_f32_3d(&mX, x, dim, rows, L, dim, rows * dim, 32, HP_BM)) return 0;
-  if (!encode_map_f16_3d(&mTh, Thi, dim, dim, L, dim, dim * dim, HP_TK, 128)) return 0;
-  if (!encode_map_f16_3d(&mTl, Tlo, dim, dim, L, dim, dim * dim, HP_TK, 128)) return 0;
-  if (!encode_map_f32_3d(&mY, y, dim, rows, L, dim, rows * dim, 32, 32)) return 0;
-  int used = pair ? launch_apply_h<2, 256>(mX, mTh, mTl, mY, sk, nmsk, inv_g, mt32, L, rows, dim, flag, st)
-                  : launch_apply_h<1, 128>(mX, mTh, mTl, mY, sk, nmsk, inv_g, mt32, L, rows, dim, flag, st);
-  if (used == 1) *flag_out = flag;
+  int used = run_apply_h(x, L, rows, dim, mt32, p, y, pair, st);
+  if (used == 1) *flag_out = p.flag;
+  return used;
+}
+
+// prepared form: the planes are built once from (mean_s, T, var_s); the arena must be carved identically in both calls
+int apply_h_prepare(int64_t L, int64_t dim, const float* ms32, const float* T32, const float* var32, Arena& ar, cudaStream_t st) {
+  ApplyHPlanes p;
+  if (!carve_apply_h(ar, L, dim, &p)) return OTK_ERR_WORKSPACE;
+  if (!apply_h_eligible(L, 1, dim)) return 0;
+  apply_scale_from_var_kernel<<<(unsigned)ceil_div(L * dim, 256), 256, 0, st>>>(var32, ms32, L * dim, p.sk, p.nmsk);
+  OTK_LAUNCH_CHECK();
+  apply_split_t_kernel<<<(unsigned)ceil_div(L * dim * 32, 256), 256, 0, st>>>(T32, p.sk, L, dim, p.Thi, p.Tlo, p.inv_g);
+  OTK_LAUNCH_CHECK();
+  return 1;
+}
+int apply_h_run_prepared(const float* x, int64_t L, int64_t rows, int64_t dim, const float* mt32, float* y, Arena& ar, bool pair,
+                         cudaStream_t st, int** flag_out) {
+  ApplyHPlanes p;
+  if (!carve_apply_h(ar, L, dim, &p)) return OTK_ERR_WORKSPACE;
+  if (!apply_h_eligible(L, rows, dim) || !tensormap_encoder()) return 0;
+  clear_flag_kernel<<<1, 1, 0, st>>>(p.flag);
+  OTK_LAUNCH_CHECK();
+  int used = run_apply_h(x, L, rows, dim, mt32, p, y, pair, st);
+  if (used == 1) *flag_out = p.flag;
   return used;
 }
 

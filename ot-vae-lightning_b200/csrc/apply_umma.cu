@@ -300,22 +300,35 @@ static int launch_apply(const CUtensorMap& mX, const CUtensorMap& mTh, const CUt
 
 int g_apply_force_cg = 0;   // tuning aid: 1 / 2 force the single-CTA / CTA-pair TF32 instantiation (and skip the FP16 kernel)
 
-int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const float* ms32, const float* mt32,
-                   const float* T32, float* Thi_scratch, float* Tlo_scratch, float* y, Arena& ar, cudaStream_t st) {
-  if (dim < 64 || dim % 4 != 0 || rows < 1 || L > 65535 || rows > INT32_MAX || dim > INT32_MAX) return 0;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return 0;
-  if (!tensormap_encoder()) return 0;
-  const int64_t n = L * dim * dim;
+bool apply_umma_eligible(const float* x, const float* y, int64_t L, int64_t rows, int64_t dim) {
+  if (dim < 64 || dim % 4 != 0 || rows < 1 || L > 65535 || rows > INT32_MAX || dim > INT32_MAX) return false;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
+  return tensormap_encoder() != nullptr;
+}
+bool apply_umma_pair(int64_t rows, int64_t dim) { return g_apply_force_cg ? g_apply_force_cg == 2 : (dim >= 256 && rows > 128); }
+void apply_umma_split(const float* T32, int64_t n, float* Thi, float* Tlo, cudaStream_t st) {
   int64_t blocks = ceil_div(n, 256);
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
-  split_matrix_kernel<<<(unsigned)blocks, 256, 0, st>>>(T32, n, Thi_scratch, Tlo_scratch);
-  OTK_LAUNCH_CHECK();
+  split_matrix_kernel<<<(unsigned)blocks, 256, 0, st>>>(T32, n, Thi, Tlo);
+  count_launch(1);
+}
+int apply_umma_run_planes(const float* x, int64_t L, int64_t rows, int64_t dim, const float* ms32, const float* mt32,
+                          const float* Thi, const float* Tlo, float* y, bool pair, const int* run_flag, cudaStream_t st) {
   CUtensorMap mX, mTh, mTl, mY;
   if (!encode_map_f32_3d(&mX, x, dim, rows, L, dim, rows * dim, 32, AP_BM)) return 0;
-  if (!encode_map_f32_3d(&mTh, Thi_scratch, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
-  if (!encode_map_f32_3d(&mTl, Tlo_scratch, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
+  if (!encode_map_f32_3d(&mTh, Thi, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
+  if (!encode_map_f32_3d(&mTl, Tlo, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
   if (!encode_map_f32_3d(&mY, y, dim, rows, L, dim, rows * dim, 32, 32)) return 0;
-  const bool pair = g_apply_force_cg ? g_apply_force_cg == 2 : (dim >= 256 && rows > 128);
+  if (pair) return launch_apply<2, 256>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st, run_flag);
+  return launch_apply<1, 128>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st, run_flag);
+}
+
+int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const float* ms32, const float* mt32,
+                   const float* T32, float* Thi_scratch, float* Tlo_scratch, float* y, Arena& ar, cudaStream_t st) {
+  if (!apply_umma_eligible(x, y, L, rows, dim)) return 0;
+  apply_umma_split(T32, L * dim * dim, Thi_scratch, Tlo_scratch, st);
+  OTK_CUDA(cudaGetLastError());
+  const bool pair = apply_umma_pair(rows, dim);
   // FP16-split kernel first (twice the MMA rate); the TF32 kernel behind it recomputes Y only if a value left the FP16 range
   int* flag = nullptr;
   if (!g_apply_force_cg) {
@@ -323,8 +336,7 @@ int apply_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, const f
     if (used < 0) return used;
     if (!used) flag = nullptr;
   }
-  if (pair) return launch_apply<2, 256>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st, flag);
-  return launch_apply<1, 128>(mX, mTh, mTl, mY, ms32, mt32, L, rows, dim, st, flag);
+  return apply_umma_run_planes(x, L, rows, dim, ms32, mt32, Thi_scratch, Tlo_scratch, y, pair, flag, st);
 }
 
 }  // namespace otk

@@ -189,6 +189,39 @@ def apply_transport(x: Tensor, mean_s: Tensor, mean_t: Tensor, T: Tensor) -> Ten
     return y
 
 
+class PreparedTransport:
+    """Operator-only work of `apply_transport` done once (reference flow: GaussianTransport.compute builds the map,
+    transport() applies it to many batches): fp32 casts, TF32 and scaled-FP16 planes of T, per-feature input scales from
+    the source variances.  `apply(x)` is then one kernel launch (+ its device-gated TF32 fallback)."""
+
+    def __init__(self, mean_s: Tensor, mean_t: Tensor, T: Tensor, var_s: Tensor):
+        dev = N.compute_device(T, mean_s)
+        dt = T.dtype if T.dtype in (torch.float32, torch.float64) else torch.float32
+        Td, ms, mt, vs = (_dev_tensor(t, dev, dt) for t in (T, mean_s, mean_t, var_s))
+        self.lead = torch.broadcast_shapes(Td.shape[:-2], ms.shape[:-1], mt.shape[:-1], vs.shape[:-1])
+        self.L, self.d, self.device = int(torch.Size(self.lead).numel()), Td.shape[-1], dev
+        Td, ms, mt, vs = _bcast(Td, self.lead, 2), _bcast(ms, self.lead, 1), _bcast(mt, self.lead, 1), _bcast(vs, self.lead, 1)
+        lib = N.load()
+        with torch.cuda.device(dev):
+            self.state = torch.empty(lib.otk_transport_prepared_bytes(self.L, self.d), dtype=torch.uint8, device=dev)
+            st = lib.otk_transport_prepare(N.ptr(ms), N.ptr(mt), N.ptr(Td), N.ptr(vs), N.dtype_code(dt), self.L, self.d,
+                                           N.ptr(self.state), self.state.numel(), N.stream_ptr(dev))
+        N.check(st, "otk_transport_prepare")
+
+    def apply(self, x: Tensor) -> Tensor:
+        """x [*lead, B, d] (any float dtype / device) -> fp32 [*lead, B, d] on the compute device."""
+        xd = _dev_tensor(x, self.device, torch.float32)
+        if tuple(xd.shape[:-2]) != tuple(self.lead) or xd.shape[-1] != self.d:
+            raise ValueError("PreparedTransport.apply: input does not match the operator's leading shape / dimension")
+        xd = xd.contiguous()
+        y = torch.empty_like(xd)
+        with torch.cuda.device(self.device):
+            st = N.load().otk_apply_transport_prepared(N.ptr(xd), self.L, xd.shape[-2], self.d, N.ptr(self.state),
+                                                       self.state.numel(), N.ptr(y), N.stream_ptr(self.device))
+        N.check(st, "otk_apply_transport_prepared")
+        return y
+
+
 def sinkhorn_dense(a: Tensor, b: Tensor, Cm: Tensor, reg: float, max_iter: int, threshold: float,
                    want_plan: bool = True, poll_every: int = 16):
     """Returns (plan or None, u, v, iterations) on the compute device, dtype of C (fp32/fp64)."""

@@ -36,6 +36,23 @@ class GaussianTransport(TransportOperator, W2Mixin):
         super().reset()
         self.transport_operator = None
         self.cov_stochastic_noise = None
+        self._prepared = None
+
+    def fit_models(self):
+        self._prepared = None          # the means are about to change
+        super().fit_models()
+
+    def _prepared_operator(self):
+        """`kernels.PreparedTransport` of the current (means, T), rebuilt whenever one of them was replaced or written to
+        (tensor identity + version counters), so assigning `transport_operator` or refitting a model cannot go stale."""
+        T, ms, mt = self.transport_operator, self.source_model.mean, self.target_model.mean
+        key = (id(T), T._version, id(ms), ms._version, id(mt), mt._version)
+        cached = getattr(self, "_prepared", None)
+        if cached is None or cached[0] != key:
+            var_s = self.source_model.parametrizations.cov.original.diagonal(dim1=-2, dim2=-1)
+            cached = (key, K.PreparedTransport(ms, mt, T, var_s), (T, ms, mt))   # keep the keyed tensors alive
+            self._prepared = cached
+        return cached[1]
 
     def compute(self) -> Tensor:
         """Fit both Gaussians, then W2^2 [*leading_shape] and the operators (reference :64-78)."""
@@ -90,8 +107,12 @@ class GaussianTransport(TransportOperator, W2Mixin):
             raise ValueError("`inputs` leading dims must match the model batch_shape with optional trailing batch dimensions")
         is_batched = inputs.dim() == len(lead) + 2
         if not (self.diag or self.stochastic) and is_batched:
-            # deterministic full map on a batch: straight to the GEMM kernel (Cw == 0, nothing to validate)
-            moved = K.apply_transport(inputs, self.source_model.mean, self.target_model.mean, self.transport_operator)
+            # deterministic full map on a batch: straight to the GEMM kernel (Cw == 0, nothing to validate); the
+            # operator-only preparation is done once per map, not per batch
+            if self.transport_operator.is_cuda and tuple(inputs.shape[:-2]) == tuple(self.transport_operator.shape[:-2]):
+                moved = self._prepared_operator().apply(inputs)
+            else:
+                moved = K.apply_transport(inputs, self.source_model.mean, self.target_model.mean, self.transport_operator)
             return moved.to(device=inputs.device, dtype=inputs.dtype)
         moved = self.apply_transport(inputs, self.source_model.mean, self.target_model.mean, self.transport_operator,
                                      self.cov_stochastic_noise, batch_dim=-2 if is_batched else None)

@@ -418,3 +418,35 @@ def test_sharded_sinkhorn_driver_graph_replay_matches_fused_solver(api):
         assert got["iters"] == iters
         assert (got["u_local"] - want["u"]).abs().max().item() < 1e-4
         assert (got["v"] - want["v"]).abs().max().item() < 1e-4
+
+
+def test_prepared_transport_matches_functional_path_and_tracks_operator_changes(api):
+    """`GaussianTransport.transport` applies a prepared operator (built once per map): same result as the functional
+    `apply_transport`, rebuilt when the map or a mean is replaced, exact fallback for values outside the FP16 window."""
+    from ot_vae_lightning_b200 import kernels as K
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    dev = torch.device("cuda", 0)
+    d, n = 192, 6000
+    src = gaussian_latents(n, d, seed=3, device=dev)
+    tgt = gaussian_latents(n, d, seed=4, device=dev, shift=0.5, scale=1.5)
+    cfg = dict(dtype=torch.double, device=dev)
+    op = api.GaussianTransport(d, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).to(dev)
+    op.update(source_samples=src, target_samples=tgt)
+    op.compute()
+    want = (src.double() - op.source_model.mean) @ op.transport_operator.T + op.target_model.mean
+    got = op.transport(src)
+    assert got.dtype == src.dtype and rel(got, want.cpu().numpy()) < 1e-5
+    assert rel(K.apply_transport(src, op.source_model.mean, op.target_model.mean, op.transport_operator), want.cpu().numpy()) < 1e-5
+    # a latent far outside the FP16 window of the prepared scales: the device-gated TF32 kernel recomputes
+    far = src.clone()
+    far[17, 5] = 4.0e7
+    want_far = (far.double() - op.source_model.mean) @ op.transport_operator.T + op.target_model.mean
+    assert rel(op.transport(far), want_far.cpu().numpy()) < 1e-5
+    # replacing the map must not reuse the stale preparation
+    op.transport_operator = 2.0 * op.transport_operator
+    assert rel(op.transport(src), (2.0 * (want - op.target_model.mean) + op.target_model.mean).cpu().numpy()) < 1e-5
+    # ragged batch, leading dims and a second compute()
+    op.update(source_samples=tgt[:1000], target_samples=src[:1000])
+    op.compute()
+    want2 = (src[:777].double() - op.source_model.mean) @ op.transport_operator.T + op.target_model.mean
+    assert rel(op.transport(src[:777]), want2.cpu().numpy()) < 1e-5
