@@ -29,9 +29,9 @@ import torch.distributed as dist  # noqa: E402
 D_LAT, N_LAT, CHUNK = 512, 1 << 20, 1 << 16
 SK_N, SK_D, SK_EPS = 65536, 128, 0.05
 METRIC, UNIT = "cov+W2-map latents/s", "latents/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one stats_ts_kernel<2> launch on a 65536 x 512 chunk
-# (ncu --set full, profiles/prof_step_r02.md): 135.34 MB + 3.9 MB; the algorithmic figure is 134.2 MB
-STATS_TRAFFIC_BYTES_PER_LAUNCH = 139.2e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one stats_h2_kernel launch on a 65536 x 512 chunk
+# (ncu --set full, profiles/prof_stats_r03.md): 134.28 MB + 13.85 MB (partial tiles); the algorithmic figure is 134.2 MB
+STATS_TRAFFIC_BYTES_PER_LAUNCH = 148.1e6
 
 
 def load_peaks():
@@ -252,22 +252,27 @@ def main():
     stats_tflops = flops / (stats_ms / 3 * 1e-3) / 1e12
     apply_tflops = flops / (apply_ms / 3 * 1e-3) / 1e12
     n_chunks = N_LAT // CHUNK
-    # executed MMA flops of the statistics kernel: 3 TF32 MMAs per product (3xTF32 split) on the 256x128 blocks of the
-    # upper block triangle (6 of 8 at d = 512)
-    tri = 0.75 if D_LAT == 512 else 1.0
-    roofline = dict(kernel="stats_ts_kernel<2> (K1: sum x x^T, sum x, n), one launch per 65536 x 512 fp32 chunk",
-                    bound="tensor", achieved=stats_tflops, peak=tf32_peak, unit="TFLOP/s", frac=stats_tflops / tf32_peak,
+    # executed MMA flops of the statistics kernel: 3 FP16 MMAs per product (hi/lo split) on the 128x128 blocks of the
+    # upper block triangle (10 of 16 at d = 512); the kernel's tensor peak is the 16-bit dense one
+    nb = -(-D_LAT // 128)
+    tri = (nb * (nb + 1) / 2) / (nb * nb)
+    f16_peak = peaks["bf16_sustained"]
+    roofline = dict(kernel="stats_h2_kernel (K1: sum x x^T, sum x, n), one launch per 65536 x 512 fp32 chunk",
+                    bound="tensor", achieved=stats_tflops, peak=f16_peak, unit="TFLOP/s", frac=stats_tflops / f16_peak,
                     traffic=STATS_TRAFFIC_BYTES_PER_LAUNCH,
                     algorithmic=dict(flops_per_launch=2.0 * CHUNK * D_LAT * D_LAT, bytes_per_launch=CHUNK * D_LAT * 4,
                                      launches_per_step=2 * n_chunks, avg_launch_ms=stats_ms / 3 / n_chunks),
-                    executed=dict(tflops=3.0 * tri * stats_tflops, frac=3.0 * tri * stats_tflops / tf32_peak,
-                                  note="3 TF32 MMAs per fp32-accurate product, upper block triangle only: the ceiling of "
-                                       "`frac` for this scheme is 1/(3*0.75) = 0.44"),
-                    note=f"achieved = algorithmic flops 2*N*d^2 / CUDA-event time of the update calls (kernel + its 2 small "
-                         f"helper kernels); peak = TF32 dense = 1/2 of bf16_tflops_sustained ({peaks['source']}); traffic = "
-                         f"dram read+write bytes per launch from profiles/prof_step_r02.md (algorithmic: {CHUNK * D_LAT * 4})",
-                    others=dict(apply_transport_tflops=apply_tflops, apply_frac=apply_tflops / tf32_peak,
-                                apply_executed_frac=3.0 * apply_tflops / tf32_peak,
+                    executed=dict(tflops=3.0 * tri * stats_tflops, frac=3.0 * tri * stats_tflops / f16_peak,
+                                  note="3 FP16 MMAs per fp32-accurate product, upper block triangle only: the ceiling of "
+                                       f"`frac` for this scheme is 1/(3*{tri:.3f}) = {1 / (3 * tri):.2f}"),
+                    note=f"achieved = algorithmic flops 2*N*d^2 / CUDA-event time of the update calls (kernel + its small "
+                         f"helper kernels: pivot/scale, partial-tile reduction, merge); peak = measured 16-bit dense "
+                         f"bf16_tflops_sustained ({peaks['source']}) - the kernel issues kind::f16 MMAs; the kernel is bound by "
+                         f"raw-tile delivery (in-flight bytes / L2 latency), not by the tensor pipe (ncu: 35 % of FP16 peak); "
+                         f"traffic = dram read+write bytes per launch from profiles/prof_stats_r03.md "
+                         f"(algorithmic: {CHUNK * D_LAT * 4})",
+                    others=dict(apply_transport_tflops=apply_tflops, apply_frac=apply_tflops / f16_peak,
+                                apply_executed_frac=3.0 * apply_tflops / f16_peak,
                                 compute_map_ms=compute_ms / 3, stats_ms=stats_ms / 3, apply_ms=apply_ms / 3,
                                 stats_gbs=N_LAT * D_LAT * 4 / (stats_ms / 3 * 1e-3) / 1e9,
                                 apply_gbs=2 * N_LAT * D_LAT * 4 / (apply_ms / 3 * 1e-3) / 1e9, hbm_peak_gbs=peaks["hbm"]))
@@ -399,7 +404,8 @@ def main():
                     config=dict(workload="cfg2: streaming cov (2^20 source + 2^20 target 512-d latents, chunks of 65536) "
                                          "+ Gaussian W2 map + transport of the 2^20 source latents, per rank",
                                 dim=D_LAT, latents_per_rank=N_LAT, chunk=CHUNK, l2="inputs (2 x 2 GiB) exceed L2",
-                                arithmetic="fp32-accurate (3xTF32 / FFMA) products, fp64 running statistics",
+                                arithmetic="fp32-accurate products (FP16 hi/lo split with exact scales, TF32 split for the d x d matrix functions), "
+                                           "fp64 running statistics",
                                 sinkhorn_arithmetic="FP16 operand planes (TF32-size mantissa), fp32 accumulation and softmax",
                                 w2=float(w2)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
