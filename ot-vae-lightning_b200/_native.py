@@ -137,6 +137,40 @@ def stream_ptr(device: torch.device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class on_device:
+    """`torch.cuda.device(dev)` that costs nothing when `dev` is already current (the per-call overhead matters for
+    batches of a few hundred latents); also hands out the current stream once: `.stream` (handle) / `.workspace(n)`."""
+
+    __slots__ = ("device", "_ctx", "stream")
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self._ctx = None
+
+    def __enter__(self):
+        idx = self.device.index
+        if idx is not None and idx != torch.cuda.current_device():
+            self._ctx = torch.cuda.device(self.device)
+            self._ctx.__enter__()
+        self.stream = torch.cuda.current_stream(self.device).cuda_stream
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def stream_ptr(self):
+        return C.c_void_p(self.stream)
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        key = (self.device.index if self.device.index is not None else torch.cuda.current_device(), self.stream)
+        buf = _workspaces.get(key)
+        if buf is None or buf.numel() < nbytes:
+            _workspaces[key] = buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=self.device)
+        return buf
+
+
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 

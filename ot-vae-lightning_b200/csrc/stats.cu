@@ -13,10 +13,17 @@ namespace otk {
 // atomics across chunks.  This is the engine for small / unaligned dims; aligned dims go to the tcgen05 kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int ST_T = 64, ST_BK = 16, ST_THREADS = 256;
+constexpr int ST_FUSED_ROWS = 256;   // batches up to this many rows take the single-launch fused path
 
+// FUSED (small batches, one chunk = all rows): the CTA owns its output tile, so it applies the accumulate / EMA rule to the
+// running buffers itself - one launch per update, no staging area, no atomics (latency mode: batches of a few hundred).
+struct StatsRunning { void *n_obs, *sum, *sum_cov; int n_dtype, buf_dtype; double decay; };
+
+template <bool FUSED>
 __global__ void __launch_bounds__(ST_THREADS)
 stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
-                  int64_t chunk_rows, int n_tiles, double* __restrict__ ws_cov, double* __restrict__ ws_sum) {
+                  int64_t chunk_rows, int n_tiles, double* __restrict__ ws_cov, double* __restrict__ ws_sum,
+                  StatsRunning run) {
   __shared__ float As[ST_BK][ST_T + 4];
   __shared__ float Bs[ST_BK][ST_T + 4];
   // decode the upper-triangular tile pair (ti <= tj) from blockIdx.x
@@ -64,6 +71,32 @@ stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
+  }
+  if constexpr (FUSED) {
+    const double keep = run.decay < 0 ? 1.0 : run.decay, gain = run.decay < 0 ? 1.0 : 1.0 - run.decay;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int64_t gi = i0 + ty * 4 + i;
+      if (gi >= dim) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int64_t gj = j0 + tx * 4 + j;
+        if (gj >= dim) continue;
+        const int64_t e = l * dim * dim + gi * dim + gj;
+        store_real(run.sum_cov, e, run.buf_dtype, load_real(run.sum_cov, e, run.buf_dtype) * keep + acc[i][j] * gain);
+        if (ti != tj) {      // mirror the off-diagonal tile (a diagonal tile holds both triangles, computed identically)
+          const int64_t e2 = l * dim * dim + gj * dim + gi;
+          store_real(run.sum_cov, e2, run.buf_dtype, load_real(run.sum_cov, e2, run.buf_dtype) * keep + acc[i][j] * gain);
+        }
+      }
+    }
+    if (ti == tj && tid < ST_T && i0 + tid < dim) {
+      const int64_t e = l * dim + i0 + tid;
+      store_real(run.sum, e, run.buf_dtype, load_real(run.sum, e, run.buf_dtype) * keep + colsum * gain);
+    }
+    if (blockIdx.x == 0 && tid == 0)
+      store_real(run.n_obs, l, run.n_dtype, load_real(run.n_obs, l, run.n_dtype) * keep + (double)rows * gain);
+    return;
   }
   double* cov = ws_cov + l * dim * dim;
 #pragma unroll
@@ -161,6 +194,7 @@ static inline unsigned ew_grid(int64_t total) {
 
 }  // namespace otk
 
+namespace otk { extern int g_stats_force_cg; }
 using namespace otk;
 
 extern "C" size_t otk_stats_update_workspace_bytes(int64_t L, int64_t rows, int64_t dim) {
@@ -178,6 +212,18 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
   OTK_REQUIRE(row_stride >= dim, "stats_update: row_stride < dim");
   if (workspace_bytes < otk_stats_update_workspace_bytes(L, rows, dim) || !workspace) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
+  if (rows > 0 && rows <= ST_FUSED_ROWS && !g_stats_force_cg) {
+    // latency mode: one launch, every CTA merges its own output tile (exact fp64 products, as the reference's einsum)
+    const int n_tiles = (int)ceil_div(dim, ST_T);
+    const int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
+    if (pairs <= 65535 && L <= 65535) {
+      StatsRunning run{n_obs, sum, sum_cov, n_dtype, buf_dtype, decay};
+      stats_simt_kernel<true><<<dim3((unsigned)pairs, 1, (unsigned)L), ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride,
+                                                                                          rows, n_tiles, nullptr, nullptr, run);
+      OTK_LAUNCH_CHECK();
+      return OTK_OK;
+    }
+  }
   Arena ar(workspace, workspace_bytes);
   double* ws_cov = ar.take<double>((size_t)L * dim * dim);
   double* ws_sum = ar.take<double>((size_t)L * dim);
@@ -199,8 +245,8 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
       if (chunk > 65536) chunk = 65536;
       dim3 grid((unsigned)pairs, (unsigned)ceil_div(rows, chunk), (unsigned)L);
       OTK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stats_update: too many row chunks / batches");
-      stats_simt_kernel<<<grid, ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride, chunk, n_tiles, ws_cov,
-                                                     ws_sum);
+      stats_simt_kernel<false><<<grid, ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride, chunk, n_tiles, ws_cov,
+                                                            ws_sum, StatsRunning{});
       OTK_LAUNCH_CHECK();
     }
   }

@@ -17,6 +17,8 @@ from . import _native as N
 def _dev_tensor(t: Tensor, device: torch.device, dtype: Optional[torch.dtype] = None) -> Tensor:
     if dtype is None:
         dtype = t.dtype if t.dtype in (torch.float32, torch.float64) else torch.float32
+    if t.dtype == dtype and t.device == device and not t.requires_grad and t.is_contiguous():
+        return t                                   # the common case costs nothing
     return t.detach().to(device=device, dtype=dtype, non_blocking=True).contiguous()
 
 
@@ -31,20 +33,20 @@ def stats_update(x: Tensor, n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, dec
     d = run_sum.shape[-1]
     lead, L = _lead(run_sum.shape, 1)
     x = _dev_tensor(x, dev, torch.float32)
-    x = x.expand(*lead, *x.shape[-2:]) if x.shape[:-2] != lead else x
-    x = x.contiguous().view(L, -1, d)
-    rows = x.shape[1]
+    if x.shape[:-2] != lead:
+        x = x.expand(*lead, *x.shape[-2:]).contiguous()
+    rows = x.shape[-2]
     lib = N.load()
     for buf in (n_obs, run_sum, run_cov):
         if not (buf.is_cuda and buf.is_contiguous()):
             raise ValueError("running buffers must be contiguous CUDA tensors")
-    with torch.cuda.device(dev):
-        need = lib.otk_stats_update_workspace_bytes(L, rows, d)
-        ws = N.workspace(need, dev)
-        st = lib.otk_stats_update(N.ptr(x), L, rows, d, d, rows * d, -1.0 if decay is None else float(decay),
-                                  N.ptr(n_obs), N.dtype_code(n_obs.dtype), N.ptr(run_sum), N.ptr(run_cov),
-                                  N.dtype_code(run_sum.dtype), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
-    N.check(st, "otk_stats_update")
+    with N.on_device(dev) as ctx:
+        ws = ctx.workspace(lib.otk_stats_update_workspace_bytes(L, rows, d))
+        st = lib.otk_stats_update(x.data_ptr(), L, rows, d, d, rows * d, -1.0 if decay is None else float(decay),
+                                  n_obs.data_ptr(), N.dtype_code(n_obs.dtype), run_sum.data_ptr(), run_cov.data_ptr(),
+                                  N.dtype_code(run_sum.dtype), ws.data_ptr(), ws.numel(), ctx.stream)
+    if st != N.OK:
+        N.check(st, "otk_stats_update")
 
 
 def mean_cov(run_sum: Tensor, run_cov: Tensor, n_obs: Tensor) -> Tuple[Tensor, Tensor]:
@@ -213,12 +215,12 @@ class PreparedTransport:
         xd = _dev_tensor(x, self.device, torch.float32)
         if tuple(xd.shape[:-2]) != tuple(self.lead) or xd.shape[-1] != self.d:
             raise ValueError("PreparedTransport.apply: input does not match the operator's leading shape / dimension")
-        xd = xd.contiguous()
         y = torch.empty_like(xd)
-        with torch.cuda.device(self.device):
-            st = N.load().otk_apply_transport_prepared(N.ptr(xd), self.L, xd.shape[-2], self.d, N.ptr(self.state),
-                                                       self.state.numel(), N.ptr(y), N.stream_ptr(self.device))
-        N.check(st, "otk_apply_transport_prepared")
+        with N.on_device(self.device) as ctx:
+            st = N.load().otk_apply_transport_prepared(xd.data_ptr(), self.L, xd.shape[-2], self.d, self.state.data_ptr(),
+                                                       self.state.numel(), y.data_ptr(), ctx.stream)
+        if st != N.OK:
+            N.check(st, "otk_apply_transport_prepared")
         return y
 
 

@@ -53,6 +53,8 @@ class DistributionModel(nn.Module, utils.DDPMixin, ABC):
         return *self.leading_shape, self.dim
 
     def _broadcastable(self, shape):
+        if tuple(shape) == tuple(self.leading_shape):
+            return True
         return torch.broadcast_shapes(shape, self.leading_shape) == self.leading_shape
 
     def _validate_samples(self, samples: Tensor) -> None:
