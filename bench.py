@@ -44,45 +44,94 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with NVML during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed regions: NVML from a thread (every 10 ms) and, beside it,
+    the `nvidia-smi -lms` loop of the profiling recipe as a second source should NVML fail on the box."""
+
+    REASONS = (("nvmlClocksThrottleReasonHwSlowdown", "hw_slowdown"),
+               ("nvmlClocksThrottleReasonHwThermalSlowdown", "hw_thermal_slowdown"),
+               ("nvmlClocksThrottleReasonSwThermalSlowdown", "sw_thermal_slowdown"),
+               ("nvmlClocksThrottleReasonSwPowerCap", "sw_power_cap"))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.windows, self.errors, self.smi, self.smi_path = [], [], None, None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
+        except Exception as e:
             self.nv = None
+            self.errors.append(f"nvml init: {type(e).__name__}: {e}")
+        try:
+            import subprocess
+            import tempfile
+            fd, self.smi_path = tempfile.mkstemp(prefix="otk_clocks_", suffix=".csv")
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.smi = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                         "-lms", "50"], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception as e:
+            self.errors.append(f"nvidia-smi: {type(e).__name__}: {e}")
+
+    def mark(self, t0, t1):
+        """a timed region (host clock) - samples inside the regions are the ones reported"""
+        self.windows.append((t0, t1))
 
     def run(self):
         if self.nv is None:
             return
         nv = self.nv
-        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        names = [(getattr(nv, attr), name) for attr, name in self.REASONS if hasattr(nv, attr)]
         while not self.stop_flag:
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.05)
+                self.samples.append((time.perf_counter(), mhz, mask))
+            except Exception as e:
+                if len(self.errors) < 3:
+                    self.errors.append(f"nvml sample: {type(e).__name__}: {e}")
+            time.sleep(0.01)
+        self.names = names
 
     def result(self):
         self.stop_flag = True
-        if not self.samples:
-            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=[])
-        s = sorted(self.samples)
-        return dict(sm_mhz=s[len(s) // 2], sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+        if self.is_alive():
+            self.join(timeout=1.0)
+        names = getattr(self, "names", [])
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)] or self.samples
+        mhz = sorted(s[1] for s in inside)
+        reasons = {name for _, _, mask in inside for bit, name in names if mask & bit}
+        smi_mhz = []
+        if self.smi is not None:
+            self.smi.terminate()
+            try:
+                self.smi.wait(timeout=2.0)
+                for ln in open(self.smi_path):
+                    f = [t.strip() for t in ln.split(",")]
+                    if len(f) >= 6 and f[0].isdigit():
+                        smi_mhz.append(int(f[0]))
+                        self.max_mhz = self.max_mhz or int(f[1])
+                        for flag, name in zip(f[2:6], ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+                            if flag == "Active" and not mhz:
+                                reasons.add(name)
+                os.unlink(self.smi_path)
+            except Exception as e:
+                self.errors.append(f"nvidia-smi parse: {type(e).__name__}: {e}")
+        out = dict(sm_mhz=mhz[len(mhz) // 2] if mhz else None, sm_max_mhz=self.max_mhz, reasons=sorted(reasons),
+                   samples=len(mhz), source="nvml, 10 ms period, samples inside the timed regions" if mhz else None)
+        if smi_mhz:
+            smi_mhz.sort()
+            # nvidia-smi samples cover the whole run (idle gaps included): the upper quartile is the under-load clock
+            out["smi_sm_mhz_p75"] = smi_mhz[(3 * len(smi_mhz)) // 4]
+            if not mhz:
+                out.update(sm_mhz=out["smi_sm_mhz_p75"], samples=len(smi_mhz), source="nvidia-smi -lms 50, upper quartile of the run")
+        if self.errors:
+            out["sampler_errors"] = self.errors
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
@@ -130,8 +179,11 @@ def run_reference(args):
     line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic",
-                config=dict(workload="cfg2: streaming cov + W2 map + transport, 512-d latents",
-                            latents_per_step=sample, dim=D_LAT, note="bounded sample of the 2^20-latent step"),
+                config=dict(workload="cfg2: streaming cov (2^20 source + 2^20 target 512-d latents, chunks of 65536) "
+                                     "+ Gaussian W2 map + transport of the 2^20 source latents, per rank",
+                            dim=D_LAT, latents_per_rank=N_LAT, chunk=CHUNK, latents_per_step=sample,
+                            note=f"each step is a bounded sample of that workload: {sample} source + {sample} target "
+                                 f"latents through the same update / compute / transport sequence on the host cores"),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port",
                                   sample=f"{sample} source + {sample} target latents, d={D_LAT}, fp64 (oracle port of the "
                                          f"reference: einsum SYRK, eigh sqrtm, fp64 mat-vecs)"),
@@ -210,13 +262,17 @@ def main():
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             res = fn()
         e1.record()
         barrier()
+        if sampler is not None:
+            sampler.mark(t0, time.perf_counter())
         return max_over_ranks(e0.elapsed_time(e1)), res
 
+    sampler = None
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local)
@@ -286,14 +342,14 @@ def main():
         op128.compute()
 
         def stats128():
-            op128.source_model.reset()
-            op128.source_model.update(x128)
+            op128.source_model.update(x128)       # accumulating calls: the timed region holds update() only
 
         def apply128():
             op128.transport(x128)
 
         apply128()
         a_ms, _ = timed(apply128, 5)        # before stats128, which resets the source model the map was prepared from
+        op128.source_model.reset()
         stats128()
         s_ms, _ = timed(stats128, 5)
         s_ms, a_ms = s_ms / 5, a_ms / 5
@@ -356,9 +412,12 @@ def main():
                 xl, al = x[lo:hi].contiguous(), a[lo:hi].contiguous()
                 run = lambda: parallel.sharded_sinkhorn(xl, y, al, a, reg=SK_EPS, max_iter=iters, threshold=0.0, scale=scale)
             run()
+            sampler = ClockSampler(local)          # the Sinkhorn kernel runs at the board power cap: its own clock line
+            sampler.start()
             l0 = lib.otk_launch_count()
             sk_ms, _ = timed(run, 1)
             sk_launches = lib.otk_launch_count() - l0
+            sk_clocks = sampler.result()
             it_s = iters / (sk_ms * 1e-3)
             alg_gb = 2.0 * SK_N * SK_N * 4 / 1e9
             res = K.sinkhorn_points(x, y, a, a, reg=SK_EPS, max_iter=iters, threshold=0.0, scale=scale) if world == 1 else None
@@ -381,6 +440,7 @@ def main():
                                           tensor=dict(achieved=4.0 * SK_N * SK_N * SK_D * it_s / 1e12 / world,
                                                       peak=peaks["bf16_sustained"], unit="TFLOP/s per GPU",
                                                       note="executed FP16 MMA flops 2 passes x 2*N*M*d")))
+            sinkhorn["clocks"] = sk_clocks
             if res is not None:
                 s = res["summary"].cpu().tolist()
                 sinkhorn["check"] = dict(cost=s[0], mass=s[1], max_row_err=s[2], max_col_err=s[3])

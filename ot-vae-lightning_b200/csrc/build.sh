@@ -5,7 +5,7 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 cd "$HERE"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
-       -Xptxas -v -rdc=false)
+       -Xptxas -v -rdc=false ${OTK_EXTRA_NVCC_FLAGS:-})
 SRCS=$(ls *.cu)
 mkdir -p build
 pids=()

@@ -17,7 +17,7 @@ constexpr int ST_FUSED_ROWS = 256;   // batches up to this many rows take the si
 
 // FUSED (small batches, one chunk = all rows): the CTA owns its output tile, so it applies the accumulate / EMA rule to the
 // running buffers itself - one launch per update, no staging area, no atomics (latency mode: batches of a few hundred).
-struct StatsRunning { void *n_obs, *sum, *sum_cov; int n_dtype, buf_dtype; double decay; };
+// (StatsRunning: stats_umma.cuh)
 
 template <bool FUSED>
 __global__ void __launch_bounds__(ST_THREADS)
@@ -227,13 +227,17 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
   Arena ar(workspace, workspace_bytes);
   double* ws_cov = ar.take<double>((size_t)L * dim * dim);
   double* ws_sum = ar.take<double>((size_t)L * dim);
-  OTK_CUDA(cudaMemsetAsync(workspace, 0, align_up((size_t)L * dim * dim * 8, 256) + (size_t)L * dim * 8, st));
+  const size_t staging_bytes = align_up((size_t)L * dim * dim * 8, 256) + (size_t)L * dim * 8;
   int tile = ST_T;
   const float* pivot = nullptr;
+  if (rows == 0) OTK_CUDA(cudaMemsetAsync(workspace, 0, staging_bytes, st));
   if (rows > 0) {
-    int used = stats_umma_try(x, L, rows, dim, row_stride, batch_stride, ws_cov, ws_sum, ar, st, &tile, &pivot);
+    int used = stats_umma_try(x, L, rows, dim, row_stride, batch_stride, ws_cov, ws_sum, ar, st, &tile, &pivot,
+                              StatsRunning{n_obs, sum, sum_cov, n_dtype, buf_dtype, decay});
     if (used < 0) return used;
+    if (used == 2) return OTK_OK;          // FP16-split kernels: already merged into the running buffers
     if (!used) {
+      OTK_CUDA(cudaMemsetAsync(workspace, 0, staging_bytes, st));
       tile = ST_T;
       pivot = nullptr;
       int n_tiles = (int)ceil_div(dim, ST_T);

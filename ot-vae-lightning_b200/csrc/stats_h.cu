@@ -19,6 +19,7 @@
 //   epilogue every 1024 rows the accumulator is added into fp32 second-stage accumulators in shared memory (tensor-memory
 //            accumulation truncates), one fp64 atomic flush per CTA with the scales divided out.
 #include <cuda.h>
+#include <cstdio>
 #include <cuda_fp16.h>
 
 #include "otk_ptx.cuh"
@@ -28,17 +29,20 @@
 namespace otk {
 
 constexpr int SH_T = 128, SH_BK = 64;
-// Ring depths.  The raw ring and the A ring are as deep as there are converter sets, so a raw stage and an A slot belong
+// Ring depths.  All three rings are as deep as there are converter sets, so a raw stage, an A slot and a B stage belong
 // to ONE set and their barriers advance by exactly one phase per tile of that set (a parity wait cannot tell "two phases
-// behind" from "done").  The two-deep B ring is shared by the sets; see the wait order in the converter.
+// behind" from "done"); the sets are fully independent pipelines that meet only in the MMA issue order.
 constexpr int SH_SETS = 3;
-constexpr int SH_XS = SH_SETS, SH_BS = 2, SH_AS = SH_SETS, SH_ACC = 2;
+constexpr int SH_XS = SH_SETS, SH_BS = SH_SETS, SH_AS = SH_SETS, SH_ACC = 2;
 constexpr int SH_THREADS = (2 + 4 * SH_SETS + 4) * 32;   // TMA, MMA | SH_SETS x 4 converter warps | 4 epilogue warps
 constexpr int SH_SLAB = 32 * SH_BK * 4;              // 8 KiB: [64 rows x 32 features] fp32
 constexpr int SH_RAW = 4 * SH_SLAB;                  // 32 KiB
 constexpr int SH_BPLANE = SH_T * SH_BK * 2;          // 16 KiB: [128 features x 64 rows] fp16
 constexpr int SH_BSTAGE = 2 * SH_BPLANE;             // hi + lo
-constexpr int SH_SACC = SH_T * SH_T * 4;             // 64 KiB second-stage accumulators [column][row]
+constexpr int SH_SACC = SH_T * (SH_T + 1) / 2 * 4;   // 32.25 KiB second-stage accumulators, packed upper triangle: element
+                                                     // (row gi <= column gj) at gj (gj + 1) / 2 + gi  (the third B stage
+                                                     // lives in the half this packing frees)
+constexpr int SH_TRI = SH_T * (SH_T + 1) / 2;        // floats per record (packed upper triangle of the block)
 constexpr int SH_SUB = 1024;                         // rows accumulated in tensor memory per sub-chunk
 constexpr int SH_ACOL0 = 256;                        // TMEM columns [0,256): two accumulators, [256,448): A ring (3 x 64)
 constexpr int SH_SMEM = SH_XS * SH_RAW + SH_BS * SH_BSTAGE + SH_SACC + 1024 + 512;
@@ -91,7 +95,7 @@ __device__ __forceinline__ void split_rows32(uint32_t slab, int row0, int valid,
 
 __global__ void __launch_bounds__(SH_THREADS, 1)
 stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, const float* __restrict__ scale,
-               int rows, int dim, int parts, int range_len, double* __restrict__ ws_cov, double* __restrict__ ws_sum,
+               int rows, int dim, int parts, int range_len, float* __restrict__ rec_cov, double* __restrict__ ws_sum,
                int* __restrict__ overflow) {
   using namespace ptx;
   extern __shared__ uint8_t smem_raw[];
@@ -110,6 +114,11 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SH_ACC);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#ifdef OTK_SH_TIMING
+  const long long t_kernel0 = clock64();
+  unsigned long long g_kernel0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_kernel0));
+#endif
   const int l = blockIdx.x / parts, part = blockIdx.x % parts;
   const int r0 = part * range_len, r1 = min(rows, r0 + range_len);
   const int num_k = r1 > r0 ? (r1 - r0 + SH_BK - 1) / SH_BK : 0;
@@ -161,14 +170,18 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
         const uint32_t ab = tmem_base + SH_ACOL0 + sa * 64;
         const bool first = (kt == sub * k_per_sub);
         if (elect_one()) {
+#ifndef OTK_SH_NOMMA
 #pragma unroll
           for (int kk = 0; kk < SH_BK / 16; ++kk) {
             const uint64_t b_hi = smem_desc_sw128(bb + kk * 32, 16, 1024);
             const uint64_t b_lo = smem_desc_sw128(bb + SH_BPLANE + kk * 32, 16, 1024);
             umma_f16_ts(acc, ab + 32 + kk * 8, b_hi, idesc, !(first && kk == 0));   // lo * hi
+#ifndef OTK_SH_MMA1
             umma_f16_ts(acc, ab + kk * 8, b_lo, idesc, 1);                           // hi * lo
             umma_f16_ts(acc, ab + kk * 8, b_hi, idesc, 1);                           // hi * hi
+#endif
           }
+#endif
           umma_commit(&empty_b[sb]);
           umma_commit(&empty_a[sa]);
           if (kt == kt_end - 1) umma_commit(&acc_full[a]);
@@ -190,20 +203,31 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
     const float ncs = -c * s;
     double colsum = 0.0;
     float chk = 0.f;
+#ifdef OTK_SH_TIMING
+    long long tw_a = 0, tw_x = 0, tw_b = 0, t_cv = 0, t_st = 0, t_all = clock64();
+#define SH_TICK(acc) { const long long t_now = clock64(); acc += t_now - t_prev; t_prev = t_now; }
+#else
+#define SH_TICK(acc)
+#endif
     for (int it = cset; it < num_k; it += SH_SETS) {
       const int sx = it % SH_XS, sa = it % SH_AS, sb = it % SH_BS;
       const int valid = min(SH_BK, r1 - (r0 + it * SH_BK));              // rows past the range end contribute nothing
-      // Order matters: a set's consecutive tiles are SH_SETS apart, more than one phase of the two-deep B ring.  Once the
-      // MMAs of this set's previous tile (it - SH_SETS, same A slot) have retired, tile it-2 is the only user of the B
-      // stage that can still be pending, i.e. empty_b is at most one phase behind.
+#ifdef OTK_SH_TIMING
+      long long t_prev = clock64();
+#endif
+      // the A slot, the raw stage and the B stage of tile `it` were last used by this set's previous tile (it - SH_SETS)
       mbar_wait(&empty_a[sa], ((it / SH_AS) & 1) ^ 1);
       tc_fence_after();
+      SH_TICK(tw_a)
       mbar_wait(&full_a[sx], (it / SH_XS) & 1);
+      SH_TICK(tw_x)
       mbar_wait(&empty_b[sb], ((it / SH_BS) & 1) ^ 1);
+      SH_TICK(tw_b)
       float vsum = 0.f;
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + SH_ACOL0 + sa * 64;
       const uint32_t hb = brow + sb * SH_BSTAGE;
       const uint32_t slab = xbase + sx * SH_RAW;
+#ifndef OTK_SH_NOCONV
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {                                   // two halves of 32 rows
         uint32_t hw[16], lw[16];
@@ -218,28 +242,42 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
           sts128u(hb + SH_BPLANE + off, lw[4 * ch], lw[4 * ch + 1], lw[4 * ch + 2], lw[4 * ch + 3]);
         }
       }
+#endif
       colsum += (double)vsum;
       fence_proxy_async_smem();   // generic-proxy writes of the B planes -> visible to the tensor core
       __syncwarp();
+      SH_TICK(t_cv)
       if (lane == 0) { mbar_arrive(&empty_ra[sx]); mbar_arrive(&ready_b[sb]); }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready_a[sa]);
+      SH_TICK(t_st)
     }
-    if (in && num_k > 0) atomicAdd(&ws_sum[(int64_t)l * dim + col], colsum / (double)s);
+#ifdef OTK_SH_TIMING
+    if (lane == 0 && q == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && num_k > 8)
+      printf("cta %d set %d tiles %d: total %lld | wait empty_a %lld full_a %lld empty_b %lld | convert %lld | st-wait %lld (cycles per tile of this set)\n",
+             blockIdx.x, cset, (num_k - cset + SH_SETS - 1) / SH_SETS, (clock64() - t_all) / ((num_k - cset + SH_SETS - 1) / SH_SETS),
+             tw_a / ((num_k - cset + SH_SETS - 1) / SH_SETS), tw_x / ((num_k - cset + SH_SETS - 1) / SH_SETS),
+             tw_b / ((num_k - cset + SH_SETS - 1) / SH_SETS), t_cv / ((num_k - cset + SH_SETS - 1) / SH_SETS),
+             t_st / ((num_k - cset + SH_SETS - 1) / SH_SETS));
+#endif
+    // the set's raw stage is idle from here on (its last tile has been read): park the column sums there, the CTA adds
+    // the three sets up after the final barrier - one atomic per feature and CTA
+    *reinterpret_cast<double*>(xa + cset * SH_RAW + col * 8) = colsum / (double)s;
     if (!(chk == 0.f)) atomicOr(overflow, 1);                           // a value left the FP16 window, or NaN / inf input
   } else {
     // ===== epilogue: 4 warps (warp <-> TMEM lane quarter); second-stage fp32 accumulation in shared memory =====
     const int q = warp % 4;
-    const uint32_t srow = smem_u32(sacc) + (uint32_t)(q * 32 + lane) * 4;
+    const int gi = q * 32 + lane;                                        // TMEM lane = row of the block
+    const uint32_t srow = smem_u32(sacc) + (uint32_t)gi * 4;
     for (int sub = 0; sub < num_sub; ++sub) {
       const int a = sub % SH_ACC;
       mbar_wait(&acc_full[a], (sub / SH_ACC) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * SH_T;
 #pragma unroll 1
-      for (int c0 = 0; c0 < SH_T; c0 += 32) {
+      for (int c0 = q * 32; c0 < SH_T; c0 += 32) {                       // columns left of the warp's rows are never kept
         float v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
@@ -248,33 +286,53 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[a]);
         }
+        const uint32_t tri0 = (uint32_t)(c0 * (c0 + 1) / 2);
         if (sub == 0) {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) sts32(srow + (uint32_t)(c0 + jj) * (SH_T * 4), v[jj]);
+          for (int jj = 0; jj < 32; ++jj)
+            if (gi <= c0 + jj) sts32(srow + (tri0 + (uint32_t)(c0 * jj + jj * (jj + 1) / 2)) * 4, v[jj]);
         } else {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const uint32_t ad = srow + (uint32_t)(c0 + jj) * (SH_T * 4);
-            sts32(ad, lds32(ad) + v[jj]);
-          }
+          for (int jj = 0; jj < 32; ++jj)
+            if (gi <= c0 + jj) {
+              const uint32_t ad = srow + (tri0 + (uint32_t)(c0 * jj + jj * (jj + 1) / 2)) * 4;
+              sts32(ad, lds32(ad) + v[jj]);
+            }
         }
       }
     }
-    // flush: P'[gi][gj] for gi <= gj, stored TRANSPOSED (ws[gj][gi]) so that the 32 lanes of an atomic instruction hit
-    // 32 consecutive doubles (the merge kernel reads the transposed position); the power-of-two scales divide out exactly
-    const int gi = q * 32 + lane;
-    if (num_k > 0 && gi < dim) {
-      double* cov = ws_cov + (int64_t)l * dim * dim;
-      const float* sc = scale + (int64_t)l * dim;
-      const double inv_i = 1.0 / (double)sc[gi];
-#pragma unroll 4
-      for (int gj = 0; gj < dim; ++gj)
-        if (gi <= gj) atomicAdd(&cov[(int64_t)gj * dim + gi], (double)lds32(srow + (uint32_t)gj * (SH_T * 4)) * (inv_i / (double)sc[gj]));
+#ifdef OTK_SH_TIMING
+    const long long t_flush0 = clock64();
+#endif
+    // flush: the CTA's packed triangle goes to its own record with plain stores (a warp stores the 32 consecutive floats
+    // it owns of a column); stats_h_merge_kernel sums the records in fp64 and divides the power-of-two scales out.
+    // (148 CTAs x 8256 fp64 atomics on the same addresses cost 26 us here - a quarter of the kernel.)
+    {
+      float* rec = rec_cov + (int64_t)blockIdx.x * SH_TRI;
+      for (int gj = q * 32; gj < SH_T; ++gj)
+        if (gi <= gj) {
+          const uint32_t idx = (uint32_t)(gj * (gj + 1) / 2);
+          rec[idx + gi] = num_k > 0 ? lds32(srow + idx * 4) : 0.f;
+        }
     }
+#ifdef OTK_SH_TIMING
+    if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 140)) {
+      unsigned long long g1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+      printf("cta %d epi warp %d: loop end at %lld cycles after kernel start, flush %lld cycles; kernel start->flush end %llu ns (start stamp %llu)\n",
+             blockIdx.x, q, t_flush0 - t_kernel0, clock64() - t_flush0, g1 - g_kernel0, g_kernel0 % 10000000ull);
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if ((int)threadIdx.x < dim && num_k > 0) {
+    double sv = 0.0;
+#pragma unroll
+    for (int cs = 0; cs < SH_SETS; ++cs) sv += *reinterpret_cast<const double*>(xa + cs * SH_RAW + threadIdx.x * 8);
+    atomicAdd(&ws_sum[(int64_t)l * dim + threadIdx.x], sv);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -568,12 +626,16 @@ __global__ void stats_h2_reduce_kernel(const float* __restrict__ parts, const fl
 
 // pivot[l, f] = mean of the first min(rows, 64) latents; scale[l, f] = power of two mapping the largest deviation from
 // the pivot seen in those rows into [64, 128)  (1 if the feature is constant there).  Block = 32 features x 8 row groups.
+// Also resets the overflow flag and the S' staging vector of the launch that follows (saves two memset nodes).
 __global__ void pivot_scale_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride,
-                                   int64_t batch_stride, float* __restrict__ pivot, float* __restrict__ scale) {
+                                   int64_t batch_stride, float* __restrict__ pivot, float* __restrict__ scale,
+                                   int* __restrict__ flag, double* __restrict__ ws_sum) {
   __shared__ float part[8][33];
   __shared__ float piv[32];
   const int64_t l = blockIdx.y;
   const int64_t col = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) *flag = 0;
+  if (threadIdx.y == 1 && col < dim) ws_sum[l * dim + col] = 0.0;
   const int64_t n = rows < 64 ? rows : 64;
   const float* base = x + l * batch_stride + col;
   float acc = 0.f;
@@ -614,23 +676,173 @@ __global__ void zero_if_kernel(double* __restrict__ p, int64_t n, const int* __r
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = 0.0;
 }
 
-size_t stats_h_extra_workspace(int64_t L, int64_t dim) { return align_up((size_t)L * dim * 4, 256) + 256; }
+// ---------------------------------------------------------------------------------------------------------------------
+// Merge kernels: (records | partial tiles) -> running buffers, in one pass.  They replace "reduce into the fp64 staging
+// area, then merge": P'[i][j] (i <= j) is summed over the partials in fp64, the power-of-two scales are divided out, the
+// raw sums are rebuilt from the pivot-shifted ones ( sum x x^T = P' + c S'^T + S' c^T + n c c^T ,  sum x = S' + n c )
+// and the accumulate / EMA rule (gaussian_model.py:104-108, utils/__init__.py:204-206) is applied to [i][j] and [j][i].
+// If the overflow flag is up, the TF32 fallback has refilled the staging area (P' transposed at [j][i], S') and that is
+// what gets merged instead - same kernel, no extra gated launch.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int HM_OUT = 64, HM_GROUPS = 4;
 
-bool stats_h_eligible(int64_t L, int64_t rows, int64_t dim) { return dim <= SH_T && rows >= 1 && L >= 1; }
+__device__ __forceinline__ void hm_store(const StatsRunning& run, int64_t l, int dim, int gi, int gj, double pp, double rows,
+                                         const float* __restrict__ pivot, const double* __restrict__ ws_sum) {
+  const double keep = run.decay < 0 ? 1.0 : run.decay, gain = run.decay < 0 ? 1.0 : 1.0 - run.decay;
+  const double ci = pivot[l * dim + gi], cj = pivot[l * dim + gj];
+  const double si = ws_sum[l * dim + gi], sj = ws_sum[l * dim + gj];
+  const double v = pp + ci * sj + si * cj + rows * ci * cj;
+  const int64_t e = l * dim * dim + (int64_t)gi * dim + gj;
+  store_real(run.sum_cov, e, run.buf_dtype, load_real(run.sum_cov, e, run.buf_dtype) * keep + v * gain);
+  if (gi != gj) {
+    const int64_t e2 = l * dim * dim + (int64_t)gj * dim + gi;
+    store_real(run.sum_cov, e2, run.buf_dtype, load_real(run.sum_cov, e2, run.buf_dtype) * keep + v * gain);
+  } else {
+    const int64_t f = l * dim + gj;
+    store_real(run.sum, f, run.buf_dtype, load_real(run.sum, f, run.buf_dtype) * keep + (sj + rows * cj) * gain);
+  }
+}
 
-// Launches pivot/scale + the FP16-split kernel.  *flag_out (device int) is non-zero afterwards iff a value left the FP16
-// range, in which case the staging area is invalid and the caller must re-run with the TF32 kernel (stats_umma.cu).
+// narrow: thread <-> packed index t = gj (gj + 1) / 2 + gi of the triangle (consecutive threads read consecutive floats of
+// a record and write consecutive elements of row gj); HM_GROUPS thread groups share the records of an output.
+__global__ void __launch_bounds__(HM_OUT * HM_GROUPS)
+stats_h_merge_kernel(const float* __restrict__ rec_cov, int parts, const float* __restrict__ scale,
+                     const float* __restrict__ pivot, const int* __restrict__ flag, const double* __restrict__ ws_cov,
+                     const double* __restrict__ ws_sum, int dim, double rows, StatsRunning run) {
+  __shared__ double red[HM_GROUPS][HM_OUT];
+  const int tri = dim * (dim + 1) / 2;
+  const int blocks_per_l = (tri + HM_OUT - 1) / HM_OUT;
+  const int64_t l = blockIdx.x / blocks_per_l;
+  const int o = threadIdx.x % HM_OUT, g = threadIdx.x / HM_OUT;
+  const int t = (blockIdx.x % blocks_per_l) * HM_OUT + o;
+  const bool fallback = *flag != 0;
+  int gj = 0, gi = 0;
+  if (t < tri) {
+    gj = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while ((gj + 1) * (gj + 2) / 2 <= t) ++gj;
+    while (gj * (gj + 1) / 2 > t) --gj;
+    gi = t - gj * (gj + 1) / 2;
+  }
+  double acc = 0.0;
+  if (t < tri && !fallback) {
+    const float* p = rec_cov + (int64_t)l * parts * SH_TRI + t;
+    double a0 = 0.0, a1 = 0.0;
+    int r = g;
+    for (; r + HM_GROUPS < parts; r += 2 * HM_GROUPS) {
+      a0 += (double)p[(int64_t)r * SH_TRI];
+      a1 += (double)p[(int64_t)(r + HM_GROUPS) * SH_TRI];
+    }
+    if (r < parts) a0 += (double)p[(int64_t)r * SH_TRI];
+    acc = a0 + a1;
+  }
+  red[g][o] = acc;
+  __syncthreads();
+  if (g != 0 || t >= tri) return;
+  double pp;
+  if (fallback) {
+    pp = ws_cov[l * dim * dim + (int64_t)gj * dim + gi];
+  } else {
+#pragma unroll
+    for (int k = 1; k < HM_GROUPS; ++k) acc += red[k][o];
+    pp = acc * (1.0 / ((double)scale[l * dim + gi] * (double)scale[l * dim + gj]));
+  }
+  hm_store(run, l, dim, gi, gj, pp, rows, pivot, ws_sum);
+  if (t == 0) {
+    const double keep = run.decay < 0 ? 1.0 : run.decay, gain = run.decay < 0 ? 1.0 : 1.0 - run.decay;
+    store_real(run.n_obs, l, run.n_dtype, load_real(run.n_obs, l, run.n_dtype) * keep + rows * gain);
+  }
+}
+
+// wide: block <-> one row of one 128 x 128 unit; 32 float4 columns x 8 segment groups
+__global__ void __launch_bounds__(256)
+stats_h2_merge_kernel(const float* __restrict__ parts, int n_seg, int n_units, int upl, int nB,
+                      const float* __restrict__ scale, const float* __restrict__ pivot, const int* __restrict__ flag,
+                      const double* __restrict__ ws_cov, const double* __restrict__ ws_sum, int dim, double rows,
+                      StatsRunning run) {
+  __shared__ double red[8][32][4];
+  const int u = blockIdx.x / SH_T, r = blockIdx.x % SH_T;
+  const int64_t l = u / upl;
+  int w = u % upl, bi = 0;
+  while (w >= nB - bi) { w -= nB - bi; ++bi; }
+  const int bj = bi + w;
+  const int c4 = threadIdx.x % 32, g = threadIdx.x / 32;
+  const int gi = bi * SH_T + r, gj0 = bj * SH_T + c4 * 4;
+  const bool fallback = *flag != 0;
+  const bool live = gi < dim && gj0 < dim && gi <= gj0 + 3;            // dim % 4 == 0: a group is inside or outside
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  if (live && !fallback) {
+    const float4* p = reinterpret_cast<const float4*>(parts + (int64_t)u * S2_TILE + r * SH_T + c4 * 4);
+    const int64_t stride = (int64_t)n_units * S2_TILE / 4;
+    for (int sg = g; sg < n_seg; sg += 8) {
+      const float4 v = p[(int64_t)sg * stride];
+      a[0] += (double)v.x; a[1] += (double)v.y; a[2] += (double)v.z; a[3] += (double)v.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) red[g][c4][k] = a[k];
+  __syncthreads();
+  // finalise with one thread per column (128 threads: the read-modify-write latencies of the running buffers overlap)
+  if (threadIdx.x < SH_T) {
+    const int c = threadIdx.x, gj = bj * SH_T + c;
+    if (gi < dim && gj < dim && gi <= gj) {
+      double pp;
+      if (fallback) {
+        pp = ws_cov[l * dim * dim + (int64_t)gj * dim + gi];
+      } else {
+        pp = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pp += red[q][c / 4][c % 4];
+        pp *= 1.0 / ((double)scale[l * dim + gi] * (double)scale[l * dim + gj]);
+      }
+      hm_store(run, l, dim, gi, gj, pp, rows, pivot, ws_sum);
+    }
+  }
+  if (u % upl == 0 && r == 0 && threadIdx.x == 0) {
+    const double keep = run.decay < 0 ? 1.0 : run.decay, gain = run.decay < 0 ? 1.0 : 1.0 - run.decay;
+    store_real(run.n_obs, l, run.n_dtype, load_real(run.n_obs, l, run.n_dtype) * keep + rows * gain);
+  }
+}
+
+int stats_h_merge(const StatsHPlan& plan, const float* pivot, const double* ws_cov, const double* ws_sum, int64_t L,
+                  int64_t rows, int64_t dim, const StatsRunning& run, cudaStream_t st) {
+  if (plan.mode == 1) {
+    const int64_t tri = dim * (dim + 1) / 2, blocks = L * ceil_div(tri, HM_OUT);
+    stats_h_merge_kernel<<<(unsigned)blocks, HM_OUT * HM_GROUPS, 0, st>>>(plan.parts, plan.n_parts, plan.scale, pivot, plan.flag,
+                                                                        ws_cov, ws_sum, (int)dim, (double)rows, run);
+  } else {
+    stats_h2_merge_kernel<<<(unsigned)(plan.n_units * SH_T), 256, 0, st>>>(plan.parts, plan.n_parts, plan.n_units, plan.upl,
+                                                                          plan.nB, plan.scale, pivot, plan.flag, ws_cov,
+                                                                          ws_sum, (int)dim, (double)rows, run);
+  }
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+constexpr int64_t SH_MAX_L = 1024;     // leading indices the narrow kernel takes (bounds the record area: 33 KB per CTA)
+static int64_t stats_h_max_records(int64_t L) { const int64_t sms = sm_count(); return L > sms ? L : sms; }
+
+size_t stats_h_extra_workspace(int64_t L, int64_t dim) {
+  const size_t recs = (dim <= SH_T && L <= SH_MAX_L) ? align_up((size_t)stats_h_max_records(L) * SH_TRI * 4, 256) : 0;
+  return align_up((size_t)L * dim * 4, 256) + 256 + recs;
+}
+
+bool stats_h_eligible(int64_t L, int64_t rows, int64_t dim) { return dim <= SH_T && rows >= 1 && L >= 1 && L <= SH_MAX_L; }
+
+// Launches pivot/scale + the FP16-split kernel.  *plan->flag (device int) is non-zero afterwards iff a value left the FP16
+// range, in which case the records are invalid and the caller's stream re-runs the call with the TF32 kernel
+// (stats_umma.cu) into the staging area before stats_h_merge.
 int stats_h_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
-                   float* pivot, double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int** flag_out) {
+                   float* pivot, double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, StatsHPlan* plan) {
+  (void)ws_cov;
   float* scale = ar.take<float>((size_t)L * dim);
   int* flag = ar.take<int>(16);
+  float* rec = ar.take<float>((size_t)stats_h_max_records(L) * SH_TRI);
   if (!ar.ok()) return OTK_ERR_WORKSPACE;
-  OTK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  pivot_scale_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, row_stride, batch_stride,
-                                                                                             pivot, scale);
-  OTK_LAUNCH_CHECK();
   CUtensorMap mX;
   if (!encode_map_f32_3d(&mX, x, dim, rows, L, row_stride, batch_stride, 32, SH_BK, /*atom32=*/true)) return 0;
+  pivot_scale_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, row_stride, batch_stride,
+                                                                                             pivot, scale, flag, ws_sum);
+  OTK_LAUNCH_CHECK();
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -644,11 +856,11 @@ int stats_h_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   int64_t range_len = ceil_div(ceil_div(rows, parts), SH_BK) * SH_BK;
   if (range_len < 256) range_len = 256;
   parts = ceil_div(rows, range_len);
-  if (L * parts > INT32_MAX) return 0;
+  if (L * parts > stats_h_max_records(L)) return OTK_ERR_WORKSPACE;
   stats_h_kernel<<<(unsigned)(L * parts), SH_THREADS, SH_SMEM, st>>>(mX, pivot, scale, (int)rows, (int)dim, (int)parts,
-                                                                    (int)range_len, ws_cov, ws_sum, flag);
+                                                                    (int)range_len, rec, ws_sum, flag);
   OTK_LAUNCH_CHECK();
-  *flag_out = flag;
+  *plan = StatsHPlan{1, rec, (int)parts, 0, 0, 0, scale, flag};
   return 1;
 }
 
@@ -665,18 +877,17 @@ bool stats_h2_eligible(int64_t L, int64_t rows, int64_t dim) {
 
 // FP16-split kernel for dim > 128: pivot/scale, then one launch + one partial-tile reduction per super-chunk of rows.
 int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
-                    float* pivot, double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int** flag_out) {
+                    float* pivot, double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, StatsHPlan* plan) {
   const int64_t nB = ceil_div(dim, SH_T), upl = nB * (nB + 1) / 2, n_units = L * upl;
   float* scale = ar.take<float>((size_t)L * dim);
   int* flag = ar.take<int>(16);
   float* parts = ar.take<float>((size_t)S2_MAX_ITEMS * S2_TILE);
   if (!ar.ok()) return OTK_ERR_WORKSPACE;
-  OTK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  pivot_scale_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, row_stride, batch_stride,
-                                                                                             pivot, scale);
-  OTK_LAUNCH_CHECK();
   CUtensorMap mX;
   if (!encode_map_f32_3d(&mX, x, dim, rows, L, row_stride, batch_stride, 32, SH_BK, /*atom32=*/true)) return 0;
+  pivot_scale_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, row_stride, batch_stride,
+                                                                                             pivot, scale, flag, ws_sum);
+  OTK_LAUNCH_CHECK();
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -686,6 +897,11 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
   }
   const int64_t sms = sm_count();
   const int64_t max_seg = S2_MAX_ITEMS / n_units;                       // segments per launch (>= 1 by eligibility)
+  // One super-chunk (the streaming case: max_seg * 2048 rows = 209 k rows at d = 512): the partial tiles are merged
+  // straight into the running buffers by stats_h2_merge_kernel.  Longer calls reduce every super-chunk into the fp64
+  // staging area (cleared here) and leave the merge to the caller.
+  const bool single = rows <= max_seg * 2048;
+  if (!single) OTK_CUDA(cudaMemsetAsync(ws_cov, 0, (size_t)L * dim * dim * 8, st));
   for (int64_t row_lo = 0; row_lo < rows;) {
     // segment length: the smallest number of "rounds" k of the persistent grid whose segments are <= 2048 rows
     // (tensor-memory accumulation truncates) - items = n_units * segments just below k * #SMs
@@ -707,6 +923,11 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
     stats_h2_kernel<<<grid, S2_THREADS, S2_SMEM, st>>>(mX, pivot, scale, (int)dim, (int)nB, (int)upl, (int)n_units, (int)n_items,
                                                       (int)seg_len, (int)row_lo, (int)row_hi, parts, ws_sum, flag);
     OTK_LAUNCH_CHECK();
+    if (single) {
+      if (row_hi != rows) return OTK_ERR_CUDA;   // cannot happen: `single` bounds the segment count
+      *plan = StatsHPlan{2, parts, (int)n_seg, (int)n_units, (int)upl, (int)nB, scale, flag};
+      return 1;
+    }
     int64_t blocks = ceil_div(L * dim * dim / 4, 256);
     if (blocks > sms * 16) blocks = sms * 16;
     stats_h2_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(parts, scale, L, (int)dim, (int)nB, (int)upl, (int)n_units, (int)n_seg,
@@ -714,7 +935,7 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
     OTK_LAUNCH_CHECK();
     row_lo = row_hi;
   }
-  *flag_out = flag;
+  *plan = StatsHPlan{0, parts, 0, (int)n_units, (int)upl, (int)nB, scale, flag};
   return 1;
 }
 

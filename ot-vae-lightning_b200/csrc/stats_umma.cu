@@ -430,7 +430,8 @@ static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, in
 int g_stats_force_cg = 0;   // tuning aid: 1 / 2 force the single-CTA / CTA-pair instantiation
 
 int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
-                   double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile, const float** pivot_out) {
+                   double* ws_cov, double* ws_sum, Arena& ar, cudaStream_t st, int* tile, const float** pivot_out,
+                   const StatsRunning& run) {
   if (dim < 64 || dim % 4 != 0 || row_stride % 4 != 0 || batch_stride % 4 != 0) return 0;
   if (rows < 1 || rows > INT32_MAX || dim > 16384 || L > 65535) return 0;
   if (reinterpret_cast<uintptr_t>(x) & 15) return 0;
@@ -441,25 +442,27 @@ int stats_umma_try(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   if (!g_stats_force_cg && (narrow || wide)) {
     // FP16-split kernels; the TF32 kernel follows as a device-gated fallback that only runs if a value left the FP16
     // range (it then recomputes into the re-zeroed staging area with the same pivot)
-    int* flag = nullptr;
-    int used = narrow ? stats_h_launch(x, L, rows, dim, row_stride, batch_stride, pivot, ws_cov, ws_sum, ar, st, &flag)
-                      : stats_h2_launch(x, L, rows, dim, row_stride, batch_stride, pivot, ws_cov, ws_sum, ar, st, &flag);
+    StatsHPlan plan{};
+    int used = narrow ? stats_h_launch(x, L, rows, dim, row_stride, batch_stride, pivot, ws_cov, ws_sum, ar, st, &plan)
+                      : stats_h2_launch(x, L, rows, dim, row_stride, batch_stride, pivot, ws_cov, ws_sum, ar, st, &plan);
     if (used < 0) return used;
     if (used == 1) {
       CUtensorMap mF;
-      if (!encode_map_f32_3d(&mF, x, dim, rows, L, row_stride, batch_stride, 32, SU_BK, /*atom32=*/true)) return 0;
-      if (narrow) {   // (the wide path's reduction kernel clears the staging area itself when the flag is up)
-        const int64_t staged = (reinterpret_cast<char*>(ws_sum) - reinterpret_cast<char*>(ws_cov)) / 8 + L * dim;
-        OTK_TRY(stats_zero_if(ws_cov, staged, flag, st));
-      }
-      used = dim >= 512 ? launch_stats<2>(mF, pivot, L, rows, dim, ws_cov, ws_sum, st, flag)
-                        : launch_stats<1>(mF, pivot, L, rows, dim, ws_cov, ws_sum, st, flag);
+      if (!encode_map_f32_3d(&mF, x, dim, rows, L, row_stride, batch_stride, 32, SU_BK, /*atom32=*/true)) return OTK_ERR_CUDA;
+      // flag up: clear the staging area (P' and S') and let the TF32 kernel recompute the call into it
+      const int64_t staged = (reinterpret_cast<char*>(ws_sum) - reinterpret_cast<char*>(ws_cov)) / 8 + L * dim;
+      OTK_TRY(stats_zero_if(ws_cov, staged, plan.flag, st));
+      used = dim >= 512 ? launch_stats<2>(mF, pivot, L, rows, dim, ws_cov, ws_sum, st, plan.flag)
+                        : launch_stats<1>(mF, pivot, L, rows, dim, ws_cov, ws_sum, st, plan.flag);
       if (used <= 0) return used < 0 ? used : OTK_ERR_CUDA;
       *pivot_out = pivot;
       *tile = SU_T;
-      return 1;
+      if (plan.mode == 0) return 1;        // several super-chunks: the staging area holds the result, the caller merges
+      OTK_TRY(stats_h_merge(plan, pivot, ws_cov, ws_sum, L, rows, dim, run, st));
+      return 2;
     }
   }
+  OTK_CUDA(cudaMemsetAsync(ws_cov, 0, (reinterpret_cast<char*>(ws_sum) - reinterpret_cast<char*>(ws_cov)) + (size_t)L * dim * 8, st));
   pivot_kernel<<<dim3((unsigned)ceil_div(dim, 32), (unsigned)L), dim3(32, 8), 0, st>>>(x, rows, dim, row_stride, batch_stride, pivot);
   OTK_LAUNCH_CHECK();
   CUtensorMap mX;
