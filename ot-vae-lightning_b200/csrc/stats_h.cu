@@ -20,6 +20,7 @@
 //            accumulation truncates), one fp64 atomic flush per CTA with the scales divided out.
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "otk_ptx.cuh"
@@ -346,11 +347,26 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
 // A segment is short enough (<= 2048 rows) for the truncating tensor-memory accumulation; its 128 x 128 fp32 tile is
 // written with plain stores to a per-item slot and the partial tiles are summed in fp64 by stats_h2_reduce_kernel (no
 // atomics on the covariance, no second-stage accumulators in shared memory).
-constexpr int S2_XS = 2, S2_PB = 3, S2_AS = 4, S2_ACC = 2;           // raw rings (per side), B planes ring, A slots, accumulators
+constexpr int S2_XS = 3, S2_PB = 4, S2_AS = 4;                        // raw A ring, B ring (raw tile -> planes, in place), A slots
 constexpr int S2_THREADS = (2 + 8 + 8 + 4 + 1) * 32;                   // TMA (A), MMA | 8 A conv. | 8 B conv. | 4 epilogue | TMA (B)
-constexpr int S2_SMEM = 2 * S2_XS * SH_RAW + S2_PB * SH_BSTAGE + 1024 + 512;
-constexpr int S2_TILE = SH_T * SH_T;                                    // floats per partial tile
-constexpr int S2_MAX_ITEMS = 1024;                                      // partial-tile slots per launch (64 MiB)
+constexpr int S2_SMEM = S2_XS * SH_RAW + S2_PB * SH_BSTAGE + 1024 + 512;
+static_assert(SH_RAW == SH_BSTAGE, "the B planes overwrite the raw tile they were converted from");
+constexpr int S2_TILE = SH_T * SH_T;                                    // floats per 128 x 128 partial tile
+constexpr int S2_MAX_ITEMS = 2048;                                      // 128 x 128 slots per launch (128 MiB); a pair item takes 4
+
+template <int CG>
+__device__ __forceinline__ void h2_umma(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 struct S2Item { int l, bi, bj, r0, r1; };
 __device__ __forceinline__ S2Item s2_decode(int item, int n_units, int upl, int nB, int seg_len, int row_lo, int row_hi) {
@@ -366,43 +382,52 @@ __device__ __forceinline__ S2Item s2_decode(int item, int n_units, int upl, int 
   return t;
 }
 
+// CG == 2: a CTA pair (tcgen05 cta_group::2) owns a 256 x 256 block.  Each CTA still loads and converts ONE raw A block
+// (its 128 of the 256 A features -> its own tensor memory) and ONE raw B block (its 128 of the 256 B features -> its own
+// shared memory) per 64-row tile, exactly the per-CTA work of CG == 1, but the pair's MMAs (M = N = 256, issued by the
+// leader) do twice the flops per CTA with it: L2 -> SM bytes, shared-memory traffic and converter instructions per flop
+// all halve - the three things the single-CTA kernel is bound by (53 us of its 87 us per 65536 x 512 chunk is raw-tile
+// delivery alone).  Converters of both CTAs arrive on the leader's ready barriers, commits are multicast to both CTAs, each
+// CTA drains its own 128 x 256 accumulator (one accumulator: 256 of the 512 tensor-memory columns, the A ring has the rest).
+template <int CG>
 __global__ void __launch_bounds__(S2_THREADS, 1)
 stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, const float* __restrict__ scale,
                 int dim, int nB, int upl, int n_units, int n_items, int seg_len, int row_lo, int row_hi,
                 float* __restrict__ parts, double* __restrict__ ws_sum, int* __restrict__ overflow) {
   using namespace ptx;
+  constexpr int S2_ACC = CG == 2 ? 1 : 2;                 // accumulators of 128 * CG columns in tensor-memory columns [0, 256)
+  constexpr int BW = SH_T * CG;                           // block width = accumulator columns = row length of a partial tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xa = smem;                                     // raw A ring
-  uint8_t* xr = xa + S2_XS * SH_RAW;                      // raw B ring
-  uint8_t* xb = xr + S2_XS * SH_RAW;                      // B planes ring
+  uint8_t* xb = xa + S2_XS * SH_RAW;                      // B ring: a stage is a raw tile, then (in place) its hi / lo planes
   uint64_t* full_a = reinterpret_cast<uint64_t*>(xb + S2_PB * SH_BSTAGE);
   uint64_t* empty_ra = full_a + S2_XS;
   uint64_t* full_b = empty_ra + S2_XS;
-  uint64_t* empty_rb = full_b + S2_XS;
-  uint64_t* ready_a = empty_rb + S2_XS;
+  uint64_t* ready_a = full_b + S2_PB;
   uint64_t* empty_a = ready_a + S2_AS;
   uint64_t* ready_b = empty_a + S2_AS;
   uint64_t* empty_b = ready_b + S2_PB;
   uint64_t* acc_full = empty_b + S2_PB;
-  uint64_t* acc_empty = acc_full + S2_ACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + S2_ACC);
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const int group = CG == 2 ? blockIdx.x / 2 : blockIdx.x;           // item-processing unit (CTA or CTA pair)
+  const int n_groups = CG == 2 ? gridDim.x / 2 : gridDim.x;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
-    for (int s = 0; s < S2_XS; ++s) {
-      mbar_init(&full_a[s], 1); mbar_init(&empty_ra[s], 8);
-      mbar_init(&full_b[s], 1); mbar_init(&empty_rb[s], 8);
-    }
-    for (int s = 0; s < S2_AS; ++s) { mbar_init(&ready_a[s], 8); mbar_init(&empty_a[s], 1); }
-    for (int s = 0; s < S2_PB; ++s) { mbar_init(&ready_b[s], 8); mbar_init(&empty_b[s], 1); }
-    for (int a = 0; a < S2_ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    for (int s = 0; s < S2_XS; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_ra[s], 8); }
+    for (int s = 0; s < S2_PB; ++s) mbar_init(&full_b[s], 1);
+    for (int s = 0; s < S2_AS; ++s) { mbar_init(&ready_a[s], 8 * CG); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < S2_PB; ++s) { mbar_init(&ready_b[s], 8 * CG); mbar_init(&empty_b[s], 1); }
+    for (int a = 0; a < S2_ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4 * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc_cg<CG>(tmem_slot, 512); tmem_relinquish_cg<CG>(); }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -410,17 +435,19 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
     // ===== TMA producers: warp 0 streams the A blocks, warp 22 the B blocks (independent rings: a slow side must not
     // hold back the other side's loads) =====
     const bool side_b = warp == 22;
-    uint8_t* ring = side_b ? xr : xa;
+    // (a B stage is free again when the MMAs that read its planes have retired: empty_b, armed by tcgen05.commit)
+    uint8_t* ring = side_b ? xb : xa;
     uint64_t* full = side_b ? full_b : full_a;
-    uint64_t* empty = side_b ? empty_rb : empty_ra;
+    uint64_t* empty = side_b ? empty_b : empty_ra;
+    const int depth = side_b ? S2_PB : S2_XS;
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = group; item < n_items; item += n_groups) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
       const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
-      const int f0 = (side_b ? t.bj : t.bi) * SH_T;
+      const int f0 = (side_b ? t.bj : t.bi) * BW + (int)rank * SH_T;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
-        const int sx = it % S2_XS;
-        mbar_wait(&empty[sx], ((it / S2_XS) & 1) ^ 1);
+        const int sx = it % depth;
+        mbar_wait(&empty[sx], ((it / depth) & 1) ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[sx], SH_RAW);
 #pragma unroll
@@ -431,16 +458,17 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = idesc_f16(SH_T, SH_T);
+    // ===== MMA issuer (the leader CTA of a pair issues for both) =====
+    const uint32_t idesc = idesc_f16(BW, BW);
     int it = 0, n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+    if (rank == 0)
+    for (int item = group; item < n_items; item += n_groups, ++n) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
       const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
       const int a = n % S2_ACC;
       mbar_wait(&acc_empty[a], ((n / S2_ACC) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t acc = tmem_base + a * SH_T;
+      const uint32_t acc = tmem_base + a * BW;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
         const int sp = it % S2_PB, sa = it % S2_AS;
         mbar_wait(&ready_b[sp], (it / S2_PB) & 1);
@@ -449,17 +477,19 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         const uint32_t bb = smem_u32(xb + sp * SH_BSTAGE);
         const uint32_t ab = tmem_base + SH_ACOL0 + sa * 64;
         if (elect_one()) {
+#ifndef OTK_SH_NOMMA
 #pragma unroll
           for (int kk = 0; kk < SH_BK / 16; ++kk) {
             const uint64_t b_hi = smem_desc_sw128(bb + kk * 32, 16, 1024);
             const uint64_t b_lo = smem_desc_sw128(bb + SH_BPLANE + kk * 32, 16, 1024);
-            umma_f16_ts(acc, ab + 32 + kk * 8, b_hi, idesc, !(kt == 0 && kk == 0));   // lo * hi
-            umma_f16_ts(acc, ab + kk * 8, b_lo, idesc, 1);                             // hi * lo
-            umma_f16_ts(acc, ab + kk * 8, b_hi, idesc, 1);                             // hi * hi
+            h2_umma<CG>(acc, ab + 32 + kk * 8, b_hi, idesc, !(kt == 0 && kk == 0));   // lo * hi
+            h2_umma<CG>(acc, ab + kk * 8, b_lo, idesc, 1);                             // hi * lo
+            h2_umma<CG>(acc, ab + kk * 8, b_hi, idesc, 1);                             // hi * hi
           }
-          umma_commit(&empty_b[sp]);
-          umma_commit(&empty_a[sa]);
-          if (kt == num_k - 1) umma_commit(&acc_full[a]);
+#endif
+          umma_commit_cg<CG>(&empty_b[sp]);
+          umma_commit_cg<CG>(&empty_a[sa]);
+          if (kt == num_k - 1) umma_commit_cg<CG>(&acc_full[a]);
         }
         __syncwarp();
       }
@@ -470,12 +500,13 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
     const uint32_t cc = (uint32_t)lane / 8, within = (uint32_t)(lane % 8) * 4;
     const uint32_t slab0 = smem_u32(xa) + (uint32_t)q * SH_SLAB;
     const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + SH_ACOL0 + h2 * 16;
+    const uint32_t ready_a_addr = CG == 2 ? map_to_cta(smem_u32(&ready_a[0]), 0) : smem_u32(&ready_a[0]);
     float chk = 0.f;
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = group; item < n_items; item += n_groups) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
       const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
-      const int col = t.bi * SH_T + q * 32 + lane;
+      const int col = t.bi * BW + (int)rank * SH_T + q * 32 + lane;
       const bool in = col < dim;
       const float c = in ? pivot[(int64_t)t.l * dim + col] : 0.f;
       const float s = in ? scale[(int64_t)t.l * dim + col] : 1.f;
@@ -488,18 +519,20 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         mbar_wait(&empty_a[sa], ((it / S2_AS) & 1) ^ 1);
         tc_fence_after();
         mbar_wait(&full_a[sx], (it / S2_XS) & 1);
+#ifndef OTK_SH_NOCONV
         uint32_t hw[16], lw[16];
         if (valid == SH_BK) split_rows32<true>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
         else split_rows32<false>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
         tmem_st16u(ta0 + sa * 64, hw);
         tmem_st16u(ta0 + sa * 64 + 32, lw);
+#endif
         if ((kt & 3) == 3 || kt == num_k - 1) { colsum += (double)vsum; vsum = 0.f; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_ra[sx]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ready_a[sa]);
+        if (lane == 0) mbar_arrive_cluster(ready_a_addr + sa * 8);
       }
       if (t.bi == t.bj && in && num_k > 0) atomicAdd(&ws_sum[(int64_t)t.l * dim + col], colsum / (double)s);   // each feature once
     }
@@ -509,28 +542,30 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
     const int q = warp % 4, h2 = (warp - 10) / 4;
     const int nloc = q * 32 + lane;
     const uint32_t cc = (uint32_t)lane / 8, within = (uint32_t)(lane % 8) * 4;
-    const uint32_t slab0 = smem_u32(xr) + (uint32_t)q * SH_SLAB;
+    const uint32_t slab0 = smem_u32(xb) + (uint32_t)q * SH_SLAB;
     const uint32_t hb0 = smem_u32(xb) + (uint32_t)nloc * 128;
     const uint32_t sw = (uint32_t)(nloc & 7);
+    const uint32_t ready_b_addr = CG == 2 ? map_to_cta(smem_u32(&ready_b[0]), 0) : smem_u32(&ready_b[0]);
     float chk = 0.f, vsum = 0.f;
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = group; item < n_items; item += n_groups) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
       const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
-      const int col = t.bj * SH_T + nloc;
+      const int col = t.bj * BW + (int)rank * SH_T + nloc;
       const bool in = col < dim;
       const float c = in ? pivot[(int64_t)t.l * dim + col] : 0.f;
       const float s = in ? scale[(int64_t)t.l * dim + col] : 1.f;
       const float ncs = -c * s;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
-        const int sx = it % S2_XS, sp = it % S2_PB;
+        const int sp = it % S2_PB;
         const int valid = min(SH_BK, t.r1 - (t.r0 + kt * SH_BK));
-        mbar_wait(&empty_b[sp], ((it / S2_PB) & 1) ^ 1);
-        tc_fence_after();
-        mbar_wait(&full_b[sx], (it / S2_XS) & 1);
+        mbar_wait(&full_b[sp], (it / S2_PB) & 1);
+#ifndef OTK_SH_NOCONV
         uint32_t hw[16], lw[16];
-        if (valid == SH_BK) split_rows32<true>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
-        else split_rows32<false>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        if (valid == SH_BK) split_rows32<true>(slab0 + sp * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        else split_rows32<false>(slab0 + sp * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        // the planes overwrite the raw tile: every B converter must have read its share first
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint32_t hb = hb0 + sp * SH_BSTAGE;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -538,31 +573,33 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
           sts128u(hb + off, hw[4 * ch], hw[4 * ch + 1], hw[4 * ch + 2], hw[4 * ch + 3]);
           sts128u(hb + SH_BPLANE + off, lw[4 * ch], lw[4 * ch + 1], lw[4 * ch + 2], lw[4 * ch + 3]);
         }
+#endif
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&empty_rb[sx]); mbar_arrive(&ready_b[sp]); }
+        if (lane == 0) mbar_arrive_cluster(ready_b_addr + sp * 8);
       }
     }
     if (!(chk == 0.f) || !(vsum == vsum)) atomicOr(overflow, 1);
   } else if (warp < 22) {
     // ===== epilogue: TMEM accumulator of an item -> its partial-tile slot (thread <-> row of the block) =====
     const int q = warp % 4;
+    const uint32_t acc_empty_addr = CG == 2 ? map_to_cta(smem_u32(&acc_empty[0]), 0) : smem_u32(&acc_empty[0]);
     int n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+    for (int item = group; item < n_items; item += n_groups, ++n) {
       const int a = n % S2_ACC;
       mbar_wait(&acc_full[a], (n / S2_ACC) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * SH_T;
-      float4* out = reinterpret_cast<float4*>(parts + (int64_t)item * S2_TILE + (q * 32 + lane) * SH_T);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BW;
+      float4* out = reinterpret_cast<float4*>(parts + (int64_t)item * (BW * BW) + ((int)rank * SH_T + q * 32 + lane) * BW);
 #pragma unroll 1
-      for (int c0 = 0; c0 < SH_T; c0 += 32) {
+      for (int c0 = 0; c0 < BW; c0 += 32) {
         float v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 == SH_T) {
+        if (c0 + 32 == BW) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[a]);
+          if (lane == 0) mbar_arrive_cluster(acc_empty_addr + a * 8);
         }
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) out[c0 / 4 + j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
@@ -570,8 +607,8 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_cg<CG>(tmem_base, 512); }
 }
 
 // ws_cov[l][gj][gi] (the transposed position the merge kernel reads, gi <= gj) += sum over the segments of the partial
@@ -753,27 +790,30 @@ stats_h_merge_kernel(const float* __restrict__ rec_cov, int parts, const float* 
   }
 }
 
-// wide: block <-> one row of one 128 x 128 unit; 32 float4 columns x 8 segment groups
+// wide: block <-> one row of one BW x BW unit (BW = 128: single-CTA kernel, 256: CTA-pair kernel); BW / 4 float4 columns x
+// 1024 / BW segment groups, then one thread per column finalises
+template <int BW>
 __global__ void __launch_bounds__(256)
 stats_h2_merge_kernel(const float* __restrict__ parts, int n_seg, int n_units, int upl, int nB,
                       const float* __restrict__ scale, const float* __restrict__ pivot, const int* __restrict__ flag,
                       const double* __restrict__ ws_cov, const double* __restrict__ ws_sum, int dim, double rows,
                       StatsRunning run) {
-  __shared__ double red[8][32][4];
-  const int u = blockIdx.x / SH_T, r = blockIdx.x % SH_T;
+  constexpr int C4 = BW / 4, G = 256 / C4;
+  __shared__ double red[G][C4][4];
+  const int u = blockIdx.x / BW, r = blockIdx.x % BW;
   const int64_t l = u / upl;
   int w = u % upl, bi = 0;
   while (w >= nB - bi) { w -= nB - bi; ++bi; }
   const int bj = bi + w;
-  const int c4 = threadIdx.x % 32, g = threadIdx.x / 32;
-  const int gi = bi * SH_T + r, gj0 = bj * SH_T + c4 * 4;
+  const int c4 = threadIdx.x % C4, g = threadIdx.x / C4;
+  const int gi = bi * BW + r, gj0 = bj * BW + c4 * 4;
   const bool fallback = *flag != 0;
   const bool live = gi < dim && gj0 < dim && gi <= gj0 + 3;            // dim % 4 == 0: a group is inside or outside
   double a[4] = {0.0, 0.0, 0.0, 0.0};
   if (live && !fallback) {
-    const float4* p = reinterpret_cast<const float4*>(parts + (int64_t)u * S2_TILE + r * SH_T + c4 * 4);
-    const int64_t stride = (int64_t)n_units * S2_TILE / 4;
-    for (int sg = g; sg < n_seg; sg += 8) {
+    const float4* p = reinterpret_cast<const float4*>(parts + (int64_t)u * (BW * BW) + r * BW + c4 * 4);
+    const int64_t stride = (int64_t)n_units * (BW * BW) / 4;
+    for (int sg = g; sg < n_seg; sg += G) {
       const float4 v = p[(int64_t)sg * stride];
       a[0] += (double)v.x; a[1] += (double)v.y; a[2] += (double)v.z; a[3] += (double)v.w;
     }
@@ -781,9 +821,9 @@ stats_h2_merge_kernel(const float* __restrict__ parts, int n_seg, int n_units, i
 #pragma unroll
   for (int k = 0; k < 4; ++k) red[g][c4][k] = a[k];
   __syncthreads();
-  // finalise with one thread per column (128 threads: the read-modify-write latencies of the running buffers overlap)
-  if (threadIdx.x < SH_T) {
-    const int c = threadIdx.x, gj = bj * SH_T + c;
+  // finalise with one thread per column (the read-modify-write latencies of the running buffers overlap)
+  if (threadIdx.x < BW) {
+    const int c = threadIdx.x, gj = bj * BW + c;
     if (gi < dim && gj < dim && gi <= gj) {
       double pp;
       if (fallback) {
@@ -791,7 +831,7 @@ stats_h2_merge_kernel(const float* __restrict__ parts, int n_seg, int n_units, i
       } else {
         pp = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) pp += red[q][c / 4][c % 4];
+        for (int q = 0; q < G; ++q) pp += red[q][c / 4][c % 4];
         pp *= 1.0 / ((double)scale[l * dim + gi] * (double)scale[l * dim + gj]);
       }
       hm_store(run, l, dim, gi, gj, pp, rows, pivot, ws_sum);
@@ -809,10 +849,14 @@ int stats_h_merge(const StatsHPlan& plan, const float* pivot, const double* ws_c
     const int64_t tri = dim * (dim + 1) / 2, blocks = L * ceil_div(tri, HM_OUT);
     stats_h_merge_kernel<<<(unsigned)blocks, HM_OUT * HM_GROUPS, 0, st>>>(plan.parts, plan.n_parts, plan.scale, pivot, plan.flag,
                                                                         ws_cov, ws_sum, (int)dim, (double)rows, run);
-  } else {
-    stats_h2_merge_kernel<<<(unsigned)(plan.n_units * SH_T), 256, 0, st>>>(plan.parts, plan.n_parts, plan.n_units, plan.upl,
-                                                                          plan.nB, plan.scale, pivot, plan.flag, ws_cov,
-                                                                          ws_sum, (int)dim, (double)rows, run);
+  } else if (plan.mode == 2) {
+    stats_h2_merge_kernel<128><<<(unsigned)(plan.n_units * 128), 256, 0, st>>>(plan.parts, plan.n_parts, plan.n_units, plan.upl,
+                                                                              plan.nB, plan.scale, pivot, plan.flag, ws_cov,
+                                                                              ws_sum, (int)dim, (double)rows, run);
+  } else {   // mode 3: 256 x 256 units of the CTA-pair kernel
+    stats_h2_merge_kernel<256><<<(unsigned)(plan.n_units * 256), 256, 0, st>>>(plan.parts, plan.n_parts, plan.n_units, plan.upl,
+                                                                              plan.nB, plan.scale, pivot, plan.flag, ws_cov,
+                                                                              ws_sum, (int)dim, (double)rows, run);
   }
   OTK_LAUNCH_CHECK();
   return OTK_OK;
@@ -892,10 +936,54 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OTK_CUDA(cudaFuncSetAttribute(stats_h2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+    OTK_CUDA(cudaFuncSetAttribute(stats_h2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
     attr_set[dev] = true;
   }
   const int64_t sms = sm_count();
+  // CTA-pair kernel (dim >= 512): 256 x 256 units, one super-chunk only (a pair item takes four 128 x 128 slots)
+  {
+    const int64_t nB2 = ceil_div(dim, 2 * SH_T), upl2 = nB2 * (nB2 + 1) / 2, n_units2 = L * upl2, pairs = sms / 2;
+    const int64_t max_seg2 = (S2_MAX_ITEMS / 4) / (n_units2 > 0 ? n_units2 : 1);
+    static const bool pair_ok = [] { const char* e = getenv("OTK_STATS_H2_PAIR"); return !(e && e[0] == '0'); }();   // tuning aid
+    if (dim >= 512 && pair_ok && pairs >= 1 && max_seg2 >= 1 && rows <= max_seg2 * 2048) {
+      static bool attr2_set[64] = {false};
+      if (dev >= 0 && dev < 64 && !attr2_set[dev]) {
+        OTK_CUDA(cudaFuncSetAttribute(stats_h2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+        attr2_set[dev] = true;
+      }
+      int64_t seg_len = 0;
+      for (int64_t k = 1;; ++k) {
+        int64_t sgs = pairs * k / n_units2;
+        if (sgs < 1) continue;
+        if (sgs > max_seg2) sgs = max_seg2;
+        seg_len = ceil_div(ceil_div(rows, sgs), SH_BK) * SH_BK;
+        if (seg_len < 256) seg_len = 256;
+        if (seg_len <= 2048 || sgs == max_seg2) break;
+      }
+      if (seg_len > 2048) seg_len = 2048;
+      const int64_t n_seg = ceil_div(rows, seg_len), n_items = n_units2 * n_seg;
+      if (n_seg <= max_seg2) {
+        const unsigned groups = (unsigned)(n_items < pairs ? n_items : pairs);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(groups * 2);
+        cfg.blockDim = dim3(S2_THREADS);
+        cfg.dynamicSmemBytes = S2_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        OTK_CUDA(cudaLaunchKernelEx(&cfg, stats_h2_kernel<2>, mX, (const float*)pivot, (const float*)scale, (int)dim, (int)nB2,
+                                    (int)upl2, (int)n_units2, (int)n_items, (int)seg_len, 0, (int)rows, parts, ws_sum, flag));
+        count_launch(1);
+        *plan = StatsHPlan{3, parts, (int)n_seg, (int)n_units2, (int)upl2, (int)nB2, scale, flag};
+        return 1;
+      }
+    }
+  }
   const int64_t max_seg = S2_MAX_ITEMS / n_units;                       // segments per launch (>= 1 by eligibility)
   // One super-chunk (the streaming case: max_seg * 2048 rows = 209 k rows at d = 512): the partial tiles are merged
   // straight into the running buffers by stats_h2_merge_kernel.  Longer calls reduce every super-chunk into the fp64
@@ -920,7 +1008,7 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
     const int64_t row_hi = row_lo + n_seg * seg_len < rows ? row_lo + n_seg * seg_len : rows;
     const int64_t n_items = n_units * n_seg;
     const unsigned grid = (unsigned)(n_items < sms ? n_items : sms);
-    stats_h2_kernel<<<grid, S2_THREADS, S2_SMEM, st>>>(mX, pivot, scale, (int)dim, (int)nB, (int)upl, (int)n_units, (int)n_items,
+    stats_h2_kernel<1><<<grid, S2_THREADS, S2_SMEM, st>>>(mX, pivot, scale, (int)dim, (int)nB, (int)upl, (int)n_units, (int)n_items,
                                                       (int)seg_len, (int)row_lo, (int)row_hi, parts, ws_sum, flag);
     OTK_LAUNCH_CHECK();
     if (single) {
