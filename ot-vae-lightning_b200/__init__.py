@@ -20,8 +20,10 @@ def install_as_reference(name: str = "ot_vae_lightning") -> None:
         root.__path__ = []
         sys.modules[name] = root
     for sub in ("utils", "ot", "ot.matrix_utils", "ot.w2_utils", "ot.distribution_models", "ot.distribution_models.base",
-                "ot.distribution_models.gaussian_model", "ot.distribution_models.codebook_model", "ot.transport",
+                "ot.distribution_models.gaussian_model", "ot.distribution_models.codebook_model",
+                "ot.distribution_models.gassian_mixture_model", "ot.transport",
                 "ot.transport.base", "ot.transport.gaussian_transport", "ot.transport.discrete_transport",
+                "ot.transport.gmm_transport",
                 "metrics", "metrics.fid"):
         mod = importlib.import_module(f"{__name__}.{sub}")
         sys.modules[f"{name}.{sub}"] = mod

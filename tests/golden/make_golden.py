@@ -154,12 +154,67 @@ def case_sinkhorn():
     np.savez(os.path.join(HERE, "energy.npz"), pts=npy(pts), codebook=npy(cb.codebook), energy=npy(cb.energy(pts)))
 
 
+def gmm_clouds(g, n, d, centres, spread):
+    """n points around len(centres) well separated centres (so that hard assignments do not depend on round-off)"""
+    k = len(centres)
+    which = torch.arange(n) % k
+    mix = torch.randn(k, d, d, generator=g, dtype=torch.double) * spread / np.sqrt(d)
+    z = torch.randn(n, d, generator=g, dtype=torch.double)
+    pts = torch.einsum("nij,nj->ni", mix[which], z) + torch.tensor(centres, dtype=torch.double)[which]
+    return pts[torch.randperm(n, generator=g)].float()
+
+
+def run_gmm(src, tgt, probe, d, ks, kt, batch, diag, transport_type):
+    from ot_vae_lightning.ot.transport.gmm_transport import GMMTransport
+    op = GMMTransport(d, transport_type=transport_type,
+                      transport_cfg=dict(diag=diag, stochastic=False, make_pd=True, dtype=torch.double),
+                      source_cfg=dict(mixture_cfg=dict(n_components=ks), dtype=torch.double),
+                      target_cfg=dict(mixture_cfg=dict(n_components=kt), dtype=torch.double))
+    # the models draw their initial means with the global generator on their first update: one seed per model
+    torch.manual_seed(11)
+    for lo in range(0, src.shape[0], batch):
+        op.update(source_samples=src[lo:lo + batch])
+    torch.manual_seed(12)
+    for lo in range(0, tgt.shape[0], batch):
+        op.update(target_samples=tgt[lo:lo + batch])
+    cost = op.compute()
+    torch.manual_seed(13)
+    moved = op.transport(probe)
+    out = dict(cost=npy(cost), coupling=npy(op.transport_matrix), moved=npy(moved))
+    for tag, m in (("s", op.source_model), ("t", op.target_model)):
+        out.update({f"n_{tag}": npy(m._n_obs), f"sum_{tag}": npy(m._running_sum), f"sumcov_{tag}": npy(m._running_sum_cov),
+                    f"mean_{tag}": npy(m.mean), f"var_{tag}": npy(m.variances), f"w_{tag}": npy(m.weights)})
+    out["energy_s"] = npy(op.source_model.energy(probe.double()))
+    return out
+
+
+def case_gmm():
+    """GaussianMixtureModel + GMMTransport on separated clusters, full and diagonal covariances."""
+    g = torch.Generator().manual_seed(505)
+    d = 6
+    cs = [[6.0 * (i == j) - 3.0 * (i == (j + 1) % 3) for j in range(d)] for i in range(3)]
+    ct = [[-5.0 if j % 2 == i else 4.0 for j in range(d)] for i in range(2)]
+    src, tgt = gmm_clouds(g, 600, d, cs, 0.8), gmm_clouds(g, 500, d, ct, 0.5)
+    probe = src[:40].clone()
+    out = run_gmm(src, tgt, probe, d, 3, 2, 150, diag=False, transport_type="argmax")
+    np.savez(os.path.join(HERE, "gmm_full_argmax.npz"), src=npy(src), tgt=npy(tgt), probe=npy(probe), batch=150, **out)
+    # ('barycenter' cannot be pinned: the reference feeds `assignments @ coupling` - rows summing to the source weight,
+    # not to 1 - to gaussian_barycenter, whose validation raises "`weights` is expected to be a valid probability
+    # vector" (gmm_transport.py:106-111 -> w2_utils.py:648; probed here))
+    out = run_gmm(src, tgt, probe, d, 3, 2, 200, diag=True, transport_type="argmax")
+    np.savez(os.path.join(HERE, "gmm_diag_argmax.npz"), src=npy(src), tgt=npy(tgt), probe=npy(probe), batch=200, **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gmm":      # only the fixtures added later (the others stay byte-identical)
+        case_gmm()
+        sys.exit(0)
     case_matrix()
     case_gaussian()
     case_w2_functions()
     case_sinkhorn()
+    case_gmm()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

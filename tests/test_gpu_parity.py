@@ -450,3 +450,59 @@ def test_prepared_transport_matches_functional_path_and_tracks_operator_changes(
     op.compute()
     want2 = (src[:777].double() - op.source_model.mean) @ op.transport_operator.T + op.target_model.mean
     assert rel(op.transport(src[:777]), want2.cpu().numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------- GMM
+
+def _gmm_on_gpu(api, g, diag, n_rep=1):
+    d, bs = int(g["src"].shape[1]), int(g["batch"])
+    cfg = dict(dtype=torch.double, device="cuda")
+    op = api.GMMTransport(d, transport_type="argmax",
+                          transport_cfg=dict(diag=diag, stochastic=False, make_pd=True, dtype=torch.double),
+                          source_cfg=dict(mixture_cfg=dict(n_components=int(g["n_s"].shape[0])), **cfg),
+                          target_cfg=dict(mixture_cfg=dict(n_components=int(g["n_t"].shape[0])), **cfg)).cuda()
+    src, tgt = T(g["src"]), T(g["tgt"])
+    torch.manual_seed(11)                       # the seeds of tests/golden/make_golden.py::run_gmm (host-side randperm)
+    for lo in range(0, src.shape[0], bs):
+        op.update(source_samples=src[lo:lo + bs])
+    torch.manual_seed(12)
+    for lo in range(0, tgt.shape[0], bs):
+        op.update(target_samples=tgt[lo:lo + bs])
+    return op
+
+
+@pytest.mark.parametrize("name,diag", [("gmm_full_argmax", False), ("gmm_diag_argmax", True)])
+def test_golden_gmm_transport(api, golden, name, diag):
+    """GaussianMixtureModel streaming fit (per-component weighted SYRK through otk_stats_update), component OT through
+    the Sinkhorn kernel and the per-pair Gaussian maps, against the unmodified reference's outputs."""
+    g = golden(name)
+    op = _gmm_on_gpu(api, g, diag)
+    cost = op.compute()
+    moved = op.transport(T(g["probe"]))
+    for tag, m in (("s", op.source_model), ("t", op.target_model)):
+        assert np.allclose(m._n_obs.cpu().numpy(), g[f"n_{tag}"])                      # same hard assignments
+        assert rel(m._running_sum, g[f"sum_{tag}"]) < TOL_STATS
+        assert rel(m._running_sum_cov, g[f"sumcov_{tag}"]) < TOL_STATS
+        assert rel(m.mean, g[f"mean_{tag}"]) < TOL_STATS and rel(m.variances, g[f"var_{tag}"]) < TOL_STATS
+        assert rel(m.weights, g[f"w_{tag}"]) < 1e-6
+    assert rel(cost, g["cost"]) < TOL_MATFUN
+    assert np.abs(op.transport_matrix.cpu().numpy() - g["coupling"]).max() < TOL_SINKHORN
+    assert rel(op.source_model.energy(T(g["probe"]).double()), g["energy_s"]) < TOL_MATFUN
+    assert moved.dtype == torch.float32 and moved.is_cuda and rel(moved, g["moved"]) < TOL_MATFUN
+
+
+def test_gmm_weighted_syrk_soft_assignments_vs_dense(api):
+    """soft ('mean' mode) assignments: sum_b w_bk x_b x_b^T from the kernel path == the reference's dense expression
+    (gassian_mixture_model.py:109-115) on a size the dense form can still hold (B x d^2 = 2000 x 48^2)."""
+    torch.manual_seed(5)
+    d, k, b = 48, 5, 2000
+    m = api.GaussianMixtureModel(d, mixture_cfg=dict(n_components=k, inference_mode="mean"), dtype=torch.double,
+                                 device="cuda").cuda().eval()
+    x = torch.randn(b, d, device="cuda", dtype=torch.double) * 0.7 + torch.randn(1, d, device="cuda", dtype=torch.double)
+    with torch.no_grad():
+        m.mean.copy_(x[:k] * 0.5)
+    n, s, ss = m.kmean_iteration(x)
+    w, _, _ = m.assign(x)
+    dense = (w.transpose(-1, -2) @ (x.unsqueeze(-1) @ x.unsqueeze(-2)).flatten(-2)).unflatten(-1, (d, d))
+    assert rel(n, w.sum(-2).cpu()) < 1e-12 and rel(s, (w.transpose(-1, -2) @ x).cpu()) < 1e-12
+    assert rel(ss, dense.cpu()) < TOL_STATS

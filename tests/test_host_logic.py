@@ -149,3 +149,47 @@ def test_install_as_reference_aliases():
         for k in [k for k in sys.modules if k == "ot_vae_lightning" or k.startswith("ot_vae_lightning.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+# ------------------------------------------------------------------------------------------------- GMM
+
+def run_gmm_case(api, g, diag, device="cpu", rtol=1e-7):
+    d, bs = int(g["src"].shape[1]), int(g["batch"])
+    cfg = dict(dtype=torch.double, device=device)
+    op = api.GMMTransport(d, transport_type="argmax",
+                          transport_cfg=dict(diag=diag, stochastic=False, make_pd=True, dtype=torch.double),
+                          source_cfg=dict(mixture_cfg=dict(n_components=int(g["n_s"].shape[0])), **cfg),
+                          target_cfg=dict(mixture_cfg=dict(n_components=int(g["n_t"].shape[0])), **cfg))
+    src, tgt, probe = (T(g[k]).to(device) for k in ("src", "tgt", "probe"))
+    torch.manual_seed(11)                       # same seeds as tests/golden/make_golden.py::run_gmm
+    for lo in range(0, src.shape[0], bs):
+        op.update(source_samples=src[lo:lo + bs])
+    torch.manual_seed(12)
+    for lo in range(0, tgt.shape[0], bs):
+        op.update(target_samples=tgt[lo:lo + bs])
+    cost = op.compute()
+    torch.manual_seed(13)
+    moved = op.transport(probe)
+    for tag, m in (("s", op.source_model), ("t", op.target_model)):
+        close(m._n_obs.cpu(), g[f"n_{tag}"], rtol=rtol)
+        close(m._running_sum.cpu(), g[f"sum_{tag}"], rtol=rtol, atol=1e-6)
+        close(m._running_sum_cov.cpu(), g[f"sumcov_{tag}"], rtol=max(rtol, 1e-6), atol=1e-3)
+        close(m.mean.cpu(), g[f"mean_{tag}"], rtol=max(rtol, 1e-6), atol=1e-6)
+        close(m.variances.cpu(), g[f"var_{tag}"], rtol=1e-4, atol=1e-5)
+        close(m.weights.cpu(), g[f"w_{tag}"], rtol=rtol)
+    return op, cost, moved
+
+
+@pytest.mark.parametrize("name,diag", [("gmm_full_argmax", False), ("gmm_diag_argmax", True)])
+def test_gmm_transport_against_reference_golden(api, golden, name, diag):
+    g = golden(name)
+    op, cost, moved = run_gmm_case(api, g, diag)
+    close(cost, g["cost"], rtol=1e-6)
+    close(op.transport_matrix, g["coupling"], rtol=1e-5, atol=1e-9)
+    close(op.source_model.energy(T(g["probe"]).double()), g["energy_s"], rtol=1e-6, atol=1e-6)
+    assert moved.dtype == torch.float32 and torch.allclose(moved, T(g["moved"]), rtol=1e-4, atol=1e-4)
+    keys = set(op.source_model.state_dict())
+    assert {"mean", "_running_sum", "_running_sum_cov", "_n_obs", "weight_init", "parametrizations.cov.original",
+            "parametrizations._weights.original"} <= keys
+    op.reset()
+    assert op.transport_matrix is None and float(op.source_model._n_obs.sum()) == 0
