@@ -27,14 +27,31 @@ def _lead(shape, tail: int) -> Tuple[torch.Size, int]:
     return lead, int(lead.numel())
 
 
+def _strided_latents(x: Tensor, dev: torch.device, lead: torch.Size, d: int) -> Tuple[Tensor, int, int]:
+    """Latents [*lead, B, d] for the statistics kernel, WITHOUT a copy when they already are fp32 on `dev` with a unit
+    feature stride, 16-byte aligned row / leading strides and leading dims that collapse into one (the strided views
+    `utils.permute_and_flatten` hands over).  Returns (tensor, row_stride, batch_stride) in elements."""
+    if x.dtype == torch.float32 and x.device == dev and not x.requires_grad and x.dim() >= 2 \
+            and tuple(x.shape[:-2]) == tuple(lead) and x.shape[-1] == d and x.stride(-1) == 1 and x.shape[-2] > 0:
+        try:
+            v = x.view(-1, x.shape[-2], d) if x.dim() != 3 else x          # raises if the leading dims do not collapse
+        except RuntimeError:
+            v = None
+        if v is not None and v.data_ptr() % 16 == 0 and v.stride(1) % 4 == 0 and v.stride(1) >= d \
+                and (v.shape[0] == 1 or (v.stride(0) % 4 == 0 and v.stride(0) > 0)):
+            return v, int(v.stride(1)), int(v.stride(0)) if v.shape[0] > 1 else int(v.shape[1] * v.stride(1))
+    x = _dev_tensor(x, dev, torch.float32)
+    if x.shape[:-2] != lead:
+        x = x.expand(*lead, *x.shape[-2:]).contiguous()
+    return x, d, x.shape[-2] * d
+
+
 def stats_update(x: Tensor, n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, decay: Optional[float]) -> None:
     """In-place update of the running buffers (all on one CUDA device) with latents x [*L, B, d] (fp32)."""
     dev = run_sum.device
     d = run_sum.shape[-1]
     lead, L = _lead(run_sum.shape, 1)
-    x = _dev_tensor(x, dev, torch.float32)
-    if x.shape[:-2] != lead:
-        x = x.expand(*lead, *x.shape[-2:]).contiguous()
+    x, row_stride, batch_stride = _strided_latents(x, dev, lead, d)
     rows = x.shape[-2]
     lib = N.load()
     for buf in (n_obs, run_sum, run_cov):
@@ -42,7 +59,8 @@ def stats_update(x: Tensor, n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, dec
             raise ValueError("running buffers must be contiguous CUDA tensors")
     with N.on_device(dev) as ctx:
         ws = ctx.workspace(lib.otk_stats_update_workspace_bytes(L, rows, d))
-        st = lib.otk_stats_update(x.data_ptr(), L, rows, d, d, rows * d, -1.0 if decay is None else float(decay),
+        st = lib.otk_stats_update(x.data_ptr(), L, rows, d, row_stride, batch_stride,
+                                  -1.0 if decay is None else float(decay),
                                   n_obs.data_ptr(), N.dtype_code(n_obs.dtype), run_sum.data_ptr(), run_cov.data_ptr(),
                                   N.dtype_code(run_sum.dtype), ws.data_ptr(), ws.numel(), ctx.stream)
     if st != N.OK:

@@ -99,7 +99,13 @@ def unsqueeze_like(tensor: Tensor, like: Tensor) -> Tensor:
 def permute_and_flatten(x: Tensor, permute_dims: Sequence[int], batch_first: bool = True,
                         flatten_batch: bool = False) -> Tensor:
     """Layout the caller (`LatentTransport`, reference ot/transport_callback.py:36-43) feeds the operators with:
-    the `permute_dims` are moved last and flattened into the feature axis (reference utils/__init__.py:233-267)."""
+    the `permute_dims` are moved last and flattened into the feature axis (reference utils/__init__.py:233-267).
+
+    The reference materialises the permuted tensor (`.contiguous()`, :260-261) before every update.  Here the result is
+    a strided VIEW whenever the flattening allows one (e.g. ViT tokens [B, T, D] with per-token operators ->
+    [T, B, D] with strides (D, T D, 1)): the statistics kernel reads such a layout in place through its TMA descriptor
+    (`otk_stats_update` takes row and batch strides), which saves one read and one write of the latents per update.
+    Layouts that admit no view are copied exactly as in the reference."""
     others = set(range(1, x.dim()))
     if not others:
         raise ValueError("`input` is expected to have at least 2 dimensions")
@@ -111,7 +117,7 @@ def permute_and_flatten(x: Tensor, permute_dims: Sequence[int], batch_first: boo
     if not rest:
         return x.flatten(int(not flatten_batch))
     order = (0, *rest, *permute_dims) if batch_first else (*rest, 0, *permute_dims)
-    y = x.permute(*order).contiguous()
+    y = x.permute(*order)                         # flatten() = reshape(): a view if the strides allow it, else one copy
     y = y.flatten(int(batch_first and not flatten_batch), len(rest) - int(not batch_first and not flatten_batch))
     return y.flatten(-len(permute_dims))
 

@@ -506,3 +506,35 @@ def test_gmm_weighted_syrk_soft_assignments_vs_dense(api):
     dense = (w.transpose(-1, -2) @ (x.unsqueeze(-1) @ x.unsqueeze(-2)).flatten(-2)).unflatten(-1, (d, d))
     assert rel(n, w.sum(-2).cpu()) < 1e-12 and rel(s, (w.transpose(-1, -2) @ x).cpu()) < 1e-12
     assert rel(ss, dense.cpu()) < TOL_STATS
+
+
+# ------------------------------------------------------------------------------- caller-side layout
+
+def test_strided_token_latents_are_read_in_place(api):
+    """ViT tokens [B, T, D] with one operator per token (`permute_and_flatten(batch_first=False)`,
+    transport_callback.py:36-43): the view [T, B, D] with strides (D, T D, 1) goes to the kernel without the
+    reference's `.contiguous()` copy and gives the same statistics as the copied layout."""
+    from ot_vae_lightning_b200 import kernels as K
+    from ot_vae_lightning_b200.utils import permute_and_flatten, unflatten_and_unpermute
+    torch.manual_seed(3)
+    for B, Tk, D in [(700, 5, 128), (300, 3, 512), (180, 4, 96), (64, 2, 40)]:
+        lat = torch.randn(B, Tk, D, device="cuda") * 0.8 + torch.randn(1, Tk, D, device="cuda")
+        view = permute_and_flatten(lat, (2,), batch_first=False)
+        assert view.shape == (Tk, B, D) and view.data_ptr() == lat.data_ptr() and not view.is_contiguous()
+        back = unflatten_and_unpermute(view, lat.shape, (2,), batch_first=False)
+        assert torch.equal(back, lat)
+        out = []
+        for x in (view, view.contiguous()):
+            n = torch.zeros(Tk, dtype=torch.float64, device="cuda")
+            s = torch.zeros(Tk, D, dtype=torch.float64, device="cuda")
+            ss = torch.zeros(Tk, D, D, dtype=torch.float64, device="cuda")
+            K.stats_update(x, n, s, ss, None)
+            K.stats_update(x[:, :37], n, s, ss, None)                     # ragged tail batch, still a strided view
+            out.append((n, s, ss))
+        x64 = torch.cat([view, view[:, :37]], dim=1).double()
+        assert torch.equal(out[0][0], out[1][0]) and float(out[0][0][0]) == B + 37
+        assert rel(out[0][1], x64.sum(1).cpu()) < 1e-6 and rel(out[0][2], (x64.transpose(1, 2) @ x64).cpu()) < TOL_STATS
+        assert rel(out[0][2], out[1][2].cpu()) < 1e-6
+    # the flatten-everything case needs no copy either (MNIST32 CNN latents [B, 128, 1, 1] -> [B, 128])
+    lat = torch.randn(250, 128, 1, 1, device="cuda")
+    assert permute_and_flatten(lat, (1, 2, 3)).data_ptr() == lat.data_ptr()
