@@ -29,9 +29,9 @@ import torch.distributed as dist  # noqa: E402
 D_LAT, N_LAT, CHUNK = 512, 1 << 20, 1 << 16
 SK_N, SK_D, SK_EPS = 65536, 128, 0.05
 METRIC, UNIT = "cov+W2-map latents/s", "latents/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one stats_h2_kernel launch on a 65536 x 512 chunk
-# (ncu --set full, profiles/prof_stats_r03.md): 134.28 MB + 13.85 MB (partial tiles); the algorithmic figure is 134.2 MB
-STATS_TRAFFIC_BYTES_PER_LAUNCH = 148.1e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one stats_h2_kernel<2> launch on a 65536 x 512 chunk
+# (ncu --set full, profiles/prof_stats_r04.md): 135.03 MB + 16.20 MB (partial tiles); the algorithmic figure is 134.2 MB
+STATS_TRAFFIC_BYTES_PER_LAUNCH = 151.2e6
 
 
 def load_peaks():
@@ -246,7 +246,8 @@ def main():
     # of the SAME two distributions (the ranks differ in the draws, as the shards of one validation set would)
     src = gaussian_latents(N_LAT, D_LAT, seed=1234, device=dev, sample_seed=9001 + rank)
     tgt = gaussian_latents(N_LAT, D_LAT, seed=4321, device=dev, shift=0.5, scale=1.5, sample_seed=7001 + rank)
-    out = torch.empty_like(src)
+    n_chunks_all = N_LAT // CHUNK
+    outs = [None] * n_chunks_all       # transport() returns a fresh tensor per chunk (reference semantics); all are kept
     cfg = dict(dtype=torch.double, device=dev, reduce_on_update=False)
     op = GaussianTransport(D_LAT, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).to(dev)
 
@@ -255,8 +256,8 @@ def main():
         for lo in range(0, N_LAT, CHUNK):
             op.update(source_samples=src[lo:lo + CHUNK], target_samples=tgt[lo:lo + CHUNK])
         w2 = op.compute()              # one packed all-reduce of the statistics inside fit() when world > 1
-        for lo in range(0, N_LAT, CHUNK):
-            out[lo:lo + CHUNK] = op.transport(src[lo:lo + CHUNK])
+        for i, lo in enumerate(range(0, N_LAT, CHUNK)):
+            outs[i] = op.transport(src[lo:lo + CHUNK])
         return w2
 
     def timed(fn, steps):
@@ -295,8 +296,8 @@ def main():
             op.source_model.update(src[lo:lo + CHUNK])
 
     def apply_only():
-        for lo in range(0, N_LAT, CHUNK):
-            out[lo:lo + CHUNK] = op.transport(src[lo:lo + CHUNK])
+        for i, lo in enumerate(range(0, N_LAT, CHUNK)):
+            outs[i] = op.transport(src[lo:lo + CHUNK])
 
     stats_only()
     stats_ms, _ = timed(stats_only, 3)
@@ -308,12 +309,13 @@ def main():
     stats_tflops = flops / (stats_ms / 3 * 1e-3) / 1e12
     apply_tflops = flops / (apply_ms / 3 * 1e-3) / 1e12
     n_chunks = N_LAT // CHUNK
-    # executed MMA flops of the statistics kernel: 3 FP16 MMAs per product (hi/lo split) on the 128x128 blocks of the
-    # upper block triangle (10 of 16 at d = 512); the kernel's tensor peak is the 16-bit dense one
-    nb = -(-D_LAT // 128)
+    # executed MMA flops of the statistics kernel: 3 FP16 MMAs per product (hi/lo split) on the 256x256 blocks (CTA-pair
+    # kernel) of the upper block triangle (3 of 4 at d = 512); the kernel's tensor peak is the 16-bit dense one
+    nb = -(-D_LAT // 256)
     tri = (nb * (nb + 1) / 2) / (nb * nb)
     f16_peak = peaks["bf16_sustained"]
-    roofline = dict(kernel="stats_h2_kernel (K1: sum x x^T, sum x, n), one launch per 65536 x 512 fp32 chunk",
+    roofline = dict(kernel="stats_h2_kernel<2> (K1: sum x x^T, sum x, n; CTA pairs, cta_group::2), one launch per 65536 x 512 "
+                           "fp32 chunk",
                     bound="tensor", achieved=stats_tflops, peak=f16_peak, unit="TFLOP/s", frac=stats_tflops / f16_peak,
                     traffic=STATS_TRAFFIC_BYTES_PER_LAUNCH,
                     algorithmic=dict(flops_per_launch=2.0 * CHUNK * D_LAT * D_LAT, bytes_per_launch=CHUNK * D_LAT * 4,
@@ -321,12 +323,12 @@ def main():
                     executed=dict(tflops=3.0 * tri * stats_tflops, frac=3.0 * tri * stats_tflops / f16_peak,
                                   note="3 FP16 MMAs per fp32-accurate product, upper block triangle only: the ceiling of "
                                        f"`frac` for this scheme is 1/(3*{tri:.3f}) = {1 / (3 * tri):.2f}"),
-                    note=f"achieved = algorithmic flops 2*N*d^2 / CUDA-event time of the update calls (kernel + its small "
-                         f"helper kernels: pivot/scale, partial-tile reduction, merge); peak = measured 16-bit dense "
-                         f"bf16_tflops_sustained ({peaks['source']}) - the kernel issues kind::f16 MMAs; the kernel is bound by "
-                         f"raw-tile delivery (in-flight bytes / L2 latency), not by the tensor pipe (ncu: 35 % of FP16 peak); "
-                         f"traffic = dram read+write bytes per launch from profiles/prof_stats_r03.md "
-                         f"(algorithmic: {CHUNK * D_LAT * 4})",
+                    note=f"achieved = algorithmic flops 2*N*d^2 / CUDA-event time of the update calls (kernel 73 us + its "
+                         f"helper kernels: pivot/scale 4, partial-tile merge 13, gated fallback 6 us); peak = measured "
+                         f"16-bit dense bf16_tflops_sustained ({peaks['source']}) - the kernel issues kind::f16 MMAs; ncu "
+                         f"(profiles/prof_stats_r04.md): FP16 tensor ops 53 % of the nominal peak at the 1.64 GHz the "
+                         f"kernel runs at, i.e. 76 % of the measured sustained peak in executed flops; traffic = dram "
+                         f"read+write bytes per launch from the same capture (algorithmic: {CHUNK * D_LAT * 4})",
                     others=dict(apply_transport_tflops=apply_tflops, apply_frac=apply_tflops / f16_peak,
                                 apply_executed_frac=3.0 * apply_tflops / f16_peak,
                                 compute_map_ms=compute_ms / 3, stats_ms=stats_ms / 3, apply_ms=apply_ms / 3,
@@ -358,9 +360,10 @@ def main():
                     stats=dict(ms=s_ms, gbs=N_LAT * 128 * 4 / (s_ms * 1e-3) / 1e9, hbm_frac=N_LAT * 128 * 4 / (s_ms * 1e-3) / 1e9 / peaks["hbm"],
                                executed_tflops=3 * f128 / (s_ms * 1e-3) / 1e12,
                                executed_tensor_frac=3 * f128 / (s_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
-                               note="one update() call (pivot/scale + FP16 hi/lo split kernel stats_h_kernel + merge); HBM-bound: one "
-                                    "read of X needs 82 us; executed flops are FP16 MMAs (3 per product) against the measured "
-                                    "16-bit dense peak"),
+                               note="one update() call (pivot/scale + FP16 hi/lo split kernel stats_h_kernel + gated fallback + "
+                                    "record merge); HBM-bound: one read of X needs 82 us, the kernel alone takes 105 us "
+                                    "(ncu, profiles/prof_stats_r04.md: 536.9 MB DRAM read = the algorithmic bytes); executed "
+                                    "flops are FP16 MMAs (3 per product) against the measured 16-bit dense peak"),
                     apply=dict(ms=a_ms, gbs=2 * N_LAT * 128 * 4 / (a_ms * 1e-3) / 1e9,
                                hbm_frac=2 * N_LAT * 128 * 4 / (a_ms * 1e-3) / 1e9 / peaks["hbm"],
                                note="one transport() call; HBM-bound (read X, write Y)"))
@@ -397,7 +400,8 @@ def main():
     sinkhorn = None
     if not args.skip_sinkhorn:
         try:
-            del src, tgt, out
+            del src, tgt
+            outs.clear()
             torch.cuda.empty_cache()
             x, y = point_clouds(SK_N, SK_N, SK_D, seed=99, device=dev)
             lo, hi = parallel.shard_rows(SK_N, rank, world)
