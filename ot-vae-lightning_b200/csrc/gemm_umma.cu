@@ -16,9 +16,17 @@
 //   * a launch can be made conditional on a device-side iteration limit (`ctrl[0]`), so the host enqueues iterations
 //     without synchronising and the ones past convergence retire immediately.
 //
+// Split-K over a thread-block cluster (KS = 2 or 4 CTAs along K): a d x d product streams (128 + BN) x K x 8 bytes of
+// operand planes through ONE SM's L2 port per CTA - 768 KB at 512^3, i.e. ~12 of the 17 us such a launch took - while
+// three quarters of the SMs idle.  With KS CTAs per output tile each streams 1/KS of K; the non-leaders park their fp32
+// accumulator in their own (by then idle) pipeline shared memory and the leader adds it to its registers through
+// distributed shared memory (ld.shared::cluster) before the usual epilogue.  No extra launch, no global workspace.
+//
 // CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
 // (warp w reads TMEM lanes 32*(w%4)..+31).  One 128 x BN output tile per CTA; UG_STAGES-deep smem ring over K.
 #include <cuda.h>
+#include <cstdint>
+#include <cstdlib>
 
 #include "gemm.cuh"
 #include "otk_ptx.cuh"
@@ -45,7 +53,7 @@ struct UmmaGemmParams {
 };
 struct UmmaGemmMaps { CUtensorMap A_hi, A_lo, B_hi, B_lo; };
 
-template <int BN>
+template <int BN, int KS>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_constant__ UmmaGemmMaps maps1,
                  const UmmaGemmParams p0, const UmmaGemmParams p1, int batch_per_problem, const int* __restrict__ ctrl,
@@ -65,8 +73,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
   const bool second = (int)blockIdx.z >= batch_per_problem;          // which of the two products of the launch
   const UmmaGemmMaps& maps = second ? maps1 : maps0;
   const UmmaGemmParams& p = second ? p1 : p0;
-  const int m0 = blockIdx.x * UG_BM, n0 = blockIdx.y * BN, batch = (int)blockIdx.z - (second ? batch_per_problem : 0);
-  const int num_k = (p.K + UG_BK - 1) / UG_BK;
+  const int ks = KS > 1 ? (int)cluster_ctarank() : 0;               // this CTA's share of K (cluster = KS CTAs along x)
+  const int m0 = ((int)blockIdx.x / KS) * UG_BM, n0 = blockIdx.y * BN, batch = (int)blockIdx.z - (second ? batch_per_problem : 0);
+  const int num_k_all = (p.K + UG_BK - 1) / UG_BK;
+  const int kb0 = ks * num_k_all / KS, num_k = (ks + 1) * num_k_all / KS - kb0;   // k-blocks [kb0, kb0 + num_k), >= 1 each
   const bool three = p.passes == 3;
 
   if (warp == 0 && lane == 0) {
@@ -89,7 +99,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
       const int s = kt % UG_STAGES, it = kt / UG_STAGES;
       mbar_wait(&empty[s], (it & 1) ^ 1);
       uint8_t* st = smem + s * STAGE;
-      const int k0 = kt * UG_BK;
+      const int k0 = (kb0 + kt) * UG_BK;
       if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], stage_tx);
         tma_load_3d(st, &maps.A_hi, k0, m0, batch, &full[s]);
@@ -143,6 +153,26 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
     // TMEM gives each lane one row; after the transpose lanes hold consecutive columns, so every store instruction
     // writes a full 128-byte line of C / C_hi / C_lo.
     const int q = warp % 4;                        // TMEM lane quarter this warp may access
+    if (KS > 1 && ks != 0) {
+      // non-leader of a split-K cluster: park the partial accumulator in the pipeline smem (all MMAs that read it have
+      // retired once tmem_full fires), column-major [BN][128] so that lanes write consecutive words
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      float* part = reinterpret_cast<float*>(smem);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) part[(c0 + j) * UG_BM + q * 32 + lane] = v[j];
+      }
+      tc_fence_before();
+    }
+  }
+  if constexpr (KS > 1) cluster_sync_all();        // partial accumulators of the peers are complete and visible
+  if (warp >= 2 && ks == 0) {
+    const int q = warp % 4;
     float* xp = xpose + (warp - 2) * (32 * 33);
     const int mrow0 = m0 + q * 32;
     mbar_wait(tmem_full, 0);
@@ -151,12 +181,23 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
     float* Ch = p.C_hi ? p.C_hi + (int64_t)batch * p.strideC : nullptr;
     float* Cl = p.C_lo ? p.C_lo + (int64_t)batch * p.strideC : nullptr;
     const float* bias = p.bias ? p.bias + (int64_t)batch * p.stride_bias : nullptr;
+    uint32_t peer[KS > 1 ? KS - 1 : 1];
+    if constexpr (KS > 1) {
+#pragma unroll
+      for (int r = 1; r < KS; ++r) peer[r - 1] = map_to_cta(smem_u32(smem), (uint32_t)r) + (uint32_t)(q * 32 + lane) * 4;
+    }
     double res = 0.0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
       tmem_ld_wait();
+      if constexpr (KS > 1) {
+#pragma unroll
+        for (int r = 1; r < KS; ++r)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += ld_shared_cluster_f32(peer[r - 1] + (uint32_t)((c0 + j) * UG_BM) * 4);
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = v[j];
       __syncwarp();
@@ -190,6 +231,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
     }
     tc_fence_before();
   }
+  if constexpr (KS > 1) cluster_sync_all();        // the leader has read the peers' shared memory: they may exit
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
@@ -266,10 +308,10 @@ static int prepare_gemm(const GemmArgs<float>& g, int64_t batch, int passes, int
   return 1;
 }
 
-template <int BN>
-static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, const int* ctrl,
-                       int ctrl_index, cudaStream_t st) {
-  auto kern = umma_gemm_kernel<BN>;
+template <int BN, int KS>
+static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, const int* ctrl,
+                          int ctrl_index, cudaStream_t st) {
+  auto kern = umma_gemm_kernel<BN, KS>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -277,25 +319,69 @@ static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_probl
     OTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ug_smem<BN>()));
     attr_set[dev] = true;
   }
-  dim3 grid((unsigned)ceil_div(a.p.M, UG_BM), (unsigned)ceil_div(a.p.N, BN), (unsigned)(batch * n_problems));
+  dim3 grid((unsigned)(ceil_div(a.p.M, UG_BM) * KS), (unsigned)ceil_div(a.p.N, BN), (unsigned)(batch * n_problems));
   if (grid.y > 65535 || grid.z > 65535) return 0;
-  kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index);
+  if constexpr (KS == 1) {
+    kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(UG_THREADS);
+    cfg.dynamicSmemBytes = ug_smem<BN>();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = KS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index));
+  }
   OTK_LAUNCH_CHECK();
   return 1;
 }
 
-// 64-wide tiles when 128-wide ones would fill less than half of the SMs
-static int pick_bn(int64_t M, int64_t N, int64_t batch, int n_problems) {
-  const int64_t ctas128 = ceil_div(M, UG_BM) * ceil_div(N, 128) * batch * n_problems;
-  return ctas128 * 2 <= sm_count() ? 64 : 128;
+template <int BN>
+static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, int ks, const int* ctrl,
+                       int ctrl_index, cudaStream_t st) {
+  if (ks == 4) return launch_gemm_ks<BN, 4>(a, b, n_problems, batch, ctrl, ctrl_index, st);
+  if (ks == 2) return launch_gemm_ks<BN, 2>(a, b, n_problems, batch, ctrl, ctrl_index, st);
+  return launch_gemm_ks<BN, 1>(a, b, n_problems, batch, ctrl, ctrl_index, st);
+}
+
+// Tile width and split-K factor.  Small products are bound by the bytes ONE CTA streams through its SM's L2 port,
+// (128 + BN) * K / KS * 8: among the (BN, KS) whose grid still fits one wave pick the one that minimises it (at least
+// two k-blocks per CTA); products that fill the machine anyway use 128-wide tiles without a split.
+static void pick_tile(int64_t M, int64_t N, int64_t K, int64_t batch, int n_problems, int* bn_out, int* ks_out) {
+  // Measured (B200, 512^3, paired launch): the split does not pay - the products of the Newton-Schulz chain are bound by
+  // per-launch latency, and the distributed-shared-memory reduction costs what the shorter K loop saves (compute():
+  // 2.29 ms with, 2.12 ms without).  It does shorten the truncating tensor-memory accumulation chains (relative error
+  // 9e-7 instead of 3.6e-6 at K = 512), so it stays available: OTK_GEMM_SPLITK=1.
+  static const bool split_ok = [] { const char* e = getenv("OTK_GEMM_SPLITK"); return e && e[0] == '1'; }();
+  const int64_t sms = sm_count(), num_k = ceil_div(K, UG_BK);
+  int best_bn = 128, best_ks = 1;
+  int64_t best_cost = INT64_MAX;
+  for (int bn : {128, 64}) {
+    const int64_t ctas = ceil_div(M, UG_BM) * ceil_div(N, bn) * batch * n_problems;
+    for (int ks : {1, 2, 4}) {
+      if (ks > 1 && (!split_ok || num_k < 2 * ks)) continue;
+      if (ctas * ks > sms && !(bn == 128 && ks == 1)) continue;      // (128, 1) is the fallback for large products
+      const int64_t cost = (int64_t)(UG_BM + bn) * ceil_div(num_k, ks);
+      if (cost < best_cost) { best_cost = cost; best_bn = bn; best_ks = ks; }
+    }
+  }
+  *bn_out = best_bn;
+  *ks_out = best_ks;
 }
 
 int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStream_t st) {
-  const int bn = pick_bn(g.M, g.N, batch, 1);
+  int bn, ks;
+  pick_tile(g.M, g.N, g.K, batch, 1, &bn, &ks);
   PreparedGemm a;
   int r = prepare_gemm(g, batch, passes, bn, st, &a);
   if (r <= 0) return r;
-  return bn == 64 ? launch_gemm<64>(a, a, 1, batch, nullptr, 0, st) : launch_gemm<128>(a, a, 1, batch, nullptr, 0, st);
+  return bn == 64 ? launch_gemm<64>(a, a, 1, batch, ks, nullptr, 0, st) : launch_gemm<128>(a, a, 1, batch, ks, nullptr, 0, st);
 }
 
 // two independent products of identical shape in one launch, optionally conditional on ctrl[0] > ctrl_index
@@ -303,13 +389,14 @@ int gemm_umma_dual(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t
                    cudaStream_t st) {
   const int n_problems = g1 ? 2 : 1;
   if (g1 && (g0.M != g1->M || g0.N != g1->N || g0.K != g1->K)) return 0;
-  const int bn = pick_bn(g0.M, g0.N, batch, n_problems);
+  int bn, ks;
+  pick_tile(g0.M, g0.N, g0.K, batch, n_problems, &bn, &ks);
   PreparedGemm a, b;
   int r = prepare_gemm(g0, batch, 3, bn, st, &a);
   if (r <= 0) return r;
   if (g1) { r = prepare_gemm(*g1, batch, 3, bn, st, &b); if (r <= 0) return r; } else b = a;
-  return bn == 64 ? launch_gemm<64>(a, b, n_problems, batch, ctrl, ctrl_index, st)
-                  : launch_gemm<128>(a, b, n_problems, batch, ctrl, ctrl_index, st);
+  return bn == 64 ? launch_gemm<64>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st)
+                  : launch_gemm<128>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st);
 }
 
 }  // namespace otk

@@ -7,6 +7,9 @@
 // Precision policy: the fp32-accurate engine is tried first.  Its accuracy is ~1e-7 * cond(A), so when the iteration
 // needs more than NS_F32_MAX_ITERS steps (which happens when lambda_min/||A||_F is below ~1e-4) and the caller's
 // data is fp64 (the reference default), the whole computation is repeated in fp64 on the same device.
+#include <mutex>
+#include <vector>
+#include <cstdlib>
 #include "gemm.cuh"
 #include "otk_ptx.cuh"
 
@@ -237,6 +240,73 @@ static int plane_gemm2(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int
 
 enum { NS_CONVERGED = 0, NS_SLOW = 1 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CUDA-graph cache for batches of Newton-Schulz iterations on the tcgen05 path.  A batch is ~3 launches per iteration,
+// each with ~1 KB of __grid_constant__ tensor maps encoded on the host: at d <= 512 the chain is bound by the CPU's launch
+// rate, not by the GPU.  All launches of a batch depend only on (workspace pointers, L, d, first iteration, count,
+// budget) and carry their stopping rule on the device (ctrl), so a batch that is seen a second time with the same key is
+// captured once (on a private stream: torch's legacy default stream cannot be captured) and replayed afterwards with one
+// cudaGraphLaunch on the caller's stream.
+// ---------------------------------------------------------------------------------------------------------------------
+unsigned long long launches();
+struct NsGraphKey {
+  const void *ctrl, *planes;
+  int64_t L, d;
+  int first, n, max_iters, adaptive, dev;
+  bool operator==(const NsGraphKey& o) const {
+    return ctrl == o.ctrl && planes == o.planes && L == o.L && d == o.d && first == o.first && n == o.n &&
+           max_iters == o.max_iters && adaptive == o.adaptive && dev == o.dev;
+  }
+};
+struct NsGraphEntry { NsGraphKey key; cudaGraphExec_t exec; int launches; int state; };   // state 0 seen once, 1 ready, -1 unusable
+static std::mutex g_ns_graph_mu;
+static std::vector<NsGraphEntry> g_ns_graphs;
+static cudaStream_t g_ns_capture_stream[64] = {nullptr};
+constexpr size_t NS_GRAPH_CACHE = 32;
+
+template <typename Enqueue>
+static int ns_batch(const NsGraphKey& key, cudaStream_t st, Enqueue&& enqueue) {
+  static const bool graphs_on = [] { const char* e = getenv("OTK_NS_GRAPHS"); return !(e && e[0] == '0'); }();   // tuning aid
+  if (!graphs_on || key.dev < 0 || key.dev >= 64) return enqueue(st);
+  std::lock_guard<std::mutex> lock(g_ns_graph_mu);
+  NsGraphEntry* hit = nullptr;
+  for (auto& e : g_ns_graphs) if (e.key == key) { hit = &e; break; }
+  if (!hit) {                                                   // first sighting: plain launches, remember the key
+    if (g_ns_graphs.size() >= NS_GRAPH_CACHE) {
+      if (g_ns_graphs.front().exec) cudaGraphExecDestroy(g_ns_graphs.front().exec);
+      g_ns_graphs.erase(g_ns_graphs.begin());
+    }
+    g_ns_graphs.push_back(NsGraphEntry{key, nullptr, 0, 0});
+    return enqueue(st);
+  }
+  if (hit->state < 0) return enqueue(st);
+  if (hit->state == 0) {                                        // second sighting: capture and instantiate
+    cudaStream_t& cs = g_ns_capture_stream[key.dev];
+    if (!cs && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cs = nullptr; hit->state = -1; cudaGetLastError(); return enqueue(st); }
+    const unsigned long long before = launches();
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { hit->state = -1; cudaGetLastError(); return enqueue(st); }
+    const int rc = enqueue(cs);
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    const int captured = (int)(launches() - before);
+    count_launch(-captured);                                    // nothing has run yet
+    cudaGraphExec_t exec = nullptr;
+    if (rc != OTK_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      hit->state = -1;
+      return enqueue(st);
+    }
+    cudaGraphDestroy(graph);
+    hit->exec = exec;
+    hit->launches = captured;
+    hit->state = 1;
+  }
+  OTK_CUDA(cudaGraphLaunch(hit->exec, st));
+  count_launch(hit->launches);
+  return OTK_OK;
+}
+
 // Coupled Newton-Schulz on (A + ridge I)/c:  T = (3I - Z Y)/2, Y <- Y T, Z <- T Z.
 // On return w.Y[*cur] ~ sqrt(A/c), w.Z[*cur] ~ (A/c)^-1/2 (unsymmetrised), c in w.c; *verdict says whether the
 // residual reached the working-precision floor within the budget.
@@ -270,24 +340,33 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
   while (enq < max_iters) {
     int n = adaptive ? (enq == 0 ? (planes ? NS_FIRST_BATCH : 6) : (planes ? NS_NEXT_BATCH : 1)) : max_iters;
     if (enq + n > max_iters) n = max_iters - enq;
-    for (int k = enq; k < enq + n; ++k) {
-      const int cur = k & 1;
-      bool done_planes = false;
-      if constexpr (sizeof(W) == 4) {
-        if (planes) {
-          GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, -0.5f, 1.5f, w.resid + (size_t)k * L);
-          OTK_TRY(plane_gemm2(zy, nullptr, L, w.ctrl, k, st));
-          if (adaptive) {
-            ns_ctrl_kernel<<<1, 256, 0, st>>>(w.resid + (size_t)k * L, L, k, max_iters, tol_done, tol_near, w.ctrl);
-            OTK_LAUNCH_CHECK();
+    bool done_planes = false;
+    if constexpr (sizeof(W) == 4) {
+      if (planes) {
+        auto enqueue = [&](cudaStream_t s) -> int {
+          for (int k = enq; k < enq + n; ++k) {
+            const int cur = k & 1;
+            GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, -0.5f, 1.5f, w.resid + (size_t)k * L);
+            OTK_TRY(plane_gemm2(zy, nullptr, L, w.ctrl, k, s));
+            if (adaptive) {
+              ns_ctrl_kernel<<<1, 256, 0, s>>>(w.resid + (size_t)k * L, L, k, max_iters, tol_done, tol_near, w.ctrl);
+              OTK_LAUNCH_CHECK();
+            }
+            GemmArgs<float> yt = plane_args(w.Yh[cur], w.Yl[cur], w.Th, w.Tl, w.Yh[cur ^ 1], w.Yl[cur ^ 1], d, 1.f, 0.f, nullptr);
+            GemmArgs<float> tz = plane_args(w.Th, w.Tl, w.Zh[cur], w.Zl[cur], w.Zh[cur ^ 1], w.Zl[cur ^ 1], d, 1.f, 0.f, nullptr);
+            OTK_TRY(plane_gemm2(yt, &tz, L, w.ctrl, k, s));
           }
-          GemmArgs<float> yt = plane_args(w.Yh[cur], w.Yl[cur], w.Th, w.Tl, w.Yh[cur ^ 1], w.Yl[cur ^ 1], d, 1.f, 0.f, nullptr);
-          GemmArgs<float> tz = plane_args(w.Th, w.Tl, w.Zh[cur], w.Zl[cur], w.Zh[cur ^ 1], w.Zl[cur ^ 1], d, 1.f, 0.f, nullptr);
-          OTK_TRY(plane_gemm2(yt, &tz, L, w.ctrl, k, st));
-          done_planes = true;
-        }
+          return OTK_OK;
+        };
+        int dev = 0;
+        cudaGetDevice(&dev);
+        OTK_TRY(ns_batch(NsGraphKey{w.ctrl, w.Yh[0], L, d, enq, n, max_iters, adaptive ? 1 : 0, dev}, st, enqueue));
+        done_planes = true;
       }
-      if (!done_planes) {
+    }
+    for (int k = enq; k < enq + n && !done_planes; ++k) {
+      const int cur = k & 1;
+      {
         // generic engines (FFMA / DFMA): the launches are unconditional, so they are only enqueued up to the next readback
         GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.T, d, dd, W(-0.5));
         g.diag_add = W(1.5);

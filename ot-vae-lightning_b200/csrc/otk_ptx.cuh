@@ -187,6 +187,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
   return r;
 }
+// 32-bit load from a shared::cluster address (distributed shared memory of a peer CTA)
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
 // arrive on an mbarrier given by a shared::cluster address (own or peer CTA).  Deliberately NOT .release.cluster: that
 // form compiles to MEMBAR.ALL.GPU and cost the converter warps ~30 % of the kernel (ncu r02); the data these arrivals
 // publish lives in tensor memory and is ordered by tcgen05.fence::before/after_thread_sync on either side.
