@@ -945,7 +945,8 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
     const int64_t nB2 = ceil_div(dim, 2 * SH_T), upl2 = nB2 * (nB2 + 1) / 2, n_units2 = L * upl2, pairs = sms / 2;
     const int64_t max_seg2 = (S2_MAX_ITEMS / 4) / (n_units2 > 0 ? n_units2 : 1);
     static const bool pair_ok = [] { const char* e = getenv("OTK_STATS_H2_PAIR"); return !(e && e[0] == '0'); }();   // tuning aid
-    if (dim >= 512 && pair_ok && pairs >= 1 && max_seg2 >= 1 && rows <= max_seg2 * 2048) {
+    static const int64_t pair_min_dim = [] { const char* e = getenv("OTK_STATS_H2_PAIR_MIN_DIM"); return e ? (int64_t)atoi(e) : (int64_t)512; }();
+    if (dim >= pair_min_dim && pair_ok && pairs >= 1 && max_seg2 >= 1 && rows <= max_seg2 * 2048) {
       static bool attr2_set[64] = {false};
       if (dev >= 0 && dev < 64 && !attr2_set[dev]) {
         OTK_CUDA(cudaFuncSetAttribute(stats_h2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));

@@ -205,16 +205,48 @@ def case_gmm():
     np.savez(os.path.join(HERE, "gmm_diag_argmax.npz"), src=npy(src), tgt=npy(tgt), probe=npy(probe), batch=200, **out)
 
 
+def case_operator_variants():
+    """compute_transport_operators beyond the deterministic full-matrix branch: stochastic (eq. 19,
+    with a rank-deficient source), diagonal, diagonal stochastic, each with and without a pg_star blend."""
+    g = torch.Generator().manual_seed(606)
+    d = 10
+    cs, ct = spd(g, 2, d, kappa=40.0), spd(g, 2, d, kappa=15.0) * 1.8
+    low = torch.randn(2, d, 4, generator=g, dtype=torch.double)
+    cs_low = low @ low.transpose(-1, -2)                      # rank 4 source: pinv + stochastic completion
+    vs = torch.rand(3, d, generator=g, dtype=torch.double) + 0.2
+    vt = torch.rand(3, d, generator=g, dtype=torch.double) * 2 + 0.1
+    out = dict(cs=npy(cs), ct=npy(ct), cs_low=npy(cs_low), vs=npy(vs), vt=npy(vt))
+    for tag, pg in (("p0", 0.0), ("p3", 0.3)):
+        T, Cw = ref_w2.compute_transport_operators(cs.clone(), ct.clone(), stochastic=True, diag=False, pg_star=pg, make_pd=True)
+        out[f"full_st_T_{tag}"], out[f"full_st_Cw_{tag}"] = npy(T), npy(Cw)
+        # (a rank-deficient source, the case eq. 19 exists for, cannot be pinned: the reference's own `is_spd(Cw)` check
+        # dies in `eigh` on the non-finite Cw it produces for cs_low - w2_utils.py:453, probed here)
+        T, Cw = ref_w2.compute_transport_operators(vs.clone(), vt.clone(), stochastic=False, diag=True, pg_star=pg)
+        out[f"diag_T_{tag}"], out[f"diag_Cw_{tag}"] = npy(T), npy(Cw)
+        T, Cw = ref_w2.compute_transport_operators(vs.clone(), vt.clone(), stochastic=True, diag=True, pg_star=pg)
+        out[f"diag_st_T_{tag}"], out[f"diag_st_Cw_{tag}"] = npy(T), npy(Cw)
+    x = torch.randn(3, 7, d, generator=g, dtype=torch.double)
+    ms, mt = torch.randn(3, 1, d, generator=g, dtype=torch.double), torch.randn(3, 1, d, generator=g, dtype=torch.double)
+    Td, Cwd = ref_w2.compute_transport_operators(vs.clone(), vt.clone(), stochastic=False, diag=True)
+    out.update(x=npy(x), ms=npy(ms), mt=npy(mt),
+               y_diag=npy(ref_w2.apply_transport(x, ms, mt, Td.unsqueeze(-2), Cwd.unsqueeze(-2), diag=True)))
+    np.savez(os.path.join(HERE, "operator_variants.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gmm":      # only the fixtures added later (the others stay byte-identical)
         case_gmm()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "operators":
+        case_operator_variants()
         sys.exit(0)
     case_matrix()
     case_gaussian()
     case_w2_functions()
     case_sinkhorn()
     case_gmm()
+    case_operator_variants()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

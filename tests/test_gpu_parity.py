@@ -538,3 +538,9 @@ def test_strided_token_latents_are_read_in_place(api):
     # the flatten-everything case needs no copy either (MNIST32 CNN latents [B, 128, 1, 1] -> [B, 128])
     lat = torch.randn(250, 128, 1, 1, device="cuda")
     assert permute_and_flatten(lat, (1, 2, 3)).data_ptr() == lat.data_ptr()
+
+
+def test_golden_operator_variants(api, golden):
+    """stochastic (eq. 19) / diagonal / pg_star-blended operators against the unmodified reference's outputs"""
+    from tests.test_host_logic import check_operator_variants
+    check_operator_variants(api, golden("operator_variants"), "cuda", rtol=TOL_MATFUN, cw_atol=1e-4)

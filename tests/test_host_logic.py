@@ -193,3 +193,26 @@ def test_gmm_transport_against_reference_golden(api, golden, name, diag):
             "parametrizations._weights.original"} <= keys
     op.reset()
     assert op.transport_matrix is None and float(op.source_model._n_obs.sum()) == 0
+
+
+# ------------------------------------------------------------------------------- operator variants
+
+def check_operator_variants(api, g, dev, rtol, cw_atol):
+    cs, ct, vs, vt = (T(g[k]).to(dev) for k in ("cs", "ct", "vs", "vt"))
+    for tag, pg in (("p0", 0.0), ("p3", 0.3)):
+        Tm, Cw = api.compute_transport_operators(cs.clone(), ct.clone(), stochastic=True, diag=False, pg_star=pg, make_pd=True)
+        want = T(g[f"full_st_T_{tag}"])
+        assert ((Tm.cpu() - want).norm() / want.norm()).item() < rtol
+        assert (Cw.cpu() - T(g[f"full_st_Cw_{tag}"])).abs().max().item() < cw_atol     # analytically zero for a full-rank source
+        for st, key in ((False, "diag"), (True, "diag_st")):
+            Tm, Cw = api.compute_transport_operators(vs.clone(), vt.clone(), stochastic=st, diag=True, pg_star=pg)
+            close(Tm.cpu(), g[f"{key}_T_{tag}"], rtol=1e-9)
+            close(Cw.cpu(), g[f"{key}_Cw_{tag}"], rtol=1e-6, atol=1e-12)
+    Td, Cwd = api.compute_transport_operators(vs.clone(), vt.clone(), stochastic=False, diag=True)
+    y = api.apply_transport(T(g["x"]).to(dev), T(g["ms"]).to(dev), T(g["mt"]).to(dev), Td.unsqueeze(-2), Cwd.unsqueeze(-2),
+                            diag=True)
+    close(y.cpu(), g["y_diag"], rtol=1e-9)
+
+
+def test_operator_variants_against_reference_golden(api, golden):
+    check_operator_variants(api, golden("operator_variants"), "cpu", rtol=1e-6, cw_atol=1e-6)
