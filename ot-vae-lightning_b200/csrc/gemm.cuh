@@ -8,8 +8,12 @@ int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStrea
 int gemm_f32(const GemmArgs<float>& g, int64_t batch, int engine, cudaStream_t st);
 // one or two independent 3xTF32 products (operands given as hi/lo planes) in one launch; with ctrl != nullptr the launch
 // is a no-op when ctrl[0] <= ctrl_index (device-side iteration limit of the Newton-Schulz loop)   (gemm_umma.cu)
+// Optional stopping rule of the Newton-Schulz loop, evaluated by ONE CTA at the end of the launch (instead of a
+// separate one-block kernel between two products): reads the residuals resid_k[0..L) of iteration k and lowers the
+// iteration limit ctrl[0] / sets the verdict ctrl[1], ctrl[2] exactly as ns_ctrl_kernel (matfun.cu) does.
+struct NsCtrlEval { const double* resid_k; int64_t L; int k, max_iters; double tol_done, tol_near; int* ctrl; };
 int gemm_umma_dual(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t batch, const int* ctrl, int ctrl_index,
-                   cudaStream_t st);
+                   cudaStream_t st, const NsCtrlEval* eval = nullptr);
 // precision-generic NT product: float -> tcgen05 / FFMA dispatch, double -> DFMA
 inline int gemm_any(const GemmArgs<float>& g, int64_t batch, cudaStream_t st) { return gemm_f32(g, batch, ENGINE_AUTO, st); }
 inline int gemm_any(const GemmArgs<double>& g, int64_t batch, cudaStream_t st) { return gemm_simt<double>(g, batch, st); }

@@ -57,7 +57,7 @@ template <int BN, int KS>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_constant__ UmmaGemmMaps maps1,
                  const UmmaGemmParams p0, const UmmaGemmParams p1, int batch_per_problem, const int* __restrict__ ctrl,
-                 int ctrl_index) {
+                 int ctrl_index, const NsCtrlEval ev) {
   using namespace ptx;
   if (ctrl && ctrl_index >= ctrl[0]) return;       // past the device-side iteration limit: nothing to do
   constexpr int BTILE = ug_btile<BN>(), STAGE = ug_stage<BN>(), UG_STAGES = ug_stages<BN>();
@@ -234,6 +234,23 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
   if constexpr (KS > 1) cluster_sync_all();        // the leader has read the peers' shared memory: they may exit
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+  // Newton-Schulz stopping rule (same logic as ns_ctrl_kernel), by one warp of one CTA: the residuals of iteration
+  // ev.k were completed by the previous launch; the lowered limit is seen by the launches of iteration ev.k + 1 on.
+  if (ev.ctrl && warp == 2 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ev.k < ev.ctrl[0] &&
+      (ev.k >= 5 || ev.k + 1 == ev.max_iters)) {
+    double worst = 0;
+    for (int64_t l = lane; l < ev.L; l += 32) {
+      const double r = ev.resid_k[l];
+      const double v = (r == r && r <= 1e30) ? r : 1e300;
+      worst = v > worst ? v : worst;
+    }
+    worst = warp_max(worst);
+    if (lane == 0) {
+      if (worst >= 1e300) { ev.ctrl[0] = ev.k + 1; ev.ctrl[1] = 1; ev.ctrl[2] = 1; }
+      else if (worst < ev.tol_done) { if (ev.k + 1 < ev.ctrl[0]) ev.ctrl[0] = ev.k + 1; ev.ctrl[1] = 0; }
+      else if (worst < ev.tol_near) { if (ev.k + 2 < ev.ctrl[0]) ev.ctrl[0] = ev.k + 2; ev.ctrl[1] = 0; }
+    }
+  }
 }
 
 // elementwise split of a strided [batch][rows][cols] operand into dense TF32 hi/lo planes [batch][rows][cols]
@@ -310,7 +327,7 @@ static int prepare_gemm(const GemmArgs<float>& g, int64_t batch, int passes, int
 
 template <int BN, int KS>
 static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, const int* ctrl,
-                          int ctrl_index, cudaStream_t st) {
+                          int ctrl_index, cudaStream_t st, const NsCtrlEval& ev) {
   auto kern = umma_gemm_kernel<BN, KS>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -322,7 +339,7 @@ static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_pr
   dim3 grid((unsigned)(ceil_div(a.p.M, UG_BM) * KS), (unsigned)ceil_div(a.p.N, BN), (unsigned)(batch * n_problems));
   if (grid.y > 65535 || grid.z > 65535) return 0;
   if constexpr (KS == 1) {
-    kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index);
+    kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -336,7 +353,7 @@ static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_pr
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index));
+    OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev));
   }
   OTK_LAUNCH_CHECK();
   return 1;
@@ -344,10 +361,10 @@ static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_pr
 
 template <int BN>
 static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, int ks, const int* ctrl,
-                       int ctrl_index, cudaStream_t st) {
-  if (ks == 4) return launch_gemm_ks<BN, 4>(a, b, n_problems, batch, ctrl, ctrl_index, st);
-  if (ks == 2) return launch_gemm_ks<BN, 2>(a, b, n_problems, batch, ctrl, ctrl_index, st);
-  return launch_gemm_ks<BN, 1>(a, b, n_problems, batch, ctrl, ctrl_index, st);
+                       int ctrl_index, cudaStream_t st, const NsCtrlEval& ev = NsCtrlEval{}) {
+  if (ks == 4) return launch_gemm_ks<BN, 4>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev);
+  if (ks == 2) return launch_gemm_ks<BN, 2>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev);
+  return launch_gemm_ks<BN, 1>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev);
 }
 
 // Tile width and split-K factor.  Small products are bound by the bytes ONE CTA streams through its SM's L2 port,
@@ -386,7 +403,7 @@ int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStrea
 
 // two independent products of identical shape in one launch, optionally conditional on ctrl[0] > ctrl_index
 int gemm_umma_dual(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t batch, const int* ctrl, int ctrl_index,
-                   cudaStream_t st) {
+                   cudaStream_t st, const NsCtrlEval* eval) {
   const int n_problems = g1 ? 2 : 1;
   if (g1 && (g0.M != g1->M || g0.N != g1->N || g0.K != g1->K)) return 0;
   int bn, ks;
@@ -395,8 +412,9 @@ int gemm_umma_dual(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t
   int r = prepare_gemm(g0, batch, 3, bn, st, &a);
   if (r <= 0) return r;
   if (g1) { r = prepare_gemm(*g1, batch, 3, bn, st, &b); if (r <= 0) return r; } else b = a;
-  return bn == 64 ? launch_gemm<64>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st)
-                  : launch_gemm<128>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st);
+  const NsCtrlEval ev = eval ? *eval : NsCtrlEval{};
+  return bn == 64 ? launch_gemm<64>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st, ev)
+                  : launch_gemm<128>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st, ev);
 }
 
 }  // namespace otk

@@ -232,8 +232,9 @@ static GemmArgs<float> plane_args(const float* Ah, const float* Al, const float*
   g.A_lo = Al; g.B_lo = Bl; g.C_hi = Ch; g.C_lo = Cl; g.diag_add = diag; g.resid = resid;
   return g;
 }
-static int plane_gemm2(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t L, const int* ctrl, int k, cudaStream_t st) {
-  int r = gemm_umma_dual(g0, g1, L, ctrl, k, st);
+static int plane_gemm2(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t L, const int* ctrl, int k, cudaStream_t st,
+                       const NsCtrlEval* eval = nullptr) {
+  int r = gemm_umma_dual(g0, g1, L, ctrl, k, st, eval);
   if (r == 0) { set_last_error_msg("sqrtm: tcgen05 engine rejected an eligible shape"); return OTK_ERR_CUDA; }
   return r < 0 ? r : OTK_OK;
 }
@@ -348,13 +349,12 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
             const int cur = k & 1;
             GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, -0.5f, 1.5f, w.resid + (size_t)k * L);
             OTK_TRY(plane_gemm2(zy, nullptr, L, w.ctrl, k, s));
-            if (adaptive) {
-              ns_ctrl_kernel<<<1, 256, 0, s>>>(w.resid + (size_t)k * L, L, k, max_iters, tol_done, tol_near, w.ctrl);
-              OTK_LAUNCH_CHECK();
-            }
+            // the stopping rule on the residuals of iteration k rides in the paired launch (one warp of its first CTA):
+            // it only has to act before the launches of iteration k + 1
+            const NsCtrlEval ev{w.resid + (size_t)k * L, L, k, max_iters, tol_done, tol_near, w.ctrl};
             GemmArgs<float> yt = plane_args(w.Yh[cur], w.Yl[cur], w.Th, w.Tl, w.Yh[cur ^ 1], w.Yl[cur ^ 1], d, 1.f, 0.f, nullptr);
             GemmArgs<float> tz = plane_args(w.Th, w.Tl, w.Zh[cur], w.Zl[cur], w.Zh[cur ^ 1], w.Zl[cur ^ 1], d, 1.f, 0.f, nullptr);
-            OTK_TRY(plane_gemm2(yt, &tz, L, w.ctrl, k, s));
+            OTK_TRY(plane_gemm2(yt, &tz, L, w.ctrl, k, s, adaptive ? &ev : nullptr));
           }
           return OTK_OK;
         };
