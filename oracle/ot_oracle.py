@@ -191,6 +191,106 @@ def gaussian_transport_pipeline(src: Tensor, tgt: Tensor, batch: int, decay: Opt
 
 
 # ---------------------------------------------------------------------------------------------------
+# operator variants (ot/w2_utils.py:714-793) and the Gaussian-mixture layer built on the same pieces
+# (ot/w2_utils.py:86-270, distribution_models/gassian_mixture_model.py, transport/gmm_transport.py)
+# ---------------------------------------------------------------------------------------------------
+
+def transport_operator_diag(var_s: Tensor, var_t: Tensor, pg_star: float = 0.0) -> Tuple[Tensor, Tensor]:
+    """T = (1-p) sqrt(vt / vs + 1e-8) + p ; Cw = 0.  ot/w2_utils.py:714-721."""
+    var_s, var_t = var_s.double(), var_t.double()
+    T = (1.0 - pg_star) * torch.sqrt(var_t / var_s + STABILITY_CONST) + pg_star
+    return T, torch.zeros_like(T)
+
+
+def transport_operator_diag_stochastic(var_s: Tensor, var_t: Tensor, pg_star: float = 0.0) -> Tuple[Tensor, Tensor]:
+    """Diagonal form of eq. 19: T = (1-p) sqrt(vt vs) pinv(vs) + p, Cw = sqrt(1-p) vt (1 - vt pinv(vs) T*^2) with
+    T* = sqrt(vs / vt + 1e-8) and the thresholded pseudo-inverse of the source variances.  ot/w2_utils.py:729-750."""
+    var_s, var_t = var_s.double(), var_t.double()
+    T_star = torch.sqrt(var_s / var_t + STABILITY_CONST)
+    pinv_s = torch.where(var_s > STABILITY_CONST, 1.0 / var_s, torch.zeros_like(var_s))
+    T = (1.0 - pg_star) * torch.sqrt(var_t * var_s) * pinv_s + pg_star
+    Cw = (1.0 - pg_star) ** 0.5 * var_t * (1.0 - var_t * pinv_s * T_star ** 2)
+    return T, Cw
+
+
+def transport_operator_full_stochastic(cov_s: Tensor, cov_t: Tensor, pg_star: float = 0.0) -> Tuple[Tensor, Tensor]:
+    """Eq. 19 of Freirich et al. with the pseudo-inverse of the source covariance.  ot/w2_utils.py:774-793."""
+    cov_s, cov_t = cov_s.double(), cov_t.double()
+    eye = identity_like(cov_s)
+    pinv_s = torch.linalg.pinv(cov_s)
+    root_t = sqrtm(cov_t)
+    iroot_t = invsqrtm(cov_t + STABILITY_CONST * eye)
+    T_star, _ = transport_operator_full(cov_t, cov_s, 0.0)
+    T = (1.0 - pg_star) * (root_t @ sqrtm(root_t @ cov_s @ root_t) @ iroot_t @ pinv_s) + pg_star * eye
+    Cw = (1.0 - pg_star) ** 0.5 * root_t @ (eye - root_t @ T_star @ pinv_s @ T_star @ root_t) @ root_t
+    return T, Cw
+
+
+def w2_dissimilarity(mean_s: Tensor, mean_t: Tensor, var_s: Tensor, var_t: Tensor, diag: bool) -> Tensor:
+    """All-pairs Gaussian W2^2 between N source and M target components, [*, N, M].
+    ot/w2_utils.py:86-134 (diagonal: |ms-mt|^2 + |sqrt(vs)-sqrt(vt)|^2) and :140-191 (full)."""
+    mean_s, mean_t, var_s, var_t = (t.double() for t in (mean_s, mean_t, var_s, var_t))
+    if diag:
+        dm = ((mean_s.unsqueeze(-2) - mean_t.unsqueeze(-3)) ** 2).sum(-1)
+        dv = ((var_s.sqrt().unsqueeze(-2) - var_t.sqrt().unsqueeze(-3)) ** 2).sum(-1)
+        return dm + dv
+    n, m = mean_s.shape[-2], mean_t.shape[-2]
+    lead = mean_s.shape[:-2]
+    return w2_gaussian(mean_s.unsqueeze(-2).expand(*lead, n, m, -1), mean_t.unsqueeze(-3).expand(*lead, n, m, -1),
+                       var_s.unsqueeze(-3).expand(*lead, n, m, -1, -1), var_t.unsqueeze(-4).expand(*lead, n, m, -1, -1))
+
+
+def ot_gmm(mean_s: Tensor, mean_t: Tensor, var_s: Tensor, var_t: Tensor, w_s: Tensor, w_t: Tensor, diag: bool,
+           **sinkhorn_kwargs) -> Tuple[Tensor, Tensor]:
+    """Entropic OT between the components: cost normalised by its max for the solve, total reported with the
+    un-normalised cost.  ot/w2_utils.py:197-270."""
+    cost = w2_dissimilarity(mean_s, mean_t, var_s, var_t, diag)
+    plan = sinkhorn_log(w_s.double(), w_t.double(), cost / cost.amax(dim=(-2, -1), keepdim=True), **sinkhorn_kwargs)
+    return (cost * plan).sum(dim=(-2, -1)), plan
+
+
+def gmm_energy(x: Tensor, mean: Tensor, var: Tensor, weights: Tensor, diag: bool) -> Tensor:
+    """log N(x_b | mean_k, var_k) + log w_k, [*, B, K].  gassian_mixture_model.py:86-94."""
+    x, mean, var, weights = (t.double() for t in (x, mean, var, weights))
+    d = x.shape[-1]
+    diff = x.unsqueeze(-2) - mean.unsqueeze(-3)                                  # [*, B, K, d]
+    if diag:
+        maha = (diff * diff / var.unsqueeze(-3)).sum(-1)
+        logdet = var.log().sum(-1).unsqueeze(-2)
+    else:
+        chol = torch.linalg.cholesky(var)                                        # [*, K, d, d]
+        sol = torch.linalg.solve_triangular(chol.unsqueeze(-4), diff.unsqueeze(-1), upper=False).squeeze(-1)
+        maha = (sol * sol).sum(-1)
+        logdet = 2.0 * torch.diagonal(chol, dim1=-2, dim2=-1).log().sum(-1).unsqueeze(-2)
+    log_prob = -0.5 * (maha + logdet + d * torch.log(torch.tensor(2.0 * torch.pi, dtype=torch.double)))
+    return log_prob + torch.log_softmax(weights.log(), dim=-1).unsqueeze(-2)
+
+
+def gmm_weighted_stats(x: Tensor, weights: Tensor, diag: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """(sum_b w_bk, sum_b w_bk x_b, sum_b w_bk x_b x_b^T) per component, the dense expression of
+    gassian_mixture_model.py:104-117 (it materialises the B x d^2 outer products)."""
+    x, weights = x.double(), weights.double()
+    wt = weights.transpose(-1, -2)
+    if diag:
+        return weights.sum(-2), wt @ x, wt @ (x * x)
+    outer = (x.unsqueeze(-1) @ x.unsqueeze(-2)).flatten(-2)
+    return weights.sum(-2), wt @ x, (wt @ outer).unflatten(-1, (x.shape[-1], x.shape[-1]))
+
+
+def gmm_transport_hard(x: Tensor, src_idx: Tensor, tgt_idx: Tensor, mean_s: Tensor, mean_t: Tensor, cov_s: Tensor,
+                       cov_t: Tensor, diag: bool) -> Tensor:
+    """Every input goes through the Gaussian map between the source component it is assigned to and its target
+    component (hard assignments).  gmm_transport.py:82-121 with one-hot assignments."""
+    x64 = x.double()
+    ms, mt = mean_s.double()[src_idx], mean_t.double()[tgt_idx]
+    if diag:
+        T, _ = transport_operator_diag(cov_s[src_idx], cov_t[tgt_idx])
+        return T * (x64 - ms) + mt
+    T, _ = transport_operator_full(cov_s[src_idx], cov_t[tgt_idx])
+    return (T @ (x64 - ms).unsqueeze(-1)).squeeze(-1) + mt
+
+
+# ---------------------------------------------------------------------------------------------------
 # log-domain Sinkhorn (ot/w2_utils.py:276-319) and its cost producers
 # ---------------------------------------------------------------------------------------------------
 

@@ -58,6 +58,17 @@ def _worker(rank, world, port, out_dir):
             u2, v2 = O.sinkhorn_log(a.double(), b.double(), C, 0.05, res["iters"], 0.0, return_potentials=True)[1:3]
             assert torch.allclose(res["u_local"].double(), u2[lo:hi], atol=2e-4)
             assert torch.allclose(res["v"].double(), v2, atol=2e-4)
+            # the caller-owned plan (buffers [+ graph on CUDA]) can be handed back: same problem, same answer; a plan
+            # of another problem is ignored
+            xl, al = xs[lo:hi].contiguous(), a[lo:hi].contiguous()
+            first = parallel.sharded_sinkhorn(xl, ys, al, b, reg=0.05, max_iter=40, threshold=0.0, kernels=fake_kernels)
+            again = parallel.sharded_sinkhorn(xl, ys, al, b, reg=0.05, max_iter=40, threshold=0.0, kernels=fake_kernels,
+                                              plan=first["plan"])
+            assert again["plan"] is first["plan"]
+            assert torch.equal(first["u_local"], again["u_local"]) and torch.equal(first["v"], again["v"])
+            other = parallel.sharded_sinkhorn(xl, ys, al, b, reg=0.07, max_iter=5, threshold=0.0, kernels=fake_kernels,
+                                              plan=first["plan"])
+            assert other["plan"] is not first["plan"]
         open(os.path.join(out_dir, f"ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()

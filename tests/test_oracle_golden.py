@@ -90,3 +90,40 @@ def test_sinkhorn(golden):
 def test_energy_cost(golden):
     g = golden("energy")
     close(O.inverse_distance_energy(T(g["pts"]), T(g["codebook"])), g["energy"])
+
+
+def test_operator_variants(golden):
+    """stochastic / diagonal / pg_star-blended operators (ot/w2_utils.py:714-793)"""
+    g = golden("operator_variants")
+    cs, ct, vs, vt = T(g["cs"]), T(g["ct"]), T(g["vs"]), T(g["vt"])
+    for tag, pg in (("p0", 0.0), ("p3", 0.3)):
+        Tm, Cw = O.transport_operator_full_stochastic(cs, ct, pg)
+        close(Tm, g[f"full_st_T_{tag}"], rtol=1e-6, atol=1e-8)
+        assert (Cw - T(g[f"full_st_Cw_{tag}"])).abs().max().item() < 1e-6         # analytically zero: round-off on both sides
+        Tm, Cw = O.transport_operator_diag(vs, vt, pg)
+        close(Tm, g[f"diag_T_{tag}"]); close(Cw, g[f"diag_Cw_{tag}"])
+        Tm, Cw = O.transport_operator_diag_stochastic(vs, vt, pg)
+        close(Tm, g[f"diag_st_T_{tag}"]); close(Cw, g[f"diag_st_Cw_{tag}"], rtol=1e-6, atol=1e-12)
+
+
+def test_gmm_layer(golden):
+    """energies, component OT and hard-assignment transport of the GMM layer on the reference's fitted parameters"""
+    for name, diag in (("gmm_full_argmax", False), ("gmm_diag_argmax", True)):
+        g = golden(name)
+        probe = T(g["probe"]).double()
+        ms, mt, vs, vt, ws, wt = (T(g[k]) for k in ("mean_s", "mean_t", "var_s", "var_t", "w_s", "w_t"))
+        energy = O.gmm_energy(probe, ms, vs, ws, diag)
+        close(energy, g["energy_s"], rtol=1e-9, atol=1e-9)
+        cost, plan = O.ot_gmm(ms, mt, vs, vt, ws, wt, diag, max_iter=100)
+        close(cost, g["cost"], rtol=1e-9); close(plan, g["coupling"], rtol=1e-8, atol=1e-12)
+        src_idx = energy.argmax(-1)
+        tgt_idx = (torch.nn.functional.one_hot(src_idx, ws.numel()).double() @ plan).argmax(-1)
+        moved = O.gmm_transport_hard(probe, src_idx, tgt_idx, ms, mt, vs, vt, diag)
+        assert torch.allclose(moved.float(), T(g["moved"]), rtol=1e-5, atol=1e-5)
+    # weighted statistics: one-hot weights reduce to per-group batch statistics
+    x = torch.randn(50, 4, dtype=torch.double, generator=torch.Generator().manual_seed(1))
+    w = torch.nn.functional.one_hot(torch.arange(50) % 3, 3).double()
+    n, s, ss = O.gmm_weighted_stats(x, w, diag=False)
+    for k in range(3):
+        nk, sk, ssk = O.batch_stats(x[k::3])
+        close(n[k], nk); close(s[k], sk); close(ss[k], ssk)
