@@ -59,7 +59,6 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
                  const UmmaGemmParams p0, const UmmaGemmParams p1, int batch_per_problem, const int* __restrict__ ctrl,
                  int ctrl_index, const NsCtrlEval ev) {
   using namespace ptx;
-  if (ctrl && ctrl_index >= ctrl[0]) return;       // past the device-side iteration limit: nothing to do
   constexpr int BTILE = ug_btile<BN>(), STAGE = ug_stage<BN>(), UG_STAGES = ug_stages<BN>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -91,6 +90,15 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above touched no global data, so it overlaps the tail of the previous
+  // launch of the chain; the successor may be scheduled from here on, and nothing below runs before the predecessor
+  // grid has completed (its planes, residuals and the iteration limit are then visible).
+  pdl_launch_dependents();
+  pdl_wait();
+  if (ctrl && ctrl_index >= ctrl[0]) {             // past the device-side iteration limit: nothing to do
+    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    return;
+  }
 
   if (warp == 0) {
     // ===== TMA producer: warp-uniform loop, one elected lane issues (descriptors stay in uniform registers) =====
@@ -338,8 +346,23 @@ static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_pr
   }
   dim3 grid((unsigned)(ceil_div(a.p.M, UG_BM) * KS), (unsigned)ceil_div(a.p.N, BN), (unsigned)(batch * n_problems));
   if (grid.y > 65535 || grid.z > 65535) return 0;
+  static const bool pdl_on = [] { const char* e = getenv("OTK_GEMM_PDL"); return !(e && e[0] == '0'); }();   // tuning aid
   if constexpr (KS == 1) {
-    kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev);
+    if (pdl_on) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(UG_THREADS);
+      cfg.dynamicSmemBytes = ug_smem<BN>();
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev));
+    } else {
+      kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev);
+    }
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

@@ -187,6 +187,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
   return r;
 }
+// Programmatic dependent launch (a launch with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream still runs): `pdl_launch_dependents` lets the successor's CTAs be scheduled from here on,
+// `pdl_wait` blocks until the predecessor grid has completed and its memory is visible.  Both are no-ops for launches
+// without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // 32-bit load from a shared::cluster address (distributed shared memory of a peer CTA)
 __device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
   float v;
