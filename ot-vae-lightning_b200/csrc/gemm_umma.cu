@@ -25,6 +25,7 @@
 // CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
 // (warp w reads TMEM lanes 32*(w%4)..+31).  One 128 x BN output tile per CTA; UG_STAGES-deep smem ring over K.
 #include <cuda.h>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 
@@ -53,12 +54,42 @@ struct UmmaGemmParams {
 };
 struct UmmaGemmMaps { CUtensorMap A_hi, A_lo, B_hi, B_lo; };
 
+// Epilogue rows of the common case of the Newton-Schulz chain - full 32-row slice, result emitted as TF32 hi/lo planes
+// only - without per-row pointer / bounds tests: the 32 rows are independent straight-line code the scheduler can
+// interleave.  (With the tests inside the loop every row was a branchy dependent chain of ~190 cycles on the single
+// epilogue warp of its scheduler: 3.1 us per 32-row chunk, 6.9 us of a 10 - 16 us launch - globaltimer stamps.)
+template <bool RESID>
+__device__ __forceinline__ void epilogue_rows_planes(const float (&v)[32], int mrow0, int n, int64_t ldc, float alpha,
+                                                     float bn, float diag_add, float* __restrict__ Ch,
+                                                     float* __restrict__ Cl, double& res) {
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const int m = mrow0 + r;
+    const float acc = v[r];
+    if (RESID) { const float e = acc - (m == n ? 1.f : 0.f); res += (double)(e * e); }
+    float t = alpha * acc + bn;
+    if (m == n) t += diag_add;
+    float h, lo;
+    ptx::split_tf32(t, h, lo);
+    const int64_t idx = (int64_t)m * ldc + n;
+    Ch[idx] = h;
+    Cl[idx] = lo;
+  }
+}
+
 template <int BN, int KS>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_constant__ UmmaGemmMaps maps1,
                  const UmmaGemmParams p0, const UmmaGemmParams p1, int batch_per_problem, const int* __restrict__ ctrl,
                  int ctrl_index, const NsCtrlEval ev) {
   using namespace ptx;
+#ifdef OTK_GEMM_TIMING
+  unsigned long long gt0, gts[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};       // per-thread stamps, printed once at the very end
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+#define GT_STAMP(slot) { asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gts[slot])); }
+#else
+#define GT_STAMP(slot) {}
+#endif
   constexpr int BTILE = ug_btile<BN>(), STAGE = ug_stage<BN>(), UG_STAGES = ug_stages<BN>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -93,8 +124,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
   // Programmatic dependent launch: everything above touched no global data, so it overlaps the tail of the previous
   // launch of the chain; the successor may be scheduled from here on, and nothing below runs before the predecessor
   // grid has completed (its planes, residuals and the iteration limit are then visible).
+  GT_STAMP(0)
   pdl_launch_dependents();
   pdl_wait();
+  GT_STAMP(1)
   if (ctrl && ctrl_index >= ctrl[0]) {             // past the device-side iteration limit: nothing to do
     if (warp == 1) tmem_dealloc(tmem_base, BN);
     return;
@@ -134,6 +167,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
       const int s = kt % UG_STAGES, it = kt / UG_STAGES;
       mbar_wait(&full[s], it & 1);
       tc_fence_after();
+      if (kt == 0) GT_STAMP(2)
+      if (kt == num_k - 1) GT_STAMP(3)
       const uint32_t base = smem_u32(smem + s * STAGE);
       if (elect_one()) {
 #pragma unroll
@@ -181,10 +216,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
   if constexpr (KS > 1) cluster_sync_all();        // partial accumulators of the peers are complete and visible
   if (warp >= 2 && ks == 0) {
     const int q = warp % 4;
-    float* xp = xpose + (warp - 2) * (32 * 33);
+    const uint32_t xp_addr = smem_u32(xpose + (warp - 2) * (32 * 33));
     const int mrow0 = m0 + q * 32;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    GT_STAMP(4)
     float* C = p.C ? p.C + (int64_t)batch * p.strideC : nullptr;
     float* Ch = p.C_hi ? p.C_hi + (int64_t)batch * p.strideC : nullptr;
     float* Cl = p.C_lo ? p.C_lo + (int64_t)batch * p.strideC : nullptr;
@@ -200,23 +236,35 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
       tmem_ld_wait();
+      if (c0 == 0) GT_STAMP(6)
       if constexpr (KS > 1) {
 #pragma unroll
         for (int r = 1; r < KS; ++r)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += ld_shared_cluster_f32(peer[r - 1] + (uint32_t)((c0 + j) * UG_BM) * 4);
       }
+      // 32 x 32 transpose through shared memory with explicit st.shared / ld.shared: through the generic `float*` the
+      // compiler emitted generic LD.E / ST.E and, unable to tell them from the global stores of C_hi / C_lo, kept one
+      // load -> split -> store chain per row in order (globaltimer stamps: 6.9 us of a 10 - 16 us launch were this
+      // loop, for any d).  All 32 loads are issued before the first store.
 #pragma unroll
-      for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = v[j];
+      for (int j = 0; j < 32; ++j) sts32(xp_addr + (uint32_t)(lane * 33 + j) * 4, v[j]);
       __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; ++r) v[r] = lds32(xp_addr + (uint32_t)(r * 33 + lane) * 4);
+      if (c0 == 0) GT_STAMP(7)
       const int n = n0 + c0 + lane;
-      if (n < p.N) {
+      if (n < p.N && !C && Ch && mrow0 + 32 <= p.M) {
         const float bn = bias ? bias[n] : 0.f;
-#pragma unroll 8
+        if (p.resid) epilogue_rows_planes<true>(v, mrow0, n, p.ldc, p.alpha, bn, p.diag_add, Ch, Cl, res);
+        else epilogue_rows_planes<false>(v, mrow0, n, p.ldc, p.alpha, bn, p.diag_add, Ch, Cl, res);
+      } else if (n < p.N) {
+        const float bn = bias ? bias[n] : 0.f;
+#pragma unroll
         for (int r = 0; r < 32; ++r) {
           const int m = mrow0 + r;
           if (m >= p.M) continue;
-          const float acc = xp[r * 33 + lane];
+          const float acc = v[r];
           const int64_t idx = (int64_t)m * p.ldc + n;
           if (p.resid) { const float e = acc - (m == n ? 1.f : 0.f); res += (double)(e * e); }
           float t = p.alpha * acc + bn;
@@ -232,16 +280,29 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
         }
       }
       __syncwarp();
+      if (c0 == 0) GT_STAMP(8)
     }
+    GT_STAMP(9)
     if (p.resid) {
       res = warp_sum(res);
       if (lane == 0) atomicAdd(&p.resid[batch], res);
     }
     tc_fence_before();
+    GT_STAMP(5)
   }
   if constexpr (KS > 1) cluster_sync_all();        // the leader has read the peers' shared memory: they may exit
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+#ifdef OTK_GEMM_TIMING
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x % 32) == 0 && ctrl_index == 7) {
+    unsigned long long ge;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ge));
+    printf("gemm k=7 grid %d warp %d: prologue %lld | pdl wait %lld | first stage %lld | last stage %lld | acc complete %lld | epilogue %lld | end %lld ns || tmem_ld0 %lld lds0 %lld rows0 %lld rows1 %lld\n",
+           (int)(gridDim.x * gridDim.y * gridDim.z), (int)(threadIdx.x / 32), (long long)(gts[0] - gt0), (long long)(gts[1] - gt0), gts[2] ? (long long)(gts[2] - gt0) : -1LL,
+           gts[3] ? (long long)(gts[3] - gt0) : -1LL, gts[4] ? (long long)(gts[4] - gt0) : -1LL, gts[5] ? (long long)(gts[5] - gt0) : -1LL, (long long)(ge - gt0),
+           gts[6] ? (long long)(gts[6] - gt0) : -1LL, gts[7] ? (long long)(gts[7] - gt0) : -1LL, gts[8] ? (long long)(gts[8] - gt0) : -1LL, gts[9] ? (long long)(gts[9] - gt0) : -1LL);
+  }
+#endif
   // Newton-Schulz stopping rule (same logic as ns_ctrl_kernel), by one warp of one CTA: the residuals of iteration
   // ev.k were completed by the previous launch; the lowered limit is seen by the launches of iteration ev.k + 1 on.
   if (ev.ctrl && warp == 2 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ev.k < ev.ctrl[0] &&
