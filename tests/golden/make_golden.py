@@ -164,11 +164,12 @@ def gmm_clouds(g, n, d, centres, spread):
     return pts[torch.randperm(n, generator=g)].float()
 
 
-def run_gmm(src, tgt, probe, d, ks, kt, batch, diag, transport_type):
+def run_gmm(src, tgt, probe, d, ks, kt, batch, diag, transport_type, source_mode="argmax"):
     from ot_vae_lightning.ot.transport.gmm_transport import GMMTransport
     op = GMMTransport(d, transport_type=transport_type,
                       transport_cfg=dict(diag=diag, stochastic=False, make_pd=True, dtype=torch.double),
-                      source_cfg=dict(mixture_cfg=dict(n_components=ks), dtype=torch.double),
+                      source_cfg=dict(mixture_cfg=dict(n_components=ks, training_mode=source_mode,
+                                                       inference_mode=source_mode), dtype=torch.double),
                       target_cfg=dict(mixture_cfg=dict(n_components=kt), dtype=torch.double))
     # the models draw their initial means with the global generator on their first update: one seed per model
     torch.manual_seed(11)
@@ -188,7 +189,7 @@ def run_gmm(src, tgt, probe, d, ks, kt, batch, diag, transport_type):
     return out
 
 
-def case_gmm():
+def case_gmm(only_soft=None):
     """GaussianMixtureModel + GMMTransport on separated clusters, full and diagonal covariances."""
     g = torch.Generator().manual_seed(505)
     d = 6
@@ -203,6 +204,10 @@ def case_gmm():
     # vector" (gmm_transport.py:106-111 -> w2_utils.py:648; probed here))
     out = run_gmm(src, tgt, probe, d, 3, 2, 200, diag=True, transport_type="argmax")
     np.savez(os.path.join(HERE, "gmm_diag_argmax.npz"), src=npy(src), tgt=npy(tgt), probe=npy(probe), batch=200, **out)
+    if only_soft is not False:
+        # soft ('mean') source assignments: weighted statistics with fractional weights, one operator per input
+        out = run_gmm(src, tgt, probe[:12], d, 3, 2, 150, diag=False, transport_type="argmax", source_mode="mean")
+        np.savez(os.path.join(HERE, "gmm_full_soft.npz"), src=npy(src), tgt=npy(tgt), probe=npy(probe[:12]), batch=150, **out)
 
 
 def case_operator_variants():

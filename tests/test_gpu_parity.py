@@ -544,3 +544,4 @@ def test_golden_operator_variants(api, golden):
     """stochastic (eq. 19) / diagonal / pg_star-blended operators against the unmodified reference's outputs"""
     from tests.test_host_logic import check_operator_variants
     check_operator_variants(api, golden("operator_variants"), "cuda", rtol=TOL_MATFUN, cw_atol=1e-4)
+

@@ -153,12 +153,13 @@ def test_install_as_reference_aliases():
 
 # ------------------------------------------------------------------------------------------------- GMM
 
-def run_gmm_case(api, g, diag, device="cpu", rtol=1e-7):
+def run_gmm_case(api, g, diag, device="cpu", rtol=1e-7, source_mode="argmax"):
     d, bs = int(g["src"].shape[1]), int(g["batch"])
     cfg = dict(dtype=torch.double, device=device)
     op = api.GMMTransport(d, transport_type="argmax",
                           transport_cfg=dict(diag=diag, stochastic=False, make_pd=True, dtype=torch.double),
-                          source_cfg=dict(mixture_cfg=dict(n_components=int(g["n_s"].shape[0])), **cfg),
+                          source_cfg=dict(mixture_cfg=dict(n_components=int(g["n_s"].shape[0]), training_mode=source_mode,
+                                                           inference_mode=source_mode), **cfg),
                           target_cfg=dict(mixture_cfg=dict(n_components=int(g["n_t"].shape[0])), **cfg))
     src, tgt, probe = (T(g[k]).to(device) for k in ("src", "tgt", "probe"))
     torch.manual_seed(11)                       # same seeds as tests/golden/make_golden.py::run_gmm
@@ -216,3 +217,12 @@ def check_operator_variants(api, g, dev, rtol, cw_atol):
 
 def test_operator_variants_against_reference_golden(api, golden):
     check_operator_variants(api, golden("operator_variants"), "cpu", rtol=1e-6, cw_atol=1e-6)
+
+
+def test_gmm_soft_assignments_against_reference_golden(api, golden):
+    """'mean' (soft) source assignments: fractional weighted statistics and one Gaussian map per input"""
+    g = golden("gmm_full_soft")
+    op, cost, moved = run_gmm_case(api, g, False, source_mode="mean", rtol=1e-6)
+    close(cost, g["cost"], rtol=1e-6)
+    close(op.transport_matrix, g["coupling"], rtol=1e-5, atol=1e-9)
+    assert torch.allclose(moved, T(g["moved"]), rtol=1e-4, atol=1e-4)
