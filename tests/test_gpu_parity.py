@@ -545,3 +545,13 @@ def test_golden_operator_variants(api, golden):
     from tests.test_host_logic import check_operator_variants
     check_operator_variants(api, golden("operator_variants"), "cuda", rtol=TOL_MATFUN, cw_atol=1e-4)
 
+
+
+def test_golden_gmm_soft_assignments(api, golden):
+    """soft ('mean') source assignments through the sqrt(w)-scaled weighted SYRK and the per-input operator path"""
+    from tests.test_host_logic import run_gmm_case
+    g = golden("gmm_full_soft")
+    op, cost, moved = run_gmm_case(api, g, False, device="cuda", source_mode="mean", rtol=TOL_STATS)
+    assert rel(cost, g["cost"]) < TOL_MATFUN
+    assert np.abs(op.transport_matrix.cpu().numpy() - g["coupling"]).max() < TOL_SINKHORN
+    assert moved.is_cuda and rel(moved, g["moved"]) < TOL_MATFUN
