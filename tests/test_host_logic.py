@@ -226,3 +226,26 @@ def test_gmm_soft_assignments_against_reference_golden(api, golden):
     close(cost, g["cost"], rtol=1e-6)
     close(op.transport_matrix, g["coupling"], rtol=1e-5, atol=1e-9)
     assert torch.allclose(moved, T(g["moved"]), rtol=1e-4, atol=1e-4)
+
+
+def test_public_surface_matches_the_reference_exports():
+    """every name the reference star-exports from `ot_vae_lightning.ot` (matrix_utils.py:20-31,
+    w2_utils.py:26-36, the model / transport classes) resolves here, also under the reference's module paths."""
+    import importlib
+
+    import ot_vae_lightning_b200 as pkg
+    import ot_vae_lightning_b200.ot as ot
+    names = ["eye_like", "sqrtm", "invsqrtm", "is_spd", "is_pd", "is_symmetric", "min_eig", "make_psd", "mean_cov",
+             "STABILITY_CONST", "w2_gaussian", "batch_w2_dissimilarity_gaussian_diag", "batch_w2_dissimilarity_gaussian",
+             "batch_ot_gmm", "sinkhorn_log", "gaussian_barycenter", "compute_transport_operators", "apply_transport",
+             "W2Mixin", "GaussianModel", "CodebookModel", "CategoricalEmbeddings", "GaussianMixtureModel",
+             "TransportOperator", "GaussianTransport", "DiscreteTransport", "GMMTransport"]
+    assert [n for n in names if not hasattr(ot, n)] == []
+    from ot_vae_lightning_b200.ot import w2_utils
+    assert hasattr(w2_utils, "mean_cov")        # w2_utils re-exports matrix_utils (reference w2_utils.py:24, fid.py:24)
+    pkg.install_as_reference("ot_vae_lightning_surface_check")
+    for mod, cls in (("ot.transport.gaussian_transport", "GaussianTransport"), ("ot.transport.gmm_transport", "GMMTransport"),
+                     ("ot.transport.discrete_transport", "DiscreteTransport"),
+                     ("ot.distribution_models.gassian_mixture_model", "GaussianMixtureModel"),
+                     ("ot.distribution_models.gaussian_model", "GaussianModel"), ("metrics.fid", "FrechetInceptionDistance")):
+        assert hasattr(importlib.import_module(f"ot_vae_lightning_surface_check.{mod}"), cls)
