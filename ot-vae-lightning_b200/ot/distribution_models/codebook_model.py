@@ -172,6 +172,7 @@ class CodebookModel(DistributionModel, MixtureMixin):
 
     def _init_parameters(self, samples: Tensor) -> None:
         if bool(torch.allclose(self.codebook, self.vec_init)):
-            pick = torch.randperm(samples.size(-2), device=samples.device)[:self.n_components]
+            # host-side draw, as the reference (codebook_model.py:211): a seeded run picks the same rows
+            pick = torch.randperm(samples.size(-2))[:self.n_components].to(samples.device)
             self.codebook.copy_(samples[..., pick, :])
             self._n_obs += 1

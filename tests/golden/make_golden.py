@@ -210,6 +210,38 @@ def case_gmm(only_soft=None):
         np.savez(os.path.join(HERE, "gmm_full_soft.npz"), src=npy(src), tgt=npy(tgt), probe=npy(probe[:12]), batch=150, **out)
 
 
+def case_discrete():
+    """DiscreteTransport end to end: streaming k-means codebooks, inverse-distance cost, Sinkhorn plan,
+    argmax / mean routing (discrete_transport.py:27-98, codebook_model.py:122-214)."""
+    from ot_vae_lightning.ot.transport.discrete_transport import DiscreteTransport
+    g = torch.Generator().manual_seed(707)
+    d = 8
+    src = gmm_clouds(g, 400, d, [[4.0 * ((i + j) % 3 == 0) for j in range(d)] for i in range(6)], 0.4)
+    # (equal codebook sizes: the reference builds the cost as source.energy(target codebook) = [k, n] and hands it to
+    # sinkhorn_log with a [n], b [k] - discrete_transport.py:58-66 - so n != k raises in its own logsumexp; probed here)
+    tgt = gmm_clouds(g, 400, d, [[-3.0 * ((i + 2 * j) % 4 == 0) + 1.0 for j in range(d)] for i in range(6)], 0.3)
+    probe = src[:32].clone()
+    out = dict(src=npy(src), tgt=npy(tgt), probe=npy(probe), batch=100)
+    for kind in ("argmax", "mean"):
+        op = DiscreteTransport(d, transport_type=kind, sinkhorn_reg=0.05, sinkhorn_max_iter=300, sinkhorn_threshold=1e-9,
+                               source_cfg=dict(mixture_cfg=dict(n_components=6), dtype=torch.double),
+                               target_cfg=dict(mixture_cfg=dict(n_components=6), dtype=torch.double))
+        torch.manual_seed(21)                      # the codebooks start from host-side randperm picks: one seed per model
+        for lo in range(0, 400, 100):
+            op.update(source_samples=src[lo:lo + 100])
+        torch.manual_seed(22)
+        for lo in range(0, 400, 100):
+            op.update(target_samples=tgt[lo:lo + 100])
+        cost = op.compute()
+        torch.manual_seed(23)
+        moved = op.transport(probe)
+        out.update({f"cost_{kind}": npy(cost), f"plan_{kind}": npy(op.transport_matrix), f"moved_{kind}": npy(moved)})
+    sm, tm = op.source_model, op.target_model
+    out.update(codebook_s=npy(sm.codebook), codebook_t=npy(tm.codebook), n_s=npy(sm._n_obs), n_t=npy(tm._n_obs),
+               sum_s=npy(sm._running_sum), w_s=npy(sm.weights), w_t=npy(tm.weights))
+    np.savez(os.path.join(HERE, "discrete.npz"), **out)
+
+
 def case_operator_variants():
     """compute_transport_operators beyond the deterministic full-matrix branch: stochastic (eq. 19,
     with a rank-deficient source), diagonal, diagonal stochastic, each with and without a pg_star blend."""
@@ -243,6 +275,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gmm":      # only the fixtures added later (the others stay byte-identical)
         case_gmm()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "discrete":
+        case_discrete()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "operators":
         case_operator_variants()
         sys.exit(0)
@@ -252,6 +287,7 @@ if __name__ == "__main__":
     case_sinkhorn()
     case_gmm()
     case_operator_variants()
+    case_discrete()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

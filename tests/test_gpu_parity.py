@@ -555,3 +555,17 @@ def test_golden_gmm_soft_assignments(api, golden):
     assert rel(cost, g["cost"]) < TOL_MATFUN
     assert np.abs(op.transport_matrix.cpu().numpy() - g["coupling"]).max() < TOL_SINKHORN
     assert moved.is_cuda and rel(moved, g["moved"]) < TOL_MATFUN
+
+
+@pytest.mark.parametrize("kind", ["argmax", "mean"])
+def test_golden_discrete_transport(api, golden, kind):
+    """DiscreteTransport end to end (streaming k-means codebooks -> inverse-distance cost kernel -> Sinkhorn kernel ->
+    routing) against the unmodified reference's outputs"""
+    from tests.test_host_logic import run_discrete_case
+    g = golden("discrete")
+    op, cost, moved = run_discrete_case(api, g, kind, device="cuda")
+    assert np.allclose(op.source_model._n_obs.cpu().numpy(), g["n_s"]) and np.allclose(op.target_model._n_obs.cpu().numpy(), g["n_t"])
+    assert rel(op.source_model.codebook, g["codebook_s"]) < TOL_STATS and rel(op.target_model.codebook, g["codebook_t"]) < TOL_STATS
+    assert rel(cost, g[f"cost_{kind}"]) < TOL_SINKHORN
+    assert np.abs(op.transport_matrix.cpu().numpy() - g[f"plan_{kind}"]).max() < TOL_SINKHORN
+    assert moved.is_cuda and moved.dtype == torch.float32 and rel(moved, g[f"moved_{kind}"]) < TOL_MATFUN

@@ -249,3 +249,38 @@ def test_public_surface_matches_the_reference_exports():
                      ("ot.distribution_models.gassian_mixture_model", "GaussianMixtureModel"),
                      ("ot.distribution_models.gaussian_model", "GaussianModel"), ("metrics.fid", "FrechetInceptionDistance")):
         assert hasattr(importlib.import_module(f"ot_vae_lightning_surface_check.{mod}"), cls)
+
+
+# ------------------------------------------------------------------------------------ DiscreteTransport
+
+def run_discrete_case(api, g, kind, device="cpu"):
+    d = int(g["src"].shape[1])
+    cfg = dict(dtype=torch.double, device=device)
+    op = api.DiscreteTransport(d, transport_type=kind, sinkhorn_reg=0.05, sinkhorn_max_iter=300, sinkhorn_threshold=1e-9,
+                               source_cfg=dict(mixture_cfg=dict(n_components=int(g["n_s"].shape[0])), **cfg),
+                               target_cfg=dict(mixture_cfg=dict(n_components=int(g["n_t"].shape[0])), **cfg)).to(device)
+    src, tgt, bs = T(g["src"]).to(device), T(g["tgt"]).to(device), int(g["batch"])
+    torch.manual_seed(21)                        # same seeds as tests/golden/make_golden.py::case_discrete
+    for lo in range(0, src.shape[0], bs):
+        op.update(source_samples=src[lo:lo + bs])
+    torch.manual_seed(22)
+    for lo in range(0, tgt.shape[0], bs):
+        op.update(target_samples=tgt[lo:lo + bs])
+    cost = op.compute()
+    torch.manual_seed(23)
+    moved = op.transport(T(g["probe"]).to(device))
+    return op, cost, moved
+
+
+@pytest.mark.parametrize("kind", ["argmax", "mean"])
+def test_discrete_transport_against_reference_golden(api, golden, kind):
+    g = golden("discrete")
+    op, cost, moved = run_discrete_case(api, g, kind)
+    close(op.source_model.codebook, g["codebook_s"], rtol=1e-9)
+    close(op.target_model.codebook, g["codebook_t"], rtol=1e-9)
+    close(op.source_model._n_obs, g["n_s"]); close(op.target_model._n_obs, g["n_t"])
+    close(op.source_model._running_sum, g["sum_s"], rtol=1e-9)
+    close(op.source_model.weights, g["w_s"], rtol=1e-9); close(op.target_model.weights, g["w_t"], rtol=1e-9)
+    close(cost, g[f"cost_{kind}"], rtol=1e-7)
+    close(op.transport_matrix, g[f"plan_{kind}"], rtol=1e-6, atol=1e-10)
+    assert moved.dtype == torch.float32 and torch.allclose(moved, T(g[f"moved_{kind}"]), rtol=1e-5, atol=1e-6)
