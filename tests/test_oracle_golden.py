@@ -127,3 +127,14 @@ def test_gmm_layer(golden):
     for k in range(3):
         nk, sk, ssk = O.batch_stats(x[k::3])
         close(n[k], nk); close(s[k], sk); close(ss[k], ssk)
+
+
+def test_discrete_transport_on_fitted_codebooks(golden):
+    """cost = source.energy(target codebook) (inverse distance, codebook_model.py:155-160), Sinkhorn plan and total cost
+    of DiscreteTransport.compute (discrete_transport.py:55-68) on the reference's fitted codebooks"""
+    g = golden("discrete")
+    cb_s, cb_t, w_s, w_t = (T(g[k]) for k in ("codebook_s", "codebook_t", "w_s", "w_t"))
+    cost = O.inverse_distance_energy(cb_t, cb_s)
+    plan = O.sinkhorn_log(w_s, w_t, cost, reg=0.05, max_iter=300, threshold=1e-9)
+    close(plan, g["plan_argmax"], rtol=1e-8, atol=1e-12)
+    close((cost * plan).sum(), g["cost_argmax"], rtol=1e-9)
