@@ -249,6 +249,23 @@ def ot_gmm(mean_s: Tensor, mean_t: Tensor, var_s: Tensor, var_t: Tensor, w_s: Te
     return (cost * plan).sum(dim=(-2, -1)), plan
 
 
+def gaussian_barycenter(mean: Tensor, cov: Tensor, weights: Tensor, diag: bool, n_iter: int = 100, start: int = 0
+                        ) -> Tuple[Tensor, Tensor]:
+    """W2 barycenter of N(mean_i, cov_i) with weights w_i: mean = sum w_i mean_i; variances (sum w_i sqrt(v_i))^2 when
+    `diag`, else the fixed point S <- sum_i w_i (S^1/2 C_i S^1/2)^1/2 started from C_start (the reference draws the start
+    at random; the fixed point does not depend on it).  ot/w2_utils.py:325-385."""
+    mean, cov, weights = mean.double(), cov.double(), weights.double()
+    mean_b = (weights.unsqueeze(-2) @ mean).squeeze(-2)
+    if diag:
+        return mean_b, ((weights.unsqueeze(-2) @ cov.sqrt()) ** 2).squeeze(-2)
+    w = weights[..., None, None]
+    cov_b = cov.select(-3, start).unsqueeze(-3)
+    for _ in range(n_iter):
+        root = sqrtm(cov_b)
+        cov_b = (w * sqrtm(root @ cov @ root)).sum(-3, keepdim=True)
+    return mean_b, cov_b.squeeze(-3)
+
+
 def gmm_energy(x: Tensor, mean: Tensor, var: Tensor, weights: Tensor, diag: bool) -> Tensor:
     """log N(x_b | mean_k, var_k) + log w_k, [*, B, K].  gassian_mixture_model.py:86-94."""
     x, mean, var, weights = (t.double() for t in (x, mean, var, weights))

@@ -210,6 +210,23 @@ def case_gmm(only_soft=None):
         np.savez(os.path.join(HERE, "gmm_full_soft.npz"), src=npy(src), tgt=npy(tgt), probe=npy(probe[:12]), batch=150, **out)
 
 
+def case_barycenter():
+    """gaussian_barycenter (w2_utils.py:325-385): closed form for variances, the Alvarez-Esteban fixed point for full
+    covariances (the fixed point does not depend on the randomly drawn start, so n_iter = 100 pins it)."""
+    g = torch.Generator().manual_seed(808)
+    d, n = 8, 4
+    mean = torch.randn(2, n, d, generator=g, dtype=torch.double)
+    cov = spd(g, 2, n, d, kappa=25.0) * (1.0 + torch.arange(n, dtype=torch.double).view(1, n, 1, 1))
+    var = torch.rand(2, n, d, generator=g, dtype=torch.double) + 0.1
+    w = torch.rand(2, n, generator=g, dtype=torch.double) + 0.05
+    w = w / w.sum(-1, keepdim=True)
+    torch.manual_seed(31)
+    mb, cb = ref_w2.gaussian_barycenter(mean, cov, w, diag=False, n_iter=100)
+    mbd, vbd = ref_w2.gaussian_barycenter(mean, var, w, diag=True)
+    np.savez(os.path.join(HERE, "barycenter.npz"), mean=npy(mean), cov=npy(cov), var=npy(var), w=npy(w),
+             mean_b=npy(mb), cov_b=npy(cb), mean_b_diag=npy(mbd), var_b_diag=npy(vbd))
+
+
 def case_discrete():
     """DiscreteTransport end to end: streaming k-means codebooks, inverse-distance cost, Sinkhorn plan,
     argmax / mean routing (discrete_transport.py:27-98, codebook_model.py:122-214)."""
@@ -275,6 +292,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gmm":      # only the fixtures added later (the others stay byte-identical)
         case_gmm()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "barycenter":
+        case_barycenter()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "discrete":
         case_discrete()
         sys.exit(0)
@@ -288,6 +308,7 @@ if __name__ == "__main__":
     case_gmm()
     case_operator_variants()
     case_discrete()
+    case_barycenter()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

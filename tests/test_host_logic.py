@@ -284,3 +284,17 @@ def test_discrete_transport_against_reference_golden(api, golden, kind):
     close(cost, g[f"cost_{kind}"], rtol=1e-7)
     close(op.transport_matrix, g[f"plan_{kind}"], rtol=1e-6, atol=1e-10)
     assert moved.dtype == torch.float32 and torch.allclose(moved, T(g[f"moved_{kind}"]), rtol=1e-5, atol=1e-6)
+
+
+def check_barycenter(api, g, dev, tol):
+    mean, cov, var, w = (T(g[k]).to(dev) for k in ("mean", "cov", "var", "w"))
+    torch.manual_seed(31)
+    mb, cb = api.gaussian_barycenter(mean, cov, w, diag=False, n_iter=100)
+    assert ((mb.cpu() - T(g["mean_b"])).norm() / T(g["mean_b"]).norm()).item() < 1e-12
+    assert ((cb.cpu() - T(g["cov_b"])).norm() / T(g["cov_b"]).norm()).item() < tol
+    mb, vb = api.gaussian_barycenter(mean, var, w, diag=True)
+    close(mb.cpu(), g["mean_b_diag"]); close(vb.cpu(), g["var_b_diag"])
+
+
+def test_gaussian_barycenter_against_reference_golden(api, golden):
+    check_barycenter(api, golden("barycenter"), "cpu", 1e-8)

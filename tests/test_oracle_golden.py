@@ -138,3 +138,13 @@ def test_discrete_transport_on_fitted_codebooks(golden):
     plan = O.sinkhorn_log(w_s, w_t, cost, reg=0.05, max_iter=300, threshold=1e-9)
     close(plan, g["plan_argmax"], rtol=1e-8, atol=1e-12)
     close((cost * plan).sum(), g["cost_argmax"], rtol=1e-9)
+
+
+def test_gaussian_barycenter(golden):
+    g = golden("barycenter")
+    mean, cov, var, w = (T(g[k]) for k in ("mean", "cov", "var", "w"))
+    for start in (0, 3):                                  # the fixed point does not depend on the start
+        mb, cb = O.gaussian_barycenter(mean, cov, w, diag=False, n_iter=100, start=start)
+        close(mb, g["mean_b"]); close(cb, g["cov_b"], rtol=1e-8, atol=1e-10)
+    mb, vb = O.gaussian_barycenter(mean, var, w, diag=True)
+    close(mb, g["mean_b_diag"]); close(vb, g["var_b_diag"])

@@ -77,3 +77,17 @@ def test_streaming_statistics_equal_one_shot():
     assert ((cov - cov_all).norm() / cov_all.norm()).item() < EPS
     ridge = 1e-8 * torch.eye(d, dtype=torch.double)
     assert O.w2_gaussian(mean_all, mean, cov_all + ridge, cov + ridge).abs().item() < EPS ** 0.5
+
+
+def test_gaussian_barycenter_of_identical_components_is_the_component():
+    """tests/test_w2_utils.py:85-104"""
+    g = torch.Generator().manual_seed(6)
+    mean, cov = rand_mean_cov(g, (2, 1), DIM)
+    mean, cov = mean.repeat(1, 3, 1), cov.repeat(1, 3, 1, 1)
+    var = torch.diagonal(cov, dim1=-1, dim2=-2)
+    w = torch.randn(2, 3, generator=g, dtype=torch.double).abs()
+    w = w / w.sum(-1, keepdim=True)
+    mb, vb = O.gaussian_barycenter(mean, var, w, diag=True)
+    assert torch.allclose(mb, mean[:, 0]) and torch.allclose(vb, var[:, 0])
+    mb, cb = O.gaussian_barycenter(mean, cov, w, diag=False)
+    assert torch.allclose(mb, mean[:, 0]) and torch.allclose(cb, cov[:, 0], atol=1e-7)
