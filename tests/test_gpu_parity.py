@@ -569,3 +569,9 @@ def test_golden_discrete_transport(api, golden, kind):
     assert rel(cost, g[f"cost_{kind}"]) < TOL_SINKHORN
     assert np.abs(op.transport_matrix.cpu().numpy() - g[f"plan_{kind}"]).max() < TOL_SINKHORN
     assert moved.is_cuda and moved.dtype == torch.float32 and rel(moved, g[f"moved_{kind}"]) < TOL_MATFUN
+
+
+def test_golden_gaussian_barycenter(api, golden):
+    """Alvarez-Esteban fixed point (100 iterations of batched Newton-Schulz roots) and the diagonal closed form"""
+    from tests.test_host_logic import check_barycenter
+    check_barycenter(api, golden("barycenter"), "cuda", TOL_MATFUN)
