@@ -364,3 +364,48 @@ def synthetic_gaussian(n: int, d: int, seed: int, kappa: float = 1e2, dtype=torc
     z = torch.randn(n, d, generator=g, dtype=torch.double)
     x = mu + z @ half.T
     return x.to(dtype), mu, (half @ half.T)
+
+
+# ---------------------------------------------------------------------------------------------------
+# FID accumulation + score (metrics/fid.py:99-130)
+# ---------------------------------------------------------------------------------------------------
+
+def frechet_distance(mean_1: Tensor, cov_1: Tensor, mean_2: Tensor, cov_2: Tensor) -> Tensor:
+    """`_compute_fid` of torchmetrics (third-party, `torchmetrics>=0.9.2` UNPINNED in the reference's requirements.txt:4,
+    absent from /root/reference and from this image; call site metrics/fid.py:130).  Published algorithm
+    (torchmetrics/image/fid.py, v1.x): |m1-m2|^2 + tr(C1) + tr(C2) - 2 * sum(sqrt(eigvals(C1 C2))).real.
+    C1 C2 is similar to the symmetric PSD matrix C1^1/2 C2 C1^1/2, whose eigenvalues are evaluated here with `eigh`
+    (negative round-off eigenvalues contribute nothing, as `.sqrt().real` drops them there)."""
+    root = spectral_apply(cov_1, lambda lam: torch.sqrt(lam.clamp_min(0.0)))
+    mid = root @ cov_2 @ root
+    lam = torch.linalg.eigvalsh((mid + mid.transpose(-1, -2)) / 2).clamp_min(0.0)
+    diff = mean_1 - mean_2
+    return (diff * diff).sum(-1) + torch.diagonal(cov_1, dim1=-2, dim2=-1).sum(-1) \
+        + torch.diagonal(cov_2, dim1=-2, dim2=-1).sum(-1) - 2.0 * lam.sqrt().sum(-1)
+
+
+class FidStats:
+    """States and update rule of the reference's `FrechetInceptionDistance` (metrics/fid.py:88-122): fp64 feature sums
+    and `features.T @ features`, int64 counts of shape [1]; NB `generated` feeds the `real_*` states (:113-117)."""
+
+    def __init__(self, feature_size: int):
+        self.sum = {k: torch.zeros(feature_size, dtype=torch.double) for k in ("real", "fake")}
+        self.corr = {k: torch.zeros(feature_size, feature_size, dtype=torch.double) for k in ("real", "fake")}
+        self.n = {k: torch.zeros(1, dtype=torch.long) for k in ("real", "fake")}
+
+    def update(self, generated_features: Optional[Tensor] = None, sample_features: Optional[Tensor] = None) -> None:
+        for kind, feats in (("real", generated_features), ("fake", sample_features)):
+            if feats is None:
+                continue
+            f = feats.double().reshape(feats.shape[0], -1)          # fid.py:102
+            self.sum[kind] += f.sum(dim=0)                          # fid.py:103
+            self.corr[kind] += f.T @ f                              # fid.py:104
+            self.n[kind] += feats.shape[0]
+
+    def compute(self) -> Tensor:
+        """fid.py:124-130"""
+        if self.n["fake"] < 1e3 or self.n["real"] < 1000:
+            return torch.ones(1) * float("inf")
+        m_r, c_r = mean_cov(self.sum["real"], self.corr["real"], self.n["real"].double())
+        m_f, c_f = mean_cov(self.sum["fake"], self.corr["fake"], self.n["fake"].double())
+        return frechet_distance(m_r, c_r, m_f, c_f)

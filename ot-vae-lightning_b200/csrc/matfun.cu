@@ -25,6 +25,11 @@ constexpr int NS_F32_OPERATOR_ITERS = 20;
 constexpr double NS_F32_RICCATI_TOL = 2e-4;   // ||T Cs T - Ct||_F / ||Ct||_F accepted from the fp32 engine
 constexpr int64_t NS_SMALL_DIM = 64;          // fp64 data with dim <= 64: the DFMA engine is as fast and exact
 constexpr int NS_F32_IROOT_ITERS = 18;
+// The fp64 engine adds NS_F64_REL_RIDGE * ||A||_F to the diagonal: ten fp64 ulps of the norm, below the iteration's own
+// round-off for any PD input, but it turns an exactly singular SPSD matrix (a rank-deficient covariance, the 'spsd'
+// arguments of the reference: w2_utils.py:73-76, 423-426; FID with fewer samples than features) into one the iteration
+// converges on in ~48 steps with a root error of sqrt(1e-15) - the reference's eigh-based sqrtm is finite there too.
+constexpr double NS_F64_REL_RIDGE = 1e-15;
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
   v = warp_sum(v);
@@ -55,17 +60,24 @@ __global__ void frob_sq_kernel(const void* a, int dt, int64_t dim, double ridge,
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(&c[l], acc);
 }
-__global__ void sqrt_inplace_kernel(double* c, int64_t n) {
+// c[l] holds ||A + ridge I||_F^2 on entry.  ridge_l[l] = ridge + rel * c0,  c[l] <- c0 * (1 + rel * sqrt(dim)) with
+// c0 = sqrt(c[l])  (an upper bound of ||A + ridge_l I||_F)
+__global__ void ns_ridge_kernel(double* c, int64_t L, double ridge, double rel, double sqrt_dim, double* ridge_l) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e < n) c[e] = sqrt(c[e]);
+  if (e < L) {
+    const double c0 = sqrt(c[e]);
+    ridge_l[e] = ridge + rel * c0;
+    c[e] = c0 > 0 ? c0 * (1.0 + rel * sqrt_dim) : 1.0;   // the zero matrix: Y stays 0, the solve reports not-converged
+  }
 }
-static int frob_norm(const void* a, int dt, int64_t L, int64_t dim, double ridge, double* c, cudaStream_t st) {
+static int frob_norm(const void* a, int dt, int64_t L, int64_t dim, double ridge, double rel, double* c, double* ridge_l,
+                     cudaStream_t st) {
   OTK_CUDA(cudaMemsetAsync(c, 0, (size_t)L * 8, st));
   int64_t bx = ceil_div(dim * dim, 256 * 8);
   if (bx > 256) bx = 256;
   if (bx < 1) bx = 1;
   frob_sq_kernel<<<dim3((unsigned)bx, (unsigned)L), 256, 0, st>>>(a, dt, dim, ridge, c);
-  sqrt_inplace_kernel<<<(unsigned)ceil_div(L, 256), 256, 0, st>>>(c, L);
+  ns_ridge_kernel<<<(unsigned)ceil_div(L, 256), 256, 0, st>>>(c, L, ridge, rel, sqrt((double)dim), ridge_l);
   count_launch(1);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
@@ -73,12 +85,12 @@ static int frob_norm(const void* a, int dt, int64_t L, int64_t dim, double ridge
 
 // Y = (A + ridge I)/c, Z = I
 template <typename W>
-__global__ void ns_init_kernel(const void* a, int dt, int64_t L, int64_t dim, double ridge, const double* c, W* Y, W* Z) {
+__global__ void ns_init_kernel(const void* a, int dt, int64_t L, int64_t dim, const double* ridge_l, const double* c, W* Y, W* Z) {
   const int64_t total = L * dim * dim;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t l = e / (dim * dim), r = e % (dim * dim);
     bool diag = (r / dim == r % dim);
-    double v = load_real(a, e, dt) + (diag ? ridge : 0.0);
+    double v = load_real(a, e, dt) + (diag ? ridge_l[l] : 0.0);
     Y[e] = (W)(v / c[l]);
     Z[e] = diag ? W(1) : W(0);
   }
@@ -180,10 +192,11 @@ struct NsWork {
   W *Yh[2], *Yl[2], *Zh[2], *Zl[2], *Th, *Tl;
   W* scratch;         // 4 planes: operand splits for the products outside the iteration
   double *c, *resid;  // c [L]; resid [NS_MAX_ITERS][L]
+  double* ridge_l;    // [L] diagonal shift of the current solve
   int* ctrl;          // device-side loop control (ns_ctrl_kernel)
   static constexpr int kPlanes = sizeof(W) == 4 ? 5 + 10 + 4 : 5;
   static size_t bytes(int64_t L, int64_t d) {
-    return kPlanes * align_up((size_t)L * d * d * sizeof(W), 256) + align_up((size_t)L * 8, 256) +
+    return kPlanes * align_up((size_t)L * d * d * sizeof(W), 256) + 2 * align_up((size_t)L * 8, 256) +
            align_up((size_t)NS_MAX_ITERS * L * 8, 256) + 256;
   }
   void carve(Arena& ar, int64_t L, int64_t d) {
@@ -198,6 +211,7 @@ struct NsWork {
       scratch = nullptr;
     }
     c = ar.take<double>((size_t)L);
+    ridge_l = ar.take<double>((size_t)L);
     resid = ar.take<double>((size_t)NS_MAX_ITERS * L);
     ctrl = ar.take<int>(16);
   }
@@ -208,13 +222,13 @@ static size_t ns_work_bytes(int64_t L, int64_t d) {
 }
 
 // plane-mode helpers (fp32 engine on tcgen05)
-__global__ void ns_init_planes_kernel(const void* a, int dt, int64_t L, int64_t dim, double ridge, const double* c, float* Yh,
+__global__ void ns_init_planes_kernel(const void* a, int dt, int64_t L, int64_t dim, const double* ridge_l, const double* c, float* Yh,
                                       float* Yl, float* Zh, float* Zl) {
   const int64_t total = L * dim * dim;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t l = e / (dim * dim), r = e % (dim * dim);
     bool diag = (r / dim == r % dim);
-    float v = (float)((load_real(a, e, dt) + (diag ? ridge : 0.0)) / c[l]);
+    float v = (float)((load_real(a, e, dt) + (diag ? ridge_l[l] : 0.0)) / c[l]);
     float h, lo;
     ptx::split_tf32(v, h, lo);
     Yh[e] = h; Yl[e] = lo;
@@ -318,11 +332,11 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
   const bool f32 = sizeof(W) == 4;
   bool planes = false;
   if constexpr (sizeof(W) == 4) planes = ns_planes_eligible(d) && L <= 65535;
-  OTK_TRY(frob_norm(a, dt, L, d, ridge, w.c, st));
+  OTK_TRY(frob_norm(a, dt, L, d, ridge, f32 ? 0.0 : NS_F64_REL_RIDGE, w.c, w.ridge_l, st));
   if constexpr (sizeof(W) == 4) {
-    if (planes) ns_init_planes_kernel<<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, ridge, w.c, w.Yh[0], w.Yl[0], w.Zh[0], w.Zl[0]);
+    if (planes) ns_init_planes_kernel<<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, w.ridge_l, w.c, w.Yh[0], w.Yl[0], w.Zh[0], w.Zl[0]);
   }
-  if (!planes) ns_init_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, ridge, w.c, w.Y[0], w.Z[0]);
+  if (!planes) ns_init_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(a, dt, L, d, w.ridge_l, w.c, w.Y[0], w.Z[0]);
   OTK_LAUNCH_CHECK();
   OTK_CUDA(cudaMemsetAsync(w.resid, 0, (size_t)NS_MAX_ITERS * L * 8, st));
   const bool adaptive = iters <= 0;

@@ -73,7 +73,10 @@ def mean_cov(run_sum: Tensor, run_cov: Tensor, n_obs: Tensor) -> Tuple[Tensor, T
     s, c = _dev_tensor(run_sum, dev, dt), _dev_tensor(run_cov, dev, dt)
     d = s.shape[-1]
     lead, L = _lead(s.shape, 1)
-    n = _dev_tensor(n_obs, dev, torch.float64).expand(lead).contiguous()
+    n = _dev_tensor(n_obs, dev, torch.float64)
+    # one count per leading index; a count of shape [1] next to a single [d] / [d, d] pair (the FID states,
+    # reference metrics/fid.py:96-97,127-128) broadcasts the way the reference's `unsqueeze_like` division does
+    n = (n.reshape(lead) if n.numel() == L else n.expand(lead)).contiguous()
     mean, cov = torch.empty_like(s), torch.empty_like(c)
     with torch.cuda.device(dev):
         st = N.load().otk_mean_cov(N.ptr(s), N.ptr(c), N.ptr(n), N.F64, L, d, N.ptr(mean), N.ptr(cov),

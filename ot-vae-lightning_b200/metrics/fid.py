@@ -4,7 +4,10 @@ metrics/fid.py:27-131: same state names, `update(generated=, samples=)` / `compu
 In scope: the fp64 running sum / correlation of the features (`features.T @ features`, reference
 :103-104,115-121) - the same libotk statistics kernel as `GaussianModel` - and `mean_cov`.  Out of scope: the
 Inception network (torchmetrics' `NoTrainInceptionV3`, a third-party dependency absent from this image) - pass any
-feature extractor as `net`; the final score is the Gelbrich distance, evaluated with `otk_w2_gaussian`.
+feature extractor as `net`.  The final score (torchmetrics' `_compute_fid`, fid.py:130:
+|m1-m2|^2 + tr C1 + tr C2 - 2 sum sqrt(eig(C1 C2))) is the Gelbrich distance and is evaluated on the device by
+`otk_w2_gaussian`; covariances of fewer observations than features are exactly singular, which the fp64 Newton-Schulz
+engine handles through its relative ridge (csrc/matfun.cu, NS_F64_REL_RIDGE).
 """
 from __future__ import annotations
 
@@ -84,9 +87,9 @@ class FrechetInceptionDistance(nn.Module):
         n_real, n_fake = self._synced(self.num_real_obs), self._synced(self.num_fake_obs)
         if n_fake < 1e3 or n_real < 1000:
             return torch.ones(1) * float("inf")
-        r_mean, r_cov = mean_cov(self._synced(self.real_sum), self._synced(self.real_correlation), n_real.double())
-        f_mean, f_cov = mean_cov(self._synced(self.fake_sum), self._synced(self.fake_correlation), n_fake.double())
-        return K.w2_gaussian(r_mean.squeeze(0) if r_mean.dim() > 1 else r_mean, f_mean, r_cov, f_cov).reshape(())
+        r_mean, r_cov = mean_cov(self._synced(self.real_sum), self._synced(self.real_correlation), n_real)
+        f_mean, f_cov = mean_cov(self._synced(self.fake_sum), self._synced(self.fake_correlation), n_fake)
+        return K.w2_gaussian(r_mean, f_mean, r_cov, f_cov).reshape(())
 
     def forward(self, *args, **kwargs):
         self.update(*args, **kwargs)

@@ -31,6 +31,9 @@ def stream_update(op, source: Optional[Tensor] = None, target: Optional[Tensor] 
     copy = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
     rings = {k: _Ring(min(chunk, n), d, dev) for k, t in (("s", source), ("t", target)) if t is not None}
+    # the rings come from the caching allocator on `main`: blocks it hands back may still be read by kernels queued on
+    # `main` (e.g. the previous call's last update), so the copy stream may not touch them before `main` gets here
+    copy.wait_stream(main)
     host = dict(s=source, t=target)
     n_chunks = (n + chunk - 1) // chunk
 
@@ -57,10 +60,12 @@ def stream_update(op, source: Optional[Tensor] = None, target: Optional[Tensor] 
         op.update(**kw)
         for ring in rings.values():
             ring.freed[slot].record(main)
+    main.wait_stream(copy)      # every side-stream access to the rings is ordered before `main` frees them
 
 
 def stream_transport(op, inputs: Tensor, out: Tensor, chunk: int = 1 << 16, device: Optional[torch.device] = None) -> Tensor:
-    """out[...] = op.transport(inputs) for host tensors [N, d]; H2D / kernels / D2H overlapped."""
+    """out[...] = op.transport(inputs) for host tensors [N, d]; H2D / kernels / D2H overlapped.  Returns after the last
+    D2H copy has landed in `out` (the D2H stream is synchronised), so the host may read it at once."""
     dev = device or next(op.buffers()).device
     n, d = inputs.shape
     h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -70,6 +75,8 @@ def stream_transport(op, inputs: Tensor, out: Tensor, chunk: int = 1 << 16, devi
     done = [torch.cuda.Event() for _ in range(2)]
     stored = [torch.cuda.Event() for _ in range(2)]
     n_chunks = (n + chunk - 1) // chunk
+    h2d.wait_stream(main)       # see stream_update: the ring blocks may still be in use on `main`
+    d2h.wait_stream(main)
 
     def launch_copy(i):
         slot = i % 2
@@ -96,5 +103,7 @@ def stream_transport(op, inputs: Tensor, out: Tensor, chunk: int = 1 << 16, devi
             d2h.wait_event(done[slot])
             out[lo:hi].copy_(outs[slot], non_blocking=True)
             stored[slot].record(d2h)
+    main.wait_stream(h2d)
     main.wait_stream(d2h)
+    d2h.synchronize()           # `out` is host memory: the caller reads it without any stream in between
     return out

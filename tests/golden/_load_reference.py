@@ -68,6 +68,39 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
             module.apply_to_collection = lambda data, dtype, fn, *a, **k: fn(data)
         if name == "retrying":
             module.retry = lambda *a, **k: (lambda f: f)
+        if name == "torchmetrics.metric":
+            module.Metric = _metric_base()
+        if name == "torchmetrics.image.fid":
+            import torch
+
+            class NoTrainInceptionV3(torch.nn.Module):        # never instantiated: the fixtures pass their own `net`
+                pass
+
+            def _compute_fid(mu1, sigma1, mu2, sigma2):
+                """torchmetrics (third-party, unpinned `torchmetrics>=0.9.2`, absent here): the published v1.x body of
+                torchmetrics/image/fid.py::_compute_fid, restated - the only non-reference code on the FID fixture path."""
+                a = (mu1 - mu2).square().sum(dim=-1)
+                b = sigma1.trace() + sigma2.trace()
+                c = torch.linalg.eigvals(sigma1 @ sigma2).sqrt().real.sum(dim=-1)
+                return a + b - 2 * c
+
+            module.NoTrainInceptionV3 = NoTrainInceptionV3
+            module._compute_fid = _compute_fid
+
+
+def _metric_base():
+    """The part of torchmetrics' `Metric` the reference FID class relies on (metrics/fid.py:66-97): an nn.Module whose
+    `add_state` registers the default tensor as an attribute that `update` accumulates into."""
+    import torch
+
+    class Metric(torch.nn.Module):
+        def __init__(self, **kwargs):
+            super().__init__()
+
+        def add_state(self, name, default, dist_reduce_fx=None):
+            self.register_buffer(name, default.clone())
+
+    return Metric
 
 
 def load_reference():

@@ -287,8 +287,47 @@ def case_operator_variants():
     np.savez(os.path.join(HERE, "operator_variants.npz"), **out)
 
 
+def case_fid():
+    """The UNMODIFIED reference `FrechetInceptionDistance` (metrics/fid.py:27-131) behind the torchmetrics stub of
+    `_load_reference.py`, fed by the stand-in feature net / images of tests/fid_stub.py.  The 2048 x 2048 correlations are
+    too large to commit: the fixture keeps the score, the sums, the counts, the traces and a strided 32 x 32 sample."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from fid_stub import CASES, FeatureNet, images
+    from ot_vae_lightning.metrics.fid import FrechetInceptionDistance
+    out = {}
+    for name, (fsize, n_gen, n_smp, batch) in CASES.items():
+        fid = FrechetInceptionDistance(net=FeatureNet(fsize), feature_size=fsize)
+        gen, smp = images(11, n_gen), images(12, n_smp, gain=0.85, offset=0.05)
+        for lo in range(0, n_gen, batch):
+            fid.update(generated=gen[lo:lo + batch])
+        for lo in range(0, n_smp, batch):
+            fid.update(samples=smp[lo:lo + batch])
+        step = max(1, fsize // 32)
+        out.update({f"{name}_score": npy(fid.compute()), f"{name}_real_sum": npy(fid.real_sum),
+                    f"{name}_fake_sum": npy(fid.fake_sum), f"{name}_num_real": npy(fid.num_real_obs),
+                    f"{name}_num_fake": npy(fid.num_fake_obs),
+                    f"{name}_real_trace": npy(fid.real_correlation.trace()),
+                    f"{name}_fake_trace": npy(fid.fake_correlation.trace()),
+                    f"{name}_real_corr_sample": npy(fid.real_correlation[::step, ::step]),
+                    f"{name}_fake_corr_sample": npy(fid.fake_correlation[::step, ::step])})
+        print(name, "FID", float(fid.compute()))
+    few = FrechetInceptionDistance(net=FeatureNet(64), feature_size=64)
+    few.update(generated=images(13, 999), samples=images(14, 1200))
+    out["few_score"] = npy(few.compute())                      # < 1000 observations: +inf (fid.py:126)
+    np.savez(os.path.join(HERE, "fid.npz"), **out)
+
+
+# NOTE (probed here, seed 909, d=10, rank-4 `low @ low.T`): exactly singular 'spsd' arguments cannot be pinned - the
+# reference's `sqrtm` returns NaN for them (eigh yields eigenvalues like -1.8e-15 and matrix_utils.py:37-46 takes their
+# sqrt), and so does `compute_transport_operators(cs, ct_low, stochastic=False, make_pd=True/False)`.  The GPU tests
+# compare against the oracle with those eigenvalues clamped at 0 (tests/test_gpu_parity.py::test_singular_spsd_*).
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fid":
+        case_fid()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gmm":      # only the fixtures added later (the others stay byte-identical)
         case_gmm()
         sys.exit(0)
@@ -309,6 +348,7 @@ if __name__ == "__main__":
     case_operator_variants()
     case_discrete()
     case_barycenter()
+    case_fid()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

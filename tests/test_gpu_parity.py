@@ -575,3 +575,161 @@ def test_golden_gaussian_barycenter(api, golden):
     """Alvarez-Esteban fixed point (100 iterations of batched Newton-Schulz roots) and the diagonal closed form"""
     from tests.test_host_logic import check_barycenter
     check_barycenter(api, golden("barycenter"), "cuda", TOL_MATFUN)
+
+
+# ------------------------------------------------------------------------------------------------- FID (SURVEY a2)
+
+def _fid_features(name):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fid_stub import CASES, FeatureNet, images
+    fsize, n_gen, n_smp, batch = CASES[name]
+    net = FeatureNet(fsize)
+    gen, smp = images(11, n_gen), images(12, n_smp, gain=0.85, offset=0.05)
+    return fsize, batch, net, gen, smp
+
+
+@pytest.mark.parametrize("name", ["f64", "f2048_deficient", "f2048_full"])
+def test_golden_fid_statistics_and_score(golden, oracle, name):
+    """`FrechetInceptionDistance` (reference metrics/fid.py:99-130) at feature_size 64 / 2048, with fewer and with more
+    observations than features, against the golden of the unmodified reference class and against the oracle.  The
+    features are computed once on the CPU (bit-identical to the fixture's) and fed through an identity `net`."""
+    from ot_vae_lightning_b200.metrics.fid import FrechetInceptionDistance
+    g = golden("fid")
+    fsize, batch, net, gen, smp = _fid_features(name)
+    fid = FrechetInceptionDistance(net=torch.nn.Identity(), feature_size=fsize, device="cuda")
+    st = oracle.FidStats(fsize)
+    for lo in range(0, gen.shape[0], batch):
+        f = net(gen[lo:lo + batch])
+        fid.update(generated=f.cuda())
+        st.update(generated_features=f)
+    for lo in range(0, smp.shape[0], batch):
+        f = net(smp[lo:lo + batch])
+        fid.update(samples=f.cuda())
+        st.update(sample_features=f)
+    assert fid.num_real_obs.cpu().tolist() == g[f"{name}_num_real"].tolist() and fid.num_real_obs.dtype == torch.long
+    assert fid.real_sum.dtype == torch.double and fid.real_correlation.shape == (fsize, fsize)
+    assert rel(fid.real_sum, g[f"{name}_real_sum"]) < 1e-6 and rel(fid.fake_sum, g[f"{name}_fake_sum"]) < 1e-6
+    step = max(1, fsize // 32)
+    assert rel(fid.real_correlation[::step, ::step], g[f"{name}_real_corr_sample"]) < 1e-5
+    assert rel(fid.fake_correlation, st.corr["fake"]) < 1e-5
+    assert abs(float(fid.fake_correlation.trace()) - float(g[f"{name}_fake_trace"])) < 1e-6 * float(g[f"{name}_fake_trace"])
+    score = fid.compute()
+    assert score.shape == () and score.dtype == torch.double
+    want, want_oracle = float(g[f"{name}_score"]), float(st.compute())
+    assert abs(float(score) - want) < TOL_MATFUN * want and abs(float(score) - want_oracle) < TOL_MATFUN * want_oracle
+
+
+def test_fid_with_a_device_feature_net_and_too_few_observations(golden):
+    """the `net` forward on the GPU (grey images are replicated to 3 channels, fid.py:100) and the < 1000 rule (:126)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fid_stub import FeatureNet, images
+    from ot_vae_lightning_b200.metrics.fid import FrechetInceptionDistance
+    g = golden("fid")
+    fid = FrechetInceptionDistance(net=FeatureNet(64).cuda(), feature_size=64, device="cuda")
+    gen, smp = images(11, 1100), images(12, 1200, gain=0.85, offset=0.05)
+    for lo in range(0, 1100, 275):
+        fid.update(generated=gen[lo:lo + 275].cuda())
+    fid.update(samples=smp[:999].cuda())
+    assert torch.isinf(fid.compute()).all()
+    fid.update(samples=smp[999:].cuda())
+    assert abs(float(fid.compute()) - float(g["f64_score"])) < TOL_MATFUN * float(g["f64_score"])
+    fid.reset()
+    assert int(fid.num_real_obs) == 0 and float(fid.real_correlation.abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------- a6 at d >= 128
+
+def _spectrum_matrix(d, lam, seed):
+    g = torch.Generator().manual_seed(seed)
+    q, _ = torch.linalg.qr(torch.randn(d, d, generator=g, dtype=torch.double))
+    a = (q * lam) @ q.T
+    return (a + a.T) / 2
+
+
+@pytest.mark.parametrize("d", [128, 512, 1024])
+def test_min_eig_is_exact_beyond_the_krylov_cap(api, d):
+    """min_eig / is_pd / make_psd (reference matrix_utils.py:91-142) on indefinite, near-singular (lambda_min = +-1e-7)
+    and rank-deficient matrices at d >= 128, against LAPACK's eigvalsh: the sign decides `is_pd`, and the repaired matrix
+    must be positive definite (Cholesky succeeds), which an upper bound on lambda_min does not guarantee."""
+    body = torch.logspace(-3, 0, d - 1, dtype=torch.double)
+    cases = {
+        "indefinite": torch.cat([torch.tensor([-0.37], dtype=torch.double), body]),
+        "barely_negative": torch.cat([torch.tensor([-1e-7], dtype=torch.double), body]),
+        "barely_positive": torch.cat([torch.tensor([1e-7], dtype=torch.double), body]),
+        "two_negative_close": torch.cat([torch.tensor([-2e-7, -1e-7], dtype=torch.double), body[1:]]),
+    }
+    mats = torch.stack([_spectrum_matrix(d, lam, 70 + i) for i, lam in enumerate(cases.values())])
+    g = torch.Generator().manual_seed(5)
+    low = torch.randn(d, d // 4, generator=g, dtype=torch.double)
+    deficient = low @ low.T / d                                         # rank d/4: a cluster of ~0 eigenvalues
+    mats = torch.cat([mats, deficient[None]])
+    want = torch.linalg.eigvalsh(mats).amin(-1)
+    scale = mats.flatten(1).norm(dim=1)
+    got = api.min_eig(mats.cuda()).cpu()
+    assert got.dtype == torch.double
+    assert float(((got - want).abs() / scale).max()) < 1e-11, (got, want)
+    assert api.is_pd(mats[:4].cuda()).cpu().tolist() == (want[:4] > 0).tolist() == [False, False, True, False]
+    fixed, shift = api.make_psd(mats.cuda(), strict=True, return_correction=True)
+    assert float((shift.cpu() - (want.clamp(max=0).abs() + 1e-8)).abs().max()) < 1e-11 * float(scale.max())
+    _, info = torch.linalg.cholesky_ex(fixed.cpu())
+    assert info.tolist() == [0] * mats.shape[0]
+    # float32 input follows the same path (cast to fp64 inside the kernel)
+    assert abs(float(api.min_eig(mats[0].float().cuda())) + 0.37) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------- singular 'spsd' arguments
+
+@pytest.mark.parametrize("d,rank", [(10, 4), (256, 100), (512, 500)])
+def test_singular_spsd_sqrtm_and_target_covariance(api, oracle, d, rank):
+    """Exactly singular SPSD input (a covariance of fewer samples than dimensions).  The reference is NaN there whenever
+    `eigh` returns a round-off-negative eigenvalue (probed: tests/golden/make_golden.py note); the oracle clamps those at
+    0, and the CUDA path must return that finite root / operator (fp64 Newton-Schulz with a 1e-15 relative ridge)."""
+    g = torch.Generator().manual_seed(909 + d)
+    low = torch.randn(2, d, rank, generator=g, dtype=torch.double)
+    ct_low = low @ low.transpose(-1, -2) / rank
+    clamp_sqrt = lambda lam: lam.clamp_min(0).sqrt()
+    root = api.sqrtm(ct_low.cuda())
+    assert bool(torch.isfinite(root).all()) and rel(root, oracle.spectral_apply(ct_low, clamp_sqrt)) < TOL_MATFUN
+    assert rel(root @ root, ct_low) < TOL_MATFUN
+    cs = torch.stack([_spectrum_matrix(d, torch.logspace(-1.5, 0, d, dtype=torch.double), 3 + i) for i in range(2)])
+    Top, Cw = api.compute_transport_operators(cs.cuda(), ct_low.cuda(), stochastic=False, diag=False, make_pd=True)
+    s, si = oracle.sqrtm(cs), oracle.invsqrtm(cs + 1e-8 * torch.eye(d, dtype=torch.double))
+    mid = s @ ct_low @ s
+    want = si @ oracle.spectral_apply((mid + mid.transpose(-1, -2)) / 2, clamp_sqrt) @ si
+    assert rel(Top, want) < TOL_MATFUN and float(Cw.abs().max()) == 0.0
+    assert rel(Top @ cs.cuda() @ Top, ct_low) < 5 * TOL_MATFUN
+
+
+# ------------------------------------------------------------------------------------------------- cfg4 at full size
+
+def test_cfg4_conditional_transport_10x1024_vs_oracle(api, oracle):
+    """BASELINE.json configs[3]: `GaussianTransport(10, 1024)` (one operator per class, transport_callback.py:388-453),
+    4 d samples per class, against the oracle pipeline (update -> fit -> W2 -> T -> transport) at full width."""
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    L, d, n, bs = 10, 1024, 4096, 1024
+    src = torch.stack([gaussian_latents(n, d, seed=120 + k, device="cuda") for k in range(L)])
+    tgt = torch.stack([gaussian_latents(n, d, seed=140 + k, device="cuda", shift=1.0, scale=0.8) for k in range(L)])
+    op = api.GaussianTransport(L, d, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double),
+                               target_cfg=dict(dtype=torch.double)).cuda()
+    for lo in range(0, n, bs):
+        op.update(src[:, lo:lo + bs], tgt[:, lo:lo + bs])
+    w2 = op.compute()
+    moved = op.transport(src[:, :512])
+    s_st, t_st = oracle.GaussianStats(L, d), oracle.GaussianStats(L, d)
+    for lo in range(0, n, bs):
+        s_st.update(src[:, lo:lo + bs].cpu())
+        t_st.update(tgt[:, lo:lo + bs].cpu())
+    (mean_s, cov_s), (mean_t, cov_t) = s_st.fit(), t_st.fit()
+    want_w2 = oracle.w2_gaussian(mean_s, mean_t, cov_s, cov_t)
+    want_T, _ = oracle.transport_operator_full(cov_s, cov_t, 0.0)
+    # oracle.apply_transport broadcasts one d x d operator per latent (the reference's bmm, w2_utils.py:515-520): the same
+    # product written as a GEMM per class, so that the 10 x 512 x 1024 x 1024 broadcast is never materialised
+    want_moved = (src[:, :512].cpu().double() - mean_s[:, None]) @ want_T.transpose(-1, -2) + mean_t[:, None]
+    assert w2.shape == (L,) and rel(w2, want_w2) < TOL_MATFUN
+    assert rel(op.source_model.mean, mean_s) < TOL_STATS and rel(op.source_model.cov, cov_s) < TOL_STATS
+    assert rel(op.transport_operator, want_T) < TOL_MATFUN
+    assert moved.dtype == torch.float32 and rel(moved, want_moved) < TOL_MATFUN

@@ -148,3 +148,38 @@ def test_gaussian_barycenter(golden):
         close(mb, g["mean_b"]); close(cb, g["cov_b"], rtol=1e-8, atol=1e-10)
     mb, vb = O.gaussian_barycenter(mean, var, w, diag=True)
     close(mb, g["mean_b_diag"]); close(vb, g["var_b_diag"])
+
+
+def _fid_oracle_run(name):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fid_stub import CASES, FeatureNet, images
+    fsize, n_gen, n_smp, batch = CASES[name]
+    net, st = FeatureNet(fsize), O.FidStats(fsize)
+    gen, smp = images(11, n_gen), images(12, n_smp, gain=0.85, offset=0.05)
+    for lo in range(0, n_gen, batch):
+        st.update(generated_features=net(gen[lo:lo + batch]))
+    for lo in range(0, n_smp, batch):
+        st.update(sample_features=net(smp[lo:lo + batch]))
+    return st
+
+
+def test_fid_statistics_and_score(golden):
+    """metrics/fid.py:99-130 behind the torchmetrics stub (tests/golden/_load_reference.py): running sums, correlations,
+    counts and the score, at feature_size 64 and 2048 (fewer and more observations than features)."""
+    g = golden("fid")
+    for name, tol in (("f64", 1e-10), ("f2048_deficient", 2e-6), ("f2048_full", 1e-9)):
+        st = _fid_oracle_run(name)
+        close(st.sum["real"], g[f"{name}_real_sum"]); close(st.sum["fake"], g[f"{name}_fake_sum"])
+        assert st.n["real"].tolist() == g[f"{name}_num_real"].tolist() and st.n["fake"].tolist() == g[f"{name}_num_fake"].tolist()
+        step = max(1, st.corr["real"].shape[0] // 32)
+        close(st.corr["real"][::step, ::step], g[f"{name}_real_corr_sample"], rtol=1e-9, atol=1e-9)
+        close(st.corr["fake"].trace(), g[f"{name}_fake_trace"], rtol=1e-9)
+        # the singular case: sqrt(eigvals) of a non-symmetric singular product (reference side) vs eigvalsh of the
+        # symmetric form (oracle) agree to ~1e-7 relative
+        want = float(g[f"{name}_score"])
+        assert abs(float(st.compute()) - want) <= tol * abs(want), (name, float(st.compute()), want)
+    few = O.FidStats(64)
+    few.update(torch.zeros(999, 64), torch.zeros(1200, 64))
+    assert torch.isinf(few.compute()).all() and np.isinf(g["few_score"]).all()
