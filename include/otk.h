@@ -36,7 +36,7 @@ typedef enum {
   OTK_ERR_WORKSPACE = -2,        /* workspace too small                                -> ValueError          */
   OTK_ERR_CUDA = -3,             /* a CUDA runtime / driver call failed                -> RuntimeError        */
   OTK_ERR_UNSUPPORTED_DEVICE = -4, /* not an sm_100 device                             -> RuntimeError        */
-  OTK_ERR_NOT_CONVERGED = -5     /* reserved                                                                  */
+  OTK_ERR_NOT_CONVERGED = -5     /* Newton-Schulz diverged: the matrix is indefinite         -> NotConverged      */
 } otk_status;
 
 typedef enum { OTK_F32 = 0, OTK_F64 = 1 } otk_dtype;
@@ -91,8 +91,9 @@ int otk_symmetrize_shift(const void* a, const void* shift, int64_t L, int64_t di
 int otk_asymmetry(const void* a, int64_t L, int64_t dim, int dtype, double* asym, otk_stream_t stream);
 
 /* K4  smallest eigenvalue per matrix -> lam_min [L] fp64.  Replaces min_eig, ot/matrix_utils.py:91-98
- * (used by is_pd :109 and make_psd :132).  Lanczos with full re-orthogonalisation (steps <= dim,
- * default when steps<=0: min(dim, 96)) + Sturm bisection; not a full eigensolve. */
+ * (used by is_pd :109 and make_psd :132).  Lanczos with full re-orthogonalisation + Sturm multisection.
+ * steps <= 0 (default): runs until the smallest Ritz pair has converged (residual bound 1e-13 ||A||) or for `dim` steps -
+ * a complete tridiagonalisation, i.e. the exact lambda_min.  steps > 0: exactly min(steps, dim) steps (an upper bound). */
 size_t otk_min_eig_workspace_bytes(int64_t L, int64_t dim, int steps);
 int otk_min_eig(const void* a, int64_t L, int64_t dim, int dtype, int steps, double* lam_min,
                 void* workspace, size_t workspace_bytes, otk_stream_t stream);
@@ -189,6 +190,16 @@ int otk_sinkhorn_points_rowstep(const float* x_local, const float* y, int64_t n_
                                 int64_t dim, const float* a_local, const float* v, int cost_kind,
                                 double scale, double reg, int precision, int reuse_prepared,
                                 float* u_local, float* diff /* += sum|du| */, void* workspace,
+                                size_t workspace_bytes, otk_stream_t stream);
+/* Plan statistics of a row shard without the plan: pi_ij = exp(u_i + v_j - scale*cost(x_i, y_j)/reg) for the LOCAL rows.
+ *   part [4] fp64: <C,pi> over the local rows, their mass, max_i |sum_j pi_ij - a_i|, local max_j |col_partial_j - b_j|
+ *   row_marginal [n_local] (may be NULL), col_partial [M] = sum over the local rows of pi_ij.
+ * Row-sharded use (the `check` of the multi-GPU bench, SURVEY 8e "<C,pi> and column marginals need one more SUM
+ * allreduce"): SUM-reduce part[0..1] and col_partial over the ranks, MAX-reduce part[2]. */
+int otk_sinkhorn_points_summary(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
+                                const float* a_local, const float* b, const float* u_local, const float* v,
+                                int cost_kind, double scale, double reg, int precision, int reuse_prepared,
+                                double* part, float* row_marginal, float* col_partial, void* workspace,
                                 size_t workspace_bytes, otk_stream_t stream);
 /* max_ij cost(x_i, y_j) -> *out (device fp32), for the 1/max normalisation */
 int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,

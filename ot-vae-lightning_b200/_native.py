@@ -60,6 +60,8 @@ SIGNATURES = {
     "otk_lse_combine": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "otk_sinkhorn_points_rowstep": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _dbl, _dbl, _int, _int, _ptr,
                                            _ptr, _ptr, _sz, _ptr]),
+    "otk_sinkhorn_points_summary": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _int, _dbl, _dbl, _int, _int,
+                                           _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "otk_cost_max": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _ptr, _sz, _ptr]),
     "otk_cost_matrix": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _dbl, _ptr, _ptr, _sz, _ptr]),
     "otk_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),

@@ -44,42 +44,113 @@ __global__ void sk_prep_kernel(const T* a, const T* b, int64_t LN, int64_t LM, T
   }
 }
 
+// ---- vectorised streaming kernels -------------------------------------------------------------------------------
+// Both half-steps read C exactly once with 16-byte loads (VEC = 4 floats / 2 doubles per load; VEC = 1 when a row of C is
+// not 16-byte aligned), UNROLL independent loads in flight per thread, and a branch-free online log-sum-exp: a group of
+// values is folded into the running (max, sum) pair with one rescaling exponential per GROUP instead of a data-dependent
+// branch per element.  Grids are persistent-sized (a few CTAs per SM, grid-stride over rows / slabs).
+template <typename T, int VEC> struct VecLoad;
+template <typename T> struct VecLoad<T, 1> {
+  static __device__ __forceinline__ void ld(const T* p, T (&o)[1]) { o[0] = __ldg(p); }
+  static __device__ __forceinline__ void ld_stream(const T* p, T (&o)[1]) { o[0] = __ldcs(p); }
+};
+template <> struct VecLoad<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&o)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  }
+  static __device__ __forceinline__ void ld_stream(const float* p, float (&o)[4]) {   // C is read once: evict first
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  }
+};
+template <> struct VecLoad<double, 2> {
+  static __device__ __forceinline__ void ld(const double* p, double (&o)[2]) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(p)); o[0] = t.x; o[1] = t.y;
+  }
+  static __device__ __forceinline__ void ld_stream(const double* p, double (&o)[2]) {
+    const double2 t = __ldcs(reinterpret_cast<const double2*>(p)); o[0] = t.x; o[1] = t.y;
+  }
+};
+template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
+
 // partial column LSE over a slab of rows:  (pm, ps)[l, slab, j] = online-LSE_i( u_i - C_ij/reg )
-constexpr int SKC_COLS = 128, SKC_WARPS = 8;
-template <typename T>
-__global__ void __launch_bounds__(SKC_WARPS * 32)
-sk_col_partial_kernel(const T* __restrict__ C, const T* __restrict__ u, int64_t N, int64_t M, int64_t rows_per_slab,
-                      T neg_inv_reg, T* __restrict__ pm, T* __restrict__ ps, const SkState* state) {
+// Block = TX x TY threads: thread (tx, ty) owns the VEC columns j0 + tx*VEC .. and the rows r0 + ty, r0 + ty + TY, ...
+// of its slab (so a warp reads >= 512 contiguous bytes of one row); the TY row phases are merged through shared memory.
+constexpr int SKC_THREADS = 256, SKC_UNROLL = 4, SK_MAX_SLABS = 256;
+template <typename T, int VEC>
+__global__ void __launch_bounds__(SKC_THREADS)
+sk_col_partial_kernel(const T* __restrict__ C, const T* __restrict__ u, int64_t N, int64_t M, int tx_count, int slabs,
+                      int64_t rows_per_slab, T neg_inv_reg, T* __restrict__ pm, T* __restrict__ ps, const SkState* state) {
   if (state->done) return;
-  __shared__ T sm_m[SKC_WARPS][SKC_COLS], sm_s[SKC_WARPS][SKC_COLS];
-  const int64_t l = blockIdx.z, slab = blockIdx.y, slabs = gridDim.y;
-  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
-  const int64_t j0 = (int64_t)blockIdx.x * SKC_COLS;
-  const int64_t r0 = slab * rows_per_slab, r1 = min(N, r0 + rows_per_slab);
+  extern __shared__ unsigned char sk_smem_raw[];
+  T* sm_m = reinterpret_cast<T*>(sk_smem_raw);               // [TY][TX * VEC]
+  T* sm_s = sm_m + SKC_THREADS * VEC;
+  const int ty_count = SKC_THREADS / tx_count;
+  const int tx = threadIdx.x % tx_count, ty = threadIdx.x / tx_count;
+  const int64_t col_blocks = (M + (int64_t)tx_count * VEC - 1) / ((int64_t)tx_count * VEC);
+  const int64_t l = blockIdx.y;
   const T* Cl = C + l * N * M;
   const T* ul = u + l * N;
-  T m[4], s[4];
+  for (int64_t item = blockIdx.x; item < col_blocks * slabs; item += gridDim.x) {
+    const int64_t cb = item % col_blocks, slab = item / col_blocks;
+    const int64_t j = cb * tx_count * VEC + (int64_t)tx * VEC;
+    const int64_t r0 = slab * rows_per_slab, r1 = min(N, r0 + rows_per_slab);
+    T m[VEC], s[VEC];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) { m[c] = SkMath<T>::ninf(); s[c] = T(0); }
-  for (int64_t i = r0 + warp; i < r1; i += SKC_WARPS) {
-    const T ui = ul[i];
-    const T* row = Cl + i * M + j0;
+    for (int c = 0; c < VEC; ++c) { m[c] = SkMath<T>::ninf(); s[c] = T(0); }
+    if (j < M) {
+      int64_t i = r0 + ty;
+      for (; i + (int64_t)(SKC_UNROLL - 1) * ty_count < r1; i += (int64_t)SKC_UNROLL * ty_count) {
+        T cv[SKC_UNROLL][VEC], ui[SKC_UNROLL];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      int64_t j = j0 + lane + 32 * c;
-      if (j < M) lse_push(m[c], s[c], fma(row[lane + 32 * c], neg_inv_reg, ui));
+        for (int k = 0; k < SKC_UNROLL; ++k) {
+          VecLoad<T, VEC>::ld_stream(Cl + (i + (int64_t)k * ty_count) * M + j, cv[k]);
+          ui[k] = __ldg(ul + i + (int64_t)k * ty_count);
+        }
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          T t[SKC_UNROLL];
+#pragma unroll
+          for (int k = 0; k < SKC_UNROLL; ++k) t[k] = fma(cv[k][c], neg_inv_reg, ui[k]);
+          T nm = m[c];
+#pragma unroll
+          for (int k = 0; k < SKC_UNROLL; ++k) nm = tmax(nm, t[k]);
+          T acc = s[c] * SkMath<T>::ex(m[c] - nm);
+#pragma unroll
+          for (int k = 0; k < SKC_UNROLL; ++k) acc += SkMath<T>::ex(t[k] - nm);
+          m[c] = nm; s[c] = acc;
+        }
+      }
+      for (; i < r1; i += ty_count) {
+        T cv[VEC];
+        VecLoad<T, VEC>::ld_stream(Cl + i * M + j, cv);
+        const T ui = __ldg(ul + i);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          const T t = fma(cv[c], neg_inv_reg, ui), nm = tmax(m[c], t);
+          s[c] = s[c] * SkMath<T>::ex(m[c] - nm) + SkMath<T>::ex(t - nm);
+          m[c] = nm;
+        }
+      }
     }
-  }
+    if (ty_count > 1) {
+      __syncthreads();     // the previous item's merge has finished reading the arrays
 #pragma unroll
-  for (int c = 0; c < 4; ++c) { sm_m[warp][lane + 32 * c] = m[c]; sm_s[warp][lane + 32 * c] = s[c]; }
-  __syncthreads();
-  if (threadIdx.x < SKC_COLS) {
-    int cidx = threadIdx.x;
-    T mm = sm_m[0][cidx], ss = sm_s[0][cidx];
+      for (int c = 0; c < VEC; ++c) { sm_m[(ty * tx_count + tx) * VEC + c] = m[c]; sm_s[(ty * tx_count + tx) * VEC + c] = s[c]; }
+      __syncthreads();
+      if (ty == 0) {
+        for (int w = 1; w < ty_count; ++w) {
 #pragma unroll
-    for (int w = 1; w < SKC_WARPS; ++w) lse_merge(mm, ss, sm_m[w][cidx], sm_s[w][cidx]);
-    int64_t j = j0 + cidx;
-    if (j < M) { pm[(l * slabs + slab) * M + j] = mm; ps[(l * slabs + slab) * M + j] = ss; }
+          for (int c = 0; c < VEC; ++c) lse_merge(m[c], s[c], sm_m[(w * tx_count + tx) * VEC + c], sm_s[(w * tx_count + tx) * VEC + c]);
+        }
+      }
+    }
+    if (ty == 0 && j < M) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        pm[(l * slabs + slab) * M + j + c] = m[c];
+        ps[(l * slabs + slab) * M + j + c] = s[c];
+      }
+    }
   }
 }
 
@@ -99,40 +170,74 @@ __global__ void sk_col_final_kernel(const T* __restrict__ pm, const T* __restric
   }
 }
 
-// u_i = log a_i - LSE_j( v_j - C_ij/reg ) ; TPR threads cooperate on one row
-template <typename T, int TPR>
+// u_i = log a_i - LSE_j( v_j - C_ij/reg ) ; TPR threads cooperate on one row, rows are dealt grid-stride
+template <typename T, int TPR, int VEC>
 __global__ void __launch_bounds__(256)
 sk_row_kernel(const T* __restrict__ C, const T* __restrict__ v, int64_t N, int64_t M, T neg_inv_reg,
               const T* __restrict__ log_a, T* __restrict__ u, T* __restrict__ du, const SkState* state) {
   if (state->done) return;
-  constexpr int ROWS = 256 / TPR;
+  constexpr int ROWS = 256 / TPR, UNR = 4;
   __shared__ T sm_m[8], sm_s[8];
   const int64_t l = blockIdx.y;
   const int sub = threadIdx.x / TPR, t = threadIdx.x % TPR;
-  const int64_t i = (int64_t)blockIdx.x * ROWS + sub;
-  T m = SkMath<T>::ninf(), s = T(0);
-  if (i < N) {
-    const T* row = C + (l * N + i) * M;
-    const T* vl = v + l * M;
-    for (int64_t j = t; j < M; j += TPR) lse_push(m, s, fma(row[j], neg_inv_reg, vl[j]));
-  }
-  // warp combine
+  const T* vl = v + l * M;
+  for (int64_t ib = (int64_t)blockIdx.x * ROWS; ib < N; ib += (int64_t)gridDim.x * ROWS) {
+    const int64_t i = ib + sub;
+    T m = SkMath<T>::ninf(), s = T(0);
+    if (i < N) {
+      const T* row = C + (l * N + i) * M;
+      int64_t j = (int64_t)t * VEC;
+      for (; j + (int64_t)(UNR - 1) * TPR * VEC < M; j += (int64_t)UNR * TPR * VEC) {
+        T cv[UNR][VEC], vv[UNR][VEC];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    T m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
-    lse_merge(m, s, m2, s2);
-  }
-  if (TPR == 256) {
-    if (threadIdx.x % 32 == 0) { sm_m[threadIdx.x / 32] = m; sm_s[threadIdx.x / 32] = s; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; ++w) lse_merge(m, s, sm_m[w], sm_s[w]);
+        for (int k = 0; k < UNR; ++k) {
+          VecLoad<T, VEC>::ld_stream(row + j + (int64_t)k * TPR * VEC, cv[k]);
+          VecLoad<T, VEC>::ld(vl + j + (int64_t)k * TPR * VEC, vv[k]);
+        }
+        T nm = m;
+#pragma unroll
+        for (int k = 0; k < UNR; ++k)
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) { cv[k][c] = fma(cv[k][c], neg_inv_reg, vv[k][c]); nm = tmax(nm, cv[k][c]); }
+        T acc = s * SkMath<T>::ex(m - nm);
+#pragma unroll
+        for (int k = 0; k < UNR; ++k)
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) acc += SkMath<T>::ex(cv[k][c] - nm);
+        m = nm; s = acc;
+      }
+      for (; j < M; j += (int64_t)TPR * VEC) {
+        T cv[VEC], vv[VEC];
+        VecLoad<T, VEC>::ld_stream(row + j, cv);
+        VecLoad<T, VEC>::ld(vl + j, vv);
+        T nm = m;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) { cv[c] = fma(cv[c], neg_inv_reg, vv[c]); nm = tmax(nm, cv[c]); }
+        T acc = s * SkMath<T>::ex(m - nm);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) acc += SkMath<T>::ex(cv[c] - nm);
+        m = nm; s = acc;
+      }
     }
-  }
-  if (t == 0 && i < N) {
-    T un = log_a[l * N + i] - (m + SkMath<T>::lg(s));
-    du[l * N + i] = fabs(un - u[l * N + i]);
-    u[l * N + i] = un;
+    // warp combine
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      T m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      lse_merge(m, s, m2, s2);
+    }
+    if (TPR == 256) {
+      __syncthreads();
+      if (threadIdx.x % 32 == 0) { sm_m[threadIdx.x / 32] = m; sm_s[threadIdx.x / 32] = s; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) lse_merge(m, s, sm_m[w], sm_s[w]);
+      }
+    }
+    if (t == 0 && i < N) {
+      T un = log_a[l * N + i] - (m + SkMath<T>::lg(s));
+      du[l * N + i] = fabs(un - u[l * N + i]);
+      u[l * N + i] = un;
+    }
   }
 }
 
@@ -178,21 +283,69 @@ __global__ void sk_plan_kernel(const T* __restrict__ C, const T* __restrict__ u,
   }
 }
 
-static int sk_slabs(int64_t L, int64_t N, int64_t M) {
-  int64_t col_blocks = ceil_div(M, SKC_COLS) * L;
-  int64_t want = ceil_div((int64_t)sm_count() * 8, col_blocks);
-  int64_t max_by_rows = ceil_div(N, 64);  // at least 64 rows per slab
+// launch geometry shared by the full loop and the single half-steps
+struct SkGeom {
+  int vec;            // elements per 16-byte load (1 = scalar path: a row of C is not 16-byte aligned)
+  int tx, slabs;      // column kernel: threads along a row, row slabs
+  int64_t rows_per_slab;
+  unsigned col_grid, row_grid;
+  bool wide_rows;     // row kernel: 256 threads per row instead of a warp
+};
+template <typename T>
+static SkGeom sk_geometry(const T* C, const T* v, int64_t L, int64_t N, int64_t M) {
+  SkGeom g;
+  const int full = 16 / (int)sizeof(T);
+  const bool aligned = M % full == 0 && reinterpret_cast<uintptr_t>(C) % 16 == 0 && reinterpret_cast<uintptr_t>(v) % 16 == 0;
+  g.vec = aligned ? full : 1;
+  int tx = 1;
+  while (tx < SKC_THREADS && (int64_t)tx * g.vec < M) tx <<= 1;
+  g.tx = tx;
+  const int ty = SKC_THREADS / tx;
+  const int64_t col_blocks = ceil_div(M, (int64_t)tx * g.vec);
+  int64_t want = ceil_div((int64_t)sm_count() * 8, col_blocks * L);
+  const int64_t max_by_rows = ceil_div(N, (int64_t)ty * SKC_UNROLL * 4);   // >= 4 unrolled groups per thread
   if (want > max_by_rows) want = max_by_rows;
+  if (want > SK_MAX_SLABS) want = SK_MAX_SLABS;
   if (want < 1) want = 1;
-  if (want > 64) want = 64;
-  return (int)want;
+  g.slabs = (int)want;
+  g.rows_per_slab = ceil_div(N, want);
+  g.col_grid = (unsigned)std::min<int64_t>(col_blocks * want, (int64_t)sm_count() * 8);
+  g.wide_rows = M > 4096;
+  const int64_t row_blocks = g.wide_rows ? N : ceil_div(N, 8);
+  g.row_grid = (unsigned)std::min<int64_t>(row_blocks, (int64_t)sm_count() * 8);
+  return g;
+}
+template <typename T>
+static void sk_launch_col(const SkGeom& g, const T* C, const T* u, int64_t L, int64_t N, int64_t M, T nir, T* pm, T* ps,
+                          const SkState* state, cudaStream_t st) {
+  constexpr int FULL = 16 / (int)sizeof(T);
+  const dim3 grid(g.col_grid, (unsigned)L);
+  const size_t smem = (size_t)2 * SKC_THREADS * g.vec * sizeof(T);
+  if (g.vec == FULL)
+    sk_col_partial_kernel<T, FULL><<<grid, SKC_THREADS, smem, st>>>(C, u, N, M, g.tx, g.slabs, g.rows_per_slab, nir, pm, ps, state);
+  else
+    sk_col_partial_kernel<T, 1><<<grid, SKC_THREADS, smem, st>>>(C, u, N, M, g.tx, g.slabs, g.rows_per_slab, nir, pm, ps, state);
+}
+template <typename T>
+static void sk_launch_row(const SkGeom& g, const T* C, const T* v, int64_t L, int64_t N, int64_t M, T nir, const T* log_a,
+                          T* u, T* du, const SkState* state, cudaStream_t st) {
+  constexpr int FULL = 16 / (int)sizeof(T);
+  const dim3 grid(g.row_grid, (unsigned)L);
+  if (g.wide_rows) {
+    if (g.vec == FULL) sk_row_kernel<T, 256, FULL><<<grid, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
+    else sk_row_kernel<T, 256, 1><<<grid, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
+  } else {
+    if (g.vec == FULL) sk_row_kernel<T, 32, FULL><<<grid, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
+    else sk_row_kernel<T, 32, 1><<<grid, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
+  }
 }
 
 template <typename T>
 static int sinkhorn_dense_impl(const T* a, const T* b, const T* C, int64_t L, int64_t N, int64_t M, double reg,
                                int max_iter, double threshold, int poll_every, T* u, T* v, T* plan, int* iters_done_host,
                                void* workspace, size_t workspace_bytes, cudaStream_t st, bool warm = false) {
-  const int slabs = sk_slabs(L, N, M);
+  const SkGeom g = sk_geometry<T>(C, v, L, N, M);
+  const int slabs = g.slabs;
   Arena ar(workspace, workspace_bytes);
   T* log_a = ar.take<T>((size_t)L * N);
   T* log_b = ar.take<T>((size_t)L * M);
@@ -209,21 +362,13 @@ static int sinkhorn_dense_impl(const T* a, const T* b, const T* C, int64_t L, in
   unsigned pg = (unsigned)std::min<int64_t>(ceil_div(L * (N + M), 256), (int64_t)sm_count() * 8);
   sk_prep_kernel<T><<<pg ? pg : 1, 256, 0, st>>>(a, b, L * N, L * M, log_a, log_b, u, v, state, warm);
   OTK_LAUNCH_CHECK();
-  const int64_t rows_per_slab = ceil_div(N, slabs);
-  dim3 gcol((unsigned)ceil_div(M, SKC_COLS), (unsigned)slabs, (unsigned)L);
   unsigned gfin = (unsigned)std::min<int64_t>(ceil_div(L * M, 256), (int64_t)sm_count() * 8);
   if (poll_every <= 0) poll_every = 16;
   SkState host_state{0, 0};
   for (int it = 0; it < max_iter; ++it) {
-    sk_col_partial_kernel<T><<<gcol, SKC_WARPS * 32, 0, st>>>(C, u, N, M, rows_per_slab, nir, pm, ps, state);
+    sk_launch_col<T>(g, C, u, L, N, M, nir, pm, ps, state, st);
     sk_col_final_kernel<T><<<gfin, 256, 0, st>>>(pm, ps, slabs, L, M, log_b, v, dv, state);
-    if (M <= 2048) {
-      dim3 g((unsigned)ceil_div(N, 8), (unsigned)L);
-      sk_row_kernel<T, 32><<<g, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
-    } else {
-      dim3 g((unsigned)N, (unsigned)L);
-      sk_row_kernel<T, 256><<<g, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
-    }
+    sk_launch_row<T>(g, C, v, L, N, M, nir, log_a, u, du, state, st);
     sk_check_kernel<T><<<(unsigned)L, 256, 0, st>>>(du, dv, L, N, M, threshold, diff, ticket, state);
     count_launch(3);
     OTK_LAUNCH_CHECK();
@@ -234,8 +379,8 @@ static int sinkhorn_dense_impl(const T* a, const T* b, const T* C, int64_t L, in
     }
   }
   if (plan) {
-    unsigned g = (unsigned)std::min<int64_t>(ceil_div(L * N * M, 256), (int64_t)sm_count() * 32);
-    sk_plan_kernel<T><<<g ? g : 1, 256, 0, st>>>(C, u, v, L, N, M, nir, plan);
+    unsigned gp = (unsigned)std::min<int64_t>(ceil_div(L * N * M, 256), (int64_t)sm_count() * 32);
+    sk_plan_kernel<T><<<gp ? gp : 1, 256, 0, st>>>(C, u, v, L, N, M, nir, plan);
     OTK_LAUNCH_CHECK();
   }
   if (iters_done_host) {
@@ -278,15 +423,15 @@ __global__ void sk_sum_abs_kernel(const float* d, int64_t n, float* acc) {
 
 int dense_col_partial_f32(const float* C, const float* u, int64_t N, int64_t M, double reg, float* col_max, float* col_sum,
                           void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  const int slabs = sk_slabs(1, N, M);
+  const SkGeom g = sk_geometry<float>(C, C, 1, N, M);
+  const int slabs = g.slabs;
   Arena ar(workspace, workspace_bytes);
   float* pm = ar.take<float>((size_t)slabs * M);
   float* ps = ar.take<float>((size_t)slabs * M);
   SkState* state = ar.take<SkState>(1);
   if (!ar.ok()) return OTK_ERR_WORKSPACE;
   sk_zero_state_kernel<<<1, 1, 0, st>>>(state);
-  dim3 gcol((unsigned)ceil_div(M, SKC_COLS), (unsigned)slabs, 1);
-  sk_col_partial_kernel<float><<<gcol, SKC_WARPS * 32, 0, st>>>(C, u, N, M, ceil_div(N, slabs), (float)(-1.0 / reg), pm, ps, state);
+  sk_launch_col<float>(g, C, u, 1, N, M, (float)(-1.0 / reg), pm, ps, state, st);
   sk_slab_merge_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(pm, ps, slabs, M, col_max, col_sum);
   count_launch(2);
   OTK_LAUNCH_CHECK();
@@ -304,13 +449,7 @@ int dense_row_step_f32(const float* C, const float* v, int64_t N, int64_t M, dou
   unsigned g1 = (unsigned)std::min<int64_t>(ceil_div(N, 256), (int64_t)sm_count() * 8);
   sk_log_eps_kernel<<<g1, 256, 0, st>>>(a, N, log_a);
   const float nir = (float)(-1.0 / reg);
-  if (M <= 2048) {
-    dim3 g((unsigned)ceil_div(N, 8), 1);
-    sk_row_kernel<float, 32><<<g, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
-  } else {
-    dim3 g((unsigned)N, 1);
-    sk_row_kernel<float, 256><<<g, 256, 0, st>>>(C, v, N, M, nir, log_a, u, du, state);
-  }
+  sk_launch_row<float>(sk_geometry<float>(C, v, 1, N, M), C, v, 1, N, M, nir, log_a, u, du, state, st);
   if (diff) sk_sum_abs_kernel<<<g1, 256, 0, st>>>(du, N, diff);
   count_launch(diff ? 3 : 2);
   OTK_LAUNCH_CHECK();
@@ -322,7 +461,7 @@ using namespace otk;
 extern "C" size_t otk_sinkhorn_dense_workspace_bytes(int64_t L, int64_t N, int64_t M) {
   size_t per = 8;  // sized for fp64
   return 2 * (align_up((size_t)L * N * per, 256) + align_up((size_t)L * M * per, 256)) +
-         2 * align_up((size_t)L * 64 * M * per, 256) + align_up((size_t)L * 8, 256) + 2048;
+         2 * align_up((size_t)L * SK_MAX_SLABS * M * per, 256) + align_up((size_t)L * 8, 256) + 2048;
 }
 
 extern "C" int otk_sinkhorn_dense(const void* a, const void* b, const void* C, int64_t L, int64_t N, int64_t M, int dtype,

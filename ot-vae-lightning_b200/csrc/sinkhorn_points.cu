@@ -304,3 +304,32 @@ extern "C" int otk_sinkhorn_points_rowstep(const float* x_local, const float* y,
   return dense_row_step_f32(C, v, n_local, M, reg, a_local, u_local, diff, (char*)workspace + used, workspace_bytes - used,
                             st);
 }
+
+extern "C" int otk_sinkhorn_points_summary(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
+                                           const float* a_local, const float* b, const float* u_local, const float* v,
+                                           int cost_kind, double scale, double reg, int precision, int reuse_prepared,
+                                           double* part, float* row_marginal, float* col_partial, void* workspace,
+                                           size_t workspace_bytes, otk_stream_t stream) {
+  (void)precision;
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x_local && y && a_local && b && u_local && v && part && col_partial && n_local > 0 && M > 0 && dim > 0,
+              "sinkhorn_points_summary: bad arguments");
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  if (sk_umma_eligible(n_local, M, dim, cost_kind))
+    return sk_umma_summary(x_local, y, n_local, M, dim, a_local, b, u_local, v, scale, reg, reuse_prepared, part,
+                           row_marginal, col_partial, workspace, workspace_bytes, st);
+  Arena ar(workspace, workspace_bytes);
+  float* C = ar.take<float>((size_t)n_local * M);
+  float* nx = ar.take<float>((size_t)n_local);
+  float* ny = ar.take<float>((size_t)M);
+  OTK_TRY(build_cost(x_local, y, n_local, M, dim, cost_kind, nullptr, (float)scale, nx, ny, C, st));
+  OTK_CUDA(cudaMemsetAsync(part, 0, 4 * sizeof(double), st));
+  OTK_CUDA(cudaMemsetAsync(col_partial, 0, (size_t)M * 4, st));
+  plan_row_summary_kernel<<<(unsigned)n_local, 256, 0, st>>>(C, u_local, v, a_local, n_local, M, (float)(-1.0 / reg), part,
+                                                           col_partial, row_marginal);
+  plan_col_err_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(col_partial, b, M, part);
+  count_launch(1);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}

@@ -678,4 +678,33 @@ int sk_umma_rowstep(const float* x_local, const float* y, int64_t n_local, int64
   return OTK_OK;
 }
 
+// Plan statistics of a row shard (x_local, u_local) against the replicated (y, v), on the prepared operands:
+//   part[0] += <C, pi> over the local rows, part[1] += their mass, part[2] = max_i |sum_j pi_ij - a_i|  (local rows are
+//   complete: y is replicated), row_marginal[n_local], and col_partial[M] = sum over the LOCAL rows of pi_ij - the caller
+//   sums it over the ranks (it is a column marginal only then; part[3] is the local max |col_partial - b| and is
+//   meaningful on one rank only).
+int sk_umma_summary(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* a_local,
+                    const float* b, const float* u_local, const float* v, double scale, double reg, int reuse_prepared,
+                    double* part, float* row_marginal, float* col_partial, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st) {
+  FsWork w;
+  OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st, !reuse_prepared));
+  const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
+  fs_bias_kernel<<<fs_grid(n_local), 256, 0, st>>>(u_local, w.X.sq, nrm_scale, n_local, w.biasX2);
+  fs_bias_kernel<<<fs_grid(M), 256, 0, st>>>(v, w.Y.sq, nrm_scale, M, w.biasY2);
+  count_launch(1);
+  OTK_LAUNCH_CHECK();
+  OTK_CUDA(cudaMemsetAsync(part, 0, 4 * sizeof(double), st));
+  int parts = 0;
+  OTK_TRY(fs_pass<true>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
+  fs_summary_kernel<<<fs_grid(n_local), 256, 0, st>>>(w.pm, w.pl, w.pc, parts, n_local, u_local, w.X.sq, nrm_scale, (float)scale,
+                                                     a_local, part, 2, row_marginal);
+  OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
+  fs_summary_kernel<<<fs_grid(M), 256, 0, st>>>(w.pm, w.pl, nullptr, parts, M, v, w.Y.sq, nrm_scale, (float)scale, b, part, 3,
+                                               col_partial);
+  count_launch(1);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
 }  // namespace otk

@@ -16,4 +16,8 @@ int sk_umma_colstep(const float* x_local, const float* y, int64_t n_local, int64
 int sk_umma_rowstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* a_local,
                     const float* v, double scale, double reg, int reuse_prepared, float* u_local, float* diff, void* workspace,
                     size_t workspace_bytes, cudaStream_t st);
+int sk_umma_summary(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* a_local,
+                    const float* b, const float* u_local, const float* v, double scale, double reg, int reuse_prepared,
+                    double* part, float* row_marginal, float* col_partial, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st);
 }  // namespace otk

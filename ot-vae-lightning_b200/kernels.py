@@ -381,6 +381,29 @@ def rowstep(x_local: Tensor, y: Tensor, a_local: Tensor, v: Tensor, u_local: Ten
     N.check(st, "otk_sinkhorn_points_rowstep")
 
 
+def points_summary(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, u_local: Tensor, v: Tensor, scale: float,
+                   reg: float, cost: int = N.COST_SQEUCLIDEAN, precision: int = 0, ws: Optional[Tensor] = None,
+                   reuse: bool = False):
+    """Plan statistics of a row shard (no plan in memory): returns (part [4] fp64 = <C,pi>, mass, max row error, local max
+    |col_partial - b|; row_marginal [n_local]; col_partial [M] = sum over the local rows of pi_ij)."""
+    dev = x_local.device
+    n, d = x_local.shape
+    m = y.shape[0]
+    part = torch.zeros(4, dtype=torch.float64, device=dev)
+    row_marg = torch.empty(n, dtype=torch.float32, device=dev)
+    col_part = torch.empty(m, dtype=torch.float32, device=dev)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        if ws is None:
+            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), False
+        st = lib.otk_sinkhorn_points_summary(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(a_local), N.ptr(b), N.ptr(u_local),
+                                             N.ptr(v), int(cost), float(scale), float(reg), int(precision), int(bool(reuse)),
+                                             N.ptr(part), N.ptr(row_marg), N.ptr(col_part), N.ptr(ws), ws.numel(),
+                                             N.stream_ptr(dev))
+    N.check(st, "otk_sinkhorn_points_summary")
+    return part, row_marg, col_part
+
+
 def gemm(A: Tensor, B: Tensor, alpha: float = 1.0, engine: int = 0, nn: bool = False) -> Tensor:
     """C = alpha * A @ B^T (nn=False, B [*, N, K]) or alpha * A @ B (nn=True, B [*, K, N]); fp32.
     engine: 0 auto, 1 FFMA, 2 tcgen05 3xTF32, 3 tcgen05 1xTF32.  Exported for the kernel unit tests."""

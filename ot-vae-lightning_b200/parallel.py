@@ -112,6 +112,22 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
     return dict(u_local=u.clone(), v=v.clone(), iters=done_iters, scale=scale, plan=plan)
 
 
+def sharded_summary(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, u_local: Tensor, v: Tensor, scale: float,
+                    reg: float, cost: int = 0, precision: int = 0, group=None, kernels=K) -> dict:
+    """<C,pi>, total mass and the marginal errors of the row-sharded plan pi_ij = exp(u_i + v_j - C_ij/reg), which is never
+    materialised: every rank evaluates its rows (`otk_sinkhorn_points_summary`), then ONE packed SUM all-reduce of
+    [cost, mass | column partial marginals] and one MAX all-reduce of the row error.  Same numbers on every
+    rank; at world size 1 they equal `kernels.sinkhorn_points(...)["summary"]`."""
+    part, _, col_part = kernels.points_summary(x_local, y, a_local, b, u_local, v, scale, reg, cost, precision)
+    packed = torch.cat([part[:2], col_part.double()])
+    row_err = part[2:3].clone()
+    if _world(group) > 1:
+        dist.all_reduce(packed, group=group)
+        dist.all_reduce(row_err, op=dist.ReduceOp.MAX, group=group)
+    col_err = (packed[2:] - b.double()).abs().max()
+    return dict(cost=float(packed[0]), mass=float(packed[1]), max_row_err=float(row_err), max_col_err=float(col_err))
+
+
 def _capture(iteration, dev):
     """Capture one steady-state iteration (prepared operands reused) into a CUDA graph; None if capture is refused."""
     try:

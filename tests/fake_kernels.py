@@ -109,9 +109,17 @@ def rowstep(x_local, y, a_local, v, u_local, diff, scale, reg, cost=0, precision
     u_local.copy_(new.float())
 
 
+def points_summary(x_local, y, a_local, b, u_local, v, scale, reg, cost=0, precision=0, ws=None, reuse=False):
+    C = cost_matrix(x_local, y, cost, scale).double()
+    pi = torch.exp(u_local.double()[:, None] + v.double()[None, :] - C / reg)
+    rows, cols = pi.sum(1), pi.sum(0)
+    part = torch.stack([(C * pi).sum(), pi.sum(), (rows - a_local.double()).abs().max(), (cols - b.double()).abs().max()])
+    return part, rows.float(), cols.float()
+
+
 NAMES = ["stats_update", "mean_cov", "symmetrize_shift", "asymmetry", "min_eig", "sqrtm_pair", "w2_gaussian",
          "transport_operator", "apply_transport", "sinkhorn_dense", "cost_matrix", "cost_max", "colstep", "lse_combine",
-         "rowstep"]
+         "rowstep", "points_summary"]
 
 
 @contextlib.contextmanager

@@ -1,122 +1,16 @@
 """Load the UNMODIFIED reference (`/root/reference/ot_vae_lightning`) in the authoring container.
 
-Only `tests/golden/make_golden.py` uses this (to write the committed fixtures).  Nothing that runs on the
-GPU box imports it: `/root/reference` does not exist there.
-
-The reference's `utils/__init__.py` imports `pytorch_lightning`, which is not installed, so we serve inert
-stub modules for `pytorch_lightning.*` (and `torch_ema`, `wandb`-style optional deps) from a meta-path
-finder.  The DDP helpers become identities, exactly what Lightning itself returns when no process group
-exists (reference `utils/__init__.py:21-34`).
+Only `tests/golden/make_golden.py` uses this (to write the committed fixtures).  Nothing that runs on the GPU box imports
+it: `/root/reference` does not exist there.  The stub machinery for the absent third-party packages (pytorch_lightning,
+torchmetrics, ...) lives in `baseline/ref_loader.py`, shared with `bench.py --impl reference`.
 """
-import importlib.abc
-import importlib.machinery
+import os
 import sys
-import types
-import warnings
 
 REF_ROOT = "/root/reference"
-
-
-class _Anything:
-    """Attribute sink: any attribute / call / subclassing works and does nothing."""
-
-    def __init__(self, *a, **k):
-        pass
-
-    def __call__(self, *a, **k):
-        return _Anything()
-
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        return _Anything()
-
-
-class _StubModule(types.ModuleType):
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        cls = type(name, (_Anything,), {})
-        setattr(self, name, cls)
-        return cls
-
-
-class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
-    PREFIXES = ("pytorch_lightning", "torch_ema", "jsonargparse", "torchmetrics", "lovely_tensors", "retrying")
-
-    def find_spec(self, fullname, path=None, target=None):
-        if fullname.split(".")[0] in self.PREFIXES:
-            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
-        return None
-
-    def create_module(self, spec):
-        m = _StubModule(spec.name)
-        m.__path__ = []
-        return m
-
-    def exec_module(self, module):
-        name = module.__name__
-        if name == "pytorch_lightning.utilities.distributed":
-            module.sync_ddp_if_available = lambda x, *a, **k: x
-            module.gather_all_tensors = lambda x, *a, **k: [x]
-            module.distributed_available = lambda: False
-        if name == "pytorch_lightning.utilities":
-            module.rank_zero_warn = warnings.warn
-            module.rank_zero_info = print
-            module.rank_zero_only = lambda f: f
-        if name == "pytorch_lightning.utilities.apply_func":
-            module.apply_to_collection = lambda data, dtype, fn, *a, **k: fn(data)
-        if name == "retrying":
-            module.retry = lambda *a, **k: (lambda f: f)
-        if name == "torchmetrics.metric":
-            module.Metric = _metric_base()
-        if name == "torchmetrics.image.fid":
-            import torch
-
-            class NoTrainInceptionV3(torch.nn.Module):        # never instantiated: the fixtures pass their own `net`
-                pass
-
-            def _compute_fid(mu1, sigma1, mu2, sigma2):
-                """torchmetrics (third-party, unpinned `torchmetrics>=0.9.2`, absent here): the published v1.x body of
-                torchmetrics/image/fid.py::_compute_fid, restated - the only non-reference code on the FID fixture path."""
-                a = (mu1 - mu2).square().sum(dim=-1)
-                b = sigma1.trace() + sigma2.trace()
-                c = torch.linalg.eigvals(sigma1 @ sigma2).sqrt().real.sum(dim=-1)
-                return a + b - 2 * c
-
-            module.NoTrainInceptionV3 = NoTrainInceptionV3
-            module._compute_fid = _compute_fid
-
-
-def _metric_base():
-    """The part of torchmetrics' `Metric` the reference FID class relies on (metrics/fid.py:66-97): an nn.Module whose
-    `add_state` registers the default tensor as an attribute that `update` accumulates into."""
-    import torch
-
-    class Metric(torch.nn.Module):
-        def __init__(self, **kwargs):
-            super().__init__()
-
-        def add_state(self, name, default, dist_reduce_fx=None):
-            self.register_buffer(name, default.clone())
-
-    return Metric
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "baseline"))
+import ref_loader  # noqa: E402
 
 
 def load_reference():
-    """Returns the reference's `ot_vae_lightning` namespace with `ot.*` and `utils` importable."""
-    if "ot_vae_lightning" in sys.modules and getattr(sys.modules["ot_vae_lightning"], "_is_reference", False):
-        return sys.modules["ot_vae_lightning"]
-    sys.meta_path.insert(0, _StubFinder())
-    pkg = types.ModuleType("ot_vae_lightning")
-    pkg.__path__ = [REF_ROOT + "/ot_vae_lightning"]  # skip the star-importing __init__
-    pkg._is_reference = True
-    sys.modules["ot_vae_lightning"] = pkg
-    import ot_vae_lightning.utils  # noqa: F401
-    import ot_vae_lightning.ot.matrix_utils  # noqa: F401
-    import ot_vae_lightning.ot.w2_utils  # noqa: F401
-    import ot_vae_lightning.ot.distribution_models.gaussian_model  # noqa: F401
-    import ot_vae_lightning.ot.distribution_models.codebook_model  # noqa: F401
-    import ot_vae_lightning.ot.transport.gaussian_transport  # noqa: F401
-    import ot_vae_lightning.ot.transport.discrete_transport  # noqa: F401
-    return pkg
+    return ref_loader.load_reference(REF_ROOT)

@@ -58,6 +58,12 @@ def _worker(rank, world, port, out_dir):
             u2, v2 = O.sinkhorn_log(a.double(), b.double(), C, 0.05, res["iters"], 0.0, return_potentials=True)[1:3]
             assert torch.allclose(res["u_local"].double(), u2[lo:hi], atol=2e-4)
             assert torch.allclose(res["v"].double(), v2, atol=2e-4)
+            # plan statistics of the sharded solution: one packed SUM all-reduce (+ MAX of the row error), no plan in memory
+            chk = parallel.sharded_summary(xs[lo:hi], ys, a[lo:hi], b, res["u_local"], res["v"], res["scale"], 0.05,
+                                           kernels=fake_kernels)
+            pi = torch.exp(u2[:, None] + v2[None, :] - C / 0.05)
+            assert abs(chk["cost"] - float((C * pi).sum())) < 1e-4 and abs(chk["mass"] - float(pi.sum())) < 1e-4
+            assert abs(chk["max_col_err"] - float((pi.sum(0) - b.double()).abs().max())) < 1e-4 and chk["max_row_err"] < 1e-4
             # the caller-owned plan (buffers [+ graph on CUDA]) can be handed back: same problem, same answer; a plan
             # of another problem is ignored
             xl, al = xs[lo:hi].contiguous(), a[lo:hi].contiguous()

@@ -733,3 +733,44 @@ def test_cfg4_conditional_transport_10x1024_vs_oracle(api, oracle):
     assert rel(op.source_model.mean, mean_s) < TOL_STATS and rel(op.source_model.cov, cov_s) < TOL_STATS
     assert rel(op.transport_operator, want_T) < TOL_MATFUN
     assert moved.dtype == torch.float32 and rel(moved, want_moved) < TOL_MATFUN
+
+
+# ------------------------------------------------------------------------------------------------- dense Sinkhorn, all kernel variants
+
+@pytest.mark.parametrize("n,m,dt", [(1500, 4100, torch.float32), (700, 4099, torch.float32), (2048, 1024, torch.float32),
+                                    (5, 8200, torch.float32), (333, 130, torch.float64), (64, 4098, torch.float64)])
+def test_sinkhorn_dense_vector_and_scalar_variants_vs_oracle(api, oracle, n, m, dt):
+    """`sinkhorn_log` on a materialised cost (reference w2_utils.py:276-319) through every variant of the streaming kernels:
+    16-byte and scalar loads (M % 4), warp-per-row and block-per-row (M > 4096), several column blocks and row slabs."""
+    g = torch.Generator().manual_seed(n + m)
+    x, y = torch.randn(n, 16, generator=g, dtype=torch.double), torch.randn(m, 16, generator=g, dtype=torch.double) + 0.3
+    C = oracle.sqeuclidean_cost(x, y)
+    C = (C / C.max()).to(dt)
+    a = torch.rand(n, generator=g, dtype=torch.double) + 0.2
+    a = (a / a.sum()).to(dt)
+    b = torch.full((m,), 1.0 / m, dtype=dt)
+    plan = api.sinkhorn_log(a.cuda(), b.cuda(), C.cuda(), reg=0.05, max_iter=30, threshold=0.0)
+    want = oracle.sinkhorn_log(a.double(), b.double(), C.double(), reg=0.05, max_iter=30, threshold=0.0)
+    assert plan.dtype == dt and plan.shape == (n, m)
+    tol = 1e-9 if dt == torch.float64 else TOL_SINKHORN
+    cost, want_cost = float((plan.double().cpu() * C.double()).sum()), float((want * C.double()).sum())
+    assert abs(cost - want_cost) < tol * want_cost
+    assert float((plan.double().cpu().sum(1) - want.sum(1)).abs().max()) < tol * float(a.max())
+    assert float((plan.double().cpu().sum(0) - want.sum(0)).abs().max()) < tol * float(b.max()) * (1 if dt == torch.float64 else 10)
+
+
+def test_sharded_summary_matches_fused_solver_summary(api):
+    """the plan statistics entry point used by the multi-GPU `check` (world size 1 here) == the solver's own summary"""
+    from ot_vae_lightning_b200 import kernels as K
+    from ot_vae_lightning_b200 import parallel
+    from ot_vae_lightning_b200.synthetic import point_clouds
+    for (n, m, d) in [(1024, 768, 128), (300, 200, 20)]:            # fused tcgen05 engine / streaming engine
+        x, y = point_clouds(n, m, d, seed=8, device="cuda")
+        a = torch.full((n,), 1.0 / n, device="cuda")
+        b = torch.full((m,), 1.0 / m, device="cuda")
+        res = K.sinkhorn_points(x, y, a, b, reg=0.05, max_iter=25, threshold=0.0)
+        scale = 1.0 / float(K.cost_max(x, y, 0).item())
+        chk = parallel.sharded_summary(x, y, a, b, res["u"], res["v"], scale, 0.05)
+        s = res["summary"].cpu().tolist()
+        assert abs(chk["cost"] - s[0]) < 1e-5 * s[0] and abs(chk["mass"] - s[1]) < 1e-6
+        assert abs(chk["max_row_err"] - s[2]) < 1e-7 and abs(chk["max_col_err"] - s[3]) < 1e-6
