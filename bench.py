@@ -149,18 +149,70 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
 
-def cpu_pipeline(sample_rows, threads):
-    """Reference CPU path (oracle port, torch fp64) on `sample_rows` source + target latents of the same workload."""
-    from oracle import ot_oracle as O
-    from ot_vae_lightning_b200.synthetic import gaussian_latents
-    torch.set_num_threads(threads)
-    src = gaussian_latents(sample_rows, D_LAT, seed=1234)
-    tgt = gaussian_latents(sample_rows, D_LAT, seed=4321, shift=0.5, scale=1.5)
+WORKLOAD = ("cfg2: streaming cov (2^20 source + 2^20 target 512-d latents, chunks of 65536) + Gaussian W2 map + transport of "
+            "the 2^20 source latents, per rank")
+
+
+def shared_config():
+    """identical in both arms (the driver compares it): what one step is, nothing about how an arm computes it"""
+    return dict(workload=WORKLOAD, dim=D_LAT, latents_per_rank=N_LAT, chunk=CHUNK, l2="inputs (2 x 2 GiB) exceed L2")
+
+
+def load_reference_package():
+    """The UNMODIFIED reference, pip-installed into baseline/_ref by `__graft_entry__.build()` (git-ignored, shipped to the
+    GPU box), imported behind the third-party stubs of baseline/ref_loader.py.  None if it is not there."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "ot_vae_lightning")):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_loader
+    return ref_loader.load_reference(ref_root)
+
+
+def ref_gaussian_step(ref, src, tgt, chunk, dim):
+    """update(source, target) per chunk -> compute() -> transport(source) per chunk, through the reference's own classes on
+    the host cores, with the reference's defaults for the path (fp64: `dtype=torch.double`)."""
+    from ot_vae_lightning.ot.transport.gaussian_transport import GaussianTransport as RefGT
+    cfg = dict(dtype=torch.double)
+    op = RefGT(dim, transport_cfg=dict(diag=False, stochastic=False, make_pd=True, dtype=torch.double),
+               source_cfg=dict(cfg), target_cfg=dict(cfg))
+    n = src.shape[0]
     t0 = time.perf_counter()
-    out = O.gaussian_transport_pipeline(src, tgt, min(CHUNK, sample_rows))
+    for lo in range(0, n, chunk):
+        op.update(source_samples=src[lo:lo + chunk], target_samples=tgt[lo:lo + chunk])
+    w2 = op.compute()
+    last = None
+    for lo in range(0, n, chunk):
+        last = op.transport(src[lo:lo + chunk])
+    dt = time.perf_counter() - t0
+    assert torch.isfinite(last).all()
+    return dt, float(w2)
+
+
+def port_gaussian_step(src, tgt, chunk):
+    from oracle import ot_oracle as O
+    t0 = time.perf_counter()
+    out = O.gaussian_transport_pipeline(src, tgt, chunk)
     dt = time.perf_counter() - t0
     assert torch.isfinite(out["moved"]).all()
-    return dt
+    return dt, float(out["w2"])
+
+
+def cpu_gaussian(sample_rows, threads, dim=D_LAT, chunk=CHUNK, reps=1):
+    """(seconds per pass, kind, w2) of the CPU path on `sample_rows` source + target latents of the bench workload"""
+    from ot_vae_lightning_b200.synthetic import gaussian_latents
+    torch.set_num_threads(threads)
+    src = gaussian_latents(sample_rows, dim, seed=1234, sample_seed=9001)
+    tgt = gaussian_latents(sample_rows, dim, seed=4321, shift=0.5, scale=1.5, sample_seed=7001)
+    ref = load_reference_package()
+    times = []
+    for _ in range(reps):
+        if ref is not None:
+            dt, w2 = ref_gaussian_step(ref, src, tgt, min(chunk, sample_rows), dim)
+        else:
+            dt, w2 = port_gaussian_step(src, tgt, min(chunk, sample_rows))
+        times.append(dt)
+    return sum(times) / len(times), ("reference" if ref is not None else "port"), w2
 
 
 def cpu_sinkhorn(n, iters, threads):
@@ -171,8 +223,13 @@ def cpu_sinkhorn(n, iters, threads):
     C = O.sqeuclidean_cost(x, y)
     C = C / C.max()
     a = torch.full((n,), 1.0 / n)
+    ref = load_reference_package()
     t0 = time.perf_counter()
-    O.sinkhorn_log(a, a, C, reg=SK_EPS, max_iter=iters, threshold=0.0)
+    if ref is not None:
+        from ot_vae_lightning.ot.w2_utils import sinkhorn_log as ref_sinkhorn
+        ref_sinkhorn(a, a, C, reg=SK_EPS, max_iter=iters, threshold=0.0)
+    else:
+        O.sinkhorn_log(a, a, C, reg=SK_EPS, max_iter=iters, threshold=0.0)
     return (time.perf_counter() - t0) / iters
 
 
@@ -181,29 +238,30 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 1 << 17  # bounded sample: 131072 source + 131072 target latents per step
-    for _ in range(min(args.warmup, 1)):
-        cpu_pipeline(1 << 14, threads)
-    times = [cpu_pipeline(sample, threads) for _ in range(args.steps)]
-    t = sum(times) / len(times)
-    val = sample / t
+    # the SAME workload as the B200 arm: 2^20 source + 2^20 target 512-d latents per step.  One step takes ~30-60 s on the
+    # host cores, so at most two steps are timed (after one small warm-up pass): `steps` is what was timed.
+    timed = max(1, min(args.steps, 2))
+    if args.warmup > 0:
+        cpu_gaussian(1 << 14, threads)
+    t, kind, w2 = cpu_gaussian(N_LAT, threads, reps=timed)
+    val = N_LAT / t
     sk_n = 4096
     sk_t = cpu_sinkhorn(sk_n, 3, threads)
-    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f64", data="synthetic",
-                config=dict(workload="cfg2: streaming cov (2^20 source + 2^20 target 512-d latents, chunks of 65536) "
-                                     "+ Gaussian W2 map + transport of the 2^20 source latents, per rank",
-                            dim=D_LAT, latents_per_rank=N_LAT, chunk=CHUNK, latents_per_step=sample,
-                            note=f"each step is a bounded sample of that workload: {sample} source + {sample} target "
-                                 f"latents through the same update / compute / transport sequence on the host cores"),
-                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port",
-                                  sample=f"{sample} source + {sample} target latents, d={D_LAT}, fp64 (oracle port of the "
-                                         f"reference: einsum SYRK, eigh sqrtm, fp64 mat-vecs)"),
+    how = ("unmodified reference classes from baseline/_ref (GaussianTransport.update / compute / transport; fp64 einsum "
+           "SYRK, eigh-based sqrtm, fp64 broadcast mat-vecs)" if kind == "reference" else
+           "oracle port of the reference (baseline/_ref not installed)")
+    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=timed,
+                steps_requested=args.steps, warmup=min(args.warmup, 1), ms_per_step=t * 1e3, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=shared_config(),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind=kind,
+                                  sample=f"the full step: {N_LAT} source + {N_LAT} target latents, d={D_LAT}, chunks of "
+                                         f"{CHUNK}; {timed} timed step(s); {how}"),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                check=dict(w2=w2),
                 sinkhorn=dict(metric="Sinkhorn iters/s", value=1.0 / (sk_t * (SK_N / sk_n) ** 2), unit="iters/s",
-                              measured_at=f"N=M={sk_n} fp32 ({1.0 / sk_t:.3f} it/s), extrapolated to 65536^2 by N*M",
-                              cores=threads))
+                              measured_at=f"N=M={sk_n} fp32 ({1.0 / sk_t:.3f} it/s), EXTRAPOLATED to 65536^2 by N*M (the "
+                                          f"reference materialises ~3 N x M buffers: 51 GB fp32 at 65536^2)",
+                              cores=threads, kind=kind))
     print(json.dumps(line))
 
 
@@ -219,6 +277,7 @@ def main():
     ap.add_argument("--skip-sinkhorn", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-sweeps", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -386,6 +445,121 @@ def main():
     except Exception as e:  # secondary numbers must never take the primary line down
         d128 = dict(error=f"{type(e).__name__}: {e}")
 
+    def guarded(fn):
+        try:
+            return fn()
+        except Exception as e:  # secondary numbers must never take the primary line down
+            torch.cuda.synchronize()
+            return dict(error=f"{type(e).__name__}: {e}"[:300])
+
+    def pipeline_parts(op_, xs, xt, batch, reps):
+        """ms per step (reset, update both models per batch, compute, transport every source batch) and its three parts"""
+        n_ = xs.shape[-2]
+        keep = [None] * (-(-n_ // batch))
+
+        def upd():
+            op_.reset()
+            for lo in range(0, n_, batch):
+                op_.update(source_samples=xs[..., lo:lo + batch, :], target_samples=xt[..., lo:lo + batch, :])
+
+        def mov():
+            for i, lo in enumerate(range(0, n_, batch)):
+                keep[i] = op_.transport(xs[..., lo:lo + batch, :])
+
+        def step():
+            upd()
+            op_.compute()
+            mov()
+
+        step()
+        step()
+        ms, _ = timed(step, reps)
+        u_ms, _ = timed(upd, reps)
+        c_ms, _ = timed(lambda: op_.compute(), reps)
+        t_ms, _ = timed(mov, reps)
+        return dict(ms_per_step=ms / reps, update_ms=u_ms / reps, compute_ms=c_ms / reps, transport_ms=t_ms / reps)
+
+    # ---- cfg1: the reference's own operating point (README.md:54-57, tests/test_latent_transport.py:66-98):
+    # 10 000 latents of width 128 in batches of 250 -> 40 update calls per model, compute(), 40 transport calls
+    def bench_cfg1():
+        n1, d1, b1 = 10000, 128, 250
+        xs = gaussian_latents(n1, d1, seed=11, device=dev, sample_seed=100 + rank)
+        xt = gaussian_latents(n1, d1, seed=12, device=dev, shift=0.5, scale=1.5, sample_seed=200 + rank)
+        op1 = GaussianTransport(d1, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).to(dev)
+        l0 = lib.otk_launch_count()
+        out = pipeline_parts(op1, xs, xt, b1, 10)
+        out.update(workload="cfg1: N=10000, d=128, batches of 250: update(source, target) x40 -> compute -> transport x40",
+                   latents_per_s=world * n1 / (out["ms_per_step"] * 1e-3), per_update_call_us=out["update_ms"] * 1e3 / 40,
+                   per_transport_call_us=out["transport_ms"] * 1e3 / 40, gpu_launches_per_step=int((lib.otk_launch_count() - l0) / 42),
+                   note="latency-bound: 120 small calls + one map per step; per-call figures include the Python mirror")
+        return out
+
+    # ---- cfg4: conditional transport, one operator per class: GaussianTransport(10, 1024) (transport_callback.py:388-453)
+    def bench_cfg4():
+        L4, d4, n4, b4 = 10, 1024, 4096, 1024
+        xs = torch.stack([gaussian_latents(n4, d4, seed=120 + k, device=dev) for k in range(L4)])
+        xt = torch.stack([gaussian_latents(n4, d4, seed=140 + k, device=dev, shift=1.0, scale=0.8) for k in range(L4)])
+        op4 = GaussianTransport(L4, d4, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).to(dev)
+        out = pipeline_parts(op4, xs, xt, b4, 3)
+        flop_map = L4 * (12 * 14 + 8) * float(d4) ** 3
+        out.update(workload="cfg4: 10 classes x d=1024, 4096 latents per class (4 d), batches of 1024 per class",
+                   latents_per_s=world * L4 * n4 / (out["ms_per_step"] * 1e-3),
+                   map_tflops_algorithmic=flop_map / (out["compute_ms"] * 1e-3) / 1e12,
+                   note="sample covariances of 4 d observations (condition number ~ 9 x the population's 1e2); "
+                        "map flops counted as (12 K + 8) d^3 with K = 14 per operator (SURVEY 8d)")
+        return out
+
+    # ---- cfg5: sweeps d = 64 .. 4096 (statistics / map / transport) and Sinkhorn N = 4k .. 256k
+    def bench_cfg5():
+        rows_out = []
+        for d5 in (64, 128, 256, 512, 1024, 2048, 4096):
+            def one(d5=d5):
+                n5 = 65536 if d5 <= 1024 else 16384
+                xs = gaussian_latents(n5, d5, seed=300 + d5, device=dev)
+                xt = (xs.roll(1, dims=1) * 1.5 + 0.5).contiguous()     # same spectrum, other eigenvectors: one QR per width
+                op5 = GaussianTransport(d5, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).to(dev)
+                r = pipeline_parts(op5, xs, xt, n5, 3)
+                fl = 2.0 * n5 * d5 * d5
+                return dict(d=d5, rows=n5, update_ms=r["update_ms"] / 2, compute_ms=r["compute_ms"], transport_ms=r["transport_ms"],
+                            update_tflops=fl / (r["update_ms"] / 2 * 1e-3) / 1e12, update_gbs=n5 * d5 * 4 / (r["update_ms"] / 2 * 1e-3) / 1e9,
+                            transport_tflops=fl / (r["transport_ms"] * 1e-3) / 1e12,
+                            transport_gbs=2 * n5 * d5 * 4 / (r["transport_ms"] * 1e-3) / 1e9)
+            res = guarded(one)
+            res.setdefault("d", d5)
+            rows_out.append(res)
+            torch.cuda.empty_cache()
+        sk_out = []
+        for n5 in (4096, 16384, 65536, 262144):
+            def one(n5=n5):
+                x5, y5 = point_clouds(n5, n5, SK_D, seed=500 + (n5 >> 10), device=dev)
+                a5 = torch.full((n5,), 1.0 / n5, device=dev)
+                lo5, hi5 = parallel.shard_rows(n5, rank, world)
+                it5 = 20
+                if world == 1:
+                    sc5 = 1.0 / float(K.cost_max(x5, y5, 0).item())
+                    run5 = lambda: K.sinkhorn_points(x5, y5, a5, a5, reg=SK_EPS, max_iter=it5, threshold=0.0, scale=sc5,
+                                                     want_summary=False, want_iters=False)
+                else:
+                    xl5, al5 = x5[lo5:hi5].contiguous(), a5[lo5:hi5].contiguous()
+                    sc5 = parallel.global_cost_scale(xl5, y5)
+                    run5 = lambda: parallel.sharded_sinkhorn(xl5, y5, al5, a5, reg=SK_EPS, max_iter=it5, threshold=0.0,
+                                                             scale=sc5, use_graph=False)
+                run5()
+                ms5, _ = timed(run5, 1)
+                return dict(N=n5, iters_per_s=it5 / (ms5 * 1e-3), ms_per_iter=ms5 / it5)
+            res = guarded(one)
+            res.setdefault("N", n5)
+            sk_out.append(res)
+            torch.cuda.empty_cache()
+        return dict(workload="cfg5: one 65536-row chunk (16384 rows for d >= 2048) per width through update / compute / "
+                             "transport; fused Sinkhorn at d=128, eps=0.05, 20 iterations per size, rows sharded over the ranks",
+                    cov_map=rows_out, sinkhorn=sk_out)
+
+    cfg1 = guarded(bench_cfg1)
+    cfg4 = guarded(bench_cfg4)
+    cfg5 = guarded(bench_cfg5) if not args.skip_sweeps else None
+    torch.cuda.empty_cache()
+
     # ---- e2e: same step through the public API with pinned HOST buffers
     e2e = None
     if not args.skip_e2e:
@@ -447,11 +621,22 @@ def main():
             sk_clocks = sampler.result()
             it_s = iters / (sk_ms * 1e-3)
             alg_gb = 2.0 * SK_N * SK_N * 4 / 1e9
-            res = K.sinkhorn_points(x, y, a, a, reg=SK_EPS, max_iter=iters, threshold=0.0, scale=scale) if world == 1 else None
+            # correctness of what was timed: plan statistics WITHOUT the plan, on every rank count (the sharded rows'
+            # <C,pi>, mass and column partials are summed with one all-reduce; same problem, so the numbers must agree
+            # across n_gpus to the solver's accuracy)
+            if world == 1:
+                res = K.sinkhorn_points(x, y, a, a, reg=SK_EPS, max_iter=iters, threshold=0.0, scale=scale)
+                s4 = res["summary"].cpu().tolist()
+                check = dict(cost=s4[0], mass=s4[1], max_row_err=s4[2], max_col_err=s4[3])
+                del res
+            else:
+                out = run()
+                check = parallel.sharded_summary(xl, y, al, a, out["u_local"], out["v"], scale, SK_EPS)
+                del out
             sinkhorn = dict(metric="Sinkhorn iters/s", value=it_s, unit="iters/s", ms_per_iter=sk_ms / iters, n_gpus=world,
                             scaling="strong", config=dict(N=SK_N, M=SK_N, d=SK_D, eps=SK_EPS, iters=iters, threshold=0.0,
                                                           cost="sqeuclidean / max", scale=scale),
-                            gpu_launches=int(sk_launches),
+                            gpu_launches=int(sk_launches), check=check,
                             roofline=dict(bound="hbm", achieved=alg_gb * it_s, peak=peaks["hbm"], unit="GB/s",
                                           frac=alg_gb * it_s / peaks["hbm"], traffic=34.1e6,
                                           note="algorithmic bytes 2*N*M*4 per iteration (one fp32 cost read per half-step: "
@@ -468,9 +653,30 @@ def main():
                                                       peak=peaks["bf16_sustained"], unit="TFLOP/s per GPU",
                                                       note="executed FP16 MMA flops 2 passes x 2*N*M*d")))
             sinkhorn["clocks"] = sk_clocks
-            if res is not None:
-                s = res["summary"].cpu().tolist()
-                sinkhorn["check"] = dict(cost=s[0], mass=s[1], max_row_err=s[2], max_col_err=s[3])
+            # the reference signature (`sinkhorn_log` on a MATERIALISED cost, w2_utils.py:276-319) at the same size: the
+            # streaming kernels read the 17 GB fp32 cost once per half-step
+            if world == 1:
+                def dense_leg():
+                    Cd = K.cost_matrix(x, y, 0, scale)
+                    d_iters = 10
+                    rund = lambda: K.sinkhorn_dense(a, a, Cd, SK_EPS, d_iters, 0.0, want_plan=False)
+                    rund()
+                    l0d = lib.otk_launch_count()
+                    d_ms, outd = timed(rund, 1)
+                    ud, vd = outd[1], outd[2]
+                    ref10 = K.sinkhorn_points(x, y, a, a, reg=SK_EPS, max_iter=d_iters, threshold=0.0, scale=scale,
+                                              want_summary=False, want_iters=False)
+                    gbs = alg_gb * d_iters / (d_ms * 1e-3)
+                    return dict(iters_per_s=d_iters / (d_ms * 1e-3), ms_per_iter=d_ms / d_iters, iters=d_iters,
+                                gpu_launches=int(lib.otk_launch_count() - l0d),
+                                roofline=dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                                              traffic=None,
+                                              note="algorithmic bytes 2*N*M*4 per iteration / CUDA-event time of the loop"),
+                                max_abs_u_vs_fused=float((ud - ref10["u"]).abs().max()),
+                                max_abs_v_vs_fused=float((vd - ref10["v"]).abs().max()),
+                                note="sk_col_partial_kernel + sk_row_kernel (sinkhorn_dense.cu): 16-byte loads, grouped "
+                                     "branch-free online LSE, persistent grids; potentials compared with the fused engine")
+                sinkhorn["dense"] = guarded(dense_leg)
         except Exception as e:  # keep the primary line even if the secondary workload fails
             sinkhorn = dict(error=f"{type(e).__name__}: {e}")
         finally:                # NCCL cannot tear the communicator down while a graph that captured it is alive
@@ -483,25 +689,27 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         threads = os.cpu_count() or 1
-        sample = 1 << 17
-        cpu_pipeline(1 << 13, threads)
-        t = cpu_pipeline(sample, threads)
-        cpu = dict(value=sample / t, unit=UNIT, cores=threads, kind="port",
-                   sample=f"{sample} source + {sample} target latents, d={D_LAT}, fp64, one pass ({t:.1f} s)")
+        sample = 1 << 18
+        cpu_gaussian(1 << 13, threads)
+        t, kind, _ = cpu_gaussian(sample, threads)
+        cpu = dict(value=sample / t, unit=UNIT, cores=threads, kind=kind,
+                   sample=f"{sample} source + {sample} target latents of the same workload (a quarter of a step), d={D_LAT}, "
+                          f"chunks of {CHUNK}, fp64, one pass ({t:.1f} s); `--impl reference` times the full step")
+        if isinstance(cfg1, dict) and "error" not in cfg1:
+            t1, kind1, _ = cpu_gaussian(10000, threads, dim=128, chunk=250)
+            cfg1["cpu_reference"] = dict(ms_per_step=t1 * 1e3, latents_per_s=10000 / t1, cores=threads, kind=kind1)
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                     data="synthetic",
-                    config=dict(workload="cfg2: streaming cov (2^20 source + 2^20 target 512-d latents, chunks of 65536) "
-                                         "+ Gaussian W2 map + transport of the 2^20 source latents, per rank",
-                                dim=D_LAT, latents_per_rank=N_LAT, chunk=CHUNK, l2="inputs (2 x 2 GiB) exceed L2",
-                                arithmetic="fp32-accurate products (FP16 hi/lo split with exact scales, TF32 split for the d x d matrix functions), "
-                                           "fp64 running statistics",
-                                sinkhorn_arithmetic="FP16 operand planes (TF32-size mantissa), fp32 accumulation and softmax",
-                                w2=float(w2)),
+                    config=shared_config(),
+                    arithmetic=dict(gaussian="fp32-accurate products (FP16 hi/lo split with exact scales, TF32 split for the "
+                                             "d x d matrix functions), fp64 running statistics",
+                                    sinkhorn="FP16 operand planes (TF32-size mantissa), fp32 accumulation and softmax"),
+                    check=dict(w2=float(w2)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
-                    d128=d128, sinkhorn=sinkhorn)
+                    d128=d128, cfg1=cfg1, cfg4=cfg4, cfg5=cfg5, sinkhorn=sinkhorn)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
