@@ -76,6 +76,14 @@ int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t dim, int64
                      void* sum_cov, int buf_dtype, void* workspace, size_t workspace_bytes,
                      otk_stream_t stream);
 
+/* Same contract for fp64 latents (the reference casts `samples.type_as(buffer)`, gaussian_model.py:103; FID accumulates
+ * `features.double()`, metrics/fid.py:101-104): fp64 products and accumulation on the DFMA engine, so that sums of outer
+ * products stay positive semi-definite to fp64 round-off. */
+int otk_stats_update_f64(const double* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,
+                         int64_t batch_stride, double decay, void* n_obs, int n_dtype, void* sum,
+                         void* sum_cov, int buf_dtype, void* workspace, size_t workspace_bytes,
+                         otk_stream_t stream);
+
 /* K2  mean = sum/n ; cov = sum_cov/n - mean mean^T (biased).  Replaces mean_cov, ot/matrix_utils.py:145-158
  * (full-matrix branch).  n is a device vector [L] (a python int crashes the reference: utils/__init__.py:322). */
 int otk_mean_cov(const void* sum, const void* sum_cov, const void* n_obs, int n_dtype, int64_t L,
@@ -125,6 +133,15 @@ int otk_transport_operator(const void* cov_s, const void* cov_t, int64_t L, int6
                            const void* mean_t, double* w2, void* workspace, size_t workspace_bytes,
                            otk_stream_t stream);
 
+/* K6, stochastic variant (eq. 19): T = (1-p) Ct^1/2 (Ct^1/2 Cs Ct^1/2)^1/2 (Ct + 1e-8 I)^-1/2 Cs^+ + p I and the noise
+ * covariance Cw = sqrt(1-p) Ct^1/2 (I - Ct^1/2 T* Cs^+ T* Ct^1/2) Ct^1/2, T* = T_{t->s} of eq. 17.
+ * Replaces _compute_transport_full_mat_stochastic, ot/w2_utils.py:774-793 (torch.linalg.pinv + 5 eigh + 14 matmuls):
+ * three Newton-Schulz solves and the products on the device.  Cs^+ is taken as Cs^-1 (positive definite source). */
+size_t otk_transport_operator_stochastic_workspace_bytes(int64_t L, int64_t dim);
+int otk_transport_operator_stochastic(const void* cov_s, const void* cov_t, int64_t L, int64_t dim, int dtype,
+                                      double pg_star, int iters, int polish, void* T, void* Cw, void* workspace,
+                                      size_t workspace_bytes, otk_stream_t stream);
+
 /* K7  y[l,b,:] = T[l] (x[l,b,:] - mean_s[l]) + mean_t[l].  Replaces apply_transport, ot/w2_utils.py:464-527
  * (deterministic, full-matrix; as called by W2Mixin.apply_transport :581-597 and
  * GaussianTransport.transport, transport/gaussian_transport.py:80-95).
@@ -168,7 +185,8 @@ size_t otk_sinkhorn_points_workspace_bytes(int64_t N, int64_t M, int64_t dim, in
 /* scale = 1/max_ij cost (w2_utils.py:265-266) if scale_inv_max != 0, else `scale`; result in *scale_out_host */
 int otk_sinkhorn_points(const float* x, const float* y, int64_t N, int64_t M, int64_t dim,
                         const float* a, const float* b, int cost_kind, double scale, int scale_inv_max,
-                        double reg, int max_iter, double threshold, int poll_every, int precision,
+                        double reg, int max_iter, double threshold, int poll_every,
+                        int precision /* 0 auto: fused tcgen05 engine when eligible; 1: exact fp32 cost tiles */,
                         float* u, float* v, double* summary /* [4]: <C,pi>, sum pi, max|row err|, max|col err| */,
                         float* row_marginal /* [N] or NULL */, float* col_marginal /* [M] or NULL */,
                         int* iters_done_host, void* workspace, size_t workspace_bytes,
@@ -201,6 +219,12 @@ int otk_sinkhorn_points_summary(const float* x_local, const float* y, int64_t n_
                                 int cost_kind, double scale, double reg, int precision, int reuse_prepared,
                                 double* part, float* row_marginal, float* col_partial, void* workspace,
                                 size_t workspace_bytes, otk_stream_t stream);
+/* The plan on request: plan [N,M] = exp(u_i + v_j - scale*cost(x_i, y_j)/reg) from the potentials of otk_sinkhorn_points
+ * (DiscreteTransport.transport_matrix, transport/discrete_transport.py:60-77; the coupling batch_ot_gmm returns,
+ * w2_utils.py:266-269).  workspace >= (N+M)*4 + 512 bytes. */
+int otk_sinkhorn_points_plan(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, const float* u,
+                             const float* v, int cost_kind, double scale, double reg, float* plan, void* workspace,
+                             size_t workspace_bytes, otk_stream_t stream);
 /* max_ij cost(x_i, y_j) -> *out (device fp32), for the 1/max normalisation */
 int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
                  float* out, void* workspace, size_t workspace_bytes, otk_stream_t stream);

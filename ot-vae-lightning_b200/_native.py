@@ -33,6 +33,7 @@ SIGNATURES = {
     "otk_launch_count": (C.c_ulonglong, []),
     "otk_stats_update_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_stats_update": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _dbl, _ptr, _int, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
+    "otk_stats_update_f64": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _dbl, _ptr, _int, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
     "otk_mean_cov": (_int, [_ptr, _ptr, _ptr, _int, _i64, _i64, _ptr, _ptr, _int, _ptr]),
     "otk_symmetrize_shift": (_int, [_ptr, _ptr, _i64, _i64, _ptr, _int, _ptr]),
     "otk_asymmetry": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr]),
@@ -44,6 +45,8 @@ SIGNATURES = {
     "otk_w2_gaussian": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _int, _int, _int, _ptr, _ptr, _sz, _ptr]),
     "otk_transport_operator_workspace_bytes": (_sz, [_i64, _i64]),
     "otk_transport_operator": (_int, [_ptr, _ptr, _i64, _i64, _int, _dbl, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "otk_transport_operator_stochastic_workspace_bytes": (_sz, [_i64, _i64]),
+    "otk_transport_operator_stochastic": (_int, [_ptr, _ptr, _i64, _i64, _int, _dbl, _int, _int, _ptr, _ptr, _ptr, _sz, _ptr]),
     "otk_apply_transport_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_apply_transport": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _int, _ptr, _ptr, _sz, _ptr]),
     "otk_transport_prepared_bytes": (_sz, [_i64, _i64]),
@@ -62,6 +65,7 @@ SIGNATURES = {
                                            _ptr, _ptr, _sz, _ptr]),
     "otk_sinkhorn_points_summary": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _int, _dbl, _dbl, _int, _int,
                                            _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "otk_sinkhorn_points_plan": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _dbl, _dbl, _ptr, _ptr, _sz, _ptr]),
     "otk_cost_max": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _ptr, _sz, _ptr]),
     "otk_cost_matrix": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _dbl, _ptr, _ptr, _sz, _ptr]),
     "otk_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),

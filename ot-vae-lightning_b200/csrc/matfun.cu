@@ -47,37 +47,52 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return r;
 }
 
-// c[l] = || A_l + ridge I ||_F : partial sums of squares with fp64 atomics (grid = blocks x L), then a sqrt pass
-__global__ void frob_sq_kernel(const void* a, int dt, int64_t dim, double ridge, double* c) {
-  __shared__ double red[32];
+// Scale of the iteration: c[l] >= lambda_max(A_l + ridge I), the smaller of the Frobenius norm and the maximum absolute row
+// sum (both bound the spectral radius; for a covariance with a spread spectrum the row-sum norm is several times tighter
+// than the Frobenius norm, and every factor 2.25 saved is one Newton-Schulz iteration).  One warp per row: sum of squares
+// with an fp64 atomic into c[l], row sum with an atomic max (bit pattern of a non-negative double) into cmax[l].
+__global__ void norm_rows_kernel(const void* a, int dt, int64_t dim, double ridge, double* c, double* cmax) {
   const int64_t l = blockIdx.y;
-  double acc = 0;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < dim * dim; e += (int64_t)gridDim.x * blockDim.x) {
-    double v = load_real(a, l * dim * dim + e, dt);
-    if (e / dim == e % dim) v += ridge;
-    acc += v * v;
+  const int lane = threadIdx.x % 32;
+  double sq_tot = 0, mx = 0;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; row < dim; row += (int64_t)gridDim.x * (blockDim.x / 32)) {
+    double sq = 0, ab = 0;
+    for (int64_t j = lane; j < dim; j += 32) {
+      double v = load_real(a, l * dim * dim + row * dim + j, dt);
+      if (j == row) v += ridge;
+      sq += v * v;
+      ab += fabs(v);
+    }
+    sq = warp_sum(sq);
+    ab = warp_sum(ab);
+    sq_tot += sq;
+    mx = ab > mx ? ab : mx;
   }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(&c[l], acc);
+  if (lane == 0) {
+    atomicAdd(&c[l], sq_tot);
+    atomicMax(reinterpret_cast<unsigned long long*>(&cmax[l]), (unsigned long long)__double_as_longlong(mx));
+  }
 }
-// c[l] holds ||A + ridge I||_F^2 on entry.  ridge_l[l] = ridge + rel * c0,  c[l] <- c0 * (1 + rel * sqrt(dim)) with
-// c0 = sqrt(c[l])  (an upper bound of ||A + ridge_l I||_F)
-__global__ void ns_ridge_kernel(double* c, int64_t L, double ridge, double rel, double sqrt_dim, double* ridge_l) {
+// On entry c[l] = ||A + ridge I||_F^2 and ridge_l[l] = its maximum absolute row sum.  c0 = min(sqrt(c[l]), row-sum norm);
+// ridge_l[l] <- ridge + rel * c0 ;  c[l] <- c0 * (1 + rel)  (still an upper bound of lambda_max(A + ridge_l I))
+__global__ void ns_ridge_kernel(double* c, int64_t L, double ridge, double rel, double* ridge_l) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e < L) {
-    const double c0 = sqrt(c[e]);
+    const double fro = sqrt(c[e]), rs = ridge_l[e];
+    const double c0 = (rs > 0 && rs < fro) ? rs : fro;
     ridge_l[e] = ridge + rel * c0;
-    c[e] = c0 > 0 ? c0 * (1.0 + rel * sqrt_dim) : 1.0;   // the zero matrix: Y stays 0, the solve reports not-converged
+    c[e] = c0 > 0 ? c0 * (1.0 + rel) : 1.0;   // the zero matrix: Y stays 0, the solve reports not-converged
   }
 }
 static int frob_norm(const void* a, int dt, int64_t L, int64_t dim, double ridge, double rel, double* c, double* ridge_l,
                      cudaStream_t st) {
   OTK_CUDA(cudaMemsetAsync(c, 0, (size_t)L * 8, st));
-  int64_t bx = ceil_div(dim * dim, 256 * 8);
-  if (bx > 256) bx = 256;
+  OTK_CUDA(cudaMemsetAsync(ridge_l, 0, (size_t)L * 8, st));
+  int64_t bx = ceil_div(dim, 8);
+  if (bx > 128) bx = 128;
   if (bx < 1) bx = 1;
-  frob_sq_kernel<<<dim3((unsigned)bx, (unsigned)L), 256, 0, st>>>(a, dt, dim, ridge, c);
-  ns_ridge_kernel<<<(unsigned)ceil_div(L, 256), 256, 0, st>>>(c, L, ridge, rel, sqrt((double)dim), ridge_l);
+  norm_rows_kernel<<<dim3((unsigned)bx, (unsigned)L), 256, 0, st>>>(a, dt, dim, ridge, c, ridge_l);
+  ns_ridge_kernel<<<(unsigned)ceil_div(L, 256), 256, 0, st>>>(c, L, ridge, rel, ridge_l);
   count_launch(1);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
@@ -534,8 +549,96 @@ static int operator_impl(const void* cov_s, const void* cov_t, int64_t L, int64_
   return OTK_OK;
 }
 
+// out = s0 * in + diag_add * I   (no symmetrisation: the stochastic operator is not symmetric), cast to out_dt
+template <typename W>
+__global__ void scale_add_kernel(const W* in, int64_t L, int64_t dim, double s0, double diag_add, void* out, int out_dt) {
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e % (dim * dim);
+    store_real(out, e, out_dt, s0 * (double)in[e] + ((r / dim == r % dim) ? diag_add : 0.0));
+  }
+}
+
+// Stochastic operator, eq. 19 of Freirich et al. (reference _compute_transport_full_mat_stochastic, w2_utils.py:774-793):
+//   St = Ct^1/2, iSt = (Ct + 1e-8 I)^-1/2, R = (St Cs St)^1/2, P = Cs^+ (= Cs^-1: the source must be PD here - the
+//   reference's own pipeline is non-finite for a rank-deficient source, tests/golden/make_golden.py note),
+//   T* = iSt R iSt,  T = (1-p) St R iSt P + p I,  Cw = sqrt(1-p) St (I - St T* P T* St) St.
+// Three Newton-Schulz solves and fourteen d x d products, all on the device (the reference: 5 eigh + pinv (SVD) + 14 matmuls).
+template <typename W>
+static int stochastic_impl(const void* cov_s, const void* cov_t, int64_t L, int64_t dim, int dtype, double pg_star, int iters,
+                           void* T, void* Cw, void* workspace, size_t workspace_bytes, int* verdict, cudaStream_t st) {
+  Arena ar(workspace, workspace_bytes);
+  NsWork<W> w; w.carve(ar, L, dim);
+  const size_t n = (size_t)L * dim * dim;
+  const int64_t d = dim, dd = dim * dim;
+  const W* none = nullptr;
+  const int wdt = sizeof(W) == 8 ? OTK_F64 : OTK_F32;
+  W *St = ar.take<W>(n), *iSt = ar.take<W>(n), *Q32 = ar.take<W>(n), *G = ar.take<W>(n), *mix = ar.take<W>(n);
+  W *R = ar.take<W>(n), *P = ar.take<W>(n), *Tst = ar.take<W>(n), *H = ar.take<W>(n);
+  if (!ar.ok()) return OTK_ERR_WORKSPACE;
+  int cur = 0, cur2 = 0, v0 = 0, v1 = 0, used = 0;
+  auto mul = [&](const W* A, const W* B, W* C) { return gemm_any(with_scratch(nn_args_t<W>(A, B, C, d, dd, W(1)), w.scratch), L, st); };
+  // P = Cs^-1 from the inverse root of the source
+  OTK_TRY(ns_solve<W>(cov_s, dtype, L, d, 0.0, iters, w, &cur, &v0, &used, st));
+  sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(w.Z[cur], none, L, d, w.c, -0.5, 1.0, 0, 0, 0.0, G, wdt);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(mul(G, G, P));
+  // roots of the TARGET (roles swapped on purpose, reference :786-787), then R = (St Cs St)^1/2
+  OTK_TRY(rooted_mix<W>(cov_t, cov_s, dtype, L, d, 1e-8, iters, w, St, iSt, Q32, G, mix, &cur2, &v1, &used, st));
+  sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(w.Y[cur2], none, L, d, w.c, 0.5, 1.0, 0, 0, 0.0, R, wdt);
+  OTK_LAUNCH_CHECK();
+  *verdict = (v0 == NS_CONVERGED && v1 == NS_CONVERGED) ? NS_CONVERGED : NS_SLOW;
+  // T = (1-p) St R iSt P + p I
+  OTK_TRY(mul(St, R, G));
+  OTK_TRY(mul(G, iSt, H));
+  OTK_TRY(mul(H, P, G));
+  scale_add_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(G, L, d, 1.0 - pg_star, pg_star, T, dtype);
+  OTK_LAUNCH_CHECK();
+  // T* = iSt R iSt ;  Cw = sqrt(1-p) St (I - St T* P T* St) St
+  OTK_TRY(mul(iSt, R, G));
+  OTK_TRY(mul(G, iSt, Tst));
+  OTK_TRY(mul(St, Tst, G));
+  OTK_TRY(mul(G, P, H));
+  OTK_TRY(mul(H, Tst, G));
+  OTK_TRY(mul(G, St, H));
+  scale_add_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(H, L, d, -1.0, 1.0, G, wdt);     // I - St T* P T* St
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(mul(St, G, H));
+  OTK_TRY(mul(H, St, G));
+  scale_add_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(G, L, d, sqrt(1.0 - pg_star), 0.0, Cw, dtype);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
 }  // namespace otk
 using namespace otk;
+
+extern "C" size_t otk_transport_operator_stochastic_workspace_bytes(int64_t L, int64_t dim) {
+  return ns_work_bytes(L, dim) + 9 * align_up((size_t)L * dim * dim * 8, 256) + 4096;
+}
+
+extern "C" int otk_transport_operator_stochastic(const void* cov_s, const void* cov_t, int64_t L, int64_t dim, int dtype,
+                                                 double pg_star, int iters, int polish, void* T, void* Cw, void* workspace,
+                                                 size_t workspace_bytes, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(cov_s && cov_t && T && Cw && L > 0 && dim > 0, "transport_operator_stochastic: bad arguments");
+  OTK_REQUIRE(pg_star >= 0.0 && pg_star <= 1.0, "transport_operator_stochastic: pg_star outside [0, 1]");
+  if (!workspace || workspace_bytes < otk_transport_operator_stochastic_workspace_bytes(L, dim)) return OTK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  int verdict = NS_SLOW;
+  // Cw = St (I - ...) St cancels to zero for a PD source: only the fp64 engine resolves it for fp64 data
+  if (polish == 0 && dtype == OTK_F64 && iters <= 0) polish = 1;
+  if (polish <= 0) {
+    OTK_TRY(stochastic_impl<float>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, Cw, workspace, workspace_bytes, &verdict, st));
+    if (verdict == NS_CONVERGED || polish < 0 || iters > 0) return OTK_OK;
+  }
+  OTK_TRY(stochastic_impl<double>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, Cw, workspace, workspace_bytes, &verdict, st));
+  if (verdict != NS_CONVERGED && iters <= 0) {
+    set_last_error_msg("transport_operator_stochastic: Newton-Schulz did not converge (a covariance is not positive definite)");
+    return OTK_ERR_NOT_CONVERGED;
+  }
+  return OTK_OK;
+}
 
 // workspaces are sized for the fp64 escalation
 extern "C" size_t otk_sqrtm_workspace_bytes(int64_t L, int64_t dim) { return ns_work_bytes(L, dim) + 4096; }

@@ -146,9 +146,18 @@ static size_t stream_ws_bytes(int64_t N, int64_t M) {
 }  // namespace otk
 using namespace otk;
 
+// precision 0 = automatic: the fused tcgen05 engine (FP16 operand planes) when the shape is eligible, else the streaming
+// engine; precision 1 = exact fp32 cost tiles (streaming engine) whatever the shape - the small codebook / mixture problems
+// of DiscreteTransport and batch_ot_gmm, whose plans are compared entry by entry.
+static bool use_fused(int64_t N, int64_t M, int64_t dim, int cost_kind, int precision) {
+  return precision == 0 && sk_umma_eligible(N, M, dim, cost_kind);
+}
+
 extern "C" size_t otk_sinkhorn_points_workspace_bytes(int64_t N, int64_t M, int64_t dim, int cost_kind) {
-  if (sk_umma_eligible(N, M, dim, cost_kind)) return sk_umma_workspace_bytes(N, M, dim);
-  return stream_ws_bytes(N, M);
+  // sized for either engine, so that the same workspace serves every `precision`
+  const size_t a = sk_umma_eligible(N, M, dim, cost_kind) ? sk_umma_workspace_bytes(N, M, dim) : 0;
+  const size_t b = (double)N * (double)M <= 3.0e9 ? stream_ws_bytes(N, M) : 0;
+  return a > b ? a : (b ? b : stream_ws_bytes(N, M));
 }
 
 extern "C" int otk_cost_matrix(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
@@ -193,7 +202,7 @@ extern "C" int otk_sinkhorn_points(const float* x, const float* y, int64_t N, in
   OTK_REQUIRE(reg > 0 && max_iter >= 0, "sinkhorn_points: reg must be > 0");
   if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(N, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  if (sk_umma_eligible(N, M, dim, cost_kind))
+  if (use_fused(N, M, dim, cost_kind, precision))
     return sk_umma_solve(x, y, N, M, dim, a, b, scale, scale_inv_max, reg, max_iter, threshold, poll_every, precision, u,
                          v, summary, row_marginal, col_marginal, iters_done_host, workspace, workspace_bytes, st);
   // streaming engine
@@ -238,7 +247,7 @@ extern "C" int otk_sinkhorn_points_colstep(const float* x_local, const float* y,
   OTK_REQUIRE(x_local && y && u_local && col_max && col_sum && n_local > 0 && M > 0 && dim > 0, "colstep: bad arguments");
   if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  if (sk_umma_eligible(n_local, M, dim, cost_kind))
+  if (use_fused(n_local, M, dim, cost_kind, precision))
     return sk_umma_colstep(x_local, y, n_local, M, dim, u_local, scale, reg, reuse_prepared, col_max, col_sum, workspace,
                            workspace_bytes, st);
   Arena ar(workspace, workspace_bytes);
@@ -292,7 +301,7 @@ extern "C" int otk_sinkhorn_points_rowstep(const float* x_local, const float* y,
   OTK_REQUIRE(x_local && y && a_local && v && u_local && n_local > 0 && M > 0 && dim > 0, "rowstep: bad arguments");
   if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  if (sk_umma_eligible(n_local, M, dim, cost_kind))
+  if (use_fused(n_local, M, dim, cost_kind, precision))
     return sk_umma_rowstep(x_local, y, n_local, M, dim, a_local, v, scale, reg, reuse_prepared, u_local, diff, workspace,
                            workspace_bytes, st);
   Arena ar(workspace, workspace_bytes);
@@ -310,13 +319,12 @@ extern "C" int otk_sinkhorn_points_summary(const float* x_local, const float* y,
                                            int cost_kind, double scale, double reg, int precision, int reuse_prepared,
                                            double* part, float* row_marginal, float* col_partial, void* workspace,
                                            size_t workspace_bytes, otk_stream_t stream) {
-  (void)precision;
   OTK_TRY(require_device());
   OTK_REQUIRE(x_local && y && a_local && b && u_local && v && part && col_partial && n_local > 0 && M > 0 && dim > 0,
               "sinkhorn_points_summary: bad arguments");
   if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  if (sk_umma_eligible(n_local, M, dim, cost_kind))
+  if (use_fused(n_local, M, dim, cost_kind, precision))
     return sk_umma_summary(x_local, y, n_local, M, dim, a_local, b, u_local, v, scale, reg, reuse_prepared, part,
                            row_marginal, col_partial, workspace, workspace_bytes, st);
   Arena ar(workspace, workspace_bytes);
@@ -330,6 +338,34 @@ extern "C" int otk_sinkhorn_points_summary(const float* x_local, const float* y,
                                                            col_partial, row_marginal);
   plan_col_err_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(col_partial, b, M, part);
   count_launch(1);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+namespace otk {
+// in place: C_ij (already scale * cost) -> exp(u_i + v_j - C_ij / reg)
+__global__ void plan_from_cost_kernel(float* __restrict__ C, const float* __restrict__ u, const float* __restrict__ v, int64_t N,
+                                      int64_t M, float nir) {
+  const int64_t total = N * M;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    C[e] = __expf(fmaf(C[e], nir, u[e / M] + v[e % M]));
+}
+}  // namespace otk
+
+extern "C" int otk_sinkhorn_points_plan(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, const float* u,
+                                        const float* v, int cost_kind, double scale, double reg, float* plan, void* workspace,
+                                        size_t workspace_bytes, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x && y && u && v && plan && N > 0 && M > 0 && dim > 0 && reg > 0, "sinkhorn_points_plan: bad arguments");
+  if (!workspace || workspace_bytes < (size_t)(N + M) * 4 + 512) return OTK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  Arena ar(workspace, workspace_bytes);
+  float* nx = ar.take<float>((size_t)N);
+  float* ny = ar.take<float>((size_t)M);
+  OTK_TRY(build_cost(x, y, N, M, dim, cost_kind, nullptr, (float)scale, nx, ny, plan, st));
+  int64_t blocks = ceil_div(N * M, 256);
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  plan_from_cost_kernel<<<(unsigned)blocks, 256, 0, st>>>(plan, u, v, N, M, (float)(-1.0 / reg));
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }

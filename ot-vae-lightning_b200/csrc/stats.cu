@@ -19,13 +19,13 @@ constexpr int ST_FUSED_ROWS = 256;   // batches up to this many rows take the si
 // running buffers itself - one launch per update, no staging area, no atomics (latency mode: batches of a few hundred).
 // (StatsRunning: stats_umma.cuh)
 
-template <bool FUSED>
+template <bool FUSED, typename X>
 __global__ void __launch_bounds__(ST_THREADS)
-stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
+stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
                   int64_t chunk_rows, int n_tiles, double* __restrict__ ws_cov, double* __restrict__ ws_sum,
                   StatsRunning run) {
-  __shared__ float As[ST_BK][ST_T + 4];
-  __shared__ float Bs[ST_BK][ST_T + 4];
+  __shared__ X As[ST_BK][ST_T + 4];
+  __shared__ X Bs[ST_BK][ST_T + 4];
   // decode the upper-triangular tile pair (ti <= tj) from blockIdx.x
   int p = blockIdx.x, ti = 0;
   while (p >= n_tiles - ti) { p -= n_tiles - ti; ++ti; }
@@ -33,7 +33,7 @@ stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_
   const int64_t l = blockIdx.z;
   const int64_t r0 = (int64_t)blockIdx.y * chunk_rows;
   const int64_t r1 = min(rows, r0 + chunk_rows);
-  const float* xb = x + l * batch_stride;
+  const X* xb = x + l * batch_stride;
   const int64_t i0 = (int64_t)ti * ST_T, j0 = (int64_t)tj * ST_T;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   double acc[4][4];
@@ -50,8 +50,8 @@ stats_simt_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_
       int kk = e / ST_T, cc = e % ST_T;
       int64_t row = k0 + kk;
       bool rok = row < r1;
-      As[kk][cc] = (rok && i0 + cc < dim) ? xb[row * row_stride + i0 + cc] : 0.f;
-      Bs[kk][cc] = (rok && j0 + cc < dim) ? xb[row * row_stride + j0 + cc] : 0.f;
+      As[kk][cc] = (rok && i0 + cc < dim) ? xb[row * row_stride + i0 + cc] : X(0);
+      Bs[kk][cc] = (rok && j0 + cc < dim) ? xb[row * row_stride + j0 + cc] : X(0);
     }
     __syncthreads();
     if (ti == tj && tid < ST_T) {
@@ -202,9 +202,15 @@ extern "C" size_t otk_stats_update_workspace_bytes(int64_t L, int64_t rows, int6
   return align_up((size_t)L * dim * dim * 8, 256) + align_up((size_t)L * dim * 8, 256) + stats_umma_extra_workspace(L, dim);
 }
 
-extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,
-                                int64_t batch_stride, double decay, void* n_obs, int n_dtype, void* sum, void* sum_cov,
-                                int buf_dtype, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
+// X = float: the product path (tcgen05 kernels, DFMA engine for small / unaligned shapes and small batches).
+// X = double: fp64 latents (the reference casts `samples.type_as(buffer)`, gaussian_model.py:103, and FID takes
+//   `features.double()`, fid.py:101) always run on the DFMA engine - fp64 products, fp64 accumulation - so that sums of
+//   outer products stay positive semi-definite to fp64 round-off (a rank-deficient covariance is then singular, not
+//   indefinite at the 1e-7 level of an fp32-accurate product).
+template <typename X>
+static int stats_update_impl(const X* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
+                             double decay, void* n_obs, int n_dtype, void* sum, void* sum_cov, int buf_dtype,
+                             void* workspace, size_t workspace_bytes, otk_stream_t stream) {
   OTK_TRY(require_device());
   OTK_REQUIRE(L > 0 && dim > 0 && rows >= 0, "stats_update: bad shape");
   OTK_REQUIRE(rows == 0 || x, "stats_update: null latents");
@@ -212,14 +218,15 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
   OTK_REQUIRE(row_stride >= dim, "stats_update: row_stride < dim");
   if (workspace_bytes < otk_stats_update_workspace_bytes(L, rows, dim) || !workspace) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  if (rows > 0 && rows <= ST_FUSED_ROWS && !g_stats_force_cg) {
+  constexpr bool kF32 = sizeof(X) == 4;
+  if (rows > 0 && rows <= ST_FUSED_ROWS && !(kF32 && g_stats_force_cg)) {
     // latency mode: one launch, every CTA merges its own output tile (exact fp64 products, as the reference's einsum)
     const int n_tiles = (int)ceil_div(dim, ST_T);
     const int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
     if (pairs <= 65535 && L <= 65535) {
       StatsRunning run{n_obs, sum, sum_cov, n_dtype, buf_dtype, decay};
-      stats_simt_kernel<true><<<dim3((unsigned)pairs, 1, (unsigned)L), ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride,
-                                                                                          rows, n_tiles, nullptr, nullptr, run);
+      stats_simt_kernel<true, X><<<dim3((unsigned)pairs, 1, (unsigned)L), ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride,
+                                                                                             rows, n_tiles, nullptr, nullptr, run);
       OTK_LAUNCH_CHECK();
       return OTK_OK;
     }
@@ -232,10 +239,13 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
   const float* pivot = nullptr;
   if (rows == 0) OTK_CUDA(cudaMemsetAsync(workspace, 0, staging_bytes, st));
   if (rows > 0) {
-    int used = stats_umma_try(x, L, rows, dim, row_stride, batch_stride, ws_cov, ws_sum, ar, st, &tile, &pivot,
-                              StatsRunning{n_obs, sum, sum_cov, n_dtype, buf_dtype, decay});
-    if (used < 0) return used;
-    if (used == 2) return OTK_OK;          // FP16-split kernels: already merged into the running buffers
+    int used = 0;
+    if constexpr (kF32) {
+      used = stats_umma_try(x, L, rows, dim, row_stride, batch_stride, ws_cov, ws_sum, ar, st, &tile, &pivot,
+                            StatsRunning{n_obs, sum, sum_cov, n_dtype, buf_dtype, decay});
+      if (used < 0) return used;
+      if (used == 2) return OTK_OK;          // FP16-split kernels: already merged into the running buffers
+    }
     if (!used) {
       OTK_CUDA(cudaMemsetAsync(workspace, 0, staging_bytes, st));
       tile = ST_T;
@@ -249,8 +259,8 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
       if (chunk > 65536) chunk = 65536;
       dim3 grid((unsigned)pairs, (unsigned)ceil_div(rows, chunk), (unsigned)L);
       OTK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stats_update: too many row chunks / batches");
-      stats_simt_kernel<false><<<grid, ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride, chunk, n_tiles, ws_cov,
-                                                            ws_sum, StatsRunning{});
+      stats_simt_kernel<false, X><<<grid, ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride, chunk, n_tiles, ws_cov,
+                                                               ws_sum, StatsRunning{});
       OTK_LAUNCH_CHECK();
     }
   }
@@ -258,6 +268,20 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
                                                             n_dtype, sum, sum_cov, buf_dtype);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
+}
+
+extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,
+                                int64_t batch_stride, double decay, void* n_obs, int n_dtype, void* sum, void* sum_cov,
+                                int buf_dtype, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
+  return stats_update_impl<float>(x, L, rows, dim, row_stride, batch_stride, decay, n_obs, n_dtype, sum, sum_cov, buf_dtype,
+                                  workspace, workspace_bytes, stream);
+}
+
+extern "C" int otk_stats_update_f64(const double* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,
+                                    int64_t batch_stride, double decay, void* n_obs, int n_dtype, void* sum, void* sum_cov,
+                                    int buf_dtype, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
+  return stats_update_impl<double>(x, L, rows, dim, row_stride, batch_stride, decay, n_obs, n_dtype, sum, sum_cov, buf_dtype,
+                                   workspace, workspace_bytes, stream);
 }
 
 extern "C" int otk_mean_cov(const void* sum, const void* sum_cov, const void* n_obs, int n_dtype, int64_t L,

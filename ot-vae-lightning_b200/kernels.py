@@ -51,15 +51,24 @@ def stats_update(x: Tensor, n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, dec
     dev = run_sum.device
     d = run_sum.shape[-1]
     lead, L = _lead(run_sum.shape, 1)
-    x, row_stride, batch_stride = _strided_latents(x, dev, lead, d)
-    rows = x.shape[-2]
     lib = N.load()
+    if x.dtype == torch.float64:
+        # fp64 latents keep fp64 products (otk_stats_update_f64): what the reference's einsum on `samples.type_as(buffer)` /
+        # FID's `features.double()` computes; everything else is streamed as fp32 through the tensor-core kernels
+        x = _dev_tensor(x, dev, torch.float64)
+        if x.shape[:-2] != lead:
+            x = x.expand(*lead, *x.shape[-2:]).contiguous()
+        row_stride, batch_stride, entry = d, x.shape[-2] * d, lib.otk_stats_update_f64
+    else:
+        x, row_stride, batch_stride = _strided_latents(x, dev, lead, d)
+        entry = lib.otk_stats_update
+    rows = x.shape[-2]
     for buf in (n_obs, run_sum, run_cov):
         if not (buf.is_cuda and buf.is_contiguous()):
             raise ValueError("running buffers must be contiguous CUDA tensors")
     with N.on_device(dev) as ctx:
         ws = ctx.workspace(lib.otk_stats_update_workspace_bytes(L, rows, d))
-        st = lib.otk_stats_update(x.data_ptr(), L, rows, d, row_stride, batch_stride,
+        st = entry(x.data_ptr(), L, rows, d, row_stride, batch_stride,
                                   -1.0 if decay is None else float(decay),
                                   n_obs.data_ptr(), N.dtype_code(n_obs.dtype), run_sum.data_ptr(), run_cov.data_ptr(),
                                   N.dtype_code(run_sum.dtype), ws.data_ptr(), ws.numel(), ctx.stream)
@@ -190,6 +199,25 @@ def transport_operator(cov_s: Tensor, cov_t: Tensor, pg_star: float = 0.0, mean_
     return T, w2
 
 
+def transport_operator_stochastic(cov_s: Tensor, cov_t: Tensor, pg_star: float = 0.0) -> Tuple[Tensor, Tensor]:
+    """(T, Cw) of eq. 19 [*L, d, d] in the dtype of the covariances (otk_transport_operator_stochastic)."""
+    dev = N.compute_device(cov_s, cov_t)
+    dt = torch.float64 if (cov_s.dtype == torch.float64 or cov_t.dtype == torch.float64) else torch.float32
+    cs, ct = _dev_tensor(cov_s, dev, dt), _dev_tensor(cov_t, dev, dt)
+    d = cs.shape[-1]
+    lead = torch.broadcast_shapes(cs.shape[:-2], ct.shape[:-2])
+    L = int(lead.numel())
+    cs, ct = _bcast(cs, lead, 2), _bcast(ct, lead, 2)
+    T, Cw = torch.empty_like(cs), torch.empty_like(cs)
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_transport_operator_stochastic_workspace_bytes(L, d), dev)
+        st = lib.otk_transport_operator_stochastic(N.ptr(cs), N.ptr(ct), L, d, N.dtype_code(dt), float(pg_star), 0, 0,
+                                                   N.ptr(T), N.ptr(Cw), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_transport_operator_stochastic")
+    return T, Cw
+
+
 def apply_transport(x: Tensor, mean_s: Tensor, mean_t: Tensor, T: Tensor) -> Tensor:
     """y = T (x - mean_s) + mean_t; x [*L, B, d] any float dtype/device -> fp32 result on the compute device."""
     dev = N.compute_device(T, mean_s, x)
@@ -295,6 +323,21 @@ def sinkhorn_points(x: Tensor, y: Tensor, a: Tensor, b: Tensor, reg: float, max_
                                      ws.numel(), N.stream_ptr(dev))
     N.check(st, "otk_sinkhorn_points")
     return dict(u=u, v=v, summary=summary, row_marginal=row_marg, col_marginal=col_marg, iters=iters.value)
+
+
+def points_plan(x: Tensor, y: Tensor, u: Tensor, v: Tensor, scale: float, reg: float, cost: int = N.COST_SQEUCLIDEAN) -> Tensor:
+    """plan [N, M] = exp(u_i + v_j - scale * cost(x_i, y_j) / reg) from the potentials of `sinkhorn_points` (fp32)."""
+    dev = N.compute_device(x, y)
+    xd, yd = _dev_tensor(x, dev, torch.float32), _dev_tensor(y, dev, torch.float32)
+    n, d = xd.shape
+    m = yd.shape[0]
+    plan = torch.empty(n, m, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = N.workspace((n + m) * 4 + 512, dev)
+        st = N.load().otk_sinkhorn_points_plan(N.ptr(xd), N.ptr(yd), n, m, d, N.ptr(u), N.ptr(v), int(cost), float(scale),
+                                               float(reg), N.ptr(plan), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_sinkhorn_points_plan")
+    return plan
 
 
 def cost_matrix(x: Tensor, y: Tensor, cost: int, scale: float = 1.0) -> Tensor:

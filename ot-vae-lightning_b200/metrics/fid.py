@@ -59,7 +59,7 @@ class FrechetInceptionDistance(nn.Module):
             img = torch.cat([img, img, img], dim=1)
         if self.to_255:
             img = (255 * (img - self.data_low) / self.data_range).type(torch.uint8)
-        return self.net(img).reshape(img.shape[0], -1)
+        return self.net(img).double().reshape(img.shape[0], -1)          # fp64 features, as fid.py:101
 
     @torch.no_grad()
     def _accumulate(self, img: Tensor, kind: str) -> None:

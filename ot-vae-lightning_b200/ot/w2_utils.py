@@ -178,6 +178,10 @@ def batch_ot_gmm(mean_source: Tensor, mean_target: Tensor, cov_source: Tensor, c
         mean_target, "mean_target", "vec", cov_target, "cov_target", kind, weight_target, "weight_target", "prob",
         dtype=dtype)
     if diag:
+        routed = _ot_gmm_diag_on_points(mean_source, mean_target, cov_source, cov_target, weight_source, weight_target,
+                                        **sinkhorn_kwargs)
+        if routed is not None:
+            return routed
         cost = batch_w2_dissimilarity_gaussian_diag(mean_source, mean_target, cov_source, cov_target, dtype=dtype)
     else:
         cost = batch_w2_dissimilarity_gaussian(mean_source, mean_target, cov_source, cov_target, make_pd=True,
@@ -185,6 +189,26 @@ def batch_ot_gmm(mean_source: Tensor, mean_target: Tensor, cov_source: Tensor, c
     peak = cost.amax(dim=(-2, -1), keepdim=True)
     coupling = sinkhorn_log(weight_source, weight_target, cost / peak, **sinkhorn_kwargs)
     return (cost * coupling).sum(dim=(-2, -1)), coupling
+
+
+def _ot_gmm_diag_on_points(mean_s: Tensor, mean_t: Tensor, var_s: Tensor, var_t: Tensor, w_s: Tensor, w_t: Tensor,
+                           reg: float = 1e-5, max_iter: int = 1000, threshold: float = STABILITY_CONST
+                           ) -> Optional[Tuple[Tensor, Tensor]]:
+    """The diagonal mixture OT without a host-visible cost matrix: W2^2 between diagonal Gaussians is the squared distance
+    between the stacked features [m, sqrt(v)] (reference w2_utils.py:121-125), so the component problem is a point-cloud
+    Sinkhorn (`otk_sinkhorn_points`, squared-Euclidean tiles, cost normalised by its max as at :265-266).  Used for
+    un-batched CUDA inputs whose 1 / reg stays within fp32 (the normalised cost is <= 1); None otherwise."""
+    if mean_s.dim() != 2 or not mean_s.is_cuda or 1.0 / reg > 1.0e3:
+        return None
+    fs = torch.cat([mean_s, var_s.sqrt()], dim=-1).float().contiguous()
+    ft = torch.cat([mean_t, var_t.sqrt()], dim=-1).float().contiguous()
+    peak = float(K.cost_max(fs, ft, 0))
+    if not peak > 0:
+        return None
+    res = K.sinkhorn_points(fs, ft, w_s, w_t, reg=reg, max_iter=max_iter, threshold=threshold, scale=1.0 / peak, precision=1,
+                            want_iters=False)
+    coupling = K.points_plan(fs, ft, res["u"], res["v"], 1.0 / peak, reg).to(mean_s.dtype)
+    return (res["summary"][0] * peak).to(mean_s.dtype), coupling
 
 
 def sinkhorn_log(a: Tensor, b: Tensor, C: Tensor, reg: float = 1e-5, max_iter: int = 1000,
@@ -263,9 +287,16 @@ def apply_transport(input: Tensor, mean_source: Tensor, mean_target: Tensor, T: 
     else:
         moved = _apply_full(input, mean_source, mean_target, T)
     if not ignore_cw:
-        zero = torch.zeros_like(mean_target)
-        noise = D.Normal(zero, Cw) if diag else D.MultivariateNormal(zero, Cw)
-        moved = moved + noise.sample()
+        # W ~ N(0, Cw) (reference :522-525) without leaving the device kernels: standard normal draws (torch's generator is
+        # plumbing) shaped by Cw^1/2 - the Newton-Schulz root, applied with the same streaming GEMM as the map itself -
+        # instead of `MultivariateNormal`'s Cholesky factor; the two factors give the same distribution, not the same draws.
+        # The diagonal branch keeps the reference's quirk of passing Cw as the *scale* of `D.Normal`.
+        eps = torch.randn(moved.shape, dtype=moved.dtype, device=moved.device)
+        if diag:
+            moved = moved + eps * Cw
+        else:
+            zero = torch.zeros_like(mean_target)
+            moved = moved + _apply_full(eps, zero, zero, sqrtm(Cw))
     return moved
 
 
@@ -368,11 +399,9 @@ def _compute_transport_full_mat(cov_source: Tensor, cov_target: Tensor, p_gstar:
 
 def _compute_transport_full_mat_stochastic(cov_source: Tensor, cov_target: Tensor, pg_star: float
                                            ) -> Tuple[Tensor, Tensor]:
-    """eq. 19 (reference :774-793); `pinv` is the stock torch call, the roots are the Newton-Schulz kernels."""
-    eye = eye_like(cov_source)
-    pinv_source = torch.linalg.pinv(cov_source)
-    root_t, iroot_t = sqrtm(cov_target), invsqrtm(cov_target + STABILITY_CONST * eye)
-    T_star = _compute_transport_full_mat(cov_source=cov_target, cov_target=cov_source, p_gstar=0)[0]
-    T = (1 - pg_star) * (root_t @ sqrtm(root_t @ cov_source @ root_t) @ iroot_t @ pinv_source) + pg_star * eye
-    Cw = sqrt(1 - pg_star) * root_t @ (eye - root_t @ T_star @ pinv_source @ T_star @ root_t) @ root_t
-    return T, Cw
+    """eq. 19 (reference :774-793) in one libotk call: the roots, the pseudo-inverse of the source (its inverse, taken from
+    a Newton-Schulz inverse root: the reference's own pipeline is non-finite for a rank-deficient source) and the fourteen
+    d x d products all run on the device; nothing goes through `torch.linalg`."""
+    T, Cw = K.transport_operator_stochastic(cov_source, cov_target, pg_star=float(pg_star))
+    return (T.to(device=cov_source.device, dtype=cov_source.dtype),
+            Cw.to(device=cov_source.device, dtype=cov_source.dtype))

@@ -54,6 +54,10 @@ def transport_operator(cs, ct, pg_star=0.0, mean_s=None, mean_t=None, iters=0):
     return T.to(cs.dtype), w2
 
 
+def transport_operator_stochastic(cs, ct, pg_star=0.0):
+    return O.transport_operator_full_stochastic(cs, ct, pg_star)
+
+
 def apply_transport(x, ms, mt, T):
     return O.apply_transport(x, ms, mt, T).float()
 
@@ -118,7 +122,7 @@ def points_summary(x_local, y, a_local, b, u_local, v, scale, reg, cost=0, preci
 
 
 NAMES = ["stats_update", "mean_cov", "symmetrize_shift", "asymmetry", "min_eig", "sqrtm_pair", "w2_gaussian",
-         "transport_operator", "apply_transport", "sinkhorn_dense", "cost_matrix", "cost_max", "colstep", "lse_combine",
+         "transport_operator", "transport_operator_stochastic", "apply_transport", "sinkhorn_dense", "cost_matrix", "cost_max", "colstep", "lse_combine",
          "rowstep", "points_summary"]
 
 

@@ -774,3 +774,35 @@ def test_sharded_summary_matches_fused_solver_summary(api):
         s = res["summary"].cpu().tolist()
         assert abs(chk["cost"] - s[0]) < 1e-5 * s[0] and abs(chk["mass"] - s[1]) < 1e-6
         assert abs(chk["max_row_err"] - s[2]) < 1e-7 and abs(chk["max_col_err"] - s[3]) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------- f3: stochastic operator, noise
+
+@pytest.mark.parametrize("d,pg", [(24, 0.0), (128, 0.3), (256, 0.0)])
+def test_stochastic_operator_native_vs_oracle(api, oracle, d, pg):
+    """eq. 19 (reference w2_utils.py:774-793) through `otk_transport_operator_stochastic` (Newton-Schulz roots, inverse of
+    the source in place of torch.linalg.pinv, fourteen products on the device) against the oracle's eigh / pinv pipeline."""
+    lam_s, lam_t = torch.logspace(-1.3, 0, d, dtype=torch.double), torch.logspace(-1.0, 0, d, dtype=torch.double) * 1.8
+    cs, ct = _spectrum_matrix(d, lam_s, 31), _spectrum_matrix(d, lam_t, 32)
+    Top, Cw = api.compute_transport_operators(cs.cuda(), ct.cuda(), stochastic=True, diag=False, pg_star=pg, make_pd=True)
+    want_T, want_Cw = oracle.transport_operator_full_stochastic(cs, ct, pg)
+    assert Top.dtype == torch.double and rel(Top, want_T) < TOL_MATFUN
+    # with a positive definite source the noise covariance cancels to zero: compare on the scale of the target covariance
+    assert float((Cw.cpu() - want_Cw).abs().max()) < 1e-6 * float(ct.abs().max())
+
+
+def test_stochastic_noise_is_sampled_with_the_requested_covariance(api):
+    """`apply_transport` with a non-zero Cw (reference w2_utils.py:522-525): W = Cw^1/2 eps from the Newton-Schulz root and
+    the streaming GEMM kernel; the empirical covariance of the noise must be Cw (statistical check, 40 000 draws)."""
+    d, n = 32, 40000
+    cw = _spectrum_matrix(d, torch.logspace(-1, 0, d, dtype=torch.double), 41).cuda()
+    zero = torch.zeros(1, d, dtype=torch.double, device="cuda")
+    eye = torch.eye(d, dtype=torch.double, device="cuda").unsqueeze(0)
+    torch.manual_seed(5)
+    y = api.apply_transport(torch.zeros(n, d, dtype=torch.double, device="cuda"), zero, zero, eye, cw.unsqueeze(0))
+    emp = (y.T @ y) / n
+    assert rel(emp, cw.cpu()) < 0.05 and float(y.mean(0).abs().max()) < 0.03
+    vw = torch.rand(d, dtype=torch.double, device="cuda") + 0.5          # diagonal branch: Cw is the *scale* (reference quirk)
+    yd = api.apply_transport(torch.zeros(n, d, dtype=torch.double, device="cuda"), zero[0], zero[0],
+                             torch.ones(d, dtype=torch.double, device="cuda"), vw, diag=True)
+    assert rel(yd.std(0), vw.cpu()) < 0.03
