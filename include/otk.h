@@ -162,6 +162,14 @@ int otk_transport_prepare(const void* mean_s, const void* mean_t, const void* T,
 int otk_apply_transport_prepared(const float* x, int64_t L, int64_t rows, int64_t dim, const void* state,
                                  size_t state_bytes, float* y, otk_stream_t stream);
 
+/* Same, for latents that are a strided VIEW (`utils.permute_and_flatten` hands over [B, T, D] token / channel views,
+ * utils/__init__.py:233-311; the reference makes them contiguous first, :260-261): x[l, b, :] starts at
+ * x + l * batch_stride + b * row_stride (elements), unit feature stride; y is dense [L, rows, dim].  Strides that are
+ * multiples of 4 elements are read in place by TMA, anything else by the FFMA engine. */
+int otk_apply_transport_prepared_strided(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,
+                                         int64_t batch_stride, const void* state, size_t state_bytes, float* y,
+                                         otk_stream_t stream);
+
 /* K8  log-domain Sinkhorn on a materialised cost.  Replaces sinkhorn_log, ot/w2_utils.py:276-319:
  *   u = v = 0; per iteration v = log(b+1e-8) - LSE_i(u_i - C_ij/reg), then u = log(a+1e-8) - LSE_j(v_j - C_ij/reg);
  *   stop after the iteration in which min over the batch of sum|du| + sum|dv| < threshold (device-side flag,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "otk_transport_prepared_bytes": (_sz, [_i64, _i64]),
     "otk_transport_prepare": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _i64, _i64, _ptr, _sz, _ptr]),
     "otk_apply_transport_prepared": (_int, [_ptr, _i64, _i64, _i64, _ptr, _sz, _ptr, _ptr]),
+    "otk_apply_transport_prepared_strided": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _sz, _ptr, _ptr]),
     "otk_sinkhorn_dense_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_sinkhorn_dense": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _dbl, _int, _dbl, _int, _ptr, _ptr, _ptr,
                                   C.POINTER(_int), _ptr, _sz, _ptr]),

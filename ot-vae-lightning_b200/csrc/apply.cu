@@ -95,28 +95,42 @@ extern "C" int otk_transport_prepare(const void* mean_s, const void* mean_t, con
   return r < 0 ? r : OTK_OK;
 }
 
-extern "C" int otk_apply_transport_prepared(const float* x, int64_t L, int64_t rows, int64_t dim, const void* state,
-                                            size_t state_bytes, float* y, otk_stream_t stream) {
+static int apply_prepared_impl(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t xrs, int64_t xbs, const void* state,
+                               size_t state_bytes, float* y, otk_stream_t stream) {
   OTK_TRY(require_device());
   OTK_REQUIRE(L > 0 && dim > 0 && rows >= 0, "apply_transport_prepared: bad arguments");
   if (rows == 0) return OTK_OK;
   OTK_REQUIRE(x && y, "apply_transport_prepared: null latents");
+  OTK_REQUIRE(xrs >= dim && (L == 1 || xbs > 0), "apply_transport_prepared: bad latent strides");
   if (!state || state_bytes < otk_transport_prepared_bytes(L, dim)) return OTK_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   Arena ar(const_cast<void*>(state), state_bytes);
   PreparedOp p;
   if (!carve_prepared(ar, L, dim, &p)) return OTK_ERR_WORKSPACE;
-  if (apply_umma_eligible(x, y, L, rows, dim)) {
+  // TMA reads the view in place when its strides are 16-byte multiples; anything else goes through the FFMA engine,
+  // which takes arbitrary element strides
+  if (apply_umma_eligible(x, y, L, rows, dim) && xrs % 4 == 0 && xbs % 4 == 0) {
     const bool pair = apply_umma_pair(rows, dim);
     int* flag = nullptr;
-    int used = apply_h_run_prepared(x, L, rows, dim, p.mt32, y, ar, pair, st, &flag);
+    int used = apply_h_run_prepared(x, L, rows, dim, p.mt32, y, ar, pair, st, &flag, xrs, xbs);
     if (used < 0) return used;
     if (!used) flag = nullptr;
-    used = apply_umma_run_planes(x, L, rows, dim, p.ms32, p.mt32, p.Thi, p.Tlo, y, pair, flag, st);
+    used = apply_umma_run_planes(x, L, rows, dim, p.ms32, p.mt32, p.Thi, p.Tlo, y, pair, flag, st, xrs, xbs);
     if (used < 0) return used;
     if (used) return OTK_OK;
   }
-  GemmArgs<float> g{x, p.T32, y, rows, dim, dim, dim, 1, dim, 1, dim, rows * dim, dim * dim, rows * dim,
+  GemmArgs<float> g{x, p.T32, y, rows, dim, dim, xrs, 1, dim, 1, dim, xbs, dim * dim, rows * dim,
                     1.f, 0.f, p.ms32, dim, p.mt32, dim, 0.f, nullptr};
   return gemm_simt<float>(g, L, st);
+}
+
+extern "C" int otk_apply_transport_prepared(const float* x, int64_t L, int64_t rows, int64_t dim, const void* state,
+                                            size_t state_bytes, float* y, otk_stream_t stream) {
+  return apply_prepared_impl(x, L, rows, dim, dim, rows * dim, state, state_bytes, y, stream);
+}
+
+extern "C" int otk_apply_transport_prepared_strided(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,
+                                                    int64_t batch_stride, const void* state, size_t state_bytes, float* y,
+                                                    otk_stream_t stream) {
+  return apply_prepared_impl(x, L, rows, dim, row_stride, batch_stride, state, state_bytes, y, stream);
 }

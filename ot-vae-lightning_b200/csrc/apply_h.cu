@@ -424,9 +424,10 @@ static bool carve_apply_h(Arena& ar, int64_t L, int64_t dim, ApplyHPlanes* p) {
   return ar.ok();
 }
 static int run_apply_h(const float* x, int64_t L, int64_t rows, int64_t dim, const float* mt32, const ApplyHPlanes& p, float* y,
-                       bool pair, cudaStream_t st) {
+                       bool pair, cudaStream_t st, int64_t x_row_stride = 0, int64_t x_batch_stride = 0) {
   CUtensorMap mX, mTh, mTl, mY;
-  if (!encode_map_f32_3d(&mX, x, dim, rows, L, dim, rows * dim, 32, HP_BM)) return 0;
+  const int64_t xrs = x_row_stride > 0 ? x_row_stride : dim, xbs = x_batch_stride > 0 ? x_batch_stride : rows * dim;
+  if (!encode_map_f32_3d(&mX, x, dim, rows, L, xrs, xbs, 32, HP_BM)) return 0;
   if (!encode_map_f16_3d(&mTh, p.Thi, dim, dim, L, dim, dim * dim, HP_TK, 128)) return 0;
   if (!encode_map_f16_3d(&mTl, p.Tlo, dim, dim, L, dim, dim * dim, HP_TK, 128)) return 0;
   if (!encode_map_f32_3d(&mY, y, dim, rows, L, dim, rows * dim, 32, 32)) return 0;
@@ -462,13 +463,13 @@ int apply_h_prepare(int64_t L, int64_t dim, const float* ms32, const float* T32,
   return 1;
 }
 int apply_h_run_prepared(const float* x, int64_t L, int64_t rows, int64_t dim, const float* mt32, float* y, Arena& ar, bool pair,
-                         cudaStream_t st, int** flag_out) {
+                         cudaStream_t st, int** flag_out, int64_t x_row_stride, int64_t x_batch_stride) {
   ApplyHPlanes p;
   if (!carve_apply_h(ar, L, dim, &p)) return OTK_ERR_WORKSPACE;
   if (!apply_h_eligible(L, rows, dim) || !tensormap_encoder()) return 0;
   clear_flag_kernel<<<1, 1, 0, st>>>(p.flag);
   OTK_LAUNCH_CHECK();
-  int used = run_apply_h(x, L, rows, dim, mt32, p, y, pair, st);
+  int used = run_apply_h(x, L, rows, dim, mt32, p, y, pair, st, x_row_stride, x_batch_stride);
   if (used == 1) *flag_out = p.flag;
   return used;
 }

@@ -313,9 +313,11 @@ void apply_umma_split(const float* T32, int64_t n, float* Thi, float* Tlo, cudaS
   count_launch(1);
 }
 int apply_umma_run_planes(const float* x, int64_t L, int64_t rows, int64_t dim, const float* ms32, const float* mt32,
-                          const float* Thi, const float* Tlo, float* y, bool pair, const int* run_flag, cudaStream_t st) {
+                          const float* Thi, const float* Tlo, float* y, bool pair, const int* run_flag, cudaStream_t st,
+                          int64_t x_row_stride, int64_t x_batch_stride) {
   CUtensorMap mX, mTh, mTl, mY;
-  if (!encode_map_f32_3d(&mX, x, dim, rows, L, dim, rows * dim, 32, AP_BM)) return 0;
+  const int64_t xrs = x_row_stride > 0 ? x_row_stride : dim, xbs = x_batch_stride > 0 ? x_batch_stride : rows * dim;
+  if (!encode_map_f32_3d(&mX, x, dim, rows, L, xrs, xbs, 32, AP_BM)) return 0;
   if (!encode_map_f32_3d(&mTh, Thi, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
   if (!encode_map_f32_3d(&mTl, Tlo, dim, dim, L, dim, dim * dim, 32, 128)) return 0;
   if (!encode_map_f32_3d(&mY, y, dim, rows, L, dim, rows * dim, 32, 32)) return 0;

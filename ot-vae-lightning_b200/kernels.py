@@ -260,16 +260,20 @@ class PreparedTransport:
         N.check(st, "otk_transport_prepare")
 
     def apply(self, x: Tensor) -> Tensor:
-        """x [*lead, B, d] (any float dtype / device) -> fp32 [*lead, B, d] on the compute device."""
-        xd = _dev_tensor(x, self.device, torch.float32)
-        if tuple(xd.shape[:-2]) != tuple(self.lead) or xd.shape[-1] != self.d:
+        """x [*lead, B, d] (any float dtype / device) -> fp32 [*lead, B, d] on the compute device.  fp32 views with a unit
+        feature stride (the strided token / channel views of `utils.permute_and_flatten`) are read in place."""
+        if tuple(x.shape[:-2]) != tuple(self.lead) or x.shape[-1] != self.d:
             raise ValueError("PreparedTransport.apply: input does not match the operator's leading shape / dimension")
-        y = torch.empty_like(xd)
+        if x.shape[-2] == 0:
+            return torch.empty(x.shape, dtype=torch.float32, device=self.device)
+        xd, row_stride, batch_stride = _strided_latents(x, self.device, torch.Size(self.lead), self.d)
+        y = torch.empty(x.shape, dtype=torch.float32, device=self.device)
         with N.on_device(self.device) as ctx:
-            st = N.load().otk_apply_transport_prepared(xd.data_ptr(), self.L, xd.shape[-2], self.d, self.state.data_ptr(),
-                                                       self.state.numel(), y.data_ptr(), ctx.stream)
+            st = N.load().otk_apply_transport_prepared_strided(xd.data_ptr(), self.L, x.shape[-2], self.d, row_stride,
+                                                               batch_stride, self.state.data_ptr(), self.state.numel(),
+                                                               y.data_ptr(), ctx.stream)
         if st != N.OK:
-            N.check(st, "otk_apply_transport_prepared")
+            N.check(st, "otk_apply_transport_prepared_strided")
         return y
 
 

@@ -806,3 +806,36 @@ def test_stochastic_noise_is_sampled_with_the_requested_covariance(api):
     yd = api.apply_transport(torch.zeros(n, d, dtype=torch.double, device="cuda"), zero[0], zero[0],
                              torch.ones(d, dtype=torch.double, device="cuda"), vw, diag=True)
     assert rel(yd.std(0), vw.cpu()) < 0.03
+
+
+# ------------------------------------------------------------------------------------------------- f4: strided views into transport
+
+def test_strided_token_latents_are_transported_in_place(api):
+    """`GaussianTransport.transport` on the [T, B, D] token view of `permute_and_flatten(batch_first=False)` (strides
+    (D, T D, 1)): `otk_apply_transport_prepared_strided` reads the view through TMA without the reference's `.contiguous()`
+    copy (utils/__init__.py:260-261) and returns what the copied layout returns; odd strides take the FFMA engine."""
+    from ot_vae_lightning_b200.utils import permute_and_flatten
+    torch.manual_seed(4)
+    for B, Tk, D in [(700, 5, 128), (300, 3, 512), (180, 4, 96), (64, 2, 40)]:
+        lat = torch.randn(B, Tk, D, device="cuda") * 0.8 + torch.randn(1, Tk, D, device="cuda")
+        tgt = torch.randn(B, Tk, D, device="cuda") * 1.3 - 0.4
+        view, tview = permute_and_flatten(lat, (2,), batch_first=False), permute_and_flatten(tgt, (2,), batch_first=False)
+        assert not view.is_contiguous()
+        op = api.GaussianTransport(Tk, D, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double),
+                                   target_cfg=dict(dtype=torch.double)).cuda()
+        op.update(source_samples=view, target_samples=tview)
+        op.compute()
+        moved_view, moved_copy = op.transport(view), op.transport(view.contiguous())
+        assert moved_view.shape == (Tk, B, D) and torch.equal(moved_view, moved_copy)
+        want = (view.double() - op.source_model.mean[:, None]) @ op.transport_operator.transpose(-1, -2) + op.target_model.mean[:, None]
+        assert rel(moved_view, want.cpu()) < TOL_MATFUN
+        ragged = op.transport(view[:, 11:48])                                   # a slice of the view: offset + same strides
+        assert torch.equal(ragged, moved_copy[:, 11:48])
+    # feature-sliced latents: row stride 130 (not a multiple of 4 elements) -> FFMA engine, same numbers
+    wide = torch.randn(257, 130, device="cuda")
+    sl = wide[:, :128]
+    op = api.GaussianTransport(128, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double),
+                               target_cfg=dict(dtype=torch.double)).cuda()
+    op.update(source_samples=sl.contiguous(), target_samples=sl.contiguous() * 1.5 + 0.5)
+    op.compute()
+    assert rel(op.transport(sl), op.transport(sl.contiguous()).cpu()) < 1e-5
