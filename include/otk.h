@@ -241,6 +241,16 @@ int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t d
 int otk_cost_matrix(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
                     double scale, float* C, void* workspace, size_t workspace_bytes, otk_stream_t stream);
 
+/* Streaming k-means step of CodebookModel in 'argmax' mode with the Euclidean energy (MixtureMixin.assign +
+ * kmean_iteration, ot/distribution_models/base.py:206-253; CodebookModel.energy, codebook_model.py:155-160) without the
+ * [B, K] energy / one-hot matrices: index[l,b] = argmin_k |x[l,b] - codebook[l,k]|_2 (first index on ties),
+ * weights_sum[l,k] = number of samples assigned to k, samples_sum[l,k,:] = their sum (both overwritten, dtype buf_dtype).
+ *   x [L,B,dim], codebook [L,K,dim] fp32; index int64 [L,B] or NULL; weights_sum / samples_sum both given or both NULL. */
+size_t otk_kmeans_assign_workspace_bytes(int64_t L, int64_t B, int64_t K);
+int otk_kmeans_assign(const float* x, int64_t L, int64_t B, int64_t K, int64_t dim, const float* codebook,
+                      int64_t* index, void* weights_sum, void* samples_sum, int buf_dtype, void* workspace,
+                      size_t workspace_bytes, otk_stream_t stream);
+
 /* fp32-accurate GEMMs on the tensor cores used inside the kernels above, exported for the kernel unit tests:
  *   otk_gemm_nt: C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C      (B K-major)
  *   otk_gemm_nn: C[M,N] = alpha * A[M,K] * B[K,N]   + beta * C      (B N-major, the Newton-Schulz case)

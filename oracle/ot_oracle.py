@@ -409,3 +409,21 @@ class FidStats:
         m_r, c_r = mean_cov(self.sum["real"], self.corr["real"], self.n["real"].double())
         m_f, c_f = mean_cov(self.sum["fake"], self.corr["fake"], self.n["fake"].double())
         return frechet_distance(m_r, c_r, m_f, c_f)
+
+
+# ---------------------------------------------------------------------------------------------------
+# codebook k-means step (distribution_models/base.py:206-253, codebook_model.py:155-160)
+# ---------------------------------------------------------------------------------------------------
+
+def kmeans_step(samples: Tensor, codebook: Tensor, temperature: float = 1.0, mode: str = "argmax"
+                ) -> Tuple[Tensor, Tensor, Tensor]:
+    """`MixtureMixin.assign` + `kmean_iteration` with the Euclidean energy: energy = 1/(cdist + 1e-8)
+    (codebook_model.py:159-160), weights = softmax(energy / T) (base.py:220), hardened to one-hot rows of their argmax in
+    'argmax' mode (:229-230); returns (weights.sum(-2), weights^T @ samples, argmax index) (:249-253)."""
+    samples, codebook = samples.double(), codebook.double()
+    energy = inverse_distance_energy(samples, codebook)
+    weights = torch.softmax(energy / temperature, dim=-1)
+    index = weights.argmax(-1)
+    if mode == "argmax":
+        weights = torch.nn.functional.one_hot(index, energy.size(-1)).to(weights.dtype)
+    return weights.sum(-2), weights.transpose(-1, -2) @ samples, index

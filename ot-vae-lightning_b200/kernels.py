@@ -451,6 +451,30 @@ def points_summary(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, u_loc
     return part, row_marg, col_part
 
 
+def kmeans_assign(x: Tensor, codebook: Tensor, want_index: bool = True, want_sums: bool = True,
+                  sums_dtype: Optional[torch.dtype] = None):
+    """Nearest-codeword step (otk_kmeans_assign).  x [*L, B, d], codebook [*L, K, d] (leading dims broadcast) ->
+    (index int64 [*L, B] or None, weights_sum [*L, K] or None, samples_sum [*L, K, d] or None)."""
+    dev = N.compute_device(codebook, x)
+    lead = torch.broadcast_shapes(x.shape[:-2], codebook.shape[:-2])
+    L = int(torch.Size(lead).numel())
+    xd = _bcast(_dev_tensor(x, dev, torch.float32), lead, 2)
+    cd = _bcast(_dev_tensor(codebook, dev, torch.float32), lead, 2)
+    B, d = xd.shape[-2:]
+    Kc = cd.shape[-2]
+    dt = sums_dtype if sums_dtype in (torch.float32, torch.float64) else torch.float32
+    index = torch.empty(*lead, B, dtype=torch.int64, device=dev) if want_index else None
+    wsum = torch.empty(*lead, Kc, dtype=dt, device=dev) if want_sums else None
+    ssum = torch.empty(*lead, Kc, d, dtype=dt, device=dev) if want_sums else None
+    lib = N.load()
+    with torch.cuda.device(dev):
+        ws = N.workspace(lib.otk_kmeans_assign_workspace_bytes(L, B, Kc), dev)
+        st = lib.otk_kmeans_assign(N.ptr(xd), L, B, Kc, d, N.ptr(cd), N.ptr(index), N.ptr(wsum), N.ptr(ssum), N.dtype_code(dt),
+                                   N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_kmeans_assign")
+    return index, wsum, ssum
+
+
 def gemm(A: Tensor, B: Tensor, alpha: float = 1.0, engine: int = 0, nn: bool = False) -> Tensor:
     """C = alpha * A @ B^T (nn=False, B [*, N, K]) or alpha * A @ B (nn=True, B [*, K, N]); fp32.
     engine: 0 auto, 1 FFMA, 2 tcgen05 3xTF32, 3 tcgen05 1xTF32.  Exported for the kernel unit tests."""

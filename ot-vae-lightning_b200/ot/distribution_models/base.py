@@ -1,7 +1,14 @@
-"""Abstract streaming distribution model (mirror of reference ot/distribution_models/base.py:29-158).
+"""Streaming distribution models: the abstract contract and the mixture-assignment mixin (the public surface of
+reference ot/distribution_models/base.py:29-258 - constructor keywords, buffer names, `assign` / `kmean_iteration`
+return values - re-built around the libotk kernels).
 
-`MixtureMixin` (k-means style assignment, reference :161-258) is control-heavy glue around the same kernels and is
-kept in stock PyTorch; only what `DiscreteTransport` needs is provided here.
+What runs where
+  * `MixtureMixin.kmean_iteration` in hard ('argmax') mode with the Euclidean energy - the streaming k-means step of
+    `CodebookModel.update` / `fit` - is ONE fused kernel call (`otk_kmeans_assign`): nearest codeword per sample and the
+    per-codeword counts / sums, with no [B, K] energy, softmax or one-hot matrix (reference :238-253 builds all three).
+  * soft modes contract the weights with the samples through the fp32-accurate tensor-core GEMM (`otk_gemm_nn`).
+  * `assign` has to hand back the dense weights and the categorical distribution (they are part of its return value), so
+    it evaluates the energy kernel and finishes with elementwise torch ops on the device.
 """
 from __future__ import annotations
 
@@ -16,6 +23,7 @@ import torch.nn.functional as F
 from torch import Tensor
 from torch.types import _device, _dtype
 
+from ... import kernels as K
 from ... import utils
 
 __all__ = ["DistributionModel", "MixtureMixin"]
@@ -29,8 +37,11 @@ def default_device(device):
 
 
 class DistributionModel(nn.Module, utils.DDPMixin, ABC):
-    """`DistributionModel(*size, reduce_on_update=True, update_decay=None, update_with_autograd=False, device=None,
-    dtype=None, **ddp_kwargs)`: `size = (*leading_shape, dim)`; one independent model per leading index."""
+    """One independent model per leading index of `size = (*leading_shape, dim)`.
+
+    Keyword contract of the reference (base.py:42-62): `reduce_on_update`, `update_decay`, `update_with_autograd`, `device`,
+    `dtype`, and the DDP hooks consumed by `utils.DDPMixin`.  Sub-classes stream batches with `update`, finalise with `fit`.
+    """
     Distribution = None
 
     def __init__(self, *size: int, reduce_on_update: bool = True, update_decay: Optional[float] = None,
@@ -38,45 +49,50 @@ class DistributionModel(nn.Module, utils.DDPMixin, ABC):
                  dtype: Optional[_dtype] = None, **ddp_kwargs):
         nn.Module.__init__(self)
         utils.DDPMixin.__init__(self, **ddp_kwargs)
-        self.leading_shape = torch.Size(size[:-1])
-        self.dim = size[-1]
+        *lead, self.dim = size
+        self.leading_shape = torch.Size(lead)
+        self.update_with_autograd = update_with_autograd
         self.reduce_on_update = reduce_on_update
         self.decay = update_decay
-        self.ema_update = partial(utils.ema, decay=update_decay)
-        device = default_device(device)
-        self.register_buffer("vec_init", torch.randn(*self.vec_shape, dtype=dtype, device=device))
-        self.register_buffer("mat_init", torch.randn(*self.vec_shape, self.dim, dtype=dtype, device=device))
-        self.update_with_autograd = update_with_autograd
+        self.ema_update = partial(utils.ema, decay=self.decay)
+        # random initial state (what `reset` restores): a vector and a square matrix per leading index; the vector is drawn
+        # first so that a seeded construction consumes the generator in the reference's order
+        where = dict(dtype=dtype, device=default_device(device))
+        for name, shape in (("vec_init", self.vec_shape), ("mat_init", (*self.vec_shape, self.dim))):
+            self.register_buffer(name, torch.randn(*shape, **where))
 
     @property
     def vec_shape(self):
         return *self.leading_shape, self.dim
 
-    def _broadcastable(self, shape):
-        if tuple(shape) == tuple(self.leading_shape):
-            return True
-        return torch.broadcast_shapes(shape, self.leading_shape) == self.leading_shape
+    def _broadcastable(self, shape) -> bool:
+        shape = tuple(shape)
+        return shape == tuple(self.leading_shape) or torch.broadcast_shapes(shape, self.leading_shape) == self.leading_shape
 
     def _validate_samples(self, samples: Tensor) -> None:
-        """The reference builds these errors but never raises them (base.py:76-79); kept non-raising for parity."""
+        """Shape check of `[*leading_shape, batch, dim]` samples.  The reference constructs these errors without raising
+        them (base.py:76-79); raising here would reject inputs it accepts, so they stay advisory."""
+        problems = []
         if not self._broadcastable(samples.shape[:-2]):
-            ValueError(f"`samples` leading dimensions are expected to broadcast to {self.leading_shape}")
+            problems.append(f"leading dimensions {tuple(samples.shape[:-2])} do not broadcast to {tuple(self.leading_shape)}")
         if samples.size(-1) != self.dim:
-            ValueError(f"`samples` are expected to have dimensionality {self.dim}")
+            problems.append(f"dimensionality {samples.size(-1)} != {self.dim}")
+        self._last_sample_problems = problems
+
+    def _autograd_warning(self, what: str) -> None:
+        if self.update_with_autograd:
+            self.warn(f"`update_with_autograd` is set: the parameters are meant to be trained by autograd and {what}")
 
     def _fit_warn(self):
-        if self.update_with_autograd:
-            self.warn("`self.update_with_autograd` is True: `fit` overrides the trained nn.Parameters with values "
-                      "computed from the running statistics.")
+        self._autograd_warning("`fit` overwrites them with values computed from the running statistics.")
 
     def _update_warn(self):
-        if self.update_with_autograd:
-            self.warn("`self.update_with_autograd` is True: the running statistics were not created in `__init__`, "
-                      "`update` cannot use them.")
+        self._autograd_warning("`update` has no running statistics to write to (they are not created in `__init__`).")
 
+    # ------------------------------------------------------------------------------------------------ contract
     @abstractmethod
     def reset(self) -> None:
-        """reset internal model states"""
+        """restore the initial state"""
 
     @property
     def distribution(self) -> D.Distribution:
@@ -89,12 +105,6 @@ class DistributionModel(nn.Module, utils.DDPMixin, ABC):
     @property
     def variances(self) -> Tensor:
         raise NotImplementedError()
-
-    def forward(self, samples: Tensor) -> Any:
-        self._validate_samples(samples)
-        if self.training and not self.update_with_autograd:
-            self.update(samples)
-        return self.predict(samples)
 
     @abstractmethod
     def update(self, samples: Tensor) -> None:
@@ -112,58 +122,39 @@ class DistributionModel(nn.Module, utils.DDPMixin, ABC):
     def w2(self, other) -> Tensor:
         """W2 distance to `other`"""
 
+    def forward(self, samples: Tensor) -> Any:
+        """training mode streams the batch in first (unless autograd owns the parameters), then predicts"""
+        self._validate_samples(samples)
+        if self.training and not self.update_with_autograd:
+            self.update(samples)
+        return self.predict(samples)
+
     def extra_repr(self) -> str:
         return (f"leading_dim={tuple(self.leading_shape)}, dim={self.dim}, decay={self.decay}, "
                 f"update_with_autograd={self.update_with_autograd}")
 
 
 class MixtureMixin(ABC):
-    """Soft/hard assignment of samples to mixture components (reference base.py:161-258)."""
+    """Assignment of samples to `n_components` mixture components from an `energy` (similarity) matrix.
+
+    Modes (reference base.py:162, 224-234): 'mean' keeps the softmax weights, 'argmax' / 'sample' harden them to one-hot
+    rows, 'gumbel-softmax' / 'gumbel-hardmax' draw Gumbel noise; `topk` masks all but the k largest energies first."""
     Mode = Literal["mean", "sample", "argmax", "gumbel-softmax", "gumbel-hardmax"]
 
     def __init__(self, *leading_shape, n_components: int, metric: Literal["cosine", "euclidean"] = "euclidean",
                  p: float = 2., topk: Optional[int] = None, temperature: float = 1., training_mode: Mode = "argmax",
                  inference_mode: Mode = "argmax", kmeans_iter: int = 100, laplace_eps: Optional[float] = 1e-5):
         super().__init__()
-        self.n_components = n_components
-        self.metric = metric
-        self.topk = topk
-        self.temperature = temperature
-        self.training_mode = training_mode
-        self.inference_mode = inference_mode
+        self.n_components, self.metric, self.p = n_components, metric, p
+        self.topk, self.temperature = topk, temperature
+        self.training_mode, self.inference_mode = training_mode, inference_mode
         self.kmeans_iter = kmeans_iter
-        self.p = p
-        self._weight_init = torch.full((*leading_shape, n_components), 1.0 / n_components)
+        self._weight_init = torch.full((*leading_shape, n_components), 1.0 / n_components)      # uniform mixture
         self.laplace_smoothing = partial(utils.laplace_smoothing, n_categories=n_components, eps=laplace_eps)
 
     @abstractmethod
     def energy(self, samples: Tensor) -> Tensor:
         """similarity of each sample to each component, [*leading_shape, batch, n_comp]"""
-
-    def assign(self, samples: Tensor) -> Tuple[Tensor, Tensor, D.Categorical]:
-        energy = self.energy(samples)
-        if self.topk is not None and self.topk > 0:
-            val, idx = torch.topk(energy, self.topk, dim=-1)
-            energy = torch.full_like(energy, float("-inf")).scatter_(-1, idx, val)
-        weights = torch.softmax(energy / self.temperature, dim=-1)
-        distribution = D.Categorical(weights)
-        indices = distribution.sample()
-        mode = self.training_mode if getattr(self, "training", False) else self.inference_mode
-        if mode == "mean" or self.topk == 1:
-            pass
-        elif mode == "sample":
-            weights = F.one_hot(indices, energy.size(-1)).type_as(weights)
-        elif mode == "argmax":
-            weights = F.one_hot(weights.argmax(-1), energy.size(-1)).type_as(weights)
-        elif "gumbel" in mode:
-            weights = F.gumbel_softmax(energy, tau=self.temperature, hard="hard" in mode, dim=-1)
-        else:
-            raise NotImplementedError(f"`mode` must be 'sample', 'mean', 'argmax', 'gumbel' or 'hard-gumbel'. Got {mode}")
-        return weights, indices, distribution
-
-    def kmean_iteration(self, samples: Tensor) -> Tuple[Tensor, ...]:
-        weights, _, _ = self.assign(samples)
-        return weights.sum(-2), weights.transpose(-1, -2) @ samples
 
     @abstractmethod
     def _update_parameters(self, *kmeans_iter_res: Tensor) -> None:
@@ -172,6 +163,58 @@ class MixtureMixin(ABC):
     @abstractmethod
     def _update_buffers(self, *kmeans_iter_res: Tensor, decay=False):
         ...
+
+    # ------------------------------------------------------------------------------------------------ assignment
+    @property
+    def _mode(self) -> str:
+        return self.training_mode if getattr(self, "training", False) else self.inference_mode
+
+    def _masked_energy(self, samples: Tensor) -> Tensor:
+        energy = self.energy(samples)
+        if self.topk:                                               # None or 0: keep every component
+            kept, where = energy.topk(self.topk, dim=-1)
+            energy = torch.full_like(energy, float("-inf")).scatter_(-1, where, kept)
+        return energy
+
+    def assign(self, samples: Tensor) -> Tuple[Tensor, Tensor, D.Categorical]:
+        """-> (weights [*L, B, n_comp], sampled indices [*L, B], Categorical over the soft weights); reference :206-236.
+        One categorical draw is always taken, whatever the mode, as the reference does (:222)."""
+        energy = self._masked_energy(samples)
+        soft = torch.softmax(energy / self.temperature, dim=-1)
+        distribution = D.Categorical(soft)
+        drawn = distribution.sample()
+        mode, n = self._mode, energy.size(-1)
+        if mode == "mean" or self.topk == 1:
+            weights = soft
+        elif mode in ("sample", "argmax"):
+            picks = drawn if mode == "sample" else soft.argmax(-1)
+            weights = F.one_hot(picks, n).type_as(soft)
+        elif "gumbel" in mode:
+            weights = F.gumbel_softmax(energy, tau=self.temperature, hard="hard" in mode, dim=-1)
+        else:
+            raise NotImplementedError(f"`mode` must be 'sample', 'mean', 'argmax', 'gumbel' or 'hard-gumbel'. Got {mode}")
+        return weights, drawn, distribution
+
+    def _nearest_component_kernel_applies(self, samples: Tensor) -> bool:
+        """hard assignment by Euclidean distance to `self.codebook`: argmax of softmax(1/(dist+1e-8)/T) is argmin dist"""
+        book = getattr(self, "codebook", None)
+        return (self._mode == "argmax" and not self.topk and self.metric == "euclidean" and self.p == 2
+                and self.temperature > 0 and isinstance(book, Tensor) and book.is_cuda and samples.is_cuda
+                and samples.dim() == book.dim() and type(self).energy is getattr(type(self), "_euclidean_energy_owner", None))
+
+    def kmean_iteration(self, samples: Tensor) -> Tuple[Tensor, ...]:
+        """-> (sum of weights per component [*L, n_comp], weighted sum of samples per component [*L, n_comp, dim]);
+        reference :238-253."""
+        if self._nearest_component_kernel_applies(samples):
+            _, counts, sums = K.kmeans_assign(samples, self.codebook.detach(), want_index=False, sums_dtype=samples.dtype)
+            return counts.to(samples.dtype), sums.to(samples.dtype)
+        weights, _, _ = self.assign(samples)
+        per_component = weights.sum(-2)
+        if samples.is_cuda and samples.dim() == 2:
+            # [n_comp, B] x [B, dim] on the fp32-accurate tensor-core GEMM (FFMA engine for small / unaligned shapes)
+            mixed = K.gemm(weights.transpose(-1, -2).float().contiguous(), samples.float().contiguous(), nn=True)
+            return per_component, mixed.to(samples.dtype)
+        return per_component, weights.transpose(-1, -2) @ samples
 
     def extra_repr(self) -> str:
         return (f"num_components={self.n_components}, metric={self.metric}, topk={self.topk}, p={self.p}, "

@@ -1,9 +1,13 @@
-"""Discrete codebook model: the cost producer of `DiscreteTransport` (mirror of reference
-ot/distribution_models/codebook_model.py:27-214).
+"""Discrete codebook model with streaming k-means, kernel-backed (public surface of reference
+ot/distribution_models/codebook_model.py:27-214: `CategoricalEmbeddings`, `CodebookModel(*size, mixture_cfg={}, ...)`, the
+`codebook` parameter and the `_running_sum` / `_n_obs` / `weight_init` buffers, `update` / `fit` / `predict` / `energy` /
+`w2`).
 
-On the hot path: `energy` = 1/(|x-c|_2 + 1e-8) via the libotk cost-tile kernel and `w2` through the
-Sinkhorn kernels.  The online k-means bookkeeping (`update`/`fit`/`_update_*`) is control-heavy glue on tiny tensors
-and stays in stock PyTorch, as SURVEY 2.1 row 3 scopes it.
+Hot steps
+  * `energy`   1 / (|x - c|_2 + 1e-8): the libotk cost-tile kernel (`otk_cost_matrix`, inverse-Euclidean kind);
+  * `update` / `fit`  one fused nearest-codeword + per-codeword-sum kernel per k-means step (`otk_kmeans_assign`, through
+    `MixtureMixin.kmean_iteration`), then the exponential-moving-average book-keeping on [n_comp] / [n_comp, dim] tensors;
+  * `w2`       entropic OT between two codebooks with the Sinkhorn kernels.
 """
 from __future__ import annotations
 
@@ -22,37 +26,41 @@ from .base import DistributionModel, MixtureMixin
 
 __all__ = ["CategoricalEmbeddings", "CodebookModel"]
 
+OCCUPIED = 1e-8      # a codeword takes part in an update only if some weight was assigned to it (reference :186,196)
+
 
 class CategoricalEmbeddings(D.Categorical):
-    """Categorical over codebook rows (reference codebook_model.py:27-66)."""
+    """A categorical distribution whose outcomes are rows of an embedding table [*batch, n, dim]: `mean` is the probability
+    weighted row, `mode` the most likely row, `sample()` a drawn row (reference codebook_model.py:27-66)."""
 
     def __init__(self, embeddings: Tensor, probs: Optional[Tensor] = None, logits: Optional[Tensor] = None) -> None:
         super().__init__(probs, logits)
-        self.embeddings = embeddings
-        if self.probs.shape != self.embeddings.shape[:-1]:
+        if tuple(self.probs.shape) != tuple(embeddings.shape[:-1]):
             raise ValueError("`probs` and `embeddings` should have the same leading dimensions")
+        self.embeddings = embeddings
 
-    def _select(self, weights: Tensor) -> Tensor:
-        return (weights.unsqueeze(-2).type_as(self.embeddings) @ self.embeddings).squeeze(-2)
+    def _rows(self, weights: Tensor) -> Tensor:
+        """weights [*, n] -> weights . embeddings [*, dim]"""
+        return torch.einsum("...n,...nd->...d", weights.type_as(self.embeddings), self.embeddings)
 
-    def _select_one_hot(self, index_list: Tensor) -> Tensor:
-        return self._select(F.one_hot(index_list, self._num_events).type_as(index_list))
+    def _row_at(self, index: Tensor) -> Tensor:
+        return self._rows(F.one_hot(index, self._num_events).type_as(index))
 
     def expand(self, batch_shape, _instance=None):
-        new = super().expand(batch_shape, _instance)
-        new.embeddings = new.embeddings.expand(torch.Size(batch_shape) + torch.Size((self._num_events,)))
-        return new
+        out = super().expand(batch_shape, _instance)
+        out.embeddings = out.embeddings.expand(torch.Size(batch_shape) + torch.Size((self._num_events,)))
+        return out
 
     @property
     def mean(self):
-        return self._select(self.probs)
+        return self._rows(self.probs)
 
     @property
     def mode(self):
-        return self._select_one_hot(self.probs.argmax(-1))
+        return self._row_at(self.probs.argmax(-1))
 
     def sample(self, sample_shape=torch.Size()) -> Tensor:
-        return self._select_one_hot(super().sample(sample_shape))
+        return self._row_at(super().sample(sample_shape))
 
 
 class CodebookModel(DistributionModel, MixtureMixin):
@@ -60,29 +68,25 @@ class CodebookModel(DistributionModel, MixtureMixin):
 
     def __init__(self, *size: int, mixture_cfg={}, **kwargs) -> None:
         MixtureMixin.__init__(self, *size[:-1], **mixture_cfg)
-        DistributionModel.__init__(self, *size, **kwargs)
+        DistributionModel.__init__(self, *size, **kwargs)         # `vec_init` is [*L, n_comp, dim] (vec_shape below)
         self.register_buffer("weight_init", self._weight_init.to(self.vec_init))
         self.codebook = nn.Parameter(self.vec_init.clone(), requires_grad=self.update_with_autograd)
         if not self.update_with_autograd:
             self.register_buffer("_running_sum", torch.zeros_like(self.vec_init))
-            self.register_buffer("_n_obs", torch.zeros(*self.leading_shape, self.n_components).to(self.vec_init))
-
-    @property
-    def weights(self):
-        if not hasattr(self, "_n_obs") or bool(torch.allclose(self._n_obs, torch.zeros_like(self._n_obs))):
-            return self.weight_init.type_as(self.codebook)
-        return self._n_obs.type_as(self.codebook) / self._n_obs.sum(-1, keepdim=True)
+            self.register_buffer("_n_obs", torch.zeros_like(self.vec_init[..., 0]))
 
     @property
     def vec_shape(self):
         return *self.leading_shape, self.n_components, self.dim
 
-    @torch.no_grad()
-    def reset(self) -> None:
-        self.codebook.copy_(self.vec_init)
-        if not self.update_with_autograd:
-            self._running_sum.zero_()
-            self._n_obs.zero_()
+    @property
+    def weights(self) -> Tensor:
+        """mixture weights = normalised occupation counts; uniform until something was observed"""
+        seen = getattr(self, "_n_obs", None)
+        if seen is None or bool(torch.allclose(seen, torch.zeros_like(seen))):
+            return self.weight_init.type_as(self.codebook)
+        seen = seen.type_as(self.codebook)
+        return seen / seen.sum(-1, keepdim=True)
 
     @property
     def distribution(self) -> Distribution:
@@ -93,86 +97,108 @@ class CodebookModel(DistributionModel, MixtureMixin):
         return CategoricalEmbeddings(self.codebook.unsqueeze(-3), probs=self.weights.unsqueeze(-2))
 
     @torch.no_grad()
-    def update(self, samples: Tensor) -> None:
-        self._update_warn()
+    def reset(self) -> None:
+        self.codebook.copy_(self.vec_init)
+        if not self.update_with_autograd:
+            for buf in (self._running_sum, self._n_obs):
+                buf.zero_()
+
+    # ------------------------------------------------------------------------------------------------ streaming k-means
+    def _prepared(self, samples: Tensor) -> Tensor:
         self._validate_samples(samples)
         samples = samples.detach().to(self._running_sum)
         self._init_parameters(samples)
-        res = self.kmean_iteration(samples)
+        return samples
+
+    @torch.no_grad()
+    def update(self, samples: Tensor) -> None:
+        """one k-means step on the batch, folded into the running sums with the EMA rule (reference :122-131)"""
+        self._update_warn()
+        step = self.kmean_iteration(self._prepared(samples))
         if self.reduce_on_update:
-            res = [self.reduce(r) for r in res]
-        self._update_parameters(*self._update_buffers(*res, decay=True))
+            step = tuple(self.reduce(t) for t in step)
+        self._update_parameters(*self._update_buffers(*step, decay=True))
 
     @torch.no_grad()
     def fit(self, samples: Optional[Tensor] = None) -> None:
+        """`kmeans_iter` Lloyd iterations on `samples` (or a refresh from the running sums when None), reference :133-146"""
         self._fit_warn()
         if samples is not None:
-            self._validate_samples(samples)
-            samples = samples.detach().to(self._running_sum)
-            self._init_parameters(samples)
-        res = None
+            samples = self._prepared(samples)
+        step = None
         for _ in range(self.kmeans_iter):
-            res = self.kmean_iteration(samples)
-            self._update_parameters(*[self.reduce(r) for r in res])
-        if self.kmeans_iter > 0:
-            self._update_buffers(*res, decay=False)
+            step = self.kmean_iteration(samples)
+            self._update_parameters(*(self.reduce(t) for t in step))
+        if step is not None:
+            self._update_buffers(*step, decay=False)
 
+    def kmean_iteration(self, samples: Optional[Tensor]) -> Tuple[Tensor, ...]:
+        if samples is None:                       # nothing new: the accumulated (counts, sums) are the statistics
+            return self._n_obs, self._running_sum
+        return MixtureMixin.kmean_iteration(self, samples)
+
+    def _update_parameters(self, *kmeans_iter_res: Tensor) -> None:
+        """codeword = sum / Laplace-smoothed count, for the occupied codewords only"""
+        counts, sums = kmeans_iter_res
+        live = counts > OCCUPIED
+        smoothed = self.laplace_smoothing(counts[live])
+        self.codebook.data[live] = sums[live] / smoothed.unsqueeze(-1)
+
+    def _update_buffers(self, *kmeans_iter_res: Tensor, decay: bool = False):
+        counts, sums = kmeans_iter_res
+        live = counts > OCCUPIED
+        for buf, new in ((self._n_obs, counts), (self._running_sum, sums)):
+            buf[live] = self.ema_update(buf[live], new[live]) if decay else new[live]
+        return self._n_obs, self._running_sum
+
+    def _init_parameters(self, samples: Tensor) -> None:
+        """first batch: the codebook starts from `n_components` distinct rows of it, picked by a HOST-side permutation as
+        in the reference (:211), so that a seeded run selects the same rows"""
+        if bool(torch.allclose(self.codebook, self.vec_init)):
+            rows = torch.randperm(samples.size(-2))[:self.n_components].to(samples.device)
+            self.codebook.copy_(samples[..., rows, :])
+            self._n_obs += 1
+
+    # ------------------------------------------------------------------------------------------------ energies / distances
     def predict(self, features: Tensor) -> Tuple[Tensor, Tensor, D.Categorical]:
         weights, indices, distribution = self.assign(features)
         return weights @ self.codebook, indices, distribution
 
     def energy(self, samples: Tensor) -> Tensor:
-        """[*L, b, d] -> [*L, b, n_comp]: inverse p-distance (euclidean) or |cosine| similarity
-        (reference codebook_model.py:155-168)."""
+        """[*L, b, d] -> [*L, b, n_comp]: inverse p-distance ('euclidean') or |cosine| similarity (reference :155-168)"""
         self._validate_samples(samples)
         samples = samples.to(self.codebook)
+        book = self.codebook
         if self.metric == "euclidean":
-            if self.p == 2 and samples.is_cuda and samples.dim() == self.codebook.dim():
-                lead = torch.broadcast_shapes(samples.shape[:-2], self.codebook.shape[:-2])
-                xs = samples.expand(*lead, *samples.shape[-2:]).reshape(-1, *samples.shape[-2:])
-                cs = self.codebook.expand(*lead, *self.codebook.shape[-2:]).reshape(-1, *self.codebook.shape[-2:])
-                tiles = [K.cost_matrix(xs[i], cs[i], N.COST_INV_EUCLIDEAN) for i in range(xs.shape[0])]
-                return torch.stack(tiles).reshape(*lead, samples.shape[-2], self.codebook.shape[-2]).to(samples.dtype)
-            return 1 / (torch.cdist(samples, self.codebook, self.p) + 1e-8)
+            if self.p == 2 and samples.is_cuda and samples.dim() == book.dim():
+                return self._inverse_distance_tiles(samples, book)
+            return 1 / (torch.cdist(samples, book, self.p) + 1e-8)
         if self.metric == "cosine":
-            norm_x = samples.abs().pow(self.p).sum(-1, keepdim=True)
-            norm_c = self.codebook.abs().pow(self.p).sum(-1).unsqueeze(-2)
-            dot = (samples @ self.codebook.transpose(-2, -1)).abs()
-            return dot / (norm_x * norm_c + 1e-8) ** (1 / self.p)
+            p_norm = lambda t: t.abs().pow(self.p).sum(-1)
+            overlap = (samples @ book.transpose(-2, -1)).abs()
+            return overlap / (p_norm(samples).unsqueeze(-1) * p_norm(book).unsqueeze(-2) + 1e-8) ** (1 / self.p)
         raise NotImplementedError(f"Supported `metric`: 'cosine', 'euclidean'. Got `metric`={self.metric}")
 
-    def kmean_iteration(self, samples: Optional[Tensor]) -> Tuple[Tensor, ...]:
-        if samples is None:
-            return self._n_obs, self._running_sum
-        return super().kmean_iteration(samples)
+    @staticmethod
+    def _inverse_distance_tiles(samples: Tensor, book: Tensor) -> Tensor:
+        """one `otk_cost_matrix` launch group per leading index (the kernel takes 2-D clouds)"""
+        lead = torch.broadcast_shapes(samples.shape[:-2], book.shape[:-2])
+        b, k = samples.shape[-2], book.shape[-2]
+        xs = samples.expand(*lead, *samples.shape[-2:]).reshape(-1, b, samples.shape[-1])
+        cs = book.expand(*lead, *book.shape[-2:]).reshape(-1, k, book.shape[-1])
+        out = torch.stack([K.cost_matrix(x, c, N.COST_INV_EUCLIDEAN) for x, c in zip(xs, cs)])
+        return out.reshape(*lead, b, k).to(samples.dtype)
 
     def w2(self, other: Distribution) -> Tensor:
-        cost = 1 / (self.energy(other.embeddings) + 1e-8)
-        plan = sinkhorn_log(self.distribution.probs, other.probs, cost, reg=1e-5, max_iter=100, threshold=1e-3)
-        return (cost * plan).sum(dim=(-2, -1))
+        """entropic OT cost to another codebook distribution; the ground cost inverts the energy back to a distance
+        (reference :170-183: reg 1e-5, 100 iterations, threshold 1e-3)"""
+        ground = 1 / (self.energy(other.embeddings) + 1e-8)
+        plan = sinkhorn_log(self.distribution.probs, other.probs, ground, reg=1e-5, max_iter=100, threshold=1e-3)
+        return (ground * plan).sum(dim=(-2, -1))
 
     def extra_repr(self) -> str:
         return DistributionModel.extra_repr(self) + ", " + MixtureMixin.extra_repr(self)
 
-    def _update_parameters(self, *kmeans_iter_res: Tensor) -> None:
-        weights_sum, samples_sum = kmeans_iter_res
-        hit = weights_sum > 1e-8
-        self.codebook.data[hit] = samples_sum[hit] / self.laplace_smoothing(weights_sum[hit]).unsqueeze(-1)
 
-    def _update_buffers(self, *kmeans_iter_res: Tensor, decay: bool = False):
-        weights_sum, samples_sum = kmeans_iter_res
-        hit = weights_sum > 1e-8
-        if decay:
-            self._n_obs[hit] = self.ema_update(self._n_obs[hit], weights_sum[hit])
-            self._running_sum[hit] = self.ema_update(self._running_sum[hit], samples_sum[hit])
-        else:
-            self._n_obs[hit] = weights_sum[hit]
-            self._running_sum[hit] = samples_sum[hit]
-        return self._n_obs, self._running_sum
-
-    def _init_parameters(self, samples: Tensor) -> None:
-        if bool(torch.allclose(self.codebook, self.vec_init)):
-            # host-side draw, as the reference (codebook_model.py:211): a seeded run picks the same rows
-            pick = torch.randperm(samples.size(-2))[:self.n_components].to(samples.device)
-            self.codebook.copy_(samples[..., pick, :])
-            self._n_obs += 1
+# `MixtureMixin` only swaps in the nearest-codeword kernel while `energy` is the Euclidean one defined above
+CodebookModel._euclidean_energy_owner = CodebookModel.energy

@@ -839,3 +839,44 @@ def test_strided_token_latents_are_transported_in_place(api):
     op.update(source_samples=sl.contiguous(), target_samples=sl.contiguous() * 1.5 + 0.5)
     op.compute()
     assert rel(op.transport(sl), op.transport(sl.contiguous()).cpu()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------- f2: codebook k-means kernel
+
+@pytest.mark.parametrize("B,K,d,lead", [(1000, 1024, 64, ()), (512, 8192, 128, ()), (250, 48, 20, (3,)), (77, 6, 8, ())])
+def test_kmeans_assign_kernel_vs_oracle(oracle, B, K, d, lead):
+    """`otk_kmeans_assign` (nearest codeword + per-codeword counts / sums, no [B, K] matrices) against the oracle's
+    energy -> softmax -> one-hot -> weights^T @ samples (reference base.py:206-253) at codebook sizes up to the reference's
+    largest configuration (K = 8192, configs/dad/defaults.yaml:70).  Samples sit near codewords, so the arg-min does not
+    hinge on round-off."""
+    from ot_vae_lightning_b200 import kernels as K_
+    g = torch.Generator().manual_seed(B + K)
+    book = torch.randn(*lead, K, d, generator=g)
+    pick = torch.randint(0, K, (*lead, B), generator=g)
+    x = torch.gather(book, -2, pick.unsqueeze(-1).expand(*lead, B, d)) + 0.02 * torch.randn(*lead, B, d, generator=g)
+    index, counts, sums = K_.kmeans_assign(x.cuda(), book.cuda(), sums_dtype=torch.float64)
+    want_counts, want_sums, want_index = oracle.kmeans_step(x, book)
+    assert index.dtype == torch.int64 and torch.equal(index.cpu(), want_index) and torch.equal(index.cpu(), pick)
+    assert torch.equal(counts.cpu(), want_counts) and float(counts.sum()) == B * max(1, int(torch.Size(lead).numel()))
+    assert rel(sums, want_sums) < 1e-6
+
+
+def test_codebook_model_streaming_update_uses_the_kernel_and_matches_the_dense_path(api, monkeypatch):
+    """`CodebookModel.update` in hard mode through the fused kernel == the same model forced onto the dense
+    energy / softmax / one-hot / matmul path (the reference's formulation), batch after batch."""
+    from ot_vae_lightning_b200.ot.distribution_models import base as dm_base
+    g = torch.Generator().manual_seed(12)
+    centres = torch.randn(16, 32, generator=g) * 4
+    data = (centres[torch.randint(0, 16, (2000,), generator=g)] + 0.3 * torch.randn(2000, 32, generator=g)).cuda()
+    models = []
+    for fused in (True, False):
+        torch.manual_seed(7)
+        cb = api.CodebookModel(32, mixture_cfg=dict(n_components=16), dtype=torch.double, update_decay=0.9).cuda()
+        if not fused:
+            monkeypatch.setattr(dm_base.MixtureMixin, "_nearest_component_kernel_applies", lambda self, s: False)
+        for lo in range(0, 2000, 250):
+            torch.manual_seed(100 + lo)
+            cb.update(data[lo:lo + 250])
+        models.append(cb)
+    assert rel(models[0].codebook, models[1].codebook.cpu()) < 1e-6 and rel(models[0]._n_obs, models[1]._n_obs.cpu()) < 1e-9
+    assert rel(models[0]._running_sum, models[1]._running_sum.cpu()) < 1e-6
