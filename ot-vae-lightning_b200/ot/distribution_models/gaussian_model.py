@@ -187,7 +187,9 @@ class GaussianModel(DistributionModel, W2Mixin):
         if seen is None:
             self.mean.copy_(val)
         else:
-            self.mean.data.copy_(torch.where(seen.unsqueeze(-1), val, self.mean.data))
+            # written through the Parameter itself (fit runs under no_grad), so that `mean._version` moves and caches keyed
+            # on it (GaussianTransport's prepared operator) notice a refit of a single model
+            self.mean.copy_(torch.where(seen.unsqueeze(-1), val, self.mean.detach()))
 
     def _update_cov(self, val: Optional[Tensor], seen: Optional[Tensor] = None):
         if val is None:
