@@ -26,6 +26,11 @@ struct GemmArgs {
   T* C_hi = nullptr;                    // optional split output planes (layout of C); C itself may then be null
   T* C_lo = nullptr;
   T* scratch = nullptr;                 // >= 2*batch*(M*K + N*K) elements: used to split A / B when no lo plane is given
+  // --- both engines: optional addend  C += add_scale * (add + add_lo), layout / batch stride of C (add_lo: the "lo" plane
+  //     when the addend is stored as TF32 planes) - the b*M term of the accelerated Newton-Schulz polynomial
+  const T* add = nullptr;
+  const T* add_lo = nullptr;
+  T add_scale = T(0);
 };
 
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
@@ -40,6 +45,8 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmArgs<T> g) {
   T* C = g.C ? g.C + batch * g.strideC : nullptr;
   const T* a_off = g.a_off ? g.a_off + batch * g.stride_aoff : nullptr;
   const T* bias = g.bias ? g.bias + batch * g.stride_bias : nullptr;
+  const T* add = g.add ? g.add + batch * g.strideC : nullptr;
+  const T* add_lo = g.add_lo ? g.add_lo + batch * g.strideC : nullptr;
   const int64_t m0 = (int64_t)blockIdx.y * SG_BM, n0 = (int64_t)blockIdx.x * SG_BN;
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads, 4 x 4 outputs each
@@ -100,6 +107,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmArgs<T> g) {
       T r = g.alpha * acc[i][j];
       if (g.beta != T(0) && C) r += g.beta * C[m * g.ldc + n];
       if (bias) r += bias[n];
+      if (add) r += g.add_scale * (add[m * g.ldc + n] + (add_lo ? add_lo[m * g.ldc + n] : T(0)));
       if (m == n) r += g.diag_add;
       if (C) C[m * g.ldc + n] = r;
       if (g.resid) { double e = (double)acc[i][j] - (m == n ? 1.0 : 0.0); res += e * e; }

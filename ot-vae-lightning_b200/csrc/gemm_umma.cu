@@ -51,6 +51,8 @@ struct UmmaGemmParams {
   const float* bias;
   int64_t stride_bias;
   double* resid;
+  const float *add_hi, *add_lo;   // optional addend planes (layout of C): C += add_scale * (add_hi + add_lo)
+  float add_scale;
 };
 struct UmmaGemmMaps { CUtensorMap A_hi, A_lo, B_hi, B_lo; };
 
@@ -58,16 +60,27 @@ struct UmmaGemmMaps { CUtensorMap A_hi, A_lo, B_hi, B_lo; };
 // only - without per-row pointer / bounds tests: the 32 rows are independent straight-line code the scheduler can
 // interleave.  (With the tests inside the loop every row was a branchy dependent chain of ~190 cycles on the single
 // epilogue warp of its scheduler: 3.1 us per 32-row chunk, 6.9 us of a 10 - 16 us launch - globaltimer stamps.)
-template <bool RESID>
+template <bool RESID, bool ADD = false>
 __device__ __forceinline__ void epilogue_rows_planes(const float (&v)[32], int mrow0, int n, int64_t ldc, float alpha,
                                                      float bn, float diag_add, float* __restrict__ Ch,
-                                                     float* __restrict__ Cl, double& res) {
+                                                     float* __restrict__ Cl, double& res,
+                                                     const float* __restrict__ Ah = nullptr,
+                                                     const float* __restrict__ Al = nullptr, float add_scale = 0.f) {
+  float addend[32];
+  if (ADD) {       // all 64 loads of the addend planes are issued before the first store of the result
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int64_t idx = (int64_t)(mrow0 + r) * ldc + n;
+      addend[r] = __ldg(Ah + idx) + __ldg(Al + idx);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
     const int m = mrow0 + r;
     const float acc = v[r];
     if (RESID) { const float e = acc - (m == n ? 1.f : 0.f); res += (double)(e * e); }
     float t = alpha * acc + bn;
+    if (ADD) t = fmaf(add_scale, addend[r], t);
     if (m == n) t += diag_add;
     float h, lo;
     ptx::split_tf32(t, h, lo);
@@ -225,6 +238,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
     float* Ch = p.C_hi ? p.C_hi + (int64_t)batch * p.strideC : nullptr;
     float* Cl = p.C_lo ? p.C_lo + (int64_t)batch * p.strideC : nullptr;
     const float* bias = p.bias ? p.bias + (int64_t)batch * p.stride_bias : nullptr;
+    const float* Ah = p.add_hi ? p.add_hi + (int64_t)batch * p.strideC : nullptr;
+    const float* Al = p.add_lo ? p.add_lo + (int64_t)batch * p.strideC : nullptr;
     uint32_t peer[KS > 1 ? KS - 1 : 1];
     if constexpr (KS > 1) {
 #pragma unroll
@@ -256,7 +271,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
       const int n = n0 + c0 + lane;
       if (n < p.N && !C && Ch && mrow0 + 32 <= p.M) {
         const float bn = bias ? bias[n] : 0.f;
-        if (p.resid) epilogue_rows_planes<true>(v, mrow0, n, p.ldc, p.alpha, bn, p.diag_add, Ch, Cl, res);
+        if (Ah && Al) epilogue_rows_planes<false, true>(v, mrow0, n, p.ldc, p.alpha, bn, p.diag_add, Ch, Cl, res, Ah, Al, p.add_scale);
+        else if (p.resid) epilogue_rows_planes<true>(v, mrow0, n, p.ldc, p.alpha, bn, p.diag_add, Ch, Cl, res);
         else epilogue_rows_planes<false>(v, mrow0, n, p.ldc, p.alpha, bn, p.diag_add, Ch, Cl, res);
       } else if (n < p.N) {
         const float bn = bias ? bias[n] : 0.f;
@@ -269,6 +285,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
           if (p.resid) { const float e = acc - (m == n ? 1.f : 0.f); res += (double)(e * e); }
           float t = p.alpha * acc + bn;
           if (p.beta != 0.f && C) t += p.beta * C[idx];
+          if (Ah) t += p.add_scale * (Ah[idx] + (Al ? Al[idx] : 0.f));
           if (m == n) t += p.diag_add;
           if (C) C[idx] = t;
           if (Ch) {
@@ -390,7 +407,7 @@ static int prepare_gemm(const GemmArgs<float>& g, int64_t batch, int passes, int
     if (!encode_map_f32_3d(&out->maps.B_lo, B_lo, b_cols, b_rows, batch, b_ld, b_bs, 32, b_box_rows, b_mn != 0)) return 0;
   }
   out->p = UmmaGemmParams{(int)g.M, (int)g.N, (int)g.K, passes == 3 ? 3 : 1, b_mn, g.C, g.C_hi, g.C_lo, g.ldc, g.strideC,
-                          g.alpha, g.beta, g.diag_add, g.bias, g.stride_bias, g.resid};
+                          g.alpha, g.beta, g.diag_add, g.bias, g.stride_bias, g.resid, g.add, g.add_lo, g.add_scale};
   return 1;
 }
 

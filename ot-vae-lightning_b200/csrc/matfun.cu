@@ -21,10 +21,25 @@ constexpr int NS_F64_MAX_ITERS = 90;
 // iterations-to-converge grows like log_2.25(||A||_F / lambda_min): used as the conditioning estimate that decides
 // when the fp32 engine's ~1e-7 * cond error would exceed the parity tolerance (measured: T err 3e-5 at cond 1e2,
 // 3e-3 at cond 1e4)
-constexpr int NS_F32_OPERATOR_ITERS = 20;
+constexpr int NS_F32_OPERATOR_ITERS = 14;   // (counts include the NS_ACCEL_STEPS accelerated iterations, each worth ~3 classical ones)
 constexpr double NS_F32_RICCATI_TOL = 2e-4;   // ||T Cs T - Ct||_F / ||Ct||_F accepted from the fp32 engine
 constexpr int64_t NS_SMALL_DIM = 64;          // fp64 data with dim <= 64: the DFMA engine is as fast and exact
-constexpr int NS_F32_IROOT_ITERS = 18;
+constexpr int NS_F32_IROOT_ITERS = 12;
+// a root alone loses ~1e-7 * sqrt(cond): accepted from the fp32 engine up to this many iterations (lambda_min / c down to
+// ~1e-6); beyond that - ill-conditioned or rank-deficient input, whose noise-level eigenvalues the fp32 engine would
+// "converge" on - the fp64 engine takes over
+constexpr int NS_F32_ROOT_ITERS = 16;
+// Accelerated start.  The classical step multiplies an eigenvalue p << 1 of Z Y by 2.25 per iteration (3 products).  The
+// first NS_ACCEL_STEPS iterations use the degree-2 polynomial in M = Z Y instead,
+//     T = a I + b M + c M^2 ,  Y <- Y T ,  Z <- T Z     (p <- p T(p)^2 : a factor a^2 = 11.9 per iteration, 4 products),
+// with the quintic coefficients published for Newton-Schulz orthogonalisation (Jordan et al., "Muon", 2024: x <- a x +
+// b x^3 + c x^5 on the singular values, here with x^2 = p).  It maps (0, 1.4] into [0.5, 1.25] but does not converge to 1,
+// so the classical (quadratically convergent, self-correcting) steps finish the job.  Measured on the fp32 simulation
+// (scratch/ns_accel.py): d = 512, cond 1e2: 27 products instead of 39, cond 1e4: 39 instead of 54, same or better accuracy.
+constexpr int NS_ACCEL_STEPS = 3;
+constexpr int NS_ACCEL_STEPS_ESCALATED = 8;   // fp64 engine re-running what the fp32 engine found ill-conditioned / singular
+constexpr double NS_ACC_A = 3.4445, NS_ACC_B = -4.7750, NS_ACC_C = 2.0315;
+static thread_local int g_ns_accel_steps = NS_ACCEL_STEPS;
 // The fp64 engine adds NS_F64_REL_RIDGE * ||A||_F to the diagonal: ten fp64 ulps of the norm, below the iteration's own
 // round-off for any PD input, but it turns an exactly singular SPSD matrix (a rank-deficient covariance, the 'spsd'
 // arguments of the reference: w2_utils.py:73-76, 423-426; FID with fewer samples than features) into one the iteration
@@ -202,14 +217,14 @@ static inline unsigned ew_grid(int64_t total) {
 
 template <typename W>
 struct NsWork {
-  W *Y[2], *Z[2], *T;
+  W *Y[2], *Z[2], *T, *M;
   // TF32 hi/lo planes of the iterates (fp32 / tcgen05 engine only): no conversion pass between chained GEMMs
-  W *Yh[2], *Yl[2], *Zh[2], *Zl[2], *Th, *Tl;
+  W *Yh[2], *Yl[2], *Zh[2], *Zl[2], *Th, *Tl, *Mh, *Ml;
   W* scratch;         // 4 planes: operand splits for the products outside the iteration
   double *c, *resid;  // c [L]; resid [NS_MAX_ITERS][L]
   double* ridge_l;    // [L] diagonal shift of the current solve
   int* ctrl;          // device-side loop control (ns_ctrl_kernel)
-  static constexpr int kPlanes = sizeof(W) == 4 ? 5 + 10 + 4 : 5;
+  static constexpr int kPlanes = sizeof(W) == 4 ? 6 + 12 + 4 : 6;
   static size_t bytes(int64_t L, int64_t d) {
     return kPlanes * align_up((size_t)L * d * d * sizeof(W), 256) + 2 * align_up((size_t)L * 8, 256) +
            align_up((size_t)NS_MAX_ITERS * L * 8, 256) + 256;
@@ -218,9 +233,11 @@ struct NsWork {
     const size_t n = (size_t)L * d * d;
     for (int i = 0; i < 2; ++i) { Y[i] = ar.take<W>(n); Z[i] = ar.take<W>(n); }
     T = ar.take<W>(n);
+    M = ar.take<W>(n);
     if (sizeof(W) == 4) {
       for (int i = 0; i < 2; ++i) { Yh[i] = ar.take<W>(n); Yl[i] = ar.take<W>(n); Zh[i] = ar.take<W>(n); Zl[i] = ar.take<W>(n); }
       Th = ar.take<W>(n); Tl = ar.take<W>(n);
+      Mh = ar.take<W>(n); Ml = ar.take<W>(n);
       scratch = ar.take<W>(4 * n);
     } else {
       scratch = nullptr;
@@ -355,6 +372,8 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
   OTK_LAUNCH_CHECK();
   OTK_CUDA(cudaMemsetAsync(w.resid, 0, (size_t)NS_MAX_ITERS * L * 8, st));
   const bool adaptive = iters <= 0;
+  // accelerated first iterations (adaptive runs only: a caller that fixes the iteration count gets the classical step)
+  const int accel = adaptive ? (f32 ? NS_ACCEL_STEPS : g_ns_accel_steps) : 0;
   const int budget = f32 ? NS_F32_MAX_ITERS : NS_F64_MAX_ITERS;
   const int max_iters = adaptive ? budget : (iters < NS_MAX_ITERS ? iters : NS_MAX_ITERS);
   // quadratic convergence: once ||I - ZY||_F^2 < tol_near one more update lands on the floor
@@ -376,8 +395,17 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
         auto enqueue = [&](cudaStream_t s) -> int {
           for (int k = enq; k < enq + n; ++k) {
             const int cur = k & 1;
-            GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, -0.5f, 1.5f, w.resid + (size_t)k * L);
-            OTK_TRY(plane_gemm2(zy, nullptr, L, w.ctrl, k, s));
+            if (k < accel) {
+              // accelerated step: M = Z Y (residual of the raw product as usual), then T = c M^2 + b M + a I
+              GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Mh, w.Ml, d, 1.f, 0.f, w.resid + (size_t)k * L);
+              OTK_TRY(plane_gemm2(zy, nullptr, L, w.ctrl, k, s));
+              GemmArgs<float> mm = plane_args(w.Mh, w.Ml, w.Mh, w.Ml, w.Th, w.Tl, d, (float)NS_ACC_C, (float)NS_ACC_A, nullptr);
+              mm.add = w.Mh; mm.add_lo = w.Ml; mm.add_scale = (float)NS_ACC_B;
+              OTK_TRY(plane_gemm2(mm, nullptr, L, w.ctrl, k, s));
+            } else {
+              GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, -0.5f, 1.5f, w.resid + (size_t)k * L);
+              OTK_TRY(plane_gemm2(zy, nullptr, L, w.ctrl, k, s));
+            }
             // the stopping rule on the residuals of iteration k rides in the paired launch (one warp of its first CTA):
             // it only has to act before the launches of iteration k + 1
             const NsCtrlEval ev{w.resid + (size_t)k * L, L, k, max_iters, tol_done, tol_near, w.ctrl};
@@ -389,7 +417,7 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
         };
         int dev = 0;
         cudaGetDevice(&dev);
-        OTK_TRY(ns_batch(NsGraphKey{w.ctrl, w.Yh[0], L, d, enq, n, max_iters, adaptive ? 1 : 0, dev}, st, enqueue));
+        OTK_TRY(ns_batch(NsGraphKey{w.ctrl, w.Yh[0], L, d, enq, n, max_iters, (adaptive ? 1 : 0) + 2 * accel, dev}, st, enqueue));
         done_planes = true;
       }
     }
@@ -397,10 +425,20 @@ static int ns_solve(const void* a, int dt, int64_t L, int64_t d, double ridge, i
       const int cur = k & 1;
       {
         // generic engines (FFMA / DFMA): the launches are unconditional, so they are only enqueued up to the next readback
-        GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.T, d, dd, W(-0.5));
-        g.diag_add = W(1.5);
-        g.resid = w.resid + (size_t)k * L;
-        OTK_TRY(gemm_any(g, L, st));
+        if (k < accel) {
+          GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.M, d, dd, W(1));
+          g.resid = w.resid + (size_t)k * L;
+          OTK_TRY(gemm_any(g, L, st));
+          GemmArgs<W> mm = nn_args_t<W>(w.M, w.M, w.T, d, dd, W(NS_ACC_C));
+          mm.diag_add = W(NS_ACC_A);
+          mm.add = w.M; mm.add_scale = W(NS_ACC_B);
+          OTK_TRY(gemm_any(mm, L, st));
+        } else {
+          GemmArgs<W> g = nn_args_t<W>(w.Z[cur], w.Y[cur], w.T, d, dd, W(-0.5));
+          g.diag_add = W(1.5);
+          g.resid = w.resid + (size_t)k * L;
+          OTK_TRY(gemm_any(g, L, st));
+        }
         OTK_TRY(gemm_any(nn_args_t<W>(w.Y[cur], w.T, w.Y[cur ^ 1], d, dd, W(1)), L, st));
         OTK_TRY(gemm_any(nn_args_t<W>(w.T, w.Z[cur], w.Z[cur ^ 1], d, dd, W(1)), L, st));
         if (adaptive) {
@@ -457,7 +495,8 @@ static int sqrtm_impl(const void* a, int64_t L, int64_t dim, int dtype, double r
 //   leaves sqrt(S Q S)/sqrt(c) in w.Y[*cur2] with c in w.c.
 template <typename W>
 static int rooted_mix(const void* P, const void* Q, int dt, int64_t L, int64_t d, double ridge, int iters, NsWork<W>& w,
-                      W* S, W* Zp, W* Q32, W* G, W* mix, int* cur2, int* verdict, int* used_first, cudaStream_t st) {
+                      W* S, W* Zp, W* Q32, W* G, W* mix, int* cur2, int* verdict, int* used_first, cudaStream_t st,
+                      int* used_mix = nullptr) {
   const int64_t dd = d * d;
   const W* none = nullptr;
   int cur = 0, v1 = 0, v2 = 0, used2 = 0;
@@ -476,6 +515,7 @@ static int rooted_mix(const void* P, const void* Q, int dt, int64_t L, int64_t d
   sym_scale_kernel<W><<<ew_grid(L * dd), 256, 0, st>>>(Q32, none, L, d, nullptr, 0, 1.0, 0, 0, 0.0, mix, wdt);
   OTK_LAUNCH_CHECK();
   OTK_TRY(ns_solve<W>(mix, wdt, L, d, 0.0, iters, w, cur2, &v2, &used2, st));
+  if (used_mix) *used_mix = used2;
   *verdict = (v1 == NS_CONVERGED && v2 == NS_CONVERGED) ? NS_CONVERGED : NS_SLOW;
   return OTK_OK;
 }
@@ -484,14 +524,17 @@ template <typename W>
 static int w2_impl(const void* mean_s, const void* mean_t, const void* cov_s, const void* cov_t, int64_t L, int64_t dim,
                    int dtype, int iters, double* w2, void* workspace, size_t workspace_bytes, int* verdict,
                    cudaStream_t st) {
-  int used_first = 0;
+  int used_first = 0, used_mix = 0;
   Arena ar(workspace, workspace_bytes);
   NsWork<W> w; w.carve(ar, L, dim);
   const size_t n = (size_t)L * dim * dim;
   W *S = ar.take<W>(n), *Q32 = ar.take<W>(n), *G = ar.take<W>(n), *mix = ar.take<W>(n);
   int cur2 = 0;
   // the reference roots the TARGET covariance for the distance (w2_utils.py:70-71)
-  OTK_TRY(rooted_mix<W>(cov_t, cov_s, dtype, L, dim, 0.0, iters, w, S, nullptr, Q32, G, mix, &cur2, verdict, &used_first, st));
+  OTK_TRY(rooted_mix<W>(cov_t, cov_s, dtype, L, dim, 0.0, iters, w, S, nullptr, Q32, G, mix, &cur2, verdict, &used_first, st,
+                        &used_mix));
+  // accuracy gate of the fp32 engine: both roots must have converged within the well-conditioned budget
+  if (sizeof(W) == 4 && (used_first > NS_F32_ROOT_ITERS || used_mix > NS_F32_ROOT_ITERS)) *verdict = NS_SLOW;
   w2_trace_kernel<W><<<(unsigned)L, 256, 0, st>>>(mean_s, mean_t, cov_s, cov_t, dtype, dim, w.Y[cur2], w.c, w2);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
@@ -662,10 +705,13 @@ extern "C" int otk_sqrtm(const void* a, int64_t L, int64_t dim, int dtype, doubl
   if (polish <= 0) {
     OTK_TRY(sqrtm_impl<float>(a, L, dim, dtype, ridge, iters, root, iroot, workspace, workspace_bytes, &verdict, &used, st));
     // the inverse root loses ~1e-7 * cond: escalate it earlier than the root
-    const bool accurate = verdict == NS_CONVERGED && (!iroot || used <= NS_F32_IROOT_ITERS);
+    const bool accurate = verdict == NS_CONVERGED && used <= (iroot ? NS_F32_IROOT_ITERS : NS_F32_ROOT_ITERS);
     if (accurate || polish < 0 || iters > 0) return OTK_OK;
   }
-  OTK_TRY(sqrtm_impl<double>(a, L, dim, dtype, ridge, iters, root, iroot, workspace, workspace_bytes, &verdict, &used, st));
+  g_ns_accel_steps = polish <= 0 ? NS_ACCEL_STEPS_ESCALATED : NS_ACCEL_STEPS;   // escalated: the input is ill-conditioned
+  const int rc64 = sqrtm_impl<double>(a, L, dim, dtype, ridge, iters, root, iroot, workspace, workspace_bytes, &verdict, &used, st);
+  g_ns_accel_steps = NS_ACCEL_STEPS;
+  OTK_TRY(rc64);
   if (verdict != NS_CONVERGED && iters <= 0) {
     set_last_error_msg("sqrtm: Newton-Schulz did not converge (the matrix is not positive definite)");
     return OTK_ERR_NOT_CONVERGED;
@@ -686,7 +732,10 @@ extern "C" int otk_w2_gaussian(const void* mean_s, const void* mean_t, const voi
     OTK_TRY(w2_impl<float>(mean_s, mean_t, cov_s, cov_t, L, dim, dtype, iters, w2, workspace, workspace_bytes, &verdict, st));
     if (verdict == NS_CONVERGED || polish < 0 || iters > 0) return OTK_OK;
   }
-  OTK_TRY(w2_impl<double>(mean_s, mean_t, cov_s, cov_t, L, dim, dtype, iters, w2, workspace, workspace_bytes, &verdict, st));
+  g_ns_accel_steps = polish <= 0 ? NS_ACCEL_STEPS_ESCALATED : NS_ACCEL_STEPS;
+  const int rc64 = w2_impl<double>(mean_s, mean_t, cov_s, cov_t, L, dim, dtype, iters, w2, workspace, workspace_bytes, &verdict, st);
+  g_ns_accel_steps = NS_ACCEL_STEPS;
+  OTK_TRY(rc64);
   if (verdict != NS_CONVERGED && iters <= 0) {
     set_last_error_msg("w2_gaussian: Newton-Schulz did not converge (a covariance is not positive definite)");
     return OTK_ERR_NOT_CONVERGED;
@@ -711,8 +760,11 @@ extern "C" int otk_transport_operator(const void* cov_s, const void* cov_t, int6
     // T = Zp R Zp cancels by a factor cond(Cs): fp32 is only kept while the source root converged quickly
     if ((verdict == NS_CONVERGED && used <= NS_F32_OPERATOR_ITERS) || polish < 0 || iters > 0) return OTK_OK;
   }
-  OTK_TRY(operator_impl<double>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, mean_s, mean_t, w2, workspace,
-                                workspace_bytes, &verdict, &used, st));
+  g_ns_accel_steps = polish <= 0 ? NS_ACCEL_STEPS_ESCALATED : NS_ACCEL_STEPS;
+  const int rc64 = operator_impl<double>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, mean_s, mean_t, w2, workspace,
+                                         workspace_bytes, &verdict, &used, st);
+  g_ns_accel_steps = NS_ACCEL_STEPS;
+  OTK_TRY(rc64);
   if (verdict != NS_CONVERGED && iters <= 0) {
     set_last_error_msg("transport_operator: Newton-Schulz did not converge (a covariance is not positive definite)");
     return OTK_ERR_NOT_CONVERGED;
