@@ -592,6 +592,332 @@ static int operator_impl(const void* cov_s, const void* cov_t, int64_t L, int64_
   return OTK_OK;
 }
 
+// =====================================================================================================================
+// Fast path of the deterministic operator (the call GaussianTransport.compute() makes, transport/gaussian_transport.py:64-78).
+//
+// The general path above is a chain of ~110 launches with three host read-backs (iteration counts of the two solves, the
+// Riccati residual): at d <= 512 it is bound by the host's launch rate, not by the GPU.  This path runs the same
+// arithmetic OPTIMISTICALLY - a fixed budget of device-gated Newton-Schulz iterations per solve, every decision that needs
+// an iteration count (which ping-pong buffer holds the result) taken on the device - as ~70 launches with no read-back in
+// between, so the whole call is captured once into a CUDA graph (keyed on the operand / workspace pointers) and replayed;
+// operands flow between the products as TF32 hi/lo planes (no split / join / cast passes).  One status block is read back
+// at the end: if a solve did not converge within the budget, needed more iterations than the fp32 accuracy gates allow,
+// or the map fails the Riccati check, the general path (with its fp64 escalation) redoes the call.
+// =====================================================================================================================
+constexpr int NS_FAST_ITERS = 12;
+
+struct FastStatus { int ctrl1[4]; int ctrl2[4]; };   // followed by acc[2 L] doubles (Riccati numerators / denominators)
+
+__device__ __forceinline__ double ns_scale_dev(const double* csq, const double* cmax, int64_t l) {
+  const double fro = sqrt(csq[l]), rs = cmax[l];
+  const double c0 = (rs > 0 && rs < fro) ? rs : fro;
+  return c0 > 0 ? c0 : 1.0;
+}
+__device__ __forceinline__ float plane_sym(const float* __restrict__ h, const float* __restrict__ l, int64_t e, int64_t et) {
+  return 0.5f * ((h[e] + l[e]) + (h[et] + l[et]));
+}
+__device__ __forceinline__ void plane_store(float* __restrict__ h, float* __restrict__ l, int64_t e, float v) {
+  float a, b;
+  ptx::split_tf32(v, a, b);
+  h[e] = a; l[e] = b;
+}
+
+// row norms of (MODE 0) A + ridge I read from `a`, or (MODE 1) sym(Rh + Rl); also resets the loop control of the solve
+template <int MODE>
+__global__ void fast_norm_kernel(const void* a, int dt, const float* __restrict__ Rh, const float* __restrict__ Rl, int64_t dim,
+                                 double ridge, double* csq, double* cmax, int* ctrl, int max_iters) {
+  const int64_t l = blockIdx.y;
+  const int lane = threadIdx.x % 32;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { ctrl[0] = max_iters; ctrl[1] = NS_SLOW; ctrl[2] = 0; ctrl[3] = 0; }
+  double sq_tot = 0, mx = 0;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; row < dim; row += (int64_t)gridDim.x * (blockDim.x / 32)) {
+    double sq = 0, ab = 0;
+    for (int64_t j = lane; j < dim; j += 32) {
+      const int64_t e = l * dim * dim + row * dim + j;
+      double v;
+      if (MODE == 0) { v = load_real(a, e, dt); if (j == row) v += ridge; }
+      else v = (double)plane_sym(Rh, Rl, e, l * dim * dim + j * dim + row);
+      sq += v * v;
+      ab += fabs(v);
+    }
+    sq = warp_sum(sq); ab = warp_sum(ab);
+    sq_tot += sq;
+    mx = ab > mx ? ab : mx;
+  }
+  if (lane == 0) {
+    atomicAdd(&csq[l], sq_tot);
+    atomicMax(reinterpret_cast<unsigned long long*>(&cmax[l]), (unsigned long long)__double_as_longlong(mx));
+  }
+}
+
+// Y = value / c as planes, Z = I
+template <int MODE>
+__global__ void fast_init_kernel(const void* a, int dt, const float* __restrict__ Rh, const float* __restrict__ Rl, int64_t L,
+                                 int64_t dim, double ridge, const double* csq, const double* cmax, float* Yh, float* Yl,
+                                 float* Zh, float* Zl) {
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
+    double v;
+    if (MODE == 0) v = load_real(a, e, dt) + (i == j ? ridge : 0.0);
+    else v = (double)plane_sym(Rh, Rl, e, l * dim * dim + j * dim + i);
+    plane_store(Yh, Yl, e, (float)(v / ns_scale_dev(csq, cmax, l)));
+    Zh[e] = i == j ? 1.f : 0.f; Zl[e] = 0.f;
+  }
+}
+
+struct PlanePair { const float *h[2], *l[2]; };   // ping-pong planes of an iterate; the live one is chosen on the device
+
+// after solve 1 (on P + ridge I): S = P^1/2 (first-order ridge correction), Zp = (P + ridge I)^-1/2, Q = cast(other cov)
+__global__ void fast_mid_kernel(PlanePair Y, PlanePair Z, const int* ctrl, int budget, const double* csq, const double* cmax,
+                                double ridge, const void* q, int dt, int64_t L, int64_t dim, float* Sh, float* Sl, float* Zph,
+                                float* Zpl, float* Qh, float* Ql) {
+  const int done = ctrl[0] < budget ? ctrl[0] : budget, cur = done & 1;
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = e / (dim * dim), r = e % (dim * dim), et = l * dim * dim + (r % dim) * dim + r / dim;
+    const double c = ns_scale_dev(csq, cmax, l), rc = sqrt(c);
+    const double y = plane_sym(Y.h[cur], Y.l[cur], e, et), z = plane_sym(Z.h[cur], Z.l[cur], e, et);
+    plane_store(Sh, Sl, e, (float)(y * rc - 0.5 * ridge * z / rc));
+    plane_store(Zph, Zpl, e, (float)(z / rc));
+    plane_store(Qh, Ql, e, (float)load_real(q, e, dt));
+  }
+}
+
+// after solve 2: R = mix^1/2 = sqrt(c2) sym(Y2) as planes; W2^2 accumulated from the diagonal (w2 zeroed beforehand)
+__global__ void fast_tail_kernel(PlanePair Y, const int* ctrl, int budget, const double* csq, const double* cmax, int64_t L,
+                                 int64_t dim, float* Rh, float* Rl, const void* ms, const void* mt, const void* cs,
+                                 const void* ct, int dt, double* w2) {
+  const int done = ctrl[0] < budget ? ctrl[0] : budget, cur = done & 1;
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim, et = l * dim * dim + j * dim + i;
+    const double rc = sqrt(ns_scale_dev(csq, cmax, l));
+    const double y = plane_sym(Y.h[cur], Y.l[cur], e, et);
+    plane_store(Rh, Rl, e, (float)(y * rc));
+    if (w2 && i == j) {
+      const double dm = load_real(ms, l * dim + i, dt) - load_real(mt, l * dim + i, dt);
+      atomicAdd(&w2[l], dm * dm + load_real(cs, e, dt) + load_real(ct, e, dt) - 2.0 * rc * y);
+    }
+  }
+}
+
+// T = (1-p) sym(Traw) + p I -> caller's dtype; T0 = sym(Traw) and Cs as planes for the Riccati check
+__global__ void fast_final_kernel(const float* __restrict__ Th, const float* __restrict__ Tl, int64_t L, int64_t dim, double pg,
+                                  void* T, int out_dt, float* T0h, float* T0l, const void* cs, int dt, float* Csh, float* Csl) {
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
+    const float t0 = plane_sym(Th, Tl, e, l * dim * dim + j * dim + i);
+    store_real(T, e, out_dt, (1.0 - pg) * (double)t0 + (i == j ? pg : 0.0));
+    plane_store(T0h, T0l, e, t0);
+    plane_store(Csh, Csl, e, (float)load_real(cs, e, dt));
+  }
+}
+
+// acc[2l] += || (Vh + Vl)_l - target_l ||_F^2 , acc[2l+1] += || target_l ||_F^2
+__global__ void fast_residual_kernel(const float* __restrict__ Vh, const float* __restrict__ Vl, const void* target, int dt,
+                                     int64_t dim, double* acc) {
+  __shared__ double red[32];
+  const int64_t l = blockIdx.y;
+  double num = 0, den = 0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < dim * dim; e += (int64_t)gridDim.x * blockDim.x) {
+    const double t = load_real(target, l * dim * dim + e, dt), df = (double)(Vh[l * dim * dim + e] + Vl[l * dim * dim + e]) - t;
+    num += df * df;
+    den += t * t;
+  }
+  num = block_sum(num, red);
+  den = block_sum(den, red);
+  if (threadIdx.x == 0) { atomicAdd(&acc[2 * l], num); atomicAdd(&acc[2 * l + 1], den); }
+}
+
+// NS_FAST_ITERS device-gated iterations on the planes of `w` (the enqueue body of ns_solve, without its read-backs)
+static int fast_iterations(NsWork<float>& w, int64_t L, int64_t d, int* ctrl, double* resid, cudaStream_t s) {
+  const double tol_done = 1e-9, tol_near = 9e-4;
+  for (int k = 0; k < NS_FAST_ITERS; ++k) {
+    const int cur = k & 1;
+    if (k < NS_ACCEL_STEPS) {
+      GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Mh, w.Ml, d, 1.f, 0.f, resid + (size_t)k * L);
+      OTK_TRY(plane_gemm2(zy, nullptr, L, ctrl, k, s));
+      GemmArgs<float> mm = plane_args(w.Mh, w.Ml, w.Mh, w.Ml, w.Th, w.Tl, d, (float)NS_ACC_C, (float)NS_ACC_A, nullptr);
+      mm.add = w.Mh; mm.add_lo = w.Ml; mm.add_scale = (float)NS_ACC_B;
+      OTK_TRY(plane_gemm2(mm, nullptr, L, ctrl, k, s));
+    } else {
+      GemmArgs<float> zy = plane_args(w.Zh[cur], w.Zl[cur], w.Yh[cur], w.Yl[cur], w.Th, w.Tl, d, -0.5f, 1.5f, resid + (size_t)k * L);
+      OTK_TRY(plane_gemm2(zy, nullptr, L, ctrl, k, s));
+    }
+    const NsCtrlEval ev{resid + (size_t)k * L, L, k, NS_F32_MAX_ITERS, tol_done, tol_near, ctrl};
+    GemmArgs<float> yt = plane_args(w.Yh[cur], w.Yl[cur], w.Th, w.Tl, w.Yh[cur ^ 1], w.Yl[cur ^ 1], d, 1.f, 0.f, nullptr);
+    GemmArgs<float> tz = plane_args(w.Th, w.Tl, w.Zh[cur], w.Zl[cur], w.Zh[cur ^ 1], w.Zl[cur ^ 1], d, 1.f, 0.f, nullptr);
+    OTK_TRY(plane_gemm2(yt, &tz, L, ctrl, k, s, &ev));
+  }
+  return OTK_OK;
+}
+
+struct FastOpArgs {
+  const void *cov_s, *cov_t, *mean_s, *mean_t;
+  void* T;
+  double* w2;
+  void* workspace;
+  size_t workspace_bytes;
+  int64_t L, d;
+  int dtype;
+  double pg_star;
+};
+struct FastOpLayout { NsWork<float> w; float* pl[8]; double *c1, *c2, *resid2; FastStatus* status; double* acc; size_t zero_lo, zero_hi; };
+
+static bool fast_layout(const FastOpArgs& a, FastOpLayout* o) {
+  Arena ar(a.workspace, a.workspace_bytes);
+  o->w.carve(ar, a.L, a.d);
+  const size_t n = (size_t)a.L * a.d * a.d;
+  for (int i = 0; i < 8; ++i) o->pl[i] = ar.take<float>(n);
+  // one zero-filled region: [c1 sq | c1 max | c2 sq | c2 max | resid1 | resid2 | status | acc]
+  ar.off = align_up(ar.off, 256);
+  o->zero_lo = ar.off;
+  o->c1 = ar.take<double>(2 * (size_t)a.L);
+  o->c2 = ar.take<double>(2 * (size_t)a.L);
+  o->resid2 = ar.take<double>((size_t)NS_MAX_ITERS * a.L);
+  o->status = ar.take<FastStatus>(1);
+  o->acc = ar.take<double>(2 * (size_t)a.L);
+  o->zero_hi = ar.off;
+  return ar.ok();
+}
+
+static int fast_enqueue(const FastOpArgs& a, FastOpLayout& o, cudaStream_t st) {
+  const int64_t L = a.L, d = a.d, dd = d * d;
+  NsWork<float>& w = o.w;
+  float *Sh = o.pl[0], *Sl = o.pl[1], *Zph = o.pl[2], *Zpl = o.pl[3], *Qh = o.pl[4], *Ql = o.pl[5], *Gh = o.pl[6], *Gl = o.pl[7];
+  const double ridge = 1e-8;    // the reference's ridge of the inverse root (w2_utils.py:766)
+  OTK_CUDA(cudaMemsetAsync(static_cast<char*>(a.workspace) + o.zero_lo, 0, o.zero_hi - o.zero_lo, st));
+  OTK_CUDA(cudaMemsetAsync(w.resid, 0, (size_t)NS_MAX_ITERS * L * 8, st));
+  if (a.w2) OTK_CUDA(cudaMemsetAsync(a.w2, 0, (size_t)L * 8, st));
+  int64_t nb = ceil_div(d, 8);
+  if (nb > 128) nb = 128;
+  const dim3 ngrid((unsigned)nb, (unsigned)L);
+  const PlanePair Y{{w.Yh[0], w.Yh[1]}, {w.Yl[0], w.Yl[1]}}, Z{{w.Zh[0], w.Zh[1]}, {w.Zl[0], w.Zl[1]}};
+  auto mul = [&](const float* Ah, const float* Al, const float* Bh, const float* Bl, float* Ch, float* Cl) {
+    return plane_gemm2(plane_args(Ah, Al, Bh, Bl, Ch, Cl, d, 1.f, 0.f, nullptr), nullptr, L, nullptr, 0, st);
+  };
+  // ---- solve 1: roots of the SOURCE covariance (+ ridge)
+  fast_norm_kernel<0><<<ngrid, 256, 0, st>>>(a.cov_s, a.dtype, nullptr, nullptr, d, ridge, o.c1, o.c1 + L, o.status->ctrl1, NS_FAST_ITERS);
+  fast_init_kernel<0><<<ew_grid(L * dd), 256, 0, st>>>(a.cov_s, a.dtype, nullptr, nullptr, L, d, ridge, o.c1, o.c1 + L, w.Yh[0], w.Yl[0],
+                                                       w.Zh[0], w.Zl[0]);
+  count_launch(1);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(fast_iterations(w, L, d, o.status->ctrl1, w.resid, st));
+  fast_mid_kernel<<<ew_grid(L * dd), 256, 0, st>>>(Y, Z, o.status->ctrl1, NS_FAST_ITERS, o.c1, o.c1 + L, ridge, a.cov_t, a.dtype, L, d,
+                                                  Sh, Sl, Zph, Zpl, Qh, Ql);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(mul(Sh, Sl, Qh, Ql, Gh, Gl));            // S Ct
+  OTK_TRY(mul(Gh, Gl, Sh, Sl, Qh, Ql));            // (S Ct) S  -> Q planes
+  // ---- solve 2: root of sym(S Ct S)
+  fast_norm_kernel<1><<<ngrid, 256, 0, st>>>(nullptr, 0, Qh, Ql, d, 0.0, o.c2, o.c2 + L, o.status->ctrl2, NS_FAST_ITERS);
+  fast_init_kernel<1><<<ew_grid(L * dd), 256, 0, st>>>(nullptr, 0, Qh, Ql, L, d, 0.0, o.c2, o.c2 + L, w.Yh[0], w.Yl[0], w.Zh[0], w.Zl[0]);
+  count_launch(1);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(fast_iterations(w, L, d, o.status->ctrl2, o.resid2, st));
+  fast_tail_kernel<<<ew_grid(L * dd), 256, 0, st>>>(Y, o.status->ctrl2, NS_FAST_ITERS, o.c2, o.c2 + L, L, d, Gh, Gl, a.mean_s, a.mean_t,
+                                                   a.cov_s, a.cov_t, a.dtype, a.w2);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(mul(Zph, Zpl, Gh, Gl, Qh, Ql));          // Zp R
+  OTK_TRY(mul(Qh, Ql, Zph, Zpl, Sh, Sl));          // (Zp R) Zp = Traw  -> S planes
+  fast_final_kernel<<<ew_grid(L * dd), 256, 0, st>>>(Sh, Sl, L, d, a.pg_star, a.T, a.dtype, Gh, Gl, a.cov_s, a.dtype, Qh, Ql);
+  OTK_LAUNCH_CHECK();
+  // ---- Riccati check of the pg_star = 0 map: T0 Cs T0 = Ct
+  OTK_TRY(mul(Gh, Gl, Qh, Ql, Sh, Sl));            // T0 Cs
+  OTK_TRY(mul(Sh, Sl, Gh, Gl, Zph, Zpl));          // (T0 Cs) T0
+  fast_residual_kernel<<<dim3(32, (unsigned)L), 256, 0, st>>>(Zph, Zpl, a.cov_t, a.dtype, d, o.acc);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+// graph cache of the fast path (same life cycle as the Newton-Schulz batch cache: plain launches on the first sighting of
+// a key, capture on the second, replay afterwards)
+struct FastGraphKey {
+  const void* p[7];
+  int64_t L, d;
+  int dtype, dev;
+  double pg;
+  bool operator==(const FastGraphKey& o) const {
+    for (int i = 0; i < 7; ++i) if (p[i] != o.p[i]) return false;
+    return L == o.L && d == o.d && dtype == o.dtype && dev == o.dev && pg == o.pg;
+  }
+};
+struct FastGraphEntry { FastGraphKey key; cudaGraphExec_t exec; int launches; int state; };
+static std::vector<FastGraphEntry> g_fast_graphs;
+constexpr size_t FAST_GRAPH_CACHE = 16;
+
+// 1 = done (T, w2 written), 0 = not taken / not accepted (the caller runs the general path), < 0 = error
+static int operator_fast(const FastOpArgs& a, cudaStream_t st) {
+  if (!ns_planes_eligible(a.d) || a.L > 4096) return 0;
+  static const bool fast_on = [] { const char* e = getenv("OTK_OPERATOR_FAST"); return !(e && e[0] == '0'); }();   // tuning aid
+  if (!fast_on) return 0;
+  FastOpLayout lay;
+  if (!fast_layout(a, &lay)) return 0;
+  auto enqueue = [&](cudaStream_t s) -> int { return fast_enqueue(a, lay, s); };
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static const bool graphs_on = [] { const char* e = getenv("OTK_NS_GRAPHS"); return !(e && e[0] == '0'); }();
+  bool launched = false;
+  if (graphs_on && dev >= 0 && dev < 64) {
+    const FastGraphKey key{{a.cov_s, a.cov_t, a.mean_s, a.mean_t, a.T, a.w2, a.workspace}, a.L, a.d, a.dtype, dev, a.pg_star};
+    std::lock_guard<std::mutex> lock(g_ns_graph_mu);
+    FastGraphEntry* hit = nullptr;
+    for (auto& e : g_fast_graphs) if (e.key == key) { hit = &e; break; }
+    if (!hit) {
+      if (g_fast_graphs.size() >= FAST_GRAPH_CACHE) {
+        if (g_fast_graphs.front().exec) cudaGraphExecDestroy(g_fast_graphs.front().exec);
+        g_fast_graphs.erase(g_fast_graphs.begin());
+      }
+      g_fast_graphs.push_back(FastGraphEntry{key, nullptr, 0, 0});
+    } else if (hit->state == 0) {
+      cudaStream_t& cs = g_ns_capture_stream[dev];
+      if (!cs && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cs = nullptr; hit->state = -1; cudaGetLastError(); }
+      if (cs && cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const unsigned long long before = launches();
+        cudaGraph_t graph = nullptr;
+        const int rc = enqueue(cs);
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        const int captured = (int)(launches() - before);
+        count_launch(-captured);
+        cudaGraphExec_t exec = nullptr;
+        if (rc == OTK_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          hit->exec = exec; hit->launches = captured; hit->state = 1;
+        } else {
+          hit->state = -1;
+          cudaGetLastError();
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else if (cs) {
+        hit->state = -1;
+        cudaGetLastError();
+      }
+    }
+    if (hit && hit->state == 1) {
+      OTK_CUDA(cudaGraphLaunch(hit->exec, st));
+      count_launch(hit->launches);
+      launched = true;
+    }
+  }
+  if (!launched) OTK_TRY(enqueue(st));
+  // ---- the one read-back: loop control of both solves + Riccati sums
+  const size_t status_bytes = sizeof(FastStatus) + 2 * (size_t)a.L * 8 + 64;
+  std::vector<char> host(status_bytes);
+  const size_t span = reinterpret_cast<char*>(lay.acc + 2 * a.L) - reinterpret_cast<char*>(lay.status);
+  OTK_CUDA(cudaMemcpyAsync(host.data(), lay.status, span, cudaMemcpyDeviceToHost, st));
+  OTK_CUDA(cudaStreamSynchronize(st));
+  const FastStatus* hs = reinterpret_cast<const FastStatus*>(host.data());
+  const double* acc = reinterpret_cast<const double*>(host.data() + (reinterpret_cast<char*>(lay.acc) - reinterpret_cast<char*>(lay.status)));
+  const bool conv = hs->ctrl1[1] == NS_CONVERGED && hs->ctrl2[1] == NS_CONVERGED && hs->ctrl1[2] == 0 && hs->ctrl2[2] == 0 &&
+                    hs->ctrl1[0] <= NS_FAST_ITERS && hs->ctrl2[0] <= NS_FAST_ITERS && hs->ctrl1[0] <= NS_F32_OPERATOR_ITERS;
+  if (!conv) return 0;
+  for (int64_t l = 0; l < a.L; ++l) {
+    const double rel = sqrt(acc[2 * l] / fmax(acc[2 * l + 1], 1e-300));
+    if (!(rel < NS_F32_RICCATI_TOL)) return 0;
+  }
+  return 1;
+}
+
 // out = s0 * in + diag_add * I   (no symmetrisation: the stochastic operator is not symmetric), cast to out_dt
 template <typename W>
 __global__ void scale_add_kernel(const W* in, int64_t L, int64_t dim, double s0, double diag_add, void* out, int out_dt) {
@@ -754,6 +1080,13 @@ extern "C" int otk_transport_operator(const void* cov_s, const void* cov_t, int6
   cudaStream_t st = as_stream(stream);
   int verdict = NS_SLOW, used = 0;
   if (polish == 0 && dtype == OTK_F64 && dim <= NS_SMALL_DIM && iters <= 0) polish = 1;
+  if (polish <= 0 && iters <= 0) {
+    // optimistic single-graph path; anything it does not accept is redone below by the general path
+    const FastOpArgs fa{cov_s, cov_t, mean_s, mean_t, T, w2, workspace, workspace_bytes, L, dim, dtype, pg_star};
+    const int fr = operator_fast(fa, st);
+    if (fr < 0) return fr;
+    if (fr == 1) return OTK_OK;
+  }
   if (polish <= 0) {
     OTK_TRY(operator_impl<float>(cov_s, cov_t, L, dim, dtype, pg_star, iters, T, mean_s, mean_t, w2, workspace,
                                  workspace_bytes, &verdict, &used, st));

@@ -94,13 +94,14 @@ def mean_cov(run_sum: Tensor, run_cov: Tensor, n_obs: Tensor) -> Tuple[Tensor, T
     return mean, cov
 
 
-def symmetrize_shift(a: Tensor, shift: Optional[Tensor]) -> Tensor:
+def symmetrize_shift(a: Tensor, shift: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
     dev = N.compute_device(a)
     a = _dev_tensor(a, dev)
     d = a.shape[-1]
     lead, L = _lead(a.shape, 2)
     sh = None if shift is None else _dev_tensor(shift, dev, a.dtype).expand(lead).contiguous()
-    out = torch.empty_like(a)
+    if out is None or out.shape != a.shape or out.dtype != a.dtype or out.device != a.device or not out.is_contiguous():
+        out = torch.empty_like(a)
     with torch.cuda.device(dev):
         st = N.load().otk_symmetrize_shift(N.ptr(a), N.ptr(sh), L, d, N.ptr(out), N.dtype_code(a.dtype),
                                            N.stream_ptr(dev))
@@ -175,8 +176,11 @@ def w2_gaussian(mean_s: Tensor, mean_t: Tensor, cov_s: Tensor, cov_t: Tensor, it
 
 
 def transport_operator(cov_s: Tensor, cov_t: Tensor, pg_star: float = 0.0, mean_s: Optional[Tensor] = None,
-                       mean_t: Optional[Tensor] = None, iters: int = 0) -> Tuple[Tensor, Optional[Tensor]]:
-    """T [*L,d,d] (dtype of the covariances) and, if means are given, W2^2 [*L] (fp64) from the same roots."""
+                       mean_t: Optional[Tensor] = None, iters: int = 0, out: Optional[Tuple[Tensor, Tensor]] = None
+                       ) -> Tuple[Tensor, Optional[Tensor]]:
+    """T [*L,d,d] (dtype of the covariances) and, if means are given, W2^2 [*L] (fp64) from the same roots.
+    `out = (T, w2)`: caller-owned result buffers.  A caller that passes the same operand and result tensors again lets
+    libotk replay the whole call as one CUDA graph (its graph cache is keyed on the pointers)."""
     dev = N.compute_device(cov_s, cov_t)
     dt = torch.float64 if (cov_s.dtype == torch.float64 or cov_t.dtype == torch.float64) else torch.float32
     cs, ct = _dev_tensor(cov_s, dev, dt), _dev_tensor(cov_t, dev, dt)
@@ -184,11 +188,18 @@ def transport_operator(cov_s: Tensor, cov_t: Tensor, pg_star: float = 0.0, mean_
     lead = torch.broadcast_shapes(cs.shape[:-2], ct.shape[:-2])
     L = int(lead.numel())
     cs, ct = _bcast(cs, lead, 2), _bcast(ct, lead, 2)
-    T = torch.empty_like(cs)
-    ms = mt = w2 = None
+    T = w2 = None
+    if out is not None and out[0].shape == cs.shape and out[0].dtype == dt and out[0].device == dev and out[0].is_contiguous():
+        T = out[0]
+    if T is None:
+        T = torch.empty_like(cs)
+    ms = mt = None
     if mean_s is not None and mean_t is not None:
         ms, mt = _bcast(_dev_tensor(mean_s, dev, dt), lead, 1), _bcast(_dev_tensor(mean_t, dev, dt), lead, 1)
-        w2 = torch.empty(lead, dtype=torch.float64, device=dev)
+        if out is not None and out[1] is not None and out[1].shape == lead and out[1].dtype == torch.float64 and out[1].device == dev:
+            w2 = out[1]
+        else:
+            w2 = torch.empty(lead, dtype=torch.float64, device=dev)
     lib = N.load()
     with torch.cuda.device(dev):
         ws = N.workspace(lib.otk_transport_operator_workspace_bytes(L, d), dev)

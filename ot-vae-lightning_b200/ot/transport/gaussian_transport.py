@@ -89,14 +89,30 @@ class GaussianTransport(TransportOperator, W2Mixin):
         raw_s, raw_t = sm.parametrizations.cov.original, tm.parametrizations.cov.original
         if not raw_s.is_cuda:
             return None
-        eps = torch.full(raw_s.shape[:-2], STABILITY_CONST, dtype=raw_s.dtype, device=raw_s.device)
-        cov_s, cov_t = K.symmetrize_shift(raw_s, eps), K.symmetrize_shift(raw_t, eps)
+        # operands and results live in buffers that persist across calls: with the same pointers every time libotk
+        # replays the whole map computation as one CUDA graph instead of ~100 launches
+        buf = getattr(self, "_map_buffers", None)
+        if buf is None or buf["cov_s"].shape != raw_s.shape or buf["cov_s"].device != raw_s.device or buf["cov_s"].dtype != self.dtype:
+            lead = raw_s.shape[:-2]
+            buf = dict(eps=torch.full(lead, STABILITY_CONST, dtype=raw_s.dtype, device=raw_s.device),
+                       cov_s=torch.empty(raw_s.shape, dtype=self.dtype, device=raw_s.device),
+                       cov_t=torch.empty(raw_s.shape, dtype=self.dtype, device=raw_s.device),
+                       T=torch.empty(raw_s.shape, dtype=self.dtype, device=raw_s.device),
+                       w2=torch.empty(lead, dtype=torch.float64, device=raw_s.device))
+            self._map_buffers = buf
+        if raw_s.dtype == self.dtype:
+            cov_s = K.symmetrize_shift(raw_s, buf["eps"], out=buf["cov_s"])
+            cov_t = K.symmetrize_shift(raw_t, buf["eps"], out=buf["cov_t"])
+        else:
+            cov_s = K.symmetrize_shift(raw_s, buf["eps"]).to(self.dtype)
+            cov_t = K.symmetrize_shift(raw_t, buf["eps"]).to(self.dtype)
         try:
-            T, w2 = K.transport_operator(cov_s.to(self.dtype), cov_t.to(self.dtype), pg_star=float(self.pg_star),
-                                         mean_s=sm.mean.to(self.dtype), mean_t=tm.mean.to(self.dtype))
+            T, w2 = K.transport_operator(cov_s, cov_t, pg_star=float(self.pg_star), mean_s=sm.mean.to(self.dtype),
+                                         mean_t=tm.mean.to(self.dtype), out=(buf["T"], buf["w2"]))
         except NotConverged:
             return None
-        return self._store(T, w2, raw_s.device)
+        # hand out copies: the buffers are overwritten by the next compute()
+        return self._store(T.clone(), w2.clone(), raw_s.device)
 
     def transport(self, inputs: Tensor) -> Tensor:
         """[*leading_shape, (B,) dim] -> same shape, dtype and device as `inputs` (reference :80-95)."""
