@@ -901,9 +901,9 @@ static int operator_fast(const FastOpArgs& a, cudaStream_t st) {
   }
   if (!launched) OTK_TRY(enqueue(st));
   // ---- the one read-back: loop control of both solves + Riccati sums
-  const size_t status_bytes = sizeof(FastStatus) + 2 * (size_t)a.L * 8 + 64;
-  std::vector<char> host(status_bytes);
+  // (the arena aligns every array to 256 bytes: the span from the status block to the end of the sums is what is copied)
   const size_t span = reinterpret_cast<char*>(lay.acc + 2 * a.L) - reinterpret_cast<char*>(lay.status);
+  std::vector<char> host(span);
   OTK_CUDA(cudaMemcpyAsync(host.data(), lay.status, span, cudaMemcpyDeviceToHost, st));
   OTK_CUDA(cudaStreamSynchronize(st));
   const FastStatus* hs = reinterpret_cast<const FastStatus*>(host.data());
