@@ -16,6 +16,8 @@ namespace otk { extern int g_apply_force_cg; extern int g_stats_force_cg; extern
 using namespace otk;
 // tuning aids (not part of include/otk.h)
 // tuning aid: 0 = automatic, 1 / 2 = force the single-CTA / CTA-pair apply kernel
+namespace otk { extern int g_fast_counters[4]; }
+extern "C" void otkdbg_fast_counters(int* out) { for (int i = 0; i < 4; ++i) out[i] = otk::g_fast_counters[i]; }
 extern "C" void otkdbg_set_apply_cg(int cg) { g_apply_force_cg = cg; }
 extern "C" void otkdbg_set_stats_cg(int cg) { g_stats_force_cg = cg; }
 extern "C" void otkdbg_set_stats_dbg(int m) { g_stats_dbg = m; }

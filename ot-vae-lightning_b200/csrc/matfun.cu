@@ -845,6 +845,7 @@ struct FastGraphKey {
 };
 struct FastGraphEntry { FastGraphKey key; cudaGraphExec_t exec; int launches; int state; };
 static std::vector<FastGraphEntry> g_fast_graphs;
+int g_fast_counters[4] = {0, 0, 0, 0};   // tuning aid: accepted, rejected, graph replays, eager runs (otkdbg_fast_counters)
 constexpr size_t FAST_GRAPH_CACHE = 16;
 
 // 1 = done (T, w2 written), 0 = not taken / not accepted (the caller runs the general path), < 0 = error
@@ -897,9 +898,10 @@ static int operator_fast(const FastOpArgs& a, cudaStream_t st) {
       OTK_CUDA(cudaGraphLaunch(hit->exec, st));
       count_launch(hit->launches);
       launched = true;
+      ++g_fast_counters[2];
     }
   }
-  if (!launched) OTK_TRY(enqueue(st));
+  if (!launched) { OTK_TRY(enqueue(st)); ++g_fast_counters[3]; }
   // ---- the one read-back: loop control of both solves + Riccati sums
   // (the arena aligns every array to 256 bytes: the span from the status block to the end of the sums is what is copied)
   const size_t span = reinterpret_cast<char*>(lay.acc + 2 * a.L) - reinterpret_cast<char*>(lay.status);
@@ -910,11 +912,12 @@ static int operator_fast(const FastOpArgs& a, cudaStream_t st) {
   const double* acc = reinterpret_cast<const double*>(host.data() + (reinterpret_cast<char*>(lay.acc) - reinterpret_cast<char*>(lay.status)));
   const bool conv = hs->ctrl1[1] == NS_CONVERGED && hs->ctrl2[1] == NS_CONVERGED && hs->ctrl1[2] == 0 && hs->ctrl2[2] == 0 &&
                     hs->ctrl1[0] <= NS_FAST_ITERS && hs->ctrl2[0] <= NS_FAST_ITERS && hs->ctrl1[0] <= NS_F32_OPERATOR_ITERS;
-  if (!conv) return 0;
+  if (!conv) { ++g_fast_counters[1]; return 0; }
   for (int64_t l = 0; l < a.L; ++l) {
     const double rel = sqrt(acc[2 * l] / fmax(acc[2 * l + 1], 1e-300));
-    if (!(rel < NS_F32_RICCATI_TOL)) return 0;
+    if (!(rel < NS_F32_RICCATI_TOL)) { ++g_fast_counters[1]; return 0; }
   }
+  ++g_fast_counters[0];
   return 1;
 }
 
