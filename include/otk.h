@@ -89,6 +89,14 @@ int otk_stats_update_f64(const double* x, int64_t L, int64_t rows, int64_t dim, 
 int otk_mean_cov(const void* sum, const void* sum_cov, const void* n_obs, int n_dtype, int64_t L,
                  int64_t dim, void* mean, void* cov, int dtype, otk_stream_t stream);
 
+/* GaussianModel.fit in one launch (gaussian_model.py:110-183: _compute_mean_cov -> _update_mean / _update_cov): for every
+ * leading index with n_obs > 1e-8, mean [L,d] = sum / n and cov_raw [L,d,d] = sum_cov / n - mean mean^T are overwritten;
+ * indices never observed keep their values.  cov_sym (may be NULL) additionally receives triu-mirror(cov_raw) + shift I,
+ * the operand of otk_transport_operator.  sum / sum_cov in buf_dtype, mean / cov_raw / cov_sym in dtype. */
+int otk_gaussian_fit(const void* sum, const void* sum_cov, int buf_dtype, const void* n_obs, int n_dtype, int64_t L,
+                     int64_t dim, void* mean, void* cov_raw, void* cov_sym, double shift, int dtype,
+                     otk_stream_t stream);
+
 /* The `Symmetric` + `MakePositiveDefinite` parametrizations read on every `.cov` access
  * (gaussian_model.py:204-229): out = triu(a) + triu(a,1)^T + shift*I, shift [L] (may be NULL). */
 int otk_symmetrize_shift(const void* a, const void* shift, int64_t L, int64_t dim, void* out,

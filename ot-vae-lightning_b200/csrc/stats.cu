@@ -156,6 +156,32 @@ __global__ void mean_cov_kernel(const void* sum, const void* sum_cov, const void
   }
 }
 
+// fit of one model in one launch (GaussianModel.fit -> _compute_mean_cov -> _update_mean / _update_cov,
+// gaussian_model.py:110-183): for every leading index with n > 1e-8, mean = sum / n and the raw covariance
+// sum_cov / n - mean mean^T (biased) are written in place; optionally also the operand GaussianTransport.compute() needs,
+// triu-mirror(raw) + shift I (the `Symmetric` + strict `MakePositiveDefinite` read of a PD matrix, :204-229).
+__global__ void gaussian_fit_kernel(const void* sum, const void* sum_cov, int buf_dt, const void* n_obs, int n_dt, int64_t L,
+                                    int64_t dim, void* mean, void* cov_raw, void* cov_sym, double shift, int out_dt) {
+  const int64_t total = L * dim * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = e / (dim * dim), r = e % (dim * dim), i = r / dim, j = r % dim;
+    const double n = load_real(n_obs, l, n_dt);
+    const bool seen = n > 1e-8;
+    double raw, sym;
+    if (seen) {
+      const double mi = load_real(sum, l * dim + i, buf_dt) / n, mj = load_real(sum, l * dim + j, buf_dt) / n;
+      raw = load_real(sum_cov, e, buf_dt) / n - mi * mj;
+      const int64_t up = l * dim * dim + (i <= j ? i * dim + j : j * dim + i);
+      sym = load_real(sum_cov, up, buf_dt) / n - mi * mj;      // the upper-triangle element, mirrored
+      store_real(cov_raw, e, out_dt, raw);
+      if (j == 0) store_real(mean, l * dim + i, out_dt, mi);
+    } else {
+      sym = load_real(cov_raw, l * dim * dim + (i <= j ? i * dim + j : j * dim + i), out_dt);
+    }
+    if (cov_sym) store_real(cov_sym, e, out_dt, sym + (i == j ? shift : 0.0));
+  }
+}
+
 __global__ void symmetrize_shift_kernel(const void* a, const void* shift, int64_t L, int64_t dim, void* out, int dt) {
   const int64_t total = L * dim * dim;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -290,6 +316,18 @@ extern "C" int otk_mean_cov(const void* sum, const void* sum_cov, const void* n_
   OTK_REQUIRE(L > 0 && dim > 0 && sum && sum_cov && n_obs && mean && cov, "mean_cov: bad arguments");
   mean_cov_kernel<<<ew_grid(L * dim * dim), 256, 0, as_stream(stream)>>>(sum, sum_cov, n_obs, n_dtype, L, dim, mean,
                                                                         cov, dtype);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+extern "C" int otk_gaussian_fit(const void* sum, const void* sum_cov, int buf_dtype, const void* n_obs, int n_dtype, int64_t L,
+                                int64_t dim, void* mean, void* cov_raw, void* cov_sym, double shift, int dtype,
+                                otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(L > 0 && dim > 0 && sum && sum_cov && n_obs && mean && cov_raw, "gaussian_fit: bad arguments");
+  OTK_REQUIRE(cov_sym != cov_raw, "gaussian_fit: cov_sym must not alias cov_raw");
+  gaussian_fit_kernel<<<ew_grid(L * dim * dim), 256, 0, as_stream(stream)>>>(sum, sum_cov, buf_dtype, n_obs, n_dtype, L, dim, mean,
+                                                                           cov_raw, cov_sym, shift, dtype);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }

@@ -94,6 +94,22 @@ def mean_cov(run_sum: Tensor, run_cov: Tensor, n_obs: Tensor) -> Tuple[Tensor, T
     return mean, cov
 
 
+def gaussian_fit(n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, mean: Tensor, cov_raw: Tensor,
+                 cov_sym: Optional[Tensor] = None, shift: float = 0.0) -> None:
+    """In-place fit of mean / raw covariance (and optionally the symmetrised + shifted covariance) from the running buffers;
+    all tensors contiguous on one CUDA device, mean / cov_raw / cov_sym of one dtype (otk_gaussian_fit)."""
+    dev = run_sum.device
+    d = run_sum.shape[-1]
+    _, L = _lead(run_sum.shape, 1)
+    with N.on_device(dev) as ctx:
+        st = N.load().otk_gaussian_fit(run_sum.data_ptr(), run_cov.data_ptr(), N.dtype_code(run_sum.dtype), n_obs.data_ptr(),
+                                       N.dtype_code(n_obs.dtype), L, d, mean.data_ptr(), cov_raw.data_ptr(),
+                                       None if cov_sym is None else cov_sym.data_ptr(), float(shift),
+                                       N.dtype_code(mean.dtype), ctx.stream)
+    if st != N.OK:
+        N.check(st, "otk_gaussian_fit")
+
+
 def symmetrize_shift(a: Tensor, shift: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
     dev = N.compute_device(a)
     a = _dev_tensor(a, dev)

@@ -105,8 +105,9 @@ class GaussianModel(DistributionModel, W2Mixin):
             K.stats_update(samples, self._n_obs, self._running_sum, self._running_sum_cov, self.decay)
 
     @torch.no_grad()
-    def fit(self, samples: Optional[Tensor] = None) -> None:
-        """reference gaussian_model.py:110-126"""
+    def fit(self, samples: Optional[Tensor] = None, cov_operand: Optional[Tensor] = None, operand_shift: float = 0.0) -> None:
+        """reference gaussian_model.py:110-126.  `cov_operand` (an extension used by `GaussianTransport.compute`): a buffer
+        [*L, d, d] of the parameter dtype that additionally receives triu-mirror(raw covariance) + `operand_shift` I."""
         self._fit_warn()
         if self.update_with_autograd:
             if samples is None:
@@ -116,10 +117,38 @@ class GaussianModel(DistributionModel, W2Mixin):
             self._update_cov(cov, seen)
         if samples is not None:
             self.update(samples)
+        if self._native_fit(cov_operand, operand_shift):
+            return
         self._n_obs, self._running_sum, self._running_sum_cov = self._stats(None, reduce=True)
         mean, cov, seen = self._compute_mean_cov(self._n_obs, self._running_sum, self._running_sum_cov)
         self._update_mean(mean, seen)
         self._update_cov(cov, seen)
+        self._fit_generation = getattr(self, "_fit_generation", 0) + 1
+        if cov_operand is not None:
+            shift = torch.full(self.vec_shape[:-1], operand_shift, dtype=cov_operand.dtype, device=cov_operand.device)
+            K.symmetrize_shift(self.parametrizations.cov.original.to(cov_operand.dtype), shift, out=cov_operand)
+
+    def _native_fit(self, cov_operand: Optional[Tensor], operand_shift: float) -> bool:
+        """The whole fit as ONE kernel (`otk_gaussian_fit`): mean = sum / n and the raw covariance written in place for every
+        leading index that has observations (the others keep their state), no host read-back.  Full-covariance models on
+        a CUDA device; under a process group the packed all-reduce of the statistics runs first."""
+        if self.diag or self.update_with_autograd or not self._running_sum.is_cuda:
+            return False
+        mean, raw = self.mean, self.parametrizations.cov.original
+        ok = (mean.dtype == raw.dtype and mean.dtype in (torch.float32, torch.float64) and mean.is_contiguous()
+              and raw.is_contiguous() and mean.device == self._running_sum.device
+              and (cov_operand is None or (cov_operand.dtype == raw.dtype and cov_operand.shape == raw.shape
+                                           and cov_operand.is_contiguous() and cov_operand.device == raw.device)))
+        if not ok:
+            return False
+        if self._reduce_is_active():
+            self._n_obs, self._running_sum, self._running_sum_cov = self._stats(None, reduce=True)
+        for buf in (self._n_obs, self._running_sum, self._running_sum_cov):
+            if not buf.is_contiguous():
+                return False
+        K.gaussian_fit(self._n_obs, self._running_sum, self._running_sum_cov, mean.data, raw.data, cov_operand, operand_shift)
+        self._fit_generation = getattr(self, "_fit_generation", 0) + 1     # caches keyed on the fitted state look at this
+        return True
 
     def predict(self, samples: Tensor) -> Tensor:
         self._validate_samples(samples)

@@ -71,8 +71,8 @@ class TransportOperator(nn.Module, utils.DDPMixin, ABC):
             if self.store_target:
                 self._target_samples = self._stash(self._target_samples, target_samples)
 
-    def fit_models(self):
-        """`fit` both models (all-gathering stored samples first), reference base.py:134-149."""
+    def _stored_samples(self):
+        """stored (and, under DDP, all-gathered) samples of the two sides; None for a side that streams statistics"""
         src = tgt = None
         if self.store_source:
             if self.gather:
@@ -82,6 +82,11 @@ class TransportOperator(nn.Module, utils.DDPMixin, ABC):
             if self.gather:
                 self._target_samples = torch.cat(self.gather(self._target_samples), dim=-2)
             tgt = self._target_samples
+        return src, tgt
+
+    def fit_models(self):
+        """`fit` both models (all-gathering stored samples first), reference base.py:134-149."""
+        src, tgt = self._stored_samples()
         self.source_model.fit(src)
         self.target_model.fit(tgt)
 

@@ -39,14 +39,23 @@ class GaussianTransport(TransportOperator, W2Mixin):
         self._prepared = None
 
     def fit_models(self):
+        """While `compute()` runs, `_fit_operands = (cov_s_buf, cov_t_buf, shift)` asks the fit kernels to write the
+        symmetrised + shifted covariances the map computation consumes as well (one launch per model does the whole fit)."""
         self._prepared = None          # the means are about to change
-        super().fit_models()
+        operands = getattr(self, "_fit_operands", None)
+        if operands is None:
+            return super().fit_models()
+        src, tgt = self._stored_samples()
+        self.source_model.fit(src, cov_operand=operands[0], operand_shift=operands[2])
+        self.target_model.fit(tgt, cov_operand=operands[1], operand_shift=operands[2])
+        self._operands_written = True
 
     def _prepared_operator(self):
         """`kernels.PreparedTransport` of the current (means, T), rebuilt whenever one of them was replaced or written to
         (tensor identity + version counters), so assigning `transport_operator` or refitting a model cannot go stale."""
         T, ms, mt = self.transport_operator, self.source_model.mean, self.target_model.mean
-        key = (id(T), T._version, id(ms), ms._version, id(mt), mt._version)
+        key = (id(T), T._version, id(ms), ms._version, id(mt), mt._version,
+               getattr(self.source_model, "_fit_generation", 0), getattr(self.target_model, "_fit_generation", 0))
         cached = getattr(self, "_prepared", None)
         if cached is None or cached[0] != key:
             var_s = self.source_model.parametrizations.cov.original.diagonal(dim1=-2, dim2=-1)
@@ -56,11 +65,12 @@ class GaussianTransport(TransportOperator, W2Mixin):
 
     def compute(self) -> Tensor:
         """Fit both Gaussians, then W2^2 [*leading_shape] and the operators (reference :64-78)."""
-        self.fit_models()
         if not (self.diag or self.stochastic):
-            fast = self._compute_full_deterministic()
+            fast = self._compute_full_deterministic()       # fits the models itself (fused with the operand preparation)
             if fast is not None:
                 return fast
+        else:
+            self.fit_models()
         with P.cached():  # evaluate each `.cov` parametrization once for everything below
             mean_s, mean_t = self.source_model.mean, self.target_model.mean
             cov_s, cov_t = self.source_model.cov, self.target_model.cov
@@ -76,7 +86,10 @@ class GaussianTransport(TransportOperator, W2Mixin):
 
     def _store(self, T: Tensor, w2: Tensor, device) -> Tensor:
         self.transport_operator = T.to(device=device, dtype=self.dtype)
-        self.cov_stochastic_noise = torch.zeros_like(self.transport_operator)
+        zero = getattr(self, "_zero_noise", None)        # Cw = 0 (reference :768): one all-zero tensor, never written to
+        if zero is None or zero.shape != T.shape or zero.dtype != self.transport_operator.dtype or zero.device != self.transport_operator.device:
+            zero = self._zero_noise = torch.zeros_like(self.transport_operator)
+        self.cov_stochastic_noise = zero
         return w2.to(device)
 
     def _compute_full_deterministic(self):
@@ -88,6 +101,7 @@ class GaussianTransport(TransportOperator, W2Mixin):
         sm, tm = self.source_model, self.target_model
         raw_s, raw_t = sm.parametrizations.cov.original, tm.parametrizations.cov.original
         if not raw_s.is_cuda:
+            self.fit_models()
             return None
         # operands and results live in buffers that persist across calls: with the same pointers every time libotk
         # replays the whole map computation as one CUDA graph instead of ~100 launches
@@ -100,12 +114,17 @@ class GaussianTransport(TransportOperator, W2Mixin):
                        T=torch.empty(raw_s.shape, dtype=self.dtype, device=raw_s.device),
                        w2=torch.empty(lead, dtype=torch.float64, device=raw_s.device))
             self._map_buffers = buf
-        if raw_s.dtype == self.dtype:
-            cov_s = K.symmetrize_shift(raw_s, buf["eps"], out=buf["cov_s"])
-            cov_t = K.symmetrize_shift(raw_t, buf["eps"], out=buf["cov_t"])
+        self._fit_operands = (buf["cov_s"], buf["cov_t"], STABILITY_CONST) if raw_s.dtype == self.dtype else None
+        self._operands_written = False
+        try:
+            self.fit_models()          # an overridden / replaced fit_models simply leaves the operands unwritten
+        finally:
+            self._fit_operands = None
+        if self._operands_written:
+            cov_s, cov_t = buf["cov_s"], buf["cov_t"]
         else:
-            cov_s = K.symmetrize_shift(raw_s, buf["eps"]).to(self.dtype)
-            cov_t = K.symmetrize_shift(raw_t, buf["eps"]).to(self.dtype)
+            cov_s = K.symmetrize_shift(raw_s, buf["eps"], out=buf["cov_s"]).to(self.dtype)
+            cov_t = K.symmetrize_shift(raw_t, buf["eps"], out=buf["cov_t"]).to(self.dtype)
         try:
             T, w2 = K.transport_operator(cov_s, cov_t, pg_star=float(self.pg_star), mean_s=sm.mean.to(self.dtype),
                                          mean_t=tm.mean.to(self.dtype), out=(buf["T"], buf["w2"]))

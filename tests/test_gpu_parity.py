@@ -880,3 +880,30 @@ def test_codebook_model_streaming_update_uses_the_kernel_and_matches_the_dense_p
         models.append(cb)
     assert rel(models[0].codebook, models[1].codebook.cpu()) < 1e-6 and rel(models[0]._n_obs, models[1]._n_obs.cpu()) < 1e-9
     assert rel(models[0]._running_sum, models[1]._running_sum.cpu()) < 1e-6
+
+
+def test_native_fit_matches_the_stepwise_fit_and_skips_unseen_indices(api, monkeypatch):
+    """`otk_gaussian_fit` (one launch: mean, raw covariance, symmetrised + shifted operand) == the step-by-step fit
+    (mean_cov -> masked assignment, reference gaussian_model.py:159-183); a leading index without observations keeps its
+    initial mean / covariance."""
+    from ot_vae_lightning_b200.ot.distribution_models import gaussian_model as gm_mod
+    torch.manual_seed(9)
+    x = torch.randn(3, 500, 24, device="cuda") * 1.7 + 0.4
+    models = []
+    for native in (True, False):
+        torch.manual_seed(1)
+        gm = api.GaussianModel(3, 24, w2_cfg=dict(make_pd=True), dtype=torch.double, reduce_on_update=False).cuda()
+        if not native:
+            monkeypatch.setattr(gm_mod.GaussianModel, "_native_fit", lambda self, c, s: False)
+        gm.update(x)
+        gm._n_obs[1] = 0                                   # class 1 never observed
+        operand = torch.empty(3, 24, 24, dtype=torch.double, device="cuda")
+        gm.fit(cov_operand=operand, operand_shift=1e-8)
+        models.append((gm, operand))
+    (a, op_a), (b, op_b) = models
+    assert rel(a.mean, b.mean.cpu()) < 1e-12 and rel(a.parametrizations.cov.original[[0, 2]], b.parametrizations.cov.original[[0, 2]].cpu()) < 1e-12
+    assert torch.equal(a.mean[1], a.vec_init[1]) and torch.equal(a.parametrizations.cov.original[1], a.cov_init[1])
+    assert rel(op_a[[0, 2]], op_b[[0, 2]].cpu()) < 1e-12
+    raw = a.parametrizations.cov.original
+    want = torch.triu(raw) + torch.triu(raw, 1).transpose(-1, -2) + 1e-8 * torch.eye(24, dtype=torch.double, device="cuda")
+    assert rel(op_a, want.cpu()) < 1e-14
