@@ -143,8 +143,13 @@ def ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def raw_stream(device_index: int) -> int:
+    """cudaStream_t of torch's current stream on `device_index` as an int (one C call, no Stream object)."""
+    return torch._C._cuda_getCurrentRawStream(device_index)
+
+
 def stream_ptr(device: torch.device):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return C.c_void_p(raw_stream(device.index if device.index is not None else torch.cuda.current_device()))
 
 
 class on_device:
@@ -159,10 +164,11 @@ class on_device:
 
     def __enter__(self):
         idx = self.device.index
-        if idx is not None and idx != torch.cuda.current_device():
+        cur = torch.cuda.current_device()
+        if idx is not None and idx != cur:
             self._ctx = torch.cuda.device(self.device)
             self._ctx.__enter__()
-        self.stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.stream = raw_stream(cur if idx is None else idx)
         return self
 
     def __exit__(self, *exc):
@@ -186,8 +192,8 @@ _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     """Per-(device, stream) scratch buffer handed to libotk (which never allocates)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, raw_stream(idx))
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         _workspaces[key] = buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

@@ -912,6 +912,13 @@ static int operator_fast(const FastOpArgs& a, cudaStream_t st) {
   const double* acc = reinterpret_cast<const double*>(host.data() + (reinterpret_cast<char*>(lay.acc) - reinterpret_cast<char*>(lay.status)));
   const bool conv = hs->ctrl1[1] == NS_CONVERGED && hs->ctrl2[1] == NS_CONVERGED && hs->ctrl1[2] == 0 && hs->ctrl2[2] == 0 &&
                     hs->ctrl1[0] <= NS_FAST_ITERS && hs->ctrl2[0] <= NS_FAST_ITERS && hs->ctrl1[0] <= NS_F32_OPERATOR_ITERS;
+  static const bool dbg = [] { const char* e = getenv("OTK_FAST_DEBUG"); return e && e[0] == '1'; }();
+  if (dbg) {
+    fprintf(stderr, "operator_fast d=%lld L=%lld: solve1 iters %d verdict %d div %d | solve2 iters %d verdict %d div %d | riccati",
+            (long long)a.d, (long long)a.L, hs->ctrl1[0], hs->ctrl1[1], hs->ctrl1[2], hs->ctrl2[0], hs->ctrl2[1], hs->ctrl2[2]);
+    for (int64_t l = 0; l < a.L && l < 4; ++l) fprintf(stderr, " %.2e", sqrt(acc[2 * l] / fmax(acc[2 * l + 1], 1e-300)));
+    fprintf(stderr, "\n");
+  }
   if (!conv) { ++g_fast_counters[1]; return 0; }
   for (int64_t l = 0; l < a.L; ++l) {
     const double rel = sqrt(acc[2 * l] / fmax(acc[2 * l + 1], 1e-300));

@@ -19,13 +19,15 @@ constexpr int ST_FUSED_ROWS = 256;   // batches up to this many rows take the si
 // running buffers itself - one launch per update, no staging area, no atomics (latency mode: batches of a few hundred).
 // (StatsRunning: stats_umma.cuh)
 
-template <bool FUSED, typename X>
+// T = tile width (64: 4 x 4 outputs per thread; 32: 2 x 2 - four times as many CTAs for the small batches of the latency
+// mode, where a 128-wide model has only three 64-wide tile pairs)
+template <bool FUSED, typename X, int T = ST_T>
 __global__ void __launch_bounds__(ST_THREADS)
 stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
                   int64_t chunk_rows, int n_tiles, double* __restrict__ ws_cov, double* __restrict__ ws_sum,
                   StatsRunning run) {
-  __shared__ X As[ST_BK][ST_T + 4];
-  __shared__ X Bs[ST_BK][ST_T + 4];
+  __shared__ X As[ST_BK][T + 4];
+  __shared__ X Bs[ST_BK][T + 4];
   // decode the upper-triangular tile pair (ti <= tj) from blockIdx.x
   int p = blockIdx.x, ti = 0;
   while (p >= n_tiles - ti) { p -= n_tiles - ti; ++ti; }
@@ -34,53 +36,54 @@ stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t ro
   const int64_t r0 = (int64_t)blockIdx.y * chunk_rows;
   const int64_t r1 = min(rows, r0 + chunk_rows);
   const X* xb = x + l * batch_stride;
-  const int64_t i0 = (int64_t)ti * ST_T, j0 = (int64_t)tj * ST_T;
+  constexpr int TH = T / 16;      // outputs per thread and direction
+  const int64_t i0 = (int64_t)ti * T, j0 = (int64_t)tj * T;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-  double acc[4][4];
+  double acc[TH][TH];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TH; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < TH; ++j) acc[i][j] = 0.0;
   double colsum = 0.0;  // threads 0..63 of a diagonal CTA own one column each
 
   for (int64_t k0 = r0; k0 < r1; k0 += ST_BK) {
 #pragma unroll
-    for (int r = 0; r < (ST_T * ST_BK) / ST_THREADS; ++r) {
+    for (int r = 0; r < (T * ST_BK) / ST_THREADS; ++r) {
       int e = tid + r * ST_THREADS;
-      int kk = e / ST_T, cc = e % ST_T;
+      int kk = e / T, cc = e % T;
       int64_t row = k0 + kk;
       bool rok = row < r1;
       As[kk][cc] = (rok && i0 + cc < dim) ? xb[row * row_stride + i0 + cc] : X(0);
       Bs[kk][cc] = (rok && j0 + cc < dim) ? xb[row * row_stride + j0 + cc] : X(0);
     }
     __syncthreads();
-    if (ti == tj && tid < ST_T) {
+    if (ti == tj && tid < T) {
 #pragma unroll
       for (int kk = 0; kk < ST_BK; ++kk) colsum += (double)As[kk][tid];
     }
 #pragma unroll
     for (int kk = 0; kk < ST_BK; ++kk) {
-      double a[4], b[4];
+      double a[TH], b[TH];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = (double)As[kk][ty * 4 + i];
+      for (int i = 0; i < TH; ++i) a[i] = (double)As[kk][ty * TH + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = (double)Bs[kk][tx * 4 + j];
+      for (int j = 0; j < TH; ++j) b[j] = (double)Bs[kk][tx * TH + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TH; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TH; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
   if constexpr (FUSED) {
     const double keep = run.decay < 0 ? 1.0 : run.decay, gain = run.decay < 0 ? 1.0 : 1.0 - run.decay;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int64_t gi = i0 + ty * 4 + i;
+    for (int i = 0; i < TH; ++i) {
+      int64_t gi = i0 + ty * TH + i;
       if (gi >= dim) continue;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int64_t gj = j0 + tx * 4 + j;
+      for (int j = 0; j < TH; ++j) {
+        int64_t gj = j0 + tx * TH + j;
         if (gj >= dim) continue;
         const int64_t e = l * dim * dim + gi * dim + gj;
         store_real(run.sum_cov, e, run.buf_dtype, load_real(run.sum_cov, e, run.buf_dtype) * keep + acc[i][j] * gain);
@@ -90,7 +93,7 @@ stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t ro
         }
       }
     }
-    if (ti == tj && tid < ST_T && i0 + tid < dim) {
+    if (ti == tj && tid < T && i0 + tid < dim) {
       const int64_t e = l * dim + i0 + tid;
       store_real(run.sum, e, run.buf_dtype, load_real(run.sum, e, run.buf_dtype) * keep + colsum * gain);
     }
@@ -100,16 +103,16 @@ stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t ro
   }
   double* cov = ws_cov + l * dim * dim;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int64_t gi = i0 + ty * 4 + i;
+  for (int i = 0; i < TH; ++i) {
+    int64_t gi = i0 + ty * TH + i;
     if (gi >= dim) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int64_t gj = j0 + tx * 4 + j;
+    for (int j = 0; j < TH; ++j) {
+      int64_t gj = j0 + tx * TH + j;
       if (gj < dim) atomicAdd(&cov[gi * dim + gj], acc[i][j]);
     }
   }
-  if (ti == tj && tid < ST_T && i0 + tid < dim) atomicAdd(&ws_sum[l * dim + i0 + tid], colsum);
+  if (ti == tj && tid < T && i0 + tid < dim) atomicAdd(&ws_sum[l * dim + i0 + tid], colsum);
 }
 
 // merge the fp64 staging area into the running buffers (mirror the lower triangle, apply the EMA rule).
@@ -251,8 +254,15 @@ static int stats_update_impl(const X* x, int64_t L, int64_t rows, int64_t dim, i
     const int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
     if (pairs <= 65535 && L <= 65535) {
       StatsRunning run{n_obs, sum, sum_cov, n_dtype, buf_dtype, decay};
-      stats_simt_kernel<true, X><<<dim3((unsigned)pairs, 1, (unsigned)L), ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride,
-                                                                                             rows, n_tiles, nullptr, nullptr, run);
+      if (pairs * L * 2 <= sm_count()) {        // too few 64-wide tile pairs to occupy the machine: 32-wide tiles
+        const int n32 = (int)ceil_div(dim, 32);
+        const int64_t pairs32 = (int64_t)n32 * (n32 + 1) / 2;
+        stats_simt_kernel<true, X, 32><<<dim3((unsigned)pairs32, 1, (unsigned)L), ST_THREADS, 0, st>>>(
+            x, rows, dim, row_stride, batch_stride, rows, n32, nullptr, nullptr, run);
+      } else {
+        stats_simt_kernel<true, X><<<dim3((unsigned)pairs, 1, (unsigned)L), ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride,
+                                                                                               rows, n_tiles, nullptr, nullptr, run);
+      }
       OTK_LAUNCH_CHECK();
       return OTK_OK;
     }

@@ -46,32 +46,43 @@ def _strided_latents(x: Tensor, dev: torch.device, lead: torch.Size, d: int) -> 
     return x, d, x.shape[-2] * d
 
 
+_stats_ws_bytes = {}      # (L, rows, d) -> otk_stats_update_workspace_bytes (one ctypes call less per update)
+
+
 def stats_update(x: Tensor, n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, decay: Optional[float]) -> None:
     """In-place update of the running buffers (all on one CUDA device) with latents x [*L, B, d] (fp32)."""
     dev = run_sum.device
     d = run_sum.shape[-1]
-    lead, L = _lead(run_sum.shape, 1)
     lib = N.load()
-    if x.dtype == torch.float64:
-        # fp64 latents keep fp64 products (otk_stats_update_f64): what the reference's einsum on `samples.type_as(buffer)` /
-        # FID's `features.double()` computes; everything else is streamed as fp32 through the tensor-core kernels
-        x = _dev_tensor(x, dev, torch.float64)
-        if x.shape[:-2] != lead:
-            x = x.expand(*lead, *x.shape[-2:]).contiguous()
-        row_stride, batch_stride, entry = d, x.shape[-2] * d, lib.otk_stats_update_f64
+    if x.dim() == 2 and run_sum.dim() == 1 and x.dtype == torch.float32 and x.device == dev and x.is_contiguous() \
+            and not x.requires_grad and x.shape[1] == d and x.shape[0] > 0 and x.data_ptr() % 16 == 0:
+        # the common call (one model, a contiguous fp32 batch on the model's device): nothing to normalise
+        L, rows, row_stride, batch_stride, entry = 1, x.shape[0], d, x.shape[0] * d, lib.otk_stats_update
     else:
-        x, row_stride, batch_stride = _strided_latents(x, dev, lead, d)
-        entry = lib.otk_stats_update
-    rows = x.shape[-2]
-    for buf in (n_obs, run_sum, run_cov):
-        if not (buf.is_cuda and buf.is_contiguous()):
-            raise ValueError("running buffers must be contiguous CUDA tensors")
+        lead, L = _lead(run_sum.shape, 1)
+        if x.dtype == torch.float64:
+            # fp64 latents keep fp64 products (otk_stats_update_f64): what the reference's einsum on
+            # `samples.type_as(buffer)` / FID's `features.double()` computes; everything else is streamed as fp32 through the
+            # tensor-core kernels
+            x = _dev_tensor(x, dev, torch.float64)
+            if x.shape[:-2] != lead:
+                x = x.expand(*lead, *x.shape[-2:]).contiguous()
+            row_stride, batch_stride, entry = d, x.shape[-2] * d, lib.otk_stats_update_f64
+        else:
+            x, row_stride, batch_stride = _strided_latents(x, dev, lead, d)
+            entry = lib.otk_stats_update
+        rows = x.shape[-2]
+    if not (run_sum.is_cuda and n_obs.is_contiguous() and run_sum.is_contiguous() and run_cov.is_contiguous()):
+        raise ValueError("running buffers must be contiguous CUDA tensors")
+    key = (L, rows, d)
+    need = _stats_ws_bytes.get(key)
+    if need is None:
+        need = _stats_ws_bytes[key] = lib.otk_stats_update_workspace_bytes(L, rows, d)
     with N.on_device(dev) as ctx:
-        ws = ctx.workspace(lib.otk_stats_update_workspace_bytes(L, rows, d))
-        st = entry(x.data_ptr(), L, rows, d, row_stride, batch_stride,
-                                  -1.0 if decay is None else float(decay),
-                                  n_obs.data_ptr(), N.dtype_code(n_obs.dtype), run_sum.data_ptr(), run_cov.data_ptr(),
-                                  N.dtype_code(run_sum.dtype), ws.data_ptr(), ws.numel(), ctx.stream)
+        ws = ctx.workspace(need)
+        st = entry(x.data_ptr(), L, rows, d, row_stride, batch_stride, -1.0 if decay is None else float(decay),
+                   n_obs.data_ptr(), N.dtype_code(n_obs.dtype), run_sum.data_ptr(), run_cov.data_ptr(),
+                   N.dtype_code(run_sum.dtype), ws.data_ptr(), ws.numel(), ctx.stream)
     if st != N.OK:
         N.check(st, "otk_stats_update")
 
@@ -285,6 +296,7 @@ class PreparedTransport:
             st = lib.otk_transport_prepare(N.ptr(ms), N.ptr(mt), N.ptr(Td), N.ptr(vs), N.dtype_code(dt), self.L, self.d,
                                            N.ptr(self.state), self.state.numel(), N.stream_ptr(dev))
         N.check(st, "otk_transport_prepare")
+        self._entry, self._state_ptr, self._state_bytes = lib.otk_apply_transport_prepared_strided, self.state.data_ptr(), self.state.numel()
 
     def apply(self, x: Tensor) -> Tensor:
         """x [*lead, B, d] (any float dtype / device) -> fp32 [*lead, B, d] on the compute device.  fp32 views with a unit
@@ -293,12 +305,15 @@ class PreparedTransport:
             raise ValueError("PreparedTransport.apply: input does not match the operator's leading shape / dimension")
         if x.shape[-2] == 0:
             return torch.empty(x.shape, dtype=torch.float32, device=self.device)
-        xd, row_stride, batch_stride = _strided_latents(x, self.device, torch.Size(self.lead), self.d)
+        if x.dim() == 2 and x.dtype == torch.float32 and x.device == self.device and x.is_contiguous() and not x.requires_grad \
+                and x.data_ptr() % 16 == 0:
+            xd, row_stride, batch_stride = x, self.d, x.shape[0] * self.d          # the common call: nothing to normalise
+        else:
+            xd, row_stride, batch_stride = _strided_latents(x, self.device, torch.Size(self.lead), self.d)
         y = torch.empty(x.shape, dtype=torch.float32, device=self.device)
         with N.on_device(self.device) as ctx:
-            st = N.load().otk_apply_transport_prepared_strided(xd.data_ptr(), self.L, x.shape[-2], self.d, row_stride,
-                                                               batch_stride, self.state.data_ptr(), self.state.numel(),
-                                                               y.data_ptr(), ctx.stream)
+            st = self._entry(xd.data_ptr(), self.L, x.shape[-2], self.d, row_stride, batch_stride, self._state_ptr,
+                             self._state_bytes, y.data_ptr(), ctx.stream)
         if st != N.OK:
             N.check(st, "otk_apply_transport_prepared_strided")
         return y

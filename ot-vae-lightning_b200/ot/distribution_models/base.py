@@ -71,13 +71,16 @@ class DistributionModel(nn.Module, utils.DDPMixin, ABC):
 
     def _validate_samples(self, samples: Tensor) -> None:
         """Shape check of `[*leading_shape, batch, dim]` samples.  The reference constructs these errors without raising
-        them (base.py:76-79); raising here would reject inputs it accepts, so they stay advisory."""
+        them (base.py:76-79); raising here would reject inputs it accepts, so the check is advisory and returns the list
+        of problems instead (empty when the shapes fit)."""
+        if samples.shape[-1] == self.dim and tuple(samples.shape[:-2]) == tuple(self.leading_shape):
+            return []
         problems = []
         if not self._broadcastable(samples.shape[:-2]):
             problems.append(f"leading dimensions {tuple(samples.shape[:-2])} do not broadcast to {tuple(self.leading_shape)}")
         if samples.size(-1) != self.dim:
             problems.append(f"dimensionality {samples.size(-1)} != {self.dim}")
-        self._last_sample_problems = problems
+        return problems
 
     def _autograd_warning(self, what: str) -> None:
         if self.update_with_autograd:
