@@ -211,6 +211,9 @@ int otk_sinkhorn_points(const float* x, const float* y, int64_t N, int64_t M, in
  * reuse_prepared != 0: the workspace still holds the operand planes (FP16 points, squared norms) an earlier
  * colstep / rowstep call prepared for the SAME (x_local, y, sizes) - the preparation passes are skipped; the
  * caller must then hand in the same, otherwise untouched, workspace.
+ * reuse_prepared == 2: in addition the previous call of this half-step on this workspace was the previous Sinkhorn
+ * iteration (its biases and partial log-sum-exps are still there): the fused engine runs its bounded-shift mode, one
+ * sweep per cost tile instead of an online maximum.
  * otk_lse_combine: part_max / part_sum rows are `part_stride` floats apart (e.g. 2*M for an all-gathered
  * [ranks, 2, M] buffer). */
 int otk_sinkhorn_points_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M,

@@ -352,6 +352,7 @@ __global__ void fs_finalize_kernel(const float* __restrict__ pm, const float* __
     } else if (mode == 1) {
       out_m[r] = m * LN2;
       out_l[r] = l;
+      if (lse_out) lse_out[r] = m + log2f(l);       // partial LSE over the local rows: next call's shift
     } else {
       out_m[r] = sq[r] + m;
     }
@@ -369,10 +370,20 @@ __global__ void fs_finalize_kernel(const float* __restrict__ pm, const float* __
 }
 
 // bias2[r] = (pot[r] - sq[r] * nrm_scale) * log2e   (bias of a side from its potentials)
+// dmax_out (optional, zeroed by the caller): max |new bias2 - bias2 of the previous call|, the bound the bounded-shift
+// mode of the next pass needs (row-sharded half-steps: the previous bias is still in the workspace)
 __global__ void fs_bias_kernel(const float* __restrict__ pot, const float* __restrict__ sq, float nrm_scale, int64_t n,
-                               float* __restrict__ bias2) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
-    bias2[r] = (pot ? pot[r] - sq[r] * nrm_scale : -sq[r] * nrm_scale) * LOG2E;
+                               float* __restrict__ bias2, float* __restrict__ dmax_out = nullptr) {
+  float dmx = 0.f;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const float nb = (pot ? pot[r] - sq[r] * nrm_scale : -sq[r] * nrm_scale) * LOG2E;
+    if (dmax_out) dmx = fmaxf(dmx, fabsf(nb - bias2[r]));
+    bias2[r] = nb;
+  }
+  if (dmax_out) {
+    dmx = warp_max(dmx);
+    if (threadIdx.x % 32 == 0) atomicMax(reinterpret_cast<unsigned*>(dmax_out), __float_as_uint(dmx));
+  }
 }
 
 __global__ void fs_check_kernel(float* diff, double threshold, FsState* state, float* dmax_next_x = nullptr,
@@ -622,18 +633,25 @@ __global__ void fs_fold_kernel(float* m, const float* sq, float nrm_scale, int64
 }
 
 // row-sharded half-steps; the prepared operands live in the caller's workspace and are reused when the caller says so
+// reuse_prepared: 0 = prepare the operands; 1 = operands in place; 2 = operands in place AND the state of the previous
+// call on this workspace (biases, partial LSEs) is that of the previous Sinkhorn iteration: bounded-shift mode - the partial
+// LSE over the local rows moved by at most max |delta bias| of the local rows, so one sweep per tile is enough
 int sk_umma_colstep(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* u_local,
                     double scale, double reg, int reuse_prepared, float* col_max, float* col_sum, void* workspace,
                     size_t workspace_bytes, cudaStream_t st) {
   FsWork w;
   OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st, !reuse_prepared));
   const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
-  fs_bias_kernel<<<fs_grid(n_local), 256, 0, st>>>(u_local, w.X.sq, nrm_scale, n_local, w.biasX2);
+  const bool bounded = reuse_prepared >= 2;
+  float* dmax = w.diff + 16;
+  if (bounded) OTK_CUDA(cudaMemsetAsync(dmax, 0, 4, st));
+  fs_bias_kernel<<<fs_grid(n_local), 256, 0, st>>>(u_local, w.X.sq, nrm_scale, n_local, w.biasX2, bounded ? dmax : nullptr);
   int parts = 0;
-  OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
+  OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st,
+                         bounded ? w.lseY : nullptr, dmax));
   // partial over the LOCAL rows of LSE_i(u_i + Cr_ij) = -nrm_j + LSE_i(bias_i + gamma x_i.y_j), natural log
   fs_finalize_kernel<<<fs_grid(M), 256, 0, st>>>(w.pm, w.pl, parts, M, 1, nullptr, nullptr, 0.f, nullptr, nullptr, col_max, col_sum,
-                                                nullptr, nullptr);
+                                                nullptr, nullptr, w.lseY);
   fs_fold_kernel<<<fs_grid(M), 256, 0, st>>>(col_max, w.Y.sq, nrm_scale, M);
   count_launch(2);
   OTK_LAUNCH_CHECK();
@@ -642,7 +660,7 @@ int sk_umma_colstep(const float* x_local, const float* y, int64_t n_local, int64
 
 __global__ void fs_rowstep_finish_kernel(const float* __restrict__ pm, const float* __restrict__ pl, int parts, int64_t n,
                                          const float* __restrict__ marg, const float* __restrict__ sq, float nrm_scale,
-                                         float* __restrict__ pot, float* diff) {
+                                         float* __restrict__ pot, float* diff, float* __restrict__ lse_out) {
   __shared__ float red[32];
   float acc = 0.f;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
@@ -653,9 +671,11 @@ __global__ void fs_rowstep_finish_kernel(const float* __restrict__ pm, const flo
       l = l * ex2(m - mm) + l2 * ex2(m2 - mm);
       m = mm;
     }
-    const float pn = logf(marg[r] + 1e-8f) - (m + log2f(l)) * LN2 + sq[r] * nrm_scale;
+    const float lse2 = m + log2f(l);
+    const float pn = logf(marg[r] + 1e-8f) - lse2 * LN2 + sq[r] * nrm_scale;
     acc += fabsf(pn - pot[r]);
     pot[r] = pn;
+    lse_out[r] = lse2;
   }
   acc = warp_sum(acc);
   if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
@@ -669,10 +689,15 @@ int sk_umma_rowstep(const float* x_local, const float* y, int64_t n_local, int64
   FsWork w;
   OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st, !reuse_prepared));
   const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
-  fs_bias_kernel<<<fs_grid(M), 256, 0, st>>>(v, w.Y.sq, nrm_scale, M, w.biasY2);
+  const bool bounded = reuse_prepared >= 2;          // see sk_umma_colstep
+  float* dmax = w.diff + 18;
+  if (bounded) OTK_CUDA(cudaMemsetAsync(dmax, 0, 4, st));
+  fs_bias_kernel<<<fs_grid(M), 256, 0, st>>>(v, w.Y.sq, nrm_scale, M, w.biasY2, bounded ? dmax : nullptr);
   int parts = 0;
-  OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st));
-  fs_rowstep_finish_kernel<<<fs_grid(n_local), 256, 0, st>>>(w.pm, w.pl, parts, n_local, a_local, w.X.sq, nrm_scale, u_local, diff);
+  OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st,
+                         bounded ? w.lseX : nullptr, dmax));
+  fs_rowstep_finish_kernel<<<fs_grid(n_local), 256, 0, st>>>(w.pm, w.pl, parts, n_local, a_local, w.X.sq, nrm_scale, u_local, diff,
+                                                            w.lseX);
   count_launch(1);
   OTK_LAUNCH_CHECK();
   return OTK_OK;

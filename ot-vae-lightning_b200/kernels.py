@@ -421,10 +421,11 @@ def points_workspace(n: int, m: int, d: int, cost: int, device) -> Tensor:
 
 
 def colstep(x_local: Tensor, y: Tensor, u_local: Tensor, scale: float, reg: float, cost: int = N.COST_SQEUCLIDEAN,
-            precision: int = 0, out: Optional[Tensor] = None, ws: Optional[Tensor] = None, reuse: bool = False
+            precision: int = 0, out: Optional[Tensor] = None, ws: Optional[Tensor] = None, reuse: int = 0
             ) -> Tuple[Tensor, Tensor]:
     """Partial column LSE over the local rows: (max, sumexp), written into `out` [2, M] if given.  `ws` + `reuse`: the
-    caller's dedicated workspace still holds the operands prepared by an earlier colstep / rowstep on the same clouds."""
+    caller's dedicated workspace still holds the operands prepared by an earlier colstep / rowstep on the same clouds
+    (reuse = 1), and the previous call was the previous Sinkhorn iteration (reuse = 2: bounded-shift mode)."""
     dev = x_local.device
     n, d = x_local.shape
     m = y.shape[0]
@@ -434,9 +435,9 @@ def colstep(x_local: Tensor, y: Tensor, u_local: Tensor, scale: float, reg: floa
     lib = N.load()
     with torch.cuda.device(dev):
         if ws is None:
-            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), False
+            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), 0
         st = lib.otk_sinkhorn_points_colstep(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(u_local), int(cost), float(scale),
-                                             float(reg), int(precision), int(bool(reuse)), N.ptr(cm), N.ptr(cs), N.ptr(ws),
+                                             float(reg), int(precision), int(reuse), N.ptr(cm), N.ptr(cs), N.ptr(ws),
                                              ws.numel(), N.stream_ptr(dev))
     N.check(st, "otk_sinkhorn_points_colstep")
     return cm, cs
@@ -456,16 +457,16 @@ def lse_combine(part_max: Tensor, part_sum: Tensor, b: Tensor, v: Tensor, diff: 
 
 def rowstep(x_local: Tensor, y: Tensor, a_local: Tensor, v: Tensor, u_local: Tensor, diff: Optional[Tensor],
             scale: float, reg: float, cost: int = N.COST_SQEUCLIDEAN, precision: int = 0, ws: Optional[Tensor] = None,
-            reuse: bool = False) -> None:
+            reuse: int = 0) -> None:
     dev = x_local.device
     n, d = x_local.shape
     m = y.shape[0]
     lib = N.load()
     with torch.cuda.device(dev):
         if ws is None:
-            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), False
+            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), 0
         st = lib.otk_sinkhorn_points_rowstep(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(a_local), N.ptr(v), int(cost),
-                                             float(scale), float(reg), int(precision), int(bool(reuse)), N.ptr(u_local),
+                                             float(scale), float(reg), int(precision), int(reuse), N.ptr(u_local),
                                              N.ptr(diff), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
     N.check(st, "otk_sinkhorn_points_rowstep")
 
@@ -484,7 +485,7 @@ def points_summary(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, u_loc
     lib = N.load()
     with torch.cuda.device(dev):
         if ws is None:
-            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), False
+            ws, reuse = N.workspace(lib.otk_sinkhorn_points_workspace_bytes(n, m, d, int(cost)), dev), 0
         st = lib.otk_sinkhorn_points_summary(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(a_local), N.ptr(b), N.ptr(u_local),
                                              N.ptr(v), int(cost), float(scale), float(reg), int(precision), int(bool(reuse)),
                                              N.ptr(part), N.ptr(row_marg), N.ptr(col_part), N.ptr(ws), ws.numel(),

@@ -82,13 +82,15 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
         plan["v"].zero_()
     u, v, diffs, part, gathered, ws = (plan[k] for k in ("u", "v", "diffs", "part", "gathered", "ws"))
 
-    def iteration(first: bool) -> None:
-        kernels.colstep(x_local, y, u, scale, reg, cost, precision, out=part, ws=ws, reuse=not first)
+    def iteration(stage: int) -> None:
+        """stage 0: first iteration (the half-steps prepare the operands); 1: second iteration; 2: steady state - both
+        half-steps find the previous iteration's biases and partial LSEs in `ws` and run in bounded-shift mode"""
+        kernels.colstep(x_local, y, u, scale, reg, cost, precision, out=part, ws=ws, reuse=min(stage, 2) if stage else 0)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), part.view(-1), group=group)
         diffs.zero_()
         kernels.lse_combine(gathered[:, 0], gathered[:, 1], b, v, diffs[1:2])
-        kernels.rowstep(x_local, y, a_local, v, u, diffs[0:1], scale, reg, cost, precision, ws=ws, reuse=True)
+        kernels.rowstep(x_local, y, a_local, v, u, diffs[0:1], scale, reg, cost, precision, ws=ws, reuse=max(1, min(stage, 2)))
 
     def converged() -> bool:
         du = diffs[0:1].clone()
@@ -99,12 +101,12 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
     done_iters = 0
     for it in range(max_iter):
         if want_graph and it == 2 and plan["graph"] is None and not plan["refused"]:
-            plan["graph"] = _capture(iteration, dev)
+            plan["graph"] = _capture(lambda **kw: iteration(2), dev)
             plan["refused"] = plan["graph"] is None
         if it >= 2 and plan["graph"] is not None:
             plan["graph"].replay()
         else:
-            iteration(first=(it == 0))
+            iteration(min(it, 2))
         done_iters = it + 1
         if threshold > 0 and ((it + 1) % poll_every == 0 or it + 1 == max_iter) and converged():
             break
