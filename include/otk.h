@@ -228,6 +228,23 @@ int otk_sinkhorn_points_rowstep(const float* x_local, const float* y, int64_t n_
                                 double scale, double reg, int precision, int reuse_prepared,
                                 float* u_local, float* diff /* += sum|du| */, void* workspace,
                                 size_t workspace_bytes, otk_stream_t stream);
+/* Row-sharded path with the exchange of the column partials fused into the kernels (no collective call):
+ * every rank owns an exchange buffer of otk_sinkhorn_exchange_bytes(world, M) bytes in SYMMETRIC memory (mapped into all
+ * peers of the node, zero-filled once), `peer_buffers_dev` is a device array [world] with each rank's mapping of it.
+ *   otk_sinkhorn_points_colstep_push: colstep whose final kernel stores this rank's (max, sumexp) partials [2, M] into every
+ *       peer's buffer over NVLink and releases a per-source flag (fused tcgen05 engine only: OTK_ERR_INVALID_ARGUMENT otherwise)
+ *   otk_lse_combine_wait: acquires the flags of all ranks, reduces the partials found in the LOCAL buffer,
+ *       v = log(b + 1e-8) - LSE, diff += sum |dv|, and advances the iteration counter.
+ * ctrl: 4 device ints per solver instance, zeroed once ([0] iteration counter, [2] != 0 after a wait timed out: a peer
+ * did not arrive within ~2 s).  One push + one combine per iteration, same order on every rank. */
+size_t otk_sinkhorn_exchange_bytes(int world, int64_t M);
+int otk_sinkhorn_points_colstep_push(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
+                                     const float* u_local, int cost_kind, double scale, double reg, int precision,
+                                     int reuse_prepared, void* const* peer_buffers_dev, int world, int rank, int* ctrl,
+                                     void* workspace, size_t workspace_bytes, otk_stream_t stream);
+int otk_lse_combine_wait(void* exchange_local, int world, int64_t M, const float* b, float* v,
+                         float* diff /* += sum|dv| */, int* ctrl, otk_stream_t stream);
+
 /* Plan statistics of a row shard without the plan: pi_ij = exp(u_i + v_j - scale*cost(x_i, y_j)/reg) for the LOCAL rows.
  *   part [4] fp64: <C,pi> over the local rows, their mass, max_i |sum_j pi_ij - a_i|, local max_j |col_partial_j - b_j|
  *   row_marginal [n_local] (may be NULL), col_partial [M] = sum over the local rows of pi_ij.

@@ -369,3 +369,26 @@ extern "C" int otk_sinkhorn_points_plan(const float* x, const float* y, int64_t 
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }
+
+// ---- peer-memory exchange entry points (fused tcgen05 engine only; see sinkhorn_umma.cu) -----------------------------
+extern "C" size_t otk_sinkhorn_exchange_bytes(int world, int64_t M) { return sk_umma_exchange_bytes(world, M); }
+
+extern "C" int otk_sinkhorn_points_colstep_push(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
+                                                const float* u_local, int cost_kind, double scale, double reg, int precision,
+                                                int reuse_prepared, void* const* peer_buffers_dev, int world, int rank,
+                                                int* ctrl, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x_local && y && u_local && peer_buffers_dev && ctrl && n_local > 0 && M > 0 && dim > 0 && world >= 1 &&
+                  world <= 32 && rank >= 0 && rank < world, "colstep_push: bad arguments");
+  OTK_REQUIRE(use_fused(n_local, M, dim, cost_kind, precision), "colstep_push: shape / cost not eligible for the fused engine");
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
+  return sk_umma_colstep_push(x_local, y, n_local, M, dim, u_local, scale, reg, reuse_prepared, peer_buffers_dev, world, rank,
+                              ctrl, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int otk_lse_combine_wait(void* exchange_local, int world, int64_t M, const float* b, float* v, float* diff, int* ctrl,
+                                    otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(exchange_local && b && v && ctrl && world >= 1 && world <= 32 && M > 0, "lse_combine_wait: bad arguments");
+  return sk_combine_wait(exchange_local, world, M, b, v, diff, ctrl, as_stream(stream));
+}

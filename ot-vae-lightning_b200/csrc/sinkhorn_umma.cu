@@ -450,13 +450,22 @@ static unsigned fs_grid(int64_t n) {
   return (unsigned)(b < cap ? (b ? b : 1) : cap);
 }
 
+// Column splits of a pass.  The grid is (P blocks) x (splits) CTAs, each sweeping ceil(q tiles / splits) tiles after a fixed
+// prologue (TMEM allocation, P-block load, first Q stage: about FS_CTA_OVERHEAD_TILES tiles' worth); CTAs are dealt to the
+// SMs in waves, so the pass takes   waves(splits) x (tiles per CTA + overhead)   tile times.  Minimise that over the split
+// count: the old rule (~6 waves) left a row shard of 64 P blocks with 14 splits = 6.05 waves, i.e. a seventh, almost empty
+// wave - 27 % above the work bound; 9 splits (3.9 waves, longer CTAs) are within 9 %.
+constexpr int FS_CTA_OVERHEAD_TILES = 3;
 static int fs_splits(int64_t p_rows, int64_t q_rows) {
-  const int64_t pblocks = ceil_div(p_rows, FS_BM), qtiles = ceil_div(q_rows, FS_BN);
-  int64_t want = ceil_div((int64_t)sm_count() * 6, pblocks);       // ~6 waves of CTAs
-  if (want > qtiles) want = qtiles;
-  if (want > 32) want = 32;
-  if (want < 1) want = 1;
-  return (int)want;
+  const int64_t pblocks = ceil_div(p_rows, FS_BM), qtiles = ceil_div(q_rows, FS_BN), sms = sm_count();
+  int best = 1;
+  int64_t best_cost = INT64_MAX;
+  for (int64_t s = 1; s <= 32 && s <= qtiles; ++s) {
+    const int64_t waves = ceil_div(pblocks * s, sms);
+    const int64_t cost = waves * (ceil_div(qtiles, s) + FS_CTA_OVERHEAD_TILES);
+    if (cost < best_cost) { best_cost = cost; best = (int)s; }
+  }
+  return best;
 }
 
 struct FsSide {           // one point cloud, prepared
@@ -699,6 +708,132 @@ int sk_umma_rowstep(const float* x_local, const float* y, int64_t n_local, int64
   fs_rowstep_finish_kernel<<<fs_grid(n_local), 256, 0, st>>>(w.pm, w.pl, parts, n_local, a_local, w.X.sq, nrm_scale, u_local, diff,
                                                             w.lseX);
   count_launch(1);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Peer-memory exchange of the column partials (row-sharded multi-GPU path).  Every rank owns one exchange buffer in
+// symmetric memory, mapped into all peers (torch.distributed._symmetric_memory on the host side):
+//     float    data[2][world][2][M]     slot (iteration parity), source rank, {max (natural log), sum}, column
+//     uint32_t flag[2][world]           flag[slot][src] = iteration + 1 once src's partials of that iteration have landed
+// The column half-step finishes with ONE kernel that merges the split partials of the pass, folds the column norms in and
+// stores the result straight into every peer's buffer over NVLink (coalesced 4-byte stores, 2 x M x 4 bytes per peer),
+// then the last CTA releases the flags; the combine kernel acquires the flags of all ranks and reduces the partials it
+// finds in its own memory.  No collective call, no host involvement, and the iteration stays capturable in a CUDA graph.
+// Double buffering by iteration parity is enough: a rank can only be one iteration ahead of the slowest peer, because its
+// combine of iteration k needs every peer's push of iteration k, which follows that peer's combine of iteration k - 1.
+// ---------------------------------------------------------------------------------------------------------------------
+struct XchgView { float* data; uint32_t* flag; };
+__host__ __device__ inline size_t xchg_data_floats(int world, int64_t M) { return (size_t)2 * world * 2 * M; }
+__device__ __forceinline__ XchgView xchg_view(void* base, int world, int64_t M) {
+  float* d = static_cast<float*>(base);
+  return XchgView{d, reinterpret_cast<uint32_t*>(d + xchg_data_floats(world, M))};
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ctrl (local device ints): [0] iteration counter (advanced by the combine kernel), [1] ticket of the push kernel,
+// [2] set if a wait timed out, [3] ticket of the combine kernel
+__global__ void fs_finalize_push_kernel(const float* __restrict__ pm, const float* __restrict__ pl, int parts, int64_t M,
+                                        const float* __restrict__ sq, float nrm_scale, float* __restrict__ lse_out,
+                                        void* const* __restrict__ peers, int world, int rank, int* ctrl) {
+  const uint32_t it = (uint32_t)ctrl[0];
+  const int slot = it & 1;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
+    float m = pm[r], l = pl[r];
+    for (int p = 1; p < parts; ++p) {
+      const float m2 = pm[(int64_t)p * M + r], l2 = pl[(int64_t)p * M + r];
+      const float mm = fmaxf(m, m2);
+      l = l * ex2(m - mm) + l2 * ex2(m2 - mm);
+      m = mm;
+    }
+    lse_out[r] = m + log2f(l);                                  // partial LSE over the local rows: next call's shift
+    const float mn = m * LN2 - sq[r] * nrm_scale;               // natural log, column norm folded in
+    for (int p = 0; p < world; ++p) {
+      float* d = xchg_view(peers[p], world, M).data + ((size_t)(slot * world + rank) * 2) * M;
+      d[r] = mn;
+      d[M + r] = l;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&ctrl[1], 1);
+    if (t == (int)gridDim.x - 1) {                              // every CTA's stores are fenced: publish
+      ctrl[1] = 0;
+      __threadfence_system();
+      for (int p = 0; p < world; ++p) st_release_sys(xchg_view(peers[p], world, M).flag + slot * world + rank, it + 1);
+    }
+  }
+}
+
+__global__ void fs_combine_wait_kernel(void* xchg, int world, int64_t M, const float* __restrict__ b, float* __restrict__ v,
+                                       float* diff, int* ctrl) {
+  __shared__ float red[32];
+  const uint32_t it = (uint32_t)ctrl[0];
+  const int slot = it & 1;
+  const XchgView x = xchg_view(xchg, world, M);
+  if ((int)threadIdx.x < world) {
+    const uint32_t* f = x.flag + slot * world + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < it + 1) {
+      if (clock64() - t0 > (1ll << 32)) { ctrl[2] = 1; break; }     // ~2 s: a peer is gone - flag the error, do not hang
+    }
+  }
+  __syncthreads();
+  const float* d = x.data + (size_t)slot * world * 2 * M;
+  float acc = 0.f;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+    float mm = d[j], ss = d[M + j];
+    for (int p = 1; p < world; ++p) {
+      const float m2 = d[(size_t)p * 2 * M + j], s2 = d[(size_t)p * 2 * M + M + j];
+      if (m2 > mm) { ss = ss * __expf(mm - m2) + s2; mm = m2; } else ss += s2 * __expf(m2 - mm);
+    }
+    const float vn = logf(b[j] + 1e-8f) - (mm + logf(ss));
+    acc += fabsf(vn - v[j]);
+    v[j] = vn;
+  }
+  acc = warp_sum(acc);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0;
+    for (int w = 0; w < (int)blockDim.x / 32; ++w) t += red[w];
+    if (diff) atomicAdd(diff, t);
+    if (atomicAdd(&ctrl[3], 1) == (int)gridDim.x - 1) { ctrl[3] = 0; ctrl[0] = (int)(it + 1); }   // all CTAs have read `it`
+  }
+}
+
+size_t sk_umma_exchange_bytes(int world, int64_t M) { return xchg_data_floats(world, M) * 4 + align_up((size_t)2 * world * 4, 256); }
+
+int sk_umma_colstep_push(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* u_local,
+                         double scale, double reg, int reuse_prepared, void* const* peers_dev, int world, int rank, int* ctrl,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  FsWork w;
+  OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st, !reuse_prepared));
+  const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
+  const bool bounded = reuse_prepared >= 2;
+  float* dmax = w.diff + 16;
+  if (bounded) OTK_CUDA(cudaMemsetAsync(dmax, 0, 4, st));
+  fs_bias_kernel<<<fs_grid(n_local), 256, 0, st>>>(u_local, w.X.sq, nrm_scale, n_local, w.biasX2, bounded ? dmax : nullptr);
+  int parts = 0;
+  OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st,
+                         bounded ? w.lseY : nullptr, dmax));
+  fs_finalize_push_kernel<<<fs_grid(M), 256, 0, st>>>(w.pm, w.pl, parts, M, w.Y.sq, nrm_scale, w.lseY, peers_dev, world, rank, ctrl);
+  count_launch(1);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
+int sk_combine_wait(void* xchg, int world, int64_t M, const float* b, float* v, float* diff, int* ctrl, cudaStream_t st) {
+  fs_combine_wait_kernel<<<fs_grid(M), 256, 0, st>>>(xchg, world, M, b, v, diff, ctrl);
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }

@@ -20,4 +20,9 @@ int sk_umma_summary(const float* x_local, const float* y, int64_t n_local, int64
                     const float* b, const float* u_local, const float* v, double scale, double reg, int reuse_prepared,
                     double* part, float* row_marginal, float* col_partial, void* workspace, size_t workspace_bytes,
                     cudaStream_t st);
+size_t sk_umma_exchange_bytes(int world, int64_t M);
+int sk_umma_colstep_push(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* u_local,
+                         double scale, double reg, int reuse_prepared, void* const* peers_dev, int world, int rank, int* ctrl,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st);
+int sk_combine_wait(void* xchg, int world, int64_t M, const float* b, float* v, float* diff, int* ctrl, cudaStream_t st);
 }  // namespace otk

@@ -443,6 +443,39 @@ def colstep(x_local: Tensor, y: Tensor, u_local: Tensor, scale: float, reg: floa
     return cm, cs
 
 
+def colstep_push(x_local: Tensor, y: Tensor, u_local: Tensor, scale: float, reg: float, peers: Tensor, world: int, rank: int,
+                 ctrl: Tensor, ws: Tensor, reuse: int = 0, cost: int = N.COST_SQEUCLIDEAN, precision: int = 0) -> None:
+    """colstep + push of this rank's column partials into every peer's exchange buffer (`peers`: int64 device tensor [world] of
+    the peers' symmetric-memory mappings; `ctrl`: int32 device tensor [4], zeroed once per solver instance)."""
+    dev = x_local.device
+    n, d = x_local.shape
+    m = y.shape[0]
+    with torch.cuda.device(dev):
+        st = N.load().otk_sinkhorn_points_colstep_push(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(u_local), int(cost), float(scale),
+                                                       float(reg), int(precision), int(reuse), N.ptr(peers), int(world),
+                                                       int(rank), N.ptr(ctrl), N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_sinkhorn_points_colstep_push")
+
+
+def lse_combine_wait(xchg: Tensor, world: int, b: Tensor, v: Tensor, diff: Optional[Tensor], ctrl: Tensor) -> None:
+    """wait for every rank's partials of the current iteration in the local exchange buffer, then v = log(b + 1e-8) - LSE"""
+    dev = v.device
+    with torch.cuda.device(dev):
+        st = N.load().otk_lse_combine_wait(N.ptr(xchg), int(world), v.shape[0], N.ptr(b), N.ptr(v), N.ptr(diff), N.ptr(ctrl),
+                                           N.stream_ptr(dev))
+    N.check(st, "otk_lse_combine_wait")
+
+
+def points_fused_eligible(n: int, m: int, d: int, cost: int = N.COST_SQEUCLIDEAN, precision: int = 0) -> bool:
+    """whether `sinkhorn_points` / the half-steps run on the fused tcgen05 engine for this shape (squared-Euclidean cost,
+    d a multiple of 8 up to 128, precision 0) - the engine the peer-memory exchange is built into"""
+    return precision == 0 and cost == N.COST_SQEUCLIDEAN and 8 <= d <= 128 and d % 8 == 0 and n >= 1 and m >= 1
+
+
+def exchange_bytes(world: int, m: int) -> int:
+    return int(N.load().otk_sinkhorn_exchange_bytes(int(world), int(m)))
+
+
 def lse_combine(part_max: Tensor, part_sum: Tensor, b: Tensor, v: Tensor, diff: Optional[Tensor]) -> None:
     """v = log(b + 1e-8) - LSE over the parts; part_max / part_sum are [parts, M] views with a common row stride."""
     dev = v.device

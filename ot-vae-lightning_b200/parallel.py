@@ -77,19 +77,37 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
         # the operands (FP16 planes, norms) are prepared by the first half-step and then reused from a dedicated workspace
         plan["ws"] = (kernels.points_workspace(x_local.shape[0], m, x_local.shape[1], cost, dev)
                       if hasattr(kernels, "points_workspace") else None)
+        plan["peer"] = None
+        if world > 1 and kernels is K and dev.type == "cuda":
+            peer = _peer_exchange(world, m, dev, group)
+            # the exchange only works if EVERY rank has it (and the fused engine takes the shape): agree once
+            ok = torch.tensor([1 if (peer is not None and K.points_fused_eligible(x_local.shape[0], m, x_local.shape[1], cost, precision))
+                               else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            plan["peer"] = peer if int(ok.item()) == 1 else None
     else:
         plan["u"].zero_()
         plan["v"].zero_()
     u, v, diffs, part, gathered, ws = (plan[k] for k in ("u", "v", "diffs", "part", "gathered", "ws"))
+    peer = plan.get("peer")
+    rank = dist.get_rank(group) if world > 1 else 0
 
     def iteration(stage: int) -> None:
         """stage 0: first iteration (the half-steps prepare the operands); 1: second iteration; 2: steady state - both
         half-steps find the previous iteration's biases and partial LSEs in `ws` and run in bounded-shift mode"""
-        kernels.colstep(x_local, y, u, scale, reg, cost, precision, out=part, ws=ws, reuse=min(stage, 2) if stage else 0)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), part.view(-1), group=group)
-        diffs.zero_()
-        kernels.lse_combine(gathered[:, 0], gathered[:, 1], b, v, diffs[1:2])
+        if peer is not None:
+            # the column partials go straight into every peer's exchange buffer from the half-step's last kernel; the
+            # combine kernel waits for all ranks' flags in local memory - no collective call in the iteration
+            kernels.colstep_push(x_local, y, u, scale, reg, peer["ptrs"], world, rank, peer["ctrl"], ws,
+                                 reuse=min(stage, 2) if stage else 0, cost=cost, precision=precision)
+            diffs.zero_()
+            kernels.lse_combine_wait(peer["xchg"], world, b, v, diffs[1:2], peer["ctrl"])
+        else:
+            kernels.colstep(x_local, y, u, scale, reg, cost, precision, out=part, ws=ws, reuse=min(stage, 2) if stage else 0)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered.view(-1), part.view(-1), group=group)
+            diffs.zero_()
+            kernels.lse_combine(gathered[:, 0], gathered[:, 1], b, v, diffs[1:2])
         kernels.rowstep(x_local, y, a_local, v, u, diffs[0:1], scale, reg, cost, precision, ws=ws, reuse=max(1, min(stage, 2)))
 
     def converged() -> bool:
@@ -112,6 +130,33 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
             break
     # the plan's buffers are reused if the caller passes the plan back: hand out copies
     return dict(u_local=u.clone(), v=v.clone(), iters=done_iters, scale=scale, plan=plan)
+
+
+def _peer_exchange(world: int, m: int, dev: torch.device, group=None) -> Optional[dict]:
+    """Symmetric-memory exchange buffer of the fused column-partial exchange (otk_sinkhorn_points_colstep_push /
+    otk_lse_combine_wait): allocated with torch's symmetric-memory allocator, mapped into every peer of the node by the
+    rendezvous.  None if that is unavailable (other engines, OTK_SINKHORN_PEER=0, no P2P): the NCCL all-gather is used."""
+    if os.environ.get("OTK_SINKHORN_PEER", "1") == "0":
+        return None
+    try:
+        import torch.distributed._symmetric_memory as symm
+        nbytes = kernels_exchange_bytes(world, m)
+        xchg = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(xchg, dist.group.WORLD if group is None else group)
+        xchg.zero_()
+        ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        ctrl = torch.zeros(8, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        hdl.barrier()                   # every rank's flags are zero before anyone pushes
+        return dict(xchg=xchg, hdl=hdl, ptrs=ptrs, ctrl=ctrl)
+    except Exception as e:  # noqa: BLE001 - an optimisation: the collective path is always valid
+        import warnings
+        warnings.warn(f"sharded_sinkhorn: peer-memory exchange unavailable ({type(e).__name__}: {e}); using all_gather")
+        return None
+
+
+def kernels_exchange_bytes(world: int, m: int) -> int:
+    return K.exchange_bytes(world, m)
 
 
 def sharded_summary(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, u_local: Tensor, v: Tensor, scale: float,
