@@ -245,6 +245,18 @@ int otk_sinkhorn_points_colstep_push(const float* x_local, const float* y, int64
 int otk_lse_combine_wait(void* exchange_local, int world, int64_t M, const float* b, float* v,
                          float* diff /* += sum|dv| */, int* ctrl, otk_stream_t stream);
 
+/* One whole row-sharded Sinkhorn iteration (v-step with the peer-memory exchange, then u-step on the local rows) in five
+ * launches: column pass -> finalize + push -> wait + combine -> row pass -> finish; each finishing kernel also produces the
+ * operand bias, the bounded-shift bound and the partial log-sum-exps of the next pass.  `stage` 0 = first iteration of a
+ * solve (u_local / v hold the initial potentials, the workspace is prepared), >= 1 = steady state (bounded-shift mode).
+ * diffs [2] (device, may be NULL): {sum |du| over the local rows, sum |dv|} of this iteration.  Same exchange buffer /
+ * ctrl contract as otk_sinkhorn_points_colstep_push; the dedicated workspace must not be touched between iterations. */
+int otk_sinkhorn_points_sharded_step(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
+                                     const float* a_local, const float* b, float* u_local, float* v, int cost_kind,
+                                     double scale, double reg, int precision, int stage, void* const* peer_buffers_dev,
+                                     int world, int rank, void* exchange_local, int* ctrl, float* diffs, void* workspace,
+                                     size_t workspace_bytes, otk_stream_t stream);
+
 /* Plan statistics of a row shard without the plan: pi_ij = exp(u_i + v_j - scale*cost(x_i, y_j)/reg) for the LOCAL rows.
  *   part [4] fp64: <C,pi> over the local rows, their mass, max_i |sum_j pi_ij - a_i|, local max_j |col_partial_j - b_j|
  *   row_marginal [n_local] (may be NULL), col_partial [M] = sum over the local rows of pi_ij.

@@ -71,6 +71,8 @@ SIGNATURES = {
     "otk_sinkhorn_exchange_bytes": (_sz, [_int, _i64]),
     "otk_sinkhorn_points_colstep_push": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _int, _dbl, _dbl, _int, _int, _ptr, _int, _int,
                                                 _ptr, _ptr, _sz, _ptr]),
+    "otk_sinkhorn_points_sharded_step": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _int, _dbl, _dbl, _int, _int,
+                                                _ptr, _int, _int, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "otk_lse_combine_wait": (_int, [_ptr, _int, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "otk_cost_max": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _ptr, _sz, _ptr]),
     "otk_cost_matrix": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _dbl, _ptr, _ptr, _sz, _ptr]),

@@ -392,3 +392,19 @@ extern "C" int otk_lse_combine_wait(void* exchange_local, int world, int64_t M, 
   OTK_REQUIRE(exchange_local && b && v && ctrl && world >= 1 && world <= 32 && M > 0, "lse_combine_wait: bad arguments");
   return sk_combine_wait(exchange_local, world, M, b, v, diff, ctrl, as_stream(stream));
 }
+
+extern "C" int otk_sinkhorn_points_sharded_step(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim,
+                                                const float* a_local, const float* b, float* u_local, float* v, int cost_kind,
+                                                double scale, double reg, int precision, int stage,
+                                                void* const* peer_buffers_dev, int world, int rank, void* exchange_local,
+                                                int* ctrl, float* diffs, void* workspace, size_t workspace_bytes,
+                                                otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(x_local && y && a_local && b && u_local && v && peer_buffers_dev && exchange_local && ctrl && n_local > 0 &&
+                  M > 0 && dim > 0 && world >= 1 && world <= 32 && rank >= 0 && rank < world && stage >= 0,
+              "sharded_step: bad arguments");
+  OTK_REQUIRE(use_fused(n_local, M, dim, cost_kind, precision), "sharded_step: shape / cost not eligible for the fused engine");
+  if (!workspace || workspace_bytes < otk_sinkhorn_points_workspace_bytes(n_local, M, dim, cost_kind)) return OTK_ERR_WORKSPACE;
+  return sk_umma_sharded_step(x_local, y, n_local, M, dim, a_local, b, u_local, v, scale, reg, stage, peer_buffers_dev, world,
+                              rank, exchange_local, ctrl, diffs, workspace, workspace_bytes, as_stream(stream));
+}

@@ -838,6 +838,156 @@ int sk_combine_wait(void* xchg, int world, int64_t M, const float* b, float* v, 
   return OTK_OK;
 }
 
+// ---- one whole row-sharded iteration in five launches (peer-memory exchange inside) ------------------------------------
+// Every kernel that finishes a half-step also produces what the NEXT pass needs - its operand bias, the bound max |delta
+// bias| of the bounded-shift mode, the partial log-sum-exps - so the iteration is
+//     pass (columns x local rows) -> finalize + push -> wait + combine -> pass (local rows x columns) -> finish
+// with no memset / bias / fold launches in between.  Slots: diff[16] = max |delta bias X| (written by `finish`, read by the
+// column pass, cleared by `combine`), diff[18] = max |delta bias Y| (written by `combine`, read by the row pass, cleared by
+// `finish`); `diffs` = {sum |du| (local rows), sum |dv|}, cleared by `push`.
+__global__ void fs_push_step_kernel(const float* __restrict__ pm, const float* __restrict__ pl, int parts, int64_t M,
+                                    const float* __restrict__ sq, float nrm_scale, float* __restrict__ lse_out,
+                                    void* const* __restrict__ peers, int world, int rank, int* ctrl, float* diffs) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && diffs) { diffs[0] = 0.f; diffs[1] = 0.f; }
+  const uint32_t it = (uint32_t)ctrl[0];
+  const int slot = it & 1;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
+    float m = pm[r], l = pl[r];
+    for (int p = 1; p < parts; ++p) {
+      const float m2 = pm[(int64_t)p * M + r], l2 = pl[(int64_t)p * M + r];
+      const float mm = fmaxf(m, m2);
+      l = l * ex2(m - mm) + l2 * ex2(m2 - mm);
+      m = mm;
+    }
+    lse_out[r] = m + log2f(l);
+    const float mn = m * LN2 - sq[r] * nrm_scale;
+    for (int p = 0; p < world; ++p) {
+      float* d = xchg_view(peers[p], world, M).data + ((size_t)(slot * world + rank) * 2) * M;
+      d[r] = mn;
+      d[M + r] = l;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&ctrl[1], 1);
+    if (t == (int)gridDim.x - 1) {
+      ctrl[1] = 0;
+      __threadfence_system();
+      for (int p = 0; p < world; ++p) st_release_sys(xchg_view(peers[p], world, M).flag + slot * world + rank, it + 1);
+    }
+  }
+}
+
+__global__ void fs_combine_step_kernel(void* xchg, int world, int64_t M, const float* __restrict__ b, float* __restrict__ v,
+                                       float* diffs, int* ctrl, const float* __restrict__ sq, float nrm_scale,
+                                       float* __restrict__ bias2, float* dmax_y, float* dmax_x_clear) {
+  __shared__ float red[32];
+  const uint32_t it = (uint32_t)ctrl[0];
+  const int slot = it & 1;
+  const XchgView x = xchg_view(xchg, world, M);
+  if (blockIdx.x == 0 && threadIdx.x == 32) *dmax_x_clear = 0.f;       // the column pass has consumed it
+  if ((int)threadIdx.x < world) {
+    const uint32_t* f = x.flag + slot * world + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < it + 1) {
+      if (clock64() - t0 > (1ll << 32)) { ctrl[2] = 1; break; }
+    }
+  }
+  __syncthreads();
+  const float* d = x.data + (size_t)slot * world * 2 * M;
+  float acc = 0.f, dmx = 0.f;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+    float mm = d[j], ss = d[M + j];
+    for (int p = 1; p < world; ++p) {
+      const float m2 = d[(size_t)p * 2 * M + j], s2 = d[(size_t)p * 2 * M + M + j];
+      if (m2 > mm) { ss = ss * __expf(mm - m2) + s2; mm = m2; } else ss += s2 * __expf(m2 - mm);
+    }
+    const float vn = logf(b[j] + 1e-8f) - (mm + logf(ss));
+    acc += fabsf(vn - v[j]);
+    v[j] = vn;
+    const float nb = (vn - sq[j] * nrm_scale) * LOG2E;                  // operand bias of the row pass
+    dmx = fmaxf(dmx, fabsf(nb - bias2[j]));
+    bias2[j] = nb;
+  }
+  dmx = warp_max(dmx);
+  if (threadIdx.x % 32 == 0 && dmx == dmx) atomicMax(reinterpret_cast<unsigned*>(dmax_y), __float_as_uint(dmx));
+  acc = warp_sum(acc);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0;
+    for (int w = 0; w < (int)blockDim.x / 32; ++w) t += red[w];
+    if (diffs) atomicAdd(&diffs[1], t);
+    if (atomicAdd(&ctrl[3], 1) == (int)gridDim.x - 1) { ctrl[3] = 0; ctrl[0] = (int)(it + 1); }
+  }
+}
+
+__global__ void fs_finish_step_kernel(const float* __restrict__ pm, const float* __restrict__ pl, int parts, int64_t n,
+                                      const float* __restrict__ marg, const float* __restrict__ sq, float nrm_scale,
+                                      float* __restrict__ pot, float* diffs, float* __restrict__ lse_out,
+                                      float* __restrict__ bias2, float* dmax_x, float* dmax_y_clear) {
+  __shared__ float red[32];
+  if (blockIdx.x == 0 && threadIdx.x == 32) *dmax_y_clear = 0.f;       // the row pass has consumed it
+  float acc = 0.f, dmx = 0.f;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    float m = pm[r], l = pl[r];
+    for (int p = 1; p < parts; ++p) {
+      const float m2 = pm[(int64_t)p * n + r], l2 = pl[(int64_t)p * n + r];
+      const float mm = fmaxf(m, m2);
+      l = l * ex2(m - mm) + l2 * ex2(m2 - mm);
+      m = mm;
+    }
+    const float lse2 = m + log2f(l);
+    const float bnat = logf(marg[r] + 1e-8f) - lse2 * LN2;
+    const float pn = bnat + sq[r] * nrm_scale;
+    acc += fabsf(pn - pot[r]);
+    pot[r] = pn;
+    lse_out[r] = lse2;
+    const float nb = bnat * LOG2E;                                      // operand bias of the next column pass
+    dmx = fmaxf(dmx, fabsf(nb - bias2[r]));
+    bias2[r] = nb;
+  }
+  dmx = warp_max(dmx);
+  if (threadIdx.x % 32 == 0) atomicMax(reinterpret_cast<unsigned*>(dmax_x), __float_as_uint(dmx));
+  acc = warp_sum(acc);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && diffs) { float t = 0; for (int w = 0; w < (int)blockDim.x / 32; ++w) t += red[w]; atomicAdd(&diffs[0], t); }
+}
+
+// stage 0: first iteration of a solve (prepares the operands, bias of the rows from u_local); stage >= 1: steady state
+int sk_umma_sharded_step(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* a_local,
+                         const float* b, float* u_local, float* v, double scale, double reg, int stage, void* const* peers_dev,
+                         int world, int rank, void* xchg_local, int* ctrl, float* diffs, void* workspace, size_t workspace_bytes,
+                         cudaStream_t st) {
+  FsWork w;
+  OTK_TRY(fs_carve(w, x_local, y, n_local, M, dim, workspace, workspace_bytes, st, stage == 0));
+  const float nrm_scale = (float)(scale / reg), g2 = (float)(2.0 * scale / reg) * LOG2E;
+  float *dmax_x = w.diff + 16, *dmax_y = w.diff + 18;
+  if (stage == 0) {
+    OTK_CUDA(cudaMemsetAsync(w.diff, 0, 64 * sizeof(float), st));
+    OTK_CUDA(cudaMemsetAsync(w.biasY2, 0, (size_t)M * 4, st));
+    fs_bias_kernel<<<fs_grid(n_local), 256, 0, st>>>(u_local, w.X.sq, nrm_scale, n_local, w.biasX2);
+    OTK_LAUNCH_CHECK();
+  }
+  const bool bounded = stage >= 1;
+  int parts = 0;
+  OTK_TRY(fs_pass<false>(w.Y, w.X, w.biasX2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st,
+                         bounded ? w.lseY : nullptr, dmax_x));
+  fs_push_step_kernel<<<fs_grid(M), 256, 0, st>>>(w.pm, w.pl, parts, M, w.Y.sq, nrm_scale, w.lseY, peers_dev, world, rank, ctrl, diffs);
+  fs_combine_step_kernel<<<fs_grid(M), 256, 0, st>>>(xchg_local, world, M, b, v, diffs, ctrl, w.Y.sq, nrm_scale, w.biasY2, dmax_y,
+                                                    dmax_x);
+  count_launch(1);
+  OTK_LAUNCH_CHECK();
+  OTK_TRY(fs_pass<false>(w.X, w.Y, w.biasY2, g2, w.sig + 1, dim, w.pm, w.pl, w.pc, nullptr, &parts, st,
+                         bounded ? w.lseX : nullptr, dmax_y));
+  fs_finish_step_kernel<<<fs_grid(n_local), 256, 0, st>>>(w.pm, w.pl, parts, n_local, a_local, w.X.sq, nrm_scale, u_local, diffs,
+                                                         w.lseX, w.biasX2, dmax_x, dmax_y);
+  OTK_LAUNCH_CHECK();
+  return OTK_OK;
+}
+
 // Plan statistics of a row shard (x_local, u_local) against the replicated (y, v), on the prepared operands:
 //   part[0] += <C, pi> over the local rows, part[1] += their mass, part[2] = max_i |sum_j pi_ij - a_i|  (local rows are
 //   complete: y is replicated), row_marginal[n_local], and col_partial[M] = sum over the LOCAL rows of pi_ij - the caller

@@ -25,4 +25,8 @@ int sk_umma_colstep_push(const float* x_local, const float* y, int64_t n_local, 
                          double scale, double reg, int reuse_prepared, void* const* peers_dev, int world, int rank, int* ctrl,
                          void* workspace, size_t workspace_bytes, cudaStream_t st);
 int sk_combine_wait(void* xchg, int world, int64_t M, const float* b, float* v, float* diff, int* ctrl, cudaStream_t st);
+int sk_umma_sharded_step(const float* x_local, const float* y, int64_t n_local, int64_t M, int64_t dim, const float* a_local,
+                         const float* b, float* u_local, float* v, double scale, double reg, int stage, void* const* peers_dev,
+                         int world, int rank, void* xchg_local, int* ctrl, float* diffs, void* workspace, size_t workspace_bytes,
+                         cudaStream_t st);
 }  // namespace otk

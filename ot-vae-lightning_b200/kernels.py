@@ -457,6 +457,21 @@ def colstep_push(x_local: Tensor, y: Tensor, u_local: Tensor, scale: float, reg:
     N.check(st, "otk_sinkhorn_points_colstep_push")
 
 
+def sharded_step(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, u_local: Tensor, v: Tensor, scale: float, reg: float,
+                 stage: int, peers: Tensor, world: int, rank: int, xchg: Tensor, ctrl: Tensor, diffs: Optional[Tensor], ws: Tensor,
+                 cost: int = N.COST_SQEUCLIDEAN, precision: int = 0) -> None:
+    """one whole row-sharded iteration (otk_sinkhorn_points_sharded_step): five launches, exchange over peer memory"""
+    dev = x_local.device
+    n, d = x_local.shape
+    m = y.shape[0]
+    with torch.cuda.device(dev):
+        st = N.load().otk_sinkhorn_points_sharded_step(N.ptr(x_local), N.ptr(y), n, m, d, N.ptr(a_local), N.ptr(b), N.ptr(u_local),
+                                                       N.ptr(v), int(cost), float(scale), float(reg), int(precision), int(stage),
+                                                       N.ptr(peers), int(world), int(rank), N.ptr(xchg), N.ptr(ctrl), N.ptr(diffs),
+                                                       N.ptr(ws), ws.numel(), N.stream_ptr(dev))
+    N.check(st, "otk_sinkhorn_points_sharded_step")
+
+
 def lse_combine_wait(xchg: Tensor, world: int, b: Tensor, v: Tensor, diff: Optional[Tensor], ctrl: Tensor) -> None:
     """wait for every rank's partials of the current iteration in the local exchange buffer, then v = log(b + 1e-8) - LSE"""
     dev = v.device

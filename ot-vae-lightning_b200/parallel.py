@@ -78,13 +78,19 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
         plan["ws"] = (kernels.points_workspace(x_local.shape[0], m, x_local.shape[1], cost, dev)
                       if hasattr(kernels, "points_workspace") else None)
         plan["peer"] = None
-        if world > 1 and kernels is K and dev.type == "cuda":
-            peer = _peer_exchange(world, m, dev, group)
-            # the exchange only works if EVERY rank has it (and the fused engine takes the shape): agree once
-            ok = torch.tensor([1 if (peer is not None and K.points_fused_eligible(x_local.shape[0], m, x_local.shape[1], cost, precision))
-                               else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            plan["peer"] = peer if int(ok.item()) == 1 else None
+        if kernels is K and dev.type == "cuda":
+            fused = K.points_fused_eligible(x_local.shape[0], m, x_local.shape[1], cost, precision)
+            if world > 1:
+                peer = _peer_exchange(world, m, dev, group)
+                # the exchange only works if EVERY rank has it (and the fused engine takes the shape): agree once
+                ok = torch.tensor([1 if (peer is not None and fused) else 0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                plan["peer"] = peer if int(ok.item()) == 1 else None
+            elif fused and os.environ.get("OTK_SINKHORN_PEER", "1") != "0":
+                # one rank: the same five-launch iteration with the "exchange" buffer in local memory
+                xchg = torch.zeros(K.exchange_bytes(1, m), dtype=torch.uint8, device=dev)
+                plan["peer"] = dict(xchg=xchg, hdl=None, ptrs=torch.tensor([xchg.data_ptr()], dtype=torch.int64, device=dev),
+                                    ctrl=torch.zeros(8, dtype=torch.int32, device=dev))
     else:
         plan["u"].zero_()
         plan["v"].zero_()
@@ -96,12 +102,11 @@ def sharded_sinkhorn(x_local: Tensor, y: Tensor, a_local: Tensor, b: Tensor, reg
         """stage 0: first iteration (the half-steps prepare the operands); 1: second iteration; 2: steady state - both
         half-steps find the previous iteration's biases and partial LSEs in `ws` and run in bounded-shift mode"""
         if peer is not None:
-            # the column partials go straight into every peer's exchange buffer from the half-step's last kernel; the
-            # combine kernel waits for all ranks' flags in local memory - no collective call in the iteration
-            kernels.colstep_push(x_local, y, u, scale, reg, peer["ptrs"], world, rank, peer["ctrl"], ws,
-                                 reuse=min(stage, 2) if stage else 0, cost=cost, precision=precision)
-            diffs.zero_()
-            kernels.lse_combine_wait(peer["xchg"], world, b, v, diffs[1:2], peer["ctrl"])
+            # the whole iteration in five launches: the column partials go straight into every peer's exchange buffer from
+            # the half-step's last kernel, the combine kernel waits for all ranks' flags in local memory - no collective
+            kernels.sharded_step(x_local, y, a_local, b, u, v, scale, reg, min(stage, 1), peer["ptrs"], world, rank,
+                                 peer["xchg"], peer["ctrl"], diffs, ws, cost=cost, precision=precision)
+            return
         else:
             kernels.colstep(x_local, y, u, scale, reg, cost, precision, out=part, ws=ws, reuse=min(stage, 2) if stage else 0)
             if world > 1:

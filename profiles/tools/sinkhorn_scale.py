@@ -54,7 +54,10 @@ for _ in range(3):
     best = min(best, float(t))
 chk = parallel.sharded_summary(xl, y, al, a, out["u_local"], out["v"], scale, EPS)
 if rank == 0:
-    print(f"n_gpus={world} iters/s={ITERS / (best * 1e-3):.1f} ms/iter={best / ITERS:.4f} check={chk}", flush=True)
+    peer = state["plan"].get("peer")
+    how = "peer-memory exchange" if peer is not None else ("NCCL all-gather" if world > 1 else "single GPU")
+    tmo = int(peer["ctrl"][2]) if peer is not None else 0
+    print(f"n_gpus={world} iters/s={ITERS / (best * 1e-3):.1f} ms/iter={best / ITERS:.4f} exchange={how} timeouts={tmo} check={chk}", flush=True)
 state.clear()
 del out
 import gc  # noqa: E402
