@@ -302,6 +302,19 @@ def main():
     lib = NV.load()
     peaks = load_peaks()
 
+    def probe_peak(kind):
+        import ctypes
+        out = ctypes.c_double(0.0)
+        st = lib.otk_microbench_peak(kind, ctypes.byref(out), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        return float(out.value) if st == 0 else None
+
+    # denominators MEASURED_PEAKS.json does not hold ("builder must measure"), measured on this GPU now
+    peaks_measured = dict(tf32_tflops=probe_peak(0), f16_tflops=probe_peak(1), mufu_ex2_tera_per_s=probe_peak(2),
+                          how="otk_microbench_peak: tcgen05 kind::tf32 / kind::f16 with CTA pairs (M = N = 256) on operands "
+                              "resident in shared / tensor memory (issue-bound ceiling of the MMA pipe, no loads); "
+                              "ex2.approx.ftz.f32, 8 independent chains per thread, 8 CTAs x 256 threads per SM; best of 3 "
+                              "launches, CUDA events")
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -403,6 +416,10 @@ def main():
                          f"(profiles/prof_stats_r04.md): FP16 tensor ops 53 % of the nominal peak at the 1.64 GHz the "
                          f"kernel runs at, i.e. 76 % of the measured sustained peak in executed flops; traffic = dram "
                          f"read+write bytes per launch from the same capture (algorithmic: {CHUNK * D_LAT * 4})",
+                    vs_measured_f16_peak=dict(peak=peaks_measured.get("f16_tflops"),
+                                              executed_frac=(3.0 * tri * stats_tflops / peaks_measured["f16_tflops"]) if peaks_measured.get("f16_tflops") else None,
+                                              note="executed FP16 MMA flops against the tcgen05 kind::f16 ceiling measured by "
+                                                   "otk_microbench_peak on this GPU"),
                     others=dict(apply_transport_tflops=apply_tflops, apply_frac=apply_tflops / f16_peak,
                                 apply_executed_frac=3.0 * apply_tflops / f16_peak,
                                 compute_map_ms=compute_ms / 3, stats_ms=stats_ms / 3, apply_ms=apply_ms / 3,
@@ -475,9 +492,10 @@ def main():
         step()
         ms, _ = timed(step, reps)
         u_ms, _ = timed(upd, reps)
-        c_ms, _ = timed(lambda: op_.compute(), reps)
+        c_reps = max(reps, 10)
+        c_ms, _ = timed(lambda: op_.compute(), c_reps)
         t_ms, _ = timed(mov, reps)
-        return dict(ms_per_step=ms / reps, update_ms=u_ms / reps, compute_ms=c_ms / reps, transport_ms=t_ms / reps)
+        return dict(ms_per_step=ms / reps, update_ms=u_ms / reps, compute_ms=c_ms / c_reps, transport_ms=t_ms / reps)
 
     # ---- cfg1: the reference's own operating point (README.md:54-57, tests/test_latent_transport.py:66-98):
     # 10 000 latents of width 128 in batches of 250 -> 40 update calls per model, compute(), 40 transport calls
@@ -621,6 +639,8 @@ def main():
             sk_clocks = sampler.result()
             it_s = iters / (sk_ms * 1e-3)
             alg_gb = 2.0 * SK_N * SK_N * 4 / 1e9
+            mufu_peak = peaks_measured.get("mufu_ex2_tera_per_s") or (148 * 16 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12)
+            mufu_src = "measured (otk_microbench_peak)" if peaks_measured.get("mufu_ex2_tera_per_s") else "148 SMs x 16/clk x max clock (estimate)"
             # correctness of what was timed: plan statistics WITHOUT the plan, on every rank count (the sharded rows'
             # <C,pi>, mass and column partials are summed with one all-reduce; same problem, so the numbers must agree
             # across n_gpus to the solver's accuracy)
@@ -644,11 +664,10 @@ def main():
                                                "materialises the cost, so frac > 1; measured dram traffic per pass "
                                                "launch: 34 MB (profiles/prof_sinkhorn_r02.md)",
                                           binding=dict(bound="mufu", achieved=2.0 * SK_N * SK_N * it_s / 1e12,
-                                                       frac=2.0 * SK_N * SK_N * it_s / (world * 148 * 16 * (clocks.get("sm_max_mhz") or 1965) * 1e6),
-                                                       peak=world * 148 * 16 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12,
-                                                       unit="T ex2/s",
-                                                       note="2*N*M exponentials per iteration on the 16/clk/SM MUFU pipe at "
-                                                            "the maximum SM clock; ncu: XU pipe 79 % active"),
+                                                       frac=2.0 * SK_N * SK_N * it_s / 1e12 / (world * mufu_peak),
+                                                       peak=world * mufu_peak, unit="T ex2/s", peak_source=mufu_src,
+                                                       note="2*N*M exponentials per iteration against the MUFU.EX2 rate "
+                                                            "measured on this GPU (peaks_measured); ncu: XU pipe 79 % active"),
                                           tensor=dict(achieved=4.0 * SK_N * SK_N * SK_D * it_s / 1e12 / world,
                                                       peak=peaks["bf16_sustained"], unit="TFLOP/s per GPU",
                                                       note="executed FP16 MMA flops 2 passes x 2*N*M*d")))
@@ -709,7 +728,7 @@ def main():
                                     sinkhorn="FP16 operand planes (TF32-size mantissa), fp32 accumulation and softmax"),
                     check=dict(w2=float(w2)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
-                    d128=d128, cfg1=cfg1, cfg4=cfg4, cfg5=cfg5, sinkhorn=sinkhorn)
+                    peaks_measured=peaks_measured, d128=d128, cfg1=cfg1, cfg4=cfg4, cfg5=cfg5, sinkhorn=sinkhorn)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
