@@ -478,12 +478,13 @@ static void pick_tile(int64_t M, int64_t N, int64_t K, int64_t batch, int n_prob
   // 9e-7 instead of 3.6e-6 at K = 512), so it stays available: OTK_GEMM_SPLITK=1.
   static const bool split_ok = [] { const char* e = getenv("OTK_GEMM_SPLITK"); return e && e[0] == '1'; }();
   const int64_t sms = sm_count(), num_k = ceil_div(K, UG_BK);
-  // Long contractions: tensor memory accumulates with truncation (relative error ~6e-8 per K = 8 step), so at K >= 2048 the
+  // Long contractions: tensor memory accumulates with truncation (relative error ~6e-8 per K = 8 step), so at K >= 4096 the
   // K loop is cut over a cluster of 4 CTAs whose partial tiles are added in fp32 registers (round to nearest) through
   // distributed shared memory - chains of K / 4.  Measured on the d = 4096 map: error against the fp64 engine 1.6e-3
-  // un-split (outside the 1e-3 budget, so the whole call used to be redone in fp64: 1.9 s).
+  // un-split (outside the 1e-3 budget, so the whole call was redone in fp64: 1.9 s) and 4.4e-4 split (89 ms).  At
+  // K = 2048 the un-split product is accurate enough (4.1e-4) and twice as fast (7.5 vs 14 ms per map), so it stays whole.
   static const bool long_k_split = [] { const char* e = getenv("OTK_GEMM_LONGK_SPLIT"); return !(e && e[0] == '0'); }();
-  if (long_k_split && K >= 2048 && M >= UG_BM && N >= 128) { *bn_out = 128; *ks_out = 4; return; }
+  if (long_k_split && K >= 4096 && M >= UG_BM && N >= 128) { *bn_out = 128; *ks_out = 4; return; }
   int best_bn = 128, best_ks = 1;
   int64_t best_cost = INT64_MAX;
   for (int bn : {128, 64}) {
