@@ -127,11 +127,21 @@ class GaussianMixtureModel(GaussianModel, CodebookModel):
         return weights_sum, weighted_sum, self._weighted_syrk(samples, weights)
 
     def _weighted_syrk(self, samples: Tensor, weights: Tensor) -> Tensor:
-        """P[*L, k] = sum_b w_bk x_b x_b^T through the statistics kernel: for every (leading index, component) the rows
-        with a non-zero weight are gathered, scaled by sqrt(w) and streamed through otk_stats_update."""
+        """P[*L, k] = sum_b w_bk x_b x_b^T through the statistics kernel (a SYRK of the rows scaled by sqrt(w))."""
         self._require_cuda_buffers()
         lead, k, d = weights.shape[:-2], weights.size(-1), samples.size(-1)
-        out = torch.zeros(*lead, k, d, d, dtype=self._running_sum_cov.dtype, device=self._running_sum_cov.device)
+        b = samples.size(-2)
+        if k * b * d * max(1, int(torch.Size(lead).numel())) * 4 <= (1 << 30):
+            # ONE batched launch: component k of leading index l is "leading index (l, k)" of the statistics kernel, fed with
+            # the batch scaled by sqrt(w_bk) (rows a component does not own are zero) - no per-component Python loop, no
+            # host read-back of the assignment pattern
+            scaled = (weights.transpose(-1, -2).sqrt().unsqueeze(-1) * samples.expand(*lead, b, d).unsqueeze(-3)).float()
+            out = torch.zeros(*lead, k, d, d, dtype=self._running_sum_cov.dtype, device=self._running_sum_cov.device)
+            n = torch.zeros(*lead, k, dtype=torch.float64, device=out.device)
+            s = torch.zeros(*lead, k, d, dtype=out.dtype, device=out.device)
+            K.stats_update(scaled.contiguous(), n, s, out, None)
+            return out
+        # very large batches: gather the rows of each component instead of materialising the K scaled copies
         x2 = samples.expand(*lead, *samples.shape[-2:]).reshape(-1, samples.size(-2), d)
         w2 = weights.reshape(-1, weights.size(-2), k)
         flat = out.view(-1, k, d, d)
