@@ -599,6 +599,7 @@ def main():
         e2e_ms /= max(1, min(args.steps, 3))
         e2e = dict(value=world * N_LAT / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=3 * N_LAT * D_LAT * 4,
                    d2h_bytes_per_step=N_LAT * D_LAT * 4, ms_per_step=e2e_ms,
+                   host_device_gbs_aggregate=world * 4 * N_LAT * D_LAT * 4 / (e2e_ms * 1e-3) / 1e9,
                    note="pinned host latents -> update(src,tgt) -> compute -> transport(src) -> pinned host result; copies "
                         "double-buffered on side streams (streaming.py); PCIe-bound")
         del h_src, h_tgt, h_out

@@ -197,6 +197,14 @@ class on_device:
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
+def workspace_for(device_index: int, stream: int, nbytes: int, device: torch.device) -> torch.Tensor:
+    """`workspace` for callers that already hold the device index and the raw stream handle"""
+    buf = _workspaces.get((device_index, stream))
+    if buf is None or buf.numel() < nbytes:
+        _workspaces[(device_index, stream)] = buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+    return buf
+
+
 def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     """Per-(device, stream) scratch buffer handed to libotk (which never allocates)."""
     idx = device.index if device.index is not None else torch.cuda.current_device()

@@ -87,6 +87,40 @@ def stats_update(x: Tensor, n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, dec
         N.check(st, "otk_stats_update")
 
 
+class StatsUpdatePlan:
+    """`stats_update` for one model with everything that does not change between batches bound once (buffer pointers,
+    dtype codes, the library entry): the call that remains is a handful of checks on the batch and one ctypes call."""
+
+    __slots__ = ("dev", "dev_index", "d", "decay", "n_ptr", "n_code", "s_ptr", "c_ptr", "b_code", "entry", "ws_query")
+
+    def __init__(self, n_obs: Tensor, run_sum: Tensor, run_cov: Tensor, decay: Optional[float]):
+        lib = N.load()
+        self.dev, self.d = run_sum.device, run_sum.shape[-1]
+        self.dev_index = run_sum.device.index if run_sum.device.index is not None else torch.cuda.current_device()
+        self.decay = -1.0 if decay is None else float(decay)
+        self.n_ptr, self.n_code = n_obs.data_ptr(), N.dtype_code(n_obs.dtype)
+        self.s_ptr, self.c_ptr, self.b_code = run_sum.data_ptr(), run_cov.data_ptr(), N.dtype_code(run_sum.dtype)
+        self.entry, self.ws_query = lib.otk_stats_update, lib.otk_stats_update_workspace_bytes
+
+    def __call__(self, x: Tensor) -> bool:
+        d = self.d
+        if x.dtype != torch.float32 or x.device != self.dev or x.shape[1] != d or not x.is_contiguous() or x.requires_grad \
+                or x.shape[0] == 0 or x.data_ptr() % 16 or torch.cuda.current_device() != self.dev_index:
+            return False
+        rows = x.shape[0]
+        key = (1, rows, d)
+        need = _stats_ws_bytes.get(key)
+        if need is None:
+            need = _stats_ws_bytes[key] = self.ws_query(1, rows, d)
+        stream = N.raw_stream(self.dev_index)
+        ws = N.workspace_for(self.dev_index, stream, need, self.dev)
+        st = self.entry(x.data_ptr(), 1, rows, d, d, rows * d, self.decay, self.n_ptr, self.n_code, self.s_ptr, self.c_ptr,
+                        self.b_code, ws.data_ptr(), ws.numel(), stream)
+        if st != N.OK:
+            N.check(st, "otk_stats_update")
+        return True
+
+
 def mean_cov(run_sum: Tensor, run_cov: Tensor, n_obs: Tensor) -> Tuple[Tensor, Tensor]:
     dev = N.compute_device(run_sum)
     dt = run_sum.dtype if run_sum.dtype in (torch.float32, torch.float64) else torch.float32
