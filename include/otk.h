@@ -276,8 +276,11 @@ int otk_sinkhorn_points_plan(const float* x, const float* y, int64_t N, int64_t 
 /* max_ij cost(x_i, y_j) -> *out (device fp32), for the 1/max normalisation */
 int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
                  float* out, void* workspace, size_t workspace_bytes, otk_stream_t stream);
-/* materialise scale*cost(x_i,y_j) -> C [N,M] fp32 (CodebookModel.energy, codebook_model.py:155-160);
- * workspace >= (N+M)*4 + 512 bytes (same for otk_cost_max) */
+/* materialise scale*cost(x_i,y_j) -> C [N,M] fp32 (CodebookModel.energy, codebook_model.py:155-160; the `cdist`
+ * contraction).  workspace >= (N+M)*4 + 512 bytes runs the 64x64 FFMA tile kernel; with otk_cost_workspace_bytes(N, M, dim)
+ * (room for the TF32 hi/lo planes of both clouds) problems of >= 2^20 entries with dim % 4 == 0, M % 4 == 0 run the
+ * contraction on tcgen05 (3xTF32) and finish the cost in one elementwise pass.  (otk_cost_max: (N+M)*4 + 512 bytes) */
+size_t otk_cost_workspace_bytes(int64_t N, int64_t M, int64_t dim);
 int otk_cost_matrix(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind,
                     double scale, float* C, void* workspace, size_t workspace_bytes, otk_stream_t stream);
 

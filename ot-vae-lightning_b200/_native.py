@@ -75,6 +75,7 @@ SIGNATURES = {
                                                 _ptr, _int, _int, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "otk_lse_combine_wait": (_int, [_ptr, _int, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "otk_cost_max": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _ptr, _ptr, _sz, _ptr]),
+    "otk_cost_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_cost_matrix": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _dbl, _ptr, _ptr, _sz, _ptr]),
     "otk_kmeans_assign_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_kmeans_assign": (_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _int, _ptr, _sz, _ptr]),

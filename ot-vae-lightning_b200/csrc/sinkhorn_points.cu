@@ -9,6 +9,7 @@
 //     on it (any dim / cost kind).
 #include "sinkhorn_dense.cuh"
 #include "sinkhorn_umma.cuh"
+#include "gemm.cuh"
 #include <cfloat>
 
 namespace otk {
@@ -127,10 +128,47 @@ __global__ void plan_col_err_kernel(const float* colsum, const float* b, int64_t
     atomicMax(reinterpret_cast<unsigned long long*>(&summary[3]), (unsigned long long)__double_as_longlong(mx));
 }
 
+// C_ij (holding -2 x_i.y_j + |y_j|^2 from the tensor-core product) -> scale * cost
+__global__ void cost_from_gram_kernel(float* __restrict__ C, const float* __restrict__ nx, int64_t N, int64_t M, int kind,
+                                      const float* scale_dev, float scale_host) {
+  const float sc = scale_dev ? *scale_dev : scale_host;
+  const int64_t total = N * M;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const float sq = fmaxf(C[e] + nx[e / M], 0.f);
+    C[e] = (kind == OTK_COST_SQEUCLIDEAN ? sq : 1.f / (sqrtf(sq) + 1e-8f)) * sc;
+  }
+}
+
+// scratch floats the tensor-core cost producer needs (TF32 hi/lo planes of both clouds)
+static size_t cost_umma_scratch_floats(int64_t N, int64_t M, int64_t d) { return (size_t)2 * (N + M) * d; }
+static bool cost_umma_eligible(const float* x, const float* y, const float* C, int64_t N, int64_t M, int64_t d) {
+  return N >= 128 && M >= 128 && d >= 8 && d % 4 == 0 && M % 4 == 0 && N * M >= (1 << 20) &&
+         reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 &&
+         reinterpret_cast<uintptr_t>(C) % 16 == 0;
+}
+
+// The contraction of the cost (K9: x.y^T of `cdist` / CodebookModel.energy) on tcgen05 (3xTF32, fp32-accurate): the product
+// kernel's epilogue emits -2 x_i.y_j + |y_j|^2, one elementwise pass finishes the cost.  `scratch` (cost_umma_scratch_floats)
+// may be null: small or unaligned problems, or a caller without the scratch, take the FFMA tile kernel.
 static int build_cost(const float* x, const float* y, int64_t N, int64_t M, int64_t d, int kind, const float* scale_dev,
-                      float scale_host, float* nx, float* ny, float* C, cudaStream_t st) {
+                      float scale_host, float* nx, float* ny, float* C, cudaStream_t st, float* scratch = nullptr) {
   row_sqnorm_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(x, N, d, nx);
   row_sqnorm_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(y, M, d, ny);
+  if (scratch && cost_umma_eligible(x, y, C, N, M, d)) {
+    GemmArgs<float> g = nt_args(x, y, C, N, M, d, d, d, M, 0, 0, 0, -2.f, 0.f);
+    g.bias = ny;
+    g.scratch = scratch;
+    const int r = gemm_umma_try(g, 1, 3, st);
+    if (r < 0) return r;
+    if (r == 1) {
+      int64_t blocks = ceil_div(N * M, 256 * 4);
+      if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+      cost_from_gram_kernel<<<(unsigned)blocks, 256, 0, st>>>(C, nx, N, M, kind, scale_dev, scale_host);
+      count_launch(2);
+      OTK_LAUNCH_CHECK();
+      return OTK_OK;
+    }
+  }
   dim3 grid((unsigned)ceil_div(M, CT), (unsigned)ceil_div(N, CT));
   cost_tile_kernel<0><<<grid, 256, 0, st>>>(x, y, nx, ny, N, M, d, kind, scale_dev, scale_host, C, nullptr);
   count_launch(2);
@@ -168,7 +206,14 @@ extern "C" int otk_cost_matrix(const float* x, const float* y, int64_t N, int64_
   Arena ar(workspace, workspace_bytes);
   float* nx = ar.take<float>((size_t)N);
   float* ny = ar.take<float>((size_t)M);
-  return build_cost(x, y, N, M, dim, cost_kind, nullptr, (float)scale, nx, ny, C, as_stream(stream));
+  // with the larger workspace of otk_cost_workspace_bytes the contraction runs on the tensor cores
+  float* scratch = ar.take<float>(cost_umma_scratch_floats(N, M, dim));
+  if (!ar.ok()) scratch = nullptr;
+  return build_cost(x, y, N, M, dim, cost_kind, nullptr, (float)scale, nx, ny, C, as_stream(stream), scratch);
+}
+
+extern "C" size_t otk_cost_workspace_bytes(int64_t N, int64_t M, int64_t dim) {
+  return 2 * align_up((size_t)(N > M ? N : M) * 4, 256) + align_up(cost_umma_scratch_floats(N, M, dim) * 4, 256) + 1024;
 }
 
 extern "C" int otk_cost_max(const float* x, const float* y, int64_t N, int64_t M, int64_t dim, int cost_kind, float* out,

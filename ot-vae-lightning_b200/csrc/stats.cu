@@ -26,8 +26,11 @@ __global__ void __launch_bounds__(ST_THREADS)
 stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
                   int64_t chunk_rows, int n_tiles, double* __restrict__ ws_cov, double* __restrict__ ws_sum,
                   StatsRunning run) {
-  __shared__ X As[ST_BK][T + 4];
-  __shared__ X Bs[ST_BK][T + 4];
+  // rows per step: the narrow-tile variant runs on a handful of CTAs and is bound by the load -> barrier -> compute round
+  // trip of a step, so it takes 64 rows per step (16 independent loads in flight per thread) instead of 16
+  constexpr int BK = T == 32 ? 64 : ST_BK;
+  __shared__ X As[BK][T + 4];
+  __shared__ X Bs[BK][T + 4];
   // decode the upper-triangular tile pair (ti <= tj) from blockIdx.x
   int p = blockIdx.x, ti = 0;
   while (p >= n_tiles - ti) { p -= n_tiles - ti; ++ti; }
@@ -46,9 +49,9 @@ stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t ro
     for (int j = 0; j < TH; ++j) acc[i][j] = 0.0;
   double colsum = 0.0;  // threads 0..63 of a diagonal CTA own one column each
 
-  for (int64_t k0 = r0; k0 < r1; k0 += ST_BK) {
+  for (int64_t k0 = r0; k0 < r1; k0 += BK) {
 #pragma unroll
-    for (int r = 0; r < (T * ST_BK) / ST_THREADS; ++r) {
+    for (int r = 0; r < (T * BK) / ST_THREADS; ++r) {
       int e = tid + r * ST_THREADS;
       int kk = e / T, cc = e % T;
       int64_t row = k0 + kk;
@@ -59,10 +62,10 @@ stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t ro
     __syncthreads();
     if (ti == tj && tid < T) {
 #pragma unroll
-      for (int kk = 0; kk < ST_BK; ++kk) colsum += (double)As[kk][tid];
+      for (int kk = 0; kk < BK; ++kk) colsum += (double)As[kk][tid];
     }
 #pragma unroll
-    for (int kk = 0; kk < ST_BK; ++kk) {
+    for (int kk = 0; kk < BK; ++kk) {
       double a[TH], b[TH];
 #pragma unroll
       for (int i = 0; i < TH; ++i) a[i] = (double)As[kk][ty * TH + i];

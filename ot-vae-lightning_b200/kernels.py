@@ -427,7 +427,7 @@ def cost_matrix(x: Tensor, y: Tensor, cost: int, scale: float = 1.0) -> Tensor:
     m = yd.shape[0]
     out = torch.empty(n, m, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        ws = N.workspace((n + m) * 4 + 512, dev)
+        ws = N.workspace(N.load().otk_cost_workspace_bytes(n, m, d), dev)
         st = N.load().otk_cost_matrix(N.ptr(xd), N.ptr(yd), n, m, d, int(cost), float(scale), N.ptr(out), N.ptr(ws),
                                       ws.numel(), N.stream_ptr(dev))
     N.check(st, "otk_cost_matrix")

@@ -907,3 +907,19 @@ def test_native_fit_matches_the_stepwise_fit_and_skips_unseen_indices(api, monke
     raw = a.parametrizations.cov.original
     want = torch.triu(raw) + torch.triu(raw, 1).transpose(-1, -2) + 1e-8 * torch.eye(24, dtype=torch.double, device="cuda")
     assert rel(op_a, want.cpu()) < 1e-14
+
+
+@pytest.mark.parametrize("n,m,d", [(2048, 4096, 128), (1024, 1280, 72), (1500, 1024, 512)])
+def test_cost_matrix_tensor_core_contraction_vs_fp64(n, m, d):
+    """`otk_cost_matrix` at sizes where the x.y^T contraction runs on tcgen05 (3xTF32) + one elementwise pass, both cost kinds
+    (squared distance, w2_utils.py:121-125; inverse distance, codebook_model.py:155-160), against fp64."""
+    from ot_vae_lightning_b200 import kernels as K
+    g = torch.Generator().manual_seed(n + d)
+    x, y = torch.randn(n, d, generator=g), torch.randn(m, d, generator=g) * 1.2 + 0.1
+    x64, y64 = x.double(), y.double()
+    sq = (x64 * x64).sum(-1, keepdim=True) + (y64 * y64).sum(-1)[None] - 2 * x64 @ y64.T
+    got = K.cost_matrix(x.cuda(), y.cuda(), cost=0, scale=0.5)
+    assert got.shape == (n, m) and rel(got, 0.5 * sq) < 2e-6
+    assert float((got.double().cpu() - 0.5 * sq).abs().max()) < 1e-5 * float(sq.max())
+    inv = K.cost_matrix(x.cuda(), y.cuda(), cost=1)
+    assert rel(inv, 1.0 / (sq.clamp_min(0).sqrt() + 1e-8)) < 1e-5
