@@ -29,8 +29,10 @@ stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t ro
   // rows per step: the narrow-tile variant runs on a handful of CTAs and is bound by the load -> barrier -> compute round
   // trip of a step, so it takes 64 rows per step (16 independent loads in flight per thread) instead of 16
   constexpr int BK = T == 32 ? 64 : ST_BK;
-  __shared__ X As[BK][T + 4];
-  __shared__ X Bs[BK][T + 4];
+  // the tiles are widened to fp64 ONCE, on the way into shared memory: every element is read by 16 threads, and the
+  // F2F.F64.F32 conversions (a quarter-rate pipe) were what bound the kernel when they sat in the inner loop
+  __shared__ double As[BK][T + 4];
+  __shared__ double Bs[BK][T + 4];
   // decode the upper-triangular tile pair (ti <= tj) from blockIdx.x
   int p = blockIdx.x, ti = 0;
   while (p >= n_tiles - ti) { p -= n_tiles - ti; ++ti; }
@@ -56,21 +58,21 @@ stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t ro
       int kk = e / T, cc = e % T;
       int64_t row = k0 + kk;
       bool rok = row < r1;
-      As[kk][cc] = (rok && i0 + cc < dim) ? xb[row * row_stride + i0 + cc] : X(0);
-      Bs[kk][cc] = (rok && j0 + cc < dim) ? xb[row * row_stride + j0 + cc] : X(0);
+      As[kk][cc] = (rok && i0 + cc < dim) ? (double)xb[row * row_stride + i0 + cc] : 0.0;
+      Bs[kk][cc] = (rok && j0 + cc < dim) ? (double)xb[row * row_stride + j0 + cc] : 0.0;
     }
     __syncthreads();
     if (ti == tj && tid < T) {
 #pragma unroll
-      for (int kk = 0; kk < BK; ++kk) colsum += (double)As[kk][tid];
+      for (int kk = 0; kk < BK; ++kk) colsum += As[kk][tid];
     }
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       double a[TH], b[TH];
 #pragma unroll
-      for (int i = 0; i < TH; ++i) a[i] = (double)As[kk][ty * TH + i];
+      for (int i = 0; i < TH; ++i) a[i] = As[kk][ty * TH + i];
 #pragma unroll
-      for (int j = 0; j < TH; ++j) b[j] = (double)Bs[kk][tx * TH + j];
+      for (int j = 0; j < TH; ++j) b[j] = Bs[kk][tx * TH + j];
 #pragma unroll
       for (int i = 0; i < TH; ++i)
 #pragma unroll
