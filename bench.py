@@ -310,6 +310,7 @@ def main():
 
     # denominators MEASURED_PEAKS.json does not hold ("builder must measure"), measured on this GPU now
     peaks_measured = dict(tf32_tflops=probe_peak(0), f16_tflops=probe_peak(1), mufu_ex2_tera_per_s=probe_peak(2),
+                          dfma_tflops=probe_peak(3),
                           how="otk_microbench_peak: tcgen05 kind::tf32 / kind::f16 with CTA pairs (M = N = 256) on operands "
                               "resident in shared / tensor memory (issue-bound ceiling of the MMA pipe, no loads); "
                               "ex2.approx.ftz.f32, 8 independent chains per thread, 8 CTAs x 256 threads per SM; best of 3 "

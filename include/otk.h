@@ -312,7 +312,7 @@ int otk_gemm_nn(const float* A, const float* B, float* C, int64_t M, int64_t N, 
 
 /* Peak probes for the roofline denominators that MEASURED_PEAKS.json does not hold ("builder must measure"):
  * kind 0 = dense tcgen05 kind::tf32, 1 = dense tcgen05 kind::f16 (TFLOP/s; CTA pairs, operands resident on chip, no loads),
- * 2 = MUFU.EX2 (1e12 ex2/s).  Synchronous (CUDA events, best of 3 launches); used by bench.py only. */
+ * 2 = MUFU.EX2 (1e12 ex2/s), 3 = DFMA (TFLOP/s).  Synchronous (CUDA events, best of 3 launches); used by bench.py only. */
 int otk_microbench_peak(int kind, double* result_host, otk_stream_t stream);
 
 #ifdef __cplusplus

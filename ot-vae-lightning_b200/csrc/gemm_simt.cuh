@@ -119,9 +119,101 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmArgs<T> g) {
   }
 }
 
+// fp64 engine for products of 128 rows / columns and more: 128 x 128 tiles, 8 x 8 outputs per thread (as 2 x 2 blocks of
+// 4 x 4, so that a warp reads two broadcast addresses of A and 16 consecutive pairs of B per step), K in steps of 16.
+// 64 DFMA per 16 shared-memory doubles read: bound by the DFMA pipe (measured ceiling, otk_microbench_peak: 36 TFLOP/s),
+// where the 64 x 64 / 4 x 4 kernel above is bound by shared-memory bandwidth and barriers (~5 TFLOP/s).  Same epilogue.
+constexpr int DG_BM = 128, DG_BN = 128, DG_BK = 16, DG_THREADS = 256;
+
+static __global__ void __launch_bounds__(DG_THREADS, 1) gemm_dfma_kernel(GemmArgs<double> g) {
+  __shared__ double As[DG_BK][DG_BM + 2];
+  __shared__ double Bs[DG_BK][DG_BN + 2];
+  const int64_t batch = blockIdx.z;
+  const double* A = g.A + batch * g.strideA;
+  const double* B = g.B + batch * g.strideB;
+  double* C = g.C ? g.C + batch * g.strideC : nullptr;
+  const double* a_off = g.a_off ? g.a_off + batch * g.stride_aoff : nullptr;
+  const double* bias = g.bias ? g.bias + batch * g.stride_bias : nullptr;
+  const double* add = g.add ? g.add + batch * g.strideC : nullptr;
+  const double* add_lo = g.add_lo ? g.add_lo + batch * g.strideC : nullptr;
+  const int64_t m0 = (int64_t)blockIdx.y * DG_BM, n0 = (int64_t)blockIdx.x * DG_BN;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  const bool a_kfast = (g.sak == 1), b_kfast = (g.sbk == 1);
+  for (int64_t k0 = 0; k0 < g.K; k0 += DG_BK) {
+#pragma unroll
+    for (int r = 0; r < (DG_BM * DG_BK) / DG_THREADS; ++r) {
+      const int e = tid + r * DG_THREADS;
+      const int kk = a_kfast ? e % DG_BK : e / DG_BM, mm = a_kfast ? e / DG_BK : e % DG_BM;
+      const int64_t m = m0 + mm, k = k0 + kk;
+      double v = 0.0;
+      if (m < g.M && k < g.K) {
+        v = A[m * g.sam + k * g.sak];
+        if (a_off) v -= a_off[k];
+      }
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < (DG_BN * DG_BK) / DG_THREADS; ++r) {
+      const int e = tid + r * DG_THREADS;
+      const int kk = b_kfast ? e % DG_BK : e / DG_BN, nn = b_kfast ? e / DG_BK : e % DG_BN;
+      const int64_t n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < g.N && k < g.K) ? B[n * g.sbn + k * g.sbk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < DG_BK; ++kk) {
+      double a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; a[4 + i] = As[kk][64 + ty * 4 + i]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { b[j] = Bs[kk][tx * 4 + j]; b[4 + j] = Bs[kk][64 + tx * 4 + j]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double res = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= g.N) continue;
+      double r = g.alpha * acc[i][j];
+      if (g.beta != 0.0 && C) r += g.beta * C[m * g.ldc + n];
+      if (bias) r += bias[n];
+      if (add) r += g.add_scale * (add[m * g.ldc + n] + (add_lo ? add_lo[m * g.ldc + n] : 0.0));
+      if (m == n) r += g.diag_add;
+      if (C) C[m * g.ldc + n] = r;
+      if (g.resid) { const double e = acc[i][j] - (m == n ? 1.0 : 0.0); res += e * e; }
+    }
+  }
+  if (g.resid) {
+    res = warp_sum(res);
+    if (tid % 32 == 0) atomicAdd(&g.resid[batch], res);
+  }
+}
+
 template <typename T>
 inline int gemm_simt(const GemmArgs<T>& g, int64_t batch, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || batch <= 0) return OTK_OK;
+  if constexpr (sizeof(T) == 8) {
+    if (g.M >= DG_BM && g.N >= DG_BN && batch <= 65535) {
+      dim3 grid((unsigned)ceil_div(g.N, DG_BN), (unsigned)ceil_div(g.M, DG_BM), (unsigned)batch);
+      gemm_dfma_kernel<<<grid, DG_THREADS, 0, st>>>(g);
+      OTK_LAUNCH_CHECK();
+      return OTK_OK;
+    }
+  }
   dim3 grid((unsigned)ceil_div(g.N, SG_BN), (unsigned)ceil_div(g.M, SG_BM), (unsigned)batch);
   gemm_simt_kernel<T><<<grid, SG_THREADS, 0, st>>>(g);
   OTK_LAUNCH_CHECK();

@@ -78,14 +78,30 @@ __global__ void __launch_bounds__(256) mb_ex2_kernel(int reps, float seed, float
   if (s == 12345.678f) out[0] = s;                               // never true: keeps the chains alive
 }
 
+// 8 independent DFMA chains per thread (the fp64 engine of the matrix functions and the latency-mode statistics kernel)
+__global__ void __launch_bounds__(256) mb_dfma_kernel(int reps, double seed, double* out) {
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = seed + 1e-3 * (double)(threadIdx.x + i);
+  const double a = 0.999999, b = 1e-7;
+  for (int r = 0; r < reps; ++r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fma(v[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 }  // namespace otk
 using namespace otk;
 
-// kind 0: tcgen05 kind::tf32 (TFLOP/s), 1: tcgen05 kind::f16 (TFLOP/s), 2: MUFU.EX2 (1e12 ex2/s).  Synchronous: times
+// kind 0: tcgen05 kind::tf32 (TFLOP/s), 1: tcgen05 kind::f16 (TFLOP/s), 2: MUFU.EX2 (1e12 ex2/s), 3: DFMA (TFLOP/s).  Synchronous: times
 // its own launches with CUDA events on `stream` (best of 3).
 extern "C" int otk_microbench_peak(int kind, double* result_host, otk_stream_t stream) {
   OTK_TRY(require_device());
-  OTK_REQUIRE(result_host && kind >= 0 && kind <= 2, "microbench_peak: bad arguments");
+  OTK_REQUIRE(result_host && kind >= 0 && kind <= 3, "microbench_peak: bad arguments");
   cudaStream_t st = as_stream(stream);
   cudaEvent_t e0, e1;
   OTK_CUDA(cudaEventCreate(&e0));
@@ -110,6 +126,12 @@ extern "C" int otk_microbench_peak(int kind, double* result_host, otk_stream_t s
       OTK_CUDA(cudaLaunchKernelEx(&cfg, mb_mma_kernel, kind, reps));
       OTK_CUDA(cudaEventRecord(e1, st));
       work = 2.0 * 256 * 256 * (kind == 1 ? 16 : 8) * 12.0 * reps * (grid / 2);        // flop
+    } else if (kind == 3) {
+      const int reps = 4000, blocks = sms * 8;
+      OTK_CUDA(cudaEventRecord(e0, st));
+      mb_dfma_kernel<<<blocks, 256, 0, st>>>(reps, 0.5, reinterpret_cast<double*>(sink));
+      OTK_CUDA(cudaEventRecord(e1, st));
+      work = 2.0 * 8.0 * reps * 256.0 * blocks;                                        // flop
     } else {
       const int reps = 20000, blocks = sms * 8;
       OTK_CUDA(cudaEventRecord(e0, st));
