@@ -126,9 +126,12 @@ class GaussianModel(DistributionModel, W2Mixin):
         return plan[3](samples)
 
     @torch.no_grad()
-    def fit(self, samples: Optional[Tensor] = None, cov_operand: Optional[Tensor] = None, operand_shift: float = 0.0) -> None:
+    def fit(self, samples: Optional[Tensor] = None, cov_operand: Optional[Tensor] = None, operand_shift: float = 0.0,
+            already_reduced: bool = False) -> None:
         """reference gaussian_model.py:110-126.  `cov_operand` (an extension used by `GaussianTransport.compute`): a buffer
-        [*L, d, d] of the parameter dtype that additionally receives triu-mirror(raw covariance) + `operand_shift` I."""
+        [*L, d, d] of the parameter dtype that additionally receives triu-mirror(raw covariance) + `operand_shift` I;
+        `already_reduced`: the caller has summed the running statistics over the ranks (one joint all-reduce for both
+        models of a `GaussianTransport`)."""
         self._fit_warn()
         if self.update_with_autograd:
             if samples is None:
@@ -138,9 +141,9 @@ class GaussianModel(DistributionModel, W2Mixin):
             self._update_cov(cov, seen)
         if samples is not None:
             self.update(samples)
-        if self._native_fit(cov_operand, operand_shift):
+        if self._native_fit(cov_operand, operand_shift, already_reduced):
             return
-        self._n_obs, self._running_sum, self._running_sum_cov = self._stats(None, reduce=True)
+        self._n_obs, self._running_sum, self._running_sum_cov = self._stats(None, reduce=not already_reduced)
         mean, cov, seen = self._compute_mean_cov(self._n_obs, self._running_sum, self._running_sum_cov)
         self._update_mean(mean, seen)
         self._update_cov(cov, seen)
@@ -149,7 +152,7 @@ class GaussianModel(DistributionModel, W2Mixin):
             shift = torch.full(self.vec_shape[:-1], operand_shift, dtype=cov_operand.dtype, device=cov_operand.device)
             K.symmetrize_shift(self.parametrizations.cov.original.to(cov_operand.dtype), shift, out=cov_operand)
 
-    def _native_fit(self, cov_operand: Optional[Tensor], operand_shift: float) -> bool:
+    def _native_fit(self, cov_operand: Optional[Tensor], operand_shift: float, already_reduced: bool = False) -> bool:
         """The whole fit as ONE kernel (`otk_gaussian_fit`): mean = sum / n and the raw covariance written in place for every
         leading index that has observations (the others keep their state), no host read-back.  Full-covariance models on
         a CUDA device; under a process group the packed all-reduce of the statistics runs first."""
@@ -162,7 +165,7 @@ class GaussianModel(DistributionModel, W2Mixin):
                                            and cov_operand.is_contiguous() and cov_operand.device == raw.device)))
         if not ok:
             return False
-        if self._reduce_is_active():
+        if self._reduce_is_active() and not already_reduced:
             self._n_obs, self._running_sum, self._running_sum_cov = self._stats(None, reduce=True)
         for buf in (self._n_obs, self._running_sum, self._running_sum_cov):
             if not buf.is_contiguous():

@@ -43,12 +43,32 @@ class GaussianTransport(TransportOperator, W2Mixin):
         symmetrised + shifted covariances the map computation consumes as well (one launch per model does the whole fit)."""
         self._prepared = None          # the means are about to change
         operands = getattr(self, "_fit_operands", None)
-        if operands is None:
-            return super().fit_models()
         src, tgt = self._stored_samples()
-        self.source_model.fit(src, cov_operand=operands[0], operand_shift=operands[2])
-        self.target_model.fit(tgt, cov_operand=operands[1], operand_shift=operands[2])
+        reduced = src is None and tgt is None and self._joint_reduce()
+        if operands is None:
+            self.source_model.fit(src, already_reduced=reduced)
+            self.target_model.fit(tgt, already_reduced=reduced)
+            return
+        self.source_model.fit(src, cov_operand=operands[0], operand_shift=operands[2], already_reduced=reduced)
+        self.target_model.fit(tgt, cov_operand=operands[1], operand_shift=operands[2], already_reduced=reduced)
         self._operands_written = True
+
+    def _joint_reduce(self) -> bool:
+        """ONE all-reduce of [n | sum x | sum x x^T] of BOTH models (the reference: three per model and update,
+        gaussian_model.py:153-156), written back into the running buffers in place.  False if the two models do not
+        share the default reduction or a process group does not exist - each model then reduces for itself."""
+        sm, tm = self.source_model, self.target_model
+        if self.diag or sm.update_with_autograd or tm.update_with_autograd or sm.reduce is not tm.reduce \
+                or not sm._reduce_is_active() or sm._running_sum.dtype != tm._running_sum.dtype:
+            return False
+        bufs = [sm._n_obs, sm._running_sum, sm._running_sum_cov, tm._n_obs, tm._running_sum, tm._running_sum_cov]
+        dt = sm._running_sum_cov.dtype
+        flat = sm.reduce(torch.cat([b.reshape(-1).to(dt) for b in bufs]))
+        lo = 0
+        for b in bufs:
+            b.copy_(flat[lo:lo + b.numel()].view(b.shape))
+            lo += b.numel()
+        return True
 
     def _prepared_operator(self):
         """`kernels.PreparedTransport` of the current (means, T), rebuilt whenever one of them was replaced or written to

@@ -41,6 +41,23 @@ def _worker(rank, world, port, out_dir):
                 gm2.update(x[s:min(hi, s + 50)])
             gm2.fit()
             assert float(gm2._n_obs) == 1200.0 and torch.allclose(gm2.mean.double(), mean, atol=1e-10)
+            # ---- (a') GaussianTransport: ONE joint all-reduce of both models' statistics inside compute()
+            y = torch.randn(600, 12, generator=torch.Generator().manual_seed(5)) * 0.7 - 0.5
+            op = ot.GaussianTransport(12, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double, device="cpu",
+                                                                                         reduce_on_update=False),
+                                      target_cfg=dict(dtype=torch.double, device="cpu", reduce_on_update=False))
+            calls = []
+            plain = op.source_model.reduce
+            counting = lambda t: (calls.append(t.numel()), plain(t))[1]
+            op.source_model.reduce = op.target_model.reduce = counting
+            lo, hi = parallel.shard_rows(600, rank, world)
+            op.update(source_samples=x[lo:hi], target_samples=y[lo:hi])
+            w2 = op.compute()
+            assert calls == [2 * (1 + 12 + 144)], calls                       # one reduction, both models packed
+            want = O.gaussian_transport_pipeline(x, y, 600)
+            assert torch.allclose(op.source_model.mean.double(), want["mean_s"], atol=1e-10)
+            assert torch.allclose(op.target_model.cov.double(), want["cov_t"], atol=1e-9)
+            assert abs(float(w2) - float(want["w2"])) < 1e-8 * float(want["w2"]) and float(op.source_model._n_obs) == 600.0
             # ---- (b) row-sharded Sinkhorn == single-process oracle
             xs = torch.randn(64, 6, generator=g)
             ys = torch.randn(48, 6, generator=g) + 0.5
