@@ -1,6 +1,7 @@
 // libotk: process-level plumbing of the C ABI (include/otk.h).
 #include "otk_common.cuh"
 #include <atomic>
+#include <cstdlib>
 
 namespace otk {
 char* last_error_buffer() {
@@ -31,6 +32,10 @@ int require_device() {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("OTK_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);

@@ -74,6 +74,38 @@ struct Arena {
   bool ok() const { return off <= cap && (base != nullptr || off == 0); }
 };
 
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// launch `kern` so that its launch processing (and whatever it does before `griddepcontrol.wait`) overlaps the tail of the
+// previous kernel of the stream; the kernel MUST execute ptx::pdl_wait() before it touches anything the predecessor
+// wrote.  `cluster` > 1 adds a cluster dimension.  OTK_PDL=0 launches plainly (tuning aid).
+bool pdl_enabled();   // api.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers -----------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

@@ -139,6 +139,7 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // launched programmatically behind pivot_scale_kernel: its pivot / scale / flag reset are visible from here
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
@@ -430,6 +431,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // launched programmatically behind pivot_scale_kernel (see stats_h_kernel)
 
   if (warp == 0 || warp == 22) {
     // ===== TMA producers: warp 0 streams the A blocks, warp 22 the B blocks (independent rings: a slow side must not
@@ -709,6 +711,7 @@ __global__ void pivot_scale_kernel(const float* __restrict__ x, int64_t rows, in
 }
 
 __global__ void zero_if_kernel(double* __restrict__ p, int64_t n, const int* __restrict__ flag) {
+  ptx::pdl_wait();
   if (*flag == 0) return;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = 0.0;
 }
@@ -747,6 +750,7 @@ stats_h_merge_kernel(const float* __restrict__ rec_cov, int parts, const float* 
                      const float* __restrict__ pivot, const int* __restrict__ flag, const double* __restrict__ ws_cov,
                      const double* __restrict__ ws_sum, int dim, double rows, StatsRunning run) {
   __shared__ double red[HM_GROUPS][HM_OUT];
+  ptx::pdl_wait();
   const int tri = dim * (dim + 1) / 2;
   const int blocks_per_l = (tri + HM_OUT - 1) / HM_OUT;
   const int64_t l = blockIdx.x / blocks_per_l;
@@ -800,6 +804,7 @@ stats_h2_merge_kernel(const float* __restrict__ parts, int n_seg, int n_units, i
                       StatsRunning run) {
   constexpr int C4 = BW / 4, G = 256 / C4;
   __shared__ double red[G][C4][4];
+  ptx::pdl_wait();
   const int u = blockIdx.x / BW, r = blockIdx.x % BW;
   const int64_t l = u / upl;
   int w = u % upl, bi = 0;
@@ -847,16 +852,16 @@ int stats_h_merge(const StatsHPlan& plan, const float* pivot, const double* ws_c
                   int64_t rows, int64_t dim, const StatsRunning& run, cudaStream_t st) {
   if (plan.mode == 1) {
     const int64_t tri = dim * (dim + 1) / 2, blocks = L * ceil_div(tri, HM_OUT);
-    stats_h_merge_kernel<<<(unsigned)blocks, HM_OUT * HM_GROUPS, 0, st>>>(plan.parts, plan.n_parts, plan.scale, pivot, plan.flag,
-                                                                        ws_cov, ws_sum, (int)dim, (double)rows, run);
+    OTK_CUDA(launch_pdl(stats_h_merge_kernel, dim3((unsigned)blocks), dim3(HM_OUT * HM_GROUPS), 0, st, 1, plan.parts, plan.n_parts,
+                        plan.scale, pivot, plan.flag, ws_cov, ws_sum, (int)dim, (double)rows, run));
   } else if (plan.mode == 2) {
-    stats_h2_merge_kernel<128><<<(unsigned)(plan.n_units * 128), 256, 0, st>>>(plan.parts, plan.n_parts, plan.n_units, plan.upl,
-                                                                              plan.nB, plan.scale, pivot, plan.flag, ws_cov,
-                                                                              ws_sum, (int)dim, (double)rows, run);
+    OTK_CUDA(launch_pdl(stats_h2_merge_kernel<128>, dim3((unsigned)(plan.n_units * 128)), dim3(256), 0, st, 1, plan.parts,
+                        plan.n_parts, plan.n_units, plan.upl, plan.nB, plan.scale, pivot, plan.flag, ws_cov, ws_sum, (int)dim,
+                        (double)rows, run));
   } else {   // mode 3: 256 x 256 units of the CTA-pair kernel
-    stats_h2_merge_kernel<256><<<(unsigned)(plan.n_units * 256), 256, 0, st>>>(plan.parts, plan.n_parts, plan.n_units, plan.upl,
-                                                                              plan.nB, plan.scale, pivot, plan.flag, ws_cov,
-                                                                              ws_sum, (int)dim, (double)rows, run);
+    OTK_CUDA(launch_pdl(stats_h2_merge_kernel<256>, dim3((unsigned)(plan.n_units * 256)), dim3(256), 0, st, 1, plan.parts,
+                        plan.n_parts, plan.n_units, plan.upl, plan.nB, plan.scale, pivot, plan.flag, ws_cov, ws_sum, (int)dim,
+                        (double)rows, run));
   }
   OTK_LAUNCH_CHECK();
   return OTK_OK;
@@ -901,8 +906,8 @@ int stats_h_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_t
   if (range_len < 256) range_len = 256;
   parts = ceil_div(rows, range_len);
   if (L * parts > stats_h_max_records(L)) return OTK_ERR_WORKSPACE;
-  stats_h_kernel<<<(unsigned)(L * parts), SH_THREADS, SH_SMEM, st>>>(mX, pivot, scale, (int)rows, (int)dim, (int)parts,
-                                                                    (int)range_len, rec, ws_sum, flag);
+  OTK_CUDA(launch_pdl(stats_h_kernel, dim3((unsigned)(L * parts)), dim3(SH_THREADS), SH_SMEM, st, 1, mX, (const float*)pivot,
+                      (const float*)scale, (int)rows, (int)dim, (int)parts, (int)range_len, rec, ws_sum, flag));
   OTK_LAUNCH_CHECK();
   *plan = StatsHPlan{1, rec, (int)parts, 0, 0, 0, scale, flag};
   return 1;
@@ -965,20 +970,9 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
       const int64_t n_seg = ceil_div(rows, seg_len), n_items = n_units2 * n_seg;
       if (n_seg <= max_seg2) {
         const unsigned groups = (unsigned)(n_items < pairs ? n_items : pairs);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(groups * 2);
-        cfg.blockDim = dim3(S2_THREADS);
-        cfg.dynamicSmemBytes = S2_SMEM;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        OTK_CUDA(cudaLaunchKernelEx(&cfg, stats_h2_kernel<2>, mX, (const float*)pivot, (const float*)scale, (int)dim, (int)nB2,
-                                    (int)upl2, (int)n_units2, (int)n_items, (int)seg_len, 0, (int)rows, parts, ws_sum, flag));
+        OTK_CUDA(launch_pdl(stats_h2_kernel<2>, dim3(groups * 2), dim3(S2_THREADS), S2_SMEM, st, 2, mX, (const float*)pivot,
+                            (const float*)scale, (int)dim, (int)nB2, (int)upl2, (int)n_units2, (int)n_items, (int)seg_len, 0,
+                            (int)rows, parts, ws_sum, flag));
         count_launch(1);
         *plan = StatsHPlan{3, parts, (int)n_seg, (int)n_units2, (int)upl2, (int)nB2, scale, flag};
         return 1;
@@ -1031,7 +1025,7 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
 int stats_zero_if(double* p, int64_t n, const int* flag, cudaStream_t st) {
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 1024) blocks = 1024;
-  zero_if_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n, flag);
+  OTK_CUDA(launch_pdl(zero_if_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, p, n, flag));
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }

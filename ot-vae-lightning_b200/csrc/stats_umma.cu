@@ -76,6 +76,7 @@ stats_ts_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
                 double* __restrict__ ws_sum, int dbg, const int* __restrict__ run_flag) {
   using namespace ptx;
   // fallback launch behind the FP16-split kernel (stats_h.cu): nothing to do unless that kernel raised its overflow flag
+  pdl_wait();      // programmatic launch: the predecessor's flag / staging area / pivot are visible from here
   if (run_flag != nullptr && *run_flag == 0) return;
   constexpr int SU_XS = su_xs<CG>(), SU_BS = su_bs<CG>();
   constexpr int BSL = 4 / CG;                          // 32-feature slabs of the B block staged by this CTA
@@ -408,20 +409,8 @@ static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, in
   const int parts = (int)p;
   const int64_t groups = nu * p;
   const long long flat_total = unit_off;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(SU_THREADS);
-  cfg.dynamicSmemBytes = su_smem<CG>();
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, mX, pivot, (int)rows, (int)dim, upl, nJ, (long long)range_len,
-                              (long long)flat_total, parts, ws_cov, ws_sum, g_stats_dbg, run_flag));
+  OTK_CUDA(launch_pdl(kern, dim3((unsigned)(groups * CG)), dim3(SU_THREADS), su_smem<CG>(), st, CG, mX, pivot, (int)rows, (int)dim,
+                      upl, nJ, (long long)range_len, (long long)flat_total, parts, ws_cov, ws_sum, g_stats_dbg, run_flag));
   OTK_LAUNCH_CHECK();
   }
   return 1;

@@ -894,7 +894,7 @@ def test_native_fit_matches_the_stepwise_fit_and_skips_unseen_indices(api, monke
         torch.manual_seed(1)
         gm = api.GaussianModel(3, 24, w2_cfg=dict(make_pd=True), dtype=torch.double, reduce_on_update=False).cuda()
         if not native:
-            monkeypatch.setattr(gm_mod.GaussianModel, "_native_fit", lambda self, c, s: False)
+            monkeypatch.setattr(gm_mod.GaussianModel, "_native_fit", lambda self, c, s, r=False: False)
         gm.update(x)
         gm._n_obs[1] = 0                                   # class 1 never observed
         operand = torch.empty(3, 24, 24, dtype=torch.double, device="cuda")
