@@ -208,26 +208,39 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
     // ===== epilogue: TMEM -> registers -> (per-warp 32x32 smem transpose) -> global =====
     // TMEM gives each lane one row; after the transpose lanes hold consecutive columns, so every store instruction
     // writes a full 128-byte line of C / C_hi / C_lo.
-    const int q = warp % 4;                        // TMEM lane quarter this warp may access
-    if (KS > 1 && ks != 0) {
-      // non-leader of a split-K cluster: park the partial accumulator in the pipeline smem (all MMAs that read it have
-      // retired once tmem_full fires), column-major [BN][128] so that lanes write consecutive words
+    // Split-K cluster (KS > 1): the tile is reduce-scattered - CTA `ks` finishes columns [ks, ks + 1) * BN / KS.  Once the
+    // MMAs of every CTA of the cluster have retired (first cluster barrier: the pipeline smem is then free everywhere),
+    // each CTA pushes the columns its peers own into the OWNER's smem with remote stores (slot = sender rank, column-major
+    // [BN / KS][128] so that lanes write consecutive words); its own share stays in tensor memory.  Remote stores are fire
+    // and forget, so the 21 B / clk distributed-shared-memory port is the only cost; the owner then reads local smem.
+    if constexpr (KS > 1) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
-      float* part = reinterpret_cast<float*>(smem);
+    }
+  }
+  if constexpr (KS > 1) {
+    cluster_sync_all();
+    if (warp >= 2) {
+      constexpr int SHARE = BN / KS;
+      const int q = warp % 4;                      // TMEM lane quarter this warp may access
+      const uint32_t land = smem_u32(smem) + (uint32_t)((ks * SHARE) * UG_BM + q * 32 + lane) * 4;   // my slot in any owner
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int owner = c0 / SHARE;
+        if (owner == ks) continue;
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
         tmem_ld_wait();
+        const uint32_t dst = map_to_cta(land, (uint32_t)owner) + (uint32_t)((c0 - owner * SHARE) * UG_BM) * 4;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) part[(c0 + j) * UG_BM + q * 32 + lane] = v[j];
+        for (int j = 0; j < 32; ++j) st_shared_cluster_f32(dst + (uint32_t)(j * UG_BM) * 4, v[j]);
       }
       tc_fence_before();
     }
+    cluster_sync_all();                            // the peers' partial columns have landed in this CTA's smem
   }
-  if constexpr (KS > 1) cluster_sync_all();        // partial accumulators of the peers are complete and visible
-  if (warp >= 2 && ks == 0) {
+  if (warp >= 2) {
+    static_assert((BN / KS) % 32 == 0, "split-K share must be whole 32-column chunks");
     const int q = warp % 4;
     const uint32_t xp_addr = smem_u32(xpose + (warp - 2) * (32 * 33));
     const int mrow0 = m0 + q * 32;
@@ -240,23 +253,21 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
     const float* bias = p.bias ? p.bias + (int64_t)batch * p.stride_bias : nullptr;
     const float* Ah = p.add_hi ? p.add_hi + (int64_t)batch * p.strideC : nullptr;
     const float* Al = p.add_lo ? p.add_lo + (int64_t)batch * p.strideC : nullptr;
-    uint32_t peer[KS > 1 ? KS - 1 : 1];
-    if constexpr (KS > 1) {
-#pragma unroll
-      for (int r = 1; r < KS; ++r) peer[r - 1] = map_to_cta(smem_u32(smem), (uint32_t)r) + (uint32_t)(q * 32 + lane) * 4;
-    }
     double res = 0.0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = ks * (BN / KS); c0 < (ks + 1) * (BN / KS); c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
       tmem_ld_wait();
       if (c0 == 0) GT_STAMP(6)
       if constexpr (KS > 1) {
+        const uint32_t mine = smem_u32(smem) + (uint32_t)((c0 - ks * (BN / KS)) * UG_BM + q * 32 + lane) * 4;
 #pragma unroll
-        for (int r = 1; r < KS; ++r)
+        for (int r = 1; r < KS; ++r) {
+          const uint32_t slot = mine + (uint32_t)((((ks + r) % KS) * (BN / KS)) * UG_BM) * 4;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += ld_shared_cluster_f32(peer[r - 1] + (uint32_t)((c0 + j) * UG_BM) * 4);
+          for (int j = 0; j < 32; ++j) v[j] += lds32(slot + (uint32_t)(j * UG_BM) * 4);
+        }
       }
       // 32 x 32 transpose through shared memory with explicit st.shared / ld.shared: through the generic `float*` the
       // compiler emitted generic LD.E / ST.E and, unable to tell them from the global stores of C_hi / C_lo, kept one
@@ -307,7 +318,6 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
     tc_fence_before();
     GT_STAMP(5)
   }
-  if constexpr (KS > 1) cluster_sync_all();        // the leader has read the peers' shared memory: they may exit
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 #ifdef OTK_GEMM_TIMING
@@ -425,35 +435,30 @@ static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_pr
   dim3 grid((unsigned)(ceil_div(a.p.M, UG_BM) * KS), (unsigned)ceil_div(a.p.N, BN), (unsigned)(batch * n_problems));
   if (grid.y > 65535 || grid.z > 65535) return 0;
   static const bool pdl_on = [] { const char* e = getenv("OTK_GEMM_PDL"); return !(e && e[0] == '0'); }();   // tuning aid
-  if constexpr (KS == 1) {
-    if (pdl_on) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = grid;
-      cfg.blockDim = dim3(UG_THREADS);
-      cfg.dynamicSmemBytes = ug_smem<BN>();
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev));
-    } else {
-      kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev);
-    }
+  if (KS == 1 && !pdl_on) {
+    kern<<<grid, UG_THREADS, ug_smem<BN>(), st>>>(a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(UG_THREADS);
     cfg.dynamicSmemBytes = ug_smem<BN>();
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = KS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned n_attr = 0;
+    if (KS > 1) {
+      attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+      attr[n_attr].val.clusterDim.x = KS;
+      attr[n_attr].val.clusterDim.y = 1;
+      attr[n_attr].val.clusterDim.z = 1;
+      ++n_attr;
+    }
+    if (pdl_on) {
+      attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+      ++n_attr;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = n_attr;
     OTK_CUDA(cudaLaunchKernelEx(&cfg, kern, a.maps, b.maps, a.p, b.p, (int)batch, ctrl, ctrl_index, ev));
   }
   OTK_LAUNCH_CHECK();
@@ -463,7 +468,8 @@ static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_pr
 template <int BN>
 static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, int ks, const int* ctrl,
                        int ctrl_index, cudaStream_t st, const NsCtrlEval& ev = NsCtrlEval{}) {
-  if (ks == 4) return launch_gemm_ks<BN, 4>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev);
+  if constexpr (BN / 4 >= 32) { if (ks == 4) return launch_gemm_ks<BN, 4>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev); }
+  if (ks == 4) ks = 2;                            // a share is at least one 32-column chunk
   if (ks == 2) return launch_gemm_ks<BN, 2>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev);
   return launch_gemm_ks<BN, 1>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev);
 }
@@ -472,11 +478,10 @@ static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_probl
 // (128 + BN) * K / KS * 8: among the (BN, KS) whose grid still fits one wave pick the one that minimises it (at least
 // two k-blocks per CTA); products that fill the machine anyway use 128-wide tiles without a split.
 static void pick_tile(int64_t M, int64_t N, int64_t K, int64_t batch, int n_problems, int* bn_out, int* ks_out) {
-  // Measured (B200, 512^3, paired launch): the split does not pay - the products of the Newton-Schulz chain are bound by
-  // per-launch latency, and the distributed-shared-memory reduction costs what the shorter K loop saves (compute():
-  // 2.29 ms with, 2.12 ms without).  It does shorten the truncating tensor-memory accumulation chains (relative error
-  // 9e-7 instead of 3.6e-6 at K = 512), so it stays available: OTK_GEMM_SPLITK=1.
-  static const bool split_ok = [] { const char* e = getenv("OTK_GEMM_SPLITK"); return e && e[0] == '1'; }();
+  // The split-K cluster reduce-scatters the tile (each CTA finishes BN / KS columns from its peers' parked partials), so the
+  // K loop, the distributed-shared-memory reads and the epilogue all shrink by KS.  It also shortens the truncating
+  // tensor-memory accumulation chains (relative error 9e-7 instead of 3.6e-6 at K = 512).  OTK_GEMM_SPLITK=0 turns it off.
+  static const bool split_ok = [] { const char* e = getenv("OTK_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
   const int64_t sms = sm_count(), num_k = ceil_div(K, UG_BK);
   // Long contractions: tensor memory accumulates with truncation (relative error ~6e-8 per K = 8 step), so at K >= 4096 the
   // K loop is cut over a cluster of 4 CTAs whose partial tiles are added in fp32 registers (round to nearest) through
@@ -485,12 +490,17 @@ static void pick_tile(int64_t M, int64_t N, int64_t K, int64_t batch, int n_prob
   // K = 2048 the un-split product is accurate enough (4.1e-4) and twice as fast (7.5 vs 14 ms per map), so it stays whole.
   static const bool long_k_split = [] { const char* e = getenv("OTK_GEMM_LONGK_SPLIT"); return !(e && e[0] == '0'); }();
   if (long_k_split && K >= 4096 && M >= UG_BM && N >= 128) { *bn_out = 128; *ks_out = 4; return; }
+  static const int forced = [] { const char* e = getenv("OTK_GEMM_TILE"); return e ? atoi(e) : 0; }();   // tuning aid: BN * 10 + KS
+  if (forced > 0 && K < 4096) {
+    const int bn = forced / 10, ks = forced % 10;
+    if ((bn == 64 || bn == 128) && (ks == 1 || ks == 2 || ks == 4) && bn / ks >= 32 && num_k >= 2 * ks) { *bn_out = bn; *ks_out = ks; return; }
+  }
   int best_bn = 128, best_ks = 1;
   int64_t best_cost = INT64_MAX;
   for (int bn : {128, 64}) {
     const int64_t ctas = ceil_div(M, UG_BM) * ceil_div(N, bn) * batch * n_problems;
     for (int ks : {1, 2, 4}) {
-      if (ks > 1 && (!split_ok || num_k < 2 * ks)) continue;
+      if (ks > 1 && (!split_ok || num_k < 4 * ks || bn / ks < 32)) continue;
       if (ctas * ks > sms && !(bn == 128 && ks == 1)) continue;      // (128, 1) is the fallback for large products
       const int64_t cost = (int64_t)(UG_BM + bn) * ceil_div(num_k, ks);
       if (cost < best_cost) { best_cost = cost; best_bn = bn; best_ks = ks; }

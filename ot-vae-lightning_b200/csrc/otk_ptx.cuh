@@ -193,7 +193,10 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta)
 // without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// 32-bit load from a shared::cluster address (distributed shared memory of a peer CTA)
+// 32-bit store to / load from a shared::cluster address (distributed shared memory of a peer CTA)
+__device__ __forceinline__ void st_shared_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
   float v;
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
