@@ -32,9 +32,11 @@ int require_device() {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
-bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("OTK_PDL"); return !(e && e[0] == '0'); }();
-  return on;
+bool pdl_enabled(int site) {
+  // sites: 0 main statistics kernels, 1 conditional clear, 2 gated TF32 fallback, 3 merge kernels.  Measured per update call
+  // (65536 x 512 chunk): none 97.3 us, sites 0-2 90.7 us, all four 101.2 us - the merge kernels launch plainly by default.
+  static const int mask = [] { const char* e = getenv("OTK_PDL"); return e ? atoi(e) : 7; }();
+  return (mask >> site) & 1;
 }
 int sm_count() {
   int dev = 0;

@@ -78,10 +78,10 @@ struct Arena {
 // launch `kern` so that its launch processing (and whatever it does before `griddepcontrol.wait`) overlaps the tail of the
 // previous kernel of the stream; the kernel MUST execute ptx::pdl_wait() before it touches anything the predecessor
 // wrote.  `cluster` > 1 adds a cluster dimension.  OTK_PDL=0 launches plainly (tuning aid).
-bool pdl_enabled();   // api.cu
+bool pdl_enabled(int site = 0);   // api.cu; OTK_PDL is a bit mask over launch sites (tuning aid), default all
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
-                              Args&&... args) {
+inline cudaError_t launch_pdl_site(int site, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   int cluster, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -96,7 +96,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (pdl_enabled()) {
+  if (pdl_enabled(site)) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -104,6 +104,12 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.attrs = attr;
   cfg.numAttrs = (unsigned)n;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                              Args&&... args) {
+  return launch_pdl_site(0, kern, grid, block, smem, st, cluster, static_cast<Args&&>(args)...);
 }
 
 // ---- device helpers -----------------------------------------------------------------------------

@@ -139,7 +139,11 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // launched programmatically behind pivot_scale_kernel: its pivot / scale / flag reset are visible from here
+  // Launched programmatically behind pivot_scale_kernel (which releases its dependents at once): the prologue above and
+  // the TMA producer - X was final before pivot_scale started - run beside it; everyone else (pivot / scale readers, the
+  // overflow flag, the column-sum atomics it zeroes) waits for its completion here.
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
@@ -431,7 +435,8 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // launched programmatically behind pivot_scale_kernel (see stats_h_kernel)
+  pdl_launch_dependents();
+  if (warp != 0 && warp != 22) pdl_wait();      // as in stats_h_kernel: only the two TMA producer warps run ahead of pivot_scale
 
   if (warp == 0 || warp == 22) {
     // ===== TMA producers: warp 0 streams the A blocks, warp 22 the B blocks (independent rings: a slow side must not
@@ -673,6 +678,7 @@ __global__ void pivot_scale_kernel(const float* __restrict__ x, int64_t rows, in
   __shared__ float piv[32];
   const int64_t l = blockIdx.y;
   const int64_t col = blockIdx.x * 32 + threadIdx.x;
+  ptx::pdl_launch_dependents();      // the statistics kernel behind may start its prologue and its raw-tile loads now
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) *flag = 0;
   if (threadIdx.y == 1 && col < dim) ws_sum[l * dim + col] = 0.0;
   const int64_t n = rows < 64 ? rows : 64;
@@ -711,6 +717,7 @@ __global__ void pivot_scale_kernel(const float* __restrict__ x, int64_t rows, in
 }
 
 __global__ void zero_if_kernel(double* __restrict__ p, int64_t n, const int* __restrict__ flag) {
+  ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   if (*flag == 0) return;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = 0.0;
@@ -852,14 +859,14 @@ int stats_h_merge(const StatsHPlan& plan, const float* pivot, const double* ws_c
                   int64_t rows, int64_t dim, const StatsRunning& run, cudaStream_t st) {
   if (plan.mode == 1) {
     const int64_t tri = dim * (dim + 1) / 2, blocks = L * ceil_div(tri, HM_OUT);
-    OTK_CUDA(launch_pdl(stats_h_merge_kernel, dim3((unsigned)blocks), dim3(HM_OUT * HM_GROUPS), 0, st, 1, plan.parts, plan.n_parts,
+    OTK_CUDA(launch_pdl_site(3, stats_h_merge_kernel, dim3((unsigned)blocks), dim3(HM_OUT * HM_GROUPS), 0, st, 1, plan.parts, plan.n_parts,
                         plan.scale, pivot, plan.flag, ws_cov, ws_sum, (int)dim, (double)rows, run));
   } else if (plan.mode == 2) {
-    OTK_CUDA(launch_pdl(stats_h2_merge_kernel<128>, dim3((unsigned)(plan.n_units * 128)), dim3(256), 0, st, 1, plan.parts,
+    OTK_CUDA(launch_pdl_site(3, stats_h2_merge_kernel<128>, dim3((unsigned)(plan.n_units * 128)), dim3(256), 0, st, 1, plan.parts,
                         plan.n_parts, plan.n_units, plan.upl, plan.nB, plan.scale, pivot, plan.flag, ws_cov, ws_sum, (int)dim,
                         (double)rows, run));
   } else {   // mode 3: 256 x 256 units of the CTA-pair kernel
-    OTK_CUDA(launch_pdl(stats_h2_merge_kernel<256>, dim3((unsigned)(plan.n_units * 256)), dim3(256), 0, st, 1, plan.parts,
+    OTK_CUDA(launch_pdl_site(3, stats_h2_merge_kernel<256>, dim3((unsigned)(plan.n_units * 256)), dim3(256), 0, st, 1, plan.parts,
                         plan.n_parts, plan.n_units, plan.upl, plan.nB, plan.scale, pivot, plan.flag, ws_cov, ws_sum, (int)dim,
                         (double)rows, run));
   }
@@ -1025,7 +1032,7 @@ int stats_h2_launch(const float* x, int64_t L, int64_t rows, int64_t dim, int64_
 int stats_zero_if(double* p, int64_t n, const int* flag, cudaStream_t st) {
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 1024) blocks = 1024;
-  OTK_CUDA(launch_pdl(zero_if_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, p, n, flag));
+  OTK_CUDA(launch_pdl_site(1, zero_if_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, p, n, flag));
   OTK_LAUNCH_CHECK();
   return OTK_OK;
 }

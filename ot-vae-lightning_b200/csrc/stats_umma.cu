@@ -76,6 +76,7 @@ stats_ts_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
                 double* __restrict__ ws_sum, int dbg, const int* __restrict__ run_flag) {
   using namespace ptx;
   // fallback launch behind the FP16-split kernel (stats_h.cu): nothing to do unless that kernel raised its overflow flag
+  pdl_launch_dependents();
   pdl_wait();      // programmatic launch: the predecessor's flag / staging area / pivot are visible from here
   if (run_flag != nullptr && *run_flag == 0) return;
   constexpr int SU_XS = su_xs<CG>(), SU_BS = su_bs<CG>();
@@ -409,7 +410,7 @@ static int launch_stats(const CUtensorMap& mX, const float* pivot, int64_t L, in
   const int parts = (int)p;
   const int64_t groups = nu * p;
   const long long flat_total = unit_off;
-  OTK_CUDA(launch_pdl(kern, dim3((unsigned)(groups * CG)), dim3(SU_THREADS), su_smem<CG>(), st, CG, mX, pivot, (int)rows, (int)dim,
+  OTK_CUDA(launch_pdl_site(2, kern, dim3((unsigned)(groups * CG)), dim3(SU_THREADS), su_smem<CG>(), st, CG, mX, pivot, (int)rows, (int)dim,
                       upl, nJ, (long long)range_len, (long long)flat_total, parts, ws_cov, ws_sum, g_stats_dbg, run_flag));
   OTK_LAUNCH_CHECK();
   }
