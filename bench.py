@@ -10,8 +10,9 @@ Primary metric  "cov+W2-map latents/s" on BASELINE.json configs[1]:
 Secondary metric (same JSON line, key "sinkhorn"): log-domain Sinkhorn iterations/s at N=M=65536, d=128, eps=0.05
     (BASELINE.json configs[2]; rows sharded over the ranks, strong scaling).
 `e2e` measures the same step through the public Python API with pinned HOST buffers (H2D of both latent sets and
-D2H of the transported latents inside the timed region).  `--impl reference` times the CPU oracle port of the
-reference (torch fp64, all host threads) on a bounded sample of the same workload.
+D2H of the transported latents inside the timed region).  `--impl reference` drives the UNMODIFIED reference
+(pip-installed into the git-ignored baseline/_ref by __graft_entry__.build(); torch fp64 on all host threads) through the
+same step; the oracle port is only the fallback when baseline/_ref is missing.
 """
 import argparse
 import json
@@ -470,6 +471,12 @@ def main():
             torch.cuda.synchronize()
             return dict(error=f"{type(e).__name__}: {e}"[:300])
 
+    def fast_counters():
+        import ctypes
+        cnt = (ctypes.c_int * 4)()
+        lib.otkdbg_fast_counters(cnt)
+        return list(cnt)
+
     def pipeline_parts(op_, xs, xt, batch, reps):
         """ms per step (reset, update both models per batch, compute, transport every source batch) and its three parts"""
         n_ = xs.shape[-2]
@@ -494,9 +501,14 @@ def main():
         ms, _ = timed(step, reps)
         u_ms, _ = timed(upd, reps)
         c_reps = max(reps, 10)
+        f0 = fast_counters()
         c_ms, _ = timed(lambda: op_.compute(), c_reps)
+        f1 = fast_counters()
         t_ms, _ = timed(mov, reps)
-        return dict(ms_per_step=ms / reps, update_ms=u_ms / reps, compute_ms=c_ms / c_reps, transport_ms=t_ms / reps)
+        # how the timed compute() calls ran: accepted / rejected by the single-graph operator path, graph replays / eager
+        path = dict(zip(("accepted", "rejected", "graph_replays", "eager"), (b - a for a, b in zip(f0, f1))))
+        return dict(ms_per_step=ms / reps, update_ms=u_ms / reps, compute_ms=c_ms / c_reps, transport_ms=t_ms / reps,
+                    compute_path=path)
 
     # ---- cfg1: the reference's own operating point (README.md:54-57, tests/test_latent_transport.py:66-98):
     # 10 000 latents of width 128 in batches of 250 -> 40 update calls per model, compute(), 40 transport calls
@@ -540,6 +552,7 @@ def main():
                 r = pipeline_parts(op5, xs, xt, n5, 3)
                 fl = 2.0 * n5 * d5 * d5
                 return dict(d=d5, rows=n5, update_ms=r["update_ms"] / 2, compute_ms=r["compute_ms"], transport_ms=r["transport_ms"],
+                            compute_path=r["compute_path"],
                             update_tflops=fl / (r["update_ms"] / 2 * 1e-3) / 1e12, update_gbs=n5 * d5 * 4 / (r["update_ms"] / 2 * 1e-3) / 1e9,
                             transport_tflops=fl / (r["transport_ms"] * 1e-3) / 1e12,
                             transport_gbs=2 * n5 * d5 * 4 / (r["transport_ms"] * 1e-3) / 1e9)

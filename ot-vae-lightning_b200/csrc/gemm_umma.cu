@@ -349,6 +349,220 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Throughput regime (batched operators, d >= 2048): persistent CTA-PAIR kernel on 256 x 256 tiles.
+// The 128 x 128 kernel above streams 64 KB of operand planes per 3.1 Mflop k-block - 21 TB/s of L2 -> SM traffic at the
+// TF32 peak, which the L2 cannot deliver (measured: 54 % of the tcgen05 TF32 ceiling at 10 x 1024^3) - and its epilogue is
+// serial with its main loop.  Here a pair of CTAs (tcgen05 cta_group::2, UMMA 256 x 256 x 8) shares one tile: each CTA
+// loads ITS 128 rows of A and ITS 128 of the 256 B columns (the same 64 KB per k-block, for twice the flops), both CTAs'
+// TMA bytes are credited to the leader's `full` barrier, the leader issues the MMAs and multicasts the commits; two
+// 256-column accumulators in tensor memory let the epilogue of tile i overlap the main loop of tile i + 1; the grid is
+// persistent (one pair per two SMs, tiles dealt round-robin).  Plane operands and plane results only (what the
+// Newton-Schulz chain uses); same residual / addend / device-side iteration limit / stop rule as the kernel above.
+constexpr int G2_BN = 256, G2_STAGES = 3, G2_THREADS = 192;
+constexpr int G2_PLANE = UG_BM * UG_BK * 4;                        // 16 KiB: 128 rows (A) or 128 columns (B half) x 32 k
+constexpr int G2_STAGE = 4 * G2_PLANE;                             // A_hi, A_lo, B_hi, B_lo
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE + 4 * UG_XPOSE + 1024 + 256;
+
+__global__ void __launch_bounds__(G2_THREADS, 1)
+umma_gemm_pair_kernel(const __grid_constant__ UmmaGemmMaps maps0, const __grid_constant__ UmmaGemmMaps maps1,
+                      const UmmaGemmParams p0, const UmmaGemmParams p1, int n_problems, int batch_per_problem,
+                      const int* __restrict__ ctrl, int ctrl_index, const NsCtrlEval ev) {
+  using namespace ptx;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* xpose = reinterpret_cast<float*>(smem + G2_STAGES * G2_STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE + 4 * UG_XPOSE);
+  uint64_t* empty = full + G2_STAGES;
+  uint64_t* acc_full = empty + G2_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+  const int tiles_m = (p0.M + 2 * UG_BM - 1) / (2 * UG_BM), tiles_n = (p0.N + G2_BN - 1) / G2_BN;
+  const int per_batch = tiles_m * tiles_n, per_problem = batch_per_problem * per_batch;
+  const int total = n_problems * per_problem;
+  const int num_k = (p0.K + UG_BK - 1) / UG_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps0.A_hi); tma_prefetch_desc(&maps0.A_lo); tma_prefetch_desc(&maps0.B_hi); tma_prefetch_desc(&maps0.B_lo);
+    for (int s = 0; s < G2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc_cg<2>(tmem_slot, 512); tmem_relinquish_cg<2>(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (ctrl && ctrl_index >= ctrl[0]) {             // past the device-side iteration limit: nothing to do (both CTAs agree)
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_cg<2>(tmem_base, 512);
+    return;
+  }
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's rows of A and its half of the B columns; bytes land on the LEADER's full barrier =====
+    const uint32_t full_leader = map_to_cta(smem_u32(&full[0]), 0);
+    int it = 0;
+    for (int tile = pair; tile < total; tile += n_pairs) {
+      const bool second = tile >= per_problem;
+      const UmmaGemmMaps& maps = second ? maps1 : maps0;
+      const UmmaGemmParams& p = second ? p1 : p0;
+      const int rem = tile - (second ? per_problem : 0);
+      const int batch = rem / per_batch, t2 = rem % per_batch;
+      const int m0 = (t2 / tiles_n) * (2 * UG_BM) + (int)rank * UG_BM;
+      const int n0 = (t2 % tiles_n) * G2_BN + (int)rank * 128;
+      for (int kt = 0; kt < num_k; ++kt, ++it) {
+        const int s = it % G2_STAGES;
+        mbar_wait(&empty[s], ((it / G2_STAGES) & 1) ^ 1);
+        uint8_t* st = smem + s * G2_STAGE;
+        const int k0 = kt * UG_BK;
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * G2_STAGE);
+          const uint32_t bar = full_leader + s * 8;
+          tma_load_3d_cg2(st, &maps.A_hi, k0, m0, batch, bar);
+          tma_load_3d_cg2(st + G2_PLANE, &maps.A_lo, k0, m0, batch, bar);
+          if (!p.b_mn_major) {
+            tma_load_3d_cg2(st + 2 * G2_PLANE, &maps.B_hi, k0, n0, batch, bar);
+            tma_load_3d_cg2(st + 3 * G2_PLANE, &maps.B_lo, k0, n0, batch, bar);
+          } else {
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {       // B is [K, N] row-major: one 32(n) x 32(k) box per 128-byte MN slab
+              tma_load_3d_cg2(st + 2 * G2_PLANE + sl * 4096, &maps.B_hi, n0 + 32 * sl, k0, batch, bar);
+              tma_load_3d_cg2(st + 3 * G2_PLANE + sl * 4096, &maps.B_lo, n0 + 32 * sl, k0, batch, bar);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only): warp-uniform loop, one elected lane issues =====
+    if (rank == 0) {
+      const uint32_t idesc = idesc_tf32(2 * UG_BM, G2_BN, 0, p0.b_mn_major);
+      const uint32_t b_kstep = p0.b_mn_major ? 1024u : 32u;
+      int it = 0, ti = 0;
+      for (int tile = pair; tile < total; tile += n_pairs, ++ti) {
+        const int a = ti & 1;
+        mbar_wait(&acc_empty[a], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + a * G2_BN;
+        for (int kt = 0; kt < num_k; ++kt, ++it) {
+          const int s = it % G2_STAGES;
+          mbar_wait(&full[s], (it / G2_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * G2_STAGE);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < UG_BK / 8; ++kk) {
+              const uint64_t a_hi = smem_desc_sw128(base + kk * 32, 16, 1024);
+              const uint64_t a_lo = smem_desc_sw128(base + G2_PLANE + kk * 32, 16, 1024);
+              const uint32_t b_hi_addr = base + 2 * G2_PLANE + kk * b_kstep, b_lo_addr = b_hi_addr + G2_PLANE;
+              const uint64_t b_hi = p0.b_mn_major ? smem_desc_mn_tf32(b_hi_addr, 4096) : smem_desc_sw128(b_hi_addr, 16, 1024);
+              const uint64_t b_lo = p0.b_mn_major ? smem_desc_mn_tf32(b_lo_addr, 4096) : smem_desc_sw128(b_lo_addr, 16, 1024);
+              umma_tf32_ss<2>(acc, a_lo, b_hi, idesc, (kt | kk) != 0);   // small terms first
+              umma_tf32_ss<2>(acc, a_hi, b_lo, idesc, 1);
+              umma_tf32_ss<2>(acc, a_hi, b_hi, idesc, 1);
+            }
+            umma_commit_cg<2>(&empty[s]);
+            if (kt == num_k - 1) umma_commit_cg<2>(&acc_full[a]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: this CTA's 128 x 256 half of the accumulator -> hi / lo planes (thread <-> row, 32-column chunks
+    // transposed through shared memory so that every store instruction writes a full 128-byte line) =====
+    const int q = warp % 4;
+    const uint32_t xp_addr = smem_u32(xpose + (warp - 2) * (32 * 33));
+    const uint32_t acc_empty_leader = map_to_cta(smem_u32(&acc_empty[0]), 0);
+    int ti = 0;
+    for (int tile = pair; tile < total; tile += n_pairs, ++ti) {
+      const bool second = tile >= per_problem;
+      const UmmaGemmParams& p = second ? p1 : p0;
+      const int rem = tile - (second ? per_problem : 0);
+      const int batch = rem / per_batch, t2 = rem % per_batch;
+      const int mrow0 = (t2 / tiles_n) * (2 * UG_BM) + (int)rank * UG_BM + q * 32;
+      const int n0 = (t2 % tiles_n) * G2_BN;
+      const int a = ti & 1;
+      float* Ch = p.C_hi + (int64_t)batch * p.strideC;
+      float* Cl = p.C_lo + (int64_t)batch * p.strideC;
+      const float* Ah = p.add_hi ? p.add_hi + (int64_t)batch * p.strideC : nullptr;
+      const float* Al = p.add_lo ? p.add_lo + (int64_t)batch * p.strideC : nullptr;
+      mbar_wait(&acc_full[a], (ti >> 1) & 1);
+      tc_fence_after();
+      double res = 0.0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < G2_BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G2_BN + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 == G2_BN) {                    // accumulator drained into registers: the MMAs of tile i + 2 may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + a * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sts32(xp_addr + (uint32_t)(lane * 33 + j) * 4, v[j]);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = lds32(xp_addr + (uint32_t)(r * 33 + lane) * 4);
+        const int n = n0 + c0 + lane;
+        if (n < p.N && mrow0 + 32 <= p.M) {
+          if (Ah && Al) epilogue_rows_planes<false, true>(v, mrow0, n, p.ldc, p.alpha, 0.f, p.diag_add, Ch, Cl, res, Ah, Al, p.add_scale);
+          else if (p.resid) epilogue_rows_planes<true>(v, mrow0, n, p.ldc, p.alpha, 0.f, p.diag_add, Ch, Cl, res);
+          else epilogue_rows_planes<false>(v, mrow0, n, p.ldc, p.alpha, 0.f, p.diag_add, Ch, Cl, res);
+        } else if (n < p.N) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int m = mrow0 + r;
+            if (m >= p.M) continue;
+            const float acc = v[r];
+            const int64_t idx = (int64_t)m * p.ldc + n;
+            if (p.resid) { const float e = acc - (m == n ? 1.f : 0.f); res += (double)(e * e); }
+            float t = p.alpha * acc;
+            if (Ah) t += p.add_scale * (Ah[idx] + (Al ? Al[idx] : 0.f));
+            if (m == n) t += p.diag_add;
+            float h, lo;
+            split_tf32(t, h, lo);
+            Ch[idx] = h;
+            Cl[idx] = lo;
+          }
+        }
+        __syncwarp();
+      }
+      if (p.resid) {
+        res = warp_sum(res);
+        if (lane == 0) atomicAdd(&p.resid[batch], res);
+      }
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_cg<2>(tmem_base, 512); }
+  // Newton-Schulz stopping rule, as in umma_gemm_kernel
+  if (ev.ctrl && warp == 2 && blockIdx.x == 0 && ev.k < ev.ctrl[0] && (ev.k >= 5 || ev.k + 1 == ev.max_iters)) {
+    double worst = 0;
+    for (int64_t l = lane; l < ev.L; l += 32) {
+      const double r = ev.resid_k[l];
+      const double v = (r == r && r <= 1e30) ? r : 1e300;
+      worst = v > worst ? v : worst;
+    }
+    worst = warp_max(worst);
+    if (lane == 0) {
+      if (worst >= 1e300) { ev.ctrl[0] = ev.k + 1; ev.ctrl[1] = 1; ev.ctrl[2] = 1; }
+      else if (worst < ev.tol_done) { if (ev.k + 1 < ev.ctrl[0]) ev.ctrl[0] = ev.k + 1; ev.ctrl[1] = 0; }
+      else if (worst < ev.tol_near) { if (ev.k + 2 < ev.ctrl[0]) ev.ctrl[0] = ev.k + 2; ev.ctrl[1] = 0; }
+    }
+  }
+}
+
 // elementwise split of a strided [batch][rows][cols] operand into dense TF32 hi/lo planes [batch][rows][cols]
 __global__ void split_planes_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t bstride,
                                     int64_t batch, float* __restrict__ hi, float* __restrict__ lo) {
@@ -465,6 +679,36 @@ static int launch_gemm_ks(const PreparedGemm& a, const PreparedGemm& b, int n_pr
   return 1;
 }
 
+// the persistent CTA-pair kernel: plane operands and plane results, no bias / beta / fp32 result, K below the long-K rule
+static bool pair_eligible(const GemmArgs<float>& g, int64_t batch, int n_problems) {
+  static const bool on = [] { const char* e = getenv("OTK_GEMM_PAIR"); return !(e && e[0] == '0'); }();   // tuning aid
+  if (!on || !g.A_lo || !g.B_lo || g.C || !g.C_hi || !g.C_lo || g.bias || g.beta != 0.f) return false;
+  if (g.M < 2 * UG_BM || g.N < G2_BN || g.K >= 4096) return false;
+  const int64_t tiles128 = ceil_div(g.M, UG_BM) * ceil_div(g.N, 128) * batch * n_problems;
+  // threshold measured on whole operators (B200): > 200 tiles of 128 x 128 (d = 2048: 6.8 -> 4.9 ms, 3 x 768: 1.66 -> 1.54,
+  // 10 x 1024: 9.1 -> 7.0, 40 x 512: 6.1 -> 4.6 ms); at > 120 the single 1024^3 and 4 x 512^3 chains lose 15 %: below the
+  // threshold the 128-wide (split-K) tiles occupy the machine better.  OTK_GEMM_PAIR_MIN overrides (tuning aid).
+  static const int64_t min_tiles = [] { const char* e = getenv("OTK_GEMM_PAIR_MIN"); return e ? (int64_t)atoi(e) : (int64_t)200; }();
+  return tiles128 > min_tiles;
+}
+static int launch_gemm_pair(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, const int* ctrl,
+                            int ctrl_index, cudaStream_t st, const NsCtrlEval& ev) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OTK_CUDA(cudaFuncSetAttribute(umma_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    attr_set[dev] = true;
+  }
+  const int64_t total = ceil_div(a.p.M, 2 * UG_BM) * ceil_div(a.p.N, G2_BN) * batch * n_problems;
+  if (total > INT32_MAX / 2) return 0;
+  const int64_t pairs = total < sm_count() / 2 ? total : sm_count() / 2;
+  OTK_CUDA(launch_pdl(umma_gemm_pair_kernel, dim3((unsigned)(2 * pairs)), dim3(G2_THREADS), (size_t)G2_SMEM, st, 2, a.maps, b.maps,
+                      a.p, b.p, n_problems, (int)batch, ctrl, ctrl_index, ev));
+  OTK_LAUNCH_CHECK();
+  return 1;
+}
+
 template <int BN>
 static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_problems, int64_t batch, int ks, const int* ctrl,
                        int ctrl_index, cudaStream_t st, const NsCtrlEval& ev = NsCtrlEval{}) {
@@ -524,6 +768,13 @@ int gemm_umma_dual(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t
                    cudaStream_t st, const NsCtrlEval* eval) {
   const int n_problems = g1 ? 2 : 1;
   if (g1 && (g0.M != g1->M || g0.N != g1->N || g0.K != g1->K)) return 0;
+  if (pair_eligible(g0, batch, n_problems) && (!g1 || pair_eligible(*g1, batch, n_problems))) {
+    PreparedGemm a, b;
+    int r = prepare_gemm(g0, batch, 3, 128, st, &a);
+    if (r <= 0) return r;
+    if (g1) { r = prepare_gemm(*g1, batch, 3, 128, st, &b); if (r <= 0) return r; } else b = a;
+    if (a.p.b_mn_major == b.p.b_mn_major) return launch_gemm_pair(a, b, n_problems, batch, ctrl, ctrl_index, st, eval ? *eval : NsCtrlEval{});
+  }
   int bn, ks;
   pick_tile(g0.M, g0.N, g0.K, batch, n_problems, &bn, &ks);
   PreparedGemm a, b;
