@@ -735,6 +735,28 @@ def test_cfg4_conditional_transport_10x1024_vs_oracle(api, oracle):
     assert moved.dtype == torch.float32 and rel(moved, want_moved) < TOL_MATFUN
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,d", [(3, 776), (2, 1000), (24, 256)])
+def test_batched_operator_on_the_cta_pair_gemm_vs_oracle(L, d, oracle):
+    """Batched maps whose products run on the persistent CTA-pair tcgen05 GEMM (256 x 256 tiles; > 200 tiles of 128 x 128 per
+    launch), with widths that leave partial row / column tiles and a peer CTA whose B half is entirely out of range, against
+    the oracle operator `T = Cs^-1/2 (Cs^1/2 Ct Cs^1/2)^1/2 Cs^-1/2` (w2_utils.py:756-768) and W2^2 (w2_utils.py:40-80)."""
+    from ot_vae_lightning_b200 import kernels as K
+    g = torch.Generator().manual_seed(31 * L + d)
+
+    def spd(scale):
+        q, _ = torch.linalg.qr(torch.randn(L, d, d, generator=g, dtype=torch.float64))
+        ev = torch.logspace(0, -2, d, dtype=torch.float64) * scale
+        return (q * ev.unsqueeze(-2)) @ q.transpose(-1, -2)
+
+    cs, ct = spd(1.0), spd(1.7)
+    ms, mt = torch.randn(L, d, generator=g, dtype=torch.float64), torch.randn(L, d, generator=g, dtype=torch.float64)
+    T, w2 = K.transport_operator(cs.cuda(), ct.cuda(), mean_s=ms.cuda(), mean_t=mt.cuda())
+    want_T, _ = oracle.transport_operator_full(cs, ct, 0.0)
+    assert T.shape == (L, d, d) and rel(T, want_T) < TOL_MATFUN
+    assert rel(w2, oracle.w2_gaussian(ms, mt, cs, ct)) < TOL_MATFUN
+
+
 # ------------------------------------------------------------------------------------------------- dense Sinkhorn, all kernel variants
 
 @pytest.mark.parametrize("n,m,dt", [(1500, 4100, torch.float32), (700, 4099, torch.float32), (2048, 1024, torch.float32),
