@@ -53,14 +53,14 @@ __device__ __forceinline__ void umma_f16_ts_cg(uint32_t tmem_d, uint32_t tmem_a,
 
 // one pair of features of one latent: centre + scale (one FFMA each), split, pack; `chk` is poisoned (NaN) by any value
 // outside the FP16 range or non-finite
-__device__ __forceinline__ void split_pair(float x0, float x1, float s0, float s1, float n0, float n1, float& chk,
+__device__ __forceinline__ void split_pair(float x0, float x1, float s0, float s1, float n0, float n1, __half2& chk,
                                            uint32_t& hw, uint32_t& lw) {
   const float v0 = fmaf(x0, s0, n0), v1 = fmaf(x1, s1, n1);
   const __half2 h = __floats2half2_rn(v0, v1);                  // .x (low half) = the even feature
   const float2 hf = __half22float2(h);
   const float l0 = v0 - hf.x, l1 = v1 - hf.y;
-  chk = fmaf(l0, 0.f, fmaf(l1, 0.f, chk));
   const __half2 lo = __floats2half2_rn(l0, l1);
+  chk = __hfma2(lo, __float2half2_rn(0.f), chk);                            // one packed 0 * residual for the pair: +-inf / NaN -> NaN
   hw = *reinterpret_cast<const uint32_t*>(&h);
   lw = *reinterpret_cast<const uint32_t*>(&lo);
 }
@@ -192,7 +192,7 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const uint32_t row_off = (uint32_t)r * 128;
     const uint32_t ready_addr = CG == 2 ? map_to_cta(smem_u32(&ready_a[0]), 0) : smem_u32(&ready_a[0]);
     const uint32_t xbase = smem_u32(xraw);
-    float chk = 0.f;
+    __half2 chk = __float2half2_rn(0.f);
     int it = 0;
     for (int tile = group; tile < total_tiles; tile += n_groups) {
       const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
@@ -231,7 +231,7 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         if (lane == 0) mbar_arrive_cluster(ready_addr + sa * 8);
       }
     }
-    if (!(chk == 0.f)) atomicOr(overflow, 1);
+    if (!(__low2float(chk) == 0.f && __high2float(chk) == 0.f)) atomicOr(overflow, 1);
   } else {
     // ===== epilogue: TMEM -> / g_j + mean_t -> 32x32 swizzled staging tile -> TMA store (eight warps: two per TMEM lane
     // quarter, half of the tile's columns each) =====

@@ -72,9 +72,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // of two); `vsum` accumulates sum v (the caller divides by s); `chk` stays 0 unless a value left the FP16 range or was not
 // finite: then hi = inf, the residual v - hi is -inf / NaN and 0 * residual poisons chk - detection costs FMA-pipe slots
 // only.  FULL tiles need no row masking (features past `dim` are zero-filled by TMA and have c = 0).
-template <bool FULL>
+// (r2 late) The converters are issue-bound (~8 instructions per element), so the check rides on ONE packed HFMA2 per pair
+// (0 * lo of both halves at once) instead of two FFMAs, and SUM = false drops the two column-sum FADDs where the sums are
+// not needed (B converters, A converters of off-diagonal blocks).
+__device__ __forceinline__ bool chk_clean(__half2 chk) { return __low2float(chk) == 0.f && __high2float(chk) == 0.f; }
+template <bool FULL, bool SUM = true>
 __device__ __forceinline__ void split_rows32(uint32_t slab, int row0, int valid, uint32_t cc, uint32_t within, float s,
-                                             float ncs, float& vsum, float& chk, uint32_t* hw, uint32_t* lw) {
+                                             float ncs, float& vsum, __half2& chk, uint32_t* hw, uint32_t* lw) {
   using namespace ptx;
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
@@ -83,12 +87,12 @@ __device__ __forceinline__ void split_rows32(uint32_t slab, int row0, int valid,
     const float x1 = lds32(slab + (uint32_t)rb * 128 + ((cc ^ (uint32_t)(rb & 3)) * 32) + within);
     float v0 = fmaf(x0, s, ncs), v1 = fmaf(x1, s, ncs);
     if (!FULL) { v0 = ra < valid ? v0 : 0.f; v1 = rb < valid ? v1 : 0.f; }
-    vsum += v0 + v1;
+    if (SUM) vsum += v0 + v1;
     const __half2 h = __floats2half2_rn(v0, v1);                  // .x (low half) = the even row
     const float2 hf = __half22float2(h);
     const float l0 = v0 - hf.x, l1 = v1 - hf.y;
-    chk = fmaf(l0, 0.f, fmaf(l1, 0.f, chk));
     const __half2 lo = __floats2half2_rn(l0, l1);
+    chk = __hfma2(lo, __float2half2_rn(0.f), chk);                            // +-inf / NaN residual -> NaN
     hw[p] = *reinterpret_cast<const uint32_t*>(&h);
     lw[p] = *reinterpret_cast<const uint32_t*>(&lo);
   }
@@ -208,7 +212,7 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
     const uint32_t sw = (uint32_t)(col & 7);
     const float ncs = -c * s;
     double colsum = 0.0;
-    float chk = 0.f;
+    __half2 chk = __float2half2_rn(0.f);
 #ifdef OTK_SH_TIMING
     long long tw_a = 0, tw_x = 0, tw_b = 0, t_cv = 0, t_st = 0, t_all = clock64();
 #define SH_TICK(acc) { const long long t_now = clock64(); acc += t_now - t_prev; t_prev = t_now; }
@@ -271,7 +275,7 @@ stats_h_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict
     // the set's raw stage is idle from here on (its last tile has been read): park the column sums there, the CTA adds
     // the three sets up after the final barrier - one atomic per feature and CTA
     *reinterpret_cast<double*>(xa + cset * SH_RAW + col * 8) = colsum / (double)s;
-    if (!(chk == 0.f)) atomicOr(overflow, 1);                           // a value left the FP16 window, or NaN / inf input
+    if (!chk_clean(chk)) atomicOr(overflow, 1);                           // a value left the FP16 window, or NaN / inf input
   } else {
     // ===== epilogue: 4 warps (warp <-> TMEM lane quarter); second-stage fp32 accumulation in shared memory =====
     const int q = warp % 4;
@@ -508,7 +512,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
     const uint32_t slab0 = smem_u32(xa) + (uint32_t)q * SH_SLAB;
     const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + SH_ACOL0 + h2 * 16;
     const uint32_t ready_a_addr = CG == 2 ? map_to_cta(smem_u32(&ready_a[0]), 0) : smem_u32(&ready_a[0]);
-    float chk = 0.f;
+    __half2 chk = __float2half2_rn(0.f);
     int it = 0;
     for (int item = group; item < n_items; item += n_groups) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
@@ -518,6 +522,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
       const float c = in ? pivot[(int64_t)t.l * dim + col] : 0.f;
       const float s = in ? scale[(int64_t)t.l * dim + col] : 1.f;
       const float ncs = -c * s;
+      const bool diag = t.bi == t.bj;                     // the column sums are taken once per feature: on the diagonal blocks
       double colsum = 0.0;
       float vsum = 0.f;                                   // fp32 over at most four tiles (128 values), then fp64
       for (int kt = 0; kt < num_k; ++kt, ++it) {
@@ -528,8 +533,12 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         mbar_wait(&full_a[sx], (it / S2_XS) & 1);
 #ifndef OTK_SH_NOCONV
         uint32_t hw[16], lw[16];
-        if (valid == SH_BK) split_rows32<true>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
-        else split_rows32<false>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        if (valid == SH_BK) {
+          if (diag) split_rows32<true, true>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+          else split_rows32<true, false>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        } else {
+          split_rows32<false, true>(slab0 + sx * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        }
         tmem_st16u(ta0 + sa * 64, hw);
         tmem_st16u(ta0 + sa * 64 + 32, lw);
 #endif
@@ -541,9 +550,9 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ready_a_addr + sa * 8);
       }
-      if (t.bi == t.bj && in && num_k > 0) atomicAdd(&ws_sum[(int64_t)t.l * dim + col], colsum / (double)s);   // each feature once
+      if (diag && in && num_k > 0) atomicAdd(&ws_sum[(int64_t)t.l * dim + col], colsum / (double)s);   // each feature once
     }
-    if (!(chk == 0.f)) atomicOr(overflow, 1);
+    if (!chk_clean(chk)) atomicOr(overflow, 1);
   } else if (warp < 18) {
     // ===== B converters: thread <-> feature of block bj (row of the K-major planes), warp <-> (quarter, 32-row half) =====
     const int q = warp % 4, h2 = (warp - 10) / 4;
@@ -553,7 +562,8 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
     const uint32_t hb0 = smem_u32(xb) + (uint32_t)nloc * 128;
     const uint32_t sw = (uint32_t)(nloc & 7);
     const uint32_t ready_b_addr = CG == 2 ? map_to_cta(smem_u32(&ready_b[0]), 0) : smem_u32(&ready_b[0]);
-    float chk = 0.f, vsum = 0.f;
+    __half2 chk = __float2half2_rn(0.f);
+    float vsum = 0.f;                                     // unused (SUM = false)
     int it = 0;
     for (int item = group; item < n_items; item += n_groups) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
@@ -569,8 +579,8 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         mbar_wait(&full_b[sp], (it / S2_PB) & 1);
 #ifndef OTK_SH_NOCONV
         uint32_t hw[16], lw[16];
-        if (valid == SH_BK) split_rows32<true>(slab0 + sp * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
-        else split_rows32<false>(slab0 + sp * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        if (valid == SH_BK) split_rows32<true, false>(slab0 + sp * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        else split_rows32<false, false>(slab0 + sp * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
         // the planes overwrite the raw tile: every B converter must have read its share first
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint32_t hb = hb0 + sp * SH_BSTAGE;
@@ -586,7 +596,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         if (lane == 0) mbar_arrive_cluster(ready_b_addr + sp * 8);
       }
     }
-    if (!(chk == 0.f) || !(vsum == vsum)) atomicOr(overflow, 1);
+    if (!chk_clean(chk)) atomicOr(overflow, 1);
   } else if (warp < 22) {
     // ===== epilogue: TMEM accumulator of an item -> its partial-tile slot (thread <-> row of the block) =====
     const int q = warp % 4;
