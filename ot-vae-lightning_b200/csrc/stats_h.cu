@@ -398,6 +398,21 @@ __device__ __forceinline__ S2Item s2_decode(int item, int n_units, int upl, int 
 // all halve - the three things the single-CTA kernel is bound by (53 us of its 87 us per 65536 x 512 chunk is raw-tile
 // delivery alone).  Converters of both CTAs arrive on the leader's ready barriers, commits are multicast to both CTAs, each
 // CTA drains its own 128 x 256 accumulator (one accumulator: 256 of the 512 tensor-memory columns, the A ring has the rest).
+// -DOTK_SH_TIMING: per-role clock64 accounting of the wide kernel (where each warp role spends its cycles), printed by
+// the lanes 0 of one CTA at the end; compiled out otherwise.
+#ifdef OTK_SH_TIMING
+#define S2_T0 long long s2_prev = clock64(), s2_a = 0, s2_b = 0, s2_c = 0, s2_d = 0, s2_e = 0; const long long s2_start = s2_prev; int s2_n = 0;
+#define S2_TICK(acc) { const long long s2_now = clock64(); acc += s2_now - s2_prev; s2_prev = s2_now; }
+#define S2_REPORT(role, na, nb, nc, nd, ne) \
+  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && s2_n > 0) \
+    printf("cta %3d %-10s tiles %4d: total %6lld | " na " %5lld | " nb " %5lld | " nc " %5lld | " nd " %5lld | " ne " %5lld (clk per tile)\n", \
+           (int)blockIdx.x, role, s2_n, (clock64() - s2_start) / s2_n, s2_a / s2_n, s2_b / s2_n, s2_c / s2_n, s2_d / s2_n, s2_e / s2_n);
+#else
+#define S2_T0
+#define S2_TICK(acc)
+#define S2_REPORT(role, na, nb, nc, nd, ne)
+#endif
+
 template <int CG>
 __global__ void __launch_bounds__(S2_THREADS, 1)
 stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, const float* __restrict__ scale,
@@ -427,7 +442,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
   const int n_groups = CG == 2 ? gridDim.x / 2 : gridDim.x;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
-    for (int s = 0; s < S2_XS; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_ra[s], 8); }
+    for (int s = 0; s < S2_XS; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_ra[s], 16); }   // 8 A + 8 B converter warps
     for (int s = 0; s < S2_PB; ++s) mbar_init(&full_b[s], 1);
     for (int s = 0; s < S2_AS; ++s) { mbar_init(&ready_a[s], 8 * CG); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < S2_PB; ++s) { mbar_init(&ready_b[s], 8 * CG); mbar_init(&empty_b[s], 1); }
@@ -452,38 +467,63 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
     uint64_t* empty = side_b ? empty_b : empty_ra;
     const int depth = side_b ? S2_PB : S2_XS;
     int it = 0;
+    S2_T0
     for (int item = group; item < n_items; item += n_groups) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
       const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
       const int f0 = (side_b ? t.bj : t.bi) * BW + (int)rank * SH_T;
+      // Diagonal block (bi == bj): the B block IS the A block.  It is loaded once, into the A ring, and the B converters
+      // read it there; the B stage still cycles (its planes are written as usual), so its full barrier gets a plain
+      // arrival.  At d = 512 that is 4 instead of 6 raw blocks per row tile: the kernel is bound by raw-tile delivery
+      // (ablation builds: loads alone 44 us of the 71 us per 65536-row chunk).
+      const bool skip_load = side_b && t.bi == t.bj;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
         const int sx = it % depth;
+        S2_TICK(s2_b)
         mbar_wait(&empty[sx], ((it / depth) & 1) ^ 1);
+        S2_TICK(s2_a)
+#ifdef OTK_SH_TIMING
+        ++s2_n;
+#endif
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[sx], SH_RAW);
+          if (skip_load) {
+            mbar_arrive(&full[sx]);
+          } else {
+            mbar_arrive_expect_tx(&full[sx], SH_RAW);
 #pragma unroll
-          for (int sl = 0; sl < 4; ++sl)
-            tma_load_3d(ring + sx * SH_RAW + sl * SH_SLAB, &mapX, f0 + 32 * sl, t.r0 + kt * SH_BK, t.l, &full[sx]);
+            for (int sl = 0; sl < 4; ++sl)
+              tma_load_3d(ring + sx * SH_RAW + sl * SH_SLAB, &mapX, f0 + 32 * sl, t.r0 + kt * SH_BK, t.l, &full[sx]);
+          }
         }
         __syncwarp();
       }
     }
+    S2_REPORT(side_b ? "tma B" : "tma A", "wait empty", "issue", "-", "-", "-")
   } else if (warp == 1) {
     // ===== MMA issuer (the leader CTA of a pair issues for both) =====
     const uint32_t idesc = idesc_f16(BW, BW);
     int it = 0, n = 0;
+    S2_T0
     if (rank == 0)
     for (int item = group; item < n_items; item += n_groups, ++n) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
       const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
       const int a = n % S2_ACC;
+      S2_TICK(s2_d)
       mbar_wait(&acc_empty[a], ((n / S2_ACC) & 1) ^ 1);
+      S2_TICK(s2_a)
       tc_fence_after();
       const uint32_t acc = tmem_base + a * BW;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
         const int sp = it % S2_PB, sa = it % S2_AS;
+        S2_TICK(s2_d)
         mbar_wait(&ready_b[sp], (it / S2_PB) & 1);
+        S2_TICK(s2_b)
         mbar_wait(&ready_a[sa], (it / S2_AS) & 1);
+        S2_TICK(s2_c)
+#ifdef OTK_SH_TIMING
+        ++s2_n;
+#endif
         tc_fence_after();
         const uint32_t bb = smem_u32(xb + sp * SH_BSTAGE);
         const uint32_t ab = tmem_base + SH_ACOL0 + sa * 64;
@@ -505,6 +545,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         __syncwarp();
       }
     }
+    S2_REPORT("mma", "wait acc_empty", "wait ready_b", "wait ready_a", "issue", "-")
   } else if (warp < 10) {
     // ===== A converters: thread <-> feature of block bi (TMEM lane q*32 + lane), warp <-> (lane quarter, 32-row half) =====
     const int q = warp % 4, h2 = (warp - 2) / 4;
@@ -514,6 +555,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
     const uint32_t ready_a_addr = CG == 2 ? map_to_cta(smem_u32(&ready_a[0]), 0) : smem_u32(&ready_a[0]);
     __half2 chk = __float2half2_rn(0.f);
     int it = 0;
+    S2_T0
     for (int item = group; item < n_items; item += n_groups) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
       const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
@@ -528,9 +570,15 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
       for (int kt = 0; kt < num_k; ++kt, ++it) {
         const int sx = it % S2_XS, sa = it % S2_AS;
         const int valid = min(SH_BK, t.r1 - (t.r0 + kt * SH_BK));
+        S2_TICK(s2_e)
         mbar_wait(&empty_a[sa], ((it / S2_AS) & 1) ^ 1);
+        S2_TICK(s2_a)
         tc_fence_after();
         mbar_wait(&full_a[sx], (it / S2_XS) & 1);
+        S2_TICK(s2_b)
+#ifdef OTK_SH_TIMING
+        ++s2_n;
+#endif
 #ifndef OTK_SH_NOCONV
         uint32_t hw[16], lw[16];
         if (valid == SH_BK) {
@@ -542,10 +590,12 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         tmem_st16u(ta0 + sa * 64, hw);
         tmem_st16u(ta0 + sa * 64 + 32, lw);
 #endif
-        if ((kt & 3) == 3 || kt == num_k - 1) { colsum += (double)vsum; vsum = 0.f; }
+        if (diag && ((kt & 3) == 3 || kt == num_k - 1)) { colsum += (double)vsum; vsum = 0.f; }   // DADD: 6 % of the kernel's stall samples when unconditional
         __syncwarp();
+        S2_TICK(s2_c)
         if (lane == 0) mbar_arrive(&empty_ra[sx]);
         tmem_st_wait();
+        S2_TICK(s2_d)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ready_a_addr + sa * 8);
@@ -553,18 +603,21 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
       if (diag && in && num_k > 0) atomicAdd(&ws_sum[(int64_t)t.l * dim + col], colsum / (double)s);   // each feature once
     }
     if (!chk_clean(chk)) atomicOr(overflow, 1);
+    if (q == 0 && h2 == 0) { S2_REPORT("conv A", "wait empty_a", "wait full_a", "convert", "tmem st-wait", "arrive+loop") }
   } else if (warp < 18) {
     // ===== B converters: thread <-> feature of block bj (row of the K-major planes), warp <-> (quarter, 32-row half) =====
     const int q = warp % 4, h2 = (warp - 10) / 4;
     const int nloc = q * 32 + lane;
     const uint32_t cc = (uint32_t)lane / 8, within = (uint32_t)(lane % 8) * 4;
     const uint32_t slab0 = smem_u32(xb) + (uint32_t)q * SH_SLAB;
+    const uint32_t slab0_a = smem_u32(xa) + (uint32_t)q * SH_SLAB;      // diagonal blocks: the raw tile sits in the A ring
     const uint32_t hb0 = smem_u32(xb) + (uint32_t)nloc * 128;
     const uint32_t sw = (uint32_t)(nloc & 7);
     const uint32_t ready_b_addr = CG == 2 ? map_to_cta(smem_u32(&ready_b[0]), 0) : smem_u32(&ready_b[0]);
     __half2 chk = __float2half2_rn(0.f);
     float vsum = 0.f;                                     // unused (SUM = false)
     int it = 0;
+    S2_T0
     for (int item = group; item < n_items; item += n_groups) {
       const S2Item t = s2_decode(item, n_units, upl, nB, seg_len, row_lo, row_hi);
       const int num_k = (t.r1 - t.r0 + SH_BK - 1) / SH_BK;
@@ -573,16 +626,33 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
       const float c = in ? pivot[(int64_t)t.l * dim + col] : 0.f;
       const float s = in ? scale[(int64_t)t.l * dim + col] : 1.f;
       const float ncs = -c * s;
+      const bool diag = t.bi == t.bj;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
-        const int sp = it % S2_PB;
+        const int sp = it % S2_PB, sx = it % S2_XS;
         const int valid = min(SH_BK, t.r1 - (t.r0 + kt * SH_BK));
+        S2_TICK(s2_e)
         mbar_wait(&full_b[sp], (it / S2_PB) & 1);
+        S2_TICK(s2_a)
+#ifdef OTK_SH_TIMING
+        ++s2_n;
+#endif
+        // The A ring's stage of this tile is released by the A AND the B converters (its barrier counts all 16 warps, so
+        // every tile needs both arrivals): wait until the tile has landed there - that also pins the barrier's phase.
+        mbar_wait(&full_a[sx], (it / S2_XS) & 1);
+        S2_TICK(s2_b)
+        const uint32_t src = diag ? slab0_a + sx * SH_RAW : slab0 + sp * SH_RAW;
 #ifndef OTK_SH_NOCONV
         uint32_t hw[16], lw[16];
-        if (valid == SH_BK) split_rows32<true, false>(slab0 + sp * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
-        else split_rows32<false, false>(slab0 + sp * SH_RAW, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        if (valid == SH_BK) split_rows32<true, false>(src, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+        else split_rows32<false, false>(src, h2 * 32, valid, cc, within, s, ncs, vsum, chk, hw, lw);
+#endif
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_ra[sx]);                 // values are in registers
+        S2_TICK(s2_c)
+#ifndef OTK_SH_NOCONV
         // the planes overwrite the raw tile: every B converter must have read its share first
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        S2_TICK(s2_d)
         const uint32_t hb = hb0 + sp * SH_BSTAGE;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -597,6 +667,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
       }
     }
     if (!chk_clean(chk)) atomicOr(overflow, 1);
+    if (q == 0 && h2 == 0) { S2_REPORT("conv B", "wait full_b", "wait full_a", "convert", "bar.sync", "sts+arrive") }
   } else if (warp < 22) {
     // ===== epilogue: TMEM accumulator of an item -> its partial-tile slot (thread <-> row of the block) =====
     const int q = warp % 4;
