@@ -17,6 +17,7 @@
 #include <cuda_fp16.h>
 
 #include "apply_umma.cuh"
+#include "role_timing.cuh"
 #include "otk_ptx.cuh"
 #include "tensormap.cuh"
 
@@ -117,14 +118,18 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     // second step (warp-uniform loop, one elected lane issues) =====
     const uint32_t full_t_leader0 = CG == 2 ? map_to_cta(smem_u32(&full_t[0]), 0) : smem_u32(&full_t[0]);
     int it = 0, jt = 0;
+    S2_T0
     for (int tile = group; tile < total_tiles; tile += n_groups) {
       const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
       const int m0 = (rem / n_tiles) * (HP_BM * CG) + (int)rank * HP_BM;
       const int n0 = (rem % n_tiles) * BN + (int)rank * 128;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
+        S2_COUNT
+        S2_TICK(s2_c)
         if ((kt & 1) == 0) {
           const int st = jt % HP_TS;
           mbar_wait(&empty_t[st], ((jt / HP_TS) & 1) ^ 1);
+          S2_TICK(s2_a)
           uint8_t* td = tpl + st * HP_TSTAGE;
           if (elect_one()) {
             if constexpr (CG == 1) {
@@ -142,7 +147,9 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
           ++jt;
         }
         const int sx = it % HP_XS;
+        S2_TICK(s2_c)
         mbar_wait(&empty_x[sx], ((it / HP_XS) & 1) ^ 1);
+        S2_TICK(s2_b)
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_x[sx], HP_XTILE);
           tma_load_3d(xraw + sx * HP_XTILE, &mapX, kt * HP_BK, m0, l, &full_x[sx]);
@@ -150,20 +157,28 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         __syncwarp();
       }
     }
+    S2_REPORT("tma", "wait empty_t", "wait empty_x", "issue", "-", "-")
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA of the pair only): warp-uniform loop, one elected lane issues =====
     if (rank == 0) {
       const uint32_t idesc = idesc_f16(HP_BM * CG, BN);
       int it = 0, ti = 0, jt = 0;
+      S2_T0
       for (int tile = group; tile < total_tiles; tile += n_groups, ++ti) {
         const int a = ti % NACC;
+        S2_TICK(s2_d)
         mbar_wait(&acc_empty[a], ((ti / NACC) & 1) ^ 1);
+        S2_TICK(s2_a)
         tc_fence_after();
         const uint32_t acc = tmem_base + a * BN;
         for (int kt = 0; kt < num_k; ++kt, ++it) {
           const int js = jt + (kt >> 1), st = js % HP_TS, sa = it % HP_AS;
+          S2_COUNT
+          S2_TICK(s2_d)
           if ((kt & 1) == 0) mbar_wait(&full_t[st], (js / HP_TS) & 1);
+          S2_TICK(s2_b)
           mbar_wait(&ready_a[sa], (it / HP_AS) & 1);
+          S2_TICK(s2_c)
           tc_fence_after();
           const uint32_t tb = smem_u32(tpl + st * HP_TSTAGE) + (uint32_t)(kt & 1) * 64;
           const uint32_t ab = tmem_base + HP_ACOL0 + sa * 32;
@@ -184,6 +199,7 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         }
         jt += num_t;
       }
+      S2_REPORT("mma", "wait acc_empty", "wait full_t", "wait ready_a", "issue", "-")
     }
   } else if (warp < 10) {
     // ===== converters: thread <-> latent row r (TMEM lane r); warps 2-5 take features 0-15 of the step, 6-9 take 16-31
@@ -194,6 +210,7 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const uint32_t xbase = smem_u32(xraw);
     __half2 chk = __float2half2_rn(0.f);
     int it = 0;
+    S2_T0
     for (int tile = group; tile < total_tiles; tile += n_groups) {
       const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
       const int m0 = (rem / n_tiles) * (HP_BM * CG) + (int)rank * HP_BM;
@@ -202,7 +219,10 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       const float* nl = nmsk + (int64_t)l * dim;
       for (int kt = 0; kt < num_k; ++kt, ++it) {
         const int sx = it % HP_XS, sa = it % HP_AS;
+        S2_COUNT
+        S2_TICK(s2_e)
         mbar_wait(&full_x[sx], (it / HP_XS) & 1);
+        S2_TICK(s2_a)
         float4 x[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -219,18 +239,22 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
           split_pair(x[c].z, x[c].w, s4.z, s4.w, n4.z, n4.w, chk, hw[2 * c + 1], lw[2 * c + 1]);
         }
         __syncwarp();
+        S2_TICK(s2_b)
         if (lane == 0) mbar_arrive(&empty_x[sx]);                 // raw tile consumed (values are in registers)
         mbar_wait(&empty_a[sa], ((it / HP_AS) & 1) ^ 1);
+        S2_TICK(s2_c)
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + HP_ACOL0 + sa * 32 + half * 8;
         tmem_st8u(ta, hw);
         tmem_st8u(ta + 16, lw);
         tmem_st_wait();
+        S2_TICK(s2_d)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ready_addr + sa * 8);
       }
     }
+    if (warp == 2) { S2_REPORT("convert", "wait full_x", "convert", "wait empty_a", "tmem st", "arrive+loop") }
     if (!(__low2float(chk) == 0.f && __high2float(chk) == 0.f)) atomicOr(overflow, 1);
   } else {
     // ===== epilogue: TMEM -> / g_j + mean_t -> 32x32 swizzled staging tile -> TMA store (eight warps: two per TMEM lane
@@ -240,6 +264,7 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const uint32_t stage0 = smem_u32(outb) + (uint32_t)(warp - 10) * 2 * HP_OUT;
     const uint32_t acc_empty_addr = CG == 2 ? map_to_cta(smem_u32(&acc_empty[0]), 0) : smem_u32(&acc_empty[0]);
     int ti = 0, nstore = 0;
+    S2_T0
     for (int tile = group; tile < total_tiles; tile += n_groups, ++ti) {
       const int l = tile / tiles_per_l, rem = tile % tiles_per_l;
       const int m0 = (rem / n_tiles) * (HP_BM * CG) + (int)rank * HP_BM + q * 32;
@@ -247,13 +272,17 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       const int a = ti % NACC;
       const float* mt = mean_t + (int64_t)l * dim;
       const float* ig = inv_g + (int64_t)l * dim;
+      S2_COUNT
+      S2_TICK(s2_e)
       mbar_wait(&acc_full[a], (ti / NACC) & 1);
+      S2_TICK(s2_a)
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < HC; c0 += 32, ++nstore) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + half * HC + c0, v);
         tmem_ld_wait();
+        S2_TICK(s2_b)
         if (c0 + 32 == HC) {                                      // this warp's share is read: hand the accumulator back
           tc_fence_before();
           __syncwarp();
@@ -262,6 +291,7 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         const uint32_t buf = stage0 + (uint32_t)(nstore & 1) * HP_OUT;
         if (elect_one()) tma_store_wait_read<1>();                // the store issued two chunks ago has read this buffer
         __syncwarp();
+        S2_TICK(s2_c)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int n = n0 + c0 + c * 4;
@@ -279,8 +309,10 @@ apply_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             tma_store_commit();
           }
         }
+        S2_TICK(s2_d)
       }
     }
+    if (warp == 10) { S2_REPORT("epilogue", "wait acc_full", "tmem ld", "store-buffer wait", "scale+sts+store", "loop") }
     if (elect_one()) tma_store_wait_all<0>();
     __syncwarp();
   }

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_fp16.h>
+#include "role_timing.cuh"
 
 #include "otk_ptx.cuh"
 #include "stats_umma.cuh"
@@ -398,21 +399,6 @@ __device__ __forceinline__ S2Item s2_decode(int item, int n_units, int upl, int 
 // all halve - the three things the single-CTA kernel is bound by (53 us of its 87 us per 65536 x 512 chunk is raw-tile
 // delivery alone).  Converters of both CTAs arrive on the leader's ready barriers, commits are multicast to both CTAs, each
 // CTA drains its own 128 x 256 accumulator (one accumulator: 256 of the 512 tensor-memory columns, the A ring has the rest).
-// -DOTK_SH_TIMING: per-role clock64 accounting of the wide kernel (where each warp role spends its cycles), printed by
-// the lanes 0 of one CTA at the end; compiled out otherwise.
-#ifdef OTK_SH_TIMING
-#define S2_T0 long long s2_prev = clock64(), s2_a = 0, s2_b = 0, s2_c = 0, s2_d = 0, s2_e = 0; const long long s2_start = s2_prev; int s2_n = 0;
-#define S2_TICK(acc) { const long long s2_now = clock64(); acc += s2_now - s2_prev; s2_prev = s2_now; }
-#define S2_REPORT(role, na, nb, nc, nd, ne) \
-  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && s2_n > 0) \
-    printf("cta %3d %-10s tiles %4d: total %6lld | " na " %5lld | " nb " %5lld | " nc " %5lld | " nd " %5lld | " ne " %5lld (clk per tile)\n", \
-           (int)blockIdx.x, role, s2_n, (clock64() - s2_start) / s2_n, s2_a / s2_n, s2_b / s2_n, s2_c / s2_n, s2_d / s2_n, s2_e / s2_n);
-#else
-#define S2_T0
-#define S2_TICK(acc)
-#define S2_REPORT(role, na, nb, nc, nd, ne)
-#endif
-
 template <int CG>
 __global__ void __launch_bounds__(S2_THREADS, 1)
 stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ pivot, const float* __restrict__ scale,
@@ -482,9 +468,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         S2_TICK(s2_b)
         mbar_wait(&empty[sx], ((it / depth) & 1) ^ 1);
         S2_TICK(s2_a)
-#ifdef OTK_SH_TIMING
-        ++s2_n;
-#endif
+        S2_COUNT
         if (elect_one()) {
           if (skip_load) {
             mbar_arrive(&full[sx]);
@@ -521,9 +505,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         S2_TICK(s2_b)
         mbar_wait(&ready_a[sa], (it / S2_AS) & 1);
         S2_TICK(s2_c)
-#ifdef OTK_SH_TIMING
-        ++s2_n;
-#endif
+        S2_COUNT
         tc_fence_after();
         const uint32_t bb = smem_u32(xb + sp * SH_BSTAGE);
         const uint32_t ab = tmem_base + SH_ACOL0 + sa * 64;
@@ -576,9 +558,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         tc_fence_after();
         mbar_wait(&full_a[sx], (it / S2_XS) & 1);
         S2_TICK(s2_b)
-#ifdef OTK_SH_TIMING
-        ++s2_n;
-#endif
+        S2_COUNT
 #ifndef OTK_SH_NOCONV
         uint32_t hw[16], lw[16];
         if (valid == SH_BK) {
@@ -633,9 +613,7 @@ stats_h2_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restric
         S2_TICK(s2_e)
         mbar_wait(&full_b[sp], (it / S2_PB) & 1);
         S2_TICK(s2_a)
-#ifdef OTK_SH_TIMING
-        ++s2_n;
-#endif
+        S2_COUNT
         // The A ring's stage of this tile is released by the A AND the B converters (its barrier counts all 16 warps, so
         // every tile needs both arrivals): wait until the tile has landed there - that also pins the barrier's phase.
         mbar_wait(&full_a[sx], (it / S2_XS) & 1);
