@@ -714,7 +714,7 @@ static int launch_gemm(const PreparedGemm& a, const PreparedGemm& b, int n_probl
                        int ctrl_index, cudaStream_t st, const NsCtrlEval& ev = NsCtrlEval{}) {
   if constexpr (BN / 4 >= 32) { if (ks == 4) return launch_gemm_ks<BN, 4>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev); }
   if (ks == 4) ks = 2;                            // a share is at least one 32-column chunk
-  if (ks == 2) return launch_gemm_ks<BN, 2>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev);
+  if constexpr (BN / 2 >= 32) { if (ks == 2) return launch_gemm_ks<BN, 2>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev); }
   return launch_gemm_ks<BN, 1>(a, b, n_problems, batch, ctrl, ctrl_index, st, ev);
 }
 
@@ -739,9 +739,11 @@ static void pick_tile(int64_t M, int64_t N, int64_t K, int64_t batch, int n_prob
     const int bn = forced / 10, ks = forced % 10;
     if ((bn == 64 || bn == 128) && (ks == 1 || ks == 2 || ks == 4) && bn / ks >= 32 && num_k >= 2 * ks) { *bn_out = bn; *ks_out = ks; return; }
   }
+  static const bool narrow_ok = [] { const char* e = getenv("OTK_GEMM_BN32"); return !(e && e[0] == '0'); }();   // tuning aid
   int best_bn = 128, best_ks = 1;
   int64_t best_cost = INT64_MAX;
-  for (int bn : {128, 64}) {
+  for (int bn : {128, 64, 32}) {
+    if (bn == 32 && (N > 256 || !narrow_ok)) continue;   // 32-wide tiles: only for the smallest products (one epilogue chunk per CTA)
     const int64_t ctas = ceil_div(M, UG_BM) * ceil_div(N, bn) * batch * n_problems;
     for (int ks : {1, 2, 4}) {
       if (ks > 1 && (!split_ok || num_k < 4 * ks || bn / ks < 32)) continue;
@@ -760,6 +762,7 @@ int gemm_umma_try(const GemmArgs<float>& g, int64_t batch, int passes, cudaStrea
   PreparedGemm a;
   int r = prepare_gemm(g, batch, passes, bn, st, &a);
   if (r <= 0) return r;
+  if (bn == 32) return launch_gemm<32>(a, a, 1, batch, ks, nullptr, 0, st);
   return bn == 64 ? launch_gemm<64>(a, a, 1, batch, ks, nullptr, 0, st) : launch_gemm<128>(a, a, 1, batch, ks, nullptr, 0, st);
 }
 
@@ -782,6 +785,7 @@ int gemm_umma_dual(const GemmArgs<float>& g0, const GemmArgs<float>* g1, int64_t
   if (r <= 0) return r;
   if (g1) { r = prepare_gemm(*g1, batch, 3, bn, st, &b); if (r <= 0) return r; } else b = a;
   const NsCtrlEval ev = eval ? *eval : NsCtrlEval{};
+  if (bn == 32) return launch_gemm<32>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st, ev);
   return bn == 64 ? launch_gemm<64>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st, ev)
                   : launch_gemm<128>(a, b, n_problems, batch, ks, ctrl, ctrl_index, st, ev);
 }
