@@ -288,8 +288,13 @@ int otk_cost_matrix(const float* x, const float* y, int64_t N, int64_t M, int64_
  * kmean_iteration, ot/distribution_models/base.py:206-253; CodebookModel.energy, codebook_model.py:155-160) without the
  * [B, K] energy / one-hot matrices: index[l,b] = argmin_k |x[l,b] - codebook[l,k]|_2 (first index on ties),
  * weights_sum[l,k] = number of samples assigned to k, samples_sum[l,k,:] = their sum (both overwritten, dtype buf_dtype).
- *   x [L,B,dim], codebook [L,K,dim] fp32; index int64 [L,B] or NULL; weights_sum / samples_sum both given or both NULL. */
+ *   x [L,B,dim], codebook [L,K,dim] fp32; index int64 [L,B] or NULL; weights_sum / samples_sum both given or both NULL.
+ * otk_kmeans_assign_workspace_bytes: the minimum (64 x 64 FFMA distance tiles).  With otk_kmeans_workspace_bytes(L, B, K,
+ * dim) - room for a chunk of the score matrix that stays in L2 and for the TF32 hi/lo planes - problems with B, K >= 256,
+ * B * K >= 2^22, dim >= 192, dim % 4 == 0, K % 4 == 0 run the contraction x . codebook^T on tcgen05 (3xTF32) chunk by chunk and find
+ * the nearest codeword with one pass over the chunk (the [B, K] matrix never exists in HBM-resident form). */
 size_t otk_kmeans_assign_workspace_bytes(int64_t L, int64_t B, int64_t K);
+size_t otk_kmeans_workspace_bytes(int64_t L, int64_t B, int64_t K, int64_t dim);
 int otk_kmeans_assign(const float* x, int64_t L, int64_t B, int64_t K, int64_t dim, const float* codebook,
                       int64_t* index, void* weights_sum, void* samples_sum, int buf_dtype, void* workspace,
                       size_t workspace_bytes, otk_stream_t stream);

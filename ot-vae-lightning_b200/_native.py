@@ -78,6 +78,7 @@ SIGNATURES = {
     "otk_cost_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_cost_matrix": (_int, [_ptr, _ptr, _i64, _i64, _i64, _int, _dbl, _ptr, _ptr, _sz, _ptr]),
     "otk_kmeans_assign_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "otk_kmeans_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "otk_kmeans_assign": (_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
     "otk_microbench_peak": (_int, [_int, C.POINTER(_dbl), _ptr]),
     "otk_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),

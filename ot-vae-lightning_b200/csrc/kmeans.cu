@@ -4,6 +4,7 @@
 // 1 / (|x - c|_2 + 1e-8) of CodebookModel.energy (codebook_model.py:155-160) in 'argmax' mode: softmax is monotone and the
 // energy is a decreasing function of the distance, so the one-hot weights select argmin_k |x_b - c_k| (first index on
 // ties, as torch.argmax), `weights.sum(-2)` is the per-codeword count and `weights^T @ samples` the per-codeword sum.
+#include "gemm.cuh"
 #include "otk_common.cuh"
 
 namespace otk {
@@ -89,6 +90,34 @@ km_nearest_kernel(const float* __restrict__ x, const float* __restrict__ cb, con
   }
 }
 
+// tensor-core path: `scores` [rows, K] holds -2 x_b . c_k + |c_k|^2 (epilogue of the tcgen05 product); one warp per row
+// finds min_k of (bits(max(|x_b|^2 + score, 0)) << 32 | k) - the key of km_nearest_kernel, so ties resolve identically
+__global__ void km_rowmin_kernel(const float* __restrict__ scores, const float* __restrict__ nx, int64_t rows, int64_t K,
+                                 unsigned long long* __restrict__ best) {
+  const int lane = threadIdx.x % 32;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  if (row >= rows) return;
+  const float4* p = reinterpret_cast<const float4*>(scores + row * K);
+  const float nxi = nx[row];
+  unsigned long long m = ~0ull;
+  for (int64_t c = lane; c < K / 4; c += 32) {
+    const float4 v = p[c];
+    const float s4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sq = fmaxf(nxi + s4[j], 0.f);
+      const unsigned long long key = ((unsigned long long)__float_as_uint(sq) << 32) | (unsigned long long)(4 * c + j);
+      m = key < m ? key : m;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long w = __shfl_xor_sync(0xffffffffu, m, o);
+    m = w < m ? w : m;
+  }
+  if (lane == 0) best[row] = m;
+}
+
 // one warp per sample: index out, count and feature sums of its codeword (atomics in the buffer dtype)
 __global__ void km_scatter_kernel(const float* __restrict__ x, const unsigned long long* __restrict__ best, int64_t L, int64_t B,
                                   int64_t K, int64_t d, int64_t* __restrict__ index, void* wsum, void* ssum, int dt) {
@@ -118,6 +147,27 @@ extern "C" size_t otk_kmeans_assign_workspace_bytes(int64_t L, int64_t B, int64_
   return align_up((size_t)L * B * 8, 256) + align_up((size_t)L * B * 4, 256) + align_up((size_t)L * K * 4, 256) + 1024;
 }
 
+// tensor-core path: rows per chunk such that the fp32 score chunk [rows, K] (48 MB) stays resident in the 126 MB L2
+// between the product that writes it and the row pass that reads it
+constexpr size_t KM_SCORE_BYTES = (size_t)48 << 20;
+static int64_t km_chunk_rows(int64_t B, int64_t K) {
+  int64_t rc = (int64_t)(KM_SCORE_BYTES / 4) / K / 128 * 128;
+  if (rc < 128) rc = 128;
+  return rc < B ? rc : B;
+}
+static bool km_umma_eligible(const float* x, const float* cb, int64_t B, int64_t K, int64_t d) {
+  static const bool on = [] { const char* e = getenv("OTK_KMEANS_TC"); return !(e && e[0] == '0'); }();   // tuning aid
+  // measured (B200): 4096 x 8192, d = 256: 0.90 -> 0.48 ms; at d = 128 the product's one-row-per-thread epilogue costs what the
+  // short contraction saves (65536 x 8192: 5.3 ms on the FFMA tiles, 5.7 ms here), so narrow codewords stay on the FFMA tiles
+  return on && B >= 256 && K >= 256 && d >= 192 && d % 4 == 0 && K % 4 == 0 && B * K >= ((int64_t)1 << 22) &&
+         reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(cb) % 16 == 0;
+}
+extern "C" size_t otk_kmeans_workspace_bytes(int64_t L, int64_t B, int64_t K, int64_t dim) {
+  const int64_t rc = km_chunk_rows(B, K);
+  return otk_kmeans_assign_workspace_bytes(L, B, K) + align_up((size_t)rc * K * 4, 256) +
+         align_up((size_t)2 * (rc + K) * dim * 4, 256) + 512;
+}
+
 extern "C" int otk_kmeans_assign(const float* x, int64_t L, int64_t B, int64_t K, int64_t dim, const float* codebook,
                                  int64_t* index, void* weights_sum, void* samples_sum, int buf_dtype, void* workspace,
                                  size_t workspace_bytes, otk_stream_t stream) {
@@ -145,8 +195,42 @@ extern "C" int otk_kmeans_assign(const float* x, int64_t L, int64_t B, int64_t K
   const int64_t k_per_cta = ceil_div(k_tiles, splits) * KM_T;
   dim3 grid((unsigned)ceil_div(K, k_per_cta), (unsigned)row_tiles, (unsigned)L);
   OTK_REQUIRE(grid.y <= 65535, "kmeans_assign: batch too large (split it)");
-  km_nearest_kernel<<<grid, 256, 0, st>>>(x, codebook, nx, nc, B, K, dim, k_per_cta, best);
-  OTK_LAUNCH_CHECK();
+  // tensor cores when the caller brought the larger workspace: per leading index and row chunk, scores = -2 x . c^T + |c|^2
+  // (3xTF32 product, bias epilogue), then one row pass; a tail of < 64 rows (and anything the product declines) takes the
+  // FFMA tiles
+  bool done = false;
+  if (km_umma_eligible(x, codebook, B, K, dim) && workspace_bytes >= otk_kmeans_workspace_bytes(L, B, K, dim)) {
+    const int64_t rc = km_chunk_rows(B, K);
+    float* scores = ar.take<float>((size_t)rc * K);
+    float* planes = ar.take<float>((size_t)2 * (rc + K) * dim);
+    done = ar.ok();
+    for (int64_t l = 0; l < L && done; ++l) {
+      for (int64_t r0 = 0; r0 < B && done; r0 += rc) {
+        const int64_t rows = B - r0 < rc ? B - r0 : rc;
+        const float* xc = x + (l * B + r0) * dim;
+        if (rows >= 64) {
+          GemmArgs<float> g = nt_args(xc, codebook + l * K * dim, scores, rows, K, dim, dim, dim, K, 0, 0, 0, -2.f, 0.f);
+          g.bias = nc + l * K;
+          g.scratch = planes;
+          const int r = gemm_umma_try(g, 1, 3, st);
+          if (r < 0) return r;
+          if (r == 0) { done = false; break; }          // declined: redo everything with the FFMA tiles below
+          km_rowmin_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(scores, nx + l * B + r0, rows, K, best + l * B + r0);
+          count_launch(1);
+        } else {
+          dim3 tail((unsigned)ceil_div(K, k_per_cta), (unsigned)ceil_div(rows, KM_T), 1);
+          km_nearest_kernel<<<tail, 256, 0, st>>>(xc, codebook + l * K * dim, nx + l * B + r0, nc + l * K, rows, K, dim,
+                                                   k_per_cta, best + l * B + r0);
+        }
+        OTK_LAUNCH_CHECK();
+      }
+    }
+    if (!done) OTK_CUDA(cudaMemsetAsync(best, 0xff, (size_t)L * B * 8, st));   // partial results of a declined attempt
+  }
+  if (!done) {
+    km_nearest_kernel<<<grid, 256, 0, st>>>(x, codebook, nx, nc, B, K, dim, k_per_cta, best);
+    OTK_LAUNCH_CHECK();
+  }
   if (samples_sum) {
     OTK_CUDA(cudaMemsetAsync(samples_sum, 0, (size_t)L * K * dim * dtype_size(buf_dtype), st));
     OTK_CUDA(cudaMemsetAsync(weights_sum, 0, (size_t)L * K * dtype_size(buf_dtype), st));

@@ -593,7 +593,7 @@ def kmeans_assign(x: Tensor, codebook: Tensor, want_index: bool = True, want_sum
     ssum = torch.empty(*lead, Kc, d, dtype=dt, device=dev) if want_sums else None
     lib = N.load()
     with torch.cuda.device(dev):
-        ws = N.workspace(lib.otk_kmeans_assign_workspace_bytes(L, B, Kc), dev)
+        ws = N.workspace(lib.otk_kmeans_workspace_bytes(L, B, Kc, d), dev)
         st = lib.otk_kmeans_assign(N.ptr(xd), L, B, Kc, d, N.ptr(cd), N.ptr(index), N.ptr(wsum), N.ptr(ssum), N.dtype_code(dt),
                                    N.ptr(ws), ws.numel(), N.stream_ptr(dev))
     N.check(st, "otk_kmeans_assign")

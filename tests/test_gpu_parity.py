@@ -865,12 +865,14 @@ def test_strided_token_latents_are_transported_in_place(api):
 
 # ------------------------------------------------------------------------------------------------- f2: codebook k-means kernel
 
-@pytest.mark.parametrize("B,K,d,lead", [(1000, 1024, 64, ()), (512, 8192, 128, ()), (250, 48, 20, (3,)), (77, 6, 8, ())])
+@pytest.mark.parametrize("B,K,d,lead", [(1000, 1024, 64, ()), (512, 8192, 128, ()), (250, 48, 20, (3,)), (77, 6, 8, ()),
+                                        (3112, 4096, 256, ()), (2100, 2048, 192, (2,))])
 def test_kmeans_assign_kernel_vs_oracle(oracle, B, K, d, lead):
     """`otk_kmeans_assign` (nearest codeword + per-codeword counts / sums, no [B, K] matrices) against the oracle's
     energy -> softmax -> one-hot -> weights^T @ samples (reference base.py:206-253) at codebook sizes up to the reference's
     largest configuration (K = 8192, configs/dad/defaults.yaml:70).  Samples sit near codewords, so the arg-min does not
-    hinge on round-off."""
+    hinge on round-off.  Cases with B * K >= 2^22 and d >= 192 take the tcgen05 contraction (row chunks of the score matrix; 3112
+    rows at K = 4096 = one 3072-row chunk + a 40-row tail on the FFMA tiles), the others the FFMA tiles."""
     from ot_vae_lightning_b200 import kernels as K_
     g = torch.Generator().manual_seed(B + K)
     book = torch.randn(*lead, K, d, generator=g)
