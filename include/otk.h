@@ -84,6 +84,15 @@ int otk_stats_update_f64(const double* x, int64_t L, int64_t rows, int64_t dim, 
                          void* sum_cov, int buf_dtype, void* workspace, size_t workspace_bytes,
                          otk_stream_t stream);
 
+/* TransportOperator.update(source_samples, target_samples) (ot/transport/base.py: the two GaussianModel.update calls of
+ * one batch, gaussian_model.py:99-108) as one call: x_a -> buffers a, x_b -> buffers b, both [rows, dim] fp32 with the same
+ * row stride, one model each (no leading shape), same decay and buffer dtypes.  Batches in the latency regime (rows <= 256)
+ * take ONE launch for both models; larger ones run the two updates back to back.  workspace as otk_stats_update (L = 1). */
+int otk_stats_update_pair(const float* x_a, const float* x_b, int64_t rows, int64_t dim, int64_t row_stride,
+                          double decay, void* n_obs_a, void* sum_a, void* sum_cov_a, void* n_obs_b, void* sum_b,
+                          void* sum_cov_b, int n_dtype, int buf_dtype, void* workspace, size_t workspace_bytes,
+                          otk_stream_t stream);
+
 /* K2  mean = sum/n ; cov = sum_cov/n - mean mean^T (biased).  Replaces mean_cov, ot/matrix_utils.py:145-158
  * (full-matrix branch).  n is a device vector [L] (a python int crashes the reference: utils/__init__.py:322). */
 int otk_mean_cov(const void* sum, const void* sum_cov, const void* n_obs, int n_dtype, int64_t L,

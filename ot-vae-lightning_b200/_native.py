@@ -34,6 +34,7 @@ SIGNATURES = {
     "otk_stats_update_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "otk_stats_update": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _dbl, _ptr, _int, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
     "otk_stats_update_f64": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _dbl, _ptr, _int, _ptr, _ptr, _int, _ptr, _sz, _ptr]),
+    "otk_stats_update_pair": (_int, [_ptr, _ptr, _i64, _i64, _i64, _dbl, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _sz, _ptr]),
     "otk_mean_cov": (_int, [_ptr, _ptr, _ptr, _int, _i64, _i64, _ptr, _ptr, _int, _ptr]),
     "otk_gaussian_fit": (_int, [_ptr, _ptr, _int, _ptr, _int, _i64, _i64, _ptr, _ptr, _ptr, _dbl, _int, _ptr]),
     "otk_symmetrize_shift": (_int, [_ptr, _ptr, _i64, _i64, _ptr, _int, _ptr]),

@@ -25,7 +25,12 @@ template <bool FUSED, typename X, int T = ST_T>
 __global__ void __launch_bounds__(ST_THREADS)
 stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t row_stride, int64_t batch_stride,
                   int64_t chunk_rows, int n_tiles, double* __restrict__ ws_cov, double* __restrict__ ws_sum,
-                  StatsRunning run) {
+                  StatsRunning run, const X* __restrict__ x_b, StatsRunning run_b) {
+  // FUSED with a second problem (otk_stats_update_pair: the source and the target batch of one GaussianTransport.update):
+  // blockIdx.y selects the problem, both go through one launch
+  if constexpr (FUSED) {
+    if (blockIdx.y == 1) { x = x_b; run = run_b; }
+  }
   // rows per step: the narrow-tile variant runs on a handful of CTAs and is bound by the load -> barrier -> compute round
   // trip of a step, so it takes 64 rows per step (16 independent loads in flight per thread) instead of 16
   constexpr int BK = T == 32 ? 64 : ST_BK;
@@ -38,7 +43,7 @@ stats_simt_kernel(const X* __restrict__ x, int64_t rows, int64_t dim, int64_t ro
   while (p >= n_tiles - ti) { p -= n_tiles - ti; ++ti; }
   const int tj = ti + p;
   const int64_t l = blockIdx.z;
-  const int64_t r0 = (int64_t)blockIdx.y * chunk_rows;
+  const int64_t r0 = FUSED ? 0 : (int64_t)blockIdx.y * chunk_rows;
   const int64_t r1 = min(rows, r0 + chunk_rows);
   const X* xb = x + l * batch_stride;
   constexpr int TH = T / 16;      // outputs per thread and direction
@@ -263,10 +268,10 @@ static int stats_update_impl(const X* x, int64_t L, int64_t rows, int64_t dim, i
         const int n32 = (int)ceil_div(dim, 32);
         const int64_t pairs32 = (int64_t)n32 * (n32 + 1) / 2;
         stats_simt_kernel<true, X, 32><<<dim3((unsigned)pairs32, 1, (unsigned)L), ST_THREADS, 0, st>>>(
-            x, rows, dim, row_stride, batch_stride, rows, n32, nullptr, nullptr, run);
+            x, rows, dim, row_stride, batch_stride, rows, n32, nullptr, nullptr, run, nullptr, StatsRunning{});
       } else {
         stats_simt_kernel<true, X><<<dim3((unsigned)pairs, 1, (unsigned)L), ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride,
-                                                                                               rows, n_tiles, nullptr, nullptr, run);
+                                                                                               rows, n_tiles, nullptr, nullptr, run, nullptr, StatsRunning{});
       }
       OTK_LAUNCH_CHECK();
       return OTK_OK;
@@ -301,7 +306,7 @@ static int stats_update_impl(const X* x, int64_t L, int64_t rows, int64_t dim, i
       dim3 grid((unsigned)pairs, (unsigned)ceil_div(rows, chunk), (unsigned)L);
       OTK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stats_update: too many row chunks / batches");
       stats_simt_kernel<false, X><<<grid, ST_THREADS, 0, st>>>(x, rows, dim, row_stride, batch_stride, chunk, n_tiles, ws_cov,
-                                                               ws_sum, StatsRunning{});
+                                                               ws_sum, StatsRunning{}, nullptr, StatsRunning{});
       OTK_LAUNCH_CHECK();
     }
   }
@@ -316,6 +321,38 @@ extern "C" int otk_stats_update(const float* x, int64_t L, int64_t rows, int64_t
                                 int buf_dtype, void* workspace, size_t workspace_bytes, otk_stream_t stream) {
   return stats_update_impl<float>(x, L, rows, dim, row_stride, batch_stride, decay, n_obs, n_dtype, sum, sum_cov, buf_dtype,
                                   workspace, workspace_bytes, stream);
+}
+
+// source + target batch of one GaussianTransport.update (reference ot/transport/base.py: two GaussianModel.update calls,
+// gaussian_model.py:99-108) in ONE launch when the batch is in the latency regime; otherwise the two updates run back to back
+extern "C" int otk_stats_update_pair(const float* x_a, const float* x_b, int64_t rows, int64_t dim, int64_t row_stride,
+                                     double decay, void* n_obs_a, void* sum_a, void* sum_cov_a, void* n_obs_b, void* sum_b,
+                                     void* sum_cov_b, int n_dtype, int buf_dtype, void* workspace, size_t workspace_bytes,
+                                     otk_stream_t stream) {
+  OTK_TRY(require_device());
+  OTK_REQUIRE(dim > 0 && rows > 0 && x_a && x_b, "stats_update_pair: bad arguments");
+  OTK_REQUIRE(n_obs_a && sum_a && sum_cov_a && n_obs_b && sum_b && sum_cov_b, "stats_update_pair: null running buffer");
+  OTK_REQUIRE(row_stride >= dim, "stats_update_pair: row_stride < dim");
+  const int n32 = (int)ceil_div(dim, 32);
+  const int64_t pairs32 = (int64_t)n32 * (n32 + 1) / 2;
+  if (rows <= ST_FUSED_ROWS && pairs32 <= 65535 && !g_stats_force_cg) {
+    const StatsRunning ra{n_obs_a, sum_a, sum_cov_a, n_dtype, buf_dtype, decay}, rb{n_obs_b, sum_b, sum_cov_b, n_dtype, buf_dtype, decay};
+    const int n_tiles = (int)ceil_div(dim, ST_T);
+    const int64_t pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
+    cudaStream_t st = as_stream(stream);
+    if (pairs * 4 <= sm_count())        // too few 64-wide tile pairs (two problems) to occupy the machine: 32-wide tiles
+      stats_simt_kernel<true, float, 32><<<dim3((unsigned)pairs32, 2, 1), ST_THREADS, 0, st>>>(
+          x_a, rows, dim, row_stride, rows * row_stride, rows, n32, nullptr, nullptr, ra, x_b, rb);
+    else
+      stats_simt_kernel<true, float><<<dim3((unsigned)pairs, 2, 1), ST_THREADS, 0, st>>>(
+          x_a, rows, dim, row_stride, rows * row_stride, rows, n_tiles, nullptr, nullptr, ra, x_b, rb);
+    OTK_LAUNCH_CHECK();
+    return OTK_OK;
+  }
+  OTK_TRY(stats_update_impl<float>(x_a, 1, rows, dim, row_stride, rows * row_stride, decay, n_obs_a, n_dtype, sum_a, sum_cov_a,
+                                   buf_dtype, workspace, workspace_bytes, stream));
+  return stats_update_impl<float>(x_b, 1, rows, dim, row_stride, rows * row_stride, decay, n_obs_b, n_dtype, sum_b, sum_cov_b,
+                                  buf_dtype, workspace, workspace_bytes, stream);
 }
 
 extern "C" int otk_stats_update_f64(const double* x, int64_t L, int64_t rows, int64_t dim, int64_t row_stride,

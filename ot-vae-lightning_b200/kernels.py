@@ -121,6 +121,42 @@ class StatsUpdatePlan:
         return True
 
 
+class StatsUpdatePairPlan:
+    """One `otk_stats_update_pair` call for the source and the target batch of a `TransportOperator.update` (two models of
+    the same width, dtype and decay): in the latency regime both updates are ONE launch.  Built from the two models'
+    `StatsUpdatePlan`s; `__call__` returns False when the batches do not qualify (the per-model path takes them)."""
+
+    __slots__ = ("a", "b", "entry")
+
+    def __init__(self, a: StatsUpdatePlan, b: StatsUpdatePlan):
+        if (a.dev, a.d, a.decay, a.n_code, a.b_code) != (b.dev, b.d, b.decay, b.n_code, b.b_code):
+            raise ValueError("the two models differ in device, width, decay or buffer dtypes")
+        self.a, self.b, self.entry = a, b, N.load().otk_stats_update_pair
+
+    def __call__(self, xa: Tensor, xb: Tensor) -> bool:
+        a = self.a
+        d = a.d
+        if xa.shape != xb.shape or xa.dim() != 2 or xa.shape[1] != d or xa.shape[0] == 0:
+            return False
+        for x in (xa, xb):
+            if x.dtype != torch.float32 or x.device != a.dev or not x.is_contiguous() or x.requires_grad or x.data_ptr() % 16:
+                return False
+        if torch.cuda.current_device() != a.dev_index:
+            return False
+        rows = xa.shape[0]
+        key = (1, rows, d)
+        need = _stats_ws_bytes.get(key)
+        if need is None:
+            need = _stats_ws_bytes[key] = a.ws_query(1, rows, d)
+        stream = N.raw_stream(a.dev_index)
+        ws = N.workspace_for(a.dev_index, stream, need, a.dev)
+        st = self.entry(xa.data_ptr(), xb.data_ptr(), rows, d, d, a.decay, a.n_ptr, a.s_ptr, a.c_ptr, self.b.n_ptr, self.b.s_ptr,
+                        self.b.c_ptr, a.n_code, a.b_code, ws.data_ptr(), ws.numel(), stream)
+        if st != N.OK:
+            N.check(st, "otk_stats_update_pair")
+        return True
+
+
 def mean_cov(run_sum: Tensor, run_cov: Tensor, n_obs: Tensor) -> Tuple[Tensor, Tensor]:
     dev = N.compute_device(run_sum)
     dt = run_sum.dtype if run_sum.dtype in (torch.float32, torch.float64) else torch.float32

@@ -110,20 +110,25 @@ class GaussianModel(DistributionModel, W2Mixin):
         """The per-batch call of the latency mode (cfg1: 40 batches of 250 per model and epoch) with the constant part of
         the native call cached: a contiguous fp32 [B, d] batch on the model's device, one model (no leading shape), no
         per-update reduction.  Returns False when the batch does not qualify (the general `update` takes it)."""
+        plan = self._fast_plan()
+        return plan is not None and plan(samples)
+
+    def _fast_plan(self):
+        """the cached `StatsUpdatePlan` of `_update_fast` (built on demand), or None when the model does not qualify"""
         plan = self.__dict__.get("_update_plan")
         rs = self._buffers.get("_running_sum")
-        if rs is None:                       # autograd mode: no running statistics
-            return False
+        if rs is None:
+            return None
         if plan is None or plan[0] is not rs or plan[1] is not self._buffers["_running_sum_cov"] or plan[2] is not self._buffers["_n_obs"]:
             if self.diag or self.update_with_autograd or len(self.leading_shape) or not rs.is_cuda \
                     or (self.reduce_on_update and self._reduce_is_active()):
-                return False
+                return None
             rc, no = self._buffers["_running_sum_cov"], self._buffers["_n_obs"]
             if not (rs.is_contiguous() and rc.is_contiguous() and no.is_contiguous()):
-                return False
+                return None
             plan = (rs, rc, no, K.StatsUpdatePlan(no, rs, rc, self.decay))
             self.__dict__["_update_plan"] = plan
-        return plan[3](samples)
+        return plan[3]
 
     @torch.no_grad()
     def fit(self, samples: Optional[Tensor] = None, cov_operand: Optional[Tensor] = None, operand_shift: float = 0.0,

@@ -863,6 +863,36 @@ def test_strided_token_latents_are_transported_in_place(api):
     assert rel(op.transport(sl), op.transport(sl.contiguous()).cpu()) < 1e-5
 
 
+def test_paired_update_is_one_launch_and_equals_two_updates(api):
+    """`GaussianTransport.update(source, target)` on a batch of the latency regime (the reference's batches of 250,
+    tests/test_latent_transport.py:66-98) goes to `otk_stats_update_pair`: ONE kernel launch for both models, bit-identical
+    to the two `GaussianModel.update` calls of the reference's `TransportOperator.update`; unequal shapes, large batches and
+    stored samples fall back to the per-model path."""
+    from ot_vae_lightning_b200 import _native as N_
+    lib = N_.load()
+    torch.manual_seed(3)
+    d = 128
+    cfg = dict(dtype=torch.double, reduce_on_update=False)
+    pair = api.GaussianTransport(d, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).cuda()
+    solo = api.GaussianTransport(d, transport_cfg=dict(make_pd=True), source_cfg=dict(cfg), target_cfg=dict(cfg)).cuda()
+    for rows in (250, 7, 256):
+        xs, xt = torch.randn(rows, d, device="cuda"), torch.randn(rows, d, device="cuda") * 1.5 + 0.5
+        torch.cuda.synchronize()
+        l0 = lib.otk_launch_count()
+        pair.update(source_samples=xs, target_samples=xt)
+        assert lib.otk_launch_count() - l0 == 1
+        solo.source_model.update(xs)
+        solo.target_model.update(xt)
+    xs, xt = torch.randn(300, d, device="cuda"), torch.randn(300, d, device="cuda")          # above the latency regime
+    pair.update(source_samples=xs, target_samples=xt); solo.source_model.update(xs); solo.target_model.update(xt)
+    xs, xt = torch.randn(100, d, device="cuda"), torch.randn(90, d, device="cuda")           # unequal batches
+    pair.update(source_samples=xs, target_samples=xt); solo.source_model.update(xs); solo.target_model.update(xt)
+    for a, b in ((pair.source_model, solo.source_model), (pair.target_model, solo.target_model)):
+        assert torch.equal(a._n_obs, b._n_obs) and torch.equal(a._running_sum, b._running_sum)
+        assert torch.equal(a._running_sum_cov, b._running_sum_cov)
+    assert float(pair.source_model._n_obs) == 250 + 7 + 256 + 300 + 100
+
+
 # ------------------------------------------------------------------------------------------------- f2: codebook k-means kernel
 
 @pytest.mark.parametrize("B,K,d,lead", [(1000, 1024, 64, ()), (512, 8192, 128, ()), (250, 48, 20, (3,)), (77, 6, 8, ()),
