@@ -2,6 +2,7 @@
 // Reference: apply_transport, ot/w2_utils.py:464-527 (deterministic full-matrix branch: :517-520), as called by
 // W2Mixin.apply_transport (:581-597) and GaussianTransport.transport (transport/gaussian_transport.py:80-95).
 // The reference runs B broadcast fp64 mat-vecs; here it is one GEMM  Y = (X - 1 mean_s^T) T^T + 1 mean_t^T.
+#include <cstdlib>
 #include "gemm.cuh"
 #include "apply_umma.cuh"
 
@@ -109,7 +110,12 @@ static int apply_prepared_impl(const float* x, int64_t L, int64_t rows, int64_t 
   if (!carve_prepared(ar, L, dim, &p)) return OTK_ERR_WORKSPACE;
   // TMA reads the view in place when its strides are 16-byte multiples; anything else goes through the FFMA engine,
   // which takes arbitrary element strides
-  if (apply_umma_eligible(x, y, L, rows, dim) && xrs % 4 == 0 && xbs % 4 == 0) {
+  // latency regime (the reference's batches of 250, tests/test_latent_transport.py:66-98): ONE launch of the FFMA engine
+  // (fp32, centring and bias fused) instead of flag reset + FP16-split tcgen05 kernel + gated fallback - the call is
+  // bound by launches, not by the 2 rows dim^2 flops (cfg1: 24.5 -> ~19 us per transport call)
+  static const bool small_simt = [] { const char* e = getenv("OTK_APPLY_SMALL_SIMT"); return !(e && e[0] == '0'); }();   // tuning aid
+  const bool latency_regime = small_simt && rows <= 256 && L * rows * dim <= (int64_t)1 << 16;
+  if (!latency_regime && apply_umma_eligible(x, y, L, rows, dim) && xrs % 4 == 0 && xbs % 4 == 0) {
     const bool pair = apply_umma_pair(rows, dim);
     int* flag = nullptr;
     int used = apply_h_run_prepared(x, L, rows, dim, p.mt32, y, ar, pair, st, &flag, xrs, xbs);
