@@ -27,7 +27,7 @@ constexpr double NS_F32_RICCATI_TOL = 2e-4;   // ||T Cs T - Ct||_F / ||Ct||_F ac
 // residual - 1.2e-4 / 4.6e-5 at d = 1024, 4.1e-4 / 1.3e-4 at 2048, 1.6e-3 / 3.4e-4 at 4096 with un-split K - so 2e-4 keeps
 // the map inside the 1e-3 budget for every width)
 static inline double riccati_tol(int64_t) { return NS_F32_RICCATI_TOL; }
-constexpr int64_t NS_SMALL_DIM = 64;          // fp64 data with dim <= 64: the DFMA engine is as fast and exact
+constexpr int64_t NS_SMALL_DIM = 48;          // fp64 data with dim <= 48: the DFMA engine is as fast and exact (d = 64: 1.46 ms there, 0.45 ms on the tcgen05 graph)
 constexpr int NS_F32_IROOT_ITERS = 12;
 // a root alone loses ~1e-7 * sqrt(cond): accepted from the fp32 engine up to this many iterations (lambda_min / c down to
 // ~1e-6); beyond that - ill-conditioned or rank-deficient input, whose noise-level eigenvalues the fp32 engine would
