@@ -886,12 +886,17 @@ def test_paired_update_is_one_launch_and_equals_two_updates(api):
         solo.target_model.update(xt)
     xs, xt = torch.randn(300, d, device="cuda"), torch.randn(300, d, device="cuda")          # above the latency regime
     pair.update(source_samples=xs, target_samples=xt); solo.source_model.update(xs); solo.target_model.update(xt)
+    # the entry point itself also takes large batches (two back-to-back updates inside the library)
+    from ot_vae_lightning_b200 import kernels as K_
+    xs, xt = torch.randn(70_000, d, device="cuda"), torch.randn(70_000, d, device="cuda") * 0.7
+    assert K_.StatsUpdatePairPlan(pair.source_model._fast_plan(), pair.target_model._fast_plan())(xs, xt)
+    solo.source_model.update(xs); solo.target_model.update(xt)
     xs, xt = torch.randn(100, d, device="cuda"), torch.randn(90, d, device="cuda")           # unequal batches
     pair.update(source_samples=xs, target_samples=xt); solo.source_model.update(xs); solo.target_model.update(xt)
     for a, b in ((pair.source_model, solo.source_model), (pair.target_model, solo.target_model)):
         assert torch.equal(a._n_obs, b._n_obs) and torch.equal(a._running_sum, b._running_sum)
         assert torch.equal(a._running_sum_cov, b._running_sum_cov)
-    assert float(pair.source_model._n_obs) == 250 + 7 + 256 + 300 + 100
+    assert float(pair.source_model._n_obs) == 250 + 7 + 256 + 300 + 70_000 + 100
 
 
 # ------------------------------------------------------------------------------------------------- f2: codebook k-means kernel
