@@ -94,10 +94,17 @@ class GaussianTransport(TransportOperator, W2Mixin):
     def _prepared_operator(self):
         """`kernels.PreparedTransport` of the current (means, T), rebuilt whenever one of them was replaced or written to
         (tensor identity + version counters), so assigning `transport_operator` or refitting a model cannot go stale."""
-        T, ms, mt = self.transport_operator, self.source_model.mean, self.target_model.mean
+        # (looked up through the module / parameter dicts: `nn.Module.__getattr__` costs ~0.4 us per hop, and this runs once
+        # per transported batch of 250 latents)
+        mods = self._modules
+        sm, tm = mods["source_model"], mods["target_model"]
+        ms, mt = sm._parameters.get("mean"), tm._parameters.get("mean")
+        if ms is None or mt is None:
+            ms, mt = sm.mean, tm.mean
+        T = self.transport_operator
         key = (id(T), T._version, id(ms), ms._version, id(mt), mt._version,
-               getattr(self.source_model, "_fit_generation", 0), getattr(self.target_model, "_fit_generation", 0))
-        cached = getattr(self, "_prepared", None)
+               sm.__dict__.get("_fit_generation", 0), tm.__dict__.get("_fit_generation", 0))
+        cached = self.__dict__.get("_prepared")
         if cached is None or cached[0] != key:
             var_s = self.source_model.parametrizations.cov.original.diagonal(dim1=-2, dim2=-1)
             cached = (key, K.PreparedTransport(ms, mt, T, var_s), (T, ms, mt))   # keep the keyed tensors alive
@@ -189,6 +196,8 @@ class GaussianTransport(TransportOperator, W2Mixin):
                 moved = self._prepared_operator().apply(inputs)
             else:
                 moved = K.apply_transport(inputs, self.source_model.mean, self.target_model.mean, self.transport_operator)
+            if moved.dtype is inputs.dtype and moved.device == inputs.device:
+                return moved
             return moved.to(device=inputs.device, dtype=inputs.dtype)
         moved = self.apply_transport(inputs, self.source_model.mean, self.target_model.mean, self.transport_operator,
                                      self.cov_stochastic_noise, batch_dim=-2 if is_batched else None)
