@@ -31,8 +31,8 @@ D_LAT, N_LAT, CHUNK = 512, 1 << 20, 1 << 16
 SK_N, SK_D, SK_EPS = 65536, 128, 0.05
 METRIC, UNIT = "cov+W2-map latents/s", "latents/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one stats_h2_kernel<2> launch on a 65536 x 512 chunk
-# (ncu --set full, profiles/prof_stats_r04.md): 135.03 MB + 16.20 MB (partial tiles); the algorithmic figure is 134.2 MB
-STATS_TRAFFIC_BYTES_PER_LAUNCH = 151.2e6
+# (ncu --set full, profiles/prof_stats_r06.md): 134.89 MB + 13.29 MB (partial tiles); the algorithmic figure is 134.2 MB
+STATS_TRAFFIC_BYTES_PER_LAUNCH = 148.2e6
 
 
 def load_peaks():
