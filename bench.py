@@ -412,11 +412,12 @@ def main():
                     executed=dict(tflops=3.0 * tri * stats_tflops, frac=3.0 * tri * stats_tflops / f16_peak,
                                   note="3 FP16 MMAs per fp32-accurate product, upper block triangle only: the ceiling of "
                                        f"`frac` for this scheme is 1/(3*{tri:.3f}) = {1 / (3 * tri):.2f}"),
-                    note=f"achieved = algorithmic flops 2*N*d^2 / CUDA-event time of the update calls (kernel 73 us + its "
-                         f"helper kernels: pivot/scale 4, partial-tile merge 13, gated fallback 6 us); peak = measured "
+                    note=f"achieved = algorithmic flops 2*N*d^2 / CUDA-event time of the update calls (kernel 67 us under ncu + "
+                         f"its helper kernels: pivot/scale 4, partial-tile merge 14-17, gated fallback + clear 6 us, chained by "
+                         f"programmatic dependent launch); peak = measured "
                          f"16-bit dense bf16_tflops_sustained ({peaks['source']}) - the kernel issues kind::f16 MMAs; ncu "
-                         f"(profiles/prof_stats_r04.md): FP16 tensor ops 53 % of the nominal peak at the 1.64 GHz the "
-                         f"kernel runs at, i.e. 76 % of the measured sustained peak in executed flops; traffic = dram "
+                         f"(profiles/prof_stats_r06.md): FP16 tensor ops 53 % of the nominal peak at the 1.77 GHz the "
+                         f"kernel ran at, tensor pipe 59 % active; traffic = dram "
                          f"read+write bytes per launch from the same capture (algorithmic: {CHUNK * D_LAT * 4})",
                     vs_measured_f16_peak=dict(peak=peaks_measured.get("f16_tflops"),
                                               executed_frac=(3.0 * tri * stats_tflops / peaks_measured["f16_tflops"]) if peaks_measured.get("f16_tflops") else None,
