@@ -212,6 +212,14 @@ def test_sinkhorn_points_vs_oracle(oracle, n, m, d):
     got = torch.exp(res["u"].double().cpu()[:, None] + res["v"].double().cpu()[None, :] - C * scale / 0.05)
     assert rel(got.sum(1), plan.sum(1)) < 2e-3 and rel(got.sum(0), plan.sum(0)) < 2e-3
     assert res["iters"] == 40
+    # `precision = 1` (exact fp32 cost tiles, what DiscreteTransport asks for): the same reconstruction on the exact cost now
+    # holds at the Sinkhorn tolerance, and so does the plan `otk_sinkhorn_points_plan` materialises
+    ex = K.sinkhorn_points(x, y, a, b, reg=0.05, max_iter=40, threshold=0.0, precision=1)
+    got = torch.exp(ex["u"].double().cpu()[:, None] + ex["v"].double().cpu()[None, :] - C * scale / 0.05)
+    assert rel(got.sum(1), plan.sum(1)) < TOL_SINKHORN and rel(got.sum(0), plan.sum(0)) < TOL_SINKHORN
+    native = K.points_plan(x, y, ex["u"], ex["v"], float(scale), 0.05)
+    assert rel(native.sum(1), plan.sum(1)) < TOL_SINKHORN and rel(native.sum(0), plan.sum(0)) < TOL_SINKHORN
+    assert rel(native, plan) < 1e-3
 
 
 def test_sinkhorn_stop_rule_matches_oracle(api, oracle):
