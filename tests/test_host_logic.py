@@ -59,6 +59,25 @@ def test_gaussian_transport_state_machine(api, golden):
         op.transport(torch.zeros(4, 15))
 
 
+def test_paired_update_hook_falls_back_to_the_per_model_updates(api):
+    """`GaussianTransport.update(source, target)` tries the one-launch pair entry only for CUDA-resident models with cached
+    native plans (`GaussianModel._fast_plan`); on the host mirror alone (no device buffers) the plans do not exist and the
+    call is exactly the reference's two `GaussianModel.update`s (ot/transport/base.py `update`), also for unequal batches and
+    for a single side."""
+    torch.manual_seed(0)
+    op = api.GaussianTransport(6, transport_cfg=dict(make_pd=True), source_cfg=dict(dtype=torch.double, device="cpu"),
+                               target_cfg=dict(dtype=torch.double, device="cpu"))
+    assert op.source_model._fast_plan() is None and op.target_model._fast_plan() is None
+    xs, xt = torch.randn(40, 6), torch.randn(40, 6) * 2 + 1
+    op.update(source_samples=xs, target_samples=xt)
+    op.update(source_samples=xs[:7], target_samples=xt[:9])
+    op.update(target_samples=xt[:3])
+    assert float(op.source_model._n_obs) == 47 and float(op.target_model._n_obs) == 52
+    both = torch.cat([xs, xs[:7]]).double()
+    close(op.source_model._running_sum, both.sum(0).numpy())
+    close(op.source_model._running_sum_cov, (both.T @ both).numpy())
+
+
 def test_leading_dims_pgstar_and_ema(api, golden):
     g = golden("gaussian_lead2_d8")
     _run(api, g, (2,), 8, pg_star=float(g["pg_star"]))
